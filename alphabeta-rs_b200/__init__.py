@@ -1,0 +1,445 @@
+"""abfit-b200 — Python binding (ctypes) of libabfit, the sm_100a implementation of the
+alphabeta-rs model-fitting hot path.
+
+This module is plumbing for tests and bench.py: it loads the in-tree ``libabfit.so`` and
+exposes the C ABI of ``include/abfit.h`` with numpy arrays, under names that mirror the
+reference's Rust interface (``ab_neutral_run`` = ``ab_neutral::run`` src/ab_neutral.rs:13,
+``boot_model_run`` = ``boot_model::run`` src/boot_model.rs:17, ``Problem.cost`` =
+``CostFunction::cost`` src/structs.rs:194, ``divergence`` = src/divergence.rs:33,
+``dmatrix`` = ``DMatrix::from`` src/pedigree.rs:214).
+
+There is no CPU fallback anywhere in the product path: if the CUDA library is missing the
+import fails, and without a CUDA device every compute call raises ``AbfitError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libabfit.so")
+
+DBL_EPSILON = 2.220446049250313e-16
+
+# flags (include/abfit.h)
+SHRINK_ON_FAILED_CONTRACTION = 1
+NO_EARLY_EXIT_ON_STALL = 2
+
+TERM_SD, TERM_MAX_ITERS, TERM_STALLED, FIT_NAN = 1, 2, 3, -1
+ERR_ARG, ERR_CUDA, ERR_TIME, ERR_NAN, ERR_TOO_LARGE, ERR_STATE = -1, -2, -3, -4, -5, -6
+
+
+class AbfitError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"abfit error {code}: {msg}")
+        self.code = code
+
+
+class _Problem(C.Structure):
+    _fields_ = [
+        ("pedigree", C.POINTER(C.c_double)),
+        ("n_pairs", C.c_int32),
+        ("p0uu", C.c_double),
+        ("eqp", C.c_double),
+        ("eqp_weight", C.c_double),
+    ]
+
+
+FIT_DTYPE = np.dtype(
+    [
+        ("theta", "<f8", (4,)),
+        ("cost", "<f8"),
+        ("lse", "<f8"),
+        ("iters", "<i4"),
+        ("evals", "<i4"),
+        ("status", "<i4"),
+        ("start_id", "<i4"),
+    ],
+    align=True,
+)
+assert FIT_DTYPE.itemsize == 64
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found — build it first (python -c 'import __graft_entry__ as g; g.build()' "
+            "or make -C alphabeta-rs_b200). abfit-b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_double
+    PP = C.POINTER(_Problem)
+    sig = {
+        "abfit_last_error": (C.c_char_p, []),
+        "abfit_version": (C.c_char_p, []),
+        "abfit_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "abfit_ctx_destroy": (None, [vp]),
+        "abfit_ctx_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
+        "abfit_measure_fp64_peak": (C.c_int, [vp, C.POINTER(dbl)]),
+        "abfit_gen_start_simplices": (None, [u64, u64, i32, dbl, vp]),
+        "abfit_gen_vary_vertices": (None, [u64, u64, i32, vp, vp]),
+        "abfit_gen_resample_idx": (None, [u64, u64, i32, i32, vp]),
+        "abfit_cost_batch": (C.c_int, [vp, PP, i32, vp, vp, i32, vp, vp]),
+        "abfit_model_divergence": (C.c_int, [vp, PP, vp, vp, vp]),
+        "abfit_fit_batch": (C.c_int, [vp, PP, i32, i32, vp, i32, dbl, u32, vp, vp, vp, vp, vp]),
+        "abfit_boot_batch": (C.c_int, [vp, PP, i32, vp, vp, vp, i32, vp, vp, i32, dbl, u32, vp, vp]),
+        "abfit_divergence": (C.c_int, [vp, vp, vp, vp, i32, i64, vp, i32, dbl, vp, vp, vp, vp, vp, vp]),
+        "abfit_batch_create": (C.c_int, [vp, PP, i32, C.POINTER(vp)]),
+        "abfit_batch_destroy": (None, [vp]),
+        "abfit_batch_upload_starts": (C.c_int, [vp, i32, vp]),
+        "abfit_batch_run_fit": (C.c_int, [vp, i32, dbl, u32]),
+        "abfit_batch_download_fit": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+        "abfit_batch_upload_boot": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
+        "abfit_batch_run_boot": (C.c_int, [vp, i32, dbl, u32]),
+        "abfit_batch_download_boot": (C.c_int, [vp, vp, vp]),
+        "abfit_batch_sync": (C.c_int, [vp]),
+        "abfit_batch_timing": (C.c_int, [vp, vp, vp, C.POINTER(i32)]),
+        "abfit_batch_flops_per_eval": (C.c_int, [vp, i32, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i32)]),
+        "abfit_analyze": (C.c_int, [vp, i32, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_lib = _load()
+EXPORTED_SYMBOLS = (
+    "abfit_last_error abfit_version abfit_ctx_create abfit_ctx_destroy abfit_ctx_info abfit_measure_fp64_peak "
+    "abfit_gen_start_simplices abfit_gen_vary_vertices abfit_gen_resample_idx abfit_cost_batch "
+    "abfit_model_divergence abfit_fit_batch abfit_boot_batch abfit_divergence abfit_batch_create "
+    "abfit_batch_destroy abfit_batch_upload_starts abfit_batch_run_fit abfit_batch_download_fit "
+    "abfit_batch_upload_boot abfit_batch_run_boot abfit_batch_download_boot abfit_batch_sync "
+    "abfit_batch_timing abfit_batch_flops_per_eval abfit_analyze"
+).split()
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise AbfitError(rc, (_lib.abfit_last_error() or b"").decode())
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def version() -> str:
+    return _lib.abfit_version().decode()
+
+
+# ---------------------------------------------------------------------------------------------
+# input generators (host, seeded; the same arrays feed the oracle and the GPU)
+# ---------------------------------------------------------------------------------------------
+def gen_start_simplices(seed: int, problem_id: int, n_starts: int, max_divergence: float) -> np.ndarray:
+    """5 x Model::new per start (src/structs.rs:78-96, src/ab_neutral.rs:49-55) -> [n_starts,5,4]."""
+    out = np.empty((n_starts, 5, 4), dtype=np.float64)
+    _lib.abfit_gen_start_simplices(seed, problem_id, n_starts, float(max_divergence), _ptr(out))
+    return out
+
+
+def gen_vary_vertices(seed: int, problem_id: int, n_boot: int, best_theta) -> np.ndarray:
+    """4 x Model::vary per replicate (src/structs.rs:100-128, src/boot_model.rs:71-74) -> [n_boot,4,4]."""
+    th = _f64(best_theta, (4,))
+    out = np.empty((n_boot, 4, 4), dtype=np.float64)
+    _lib.abfit_gen_vary_vertices(seed, problem_id, n_boot, _ptr(th), _ptr(out))
+    return out
+
+
+def gen_resample_idx(seed: int, problem_id: int, n_boot: int, n_pairs: int) -> np.ndarray:
+    """residual resampling with replacement (src/boot_model.rs:43-48) -> int32 [n_boot,n_pairs]."""
+    out = np.empty((n_boot, n_pairs), dtype=np.int32)
+    _lib.abfit_gen_resample_idx(seed, problem_id, n_boot, n_pairs, _ptr(out))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# problems
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class Problem:
+    """`Problem` of src/structs.rs:12-19. pedigree: [n_pairs,4] rows (t0,t1,t2,D)."""
+
+    pedigree: np.ndarray
+    p0uu: float
+    eqp: float
+    eqp_weight: float
+
+    def __post_init__(self):
+        self.pedigree = _f64(self.pedigree)
+        if self.pedigree.ndim != 2 or self.pedigree.shape[1] != 4:
+            raise ValueError("pedigree must be [n_pairs, 4]")
+
+    @property
+    def n_pairs(self) -> int:
+        return int(self.pedigree.shape[0])
+
+    def cost(self, theta, ctx: "Context") -> float:
+        """CostFunction::cost (src/structs.rs:194-216) evaluated on the GPU."""
+        c, _ = ctx.cost_batch([self], np.asarray(theta, dtype=np.float64).reshape(1, 4))
+        return float(c[0])
+
+
+def _pack_problems(probs: Sequence[Problem]):
+    arr = (_Problem * len(probs))()
+    for i, p in enumerate(probs):
+        arr[i].pedigree = p.pedigree.ctypes.data_as(C.POINTER(C.c_double))
+        arr[i].n_pairs = p.n_pairs
+        arr[i].p0uu = p.p0uu
+        arr[i].eqp = p.eqp
+        arr[i].eqp_weight = p.eqp_weight
+    return arr
+
+
+@dataclass
+class FitResult:
+    best: np.ndarray  # FIT_DTYPE [n_probs]
+    all: Optional[np.ndarray]  # FIT_DTYPE [n_probs, n_starts]
+    pred: np.ndarray  # concatenated [sum n_pairs]
+    resid: np.ndarray
+    status: np.ndarray  # int32 [n_probs]
+
+
+class Context:
+    """One CUDA device + stream (abfit_ctx)."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        _check(_lib.abfit_ctx_create(device, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.abfit_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        sm, khz, mem = C.c_int32(), C.c_int32(), C.c_int64()
+        _check(_lib.abfit_ctx_info(self._h, C.byref(sm), C.byref(khz), C.byref(mem)))
+        return {"sm_count": sm.value, "sm_clock_khz": khz.value, "mem_bytes": mem.value}
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double()
+        _check(_lib.abfit_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
+    # -- objective ---------------------------------------------------------------------------
+    def cost_batch(self, probs: Sequence[Problem], theta, prob_of_theta=None):
+        theta = _f64(theta).reshape(-1, 4)
+        B = theta.shape[0]
+        pot = None if prob_of_theta is None else np.ascontiguousarray(prob_of_theta, dtype=np.int32)
+        cost = np.empty(B)
+        lse = np.empty(B)
+        arr = _pack_problems(probs)
+        _check(_lib.abfit_cost_batch(self._h, arr, len(probs), _ptr(pot), _ptr(theta), B, _ptr(cost), _ptr(lse)))
+        return cost, lse
+
+    def divergence(self, prob: Problem, theta):
+        """divergence() of src/divergence.rs:33-94 -> (dt1t2 [n_pairs], p_uu)."""
+        th = _f64(theta, (4,))
+        dt = np.empty(prob.n_pairs)
+        puu = C.c_double()
+        arr = _pack_problems([prob])
+        _check(_lib.abfit_model_divergence(self._h, arr, _ptr(th), _ptr(dt), C.cast(C.byref(puu), C.c_void_p)))
+        return dt, puu.value
+
+    # -- ab_neutral::run, batched over windows --------------------------------------------------
+    def fit_batch(self, probs: Sequence[Problem], simplices, max_iters=10000, sd_tol=DBL_EPSILON, flags=0,
+                  want_all=True) -> FitResult:
+        simplices = _f64(simplices)
+        n_probs = len(probs)
+        n_starts = simplices.size // (n_probs * 20)
+        assert simplices.size == n_probs * n_starts * 20
+        best = np.zeros(n_probs, dtype=FIT_DTYPE)
+        allr = np.zeros((n_probs, n_starts), dtype=FIT_DTYPE) if want_all else None
+        total = sum(p.n_pairs for p in probs)
+        pred, resid = np.empty(total), np.empty(total)
+        status = np.zeros(n_probs, dtype=np.int32)
+        arr = _pack_problems(probs)
+        _check(
+            _lib.abfit_fit_batch(self._h, arr, n_probs, n_starts, _ptr(simplices), max_iters, sd_tol, flags,
+                                 _ptr(best), _ptr(allr), _ptr(pred), _ptr(resid), _ptr(status))
+        )
+        return FitResult(best, allr, pred, resid, status)
+
+    # -- boot_model::run, batched over windows ---------------------------------------------------
+    def boot_batch(self, probs: Sequence[Problem], best, pred, resid, resample_idx, vary_vertices, max_iters=1000,
+                   sd_tol=DBL_EPSILON, flags=0):
+        n_probs = len(probs)
+        best = np.ascontiguousarray(best, dtype=FIT_DTYPE).reshape(n_probs)
+        pred, resid = _f64(pred), _f64(resid)
+        vary = _f64(vary_vertices)
+        n_boot = vary.size // (n_probs * 16)
+        idx = np.ascontiguousarray(resample_idx, dtype=np.int32)
+        rows = np.empty((n_probs, n_boot, 7))
+        fits = np.zeros((n_probs, n_boot), dtype=FIT_DTYPE)
+        arr = _pack_problems(probs)
+        _check(
+            _lib.abfit_boot_batch(self._h, arr, n_probs, _ptr(best), _ptr(pred), _ptr(resid), n_boot, _ptr(idx),
+                                  _ptr(vary), max_iters, sd_tol, flags, _ptr(rows), _ptr(fits))
+        )
+        return rows, fits
+
+    # -- DMatrix::from + p0uu ------------------------------------------------------------------
+    def dmatrix(self, status, posterior_max, meth_lvl, thr=0.99, seg_offsets=None):
+        status = np.ascontiguousarray(status, dtype=np.uint8)
+        S, L = status.shape
+        post, meth = _f64(posterior_max, (S, L)), _f64(meth_lvl, (S, L))
+        seg = None if seg_offsets is None else np.ascontiguousarray(seg_offsets, dtype=np.int64)
+        W = 1 if seg is None else len(seg) - 1
+        P = S * (S - 1) // 2
+        D = np.empty((W, P))
+        diff = np.empty((W, P), dtype=np.uint64)
+        cnt = np.empty((W, P), dtype=np.uint64)
+        p0uu = np.empty(W)
+        methsum = np.empty((W, S))
+        nvalid = np.empty((W, S), dtype=np.int64)
+        _check(
+            _lib.abfit_divergence(self._h, _ptr(status), _ptr(post), _ptr(meth), S, L, _ptr(seg), W, thr, _ptr(D),
+                                  _ptr(diff), _ptr(cnt), _ptr(p0uu), _ptr(methsum), _ptr(nvalid))
+        )
+        return {"D": D, "diff": diff, "cnt": cnt, "p0uu": p0uu, "methsum": methsum, "nvalid": nvalid}
+
+    def batch(self, probs: Sequence[Problem]) -> "Batch":
+        return Batch(self, probs)
+
+
+class Batch:
+    """Device-resident batch of windows (abfit_batch): upload / run / download are separate so
+    callers can keep inputs in HBM (bench.py times run_* alone and the whole sequence)."""
+
+    def __init__(self, ctx: Context, probs: Sequence[Problem]):
+        self.ctx = ctx
+        self.probs = list(probs)
+        self.n_probs = len(self.probs)
+        self.total_pairs = sum(p.n_pairs for p in self.probs)
+        arr = _pack_problems(self.probs)
+        h = C.c_void_p()
+        _check(_lib.abfit_batch_create(ctx._h, arr, self.n_probs, C.byref(h)))
+        self._h = h
+        self.n_starts = 0
+        self.n_boot = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.abfit_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_starts(self, simplices: np.ndarray):
+        assert simplices.dtype == np.float64 and simplices.flags.c_contiguous
+        self.n_starts = simplices.size // (self.n_probs * 20)
+        _check(_lib.abfit_batch_upload_starts(self._h, self.n_starts, _ptr(simplices)))
+
+    def upload_starts_ptr(self, n_starts: int, host_ptr: int):
+        self.n_starts = n_starts
+        _check(_lib.abfit_batch_upload_starts(self._h, n_starts, C.c_void_p(host_ptr)))
+
+    def run_fit(self, max_iters=10000, sd_tol=DBL_EPSILON, flags=0):
+        _check(_lib.abfit_batch_run_fit(self._h, max_iters, sd_tol, flags))
+
+    def download_fit(self, want_all=False, best=None, pred=None, resid=None, status=None) -> FitResult:
+        best = np.zeros(self.n_probs, dtype=FIT_DTYPE) if best is None else best
+        allr = np.zeros((self.n_probs, self.n_starts), dtype=FIT_DTYPE) if want_all else None
+        pred = np.empty(self.total_pairs) if pred is None else pred
+        resid = np.empty(self.total_pairs) if resid is None else resid
+        status = np.zeros(self.n_probs, dtype=np.int32) if status is None else status
+        _check(_lib.abfit_batch_download_fit(self._h, _ptr(best), _ptr(allr), _ptr(pred), _ptr(resid), _ptr(status)))
+        return FitResult(best, allr, pred, resid, status)
+
+    def upload_boot(self, resample_idx: np.ndarray, vary_vertices: np.ndarray, best=None, pred=None, resid=None):
+        assert resample_idx.dtype == np.int32 and resample_idx.flags.c_contiguous
+        assert vary_vertices.dtype == np.float64 and vary_vertices.flags.c_contiguous
+        self.n_boot = vary_vertices.size // (self.n_probs * 16)
+        if best is not None:
+            best = np.ascontiguousarray(best, dtype=FIT_DTYPE)
+            pred, resid = _f64(pred), _f64(resid)
+        self._keep = (best, pred, resid)
+        _check(
+            _lib.abfit_batch_upload_boot(self._h, self.n_boot, _ptr(best), _ptr(pred), _ptr(resid),
+                                         _ptr(resample_idx), _ptr(vary_vertices))
+        )
+
+    def run_boot(self, max_iters=1000, sd_tol=DBL_EPSILON, flags=0):
+        _check(_lib.abfit_batch_run_boot(self._h, max_iters, sd_tol, flags))
+
+    def download_boot(self, want_fits=False, rows=None):
+        rows = np.empty((self.n_probs, self.n_boot, 7)) if rows is None else rows
+        fits = np.zeros((self.n_probs, self.n_boot), dtype=FIT_DTYPE) if want_fits else None
+        _check(_lib.abfit_batch_download_boot(self._h, _ptr(rows), _ptr(fits)))
+        return rows, fits
+
+    def sync(self):
+        _check(_lib.abfit_batch_sync(self._h))
+
+    def timing(self):
+        ms = (C.c_float * 3)()
+        ev = (C.c_int64 * 2)()
+        launches = C.c_int32()
+        _check(_lib.abfit_batch_timing(self._h, C.cast(ms, C.c_void_p), C.cast(ev, C.c_void_p), C.byref(launches)))
+        return {"fit_ms": ms[0], "select_ms": ms[1], "boot_ms": ms[2], "evals_fit": ev[0], "evals_boot": ev[1],
+                "launches": launches.value}
+
+    def flops_per_eval(self, p: int = 0):
+        f, u, t = C.c_double(), C.c_int32(), C.c_int32()
+        _check(_lib.abfit_batch_flops_per_eval(self._h, p, C.byref(f), C.byref(u), C.byref(t)))
+        return {"flops": f.value, "n_triples": u.value, "tmax": t.value}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference-shaped convenience wrappers (single window)
+# ---------------------------------------------------------------------------------------------
+def ab_neutral_run(ctx: Context, pedigree, p0uu, eqp, eqp_weight, n_starts, seed=0xAB0B200, problem_id=0,
+                   simplices=None, max_iters=10000, flags=0):
+    """ab_neutral::run (src/ab_neutral.rs:13-142) -> (model theta[4], predicted divergence, residuals, FitResult)."""
+    prob = Problem(pedigree, p0uu, eqp, eqp_weight)
+    if simplices is None:
+        simplices = gen_start_simplices(seed, problem_id, n_starts, float(np.max(prob.pedigree[:, 3])))
+    res = ctx.fit_batch([prob], simplices, max_iters=max_iters, flags=flags)
+    if res.status[0] != 0:
+        raise AbfitError(int(res.status[0]), "NaN in pedigree or fit (the reference panics here)")
+    return res.best[0]["theta"].copy(), res.pred, res.resid, res
+
+
+def boot_model_run(ctx: Context, pedigree, best_fit, pred, resid, p0uu, eqp, eqp_weight, n_boot, seed=0xAB0B200,
+                   problem_id=0, resample_idx=None, vary_vertices=None, max_iters=1000, flags=0):
+    """boot_model::run (src/boot_model.rs:17-115) -> (analysis[32], raw rows [n_boot,7])."""
+    prob = Problem(pedigree, p0uu, eqp, eqp_weight)
+    best = np.ascontiguousarray(best_fit, dtype=FIT_DTYPE).reshape(1)
+    if resample_idx is None:
+        resample_idx = gen_resample_idx(seed, problem_id, n_boot, prob.n_pairs)
+    if vary_vertices is None:
+        vary_vertices = gen_vary_vertices(seed, problem_id, n_boot, best[0]["theta"])
+    rows, _ = ctx.boot_batch([prob], best, pred, resid, resample_idx, vary_vertices, max_iters=max_iters, flags=flags)
+    return analyze(rows[0]), rows[0]
+
+
+def analyze(rows) -> np.ndarray:
+    """RawAnalysis::analyze (src/analysis.rs:50-98): 8 means, 8 sds, 8 (q.025,q.975) pairs."""
+    rows = _f64(rows).reshape(-1, 7)
+    out = np.empty(32)
+    _check(_lib.abfit_analyze(_ptr(rows), rows.shape[0], _ptr(out)))
+    return out

@@ -1,0 +1,856 @@
+// abfit_api.cu — C ABI of libabfit (include/abfit.h): context, problem compilation,
+// device-resident batches, host-buffer one-shot entry points, input generators.
+//
+// Host work here is O(input) bookkeeping only (validation, run/triple tables, copies);
+// every numerical result comes from the kernels in abfit_kernels.cu / abfit_divergence.cu.
+// There is deliberately no CPU implementation of the objective or the optimiser in this
+// library: without a CUDA device all compute calls fail.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <tuple>
+
+#include "abfit_internal.h"
+
+namespace abfit {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+int cuda_fail(cudaError_t e, const char *what)
+{
+    set_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what);
+    return ABFIT_ERR_CUDA;
+}
+
+// `x as i8` in Rust (saturating, NaN -> 0), src/divergence.rs:52
+static inline int as_i8(double x)
+{
+    if (x != x) return 0;
+    if (x >= 127.0) return 127;
+    if (x <= -128.0) return -128;
+    return (int)x;
+}
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    int ensure(size_t count)
+    {
+        if (count <= n && p) return 0;
+        release();
+        if (count == 0) count = 1;
+        ABFIT_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        n = count;
+        return 0;
+    }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+struct HostPlan {
+    std::vector<DevProblem> probs;
+    std::vector<double> D;
+    std::vector<uint32_t> runs, tris;
+    std::vector<uint8_t> exps;
+    std::vector<double> flops;     // algorithmic FLOPs per objective evaluation
+    std::vector<int32_t> tmax;
+    std::vector<uint8_t> d_has_nan;
+    size_t smem_with_D = 0, smem_without_D = 0;  // incl. simplex area
+    int32_t max_pairs = 0;
+};
+
+static int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
+{
+    if (!probs || n_probs <= 0) {
+        set_error("no problems");
+        return ABFIT_ERR_ARG;
+    }
+    hp.probs.resize(n_probs);
+    hp.flops.resize(n_probs);
+    hp.tmax.resize(n_probs);
+    hp.d_has_nan.assign(n_probs, 0);
+    for (int p = 0; p < n_probs; ++p) {
+        const abfit_problem &ap = probs[p];
+        if (!ap.pedigree || ap.n_pairs <= 0) {
+            set_error("problem " + std::to_string(p) + ": empty pedigree");
+            return ABFIT_ERR_ARG;
+        }
+        DevProblem dp;
+        dp.pair_off = (int64_t)hp.D.size();
+        dp.runs_off = (int64_t)hp.runs.size();
+        dp.tri_off = (int64_t)hp.tris.size();
+        dp.exp_off = (int64_t)hp.exps.size();
+        dp.n_pairs = ap.n_pairs;
+        dp.p_uu0 = ap.p0uu;
+        dp.p_mm0 = 1.0 - ap.p0uu;  // src/ab_neutral.rs:23
+        if (dp.p_mm0 + dp.p_uu0 + 0.0 != 1.0) {  // src/ab_neutral.rs:31 assert_eq!
+            set_error("problem " + std::to_string(p) + ": p0mm + p0uu + p0um != 1");
+            return ABFIT_ERR_NAN;
+        }
+        dp.eqp = ap.eqp;
+        dp.penw = ap.eqp_weight * (double)ap.n_pairs;  // src/structs.rs:210-211
+
+        // triples and exponents
+        std::vector<std::tuple<int, int, int>> key(ap.n_pairs);
+        std::vector<int> used_exp(128, 0);
+        for (int i = 0; i < ap.n_pairs; ++i) {
+            const double *row = ap.pedigree + 4 * (size_t)i;
+            const int t0 = as_i8(row[0]), t1 = as_i8(row[1]), t2 = as_i8(row[2]);
+            if (t0 < 0 || t1 < t0 || t2 < t0) {
+                set_error("problem " + std::to_string(p) + " row " + std::to_string(i) +
+                          ": needs 0 <= t0 <= t1,t2 <= 127 (the reference would invert the matrix)");
+                return ABFIT_ERR_TIME;
+            }
+            key[i] = std::make_tuple(t0, t1 - t0, t2 - t0);
+            used_exp[t0] = used_exp[t1 - t0] = used_exp[t2 - t0] = 1;
+            if (row[3] != row[3]) hp.d_has_nan[p] = 1;
+            hp.D.push_back(row[3]);
+        }
+        std::vector<int> slot_of(128, 0);
+        int n_exps = 0, tmax = 0;
+        for (int e = 1; e < 128; ++e)
+            if (used_exp[e]) {
+                hp.exps.push_back((uint8_t)e);
+                slot_of[e] = ++n_exps;
+                tmax = e;
+            }
+        std::map<std::tuple<int, int, int>, int> tri_id;
+        for (auto &k : key) tri_id.emplace(k, 0);
+        if (tri_id.size() > 65535) {
+            set_error("problem " + std::to_string(p) + ": more than 65535 distinct (t0,t1,t2) triples");
+            return ABFIT_ERR_TOO_LARGE;
+        }
+        int u = 0;
+        for (auto &kv : tri_id) {  // sorted by (t0, a, b): consecutive triples reuse loaded powers
+            kv.second = u++;
+            const int t0 = std::get<0>(kv.first), a = std::get<1>(kv.first), b = std::get<2>(kv.first);
+            hp.tris.push_back((uint32_t)slot_of[t0] | ((uint32_t)slot_of[a] << 8) | ((uint32_t)slot_of[b] << 16));
+        }
+        int n_runs = 0;
+        for (int i = 0; i < ap.n_pairs;) {
+            const int id = tri_id[key[i]];
+            int len = 1;
+            while (i + len < ap.n_pairs && len < 65535 && key[i + len] == key[i]) ++len;
+            hp.runs.push_back(((uint32_t)id << 16) | (uint32_t)len);
+            ++n_runs;
+            i += len;
+        }
+        dp.n_runs = n_runs;
+        dp.n_triples = u;
+        dp.n_exps = n_exps;
+        hp.probs[p] = dp;
+        hp.tmax[p] = tmax;
+        hp.flops[p] = 45.0 * (tmax > 1 ? tmax - 1 : 0) + 56.0 * u + 5.0 * ap.n_pairs + 40.0;
+        const SmemNeed sn = smem_need(ap.n_pairs, n_runs, u, n_exps, true);
+        hp.smem_with_D = std::max(hp.smem_with_D, sn.with_D);
+        hp.smem_without_D = std::max(hp.smem_without_D, sn.without_D);
+        hp.max_pairs = std::max(hp.max_pairs, ap.n_pairs);
+    }
+    return 0;
+}
+
+}  // namespace abfit
+
+using namespace abfit;
+
+struct abfit_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    int smem_optin = 0;
+};
+
+struct abfit_batch {
+    abfit_ctx *ctx = nullptr;
+    HostPlan hp;
+    int n_probs = 0;
+    int64_t total_pairs = 0;
+    bool d_in_shared = true;
+    size_t smem_bytes = 0;       // start kernel / select / cost
+    size_t smem_bytes_boot = 0;  // boot kernel (D never staged)
+    DevBuf<DevProblem> d_probs;
+    DevBuf<double> d_D;
+    DevBuf<uint32_t> d_runs, d_tris;
+    DevBuf<uint8_t> d_exps;
+    DevicePools pools{};
+    // fit
+    int n_starts = 0;
+    DevBuf<double> d_simplices;
+    DevBuf<WorkItem> d_items;
+    int n_items = 0;
+    DevBuf<abfit_fit> d_all, d_best;
+    DevBuf<double> d_pred, d_resid;
+    DevBuf<int32_t> d_status;
+    DevBuf<unsigned long long> d_evals_fit, d_evals_boot;
+    bool fit_done = false;
+    // boot
+    int n_boot = 0;
+    DevBuf<int32_t> d_idx;
+    DevBuf<double> d_vary, d_scratch, d_rows;
+    DevBuf<abfit_fit> d_bootfits;
+    DevBuf<WorkItem> d_boot_items;
+    int n_boot_items = 0;
+    bool boot_uploaded = false, boot_done = false;
+    // timing
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_fit = false, ev_boot = false;
+    int launches_fit = 0, launches_boot = 0;
+};
+
+static std::vector<WorkItem> make_items(const HostPlan &hp, int count_per_prob, int n_sm, bool skip_nan)
+{
+    // One warp per item.  Enough items to fill the machine several times over, but chunks as
+    // long as possible so that idle lanes can pull further fits of the same window.
+    const int64_t target = (int64_t)n_sm * 8 * 4;
+    const int n_probs = (int)hp.probs.size();
+    int64_t total = (int64_t)n_probs * count_per_prob;
+    int64_t chunk = (total + target - 1) / target;
+    chunk = ((chunk + 31) / 32) * 32;
+    if (chunk < 32) chunk = 32;
+    if (chunk > count_per_prob) chunk = count_per_prob;
+    std::vector<WorkItem> items;
+    for (int p = 0; p < n_probs; ++p) {
+        if (skip_nan && hp.d_has_nan[p]) continue;
+        for (int f = 0; f < count_per_prob; f += (int)chunk) {
+            WorkItem it;
+            it.prob = p;
+            it.first = f;
+            it.count = std::min<int>((int)chunk, count_per_prob - f);
+            it.pad = 0;
+            items.push_back(it);
+        }
+    }
+    return items;
+}
+
+extern "C" {
+
+const char *abfit_last_error(void) { return g_last_error.c_str(); }
+const char *abfit_version(void) { return "abfit-b200 0.1 (sm_100a)"; }
+
+int abfit_ctx_create(int device, abfit_ctx **out)
+{
+    if (!out) return ABFIT_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        set_error(std::string("no CUDA device available: ") + (e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)) +
+                  " — libabfit has no CPU fallback");
+        return ABFIT_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) {
+        set_error("device index out of range");
+        return ABFIT_ERR_ARG;
+    }
+    ABFIT_CUDA(cudaSetDevice(device));
+    abfit_ctx *c = new abfit_ctx();
+    c->device = device;
+    if (cudaGetDeviceProperties(&c->prop, device) != cudaSuccess) {
+        delete c;
+        return cuda_fail(cudaGetLastError(), "cudaGetDeviceProperties");
+    }
+    c->smem_optin = max_dynamic_smem(device);
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return cuda_fail(cudaGetLastError(), "cudaStreamCreate");
+    }
+    *out = c;
+    return 0;
+}
+
+void abfit_ctx_destroy(abfit_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int abfit_ctx_info(abfit_ctx *ctx, int32_t *sm_count, int32_t *sm_clock_khz, int64_t *mem_bytes)
+{
+    if (!ctx) return ABFIT_ERR_ARG;
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (sm_clock_khz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+        *sm_clock_khz = khz;
+    }
+    if (mem_bytes) *mem_bytes = (int64_t)ctx->prop.totalGlobalMem;
+    return 0;
+}
+
+int abfit_measure_fp64_peak(abfit_ctx *ctx, double *tflops_out)
+{
+    if (!ctx || !tflops_out) return ABFIT_ERR_ARG;
+    ABFIT_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<double> sink;
+    if (int rc = sink.ensure(1)) return rc;
+    cudaEvent_t a, b;
+    ABFIT_CUDA(cudaEventCreate(&a));
+    ABFIT_CUDA(cudaEventCreate(&b));
+    const int blocks = ctx->prop.multiProcessorCount * 8, threads = 256, iters = 2048;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        ABFIT_CUDA(cudaEventRecord(a, ctx->stream));
+        if (int rc = launch_fp64_peak(ctx->stream, blocks, threads, iters, sink.p)) return rc;
+        ABFIT_CUDA(cudaEventRecord(b, ctx->stream));
+        ABFIT_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        ABFIT_CUDA(cudaEventElapsedTime(&ms, a, b));
+        const double flops = (double)blocks * threads * (double)iters * 64.0 * 2.0;
+        if (rep > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops_out = best;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// input generators (host; counter-based so shards can be produced independently)
+// ---------------------------------------------------------------------------------------
+static inline uint64_t mix64(uint64_t z)
+{
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+static inline double u01(uint64_t seed, uint64_t stream, uint64_t problem, uint64_t item, uint64_t sub)
+{
+    uint64_t h = mix64(seed ^ (stream * 0xd1342543de82ef95ull));
+    h = mix64(h ^ problem);
+    h = mix64(h ^ item);
+    h = mix64(h ^ sub);
+    return (double)(h >> 11) * (1.0 / 9007199254740992.0);  // [0,1)
+}
+static inline double uniform(double lo, double hi, double u) { return lo + (hi - lo) * u; }
+
+void abfit_gen_start_simplices(uint64_t seed, uint64_t problem_id, int32_t n_starts, double max_divergence,
+                               double *out)
+{
+    double mx = max_divergence;
+    if (max_divergence <= 0.0) mx = 0.1;  // src/structs.rs:80-83
+    for (int32_t s = 0; s < n_starts; ++s)
+        for (int v = 0; v < 5; ++v) {
+            double *x = out + ((size_t)s * 5 + v) * 4;
+            x[0] = std::pow(10.0, uniform(-9.0, -2.0, u01(seed, 1, problem_id, (uint64_t)s, v * 4 + 0)));
+            x[1] = std::pow(10.0, uniform(-9.0, -2.0, u01(seed, 1, problem_id, (uint64_t)s, v * 4 + 1)));
+            x[2] = uniform(0.0, 0.1, u01(seed, 1, problem_id, (uint64_t)s, v * 4 + 2));
+            x[3] = uniform(0.0, mx, u01(seed, 1, problem_id, (uint64_t)s, v * 4 + 3));
+        }
+}
+
+void abfit_gen_vary_vertices(uint64_t seed, uint64_t problem_id, int32_t n_boot, const double best_theta[4],
+                             double *out)
+{
+    for (int32_t b = 0; b < n_boot; ++b)
+        for (int v = 0; v < 4; ++v)
+            for (int j = 0; j < 4; ++j) {
+                double n = best_theta[j];
+                if (n == 0.0) n = 0.1;  // src/structs.rs:105-108
+                double lo = n - std::fabs(n) * 0.1, hi = n + std::fabs(n) * 0.1;
+                if (lo >= hi) std::swap(lo, hi);  // src/structs.rs:113-115
+                out[((size_t)b * 4 + v) * 4 + j] = uniform(lo, hi, u01(seed, 2, problem_id, (uint64_t)b, v * 4 + j));
+            }
+}
+
+void abfit_gen_resample_idx(uint64_t seed, uint64_t problem_id, int32_t n_boot, int32_t n_pairs, int32_t *out)
+{
+    for (int32_t b = 0; b < n_boot; ++b)
+        for (int32_t i = 0; i < n_pairs; ++i) {
+            int32_t k = (int32_t)(u01(seed, 3, problem_id, (uint64_t)b, (uint64_t)i) * (double)n_pairs);
+            if (k >= n_pairs) k = n_pairs - 1;
+            out[(size_t)b * n_pairs + i] = k;
+        }
+}
+
+// ---------------------------------------------------------------------------------------
+// batches
+// ---------------------------------------------------------------------------------------
+int abfit_batch_create(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, abfit_batch **out)
+{
+    if (!ctx || !out) return ABFIT_ERR_ARG;
+    *out = nullptr;
+    ABFIT_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<abfit_batch> b(new abfit_batch());
+    b->ctx = ctx;
+    if (int rc = compile_problems(probs, n_probs, b->hp)) return rc;
+    HostPlan &hp = b->hp;
+    b->n_probs = n_probs;
+    b->total_pairs = (int64_t)hp.D.size();
+    const size_t cap = (size_t)ctx->smem_optin;
+    // D in shared while at least 4 warps still fit on an SM; else broadcast it from L1/L2
+    b->d_in_shared = hp.smem_with_D <= 56 * 1024;
+    b->smem_bytes = b->d_in_shared ? hp.smem_with_D : hp.smem_without_D;
+    b->smem_bytes_boot = hp.smem_without_D;
+    if (b->smem_bytes > cap) {
+        set_error("per-lane model state needs " + std::to_string(b->smem_bytes) + " B of shared memory (limit " +
+                  std::to_string(cap) + "): too many distinct exponents/triples in one pedigree");
+        return ABFIT_ERR_TOO_LARGE;
+    }
+    if (int rc = b->d_probs.ensure(hp.probs.size())) return rc;
+    if (int rc = b->d_D.ensure(hp.D.size())) return rc;
+    if (int rc = b->d_runs.ensure(hp.runs.size())) return rc;
+    if (int rc = b->d_tris.ensure(hp.tris.size())) return rc;
+    if (int rc = b->d_exps.ensure(hp.exps.size())) return rc;
+    cudaStream_t st = ctx->stream;
+    ABFIT_CUDA(cudaMemcpyAsync(b->d_probs.p, hp.probs.data(), hp.probs.size() * sizeof(DevProblem), cudaMemcpyHostToDevice, st));
+    ABFIT_CUDA(cudaMemcpyAsync(b->d_D.p, hp.D.data(), hp.D.size() * 8, cudaMemcpyHostToDevice, st));
+    ABFIT_CUDA(cudaMemcpyAsync(b->d_runs.p, hp.runs.data(), hp.runs.size() * 4, cudaMemcpyHostToDevice, st));
+    ABFIT_CUDA(cudaMemcpyAsync(b->d_tris.p, hp.tris.data(), hp.tris.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!hp.exps.empty())
+        ABFIT_CUDA(cudaMemcpyAsync(b->d_exps.p, hp.exps.data(), hp.exps.size(), cudaMemcpyHostToDevice, st));
+    ABFIT_CUDA(cudaStreamSynchronize(st));  // hp vectors are pageable: make the copies complete here
+    b->pools = DevicePools{b->d_probs.p, b->d_D.p, b->d_runs.p, b->d_tris.p, b->d_exps.p};
+    for (auto &e : b->ev) ABFIT_CUDA(cudaEventCreate(&e));
+    if (int rc = b->d_evals_fit.ensure(n_probs)) return rc;
+    if (int rc = b->d_evals_boot.ensure(n_probs)) return rc;
+    ABFIT_CUDA(cudaMemsetAsync(b->d_evals_fit.p, 0, (size_t)n_probs * 8, st));
+    ABFIT_CUDA(cudaMemsetAsync(b->d_evals_boot.p, 0, (size_t)n_probs * 8, st));
+    *out = b.release();
+    return 0;
+}
+
+void abfit_batch_destroy(abfit_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    for (auto &e : b->ev)
+        if (e) cudaEventDestroy(e);
+    delete b;
+}
+
+int abfit_batch_upload_starts(abfit_batch *b, int32_t n_starts, const double *simplices)
+{
+    if (!b || !simplices || n_starts <= 0) return ABFIT_ERR_ARG;
+    ABFIT_CUDA(cudaSetDevice(b->ctx->device));
+    const size_t n = (size_t)b->n_probs * n_starts * 20;
+    if (int rc = b->d_simplices.ensure(n)) return rc;
+    ABFIT_CUDA(cudaMemcpyAsync(b->d_simplices.p, simplices, n * 8, cudaMemcpyHostToDevice, b->ctx->stream));
+    if (n_starts != b->n_starts) {
+        b->n_starts = n_starts;
+        std::vector<WorkItem> items = make_items(b->hp, n_starts, b->ctx->prop.multiProcessorCount, true);
+        b->n_items = (int)items.size();
+        if (int rc = b->d_items.ensure(items.size())) return rc;
+        if (!items.empty())
+            ABFIT_CUDA(cudaMemcpyAsync(b->d_items.p, items.data(), items.size() * sizeof(WorkItem),
+                                       cudaMemcpyHostToDevice, b->ctx->stream));
+        ABFIT_CUDA(cudaStreamSynchronize(b->ctx->stream));
+        if (int rc = b->d_all.ensure((size_t)b->n_probs * n_starts)) return rc;
+        if (int rc = b->d_best.ensure(b->n_probs)) return rc;
+        if (int rc = b->d_pred.ensure((size_t)b->total_pairs)) return rc;
+        if (int rc = b->d_resid.ensure((size_t)b->total_pairs)) return rc;
+        if (int rc = b->d_status.ensure(b->n_probs)) return rc;
+    }
+    b->fit_done = false;
+    return 0;
+}
+
+int abfit_batch_run_fit(abfit_batch *b, int32_t max_iters, double sd_tol, uint32_t flags)
+{
+    if (!b || b->n_starts <= 0 || max_iters < 0) {
+        set_error("run_fit: upload_starts first");
+        return ABFIT_ERR_STATE;
+    }
+    ABFIT_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    NMParams nm{max_iters, sd_tol, flags};
+    // records of skipped (NaN) problems read back as status -1 / NaN
+    ABFIT_CUDA(cudaMemsetAsync(b->d_all.p, 0xFF, (size_t)b->n_probs * b->n_starts * sizeof(abfit_fit), st));
+    ABFIT_CUDA(cudaMemsetAsync(b->d_evals_fit.p, 0, (size_t)b->n_probs * 8, st));
+    ABFIT_CUDA(cudaEventRecord(b->ev[0], st));
+    if (int rc = launch_fit_starts(st, b->pools, b->d_items.p, b->n_items, b->d_simplices.p, b->n_starts, nm,
+                                   b->d_all.p, b->d_evals_fit.p, b->smem_bytes, b->d_in_shared))
+        return rc;
+    ABFIT_CUDA(cudaEventRecord(b->ev[1], st));
+    if (int rc = launch_select(st, b->pools, b->n_probs, b->n_starts, b->d_all.p, b->d_best.p, b->d_pred.p,
+                               b->d_resid.p, b->d_status.p, b->smem_bytes, b->d_in_shared))
+        return rc;
+    ABFIT_CUDA(cudaEventRecord(b->ev[2], st));
+    b->ev_fit = true;
+    b->fit_done = true;
+    b->launches_fit = (b->n_items > 0 ? 1 : 0) + 1;
+    return 0;
+}
+
+int abfit_batch_download_fit(abfit_batch *b, abfit_fit *best_out, abfit_fit *all_out, double *pred_out,
+                             double *resid_out, int32_t *prob_status_out)
+{
+    if (!b || !b->fit_done) {
+        set_error("download_fit: run_fit first");
+        return ABFIT_ERR_STATE;
+    }
+    ABFIT_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    if (best_out)
+        ABFIT_CUDA(cudaMemcpyAsync(best_out, b->d_best.p, (size_t)b->n_probs * sizeof(abfit_fit), cudaMemcpyDeviceToHost, st));
+    if (all_out)
+        ABFIT_CUDA(cudaMemcpyAsync(all_out, b->d_all.p, (size_t)b->n_probs * b->n_starts * sizeof(abfit_fit),
+                                   cudaMemcpyDeviceToHost, st));
+    if (pred_out)
+        ABFIT_CUDA(cudaMemcpyAsync(pred_out, b->d_pred.p, (size_t)b->total_pairs * 8, cudaMemcpyDeviceToHost, st));
+    if (resid_out)
+        ABFIT_CUDA(cudaMemcpyAsync(resid_out, b->d_resid.p, (size_t)b->total_pairs * 8, cudaMemcpyDeviceToHost, st));
+    if (prob_status_out)
+        ABFIT_CUDA(cudaMemcpyAsync(prob_status_out, b->d_status.p, (size_t)b->n_probs * 4, cudaMemcpyDeviceToHost, st));
+    ABFIT_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int abfit_batch_upload_boot(abfit_batch *b, int32_t n_boot, const abfit_fit *best, const double *pred,
+                            const double *resid, const int32_t *resample_idx, const double *vary_vertices)
+{
+    if (!b || n_boot <= 0 || !resample_idx || !vary_vertices) return ABFIT_ERR_ARG;
+    ABFIT_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    if (best) {
+        if (!pred || !resid) {
+            set_error("upload_boot: best given without pred/resid");
+            return ABFIT_ERR_ARG;
+        }
+        if (int rc = b->d_best.ensure(b->n_probs)) return rc;
+        if (int rc = b->d_pred.ensure((size_t)b->total_pairs)) return rc;
+        if (int rc = b->d_resid.ensure((size_t)b->total_pairs)) return rc;
+        ABFIT_CUDA(cudaMemcpyAsync(b->d_best.p, best, (size_t)b->n_probs * sizeof(abfit_fit), cudaMemcpyHostToDevice, st));
+        ABFIT_CUDA(cudaMemcpyAsync(b->d_pred.p, pred, (size_t)b->total_pairs * 8, cudaMemcpyHostToDevice, st));
+        ABFIT_CUDA(cudaMemcpyAsync(b->d_resid.p, resid, (size_t)b->total_pairs * 8, cudaMemcpyHostToDevice, st));
+    } else if (!b->fit_done) {
+        set_error("upload_boot: no best model on the device (run_fit first or pass best/pred/resid)");
+        return ABFIT_ERR_STATE;
+    }
+    const size_t n_idx = (size_t)b->total_pairs * n_boot, n_vary = (size_t)b->n_probs * n_boot * 16;
+    if (int rc = b->d_idx.ensure(n_idx)) return rc;
+    if (int rc = b->d_vary.ensure(n_vary)) return rc;
+    ABFIT_CUDA(cudaMemcpyAsync(b->d_idx.p, resample_idx, n_idx * 4, cudaMemcpyHostToDevice, st));
+    ABFIT_CUDA(cudaMemcpyAsync(b->d_vary.p, vary_vertices, n_vary * 8, cudaMemcpyHostToDevice, st));
+    if (n_boot != b->n_boot) {
+        b->n_boot = n_boot;
+        std::vector<WorkItem> items = make_items(b->hp, n_boot, b->ctx->prop.multiProcessorCount, true);
+        b->n_boot_items = (int)items.size();
+        if (int rc = b->d_boot_items.ensure(items.size())) return rc;
+        if (!items.empty())
+            ABFIT_CUDA(cudaMemcpyAsync(b->d_boot_items.p, items.data(), items.size() * sizeof(WorkItem),
+                                       cudaMemcpyHostToDevice, st));
+        ABFIT_CUDA(cudaStreamSynchronize(st));
+        if (int rc = b->d_scratch.ensure((size_t)std::max(b->n_boot_items, 1) * b->hp.max_pairs * 32)) return rc;
+        if (int rc = b->d_rows.ensure((size_t)b->n_probs * n_boot * 7)) return rc;
+        if (int rc = b->d_bootfits.ensure((size_t)b->n_probs * n_boot)) return rc;
+    }
+    b->boot_uploaded = true;
+    b->boot_done = false;
+    return 0;
+}
+
+int abfit_batch_run_boot(abfit_batch *b, int32_t max_iters, double sd_tol, uint32_t flags)
+{
+    if (!b || !b->boot_uploaded) {
+        set_error("run_boot: upload_boot first");
+        return ABFIT_ERR_STATE;
+    }
+    ABFIT_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    NMParams nm{max_iters, sd_tol, flags};
+    ABFIT_CUDA(cudaMemsetAsync(b->d_rows.p, 0xFF, (size_t)b->n_probs * b->n_boot * 7 * 8, st));
+    ABFIT_CUDA(cudaMemsetAsync(b->d_bootfits.p, 0xFF, (size_t)b->n_probs * b->n_boot * sizeof(abfit_fit), st));
+    ABFIT_CUDA(cudaMemsetAsync(b->d_evals_boot.p, 0, (size_t)b->n_probs * 8, st));
+    ABFIT_CUDA(cudaEventRecord(b->ev[3], st));
+    if (int rc = launch_fit_boot(st, b->pools, b->d_boot_items.p, b->n_boot_items, b->n_boot, b->d_best.p,
+                                 b->d_pred.p, b->d_resid.p, b->d_idx.p, b->d_vary.p, b->d_scratch.p,
+                                 (int64_t)b->hp.max_pairs * 32, nm, b->d_rows.p, b->d_bootfits.p,
+                                 b->d_evals_boot.p, b->smem_bytes_boot))
+        return rc;
+    ABFIT_CUDA(cudaEventRecord(b->ev[4], st));
+    b->ev_boot = true;
+    b->boot_done = true;
+    b->launches_boot = b->n_boot_items > 0 ? 1 : 0;
+    return 0;
+}
+
+int abfit_batch_download_boot(abfit_batch *b, double *rows_out, abfit_fit *fits_out)
+{
+    if (!b || !b->boot_done) {
+        set_error("download_boot: run_boot first");
+        return ABFIT_ERR_STATE;
+    }
+    ABFIT_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    if (rows_out)
+        ABFIT_CUDA(cudaMemcpyAsync(rows_out, b->d_rows.p, (size_t)b->n_probs * b->n_boot * 7 * 8, cudaMemcpyDeviceToHost, st));
+    if (fits_out)
+        ABFIT_CUDA(cudaMemcpyAsync(fits_out, b->d_bootfits.p, (size_t)b->n_probs * b->n_boot * sizeof(abfit_fit),
+                                   cudaMemcpyDeviceToHost, st));
+    ABFIT_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int abfit_batch_sync(abfit_batch *b)
+{
+    if (!b) return ABFIT_ERR_ARG;
+    ABFIT_CUDA(cudaSetDevice(b->ctx->device));
+    ABFIT_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    return 0;
+}
+
+int abfit_batch_timing(abfit_batch *b, float ms[3], int64_t evals[2], int32_t *launches)
+{
+    if (!b) return ABFIT_ERR_ARG;
+    ABFIT_CUDA(cudaSetDevice(b->ctx->device));
+    ABFIT_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    if (ms) {
+        ms[0] = ms[1] = ms[2] = 0.f;
+        if (b->ev_fit) {
+            ABFIT_CUDA(cudaEventElapsedTime(&ms[0], b->ev[0], b->ev[1]));
+            ABFIT_CUDA(cudaEventElapsedTime(&ms[1], b->ev[1], b->ev[2]));
+        }
+        if (b->ev_boot) ABFIT_CUDA(cudaEventElapsedTime(&ms[2], b->ev[3], b->ev[4]));
+    }
+    if (evals) {
+        std::vector<unsigned long long> h(b->n_probs);
+        evals[0] = evals[1] = 0;
+        ABFIT_CUDA(cudaMemcpy(h.data(), b->d_evals_fit.p, (size_t)b->n_probs * 8, cudaMemcpyDeviceToHost));
+        for (auto v : h) evals[0] += (int64_t)v;
+        ABFIT_CUDA(cudaMemcpy(h.data(), b->d_evals_boot.p, (size_t)b->n_probs * 8, cudaMemcpyDeviceToHost));
+        for (auto v : h) evals[1] += (int64_t)v;
+    }
+    if (launches) *launches = (b->ev_fit ? b->launches_fit : 0) + (b->ev_boot ? b->launches_boot : 0);
+    return 0;
+}
+
+int abfit_batch_flops_per_eval(abfit_batch *b, int32_t p, double *flops_out, int32_t *n_triples_out,
+                               int32_t *tmax_out)
+{
+    if (!b || p < 0 || p >= b->n_probs) return ABFIT_ERR_ARG;
+    if (flops_out) *flops_out = b->hp.flops[p];
+    if (n_triples_out) *n_triples_out = b->hp.probs[p].n_triples;
+    if (tmax_out) *tmax_out = b->hp.tmax[p];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// one-shot host-buffer entry points
+// ---------------------------------------------------------------------------------------
+struct BatchGuard {
+    abfit_batch *b = nullptr;
+    ~BatchGuard() { abfit_batch_destroy(b); }
+};
+
+int abfit_fit_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, int32_t n_starts,
+                    const double *simplices, int32_t max_iters, double sd_tol, uint32_t flags,
+                    abfit_fit *best_out, abfit_fit *all_out, double *pred_out, double *resid_out,
+                    int32_t *prob_status_out)
+{
+    BatchGuard g;
+    if (int rc = abfit_batch_create(ctx, probs, n_probs, &g.b)) return rc;
+    if (int rc = abfit_batch_upload_starts(g.b, n_starts, simplices)) return rc;
+    if (int rc = abfit_batch_run_fit(g.b, max_iters, sd_tol, flags)) return rc;
+    return abfit_batch_download_fit(g.b, best_out, all_out, pred_out, resid_out, prob_status_out);
+}
+
+int abfit_boot_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, const abfit_fit *best,
+                     const double *pred, const double *resid, int32_t n_boot, const int32_t *resample_idx,
+                     const double *vary_vertices, int32_t max_iters, double sd_tol, uint32_t flags,
+                     double *rows_out, abfit_fit *fits_out)
+{
+    if (!best || !pred || !resid) {
+        set_error("boot_batch: best, pred and resid are required");
+        return ABFIT_ERR_ARG;
+    }
+    BatchGuard g;
+    if (int rc = abfit_batch_create(ctx, probs, n_probs, &g.b)) return rc;
+    if (int rc = abfit_batch_upload_boot(g.b, n_boot, best, pred, resid, resample_idx, vary_vertices)) return rc;
+    if (int rc = abfit_batch_run_boot(g.b, max_iters, sd_tol, flags)) return rc;
+    return abfit_batch_download_boot(g.b, rows_out, fits_out);
+}
+
+int abfit_cost_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, const int32_t *prob_of_theta,
+                     const double *theta, int32_t B, double *cost_out, double *lse_out)
+{
+    if (!theta || !cost_out || B <= 0) return ABFIT_ERR_ARG;
+    BatchGuard g;
+    if (int rc = abfit_batch_create(ctx, probs, n_probs, &g.b)) return rc;
+    abfit_batch *b = g.b;
+    // group thetas by problem (stable), 32 per warp
+    std::vector<int32_t> order(B);
+    std::vector<std::vector<int32_t>> by_prob(n_probs);
+    for (int32_t i = 0; i < B; ++i) {
+        const int32_t p = prob_of_theta ? prob_of_theta[i] : 0;
+        if (p < 0 || p >= n_probs) {
+            set_error("prob_of_theta out of range");
+            return ABFIT_ERR_ARG;
+        }
+        by_prob[p].push_back(i);
+    }
+    std::vector<double> th((size_t)B * 4);
+    std::vector<WorkItem> items;
+    int32_t pos = 0;
+    for (int32_t p = 0; p < n_probs; ++p) {
+        const auto &v = by_prob[p];
+        for (size_t f = 0; f < v.size(); f += 32) {
+            WorkItem it{p, pos, (int32_t)std::min<size_t>(32, v.size() - f), 0};
+            for (int32_t q = 0; q < it.count; ++q) {
+                order[pos] = v[f + q];
+                std::memcpy(&th[(size_t)pos * 4], theta + (size_t)v[f + q] * 4, 32);
+                ++pos;
+            }
+            items.push_back(it);
+        }
+    }
+    cudaStream_t st = ctx->stream;
+    DevBuf<double> d_th, d_cost, d_lse;
+    DevBuf<WorkItem> d_items;
+    if (int rc = d_th.ensure((size_t)B * 4)) return rc;
+    if (int rc = d_cost.ensure(B)) return rc;
+    if (int rc = d_lse.ensure(B)) return rc;
+    if (int rc = d_items.ensure(items.size())) return rc;
+    ABFIT_CUDA(cudaMemcpyAsync(d_th.p, th.data(), (size_t)B * 32, cudaMemcpyHostToDevice, st));
+    ABFIT_CUDA(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
+    if (int rc = launch_cost_batch(st, b->pools, d_items.p, (int)items.size(), d_th.p, d_cost.p, d_lse.p,
+                                   b->smem_bytes, b->d_in_shared))
+        return rc;
+    std::vector<double> hc(B), hl(B);
+    ABFIT_CUDA(cudaMemcpyAsync(hc.data(), d_cost.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    ABFIT_CUDA(cudaMemcpyAsync(hl.data(), d_lse.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    ABFIT_CUDA(cudaStreamSynchronize(st));
+    for (int32_t i = 0; i < B; ++i) {
+        cost_out[order[i]] = hc[i];
+        if (lse_out) lse_out[order[i]] = hl[i];
+    }
+    return 0;
+}
+
+int abfit_model_divergence(abfit_ctx *ctx, const abfit_problem *prob, const double theta[4], double *dt1t2_out,
+                           double *p_uu_out)
+{
+    if (!prob || !theta || !dt1t2_out) return ABFIT_ERR_ARG;
+    BatchGuard g;
+    if (int rc = abfit_batch_create(ctx, prob, 1, &g.b)) return rc;
+    cudaStream_t st = ctx->stream;
+    DevBuf<double> d_th, d_dt, d_puu;
+    if (int rc = d_th.ensure(4)) return rc;
+    if (int rc = d_dt.ensure(prob->n_pairs)) return rc;
+    if (int rc = d_puu.ensure(1)) return rc;
+    ABFIT_CUDA(cudaMemcpyAsync(d_th.p, theta, 32, cudaMemcpyHostToDevice, st));
+    if (int rc = launch_model_divergence(st, g.b->pools, d_th.p, d_dt.p, d_puu.p, g.b->hp.smem_without_D)) return rc;
+    ABFIT_CUDA(cudaMemcpyAsync(dt1t2_out, d_dt.p, (size_t)prob->n_pairs * 8, cudaMemcpyDeviceToHost, st));
+    if (p_uu_out) ABFIT_CUDA(cudaMemcpyAsync(p_uu_out, d_puu.p, 8, cudaMemcpyDeviceToHost, st));
+    ABFIT_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int abfit_divergence(abfit_ctx *ctx, const uint8_t *status, const double *posterior_max, const double *meth_lvl,
+                     int32_t S, int64_t L, const int64_t *seg_offsets, int32_t W, double thr, double *D_out,
+                     uint64_t *diff_out, uint64_t *cnt_out, double *p0uu_out, double *methsum_out,
+                     int64_t *nvalid_out)
+{
+    if (!ctx || !status || !posterior_max || !meth_lvl || S <= 0 || L < 0 || S > 65535) return ABFIT_ERR_ARG;
+    int64_t whole[2] = {0, L};
+    if (!seg_offsets) {
+        seg_offsets = whole;
+        W = 1;
+    }
+    if (W <= 0) return ABFIT_ERR_ARG;
+    if (seg_offsets[0] < 0 || seg_offsets[W] > L) {
+        set_error("seg_offsets outside [0, L]");
+        return ABFIT_ERR_ARG;
+    }
+    ABFIT_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)S * (size_t)L;
+    const size_t P = (size_t)S * (S - 1) / 2;
+    DevBuf<uint8_t> d_status;
+    DevBuf<double> d_post, d_meth, d_D, d_methsum, d_p0uu;
+    DevBuf<unsigned long long> d_diff, d_cnt;
+    DevBuf<long long> d_nvalid;
+    if (int rc = d_status.ensure(n)) return rc;
+    if (int rc = d_post.ensure(n)) return rc;
+    if (int rc = d_meth.ensure(n)) return rc;
+    if (int rc = d_D.ensure((size_t)W * P)) return rc;
+    if (int rc = d_diff.ensure((size_t)W * P)) return rc;
+    if (int rc = d_cnt.ensure((size_t)W * P)) return rc;
+    if (int rc = d_methsum.ensure((size_t)W * S)) return rc;
+    if (int rc = d_nvalid.ensure((size_t)W * S)) return rc;
+    if (int rc = d_p0uu.ensure(W)) return rc;
+    if (n) {
+        ABFIT_CUDA(cudaMemcpyAsync(d_status.p, status, n, cudaMemcpyHostToDevice, st));
+        ABFIT_CUDA(cudaMemcpyAsync(d_post.p, posterior_max, n * 8, cudaMemcpyHostToDevice, st));
+        ABFIT_CUDA(cudaMemcpyAsync(d_meth.p, meth_lvl, n * 8, cudaMemcpyHostToDevice, st));
+    }
+    int launches = 0;
+    if (int rc = run_divergence(st, d_status.p, d_post.p, d_meth.p, S, L, seg_offsets, W, thr, d_D.p, d_diff.p,
+                                d_cnt.p, d_methsum.p, d_nvalid.p, d_p0uu.p, &launches))
+        return rc;
+    if (D_out && P) ABFIT_CUDA(cudaMemcpyAsync(D_out, d_D.p, (size_t)W * P * 8, cudaMemcpyDeviceToHost, st));
+    if (diff_out && P) ABFIT_CUDA(cudaMemcpyAsync(diff_out, d_diff.p, (size_t)W * P * 8, cudaMemcpyDeviceToHost, st));
+    if (cnt_out && P) ABFIT_CUDA(cudaMemcpyAsync(cnt_out, d_cnt.p, (size_t)W * P * 8, cudaMemcpyDeviceToHost, st));
+    if (p0uu_out) ABFIT_CUDA(cudaMemcpyAsync(p0uu_out, d_p0uu.p, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
+    if (methsum_out) ABFIT_CUDA(cudaMemcpyAsync(methsum_out, d_methsum.p, (size_t)W * S * 8, cudaMemcpyDeviceToHost, st));
+    if (nvalid_out) ABFIT_CUDA(cudaMemcpyAsync(nvalid_out, d_nvalid.p, (size_t)W * S * 8, cudaMemcpyDeviceToHost, st));
+    ABFIT_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// bootstrap statistics (src/analysis.rs:50-98) — O(n_boot) host post-processing
+// ---------------------------------------------------------------------------------------
+int abfit_analyze(const double *rows, int32_t n, double out[32])
+{
+    if (!rows || n <= 0 || !out) return ABFIT_ERR_ARG;
+    std::vector<double> col(n);
+    const int src[8] = {0, 1, -1, 2, 3, 4, 5, 6};
+    for (int f = 0; f < 8; ++f) {
+        double sum = 0.0;
+        if (src[f] < 0) {
+            // beta/alpha is an owned contiguous array in the reference: ndarray sums it with its
+            // 8-accumulator unrolled fold; strided column views are folded sequentially
+            for (int i = 0; i < n; ++i) col[i] = rows[7 * (size_t)i + 1] / rows[7 * (size_t)i];
+            double p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int i = 0;
+            for (; n - i >= 8; i += 8)
+                for (int k = 0; k < 8; ++k) p[k] += col[i + k];
+            sum += p[0] + p[4];
+            sum += p[1] + p[5];
+            sum += p[2] + p[6];
+            sum += p[3] + p[7];
+            for (; i < n; ++i) sum += col[i];
+        } else {
+            for (int i = 0; i < n; ++i) {
+                col[i] = rows[7 * (size_t)i + src[f]];
+                sum += col[i];
+            }
+        }
+        out[f] = sum / (double)n;
+        // std(ddof = 1): Welford with mul_add, as ndarray 0.15 `var`
+        double mean = 0.0, ssq = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double delta = col[i] - mean;
+            mean = mean + delta / (double)(i + 1);
+            ssq = std::fma(col[i] - mean, delta, ssq);
+        }
+        out[8 + f] = std::sqrt(ssq / ((double)n - 1.0));
+        // quantiles 0.025 / 0.975, ndarray-stats `Linear`
+        std::sort(col.begin(), col.end());
+        const double qs[2] = {0.025, 0.975};
+        for (int k = 0; k < 2; ++k) {
+            const double pos = (double)(n - 1) * qs[k];
+            const double lo = std::floor(pos), hi = std::ceil(pos);
+            const double a = col[(size_t)lo], b2 = col[(size_t)hi];
+            out[16 + 2 * f + k] = a + (b2 - a) * (pos - std::trunc(pos));
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// abfit_internal.h — host-side declarations shared by the API layer and the kernel launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "abfit_device.cuh"
+
+namespace abfit {
+
+// chunk of consecutive starts / replicates / thetas of one problem, processed by one warp
+struct WorkItem {
+    int32_t prob;
+    int32_t first;
+    int32_t count;
+    int32_t pad;
+};
+
+// shared-memory footprint of one problem (bytes) — must match carve_shared() in abfit_kernels.cu
+struct SmemNeed {
+    size_t lane_doubles;  // per-lane doubles: 9*n_exps + n_triples (+25 for the NM simplex)
+    size_t with_D, without_D;
+};
+SmemNeed smem_need(int n_pairs, int n_runs, int n_triples, int n_exps, bool with_simplex);
+
+struct DevicePools {  // device pointers of a compiled batch
+    const DevProblem *probs;
+    const double *D;
+    const uint32_t *runs;
+    const uint32_t *tris;
+    const uint8_t *exps;
+};
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+#define ABFIT_CUDA(call)                                           \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return ::abfit::cuda_fail(e_, #call); \
+    } while (0)
+
+// ---- launchers (abfit_kernels.cu) ---------------------------------------------------
+int launch_fit_starts(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items,
+                      const double *simplices, int n_starts, NMParams nm, abfit_fit *all_out,
+                      unsigned long long *evals_per_prob, size_t smem_bytes, bool d_in_shared);
+int launch_select(cudaStream_t st, const DevicePools &P, int n_probs, int n_starts, const abfit_fit *all,
+                  abfit_fit *best_out, double *pred, double *resid, int32_t *prob_status, size_t smem_bytes,
+                  bool d_in_shared);
+int launch_fit_boot(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_boot,
+                    const abfit_fit *best, const double *pred, const double *resid, const int32_t *resample_idx,
+                    const double *vary, double *dstar_scratch, int64_t scratch_stride, NMParams nm,
+                    double *rows_out, abfit_fit *fits_out, unsigned long long *evals_per_prob, size_t smem_bytes);
+int launch_cost_batch(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items,
+                      const double *theta, double *cost_out, double *lse_out, size_t smem_bytes, bool d_in_shared);
+int launch_model_divergence(cudaStream_t st, const DevicePools &P, const double *theta4, double *dt_out,
+                            double *puu_out, size_t smem_bytes);
+int launch_fp64_peak(cudaStream_t st, int blocks, int threads, int iters, double *sink);
+int max_dynamic_smem(int device);
+
+// ---- divergence (abfit_divergence.cu) -------------------------------------------------
+// h_seg is a HOST array [W+1]; every other pointer is device memory. d_p0uu [W] may be null.
+int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_post, const double *d_meth, int S,
+                   int64_t L, const int64_t *h_seg, int W, double thr, double *d_D, unsigned long long *d_diff,
+                   unsigned long long *d_cnt, double *d_methsum, long long *d_nvalid, double *d_p0uu,
+                   int *launches);
+
+}  // namespace abfit

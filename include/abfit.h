@@ -1,0 +1,212 @@
+/*
+ * abfit.h — C ABI of libabfit, the B200 (sm_100a) implementation of the
+ * alphabeta-rs model-fitting hot path.
+ *
+ * alphabeta-rs has no FFI/plugin layer; the seams this library replaces are
+ * Rust function signatures.  Each entry point below names the
+ * reference interface it stands in for (paths relative to the alphabeta-rs
+ * repository).  INTEGRATION.md shows the Rust `extern "C"` block and the
+ * three call-site changes a maintainer would make.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all arrays are caller-owned, row-major, f64
+ *    unless noted;
+ *  - every call returns 0 on success or a negative abfit_status; a message is
+ *    available from abfit_last_error() (thread-local);
+ *  - nothing here runs on the CPU: without a CUDA device every compute call
+ *    fails with ABFIT_ERR_CUDA — there is no fallback path;
+ *  - a context owns one CUDA device and one stream; use one context per host
+ *    thread (multi-GPU = one context per device, problems sharded by window).
+ *
+ * Arithmetic contract: identical to the reference's operation order
+ * (FMA chains only inside the 3x3 products, everything else unfused IEEE-754
+ * binary64, pair sums accumulated sequentially in pedigree order), so results
+ * are reproducible bit for bit against the CPU restatement in oracle/.
+ */
+#ifndef ABFIT_H
+#define ABFIT_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct abfit_ctx abfit_ctx;
+typedef struct abfit_batch abfit_batch;
+
+typedef enum {
+    ABFIT_OK = 0,
+    ABFIT_ERR_ARG = -1,      /* bad argument (null pointer, negative size, ...) */
+    ABFIT_ERR_CUDA = -2,     /* CUDA runtime / no device */
+    ABFIT_ERR_TIME = -3,     /* pedigree row violates 0 <= t0 <= t1,t2 <= 127 (src/divergence.rs:17-19,52) */
+    ABFIT_ERR_NAN = -4,      /* a value on which the reference panics (NaN divergence, p0uu+p0mm != 1, ...) */
+    ABFIT_ERR_TOO_LARGE = -5,/* per-lane model state of one problem exceeds shared memory */
+    ABFIT_ERR_STATE = -6     /* batch call sequence violated (e.g. boot before fit) */
+} abfit_status;
+
+/* per-fit termination status (abfit_fit.status) */
+enum {
+    ABFIT_TERM_SD = 1,        /* sample sd of the simplex costs < sd_tol (argmin NelderMead::terminate) */
+    ABFIT_TERM_MAX_ITERS = 2, /* iter >= max_iters (argmin Executor) */
+    ABFIT_TERM_STALLED = 3,   /* failed inside contraction left the simplex unchanged: every further
+                                 iteration is identical, so the fit returns what the reference returns
+                                 after max_iters; iters is reported as max_iters */
+    ABFIT_FIT_NAN = -1        /* best cost is NaN: the reference panics on best_param.unwrap() */
+};
+
+/* flags for fit/boot calls */
+enum {
+    ABFIT_SHRINK_ON_FAILED_CONTRACTION = 1, /* later-argmin behaviour; default (0) = argmin 0.8.1 */
+    ABFIT_NO_EARLY_EXIT_ON_STALL = 2        /* burn all max_iters iterations like the reference */
+};
+
+/* One ABneutral problem = one window's pedigree.
+ * Replaces `Problem` (src/structs.rs:12-19) / the arguments of ab_neutral::run
+ * (src/ab_neutral.rs:13-20): `pedigree` is the reference's `Pedigree(Array2<f64>)`
+ * buffer, n_pairs rows of [t0, t1, t2, D] (src/pedigree.rs:32-45).
+ * p0mm = 1 - p0uu and p0um = 0 are derived as in src/ab_neutral.rs:23-24. */
+typedef struct {
+    const double *pedigree; /* [n_pairs][4] */
+    int32_t n_pairs;
+    double p0uu;       /* Pr(UU) at G0 */
+    double eqp;        /* equilibrium target of the penalty (alphabeta.rs passes p0uu) */
+    double eqp_weight; /* penalty weight (alphabeta.rs passes 1.0) */
+} abfit_problem;
+
+/* Result of one Nelder-Mead run.  theta = [alpha, beta, weight, intercept] is
+ * `res.state.best_param` (src/ab_neutral.rs:66), cost = state.best_cost,
+ * lse = penalty-free least squares used for best-of-starts (src/ab_neutral.rs:88-93). */
+typedef struct {
+    double theta[4];
+    double cost;
+    double lse;
+    int32_t iters;
+    int32_t evals;    /* objective evaluations executed by this fit (for FLOP accounting) */
+    int32_t status;   /* ABFIT_TERM_* / ABFIT_FIT_NAN */
+    int32_t start_id; /* index of the start / replicate inside its problem */
+} abfit_fit;
+
+const char *abfit_last_error(void);
+const char *abfit_version(void);
+
+/* ---- context ------------------------------------------------------------ */
+int abfit_ctx_create(int device, abfit_ctx **out);
+void abfit_ctx_destroy(abfit_ctx *ctx);
+/* device properties the bench reports: sm count, max SM clock (kHz), HBM bytes */
+int abfit_ctx_info(abfit_ctx *ctx, int32_t *sm_count, int32_t *sm_clock_khz, int64_t *mem_bytes);
+/* FP64 peak micro-benchmark (independent DFMA chains on every SM); TFLOP/s, FMA = 2 */
+int abfit_measure_fp64_peak(abfit_ctx *ctx, double *tflops_out);
+
+/* ---- host-side input generators ------------------------------------------
+ * `north_star`: random starts and bootstrap resamples are produced on the host
+ * from a seed and fed to every implementation.  Counter-based (splitmix64 keyed
+ * by seed, problem, start/replicate, vertex, coordinate), so any shard can be
+ * generated independently.  Distributions follow the reference:                 */
+/* Model::new (src/structs.rs:78-96): alpha, beta = 10^U(-9,-2); weight ~ U(0,0.1);
+ * intercept ~ U(0, max_div) (max_div <= 0 -> 0.1); out [n_starts][5][4] */
+void abfit_gen_start_simplices(uint64_t seed, uint64_t problem_id, int32_t n_starts, double max_divergence,
+                               double *out);
+/* Model::vary (src/structs.rs:100-128): x -> U(x-0.1|x|, x+0.1|x|) (x == 0 -> U(0.09,0.11));
+ * out [n_boot][4][4] */
+void abfit_gen_vary_vertices(uint64_t seed, uint64_t problem_id, int32_t n_boot, const double best_theta[4],
+                             double *out);
+/* residual resampling with replacement (src/boot_model.rs:43-48); out [n_boot][n_pairs] */
+void abfit_gen_resample_idx(uint64_t seed, uint64_t problem_id, int32_t n_boot, int32_t n_pairs, int32_t *out);
+
+/* ---- one-shot host-buffer entry points (what the Rust FFI binds) ---------- */
+
+/* Objective only.  Replaces `<Problem as CostFunction>::cost` (src/structs.rs:191-217).
+ * theta [B][4]; prob_of_theta [B] selects the problem of each theta (NULL: all problem 0);
+ * cost_out [B] (with penalty), lse_out [B] (without; may be NULL). */
+int abfit_cost_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, const int32_t *prob_of_theta,
+                     const double *theta, int32_t B, double *cost_out, double *lse_out);
+
+/* Theoretical divergence of every pair.  Replaces `divergence()` (src/divergence.rs:33-94)
+ * for one problem and one theta; dt1t2_out [n_pairs], p_uu_out = p_uu_est(alpha,beta). */
+int abfit_model_divergence(abfit_ctx *ctx, const abfit_problem *prob, const double theta[4], double *dt1t2_out,
+                           double *p_uu_out);
+
+/* Multi-start ABneutral fit of n_probs windows.  Replaces `ab_neutral::run`
+ * (src/ab_neutral.rs:13-142), batched over windows (the reference loops windows
+ * serially in src/cli/metaprofile.rs:50-72).
+ *  simplices  [n_probs][n_starts][5][4]  start simplices (Model::new x 5, src/ab_neutral.rs:49-55)
+ *  max_iters  10000 in the reference (src/ab_neutral.rs:61); sd_tol = DBL_EPSILON (argmin default)
+ *  best_out   [n_probs]            best-of-starts by lse, ties -> lowest start id
+ *  all_out    [n_probs][n_starts]  every start's result (may be NULL)
+ *  pred_out / resid_out  [sum n_pairs] predicted divergence and residuals of the best
+ *             model, problems concatenated (src/ab_neutral.rs:123-135; may be NULL)
+ *  prob_status_out [n_probs] 0 or ABFIT_ERR_NAN where the reference would panic (may be NULL) */
+int abfit_fit_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, int32_t n_starts,
+                    const double *simplices, int32_t max_iters, double sd_tol, uint32_t flags,
+                    abfit_fit *best_out, abfit_fit *all_out, double *pred_out, double *resid_out,
+                    int32_t *prob_status_out);
+
+/* Bootstrap refits.  Replaces `boot_model::run` (src/boot_model.rs:17-115) up to and
+ * including the raw result rows (statistics: abfit_analyze).
+ *  best        [n_probs]  model to perturb (theta used)         (src/boot_model.rs:19,70)
+ *  pred, resid [sum n_pairs]                                    (src/boot_model.rs:20-21)
+ *  resample_idx  [n_probs][n_boot][n_pairs_p] concatenated per problem  (:43-48)
+ *  vary_vertices [n_probs][n_boot][4][4]                        (:71-74)
+ *  max_iters   1000 in the reference (:81)
+ *  rows_out    [n_probs][n_boot][7] = alpha,beta,weight,intercept,pr_mm,pr_um,pr_uu (:86-91)
+ *  fits_out    [n_probs][n_boot] (may be NULL) */
+int abfit_boot_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, const abfit_fit *best,
+                     const double *pred, const double *resid, int32_t n_boot, const int32_t *resample_idx,
+                     const double *vary_vertices, int32_t max_iters, double sd_tol, uint32_t flags,
+                     double *rows_out, abfit_fit *fits_out);
+
+/* Observed pairwise divergence + p0uu.  Replaces `DMatrix::from` (src/pedigree.rs:213-262)
+ * and the per-sample statistics of `Pedigree::build` (src/pedigree.rs:159-183).
+ *  status        [S][L] u8: 0 = U, 1 = I, 2 = M (src/methylation_site.rs:130-136)
+ *  posterior_max [S][L], meth_lvl [S][L] (rc.meth.lvl)
+ *  seg_offsets   [W+1] site ranges of W windows over the L axis, or NULL (one window = all sites)
+ *  thr           posterior_max_filter (0.99)
+ *  D_out    [W][S(S-1)/2]  diff/(2*cnt) in pair order (0,1),(0,2)...(S-2,S-1); 0/0 = NaN
+ *  diff_out, cnt_out [W][S(S-1)/2] exact integer sums (may be NULL)
+ *  p0uu_out [W] = mean_s(1 - methsum/nvalid) (may be NULL)
+ *  methsum_out [W][S] sum of meth_lvl over valid sites, nvalid_out [W][S] (may be NULL): the raw
+ *           per-sample partials, so site-sharded callers (one shard per GPU) can add them up.
+ * Windows of at most 65536 sites accumulate methsum sequentially in site order (bit-identical
+ * to the reference); longer ones use a fixed-shape blocked tree (deterministic, <= 1e-12 rel). */
+int abfit_divergence(abfit_ctx *ctx, const uint8_t *status, const double *posterior_max, const double *meth_lvl,
+                     int32_t S, int64_t L, const int64_t *seg_offsets, int32_t W, double thr, double *D_out,
+                     uint64_t *diff_out, uint64_t *cnt_out, double *p0uu_out, double *methsum_out,
+                     int64_t *nvalid_out);
+
+/* ---- staged, device-resident interface ------------------------------------
+ * Same computation as abfit_fit_batch + abfit_boot_batch, split into upload /
+ * run / download so a caller (bench.py, the metaprofile driver) can keep inputs
+ * resident in HBM and overlap transfers.  run_* only enqueue kernels on the
+ * context stream and record CUDA events around them. */
+int abfit_batch_create(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, abfit_batch **out);
+void abfit_batch_destroy(abfit_batch *b);
+int abfit_batch_upload_starts(abfit_batch *b, int32_t n_starts, const double *simplices);
+int abfit_batch_run_fit(abfit_batch *b, int32_t max_iters, double sd_tol, uint32_t flags);
+int abfit_batch_download_fit(abfit_batch *b, abfit_fit *best_out, abfit_fit *all_out, double *pred_out,
+                             double *resid_out, int32_t *prob_status_out);
+/* best == NULL: use the best-of-starts already on the device (needs run_fit first) */
+int abfit_batch_upload_boot(abfit_batch *b, int32_t n_boot, const abfit_fit *best, const double *pred,
+                            const double *resid, const int32_t *resample_idx, const double *vary_vertices);
+int abfit_batch_run_boot(abfit_batch *b, int32_t max_iters, double sd_tol, uint32_t flags);
+int abfit_batch_download_boot(abfit_batch *b, double *rows_out, abfit_fit *fits_out);
+int abfit_batch_sync(abfit_batch *b);
+/* device times of the last run_fit / run_boot (ms, CUDA events on the context stream):
+ * ms[0] multi-start NM kernel, ms[1] best-of-starts select, ms[2] bootstrap NM kernel;
+ * evals[0], evals[1]: objective evaluations executed by the start / bootstrap kernels;
+ * launches: kernels launched by the last run_fit + run_boot. Synchronises the stream. */
+int abfit_batch_timing(abfit_batch *b, float ms[3], int64_t evals[2], int32_t *launches);
+/* algorithmic FLOPs of one objective evaluation of problem p:
+ * 45(Tmax-1) + 56 U + 5 N + 40 */
+int abfit_batch_flops_per_eval(abfit_batch *b, int32_t p, double *flops_out, int32_t *n_triples_out,
+                               int32_t *tmax_out);
+
+/* ---- post-processing ------------------------------------------------------ */
+/* Replaces RawAnalysis::analyze (src/analysis.rs:50-98). rows [n][7] -> out[32]: 8 means,
+ * 8 sds (ddof 1), 8 (q0.025, q0.975) pairs, field order alpha, beta, beta/alpha, weight,
+ * intercept, pr_mm, pr_um, pr_uu. Host only (O(n) per window). */
+int abfit_analyze(const double *rows, int32_t n, double out[32]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,370 @@
+"""ctypes wrapper of the CPU oracle (oracle/libabref.so) plus a Python restatement of the
+reference's input side (nodelist / edgelist / methylome parsing and the pedigree graph).
+
+TEST INFRASTRUCTURE ONLY — see oracle/abref.h.  Imported by tests/, by the smoke check in
+__graft_entry__.py and by bench.py's cpu_baseline / --impl reference legs; never by the
+product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import heapq
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libabref.so")
+
+SHRINK_ON_FAILED_CONTRACTION, EARLY_EXIT_ON_STALL, FAST_DIVERGENCE = 1, 2, 4
+TERM_SD, TERM_MAX_ITERS, TERM_STALLED, ERR_NAN, ERR_TIME = 1, 2, 3, -1, -2
+DBL_EPSILON = 2.220446049250313e-16
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(HERE, f) for f in ("abref.c", "abref.h", "Makefile")]
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in src):
+        subprocess.check_call(["make", "-C", HERE, "-s", "-B", "libabref.so"])
+    return LIB
+
+
+class _Problem(C.Structure):
+    _fields_ = [("ped", C.POINTER(C.c_double)), ("n", C.c_int32), ("p_mm", C.c_double), ("p_um", C.c_double),
+                ("p_uu", C.c_double), ("eqp", C.c_double), ("eqp_weight", C.c_double)]
+
+
+FIT_DTYPE = np.dtype([("theta", "<f8", (4,)), ("cost", "<f8"), ("lse", "<f8"), ("iters", "<i4"), ("evals", "<i4"),
+                      ("status", "<i4"), ("start_id", "<i4")], align=True)
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        l = C.CDLL(LIB)
+        l.abref_cost.restype = C.c_double
+        l.abref_lse.restype = C.c_double
+        for n in ("abref_p_uu_est", "abref_p_mm_est", "abref_p_um_est", "abref_steady_state"):
+            getattr(l, n).restype = C.c_double
+            getattr(l, n).argtypes = [C.c_double, C.c_double]
+        l.abref_p0uu.restype = C.c_double
+        _lib = l
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Problem:
+    """src/structs.rs:12-19; p_mm = 1 - p_uu, p_um = 0 as in src/ab_neutral.rs:23-24 unless given."""
+
+    def __init__(self, pedigree, p_uu, eqp, eqp_weight, p_mm=None, p_um=0.0):
+        self.ped = np.ascontiguousarray(pedigree, dtype=np.float64)
+        self.n = self.ped.shape[0]
+        self.p_uu = float(p_uu)
+        self.p_mm = float(1.0 - p_uu if p_mm is None else p_mm)
+        self.p_um = float(p_um)
+        self.eqp, self.eqp_weight = float(eqp), float(eqp_weight)
+        self.c = _Problem(self.ped.ctypes.data_as(C.POINTER(C.c_double)), self.n, self.p_mm, self.p_um, self.p_uu,
+                          self.eqp, self.eqp_weight)
+
+
+def genmatrix(a, b):
+    G = np.empty(9)
+    lib().abref_genmatrix(C.c_double(a), C.c_double(b), _p(G))
+    return G.reshape(3, 3)
+
+
+def matrix_power(M, p):
+    M = np.ascontiguousarray(M, dtype=np.float64)
+    out = np.empty(9)
+    lib().abref_matrix_power(_p(M), int(p), _p(out))
+    return out.reshape(3, 3)
+
+
+def divergence(pb: Problem, alpha, beta, weight, flags=0):
+    dt = np.empty(pb.n)
+    puu = C.c_double()
+    rc = lib().abref_divergence(_p(pb.ped), pb.n, C.c_double(pb.p_mm), C.c_double(pb.p_um), C.c_double(pb.p_uu),
+                                C.c_double(alpha), C.c_double(beta), C.c_double(weight), flags, _p(dt), C.byref(puu))
+    if rc:
+        raise ValueError(f"abref_divergence rc={rc}")
+    return dt, puu.value
+
+
+def cost(pb: Problem, theta, flags=0) -> float:
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    return lib().abref_cost(C.byref(pb.c), _p(th), flags)
+
+
+def lse(pb: Problem, theta, flags=0) -> float:
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    return lib().abref_lse(C.byref(pb.c), _p(th), flags)
+
+
+def nelder_mead(pb: Problem, simplex, max_iters=10000, sd_tol=DBL_EPSILON, flags=0):
+    sx = np.ascontiguousarray(simplex, dtype=np.float64).reshape(20)
+    out = np.zeros(1, dtype=FIT_DTYPE)
+    lib().abref_nelder_mead(C.byref(pb.c), _p(sx), max_iters, C.c_double(sd_tol), flags, _p(out))
+    return out[0]
+
+
+def ab_neutral(pb: Problem, simplices, max_iters=10000, sd_tol=DBL_EPSILON, flags=0, n_threads=1):
+    sx = np.ascontiguousarray(simplices, dtype=np.float64)
+    n_starts = sx.size // 20
+    best = np.zeros(1, dtype=FIT_DTYPE)
+    allr = np.zeros(n_starts, dtype=FIT_DTYPE)
+    pred, resid = np.empty(pb.n), np.empty(pb.n)
+    rc = lib().abref_ab_neutral(C.byref(pb.c), n_starts, _p(sx), max_iters, C.c_double(sd_tol), flags, n_threads,
+                                _p(best), _p(allr), _p(pred), _p(resid))
+    return rc, best[0], allr, pred, resid
+
+
+def boot_model(pb: Problem, best_theta, pred, resid, resample_idx, vary, max_iters=1000, sd_tol=DBL_EPSILON, flags=0,
+               n_threads=1):
+    th = np.ascontiguousarray(best_theta, dtype=np.float64)
+    pred = np.ascontiguousarray(pred, dtype=np.float64)
+    resid = np.ascontiguousarray(resid, dtype=np.float64)
+    idx = np.ascontiguousarray(resample_idx, dtype=np.int32)
+    vary = np.ascontiguousarray(vary, dtype=np.float64)
+    n_boot = vary.size // 16
+    rows = np.empty((n_boot, 7))
+    fits = np.zeros(n_boot, dtype=FIT_DTYPE)
+    rc = lib().abref_boot_model(C.byref(pb.c), _p(th), _p(pred), _p(resid), n_boot, _p(idx), _p(vary), max_iters,
+                                C.c_double(sd_tol), flags, n_threads, _p(rows), _p(fits))
+    return rc, rows, fits
+
+
+def dmatrix(status, post, thr):
+    status = np.ascontiguousarray(status, dtype=np.uint8)
+    post = np.ascontiguousarray(post, dtype=np.float64)
+    S, L = status.shape
+    P = S * (S - 1) // 2
+    D = np.empty(P)
+    diff = np.empty(P, dtype=np.uint64)
+    cnt = np.empty(P, dtype=np.uint64)
+    lib().abref_dmatrix(_p(status), _p(post), S, C.c_int64(L), C.c_double(thr), _p(D), _p(diff), _p(cnt))
+    return D, diff, cnt
+
+
+def p0uu(post, meth, thr):
+    post = np.ascontiguousarray(post, dtype=np.float64)
+    meth = np.ascontiguousarray(meth, dtype=np.float64)
+    S, L = post.shape
+    rc = np.empty(S)
+    nv = np.empty(S, dtype=np.int64)
+    v = lib().abref_p0uu(_p(post), _p(meth), S, C.c_int64(L), C.c_double(thr), _p(rc), _p(nv))
+    return v, rc, nv
+
+
+def analyze(rows):
+    rows = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, 7)
+    out = np.empty(32)
+    lib().abref_analyze(_p(rows), rows.shape[0], _p(out))
+    return out
+
+
+def hw_threads() -> int:
+    return lib().abref_hw_threads()
+
+
+# ---------------------------------------------------------------------------------------------
+# input side, restated in Python (small inputs only)
+# ---------------------------------------------------------------------------------------------
+def _parse_chromosome(s: str):
+    """src/methylation_site.rs:55-68"""
+    while s.startswith("chr"):
+        s = s[3:]
+    if s == "M":
+        return "M"
+    if s == "C":
+        return "C"
+    if s.isascii() and s.isdigit() or (s.startswith("+") and s[1:].isdigit()):
+        v = int(s)
+        if 0 <= v <= 255:
+            return v
+    raise ValueError("chromosome")
+
+
+def _u32(s: str) -> int:
+    if not (s.isascii() and (s.isdigit() or (s.startswith("+") and s[1:].isdigit()))):
+        raise ValueError("u32")
+    v = int(s)
+    if v > 0xFFFFFFFF:
+        raise ValueError("u32")
+    return v
+
+
+def _status(s: str) -> int:
+    """src/methylation_site.rs:101-115,130-136: U=0, I=1, M=2; anything else parses as U"""
+    if not s:
+        raise ValueError("status")
+    return {"M": 2, "I": 1, "U": 0}.get(s[0], 0)
+
+
+def parse_methylome_line(line: str, invert_strand: bool = False):
+    """MethylationSite::from_methylome_file_line (src/methylation_site.rs:146-362), CG formats.
+    Returns dict(chromosome,start,end,strand,posteriormax,status,meth_lvl) or None."""
+    f = line.split("\t")
+
+    def mk(chrom, start, end, strand, post, status, lvl, cm, ct):
+        return {
+            "chromosome": _parse_chromosome(chrom), "start": start, "end": end,
+            "strand": ("+" if ((strand == "+") ^ invert_strand) else "-"),
+            "count_methylated": _u32(cm), "count_total": _u32(ct),
+            "posteriormax": float(post), "status": _status(status), "meth_lvl": float(lvl), "original": line,
+        }
+
+    try:
+        if len(f) == 9 and f[3] == "CG":
+            return mk(f[0], _u32(f[1]), _u32(f[1]) + 1, f[2], f[6], f[7], f[8], f[4], f[5])
+    except ValueError:
+        pass
+    try:
+        if len(f) == 10 and f[3] == "CG":
+            return mk(f[0], _u32(f[1]), _u32(f[1]) + 1, f[2], f[6], f[7], f[8], f[4], f[5])
+    except ValueError:
+        pass
+    try:
+        if len(f) == 11 and f[3] == "CG":
+            return mk(f[0], _u32(f[1]), _u32(f[2]), f[5], f[8], f[9], f[10], f[6], f[7])
+    except ValueError:
+        pass
+    g = line.replace("\t", " ").split(" ")
+    try:
+        if len(g) == 4:  # chromatin-state / bedGraph / heterogeneity formats: strand unknown, posteriormax 0
+            return {"chromosome": _parse_chromosome(g[0]), "start": _u32(g[1]), "end": _u32(g[2]), "strand": "*",
+                    "count_methylated": 0, "count_total": 0, "posteriormax": 0.0, "status": 0, "meth_lvl": 0.0,
+                    "original": line}
+    except ValueError:
+        pass
+    return None
+
+
+def read_methylome(path: str):
+    """sites of one sample as arrays (status u8, posteriormax f64, meth_lvl f64), file order
+    (src/pedigree.rs:141-157)."""
+    st, po, me = [], [], []
+    with open(path) as fh:
+        for line in fh.read().split("\n"):
+            if line.endswith("\r"):
+                line = line[:-1]
+            s = parse_methylome_line(line)
+            if s is None:
+                continue
+            st.append(s["status"])
+            po.append(s["posteriormax"])
+            me.append(s["meth_lvl"])
+    return np.array(st, dtype=np.uint8), np.array(po), np.array(me)
+
+
+def parse_nodelist(text: str):
+    """src/pedigree.rs:99-116: id = line index after the header (blank lines count)."""
+    nodes = []
+    lines = text.replace("\r", "\n").split("\n")[1:]
+    for i, line in enumerate(lines):
+        e = line.replace(",", "\t").replace(" ", "\t").split("\t")
+        if len(e) < 4:
+            continue
+        try:
+            gen = _u32(e[2])
+        except ValueError:
+            continue
+        nodes.append({"id": i, "file": e[0], "name": e[1], "generation": gen, "meth": e[3] == "Y"})
+    return nodes
+
+
+def parse_edgelist(text: str, nodes):
+    """src/pedigree.rs:123-135"""
+    byname = {}
+    for n in nodes:
+        byname.setdefault(n["name"], n)
+    edges = []
+    for line in text.replace("\r", "\n").split("\n")[1:]:
+        e = line.replace(",", "\t").replace(" ", "\t").split("\t")
+        if len(e) < 2 or e[0] not in byname or e[1] not in byname:
+            continue
+        edges.append((byname[e[0]], byname[e[1]]))
+    return edges
+
+
+def build_pedigree(nodelist_path: str, edgelist_path: str, thr: float, resolve=lambda p: p):
+    """Pedigree::build (src/pedigree.rs:92-193) + DMatrix::convert (:264-337).
+    Returns (pedigree [n,4], p0uu, dict with the per-sample arrays)."""
+    nodes = parse_nodelist(open(nodelist_path).read())
+    if not nodes:
+        raise ValueError("No nodes could be parsed from the nodelist")
+    edges = parse_edgelist(open(edgelist_path).read(), nodes)
+    meas = [n for n in nodes if n["meth"]]
+    data = [read_methylome(resolve(n["file"])) for n in meas]
+    lens = {len(d[0]) for d in data}
+    S = len(meas)
+    if len(lens) == 1:
+        status = np.stack([d[0] for d in data])
+        post = np.stack([d[1] for d in data])
+        meth = np.stack([d[2] for d in data])
+        D, diff, cnt = dmatrix(status, post, thr)
+        p0, rc, nv = p0uu(post, meth, thr)
+    else:
+        raise NotImplementedError("ragged site lists: the reference sets D = 0 for such pairs")
+    # graph: undirected, weight = |generation difference| (src/pedigree.rs:265-277)
+    adj = {}
+    gen_of = {}
+    for a, b in edges:
+        w = abs(a["generation"] - b["generation"])
+        adj.setdefault(a["id"], []).append((b["id"], w))
+        adj.setdefault(b["id"], []).append((a["id"], w))
+        gen_of.setdefault(a["id"], a["generation"])
+        gen_of.setdefault(b["id"], b["generation"])
+
+    def shortest(src, dst):
+        dist = {src: 0}
+        prev = {}
+        pq = [(0, src)]
+        while pq:
+            d, u = heapq.heappop(pq)
+            if u == dst:
+                path = [u]
+                while u in prev:
+                    u = prev[u]
+                    path.append(u)
+                return d, path
+            if d > dist.get(u, 1 << 60):
+                continue
+            for v, w in adj.get(u, []):
+                nd = d + w
+                if nd < dist.get(v, 1 << 60):
+                    dist[v] = nd
+                    prev[v] = u
+                    heapq.heappush(pq, (nd, v))
+        return None
+
+    rows = []
+    p = 0
+    for i in range(S):
+        for j in range(i + 1, S):
+            r = shortest(meas[i]["id"], meas[j]["id"]) if meas[i]["id"] in adj or meas[i]["id"] == meas[j]["id"] else None
+            if r is not None:
+                dist, path = r
+                t0 = float(min(gen_of[n] for n in path))
+                t1, t2 = float(meas[i]["generation"]), float(meas[j]["generation"])
+                assert float(dist) == t1 - t0 + t2 - t0
+                rows.append([t0, t1, t2, D[p]])
+            p += 1
+    ped = np.array(rows, dtype=np.float64).reshape(-1, 4)
+    return ped, p0, {"status": status, "post": post, "meth": meth, "D": D, "diff": diff, "cnt": cnt, "rc": rc,
+                     "nvalid": nv, "nodes": meas}
+
+
+def load_pedigree_file(path: str) -> np.ndarray:
+    """Pedigree::from_file (src/pedigree.rs:62-79): header skipped, space separated."""
+    rows = []
+    for line in open(path).read().split("\n")[1:]:
+        if not line:
+            continue
+        rows.append([float(x) for x in line.split(" ")[:4]])
+    return np.array(rows, dtype=np.float64)

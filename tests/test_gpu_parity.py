@@ -1,0 +1,291 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Integer / index work and — because the kernels keep the reference's
+operation order — all f64 results are compared BIT FOR BIT; the north-star tolerances
+(divergence 1e-12, RSS 1e-9, alpha/beta 1e-6 relative) are asserted as well."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, resolve_golden
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0xAB0B200
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def ped351(oracle):
+    return oracle.load_pedigree_file(os.path.join(GOLDEN, "pedigree.txt"))
+
+
+@pytest.fixture(scope="module")
+def ped78(oracle):
+    ped, p0uu, _ = oracle.build_pedigree(os.path.join(GOLDEN, "desired_output", "nodelist.fn"),
+                                         os.path.join(GOLDEN, "desired_output", "edgelist.fn"), 0.99, resolve_golden)
+    return ped, p0uu
+
+
+def synth_problem(rng, ped_shape, n_keep=None):
+    """C4-style synthetic window: D = c + dt(alpha,beta,w) + noise on the time structure of a real pedigree"""
+    from oracle import abref_py as o
+
+    ped = ped_shape.copy()
+    if n_keep:
+        ped = ped[np.sort(rng.choice(len(ped), n_keep, replace=False))]
+    a, b = 10 ** rng.uniform(-5, -3.3), 10 ** rng.uniform(-4, -2.3)
+    w, c = rng.uniform(0, 0.1), rng.uniform(0, 0.005)
+    p0uu = rng.uniform(0.6, 0.95)
+    pb = o.Problem(ped, p0uu, p0uu, 1.0)
+    dt, _ = o.divergence(pb, a, b, w, o.FAST_DIVERGENCE)
+    ped[:, 3] = np.maximum(c + dt + rng.normal(0, 5e-4, len(ped)), 0.0)
+    return ped, p0uu
+
+
+# ---------------------------------------------------------------------------------------------
+# objective
+# ---------------------------------------------------------------------------------------------
+def test_cost_kat_exact(ab, ctx, ped351):
+    """src/structs.rs:233 through the GPU"""
+    pb = ab.Problem(ped351, 0.75, 0.5, 0.7)
+    assert pb.cost([0.0001179555, 0.0001180614, 0.03693534, 0.003023981], ctx) == 0.0006700888539608879
+
+
+def test_divergence_same_as_r(ab, ctx, oracle, ped351):
+    """src/divergence.rs:139-161 through the GPU; and == oracle bit for bit"""
+    r = np.array([float(x) for x in open(os.path.join(GOLDEN, "divergence.txt")).read().split("\n")])
+    dt, puu = ctx.divergence(ab.Problem(ped351, 0.75, 0.5, 0.7), [3.974271e-09, 1.519045e-07, 0.06892953, 0.0])
+    assert np.max(np.abs(dt - r)) <= 1e-4 and rel(dt, r) < 1e-12
+    want, want_puu = oracle.divergence(oracle.Problem(ped351, 0.75, 0.5, 0.7), 3.974271e-09, 1.519045e-07, 0.06892953)
+    assert np.array_equal(dt, want) and puu == want_puu
+
+
+def test_cost_batch_matches_oracle_bitwise(ab, ctx, oracle, ped351, ped78):
+    rng = np.random.default_rng(1)
+    peds = [(ped351, 0.75), ped78, (np.loadtxt(os.path.join(GOLDEN, "pedigree_generated.txt"), skiprows=1), 0.655)]
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in peds]
+    oprobs = [oracle.Problem(p, u, u, 1.0) for p, u in peds]
+    B = 301  # ragged: not a multiple of 32, interleaved problems
+    pot = rng.integers(0, 3, B).astype(np.int32)
+    theta = np.stack([10 ** rng.uniform(-9, -2, B), 10 ** rng.uniform(-9, -2, B), rng.uniform(0, 0.1, B),
+                      rng.uniform(0, 0.02, B)], axis=1)
+    theta[5] = [-1e-4, 2e-3, -0.3, 0.01]  # the reference has no bounds: negative parameters are legal
+    theta[6] = [0.0, 0.0, 0.0, 0.0]       # alpha + beta = 0 -> 0/0 in p_uu_est -> NaN cost
+    cost, lse = ctx.cost_batch(probs, theta, pot)
+    for i in range(B):
+        wc = oracle.cost(oprobs[pot[i]], theta[i])
+        wl = oracle.lse(oprobs[pot[i]], theta[i])
+        assert (cost[i] == wc) or (np.isnan(cost[i]) and np.isnan(wc)), i
+        assert lse[i] == wl, i
+    assert np.isnan(cost[6]) and np.isfinite(lse[6])
+
+
+def test_time_validation(ab, ctx):
+    ped = np.array([[2.0, 1.0, 3.0, 0.1]])  # t1 < t0: the reference would take the matrix-inverse path
+    with pytest.raises(ab.AbfitError) as e:
+        ctx.cost_batch([ab.Problem(ped, 0.7, 0.7, 1.0)], np.zeros((1, 4)))
+    assert e.value.code == ab.ERR_TIME
+    # `as i8` truncation (src/divergence.rs:52): 3.9 -> 3
+    ped2 = np.array([[0.0, 3.9, 5.2, 0.1], [0.0, 3.0, 5.0, 0.1]])
+    c, _ = ctx.cost_batch([ab.Problem(ped2[:1], 0.7, 0.7, 1.0), ab.Problem(ped2[1:], 0.7, 0.7, 1.0)],
+                          np.array([[1e-4, 1e-3, 0.05, 0.0]] * 2), np.array([0, 1], dtype=np.int32))
+    assert c[0] == c[1]
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-start fit
+# ---------------------------------------------------------------------------------------------
+def check_fit_against_oracle(ab, oracle, res, p, pb_o, sx, max_iters, flags_o, off, n):
+    rc, best, allr, pred, resid = oracle.ab_neutral(pb_o, sx, max_iters=max_iters, flags=flags_o, n_threads=8)
+    assert rc == 0
+    g = res.all[p]
+    for f in ("theta", "cost", "lse", "iters", "evals", "status", "start_id"):
+        assert np.array_equal(g[f], allr[f]), f
+    gb = res.best[p]
+    assert gb["start_id"] == best["start_id"] and np.array_equal(gb["theta"], best["theta"])
+    assert np.array_equal(res.pred[off:off + n], pred) and np.array_equal(res.resid[off:off + n], resid)
+    # north-star tolerances (implied by the above)
+    assert abs(gb["lse"] - best["lse"]) <= 1e-9 * best["lse"]
+    assert rel(gb["theta"][:2], best["theta"][:2]) <= 1e-6
+
+
+def test_fit_c1_real_pedigrees_bitwise(ab, ctx, oracle, ped78):
+    """C1: data/nodelist.txt (N=6) and desired_output (N=78) fits, all starts bit-identical to the oracle"""
+    ped6, p6, _ = oracle.build_pedigree(os.path.join(GOLDEN, "nodelist.txt"), os.path.join(GOLDEN, "edgelist.txt"), 0.99,
+                                        resolve_golden)
+    cases = [(ped6, p6), ped78]
+    n_starts = 100
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    res = ctx.fit_batch(probs, sx, max_iters=10000)
+    assert np.all(res.status == 0)
+    off = 0
+    for i, (p, u) in enumerate(cases):
+        check_fit_against_oracle(ab, oracle, res, i, oracle.Problem(p, u, u, 1.0), sx[i], 10000,
+                                 oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, off, len(p))
+        off += len(p)
+    # R original within 10 % (src/macros.rs:25-34)
+    assert abs(res.best[1]["theta"][0] - 5.7985750419976e-05) < 0.1 * 5.7985750419976e-05
+    assert abs(res.best[1]["theta"][1] - 0.00655710970515347) < 0.1 * 0.00655710970515347
+
+
+def test_fit_synthetic_windows_bitwise(ab, ctx, oracle, ped351):
+    """C4-shaped windows (N=351, U=10, Tmax=32) + ragged ones; every start of every window bit-identical"""
+    rng = np.random.default_rng(42)
+    cases = [synth_problem(rng, ped351) for _ in range(3)] + [synth_problem(rng, ped351, n_keep=k) for k in (1, 33, 200)]
+    n_starts = 70  # not a multiple of 32
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    res = ctx.fit_batch(probs, sx, max_iters=10000)
+    off = 0
+    stalled = 0
+    for i, (p, u) in enumerate(cases):
+        check_fit_against_oracle(ab, oracle, res, i, oracle.Problem(p, u, u, 1.0), sx[i], 10000,
+                                 oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, off, len(p))
+        off += len(p)
+        stalled += int(np.sum(res.all[i]["status"] == ab.TERM_STALLED))
+    assert stalled > 0  # the argmin-0.8.1 stall case is exercised
+
+
+def test_fit_flag_variants_bitwise(ab, ctx, oracle, ped351):
+    """no-early-exit (burn max_iters like the reference) and shrink-on-failed-contraction"""
+    rng = np.random.default_rng(3)
+    p, u = synth_problem(rng, ped351, n_keep=60)
+    sx = ab.gen_start_simplices(SEED, 77, 40, float(p[:, 3].max()))
+    for fl_g, fl_o, mi in ((ab.NO_EARLY_EXIT_ON_STALL, 0, 600),
+                           (ab.SHRINK_ON_FAILED_CONTRACTION, oracle.SHRINK_ON_FAILED_CONTRACTION, 10000)):
+        res = ctx.fit_batch([ab.Problem(p, u, u, 1.0)], sx[None], max_iters=mi, flags=fl_g)
+        check_fit_against_oracle(ab, oracle, res, 0, oracle.Problem(p, u, u, 1.0), sx, mi,
+                                 fl_o | oracle.FAST_DIVERGENCE, 0, len(p))
+
+
+def test_fit_nan_window_is_flagged(ab, ctx, oracle, ped351):
+    """empty window -> NaN divergence: the reference panics (src/ab_neutral.rs:28); we flag that window only"""
+    rng = np.random.default_rng(5)
+    good, u = synth_problem(rng, ped351, n_keep=20)
+    bad = good.copy()
+    bad[3, 3] = np.nan
+    sx = np.stack([ab.gen_start_simplices(SEED, i, 32, 0.02) for i in range(2)])
+    res = ctx.fit_batch([ab.Problem(bad, u, u, 1.0), ab.Problem(good, u, u, 1.0)], sx)
+    assert res.status[0] == ab.ERR_NAN and res.status[1] == 0
+    assert res.best[0]["status"] == ab.FIT_NAN and np.isfinite(res.best[1]["lse"])
+
+
+# ---------------------------------------------------------------------------------------------
+# bootstrap
+# ---------------------------------------------------------------------------------------------
+def test_boot_c2_bitwise(ab, ctx, oracle, ped78, ped351):
+    """C2: boot_model on the real 78-pair pedigree and a synthetic 351-pair window; rows bit-identical"""
+    rng = np.random.default_rng(8)
+    cases = [ped78, synth_problem(rng, ped351)]
+    n_starts, n_boot = 64, 75
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    res = ctx.fit_batch(probs, sx)
+    idx = np.concatenate([ab.gen_resample_idx(SEED, i, n_boot, len(p)).ravel() for i, (p, u) in enumerate(cases)])
+    vary = np.stack([ab.gen_vary_vertices(SEED, i, n_boot, res.best[i]["theta"]) for i in range(len(cases))])
+    rows, fits = ctx.boot_batch(probs, res.best, res.pred, res.resid, idx, vary, max_iters=1000)
+    off = 0
+    for i, (p, u) in enumerate(cases):
+        n = len(p)
+        rc, orows, ofits = oracle.boot_model(oracle.Problem(p, u, u, 1.0), res.best[i]["theta"], res.pred[off:off + n],
+                                             res.resid[off:off + n], idx[off * n_boot:(off + n) * n_boot].reshape(n_boot, n),
+                                             vary[i], max_iters=1000,
+                                             flags=oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, n_threads=8)
+        assert rc == 0
+        assert np.array_equal(rows[i], orows)
+        for f in ("theta", "cost", "iters", "evals", "status"):
+            assert np.array_equal(fits[i][f], ofits[f]), f
+        assert np.array_equal(ab.analyze(rows[i]), oracle.analyze(orows))
+        off += n
+
+
+def test_staged_batch_equals_one_shot(ab, ctx, ped351):
+    """upload / run / download (device-resident) gives the same bytes as the host-buffer calls"""
+    rng = np.random.default_rng(13)
+    cases = [synth_problem(rng, ped351, n_keep=50) for _ in range(4)]
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    sx = np.stack([ab.gen_start_simplices(SEED, i, 48, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    one = ctx.fit_batch(probs, sx)
+    b = ctx.batch(probs)
+    b.upload_starts(sx)
+    b.run_fit()
+    st = b.download_fit(want_all=True)
+    assert st.best.tobytes() == one.best.tobytes() and st.all.tobytes() == one.all.tobytes()
+    assert np.array_equal(st.pred, one.pred) and np.array_equal(st.resid, one.resid)
+    n_boot = 40
+    idx = np.concatenate([ab.gen_resample_idx(SEED, i, n_boot, 50).ravel() for i in range(4)])
+    vary = np.stack([ab.gen_vary_vertices(SEED, i, n_boot, one.best[i]["theta"]) for i in range(4)])
+    rows1, _ = ctx.boot_batch(probs, one.best, one.pred, one.resid, idx, vary)
+    b.upload_boot(idx, vary)  # best / pred / resid stay on the device
+    b.run_boot()
+    rows2, _ = b.download_boot()
+    assert np.array_equal(rows1, rows2)
+    t = b.timing()
+    assert t["fit_ms"] > 0 and t["boot_ms"] > 0 and t["launches"] == 3
+    assert t["evals_fit"] == int(one.all["evals"].sum())
+    b.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# observed divergence
+# ---------------------------------------------------------------------------------------------
+def test_dmatrix_real_files_exact(ab, ctx, oracle):
+    """C1 inputs: D, integer sums, valid-site counts and p0uu bit-exact (data/pedigree_generated.txt)"""
+    _, p0, info = oracle.build_pedigree(os.path.join(GOLDEN, "nodelist.txt"), os.path.join(GOLDEN, "edgelist.txt"), 0.99,
+                                        resolve_golden)
+    out = ctx.dmatrix(info["status"], info["post"], info["meth"], 0.99)
+    want = np.loadtxt(os.path.join(GOLDEN, "pedigree_generated.txt"), skiprows=1)[:, 3]
+    assert np.array_equal(out["D"][0], want)
+    assert [int(x) for x in out["diff"][0]] == [54, 240, 3, 169, 50, 269]
+    assert [int(x) for x in out["cnt"][0]] == [247, 260, 276, 333, 271, 295]
+    assert list(out["nvalid"][0]) == [309, 378, 428, 346]
+    assert out["p0uu"][0] == p0
+
+
+def synth_methylomes(rng, S, L):
+    status = rng.choice(np.array([0, 1, 2], dtype=np.uint8), size=(S, L), p=[0.75, 0.05, 0.20])
+    post = np.where(rng.random((S, L)) < 0.9, 0.9999, rng.uniform(0.5, 0.99, (S, L)))
+    meth = np.clip(status / 2.0 + rng.normal(0, 0.05, (S, L)), 0, 1)
+    return status, post, meth
+
+
+def test_dmatrix_windows_exact(ab, ctx, oracle):
+    """windowed variant: ragged and EMPTY segments, tails that are not multiples of 64"""
+    rng = np.random.default_rng(21)
+    S, L = 9, 5000
+    status, post, meth = synth_methylomes(rng, S, L)
+    seg = np.array([0, 1, 1, 64, 129, 700, 700, 4097, 5000], dtype=np.int64)
+    out = ctx.dmatrix(status, post, meth, 0.99, seg)
+    for w in range(len(seg) - 1):
+        a, b = seg[w], seg[w + 1]
+        D, diff, cnt = oracle.dmatrix(status[:, a:b], post[:, a:b], 0.99)
+        assert np.array_equal(out["diff"][w], diff) and np.array_equal(out["cnt"][w], cnt)
+        assert np.array_equal(out["D"][w], D, equal_nan=True)
+        if b > a:
+            p0, rc, nv = oracle.p0uu(post[:, a:b], meth[:, a:b], 0.99)
+            assert np.array_equal(out["nvalid"][w], nv)
+            assert (out["p0uu"][w] == p0) or (np.isnan(p0) and np.isnan(out["p0uu"][w]))
+
+
+def test_dmatrix_large_blocked(ab, ctx, oracle):
+    """a window longer than 65536 sites uses the blocked tree for methsum: integers exact, p0uu 1e-12"""
+    rng = np.random.default_rng(22)
+    S, L = 6, 300_001
+    status, post, meth = synth_methylomes(rng, S, L)
+    out = ctx.dmatrix(status, post, meth, 0.99)
+    D, diff, cnt = oracle.dmatrix(status, post, 0.99)
+    assert np.array_equal(out["diff"][0], diff) and np.array_equal(out["cnt"][0], cnt) and np.array_equal(out["D"][0], D)
+    p0, rc, nv = oracle.p0uu(post, meth, 0.99)
+    assert np.array_equal(out["nvalid"][0], nv)
+    assert abs(out["p0uu"][0] - p0) <= 1e-12 * abs(p0)
+    # sharding the site axis (one shard per GPU) and adding the integer partials is exact
+    cut = 123_457
+    a = ctx.dmatrix(status[:, :cut], post[:, :cut], meth[:, :cut], 0.99)
+    b = ctx.dmatrix(status[:, cut:], post[:, cut:], meth[:, cut:], 0.99)
+    assert np.array_equal(a["diff"] + b["diff"], out["diff"]) and np.array_equal(a["cnt"] + b["cnt"], out["cnt"])
+    assert np.array_equal(a["nvalid"] + b["nvalid"], out["nvalid"])
