@@ -60,13 +60,15 @@ struct DevBuf {
 struct HostPlan {
     std::vector<DevProblem> probs;
     std::vector<double> D;
-    std::vector<uint32_t> runs, tris;
+    std::vector<uint32_t> tris;
+    std::vector<uint16_t> ids;
     std::vector<uint8_t> exps;
     std::vector<double> flops;     // algorithmic FLOPs per objective evaluation
     std::vector<int32_t> tmax;
     std::vector<uint8_t> d_has_nan;
     size_t smem_with_D = 0, smem_without_D = 0;  // incl. simplex area
     int32_t max_pairs = 0;
+    int64_t total_pairs = 0;
 };
 
 static int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
@@ -86,8 +88,11 @@ static int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &h
             return ABFIT_ERR_ARG;
         }
         DevProblem dp;
-        dp.pair_off = (int64_t)hp.D.size();
-        dp.runs_off = (int64_t)hp.runs.size();
+        if (hp.D.size() & 1) hp.D.push_back(0.0);  // keep every problem's D 16-byte aligned
+        dp.d_off = (int64_t)hp.D.size();
+        dp.pair_off = hp.total_pairs;
+        hp.total_pairs += ap.n_pairs;
+        dp.ids_off = (int64_t)hp.ids.size();
         dp.tri_off = (int64_t)hp.tris.size();
         dp.exp_off = (int64_t)hp.exps.size();
         dp.n_pairs = ap.n_pairs;
@@ -136,22 +141,15 @@ static int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &h
             const int t0 = std::get<0>(kv.first), a = std::get<1>(kv.first), b = std::get<2>(kv.first);
             hp.tris.push_back((uint32_t)slot_of[t0] | ((uint32_t)slot_of[a] << 8) | ((uint32_t)slot_of[b] << 16));
         }
-        int n_runs = 0;
-        for (int i = 0; i < ap.n_pairs;) {
-            const int id = tri_id[key[i]];
-            int len = 1;
-            while (i + len < ap.n_pairs && len < 65535 && key[i + len] == key[i]) ++len;
-            hp.runs.push_back(((uint32_t)id << 16) | (uint32_t)len);
-            ++n_runs;
-            i += len;
-        }
-        dp.n_runs = n_runs;
+        for (int i = 0; i < ap.n_pairs; ++i) hp.ids.push_back((uint16_t)tri_id[key[i]]);
+        while (hp.ids.size() & 3) hp.ids.push_back(0);
+        dp.n_ids = (int32_t)(hp.ids.size() - (size_t)dp.ids_off);
         dp.n_triples = u;
         dp.n_exps = n_exps;
         hp.probs[p] = dp;
         hp.tmax[p] = tmax;
         hp.flops[p] = 45.0 * (tmax > 1 ? tmax - 1 : 0) + 56.0 * u + 5.0 * ap.n_pairs + 40.0;
-        const SmemNeed sn = smem_need(ap.n_pairs, n_runs, u, n_exps, true);
+        const SmemNeed sn = smem_need(ap.n_pairs, u, n_exps, true);
         hp.smem_with_D = std::max(hp.smem_with_D, sn.with_D);
         hp.smem_without_D = std::max(hp.smem_without_D, sn.without_D);
         hp.max_pairs = std::max(hp.max_pairs, ap.n_pairs);
@@ -180,7 +178,8 @@ struct abfit_batch {
     size_t smem_bytes_boot = 0;  // boot kernel (D never staged)
     DevBuf<DevProblem> d_probs;
     DevBuf<double> d_D;
-    DevBuf<uint32_t> d_runs, d_tris;
+    DevBuf<uint32_t> d_tris;
+    DevBuf<uint16_t> d_ids;
     DevBuf<uint8_t> d_exps;
     DevicePools pools{};
     // fit
@@ -389,7 +388,7 @@ int abfit_batch_create(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_pro
     if (int rc = compile_problems(probs, n_probs, b->hp)) return rc;
     HostPlan &hp = b->hp;
     b->n_probs = n_probs;
-    b->total_pairs = (int64_t)hp.D.size();
+    b->total_pairs = hp.total_pairs;
     const size_t cap = (size_t)ctx->smem_optin;
     // D in shared while at least 4 warps still fit on an SM; else broadcast it from L1/L2
     b->d_in_shared = hp.smem_with_D <= 56 * 1024;
@@ -402,18 +401,18 @@ int abfit_batch_create(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_pro
     }
     if (int rc = b->d_probs.ensure(hp.probs.size())) return rc;
     if (int rc = b->d_D.ensure(hp.D.size())) return rc;
-    if (int rc = b->d_runs.ensure(hp.runs.size())) return rc;
+    if (int rc = b->d_ids.ensure(hp.ids.size())) return rc;
     if (int rc = b->d_tris.ensure(hp.tris.size())) return rc;
     if (int rc = b->d_exps.ensure(hp.exps.size())) return rc;
     cudaStream_t st = ctx->stream;
     ABFIT_CUDA(cudaMemcpyAsync(b->d_probs.p, hp.probs.data(), hp.probs.size() * sizeof(DevProblem), cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaMemcpyAsync(b->d_D.p, hp.D.data(), hp.D.size() * 8, cudaMemcpyHostToDevice, st));
-    ABFIT_CUDA(cudaMemcpyAsync(b->d_runs.p, hp.runs.data(), hp.runs.size() * 4, cudaMemcpyHostToDevice, st));
+    ABFIT_CUDA(cudaMemcpyAsync(b->d_ids.p, hp.ids.data(), hp.ids.size() * 2, cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaMemcpyAsync(b->d_tris.p, hp.tris.data(), hp.tris.size() * 4, cudaMemcpyHostToDevice, st));
     if (!hp.exps.empty())
         ABFIT_CUDA(cudaMemcpyAsync(b->d_exps.p, hp.exps.data(), hp.exps.size(), cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaStreamSynchronize(st));  // hp vectors are pageable: make the copies complete here
-    b->pools = DevicePools{b->d_probs.p, b->d_D.p, b->d_runs.p, b->d_tris.p, b->d_exps.p};
+    b->pools = DevicePools{b->d_probs.p, b->d_D.p, b->d_ids.p, b->d_tris.p, b->d_exps.p};
     for (auto &e : b->ev) ABFIT_CUDA(cudaEventCreate(&e));
     if (int rc = b->d_evals_fit.ensure(n_probs)) return rc;
     if (int rc = b->d_evals_boot.ensure(n_probs)) return rc;

@@ -22,15 +22,16 @@ namespace abfit {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-// One window, compiled on the host (abfit_plan.cpp): pairs grouped into runs of equal
-// (t0,t1,t2) in pedigree order, distinct triples, and the exponents whose powers of G
-// the triples need.
+// One window, compiled on the host (compile_problems in abfit_api.cu): the distinct
+// (t0,t1,t2) triples, the id of every pair's triple in pedigree order, and the exponents
+// whose powers of G the triples need.
 struct DevProblem {
-    int64_t pair_off;  // into the D / pred / resid pools
-    int64_t runs_off;  // into the runs pool   (u32: triple << 16 | len, len <= 65535)
+    int64_t d_off;     // into the D pool (even: 16-byte aligned)
+    int64_t pair_off;  // into pred / resid (problems concatenated without padding)
+    int64_t ids_off;   // into the pair-id pool (u16 triple id per pair, padded to a multiple of 4 per problem)
     int64_t tri_off;   // into the triple pool (u32: slot_t0 | slot_a << 8 | slot_b << 16)
     int64_t exp_off;   // into the exponent pool (u8, ascending, all > 0); slot s>0 = exps[s-1], slot 0 = G^0
-    int32_t n_pairs, n_runs, n_triples, n_exps;
+    int32_t n_pairs, n_ids, n_triples, n_exps;  // n_ids = n_pairs rounded up to 4
     double p_uu0, p_mm0;  // state at G0 (p0um = 0), src/ab_neutral.rs:23-24
     double eqp, penw;     // penw = eqp_weight * (double)n_pairs, src/structs.rs:210-211
 };
@@ -38,12 +39,12 @@ struct DevProblem {
 // per-warp view of the staged problem
 struct WarpCtx {
     const double *D;       // [n_pairs] shared (or global in the large-problem variant)
-    const uint32_t *runs;  // shared
+    const uint16_t *ids;   // shared, 8-byte aligned: triple id of every pair
     const uint32_t *tris;  // shared
     const uint8_t *exps;   // shared
     double *pw;            // per-lane power slots: element e of slot s at pw[((s-1)*9+e)*32 + lane]
     double *dt;            // per-lane theoretical divergence per triple: dt[u*32 + lane]
-    int32_t n_pairs, n_runs, n_triples, n_exps;
+    int32_t n_pairs, n_triples, n_exps;
     double p_uu0, p_mm0, eqp, penw;
 };
 
@@ -176,19 +177,35 @@ __device__ __forceinline__ void model_divergence(const WarpCtx &c, int lane, dou
     }
 }
 
-// D access: broadcast (every lane fits the same observed column) or a per-lane column
-// (bootstrap replicates: D*[i] at col[i*32], lane already folded into the pointer).
+// D access: broadcast (every lane fits the same observed column, staged in shared memory and
+// read four pairs at a time) or a per-lane column (bootstrap replicates: D*[i] at col[i*32],
+// lane already folded into the pointer; coalesced across the warp).
 struct DBroadcast {
-    const double *D;
+    const double *D;  // 16-byte aligned
+    __device__ __forceinline__ void load4(int i, double d[4]) const
+    {
+        const double2 a = *reinterpret_cast<const double2 *>(D + i);
+        const double2 b = *reinterpret_cast<const double2 *>(D + i + 2);
+        d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
+    }
     __device__ __forceinline__ double operator()(int i) const { return D[i]; }
 };
 struct DLaneColumn {
     const double *col;
+    __device__ __forceinline__ void load4(int i, double d[4]) const
+    {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[q] = __ldcg(col + (size_t)(i + q) * 32);
+    }
     __device__ __forceinline__ double operator()(int i) const { return __ldcg(col + (size_t)i * 32); }
 };
 
 // Objective (src/structs.rs:191-217).  penalty=false gives the penalty-free LSE of
 // src/ab_neutral.rs:88-93 (r*r + 0.0 == r*r, so one loop serves both).
+//
+// The pair sum is the reference's: sequential, in pedigree order.  Only the accumulate
+// (one DADD per pair) is a dependent chain; the loop is software-pipelined over groups of
+// four pairs so the next group's loads / residuals / squares issue under the chain latency.
 template <class DAcc>
 __device__ __forceinline__ double objective(const WarpCtx &c, const DAcc &Dat, int lane, double alpha,
                                             double beta, double weight, double icpt, bool penalty)
@@ -199,18 +216,50 @@ __device__ __forceinline__ double objective(const WarpCtx &c, const DAcc &Dat, i
         const double dq = p_uu_est(alpha, beta) - c.eqp;
         pen = c.penw * (dq * dq);
     }
+    const double *dtl = c.dt + lane;
+    const int ng = c.n_pairs >> 2;
     double sum = 0.0;
-    int pos = 0;
-    for (int r = 0; r < c.n_runs; ++r) {
-        const uint32_t rr = c.runs[r];
-        const int len = rr & 0xffff;
-        const double dtu = c.dt[(rr >> 16) * 32 + lane];
-#pragma unroll 4
-        for (int i = 0; i < len; ++i) {
-            const double res = Dat(pos + i) - icpt - dtu;
-            sum += res * res + pen;
+    int cur_id = -1;
+    double cur_dt = 0.0;
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+
+    auto terms = [&](int g, double out[4]) {
+        double d[4];
+        Dat.load4(4 * g, d);
+        const uint2 idw = *reinterpret_cast<const uint2 *>(c.ids + 4 * g);  // warp-uniform
+        const int id[4] = {(int)(idw.x & 0xffff), (int)(idw.x >> 16), (int)(idw.y & 0xffff), (int)(idw.y >> 16)};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (id[q] != cur_id) {  // uniform branch: a new (t0,t1,t2) triple starts here
+                cur_id = id[q];
+                cur_dt = dtl[cur_id * 32];
+            }
+            const double res = d[q] - icpt - cur_dt;
+            out[q] = res * res + pen;
         }
-        pos += len;
+    };
+
+    if (ng > 0) {
+        terms(0, t);
+        for (int g = 1; g < ng; ++g) {
+            double n[4];
+            terms(g, n);
+            sum += t[0];
+            sum += t[1];
+            sum += t[2];
+            sum += t[3];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) t[q] = n[q];
+        }
+        sum += t[0];
+        sum += t[1];
+        sum += t[2];
+        sum += t[3];
+    }
+    for (int i = 4 * ng; i < c.n_pairs; ++i) {
+        const int id = c.ids[i];
+        const double res = Dat(i) - icpt - dtl[id * 32];
+        sum += res * res + pen;
     }
     return sum;
 }

@@ -24,12 +24,12 @@ struct SmemNeed {
     size_t lane_doubles;  // per-lane doubles: 9*n_exps + n_triples (+25 for the NM simplex)
     size_t with_D, without_D;
 };
-SmemNeed smem_need(int n_pairs, int n_runs, int n_triples, int n_exps, bool with_simplex);
+SmemNeed smem_need(int n_pairs, int n_triples, int n_exps, bool with_simplex);
 
 struct DevicePools {  // device pointers of a compiled batch
     const DevProblem *probs;
     const double *D;
-    const uint32_t *runs;
+    const uint16_t *ids;
     const uint32_t *tris;
     const uint8_t *exps;
 };

@@ -23,14 +23,15 @@ namespace abfit {
 // ---------------------------------------------------------------------------------
 // shared-memory carve-up (one warp per block)
 // ---------------------------------------------------------------------------------
-SmemNeed smem_need(int n_pairs, int n_runs, int n_triples, int n_exps, bool with_simplex)
+SmemNeed smem_need(int n_pairs, int n_triples, int n_exps, bool with_simplex)
 {
     SmemNeed s;
+    const size_t n_ids = ((size_t)n_pairs + 3) & ~(size_t)3;
     s.lane_doubles = (size_t)9 * n_exps + n_triples + (with_simplex ? 25 : 0);
-    size_t small = (size_t)n_runs * 4 + (size_t)n_triples * 4 + (size_t)n_exps;
-    small = (small + 7) & ~(size_t)7;
+    size_t small = n_ids * 2 + (size_t)n_triples * 4 + (size_t)n_exps;
+    small = (small + 15) & ~(size_t)15;
     s.without_D = s.lane_doubles * 32 * 8 + small;
-    s.with_D = s.without_D + (size_t)n_pairs * 8;
+    s.with_D = s.without_D + (((size_t)n_pairs + 1) & ~(size_t)1) * 8;
     return s;
 }
 
@@ -59,26 +60,25 @@ __device__ __forceinline__ Carved carve_and_stage(const DevProblem &pb, const De
         cv.simplex.X = nullptr;
         cv.simplex.C = nullptr;
     }
-    const double *Dg = P.D + pb.pair_off;
+    const double *Dg = P.D + pb.d_off;
     if (D_SHARED) {
-        double *Ds = p;
-        p += pb.n_pairs;
+        double *Ds = p;  // 256-byte aligned: the per-lane areas are multiples of 256 bytes
+        p += (pb.n_pairs + 1) & ~1;
         for (int i = lane; i < pb.n_pairs; i += 32) Ds[i] = Dg[i];
         cv.ctx.D = Ds;
     } else {
-        cv.ctx.D = Dg;
+        cv.ctx.D = Dg;  // pool offsets are even: 16-byte aligned
     }
-    uint32_t *runs = reinterpret_cast<uint32_t *>(p);
-    uint32_t *tris = runs + pb.n_runs;
+    uint16_t *ids = reinterpret_cast<uint16_t *>(p);  // n_ids is a multiple of 4: tris stay 8-byte aligned
+    uint32_t *tris = reinterpret_cast<uint32_t *>(ids + pb.n_ids);
     uint8_t *exps = reinterpret_cast<uint8_t *>(tris + pb.n_triples);
-    for (int i = lane; i < pb.n_runs; i += 32) runs[i] = P.runs[pb.runs_off + i];
+    for (int i = lane; i < pb.n_ids; i += 32) ids[i] = P.ids[pb.ids_off + i];
     for (int i = lane; i < pb.n_triples; i += 32) tris[i] = P.tris[pb.tri_off + i];
     for (int i = lane; i < pb.n_exps; i += 32) exps[i] = P.exps[pb.exp_off + i];
-    cv.ctx.runs = runs;
+    cv.ctx.ids = ids;
     cv.ctx.tris = tris;
     cv.ctx.exps = exps;
     cv.ctx.n_pairs = pb.n_pairs;
-    cv.ctx.n_runs = pb.n_runs;
     cv.ctx.n_triples = pb.n_triples;
     cv.ctx.n_exps = pb.n_exps;
     cv.ctx.p_uu0 = pb.p_uu0;
@@ -222,17 +222,10 @@ k_select(DevicePools P, int n_starts, const abfit_fit *__restrict__ all, abfit_f
     // src/ab_neutral.rs:108-135 (every lane computes the same dt table; pairs are strided)
     model_divergence(c, lane, b.theta[0], b.theta[1], b.theta[2]);
     __syncwarp();
-    int pos = 0;
-    for (int r = 0; r < c.n_runs; ++r) {
-        const uint32_t rr = c.runs[r];
-        const int len = rr & 0xffff;
-        const double dtu = c.dt[(rr >> 16) * 32 + lane];
-        for (int i = lane; i < len; i += 32) {
-            const double pr = b.theta[3] + dtu;
-            if (pred) pred[pb.pair_off + pos + i] = pr;
-            if (resid) resid[pb.pair_off + pos + i] = c.D[pos + i] - pr;
-        }
-        pos += len;
+    for (int i = lane; i < c.n_pairs; i += 32) {
+        const double pr = b.theta[3] + c.dt[(int)c.ids[i] * 32 + lane];
+        if (pred) pred[pb.pair_off + i] = pr;
+        if (resid) resid[pb.pair_off + i] = c.D[i] - pr;
     }
 }
 
@@ -358,14 +351,7 @@ k_model_div(DevicePools P, const double *__restrict__ theta4, double *__restrict
     const WarpCtx &c = cv.ctx;
     model_divergence(c, lane, theta4[0], theta4[1], theta4[2]);
     __syncwarp();
-    int pos = 0;
-    for (int r = 0; r < c.n_runs; ++r) {
-        const uint32_t rr = c.runs[r];
-        const int len = rr & 0xffff;
-        const double dtu = c.dt[(rr >> 16) * 32 + lane];
-        for (int i = lane; i < len; i += 32) dt_out[pos + i] = dtu;
-        pos += len;
-    }
+    for (int i = lane; i < c.n_pairs; i += 32) dt_out[i] = c.dt[(int)c.ids[i] * 32 + lane];
     if (lane == 0 && puu_out) *puu_out = p_uu_est(theta4[0], theta4[1]);
 }
 
