@@ -61,7 +61,7 @@ struct HostPlan {
     std::vector<DevProblem> probs;
     std::vector<double> D;
     std::vector<uint32_t> tris;
-    std::vector<uint16_t> ids;
+    std::vector<uint32_t> ids;  // 256 * triple id per pair
     std::vector<uint8_t> exps;
     std::vector<double> flops;     // algorithmic FLOPs per objective evaluation
     std::vector<int32_t> tmax;
@@ -141,7 +141,7 @@ static int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &h
             const int t0 = std::get<0>(kv.first), a = std::get<1>(kv.first), b = std::get<2>(kv.first);
             hp.tris.push_back((uint32_t)slot_of[t0] | ((uint32_t)slot_of[a] << 8) | ((uint32_t)slot_of[b] << 16));
         }
-        for (int i = 0; i < ap.n_pairs; ++i) hp.ids.push_back((uint16_t)tri_id[key[i]]);
+        for (int i = 0; i < ap.n_pairs; ++i) hp.ids.push_back((uint32_t)tri_id[key[i]] * 256u);
         while (hp.ids.size() & 3) hp.ids.push_back(0);
         dp.n_ids = (int32_t)(hp.ids.size() - (size_t)dp.ids_off);
         dp.n_triples = u;
@@ -179,7 +179,7 @@ struct abfit_batch {
     DevBuf<DevProblem> d_probs;
     DevBuf<double> d_D;
     DevBuf<uint32_t> d_tris;
-    DevBuf<uint16_t> d_ids;
+    DevBuf<uint32_t> d_ids;
     DevBuf<uint8_t> d_exps;
     DevicePools pools{};
     // fit
@@ -407,7 +407,7 @@ int abfit_batch_create(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_pro
     cudaStream_t st = ctx->stream;
     ABFIT_CUDA(cudaMemcpyAsync(b->d_probs.p, hp.probs.data(), hp.probs.size() * sizeof(DevProblem), cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaMemcpyAsync(b->d_D.p, hp.D.data(), hp.D.size() * 8, cudaMemcpyHostToDevice, st));
-    ABFIT_CUDA(cudaMemcpyAsync(b->d_ids.p, hp.ids.data(), hp.ids.size() * 2, cudaMemcpyHostToDevice, st));
+    ABFIT_CUDA(cudaMemcpyAsync(b->d_ids.p, hp.ids.data(), hp.ids.size() * 4, cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaMemcpyAsync(b->d_tris.p, hp.tris.data(), hp.tris.size() * 4, cudaMemcpyHostToDevice, st));
     if (!hp.exps.empty())
         ABFIT_CUDA(cudaMemcpyAsync(b->d_exps.p, hp.exps.data(), hp.exps.size(), cudaMemcpyHostToDevice, st));

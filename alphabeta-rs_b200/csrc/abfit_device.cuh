@@ -28,7 +28,7 @@ constexpr unsigned FULL = 0xffffffffu;
 struct DevProblem {
     int64_t d_off;     // into the D pool (even: 16-byte aligned)
     int64_t pair_off;  // into pred / resid (problems concatenated without padding)
-    int64_t ids_off;   // into the pair-id pool (u16 triple id per pair, padded to a multiple of 4 per problem)
+    int64_t ids_off;   // into the pair-offset pool (u32 = 256 * triple id per pair; padded to a multiple of 4 per problem)
     int64_t tri_off;   // into the triple pool (u32: slot_t0 | slot_a << 8 | slot_b << 16)
     int64_t exp_off;   // into the exponent pool (u8, ascending, all > 0); slot s>0 = exps[s-1], slot 0 = G^0
     int32_t n_pairs, n_ids, n_triples, n_exps;  // n_ids = n_pairs rounded up to 4
@@ -39,7 +39,7 @@ struct DevProblem {
 // per-warp view of the staged problem
 struct WarpCtx {
     const double *D;       // [n_pairs] shared (or global in the large-problem variant)
-    const uint16_t *ids;   // shared, 8-byte aligned: triple id of every pair
+    const uint32_t *offs;  // shared, 16-byte aligned: 256 * triple id of every pair (byte offset into a dt column)
     const uint32_t *tris;  // shared
     const uint8_t *exps;   // shared
     double *pw;            // per-lane power slots: element e of slot s at pw[((s-1)*9+e)*32 + lane]
@@ -216,49 +216,64 @@ __device__ __forceinline__ double objective(const WarpCtx &c, const DAcc &Dat, i
         const double dq = p_uu_est(alpha, beta) - c.eqp;
         pen = c.penw * (dq * dq);
     }
-    const double *dtl = c.dt + lane;
+    // byte base of this lane's dt column; c.offs[i] = 256 * (triple id of pair i)
+    const char *dtb = reinterpret_cast<const char *>(c.dt + lane);
     const int ng = c.n_pairs >> 2;
     double sum = 0.0;
-    int cur_id = -1;
-    double cur_dt = 0.0;
-    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    double t[4] = {0.0, 0.0, 0.0, 0.0};  // terms of the previous group (adding +0.0 first is exact)
 
-    auto terms = [&](int g, double out[4]) {
-        double d[4];
-        Dat.load4(4 * g, d);
-        const uint2 idw = *reinterpret_cast<const uint2 *>(c.ids + 4 * g);  // warp-uniform
-        const int id[4] = {(int)(idw.x & 0xffff), (int)(idw.x >> 16), (int)(idw.y & 0xffff), (int)(idw.y >> 16)};
+    struct Grp {
+        double d[4], raw[4];
+        uint32_t off[4];
+    };
+    // stage 1: loads of one group of four pairs.  The first dt of a group is always fetched, the
+    // others only where the (warp-uniform) triple id changes inside the group.
+    auto load = [&](int g, Grp &G) {
+        Dat.load4(4 * g, G.d);
+        const uint4 o = *reinterpret_cast<const uint4 *>(c.offs + 4 * g);
+        G.off[0] = o.x; G.off[1] = o.y; G.off[2] = o.z; G.off[3] = o.w;
+        G.raw[0] = *reinterpret_cast<const double *>(dtb + o.x);
+#pragma unroll
+        for (int q = 1; q < 4; ++q)
+            G.raw[q] = (G.off[q] != G.off[q - 1]) ? *reinterpret_cast<const double *>(dtb + G.off[q]) : 0.0;
+    };
+    // stage 2 + 3: residuals / squares of group G, then the sequential accumulate of the previous one
+    auto step = [&](const Grp &G) {
+        double v[4], n[4];
+        v[0] = G.raw[0];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) v[q] = (G.off[q] != G.off[q - 1]) ? G.raw[q] : v[q - 1];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            if (id[q] != cur_id) {  // uniform branch: a new (t0,t1,t2) triple starts here
-                cur_id = id[q];
-                cur_dt = dtl[cur_id * 32];
-            }
-            const double res = d[q] - icpt - cur_dt;
-            out[q] = res * res + pen;
+            const double res = G.d[q] - icpt - v[q];
+            n[q] = res * res + pen;
         }
+        sum += t[0];
+        sum += t[1];
+        sum += t[2];
+        sum += t[3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) t[q] = n[q];
     };
 
     if (ng > 0) {
-        terms(0, t);
-        for (int g = 1; g < ng; ++g) {
-            double n[4];
-            terms(g, n);
-            sum += t[0];
-            sum += t[1];
-            sum += t[2];
-            sum += t[3];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) t[q] = n[q];
+        Grp A, B;
+        load(0, A);
+        int g = 0;
+        for (; g + 1 < ng; g += 2) {
+            load(g + 1, B);
+            step(A);
+            load(min(g + 2, ng - 1), A);
+            step(B);
         }
+        if (g < ng) step(A);
         sum += t[0];
         sum += t[1];
         sum += t[2];
         sum += t[3];
     }
     for (int i = 4 * ng; i < c.n_pairs; ++i) {
-        const int id = c.ids[i];
-        const double res = Dat(i) - icpt - dtl[id * 32];
+        const double res = Dat(i) - icpt - *reinterpret_cast<const double *>(dtb + c.offs[i]);
         sum += res * res + pen;
     }
     return sum;

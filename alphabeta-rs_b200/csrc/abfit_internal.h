@@ -29,7 +29,7 @@ SmemNeed smem_need(int n_pairs, int n_triples, int n_exps, bool with_simplex);
 struct DevicePools {  // device pointers of a compiled batch
     const DevProblem *probs;
     const double *D;
-    const uint16_t *ids;
+    const uint32_t *offs;
     const uint32_t *tris;
     const uint8_t *exps;
 };

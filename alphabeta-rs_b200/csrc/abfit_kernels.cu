@@ -28,7 +28,7 @@ SmemNeed smem_need(int n_pairs, int n_triples, int n_exps, bool with_simplex)
     SmemNeed s;
     const size_t n_ids = ((size_t)n_pairs + 3) & ~(size_t)3;
     s.lane_doubles = (size_t)9 * n_exps + n_triples + (with_simplex ? 25 : 0);
-    size_t small = n_ids * 2 + (size_t)n_triples * 4 + (size_t)n_exps;
+    size_t small = n_ids * 4 + (size_t)n_triples * 4 + (size_t)n_exps;
     small = (small + 15) & ~(size_t)15;
     s.without_D = s.lane_doubles * 32 * 8 + small;
     s.with_D = s.without_D + (((size_t)n_pairs + 1) & ~(size_t)1) * 8;
@@ -69,13 +69,13 @@ __device__ __forceinline__ Carved carve_and_stage(const DevProblem &pb, const De
     } else {
         cv.ctx.D = Dg;  // pool offsets are even: 16-byte aligned
     }
-    uint16_t *ids = reinterpret_cast<uint16_t *>(p);  // n_ids is a multiple of 4: tris stay 8-byte aligned
-    uint32_t *tris = reinterpret_cast<uint32_t *>(ids + pb.n_ids);
+    uint32_t *offs = reinterpret_cast<uint32_t *>(p);  // 16-byte aligned, n_ids is a multiple of 4
+    uint32_t *tris = offs + pb.n_ids;
     uint8_t *exps = reinterpret_cast<uint8_t *>(tris + pb.n_triples);
-    for (int i = lane; i < pb.n_ids; i += 32) ids[i] = P.ids[pb.ids_off + i];
+    for (int i = lane; i < pb.n_ids; i += 32) offs[i] = P.offs[pb.ids_off + i];
     for (int i = lane; i < pb.n_triples; i += 32) tris[i] = P.tris[pb.tri_off + i];
     for (int i = lane; i < pb.n_exps; i += 32) exps[i] = P.exps[pb.exp_off + i];
-    cv.ctx.ids = ids;
+    cv.ctx.offs = offs;
     cv.ctx.tris = tris;
     cv.ctx.exps = exps;
     cv.ctx.n_pairs = pb.n_pairs;
@@ -223,7 +223,7 @@ k_select(DevicePools P, int n_starts, const abfit_fit *__restrict__ all, abfit_f
     model_divergence(c, lane, b.theta[0], b.theta[1], b.theta[2]);
     __syncwarp();
     for (int i = lane; i < c.n_pairs; i += 32) {
-        const double pr = b.theta[3] + c.dt[(int)c.ids[i] * 32 + lane];
+        const double pr = b.theta[3] + c.dt[(c.offs[i] >> 8) * 32 + lane];
         if (pred) pred[pb.pair_off + i] = pr;
         if (resid) resid[pb.pair_off + i] = c.D[i] - pr;
     }
@@ -351,7 +351,7 @@ k_model_div(DevicePools P, const double *__restrict__ theta4, double *__restrict
     const WarpCtx &c = cv.ctx;
     model_divergence(c, lane, theta4[0], theta4[1], theta4[2]);
     __syncwarp();
-    for (int i = lane; i < c.n_pairs; i += 32) dt_out[i] = c.dt[(int)c.ids[i] * 32 + lane];
+    for (int i = lane; i < c.n_pairs; i += 32) dt_out[i] = c.dt[(c.offs[i] >> 8) * 32 + lane];
     if (lane == 0 && puu_out) *puu_out = p_uu_est(theta4[0], theta4[1]);
 }
 
