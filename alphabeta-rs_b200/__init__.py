@@ -80,6 +80,9 @@ def _load() -> C.CDLL:
         "abfit_ctx_destroy": (None, [vp]),
         "abfit_ctx_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
         "abfit_measure_fp64_peak": (C.c_int, [vp, C.POINTER(dbl)]),
+        "abfit_ctx_timer_start": (C.c_int, [vp]),
+        "abfit_ctx_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
+        "abfit_ctx_sync": (C.c_int, [vp]),
         "abfit_gen_start_simplices": (None, [u64, u64, i32, dbl, vp]),
         "abfit_gen_vary_vertices": (None, [u64, u64, i32, vp, vp]),
         "abfit_gen_resample_idx": (None, [u64, u64, i32, i32, vp]),
@@ -111,6 +114,7 @@ def _load() -> C.CDLL:
 _lib = _load()
 EXPORTED_SYMBOLS = (
     "abfit_last_error abfit_version abfit_ctx_create abfit_ctx_destroy abfit_ctx_info abfit_measure_fp64_peak "
+    "abfit_ctx_timer_start abfit_ctx_timer_stop abfit_ctx_sync "
     "abfit_gen_start_simplices abfit_gen_vary_vertices abfit_gen_resample_idx abfit_cost_batch "
     "abfit_model_divergence abfit_fit_batch abfit_boot_batch abfit_divergence abfit_batch_create "
     "abfit_batch_destroy abfit_batch_upload_starts abfit_batch_run_fit abfit_batch_download_fit "
@@ -236,6 +240,17 @@ class Context:
         _check(_lib.abfit_ctx_info(self._h, C.byref(sm), C.byref(khz), C.byref(mem)))
         return {"sm_count": sm.value, "sm_clock_khz": khz.value, "mem_bytes": mem.value}
 
+    def timer_start(self):
+        _check(_lib.abfit_ctx_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        _check(_lib.abfit_ctx_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        _check(_lib.abfit_ctx_sync(self._h))
+
     def measure_fp64_peak(self) -> float:
         v = C.c_double()
         _check(_lib.abfit_measure_fp64_peak(self._h, C.byref(v)))
@@ -279,6 +294,27 @@ class Context:
                                  _ptr(best), _ptr(allr), _ptr(pred), _ptr(resid), _ptr(status))
         )
         return FitResult(best, allr, pred, resid, status)
+
+    def fit_batch_into(self, probs, simplices, best, pred, resid, status, max_iters=10000, sd_tol=DBL_EPSILON,
+                       flags=0, packed=None):
+        """abfit_fit_batch writing into caller-owned (e.g. pinned) arrays; no per-start records."""
+        n_probs = len(probs)
+        n_starts = simplices.size // (n_probs * 20)
+        arr = packed if packed is not None else _pack_problems(probs)
+        _check(
+            _lib.abfit_fit_batch(self._h, arr, n_probs, n_starts, _ptr(simplices), max_iters, sd_tol, flags,
+                                 _ptr(best), None, _ptr(pred), _ptr(resid), _ptr(status))
+        )
+
+    def boot_batch_into(self, probs, best, pred, resid, resample_idx, vary_vertices, rows, max_iters=1000,
+                        sd_tol=DBL_EPSILON, flags=0, packed=None):
+        n_probs = len(probs)
+        n_boot = vary_vertices.size // (n_probs * 16)
+        arr = packed if packed is not None else _pack_problems(probs)
+        _check(
+            _lib.abfit_boot_batch(self._h, arr, n_probs, _ptr(best), _ptr(pred), _ptr(resid), n_boot,
+                                  _ptr(resample_idx), _ptr(vary_vertices), max_iters, sd_tol, flags, _ptr(rows), None)
+        )
 
     # -- boot_model::run, batched over windows ---------------------------------------------------
     def boot_batch(self, probs: Sequence[Problem], best, pred, resid, resample_idx, vary_vertices, max_iters=1000,

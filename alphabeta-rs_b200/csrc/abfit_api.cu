@@ -11,7 +11,7 @@
 #include <memory>
 #include <tuple>
 
-#include "abfit_internal.h"
+#include "abfit_plan.h"
 
 namespace abfit {
 
@@ -21,15 +21,6 @@ int cuda_fail(cudaError_t e, const char *what)
 {
     set_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what);
     return ABFIT_ERR_CUDA;
-}
-
-// `x as i8` in Rust (saturating, NaN -> 0), src/divergence.rs:52
-static inline int as_i8(double x)
-{
-    if (x != x) return 0;
-    if (x >= 127.0) return 127;
-    if (x <= -128.0) return -128;
-    return (int)x;
 }
 
 template <class T>
@@ -57,106 +48,6 @@ struct DevBuf {
     DevBuf &operator=(const DevBuf &) = delete;
 };
 
-struct HostPlan {
-    std::vector<DevProblem> probs;
-    std::vector<double> D;
-    std::vector<uint32_t> tris;
-    std::vector<uint32_t> ids;  // 256 * triple id per pair
-    std::vector<uint8_t> exps;
-    std::vector<double> flops;     // algorithmic FLOPs per objective evaluation
-    std::vector<int32_t> tmax;
-    std::vector<uint8_t> d_has_nan;
-    size_t smem_with_D = 0, smem_without_D = 0;  // incl. simplex area
-    int32_t max_pairs = 0;
-    int64_t total_pairs = 0;
-};
-
-static int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
-{
-    if (!probs || n_probs <= 0) {
-        set_error("no problems");
-        return ABFIT_ERR_ARG;
-    }
-    hp.probs.resize(n_probs);
-    hp.flops.resize(n_probs);
-    hp.tmax.resize(n_probs);
-    hp.d_has_nan.assign(n_probs, 0);
-    for (int p = 0; p < n_probs; ++p) {
-        const abfit_problem &ap = probs[p];
-        if (!ap.pedigree || ap.n_pairs <= 0) {
-            set_error("problem " + std::to_string(p) + ": empty pedigree");
-            return ABFIT_ERR_ARG;
-        }
-        DevProblem dp;
-        if (hp.D.size() & 1) hp.D.push_back(0.0);  // keep every problem's D 16-byte aligned
-        dp.d_off = (int64_t)hp.D.size();
-        dp.pair_off = hp.total_pairs;
-        hp.total_pairs += ap.n_pairs;
-        dp.ids_off = (int64_t)hp.ids.size();
-        dp.tri_off = (int64_t)hp.tris.size();
-        dp.exp_off = (int64_t)hp.exps.size();
-        dp.n_pairs = ap.n_pairs;
-        dp.p_uu0 = ap.p0uu;
-        dp.p_mm0 = 1.0 - ap.p0uu;  // src/ab_neutral.rs:23
-        if (dp.p_mm0 + dp.p_uu0 + 0.0 != 1.0) {  // src/ab_neutral.rs:31 assert_eq!
-            set_error("problem " + std::to_string(p) + ": p0mm + p0uu + p0um != 1");
-            return ABFIT_ERR_NAN;
-        }
-        dp.eqp = ap.eqp;
-        dp.penw = ap.eqp_weight * (double)ap.n_pairs;  // src/structs.rs:210-211
-
-        // triples and exponents
-        std::vector<std::tuple<int, int, int>> key(ap.n_pairs);
-        std::vector<int> used_exp(128, 0);
-        for (int i = 0; i < ap.n_pairs; ++i) {
-            const double *row = ap.pedigree + 4 * (size_t)i;
-            const int t0 = as_i8(row[0]), t1 = as_i8(row[1]), t2 = as_i8(row[2]);
-            if (t0 < 0 || t1 < t0 || t2 < t0) {
-                set_error("problem " + std::to_string(p) + " row " + std::to_string(i) +
-                          ": needs 0 <= t0 <= t1,t2 <= 127 (the reference would invert the matrix)");
-                return ABFIT_ERR_TIME;
-            }
-            key[i] = std::make_tuple(t0, t1 - t0, t2 - t0);
-            used_exp[t0] = used_exp[t1 - t0] = used_exp[t2 - t0] = 1;
-            if (row[3] != row[3]) hp.d_has_nan[p] = 1;
-            hp.D.push_back(row[3]);
-        }
-        std::vector<int> slot_of(128, 0);
-        int n_exps = 0, tmax = 0;
-        for (int e = 1; e < 128; ++e)
-            if (used_exp[e]) {
-                hp.exps.push_back((uint8_t)e);
-                slot_of[e] = ++n_exps;
-                tmax = e;
-            }
-        std::map<std::tuple<int, int, int>, int> tri_id;
-        for (auto &k : key) tri_id.emplace(k, 0);
-        if (tri_id.size() > 65535) {
-            set_error("problem " + std::to_string(p) + ": more than 65535 distinct (t0,t1,t2) triples");
-            return ABFIT_ERR_TOO_LARGE;
-        }
-        int u = 0;
-        for (auto &kv : tri_id) {  // sorted by (t0, a, b): consecutive triples reuse loaded powers
-            kv.second = u++;
-            const int t0 = std::get<0>(kv.first), a = std::get<1>(kv.first), b = std::get<2>(kv.first);
-            hp.tris.push_back((uint32_t)slot_of[t0] | ((uint32_t)slot_of[a] << 8) | ((uint32_t)slot_of[b] << 16));
-        }
-        for (int i = 0; i < ap.n_pairs; ++i) hp.ids.push_back((uint32_t)tri_id[key[i]] * 256u);
-        while (hp.ids.size() & 3) hp.ids.push_back(0);
-        dp.n_ids = (int32_t)(hp.ids.size() - (size_t)dp.ids_off);
-        dp.n_triples = u;
-        dp.n_exps = n_exps;
-        hp.probs[p] = dp;
-        hp.tmax[p] = tmax;
-        hp.flops[p] = 45.0 * (tmax > 1 ? tmax - 1 : 0) + 56.0 * u + 5.0 * ap.n_pairs + 40.0;
-        const SmemNeed sn = smem_need(ap.n_pairs, u, n_exps, true);
-        hp.smem_with_D = std::max(hp.smem_with_D, sn.with_D);
-        hp.smem_without_D = std::max(hp.smem_without_D, sn.without_D);
-        hp.max_pairs = std::max(hp.max_pairs, ap.n_pairs);
-    }
-    return 0;
-}
-
 }  // namespace abfit
 
 using namespace abfit;
@@ -166,21 +57,23 @@ struct abfit_ctx {
     cudaStream_t stream = nullptr;
     cudaDeviceProp prop{};
     int smem_optin = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    // workspace of the one-shot host-buffer calls: device buffers are kept between calls
+    // (cudaMalloc/cudaFree of multi-GB buffers costs more than the kernels of a small batch)
+    abfit_batch *scratch = nullptr;
 };
 
 struct abfit_batch {
     abfit_ctx *ctx = nullptr;
     HostPlan hp;
+    LaunchShape shape;
     int n_probs = 0;
     int64_t total_pairs = 0;
-    bool d_in_shared = true;
-    size_t smem_bytes = 0;       // start kernel / select / cost
-    size_t smem_bytes_boot = 0;  // boot kernel (D never staged)
     DevBuf<DevProblem> d_probs;
     DevBuf<double> d_D;
-    DevBuf<uint32_t> d_tris;
-    DevBuf<uint32_t> d_ids;
-    DevBuf<uint8_t> d_exps;
+    DevBuf<uint32_t> d_offs;
+    DevBuf<OpWord> d_ops;
+    DevBuf<EvWord> d_events;
     DevicePools pools{};
     // fit
     int n_starts = 0;
@@ -205,32 +98,6 @@ struct abfit_batch {
     bool ev_fit = false, ev_boot = false;
     int launches_fit = 0, launches_boot = 0;
 };
-
-static std::vector<WorkItem> make_items(const HostPlan &hp, int count_per_prob, int n_sm, bool skip_nan)
-{
-    // One warp per item.  Enough items to fill the machine several times over, but chunks as
-    // long as possible so that idle lanes can pull further fits of the same window.
-    const int64_t target = (int64_t)n_sm * 8 * 4;
-    const int n_probs = (int)hp.probs.size();
-    int64_t total = (int64_t)n_probs * count_per_prob;
-    int64_t chunk = (total + target - 1) / target;
-    chunk = ((chunk + 31) / 32) * 32;
-    if (chunk < 32) chunk = 32;
-    if (chunk > count_per_prob) chunk = count_per_prob;
-    std::vector<WorkItem> items;
-    for (int p = 0; p < n_probs; ++p) {
-        if (skip_nan && hp.d_has_nan[p]) continue;
-        for (int f = 0; f < count_per_prob; f += (int)chunk) {
-            WorkItem it;
-            it.prob = p;
-            it.first = f;
-            it.count = std::min<int>((int)chunk, count_per_prob - f);
-            it.pad = 0;
-            items.push_back(it);
-        }
-    }
-    return items;
-}
 
 extern "C" {
 
@@ -272,6 +139,9 @@ void abfit_ctx_destroy(abfit_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->scratch) abfit_batch_destroy(ctx->scratch);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -286,6 +156,36 @@ int abfit_ctx_info(abfit_ctx *ctx, int32_t *sm_count, int32_t *sm_clock_khz, int
         *sm_clock_khz = khz;
     }
     if (mem_bytes) *mem_bytes = (int64_t)ctx->prop.totalGlobalMem;
+    return 0;
+}
+
+int abfit_ctx_timer_start(abfit_ctx *ctx)
+{
+    if (!ctx) return ABFIT_ERR_ARG;
+    ABFIT_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->t0) {
+        ABFIT_CUDA(cudaEventCreate(&ctx->t0));
+        ABFIT_CUDA(cudaEventCreate(&ctx->t1));
+    }
+    ABFIT_CUDA(cudaEventRecord(ctx->t0, ctx->stream));
+    return 0;
+}
+
+int abfit_ctx_timer_stop(abfit_ctx *ctx, float *ms_out)
+{
+    if (!ctx || !ms_out || !ctx->t0) return ABFIT_ERR_ARG;
+    ABFIT_CUDA(cudaSetDevice(ctx->device));
+    ABFIT_CUDA(cudaEventRecord(ctx->t1, ctx->stream));
+    ABFIT_CUDA(cudaEventSynchronize(ctx->t1));
+    ABFIT_CUDA(cudaEventElapsedTime(ms_out, ctx->t0, ctx->t1));
+    return 0;
+}
+
+int abfit_ctx_sync(abfit_ctx *ctx)
+{
+    if (!ctx) return ABFIT_ERR_ARG;
+    ABFIT_CUDA(cudaSetDevice(ctx->device));
+    ABFIT_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -389,30 +289,26 @@ int abfit_batch_create(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_pro
     HostPlan &hp = b->hp;
     b->n_probs = n_probs;
     b->total_pairs = hp.total_pairs;
-    const size_t cap = (size_t)ctx->smem_optin;
-    // D in shared while at least 4 warps still fit on an SM; else broadcast it from L1/L2
-    b->d_in_shared = hp.smem_with_D <= 56 * 1024;
-    b->smem_bytes = b->d_in_shared ? hp.smem_with_D : hp.smem_without_D;
-    b->smem_bytes_boot = hp.smem_without_D;
-    if (b->smem_bytes > cap) {
-        set_error("per-lane model state needs " + std::to_string(b->smem_bytes) + " B of shared memory (limit " +
-                  std::to_string(cap) + "): too many distinct exponents/triples in one pedigree");
-        return ABFIT_ERR_TOO_LARGE;
-    }
+    // aux kernels (select / cost / model divergence) only need the one-warp, simplex-free shape;
+    // the fit shape is chosen in upload_starts / upload_boot when the number of fits is known
+    if (int rc = choose_launch_shape(hp, (size_t)ctx->smem_optin, (size_t)ctx->prop.sharedMemPerMultiprocessor, 1,
+                                     b->shape))
+        return rc;
     if (int rc = b->d_probs.ensure(hp.probs.size())) return rc;
     if (int rc = b->d_D.ensure(hp.D.size())) return rc;
-    if (int rc = b->d_ids.ensure(hp.ids.size())) return rc;
-    if (int rc = b->d_tris.ensure(hp.tris.size())) return rc;
-    if (int rc = b->d_exps.ensure(hp.exps.size())) return rc;
+    if (int rc = b->d_offs.ensure(hp.offs.size())) return rc;
+    if (int rc = b->d_ops.ensure(hp.ops.size())) return rc;
+    if (int rc = b->d_events.ensure(hp.events.size())) return rc;
     cudaStream_t st = ctx->stream;
     ABFIT_CUDA(cudaMemcpyAsync(b->d_probs.p, hp.probs.data(), hp.probs.size() * sizeof(DevProblem), cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaMemcpyAsync(b->d_D.p, hp.D.data(), hp.D.size() * 8, cudaMemcpyHostToDevice, st));
-    ABFIT_CUDA(cudaMemcpyAsync(b->d_ids.p, hp.ids.data(), hp.ids.size() * 4, cudaMemcpyHostToDevice, st));
-    ABFIT_CUDA(cudaMemcpyAsync(b->d_tris.p, hp.tris.data(), hp.tris.size() * 4, cudaMemcpyHostToDevice, st));
-    if (!hp.exps.empty())
-        ABFIT_CUDA(cudaMemcpyAsync(b->d_exps.p, hp.exps.data(), hp.exps.size(), cudaMemcpyHostToDevice, st));
+    ABFIT_CUDA(cudaMemcpyAsync(b->d_offs.p, hp.offs.data(), hp.offs.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!hp.ops.empty())
+        ABFIT_CUDA(cudaMemcpyAsync(b->d_ops.p, hp.ops.data(), hp.ops.size() * sizeof(OpWord), cudaMemcpyHostToDevice, st));
+    if (!hp.events.empty())
+        ABFIT_CUDA(cudaMemcpyAsync(b->d_events.p, hp.events.data(), hp.events.size() * sizeof(EvWord), cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaStreamSynchronize(st));  // hp vectors are pageable: make the copies complete here
-    b->pools = DevicePools{b->d_probs.p, b->d_D.p, b->d_ids.p, b->d_tris.p, b->d_exps.p};
+    b->pools = DevicePools{b->d_probs.p, b->d_D.p, b->d_offs.p, b->d_ops.p, b->d_events.p};
     for (auto &e : b->ev) ABFIT_CUDA(cudaEventCreate(&e));
     if (int rc = b->d_evals_fit.ensure(n_probs)) return rc;
     if (int rc = b->d_evals_boot.ensure(n_probs)) return rc;
@@ -441,7 +337,11 @@ int abfit_batch_upload_starts(abfit_batch *b, int32_t n_starts, const double *si
     ABFIT_CUDA(cudaMemcpyAsync(b->d_simplices.p, simplices, n * 8, cudaMemcpyHostToDevice, b->ctx->stream));
     if (n_starts != b->n_starts) {
         b->n_starts = n_starts;
-        std::vector<WorkItem> items = make_items(b->hp, n_starts, b->ctx->prop.multiProcessorCount, true);
+        if (int rc = choose_launch_shape(b->hp, (size_t)b->ctx->smem_optin,
+                                         (size_t)b->ctx->prop.sharedMemPerMultiprocessor, n_starts, b->shape))
+            return rc;
+        std::vector<WorkItem> items =
+            make_items(b->hp, n_starts, b->ctx->prop.multiProcessorCount, b->shape.n_warps, true);
         b->n_items = (int)items.size();
         if (int rc = b->d_items.ensure(items.size())) return rc;
         if (!items.empty())
@@ -471,12 +371,13 @@ int abfit_batch_run_fit(abfit_batch *b, int32_t max_iters, double sd_tol, uint32
     ABFIT_CUDA(cudaMemsetAsync(b->d_all.p, 0xFF, (size_t)b->n_probs * b->n_starts * sizeof(abfit_fit), st));
     ABFIT_CUDA(cudaMemsetAsync(b->d_evals_fit.p, 0, (size_t)b->n_probs * 8, st));
     ABFIT_CUDA(cudaEventRecord(b->ev[0], st));
-    if (int rc = launch_fit_starts(st, b->pools, b->d_items.p, b->n_items, b->d_simplices.p, b->n_starts, nm,
-                                   b->d_all.p, b->d_evals_fit.p, b->smem_bytes, b->d_in_shared))
+    if (int rc = launch_fit_starts(st, b->pools, b->d_items.p, b->n_items, b->shape.n_warps, b->d_simplices.p,
+                                   b->n_starts, nm, b->d_all.p, b->d_evals_fit.p, b->shape.smem_fit,
+                                   b->shape.d_shared))
         return rc;
     ABFIT_CUDA(cudaEventRecord(b->ev[1], st));
     if (int rc = launch_select(st, b->pools, b->n_probs, b->n_starts, b->d_all.p, b->d_best.p, b->d_pred.p,
-                               b->d_resid.p, b->d_status.p, b->smem_bytes, b->d_in_shared))
+                               b->d_resid.p, b->d_status.p, b->shape.smem_aux, b->shape.d_shared_aux))
         return rc;
     ABFIT_CUDA(cudaEventRecord(b->ev[2], st));
     b->ev_fit = true;
@@ -537,7 +438,7 @@ int abfit_batch_upload_boot(abfit_batch *b, int32_t n_boot, const abfit_fit *bes
     ABFIT_CUDA(cudaMemcpyAsync(b->d_vary.p, vary_vertices, n_vary * 8, cudaMemcpyHostToDevice, st));
     if (n_boot != b->n_boot) {
         b->n_boot = n_boot;
-        std::vector<WorkItem> items = make_items(b->hp, n_boot, b->ctx->prop.multiProcessorCount, true);
+        std::vector<WorkItem> items = make_items(b->hp, n_boot, b->ctx->prop.multiProcessorCount, 1, true);
         b->n_boot_items = (int)items.size();
         if (int rc = b->d_boot_items.ensure(items.size())) return rc;
         if (!items.empty())
@@ -569,7 +470,7 @@ int abfit_batch_run_boot(abfit_batch *b, int32_t max_iters, double sd_tol, uint3
     if (int rc = launch_fit_boot(st, b->pools, b->d_boot_items.p, b->n_boot_items, b->n_boot, b->d_best.p,
                                  b->d_pred.p, b->d_resid.p, b->d_idx.p, b->d_vary.p, b->d_scratch.p,
                                  (int64_t)b->hp.max_pairs * 32, nm, b->d_rows.p, b->d_bootfits.p,
-                                 b->d_evals_boot.p, b->smem_bytes_boot))
+                                 b->d_evals_boot.p, b->shape.smem_boot))
         return rc;
     ABFIT_CUDA(cudaEventRecord(b->ev[4], st));
     b->ev_boot = true;
@@ -633,7 +534,7 @@ int abfit_batch_flops_per_eval(abfit_batch *b, int32_t p, double *flops_out, int
 {
     if (!b || p < 0 || p >= b->n_probs) return ABFIT_ERR_ARG;
     if (flops_out) *flops_out = b->hp.flops[p];
-    if (n_triples_out) *n_triples_out = b->hp.probs[p].n_triples;
+    if (n_triples_out) *n_triples_out = b->hp.n_triples[p];
     if (tmax_out) *tmax_out = b->hp.tmax[p];
     return 0;
 }
@@ -717,7 +618,7 @@ int abfit_cost_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs
     ABFIT_CUDA(cudaMemcpyAsync(d_th.p, th.data(), (size_t)B * 32, cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
     if (int rc = launch_cost_batch(st, b->pools, d_items.p, (int)items.size(), d_th.p, d_cost.p, d_lse.p,
-                                   b->smem_bytes, b->d_in_shared))
+                                   b->shape.smem_aux, b->shape.d_shared_aux))
         return rc;
     std::vector<double> hc(B), hl(B);
     ABFIT_CUDA(cudaMemcpyAsync(hc.data(), d_cost.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
@@ -742,7 +643,9 @@ int abfit_model_divergence(abfit_ctx *ctx, const abfit_problem *prob, const doub
     if (int rc = d_dt.ensure(prob->n_pairs)) return rc;
     if (int rc = d_puu.ensure(1)) return rc;
     ABFIT_CUDA(cudaMemcpyAsync(d_th.p, theta, 32, cudaMemcpyHostToDevice, st));
-    if (int rc = launch_model_divergence(st, g.b->pools, d_th.p, d_dt.p, d_puu.p, g.b->hp.smem_without_D)) return rc;
+    if (int rc = launch_model_divergence(st, g.b->pools, d_th.p, d_dt.p, d_puu.p,
+                                         smem_need(g.b->hp.probs[0], false, false, 1)))
+        return rc;
     ABFIT_CUDA(cudaMemcpyAsync(dt1t2_out, d_dt.p, (size_t)prob->n_pairs * 8, cudaMemcpyDeviceToHost, st));
     if (p_uu_out) ABFIT_CUDA(cudaMemcpyAsync(p_uu_out, d_puu.p, 8, cudaMemcpyDeviceToHost, st));
     ABFIT_CUDA(cudaStreamSynchronize(st));

@@ -7,11 +7,11 @@
 #include <string>
 #include <vector>
 
-#include "abfit_device.cuh"
+#include "abfit_nm.cuh"
 
 namespace abfit {
 
-// chunk of consecutive starts / replicates / thetas of one problem, processed by one warp
+// chunk of consecutive starts / replicates / thetas of one problem, processed by one block
 struct WorkItem {
     int32_t prob;
     int32_t first;
@@ -19,20 +19,16 @@ struct WorkItem {
     int32_t pad;
 };
 
-// shared-memory footprint of one problem (bytes) — must match carve_shared() in abfit_kernels.cu
-struct SmemNeed {
-    size_t lane_doubles;  // per-lane doubles: 9*n_exps + n_triples (+25 for the NM simplex)
-    size_t with_D, without_D;
-};
-SmemNeed smem_need(int n_pairs, int n_triples, int n_exps, bool with_simplex);
-
 struct DevicePools {  // device pointers of a compiled batch
     const DevProblem *probs;
     const double *D;
     const uint32_t *offs;
-    const uint32_t *tris;
-    const uint8_t *exps;
+    const OpWord *ops;
+    const EvWord *events;
 };
+
+// dynamic shared memory of one block working on problem pb (matches carve_and_stage)
+size_t smem_need(const DevProblem &pb, bool with_simplex, bool d_shared, int n_warps);
 
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what);
@@ -43,7 +39,7 @@ int cuda_fail(cudaError_t e, const char *what);
     } while (0)
 
 // ---- launchers (abfit_kernels.cu) ---------------------------------------------------
-int launch_fit_starts(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items,
+int launch_fit_starts(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_warps,
                       const double *simplices, int n_starts, NMParams nm, abfit_fit *all_out,
                       unsigned long long *evals_per_prob, size_t smem_bytes, bool d_in_shared);
 int launch_select(cudaStream_t st, const DevicePools &P, int n_probs, int n_starts, const abfit_fit *all,

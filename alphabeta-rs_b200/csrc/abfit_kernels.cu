@@ -7,85 +7,85 @@
 //   k_model_div    dt1t2 per pair               (src/divergence.rs:33-94)
 //   k_fp64_peak    DFMA roofline micro-benchmark
 //
-// Grid shape: one 32-thread block (= one warp) per work item; an item is a chunk of
-// consecutive starts / replicates of ONE window, so the warp shares the staged
-// pedigree and runs a perfectly uniform objective.  Lanes that finish a fit pull the
-// next start of the chunk (ballot + prefix rank, no atomics), which removes the 2-4x
-// spread in NM iteration counts from the warp's critical path.  Blocks are independent
-// and far more numerous than 148 x resident-warps, so the hardware scheduler balances
-// SMs; FP64 issue (16 lanes/SMSP) saturates with 2 resident warps per SMSP.
+// Grid shape: one block per work item; an item is a chunk of consecutive starts /
+// replicates of ONE window, so all warps of the block share the staged pedigree (D column,
+// per-pair offsets, micro-op program) and every warp runs a perfectly uniform objective on 32
+// different thetas.  Lanes that finish a fit pull the next start of the chunk from a
+// block-wide counter (one shared-memory atomic per warp refill), which takes the 2-4x
+// spread in Nelder-Mead iteration counts off the warp's critical path.  The kernel is bound by
+// FP64 issue latency, so the per-fit on-chip footprint (shared bytes per lane) is what
+// buys throughput: see DESIGN.md for the accounting.
 #include <cstdio>
+#include <cstdlib>
 
 #include "abfit_internal.h"
 
 namespace abfit {
 
 // ---------------------------------------------------------------------------------
-// shared-memory carve-up (one warp per block)
+// shared-memory carve-up
+//   [ per warp: (n_lane + 25) x 32 doubles ] [ D ] [ offs ] [ ops ] [ events ] [ queue ]
 // ---------------------------------------------------------------------------------
-SmemNeed smem_need(int n_pairs, int n_triples, int n_exps, bool with_simplex)
+size_t smem_need(const DevProblem &pb, bool with_simplex, bool d_shared, int n_warps)
 {
-    SmemNeed s;
-    const size_t n_ids = ((size_t)n_pairs + 3) & ~(size_t)3;
-    s.lane_doubles = (size_t)9 * n_exps + n_triples + (with_simplex ? 25 : 0);
-    size_t small = n_ids * 4 + (size_t)n_triples * 4 + (size_t)n_exps;
-    small = (small + 15) & ~(size_t)15;
-    s.without_D = s.lane_doubles * 32 * 8 + small;
-    s.with_D = s.without_D + (((size_t)n_pairs + 1) & ~(size_t)1) * 8;
-    return s;
+    size_t b = (size_t)n_warps * ((size_t)pb.n_lane + (with_simplex ? 25 : 0)) * 32 * 8;
+    if (d_shared) b += (((size_t)pb.n_pairs + 1) & ~(size_t)1) * 8;
+    b += (size_t)pb.n_offs * 4;
+    b += (size_t)pb.n_ops * 8 + (size_t)pb.n_events * 8;
+    b += 16;
+    return (b + 15) & ~(size_t)15;
 }
 
 struct Carved {
     WarpCtx ctx;
     LaneSimplex simplex;
+    int *queue;
 };
 
 template <bool D_SHARED>
-__device__ __forceinline__ Carved carve_and_stage(const DevProblem &pb, const DevicePools &P, int lane,
-                                                  bool with_simplex)
+__device__ __forceinline__ Carved carve_and_stage(const DevProblem &pb, const DevicePools &P, bool with_simplex)
 {
     extern __shared__ double smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, n_warps = nthr >> 5;
+    const int per_warp = (pb.n_lane + (with_simplex ? 25 : 0)) * 32;
     Carved cv;
-    double *p = smem;
-    cv.ctx.pw = p;
-    p += 9 * pb.n_exps * 32;
-    cv.ctx.dt = p;
-    p += pb.n_triples * 32;
+    double *mine = smem + (size_t)warp * per_warp;
+    cv.ctx.lm = mine;
     if (with_simplex) {
-        cv.simplex.X = p + lane;
-        p += 20 * 32;
-        cv.simplex.C = p + lane;
-        p += 5 * 32;
+        cv.simplex.X = mine + pb.n_lane * 32 + lane;
+        cv.simplex.C = cv.simplex.X + 20 * 32;
     } else {
         cv.simplex.X = nullptr;
         cv.simplex.C = nullptr;
     }
+    double *p = smem + (size_t)n_warps * per_warp;  // multiple of 256 bytes
     const double *Dg = P.D + pb.d_off;
     if (D_SHARED) {
-        double *Ds = p;  // 256-byte aligned: the per-lane areas are multiples of 256 bytes
+        double *Ds = p;
         p += (pb.n_pairs + 1) & ~1;
-        for (int i = lane; i < pb.n_pairs; i += 32) Ds[i] = Dg[i];
+        for (int i = tid; i < pb.n_pairs; i += nthr) Ds[i] = Dg[i];
         cv.ctx.D = Ds;
     } else {
         cv.ctx.D = Dg;  // pool offsets are even: 16-byte aligned
     }
-    uint32_t *offs = reinterpret_cast<uint32_t *>(p);  // 16-byte aligned, n_ids is a multiple of 4
-    uint32_t *tris = offs + pb.n_ids;
-    uint8_t *exps = reinterpret_cast<uint8_t *>(tris + pb.n_triples);
-    for (int i = lane; i < pb.n_ids; i += 32) offs[i] = P.offs[pb.ids_off + i];
-    for (int i = lane; i < pb.n_triples; i += 32) tris[i] = P.tris[pb.tri_off + i];
-    for (int i = lane; i < pb.n_exps; i += 32) exps[i] = P.exps[pb.exp_off + i];
+    uint32_t *offs = reinterpret_cast<uint32_t *>(p);  // 16-byte aligned; n_offs is a multiple of 4
+    OpWord *ops = reinterpret_cast<OpWord *>(offs + pb.n_offs);
+    EvWord *evs = reinterpret_cast<EvWord *>(ops + pb.n_ops);
+    cv.queue = reinterpret_cast<int *>(evs + pb.n_events);
+    for (int i = tid; i < pb.n_offs; i += nthr) offs[i] = P.offs[pb.offs_off + i];
+    for (int i = tid; i < pb.n_ops; i += nthr) ops[i] = P.ops[pb.ops_off + i];
+    for (int i = tid; i < pb.n_events; i += nthr) evs[i] = P.events[pb.ev_off + i];
     cv.ctx.offs = offs;
-    cv.ctx.tris = tris;
-    cv.ctx.exps = exps;
+    cv.ctx.ops = ops;
+    cv.ctx.events = evs;
     cv.ctx.n_pairs = pb.n_pairs;
-    cv.ctx.n_triples = pb.n_triples;
-    cv.ctx.n_exps = pb.n_exps;
+    cv.ctx.n_events = pb.n_events;
+    cv.ctx.tmax = pb.tmax;
     cv.ctx.p_uu0 = pb.p_uu0;
     cv.ctx.p_mm0 = pb.p_mm0;
     cv.ctx.eqp = pb.eqp;
     cv.ctx.penw = pb.penw;
-    __syncwarp();
     return cv;
 }
 
@@ -99,45 +99,62 @@ __device__ __forceinline__ void store_fit(abfit_fit *dst, const abfit_fit &r)
     d[3] = make_double2(__hiloint2double(r.evals, r.iters), __hiloint2double(r.start_id, r.status));
 }
 
+__device__ __forceinline__ void lane_nm_reset(LaneNM &L)
+{
+    L.phase = PH_IDLE;
+    L.k = 0; L.ord = 0; L.iters = 0; L.evals = 0; L.status = 0; L.fit_id = -1; L.fr = 0.0;
+    L.xt[0] = L.xt[1] = L.xt[2] = L.xt[3] = 0.0;
+}
+
+// take `count` consecutive fit ids for the idle lanes in mask m; returns this lane's id (or >= end)
+__device__ __forceinline__ int queue_take(int *queue, unsigned m, int lane, int end, bool &drained)
+{
+    int base = end;
+    if (!drained) {
+        if (lane == 0) base = atomicAdd(queue, __popc(m));
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= end) drained = true;  // warp-uniform
+    }
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+
 // ---------------------------------------------------------------------------------
 // multi-start Nelder-Mead
 // ---------------------------------------------------------------------------------
 template <bool D_SHARED>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 k_fit_starts(DevicePools P, const WorkItem *__restrict__ items, const double *__restrict__ simplices,
              int n_starts, NMParams nm, abfit_fit *__restrict__ all_out,
              unsigned long long *__restrict__ evals_per_prob)
 {
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const WorkItem it = items[blockIdx.x];
     const DevProblem pb = P.probs[it.prob];
-    Carved cv = carve_and_stage<D_SHARED>(pb, P, lane, true);
+    Carved cv = carve_and_stage<D_SHARED>(pb, P, true);
+    if (threadIdx.x == 0) *cv.queue = it.first;
+    __syncthreads();
     const WarpCtx &c = cv.ctx;
     const LaneSimplex &S = cv.simplex;
     const DBroadcast Dat{c.D};
 
     LaneNM L;
-    L.phase = PH_IDLE;
-    L.k = 0; L.ord = 0; L.iters = 0; L.evals = 0; L.status = 0; L.fit_id = -1; L.fr = 0.0;
-    L.xt[0] = L.xt[1] = L.xt[2] = L.xt[3] = 0.0;
-    int next = it.first;
+    lane_nm_reset(L);
     const int end = it.first + it.count;
+    bool drained = false;
     unsigned long long my_evals = 0;
 
     for (;;) {
-        // ---- refill idle lanes from the chunk (warp-uniform bookkeeping) ----
+        // ---- refill idle lanes from the block's chunk ----
         const bool need = (L.phase == PH_IDLE);
         const unsigned m = __ballot_sync(FULL, need);
-        if (m && next < end) {
-            const int rank = __popc(m & ((1u << lane) - 1u));
-            const int idx = next + rank;
+        if (m && !drained) {
+            const int idx = queue_take(cv.queue, m, lane, end, drained);
             if (need && idx < end) {
                 const double *sx = simplices + ((size_t)it.prob * n_starts + idx) * 20;
 #pragma unroll
                 for (int q = 0; q < 20; ++q) S.X[q * 32] = sx[q];
                 nm_begin(L, S, idx);
             }
-            next += __popc(m);
         }
         const bool active = (L.phase != PH_IDLE);
         if (!__any_sync(FULL, active)) break;
@@ -168,7 +185,8 @@ k_select(DevicePools P, int n_starts, const abfit_fit *__restrict__ all, abfit_f
     const int lane = threadIdx.x;
     const int p = blockIdx.x;
     const DevProblem pb = P.probs[p];
-    Carved cv = carve_and_stage<D_SHARED>(pb, P, lane, false);
+    Carved cv = carve_and_stage<D_SHARED>(pb, P, false);
+    __syncwarp();
     const WarpCtx &c = cv.ctx;
 
     // src/ab_neutral.rs:83-101: ascending stable sort by LSE, first element wins.
@@ -223,7 +241,7 @@ k_select(DevicePools P, int n_starts, const abfit_fit *__restrict__ all, abfit_f
     model_divergence(c, lane, b.theta[0], b.theta[1], b.theta[2]);
     __syncwarp();
     for (int i = lane; i < c.n_pairs; i += 32) {
-        const double pr = b.theta[3] + c.dt[(c.offs[i] >> 8) * 32 + lane];
+        const double pr = b.theta[3] + c.lm[(c.offs[i] >> 8) * 32 + lane];
         if (pred) pred[pb.pair_off + i] = pr;
         if (resid) resid[pb.pair_off + i] = c.D[i] - pr;
     }
@@ -246,7 +264,8 @@ k_fit_boot(DevicePools P, const WorkItem *__restrict__ items, int n_boot, const 
     const int lane = threadIdx.x;
     const WorkItem it = items[blockIdx.x];
     const DevProblem pb = P.probs[it.prob];
-    Carved cv = carve_and_stage<false>(pb, P, lane, true);
+    Carved cv = carve_and_stage<false>(pb, P, true);
+    __syncwarp();
     const WarpCtx &c = cv.ctx;
     const LaneSimplex &S = cv.simplex;
     double *tile = dstar_scratch + (size_t)blockIdx.x * (size_t)scratch_stride;
@@ -257,9 +276,7 @@ k_fit_boot(DevicePools P, const WorkItem *__restrict__ items, int n_boot, const 
     const abfit_fit bm = best[it.prob];
 
     LaneNM L;
-    L.phase = PH_IDLE;
-    L.k = 0; L.ord = 0; L.iters = 0; L.evals = 0; L.status = 0; L.fit_id = -1; L.fr = 0.0;
-    L.xt[0] = L.xt[1] = L.xt[2] = L.xt[3] = 0.0;
+    lane_nm_reset(L);
     int next = it.first;
     const int end = it.first + it.count;
     unsigned long long my_evals = 0;
@@ -331,7 +348,8 @@ k_cost_batch(DevicePools P, const WorkItem *__restrict__ items, const double *__
     const int lane = threadIdx.x;
     const WorkItem it = items[blockIdx.x];
     const DevProblem pb = P.probs[it.prob];
-    Carved cv = carve_and_stage<D_SHARED>(pb, P, lane, false);
+    Carved cv = carve_and_stage<D_SHARED>(pb, P, false);
+    __syncwarp();
     const DBroadcast Dat{cv.ctx.D};
     if (lane < it.count) {
         const double *th = theta + (size_t)(it.first + lane) * 4;
@@ -347,11 +365,12 @@ k_model_div(DevicePools P, const double *__restrict__ theta4, double *__restrict
 {
     const int lane = threadIdx.x;
     const DevProblem pb = P.probs[0];
-    Carved cv = carve_and_stage<false>(pb, P, lane, false);
+    Carved cv = carve_and_stage<false>(pb, P, false);
+    __syncwarp();
     const WarpCtx &c = cv.ctx;
     model_divergence(c, lane, theta4[0], theta4[1], theta4[2]);
     __syncwarp();
-    for (int i = lane; i < c.n_pairs; i += 32) dt_out[i] = c.dt[(c.offs[i] >> 8) * 32 + lane];
+    for (int i = lane; i < c.n_pairs; i += 32) dt_out[i] = c.lm[(c.offs[i] >> 8) * 32 + lane];
     if (lane == 0 && puu_out) *puu_out = p_uu_est(theta4[0], theta4[1]);
 }
 
@@ -395,19 +414,20 @@ static int prep_kernel(K kernel, size_t smem_bytes)
     return 0;
 }
 
-int launch_fit_starts(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items,
+int launch_fit_starts(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_warps,
                       const double *simplices, int n_starts, NMParams nm, abfit_fit *all_out,
                       unsigned long long *evals_per_prob, size_t smem_bytes, bool d_in_shared)
 {
     if (n_items <= 0) return 0;
+    if (const char *pad = getenv("ABFIT_DEV_SMEM_PAD")) smem_bytes += (size_t)atoi(pad);  // occupancy experiments
     if (d_in_shared) {
         if (int rc = prep_kernel(k_fit_starts<true>, smem_bytes)) return rc;
-        k_fit_starts<true><<<n_items, 32, smem_bytes, st>>>(P, items, simplices, n_starts, nm, all_out,
-                                                           evals_per_prob);
+        k_fit_starts<true><<<n_items, 32 * n_warps, smem_bytes, st>>>(P, items, simplices, n_starts, nm, all_out,
+                                                                      evals_per_prob);
     } else {
         if (int rc = prep_kernel(k_fit_starts<false>, smem_bytes)) return rc;
-        k_fit_starts<false><<<n_items, 32, smem_bytes, st>>>(P, items, simplices, n_starts, nm, all_out,
-                                                            evals_per_prob);
+        k_fit_starts<false><<<n_items, 32 * n_warps, smem_bytes, st>>>(P, items, simplices, n_starts, nm, all_out,
+                                                                       evals_per_prob);
     }
     ABFIT_CUDA(cudaGetLastError());
     return 0;

@@ -1,0 +1,373 @@
+// abfit_model.cuh — device-side ABneutral model and objective.
+//
+// Execution model (B200, sm_100a): one LANE per fit.  A warp works on 32 fits of the
+// same window (different starts / bootstrap replicates), so the heavy part — the
+// objective — is perfectly uniform across the warp: every lane walks the same power
+// chain, the same (t0,t1,t2) triples and the same pedigree rows, on its own theta.
+// The pedigree D column is staged in shared memory and read as a warp broadcast.
+// Nothing in the objective needs a cross-lane exchange, so the FP64 pipe sees 32
+// independent streams per warp and the pair sum can be accumulated SEQUENTIALLY in
+// pedigree order, exactly as the reference does (src/structs.rs:208-213) — results
+// are bit-identical to the CPU restatement instead of "close".
+//
+// Compile with -fmad=false: the only fused operations are the explicit __fma_rn
+// chains of the 3x3 products (the pattern that reproduces the reference's cost KAT).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/abfit.h"
+
+namespace abfit {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------
+// The per-window "program".  divergence() (src/divergence.rs:33-94) recomputes three
+// matrix powers per pair; all of them are members of ONE left-associated chain
+// G, G.G, (G.G).G, ...  The host (compile_problems, abfit_api.cu) turns a pedigree into
+// a list of micro-ops that fire while the kernel walks that chain once per evaluation,
+// so that only the few values that are needed again later occupy per-lane storage:
+//   - G^m            where m is the smaller exponent of some (t1-t0, t2-t0) pair  (9 doubles)
+//   - sv0 . G^t0     for t0 > 0                                                   (3 doubles)
+//   - the three conditional divergences of an exponent pair whose t0 comes later  (3 doubles)
+//   - dt1t2 of every distinct (t0,t1,t2) triple                                   (1 double)
+// Every value is produced by the same operations in the same order as the reference
+// produces it, so the result is bit-identical; only the redundancy is gone.
+// Per-lane storage lives in shared memory as lane_mem[index * 32 + lane].
+// ---------------------------------------------------------------------------------
+enum MicroOp : uint32_t {
+    OP_STORE_M = 1,  // a = dst                     lane_mem[dst..dst+8]  <- R  (= G^k)
+    OP_CALC_S = 2,   // a = dst                     lane_mem[dst..dst+2]  <- sv0^T . R          (src/divergence.rs:55)
+    OP_D = 3,        // a = A source, b = B source  dreg <- conditional divergences of rows UU,UM,MM (:68-87)
+    OP_STORE_D = 4,  // a = dst                     lane_mem[dst..dst+2]  <- dreg
+    OP_LOAD_D = 5,   // a = src                     dreg <- lane_mem[src..src+2]
+    OP_DT = 6        // a = dst, b = s source       lane_mem[dst] <- s0*d_uu + s1*d_um + s2*d_mm (:89)
+};
+// operand sources (16 bit); anything below SRC_SPECIAL is a lane_mem index
+constexpr uint32_t SRC_SPECIAL = 0xfff0;
+constexpr uint32_t SRC_CUR = 0xfff0;    // the chain's current power R = G^k
+constexpr uint32_t SRC_G = 0xfff1;      // G itself (exponent 1), always in registers
+constexpr uint32_t SRC_IDENT = 0xfff2;  // G^0 (src/divergence.rs:21-24)
+constexpr uint32_t SRC_SV0 = 0xfff3;    // sv0^T . G^0
+// op word: opcode | a << 8 (16 bit) ; second word: b (16 bit)
+struct OpWord {
+    uint32_t x, y;
+};
+// event: x = k | n_ops << 8, y = first_op   (k ascending; k == 0 fires before the chain)
+struct EvWord {
+    uint32_t x, y;
+};
+
+struct DevProblem {
+    int64_t d_off;     // into the D pool (even: 16-byte aligned)
+    int64_t pair_off;  // into pred / resid (problems concatenated without padding)
+    int64_t offs_off;  // into the pair-offset pool: u32 = 256 * lane_mem index of the pair's dt1t2
+    int64_t ops_off;   // into the micro-op pool
+    int64_t ev_off;    // into the event pool
+    int32_t n_pairs, n_offs;  // n_offs = n_pairs rounded up to 4
+    int32_t n_ops, n_events;
+    int32_t n_lane;   // doubles of per-lane model storage
+    int32_t tmax;     // last exponent the chain has to reach
+    double p_uu0, p_mm0;  // state at G0 (p0um = 0), src/ab_neutral.rs:23-24
+    double eqp, penw;     // penw = eqp_weight * (double)n_pairs, src/structs.rs:210-211
+};
+
+// per-warp view of the staged problem
+struct WarpCtx {
+    const double *D;       // [n_pairs] shared (or global for very long pedigrees), 16-byte aligned
+    const uint32_t *offs;  // shared, 16-byte aligned
+    const OpWord *ops;     // shared
+    const EvWord *events;  // shared
+    double *lm;            // this warp's lane_mem (lane NOT folded in)
+    int32_t n_pairs, n_events, tmax;
+    double p_uu0, p_mm0, eqp, penw;
+};
+
+// src/divergence.rs:96-114 (powi(2) == x*x)
+__device__ __forceinline__ void genmatrix(double a, double b, double G[9])
+{
+    double oma = 1.0 - a, omb = 1.0 - b;
+    double b1a = b + 1.0 - a;
+    double a1b = a + 1.0 - b;
+    G[0] = oma * oma;
+    G[1] = 2.0 * oma * a;
+    G[2] = a * a;
+    G[3] = 0.25 * (b1a * b1a);
+    G[4] = 0.5 * b1a * a1b;
+    G[5] = 0.25 * (a1b * a1b);
+    G[6] = b * b;
+    G[7] = 2.0 * omb * b;
+    G[8] = omb * omb;
+}
+
+// one step of matrix_power's chain R <- R.G (src/divergence.rs:27-29); FMA chain over k ascending
+__device__ __forceinline__ void mat3_step(double R[9], const double G[9])
+{
+    double n[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double acc = R[3 * i] * G[j];
+            acc = __fma_rn(R[3 * i + 1], G[3 + j], acc);
+            acc = __fma_rn(R[3 * i + 2], G[6 + j], acc);
+            n[3 * i + j] = acc;
+        }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = n[i];
+}
+
+// src/alphabeta.rs:62-65
+__device__ __forceinline__ double p_uu_est(double a, double b)
+{
+    double omb = 1.0 - b, oma = 1.0 - a, s = a + b, sm1 = s - 1.0;
+    return (b * (omb * omb - oma * oma - 1.0)) / (s * (sm1 * sm1 - 2.0));
+}
+// src/structs.rs:146-149
+__device__ __forceinline__ double p_mm_est(double a, double b)
+{
+    double omb = 1.0 - b, oma = 1.0 - a, s = a + b, sm1 = s - 1.0;
+    return (a * (oma * oma - omb * omb - 1.0)) / (s * (sm1 * sm1 - 2.0));
+}
+// src/structs.rs:151-154
+__device__ __forceinline__ double p_um_est(double a, double b)
+{
+    double s = a + b, sm1 = s - 1.0;
+    return (4.0 * a * b * (s - 2.0)) / (s * (sm1 * sm1 - 2.0));
+}
+
+// src/divergence.rs:68-87
+__device__ __forceinline__ double cond_div(const double *a, const double *b)
+{
+    return 0.5 * (a[0] * b[1] + a[1] * b[0] + a[1] * b[2] + a[2] * b[1]) + (a[0] * b[2] + a[2] * b[0]);
+}
+
+// sv^T . M with the same FMA chain as the 3x3 products
+__device__ __forceinline__ void vec_mat(double v0, double v1, double v2, const double M[9], double s[3])
+{
+    s[0] = __fma_rn(v2, M[6], __fma_rn(v1, M[3], v0 * M[0]));
+    s[1] = __fma_rn(v2, M[7], __fma_rn(v1, M[4], v0 * M[1]));
+    s[2] = __fma_rn(v2, M[8], __fma_rn(v1, M[5], v0 * M[2]));
+}
+
+__device__ __forceinline__ void fetch_matrix(uint32_t src, const double *lml, const double R[9], const double G[9],
+                                             double M[9])
+{
+    if (src == SRC_CUR) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) M[e] = R[e];
+    } else if (src == SRC_G) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) M[e] = G[e];
+    } else if (src == SRC_IDENT) {
+        M[0] = 1.0; M[1] = 0.0; M[2] = 0.0;
+        M[3] = 0.0; M[4] = 1.0; M[5] = 0.0;
+        M[6] = 0.0; M[7] = 0.0; M[8] = 1.0;
+    } else {
+        const double *p = lml + src * 32;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) M[e] = p[e * 32];
+    }
+}
+
+// run the micro-ops of one event with R = G^k (all control flow here is warp-uniform)
+__device__ __forceinline__ void run_ops(const WarpCtx &c, double *lml, int first, int n, const double R[9],
+                                        const double G[9], const double sid[3], double sv0, double sv1, double sv2,
+                                        double dreg[3])
+{
+    for (int i = first; i < first + n; ++i) {
+        const OpWord w = c.ops[i];
+        const uint32_t op = w.x & 0xff, a = w.x >> 8, b = w.y;
+        switch (op) {
+            case OP_STORE_M: {
+                double *p = lml + a * 32;
+#pragma unroll
+                for (int e = 0; e < 9; ++e) p[e * 32] = R[e];
+                break;
+            }
+            case OP_CALC_S: {
+                double s[3];
+                vec_mat(sv0, sv1, sv2, R, s);
+                double *p = lml + a * 32;
+                p[0] = s[0]; p[32] = s[1]; p[64] = s[2];
+                break;
+            }
+            case OP_D: {
+                double A[9], B[9];
+                fetch_matrix(a, lml, R, G, A);
+                if (b == a) {
+#pragma unroll
+                    for (int e = 0; e < 9; ++e) B[e] = A[e];
+                } else {
+                    fetch_matrix(b, lml, R, G, B);
+                }
+                dreg[2] = cond_div(A + 6, B + 6);  // MM, UM, UU in the reference's order (:68-87)
+                dreg[1] = cond_div(A + 3, B + 3);
+                dreg[0] = cond_div(A, B);
+                break;
+            }
+            case OP_STORE_D: {
+                double *p = lml + a * 32;
+                p[0] = dreg[0]; p[32] = dreg[1]; p[64] = dreg[2];
+                break;
+            }
+            case OP_LOAD_D: {
+                const double *p = lml + a * 32;
+                dreg[0] = p[0]; dreg[1] = p[32]; dreg[2] = p[64];
+                break;
+            }
+            case OP_DT: {
+                double s0, s1, s2;
+                if (b == SRC_SV0) {
+                    s0 = sid[0]; s1 = sid[1]; s2 = sid[2];
+                } else {
+                    const double *p = lml + b * 32;
+                    s0 = p[0]; s1 = p[32]; s2 = p[64];
+                }
+                lml[a * 32] = s0 * dreg[0] + s1 * dreg[1] + s2 * dreg[2];  // src/divergence.rs:89
+                break;
+            }
+            default: break;
+        }
+    }
+}
+
+// Power chain + per-triple theoretical divergence (src/divergence.rs:44-90).
+__device__ __forceinline__ void model_divergence(const WarpCtx &c, int lane, double alpha, double beta,
+                                                 double weight)
+{
+    double *lml = c.lm + lane;
+    double G[9], R[9], dreg[3] = {0.0, 0.0, 0.0};
+    genmatrix(alpha, beta, G);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = G[i];
+    // sv_gzero (src/divergence.rs:44) and its product with G^0
+    const double sv0 = c.p_uu0, sv1 = weight * c.p_mm0, sv2 = (1.0 - weight) * c.p_mm0;
+    double sid[3];
+    {
+        const double I[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};
+        vec_mat(sv0, sv1, sv2, I, sid);
+    }
+    const EvWord none = {0xffu, 0u};
+    int ei = 0;
+    EvWord ev = c.n_events > 0 ? c.events[0] : none;
+    if ((ev.x & 0xff) == 0) {  // exponent-0-only triples (t0 = t1 = t2)
+        run_ops(c, lml, (int)ev.y, (int)(ev.x >> 8), R, G, sid, sv0, sv1, sv2, dreg);
+        ++ei;
+        ev = ei < c.n_events ? c.events[ei] : none;
+    }
+    for (int k = 1; k <= c.tmax; ++k) {
+        if (k > 1) mat3_step(R, G);
+        if ((int)(ev.x & 0xff) == k) {  // warp-uniform
+            run_ops(c, lml, (int)ev.y, (int)(ev.x >> 8), R, G, sid, sv0, sv1, sv2, dreg);
+            ++ei;
+            ev = ei < c.n_events ? c.events[ei] : none;
+        }
+    }
+}
+
+// D access: broadcast (every lane fits the same observed column, staged in shared memory and
+// read four pairs at a time) or a per-lane column (bootstrap replicates: D*[i] at col[i*32],
+// lane already folded into the pointer; coalesced across the warp).
+struct DBroadcast {
+    const double *D;  // 16-byte aligned
+    __device__ __forceinline__ void load4(int i, double d[4]) const
+    {
+        const double2 a = *reinterpret_cast<const double2 *>(D + i);
+        const double2 b = *reinterpret_cast<const double2 *>(D + i + 2);
+        d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
+    }
+    __device__ __forceinline__ double operator()(int i) const { return D[i]; }
+};
+struct DLaneColumn {
+    const double *col;
+    __device__ __forceinline__ void load4(int i, double d[4]) const
+    {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[q] = __ldcg(col + (size_t)(i + q) * 32);
+    }
+    __device__ __forceinline__ double operator()(int i) const { return __ldcg(col + (size_t)i * 32); }
+};
+
+// Objective (src/structs.rs:191-217).  penalty=false gives the penalty-free LSE of
+// src/ab_neutral.rs:88-93 (r*r + 0.0 == r*r, so one loop serves both).
+//
+// The pair sum is the reference's: sequential, in pedigree order.  Only the accumulate
+// (one DADD per pair) is a dependent chain; the loop is software-pipelined over groups of
+// four pairs (load -> residual/square -> accumulate) so the next groups' loads and
+// arithmetic issue under the chain latency.
+template <class DAcc>
+__device__ __forceinline__ double objective(const WarpCtx &c, const DAcc &Dat, int lane, double alpha,
+                                            double beta, double weight, double icpt, bool penalty)
+{
+    model_divergence(c, lane, alpha, beta, weight);
+    double pen = 0.0;
+    if (penalty) {
+        const double dq = p_uu_est(alpha, beta) - c.eqp;
+        pen = c.penw * (dq * dq);
+    }
+    // byte base of this lane's storage; c.offs[i] = 256 * (lane_mem index of the pair's dt1t2)
+    const char *dtb = reinterpret_cast<const char *>(c.lm + lane);
+    const int ng = c.n_pairs >> 2;
+    double sum = 0.0;
+    double t[4] = {0.0, 0.0, 0.0, 0.0};  // terms of the previous group (adding +0.0 first is exact)
+
+    struct Grp {
+        double d[4], raw[4];
+        uint32_t off[4];
+    };
+    // stage 1: loads of one group of four pairs.  The first dt of a group is always fetched, the
+    // others only where the (warp-uniform) triple changes inside the group.
+    auto load = [&](int g, Grp &G) {
+        Dat.load4(4 * g, G.d);
+        const uint4 o = *reinterpret_cast<const uint4 *>(c.offs + 4 * g);
+        G.off[0] = o.x; G.off[1] = o.y; G.off[2] = o.z; G.off[3] = o.w;
+        G.raw[0] = *reinterpret_cast<const double *>(dtb + o.x);
+#pragma unroll
+        for (int q = 1; q < 4; ++q)
+            G.raw[q] = (G.off[q] != G.off[q - 1]) ? *reinterpret_cast<const double *>(dtb + G.off[q]) : 0.0;
+    };
+    // stage 2 + 3: residuals / squares of group G, then the sequential accumulate of the previous one
+    auto step = [&](const Grp &G) {
+        double v[4], n[4];
+        v[0] = G.raw[0];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) v[q] = (G.off[q] != G.off[q - 1]) ? G.raw[q] : v[q - 1];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double res = G.d[q] - icpt - v[q];
+            n[q] = res * res + pen;
+        }
+        sum += t[0];
+        sum += t[1];
+        sum += t[2];
+        sum += t[3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) t[q] = n[q];
+    };
+
+    if (ng > 0) {
+        Grp A, B;
+        load(0, A);
+        int g = 0;
+        for (; g + 1 < ng; g += 2) {
+            load(g + 1, B);
+            step(A);
+            load(min(g + 2, ng - 1), A);
+            step(B);
+        }
+        if (g < ng) step(A);
+        sum += t[0];
+        sum += t[1];
+        sum += t[2];
+        sum += t[3];
+    }
+    for (int i = 4 * ng; i < c.n_pairs; ++i) {
+        const double res = Dat(i) - icpt - *reinterpret_cast<const double *>(dtb + c.offs[i]);
+        sum += res * res + pen;
+    }
+    return sum;
+}
+
+}  // namespace abfit

@@ -1,0 +1,295 @@
+// abfit_nm.cuh — Nelder-Mead (argmin 0.8.1 semantics) as a per-lane state machine.
+#pragma once
+#include "abfit_model.cuh"
+
+namespace abfit {
+
+// ---------------------------------------------------------------------------------
+// Nelder-Mead, argmin 0.8.1 semantics (call sites src/ab_neutral.rs:49-64 and
+// src/boot_model.rs:69-84), as a per-lane state machine: every trip of the warp loop
+// evaluates exactly one trial point per active lane, so lanes in different NM phases
+// (reflect / expand / contract / ...) still share the objective's instruction stream.
+// ---------------------------------------------------------------------------------
+enum Phase : int {
+    PH_IDLE = 0,  // needs a new fit
+    PH_INIT,      // evaluating initial vertex k
+    PH_REFLECT,
+    PH_EXPAND,
+    PH_CONTRACT,
+    PH_SHRINK,  // evaluating shrunk vertex k (sorted position)
+    PH_LSE      // final penalty-free evaluation of the best vertex
+};
+
+struct LaneNM {
+    double xt[4];  // trial point of the current evaluation
+    double fr;     // reflection cost kept across the expansion evaluation
+    int phase, k;
+    uint32_t ord;  // 5 x 3 bits: physical slot of the sorted vertex at position p
+    int iters, evals, status;
+    int fit_id;
+};
+
+// per-lane simplex storage in shared memory: X[(slot*4+j)*32 + lane], C[slot*32 + lane]
+struct LaneSimplex {
+    double *X;
+    double *C;
+    __device__ __forceinline__ double &x(int slot, int j) const { return X[(slot * 4 + j) * 32]; }
+    __device__ __forceinline__ double &c(int slot) const { return C[slot * 32]; }
+};
+
+__device__ __forceinline__ int ord_at(uint32_t ord, int p) { return (ord >> (3 * p)) & 7; }
+
+// stable insertion sort of the five vertices by cost (sort_by(partial_cmp().unwrap_or(Equal)))
+// written as a fixed compare-exchange sequence; with strict '<' it performs exactly the
+// swaps the insertion sort would, NaNs included.
+__device__ __forceinline__ uint32_t sort5(const LaneSimplex &S, uint32_t ord)
+{
+    double c[5];
+    int o[5];
+#pragma unroll
+    for (int p = 0; p < 5; ++p) {
+        o[p] = ord_at(ord, p);
+        c[p] = S.c(o[p]);
+    }
+#pragma unroll
+    for (int i = 1; i < 5; ++i)
+#pragma unroll
+        for (int j = i; j >= 1; --j) {
+            const bool sw = c[j] < c[j - 1];
+            const double tc = sw ? c[j - 1] : c[j];
+            c[j - 1] = sw ? c[j] : c[j - 1];
+            c[j] = tc;
+            const int to = sw ? o[j - 1] : o[j];
+            o[j - 1] = sw ? o[j] : o[j - 1];
+            o[j] = to;
+        }
+    uint32_t r = 0;
+#pragma unroll
+    for (int p = 0; p < 5; ++p) r |= (uint32_t)o[p] << (3 * p);
+    return r;
+}
+
+// x0 = (x[0]+x[1]+x[2]+x[3]) * (1/4)   (NelderMead::calculate_centroid)
+__device__ __forceinline__ void centroid(const LaneSimplex &S, uint32_t ord, double x0[4])
+{
+    const int a = ord_at(ord, 0), b = ord_at(ord, 1), c = ord_at(ord, 2), d = ord_at(ord, 3);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        double v = S.x(a, j);
+        v = v + S.x(b, j);
+        v = v + S.x(c, j);
+        v = v + S.x(d, j);
+        x0[j] = v * (1.0 / 4.0);
+    }
+}
+
+// xr = x0 + (x0 - x[4]) * alpha, alpha = 1   (NelderMead::reflect)
+__device__ __forceinline__ void reflect_point(const LaneSimplex &S, uint32_t ord, double xr[4])
+{
+    double x0[4];
+    centroid(S, ord, x0);
+    const int w = ord_at(ord, 4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xr[j] = x0[j] + (x0[j] - S.x(w, j)) * 1.0;
+}
+
+// shrink point for sorted position k: x[0] + (x[k] - x[0]) * sigma, sigma = 0.5
+__device__ __forceinline__ void shrink_point(const LaneSimplex &S, uint32_t ord, int k, double xs[4])
+{
+    const int b = ord_at(ord, 0), s = ord_at(ord, k);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xs[j] = S.x(b, j) + (S.x(s, j) - S.x(b, j)) * 0.5;
+}
+
+struct NMParams {
+    int max_iters;
+    double sd_tol;
+    uint32_t flags;
+};
+
+// Consume the objective value f of the lane's current trial point and advance the
+// state machine to the next trial point.  Returns true when the fit has finished
+// (lane.phase == PH_IDLE, result in `res`).
+__device__ __forceinline__ bool nm_advance(LaneNM &L, const LaneSimplex &S, const NMParams &P, double f,
+                                           abfit_fit &res)
+{
+    bool iter_done = false;   // an NM iteration (or init) completed: sort + termination test follow
+    bool finish = false;      // go to the final LSE evaluation
+    switch (L.phase) {
+        case PH_INIT: {
+            // NOTE: written as "load vertex k+1 relative to k, then bump k" on purpose.  ptxas 12.9 folds
+            // `++k; load x[k]` into an LDS with the +1 in the immediate offset AND reads the already
+            // incremented register (off-by-one vertex; caught by the bit-exact parity tests).
+            const int k = L.k;
+            S.c(k) = f;
+            ++L.evals;
+            L.k = k + 1;
+            if (k < 4) {
+                const double *nx = S.X + k * 128;  // vertex k; the next one is 128 doubles further
+                L.xt[0] = nx[128];
+                L.xt[1] = nx[160];
+                L.xt[2] = nx[192];
+                L.xt[3] = nx[224];
+            } else {
+                iter_done = true;  // sort + termination test of the Executor's first loop pass
+                L.iters = -1;      // the shared tail below counts an iteration; init is not one
+            }
+            break;
+        }
+        case PH_REFLECT: {
+            ++L.evals;
+            const double c0 = S.c(ord_at(L.ord, 0)), c3 = S.c(ord_at(L.ord, 3));
+            if (f < c3 && f >= c0) {  // Action::Reflection
+                const int w = ord_at(L.ord, 4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) S.x(w, j) = L.xt[j];
+                S.c(w) = f;
+                iter_done = true;
+            } else if (f < c0) {  // Action::Expansion: xe = x0 + (xr - x0) * 2
+                double x0[4];
+                centroid(S, L.ord, x0);
+                L.fr = f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) L.xt[j] = x0[j] + (L.xt[j] - x0[j]) * 2.0;
+                L.phase = PH_EXPAND;
+            } else if (f >= c3) {  // Action::ContractionInside: xc = x0 + (x[4] - x0) * 0.5
+                double x0[4];
+                centroid(S, L.ord, x0);
+                const int w = ord_at(L.ord, 4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) L.xt[j] = x0[j] + (S.x(w, j) - x0[j]) * 0.5;
+                L.phase = PH_CONTRACT;
+            } else {  // NaN reflection cost: Action::Shrink
+                L.k = 1;
+                shrink_point(S, L.ord, 1, L.xt);
+                L.phase = PH_SHRINK;
+            }
+            break;
+        }
+        case PH_EXPAND: {
+            ++L.evals;
+            const int w = ord_at(L.ord, 4);
+            if (f < L.fr) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) S.x(w, j) = L.xt[j];
+                S.c(w) = f;
+            } else {  // keep the reflection point (recomputed from the untouched simplex: same bits)
+                double xr[4];
+                reflect_point(S, L.ord, xr);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) S.x(w, j) = xr[j];
+                S.c(w) = L.fr;
+            }
+            iter_done = true;
+            break;
+        }
+        case PH_CONTRACT: {
+            ++L.evals;
+            const int w = ord_at(L.ord, 4);
+            if (f < S.c(w)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) S.x(w, j) = L.xt[j];
+                S.c(w) = f;
+                iter_done = true;
+            } else if (P.flags & ABFIT_SHRINK_ON_FAILED_CONTRACTION) {
+                L.k = 1;
+                shrink_point(S, L.ord, 1, L.xt);
+                L.phase = PH_SHRINK;
+            } else if (P.flags & ABFIT_NO_EARLY_EXIT_ON_STALL) {
+                iter_done = true;  // argmin 0.8.1: nothing replaced, iteration counted
+            } else {
+                // Simplex unchanged and next_iter is a pure function of it: all remaining
+                // iterations repeat this one.  Same best vertex as after max_iters.
+                L.iters = P.max_iters;
+                L.status = ABFIT_TERM_STALLED;
+                finish = true;
+            }
+            break;
+        }
+        case PH_SHRINK: {
+            ++L.evals;
+            const int k = L.k;
+            const int s = ord_at(L.ord, k);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) S.x(s, j) = L.xt[j];
+            S.c(s) = f;
+            L.k = k + 1;
+            if (k < 4) {
+                shrink_point(S, L.ord, k + 1, L.xt);
+            } else {
+                iter_done = true;
+            }
+            break;
+        }
+        case PH_LSE: {
+            const int b = ord_at(L.ord, 0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res.theta[j] = S.x(b, j);
+            res.cost = S.c(b);
+            res.lse = f;
+            res.iters = L.iters;
+            res.evals = L.evals;
+            // IterState::update never accepts a NaN cost: best_param stays None and the
+            // reference panics on unwrap (src/ab_neutral.rs:66)
+            res.status = (res.cost != res.cost) ? ABFIT_FIT_NAN : L.status;
+            res.start_id = L.fit_id;
+            L.phase = PH_IDLE;
+            return true;
+        }
+        default: break;
+    }
+
+    if (iter_done) {
+        L.ord = sort5(S, L.ord);  // sort_param_vecs (stable)
+        ++L.iters;
+        // Executor: terminate_internal at the top of the next iteration
+        double c[5];
+#pragma unroll
+        for (int p = 0; p < 5; ++p) c[p] = S.c(ord_at(L.ord, p));
+        double sum = 0.0;
+#pragma unroll
+        for (int p = 0; p < 5; ++p) sum += c[p];
+        const double c0 = sum / 5.0;
+        double ss = 0.0;
+#pragma unroll
+        for (int p = 0; p < 5; ++p) {
+            const double d = c[p] - c0;
+            ss += d * d;
+        }
+        const double sd = sqrt(1.0 / (5.0 - 1.0) * ss);
+        if (sd < P.sd_tol) {
+            L.status = ABFIT_TERM_SD;
+            finish = true;
+        } else if (L.iters >= P.max_iters) {
+            L.status = ABFIT_TERM_MAX_ITERS;
+            finish = true;
+        } else {
+            reflect_point(S, L.ord, L.xt);
+            L.phase = PH_REFLECT;
+        }
+    }
+    if (finish) {
+        const int b = ord_at(L.ord, 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) L.xt[j] = S.x(b, j);
+        L.phase = PH_LSE;
+    }
+    return false;
+}
+
+// start a new fit on this lane from a 5x4 simplex in global memory
+__device__ __forceinline__ void nm_begin(LaneNM &L, const LaneSimplex &S, int fit_id)
+{
+    L.phase = PH_INIT;
+    L.k = 0;
+    L.ord = 0u | (1u << 3) | (2u << 6) | (3u << 9) | (4u << 12);
+    L.iters = 0;
+    L.evals = 0;
+    L.status = 0;
+    L.fit_id = fit_id;
+    L.fr = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) L.xt[j] = S.x(0, j);
+}
+
+}  // namespace abfit

@@ -1,0 +1,261 @@
+// abfit_plan.cu — pedigree -> micro-op program (host).  O(pairs) bookkeeping; no numerics.
+#include <map>
+#include <set>
+#include <tuple>
+
+#include "abfit_plan.h"
+
+namespace abfit {
+
+// `x as i8` in Rust (saturating, NaN -> 0), src/divergence.rs:52
+static inline int as_i8(double x)
+{
+    if (x != x) return 0;
+    if (x >= 127.0) return 127;
+    if (x <= -128.0) return -128;
+    return (int)x;
+}
+
+static inline OpWord mk_op(uint32_t op, uint32_t a, uint32_t b = 0)
+{
+    OpWord w;
+    w.x = op | (a << 8);
+    w.y = b;
+    return w;
+}
+
+int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
+{
+    hp.clear();
+    if (!probs || n_probs <= 0) {
+        set_error("no problems");
+        return ABFIT_ERR_ARG;
+    }
+    hp.probs.resize(n_probs);
+    hp.flops.resize(n_probs);
+    hp.tmax.resize(n_probs);
+    hp.n_triples.resize(n_probs);
+    hp.d_has_nan.assign(n_probs, 0);
+    typedef std::tuple<int, int, int> Tri;  // (t0, a = t1 - t0, b = t2 - t0)
+    typedef std::pair<int, int> AB;
+    for (int p = 0; p < n_probs; ++p) {
+        const abfit_problem &ap = probs[p];
+        if (!ap.pedigree || ap.n_pairs <= 0) {
+            set_error("problem " + std::to_string(p) + ": empty pedigree");
+            return ABFIT_ERR_ARG;
+        }
+        DevProblem dp;
+        if (hp.D.size() & 1) hp.D.push_back(0.0);
+        dp.d_off = (int64_t)hp.D.size();
+        dp.pair_off = hp.total_pairs;
+        hp.total_pairs += ap.n_pairs;
+        dp.offs_off = (int64_t)hp.offs.size();
+        dp.ops_off = (int64_t)hp.ops.size();
+        dp.ev_off = (int64_t)hp.events.size();
+        dp.n_pairs = ap.n_pairs;
+        dp.p_uu0 = ap.p0uu;
+        dp.p_mm0 = 1.0 - ap.p0uu;               // src/ab_neutral.rs:23
+        if (dp.p_mm0 + dp.p_uu0 + 0.0 != 1.0) {  // src/ab_neutral.rs:31 assert_eq!
+            set_error("problem " + std::to_string(p) + ": p0mm + p0uu + p0um != 1");
+            return ABFIT_ERR_NAN;
+        }
+        dp.eqp = ap.eqp;
+        dp.penw = ap.eqp_weight * (double)ap.n_pairs;  // src/structs.rs:210-211
+
+        // ---- distinct triples --------------------------------------------------------------
+        std::vector<Tri> key(ap.n_pairs);
+        std::map<Tri, int> tri_id;
+        int max_exp = 0;
+        for (int i = 0; i < ap.n_pairs; ++i) {
+            const double *row = ap.pedigree + 4 * (size_t)i;
+            const int t0 = as_i8(row[0]), t1 = as_i8(row[1]), t2 = as_i8(row[2]);
+            if (t0 < 0 || t1 < t0 || t2 < t0) {
+                set_error("problem " + std::to_string(p) + " row " + std::to_string(i) +
+                          ": needs 0 <= t0 <= t1,t2 <= 127 (the reference would invert the matrix)");
+                return ABFIT_ERR_TIME;
+            }
+            key[i] = Tri(t0, t1 - t0, t2 - t0);
+            tri_id.emplace(key[i], 0);
+            max_exp = std::max(max_exp, std::max(t0, std::max(t1 - t0, t2 - t0)));
+            if (row[3] != row[3]) hp.d_has_nan[p] = 1;
+            hp.D.push_back(row[3]);
+        }
+        int U = 0;
+        for (auto &kv : tri_id) kv.second = U++;
+
+        // ---- storage layout: [G^m matrices][s vectors][deferred d vectors][dt per triple] ----
+        std::map<AB, std::vector<Tri>> by_ab;
+        std::set<int> Mset, T0set;
+        for (auto &kv : tri_id) {
+            const int t0 = std::get<0>(kv.first), a = std::get<1>(kv.first), b = std::get<2>(kv.first);
+            by_ab[AB(a, b)].push_back(kv.first);
+            if (a != b && std::min(a, b) >= 2) Mset.insert(std::min(a, b));
+            if (t0 >= 1) T0set.insert(t0);
+        }
+        std::map<int, uint32_t> idx_M, idx_S;
+        std::map<AB, uint32_t> idx_D;
+        uint32_t n_lane = 0;
+        for (int m : Mset) {
+            idx_M[m] = n_lane;
+            n_lane += 9;
+        }
+        for (int t : T0set) {
+            idx_S[t] = n_lane;
+            n_lane += 3;
+        }
+        for (auto &kv : by_ab) {
+            const int k = std::max(kv.first.first, kv.first.second);
+            bool deferred = false;
+            for (auto &t : kv.second) deferred |= std::get<0>(t) > k;
+            if (deferred) {
+                idx_D[kv.first] = n_lane;
+                n_lane += 3;
+            }
+        }
+        const uint32_t dt_base = n_lane;
+        n_lane += (uint32_t)U;
+        if (n_lane >= SRC_SPECIAL) {
+            set_error("problem " + std::to_string(p) + ": too many distinct (t0,t1,t2) triples");
+            return ABFIT_ERR_TOO_LARGE;
+        }
+
+        // ---- micro-ops per chain exponent ------------------------------------------------------
+        struct Ev {
+            std::vector<OpWord> head, body, tail;  // [STORE_M, CALC_S] [per exponent pair] [deferred triples]
+        };
+        std::map<int, Ev> evs;
+        for (int m : Mset) evs[m].head.push_back(mk_op(OP_STORE_M, idx_M[m]));
+        for (int t : T0set) evs[t].head.push_back(mk_op(OP_CALC_S, idx_S[t]));
+        auto src_of = [&](int e, int k) -> uint32_t {
+            if (e == k) return e == 0 ? SRC_IDENT : SRC_CUR;
+            if (e == 0) return SRC_IDENT;
+            if (e == 1) return SRC_G;
+            return idx_M[e];
+        };
+        for (auto &kv : by_ab) {
+            const int a = kv.first.first, b = kv.first.second, k = std::max(a, b);
+            Ev &ev = evs[k];
+            ev.body.push_back(mk_op(OP_D, src_of(a, k), src_of(b, k)));
+            for (auto &t : kv.second) {
+                const int t0 = std::get<0>(t);
+                const uint32_t dst = dt_base + (uint32_t)tri_id[t];
+                if (t0 == 0)
+                    ev.body.push_back(mk_op(OP_DT, dst, SRC_SV0));
+                else if (t0 <= k)
+                    ev.body.push_back(mk_op(OP_DT, dst, idx_S[t0]));
+            }
+            if (idx_D.count(kv.first)) ev.body.push_back(mk_op(OP_STORE_D, idx_D[kv.first]));
+        }
+        for (auto &kv : by_ab) {  // triples whose t0 comes after their exponent pair
+            const int k = std::max(kv.first.first, kv.first.second);
+            std::map<int, std::vector<Tri>> late;
+            for (auto &t : kv.second)
+                if (std::get<0>(t) > k) late[std::get<0>(t)].push_back(t);
+            for (auto &lv : late) {
+                Ev &ev = evs[lv.first];
+                ev.tail.push_back(mk_op(OP_LOAD_D, idx_D[kv.first]));
+                for (auto &t : lv.second)
+                    ev.tail.push_back(mk_op(OP_DT, dt_base + (uint32_t)tri_id[t], idx_S[lv.first]));
+            }
+        }
+        int tmax = 0;
+        for (auto &kv : evs) {
+            EvWord w;
+            const size_t first = hp.ops.size() - (size_t)dp.ops_off;
+            for (auto &o : kv.second.head) hp.ops.push_back(o);
+            for (auto &o : kv.second.body) hp.ops.push_back(o);
+            for (auto &o : kv.second.tail) hp.ops.push_back(o);
+            const size_t n = hp.ops.size() - (size_t)dp.ops_off - first;
+            w.x = (uint32_t)kv.first | ((uint32_t)n << 8);
+            w.y = (uint32_t)first;
+            hp.events.push_back(w);
+            tmax = std::max(tmax, kv.first);
+        }
+        dp.n_ops = (int32_t)(hp.ops.size() - (size_t)dp.ops_off);
+        dp.n_events = (int32_t)(hp.events.size() - (size_t)dp.ev_off);
+        dp.n_lane = (int32_t)n_lane;
+        dp.tmax = tmax;
+
+        for (int i = 0; i < ap.n_pairs; ++i) hp.offs.push_back(256u * (dt_base + (uint32_t)tri_id[key[i]]));
+        while (hp.offs.size() & 3) hp.offs.push_back(256u * dt_base);
+        dp.n_offs = (int32_t)(hp.offs.size() - (size_t)dp.offs_off);
+
+        hp.probs[p] = dp;
+        hp.tmax[p] = max_exp;
+        hp.n_triples[p] = U;
+        hp.flops[p] = 45.0 * (max_exp > 1 ? max_exp - 1 : 0) + 56.0 * U + 5.0 * ap.n_pairs + 40.0;
+        hp.max_pairs = std::max(hp.max_pairs, ap.n_pairs);
+    }
+    return 0;
+}
+
+int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm, int fits_per_prob, LaunchShape &out)
+{
+    auto worst = [&](bool simplex, bool d_shared, int nw) {
+        size_t m = 0;
+        for (auto &pb : hp.probs) m = std::max(m, smem_need(pb, simplex, d_shared, nw));
+        return m;
+    };
+    // multi-start kernel: as many resident warps as shared memory allows (the register file allows 16)
+    int best_w = -1;
+    const int cand_nw[3] = {4, 2, 1};
+    for (int pass = 0; pass < 2; ++pass) {  // pass 0: D in shared memory; pass 1: D broadcast from L1/L2
+        for (int nw : cand_nw) {
+            if (nw > 1 && fits_per_prob < 64 * nw) continue;  // too few fits for a multi-warp block
+            const size_t s = worst(true, pass == 0, nw);
+            if (s > smem_cap) continue;
+            int w = (int)std::min<size_t>(16, (smem_per_sm / (s + 1024)) * (size_t)nw);
+            if (w > best_w) {
+                best_w = w;
+                out.n_warps = nw;
+                out.d_shared = pass == 0;
+                out.smem_fit = s;
+            }
+        }
+        if (best_w >= 4) break;  // only give up the shared D column when occupancy would collapse
+    }
+    if (best_w <= 0) {
+        set_error("per-lane model state of one pedigree needs " + std::to_string(worst(true, false, 1)) +
+                  " B of shared memory (limit " + std::to_string(smem_cap) + "): too many distinct (t0,t1,t2) triples");
+        return ABFIT_ERR_TOO_LARGE;
+    }
+    out.smem_boot = worst(true, false, 1);
+    out.d_shared_aux = worst(false, true, 1) <= smem_cap / 2;
+    out.smem_aux = worst(false, out.d_shared_aux, 1);
+    if (out.smem_boot > smem_cap || out.smem_aux > smem_cap) {
+        set_error("pedigree too large for the shared-memory model state");
+        return ABFIT_ERR_TOO_LARGE;
+    }
+    return 0;
+}
+
+std::vector<WorkItem> make_items(const HostPlan &hp, int count_per_prob, int n_sm, int n_warps, bool skip_nan)
+{
+    // One block per item.  Enough blocks to fill the machine several times over, but chunks as
+    // long as possible so that idle lanes can pull further fits of the same window.
+    const int lanes = 32 * n_warps;
+    const int64_t target_blocks = (int64_t)n_sm * (16 / n_warps) * 3;
+    const int n_probs = (int)hp.probs.size();
+    const int64_t total = (int64_t)n_probs * count_per_prob;
+    int64_t chunk = (total + target_blocks - 1) / target_blocks;
+    chunk = ((chunk + lanes - 1) / lanes) * lanes;
+    if (chunk < 2 * lanes) chunk = 2 * lanes;
+    if (chunk > count_per_prob) chunk = count_per_prob;
+    const int n_chunks = (int)((count_per_prob + chunk - 1) / chunk);
+    chunk = (count_per_prob + n_chunks - 1) / n_chunks;  // even split
+    std::vector<WorkItem> items;
+    for (int p = 0; p < n_probs; ++p) {
+        if (skip_nan && hp.d_has_nan[p]) continue;
+        for (int f = 0; f < count_per_prob; f += (int)chunk) {
+            WorkItem it;
+            it.prob = p;
+            it.first = f;
+            it.count = std::min<int>((int)chunk, count_per_prob - f);
+            it.pad = 0;
+            items.push_back(it);
+        }
+    }
+    return items;
+}
+
+}  // namespace abfit

@@ -1,0 +1,39 @@
+// abfit_plan.h — host-side compilation of pedigrees into the per-window micro-op programs
+// the kernels interpret (see abfit_model.cuh), and the block/warp work decomposition.
+#pragma once
+#include "abfit_internal.h"
+
+namespace abfit {
+
+struct HostPlan {
+    std::vector<DevProblem> probs;
+    std::vector<double> D;         // every problem padded to an even count (16-byte alignment)
+    std::vector<uint32_t> offs;    // 256 * lane_mem index of each pair's dt1t2, padded to 4 per problem
+    std::vector<OpWord> ops;
+    std::vector<EvWord> events;
+    std::vector<double> flops;     // algorithmic FLOPs per objective evaluation
+    std::vector<int32_t> n_triples, tmax;
+    std::vector<uint8_t> d_has_nan;
+    int32_t max_pairs = 0;
+    int64_t total_pairs = 0;
+    void clear() { *this = HostPlan(); }
+};
+
+// Validates and compiles n_probs problems. Returns 0 or a negative abfit_status (message via set_error).
+int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp);
+
+// kernel configuration of one batch for a device with `smem_cap` bytes of opt-in shared memory per block
+struct LaunchShape {
+    int n_warps = 1;        // warps per block of the multi-start kernel
+    bool d_shared = true;   // D column staged in shared memory (else broadcast from L1/L2)
+    size_t smem_fit = 0;    // k_fit_starts
+    size_t smem_boot = 0;   // k_fit_boot (1 warp, D* comes from the scratch tile)
+    size_t smem_aux = 0;    // k_select / k_cost_batch / k_model_div (1 warp, no simplex)
+    bool d_shared_aux = true;
+};
+int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm, int fits_per_prob, LaunchShape &out);
+
+// chunks of `count_per_prob` fits per problem; every block gets at least 32 * n_warps * 2 fits when it can
+std::vector<WorkItem> make_items(const HostPlan &hp, int count_per_prob, int n_sm, int n_warps, bool skip_nan);
+
+}  // namespace abfit

@@ -94,6 +94,10 @@ int abfit_ctx_create(int device, abfit_ctx **out);
 void abfit_ctx_destroy(abfit_ctx *ctx);
 /* device properties the bench reports: sm count, max SM clock (kHz), HBM bytes */
 int abfit_ctx_info(abfit_ctx *ctx, int32_t *sm_count, int32_t *sm_clock_khz, int64_t *mem_bytes);
+/* CUDA-event stopwatch on the context stream (bench.py times its steps on the device with it) */
+int abfit_ctx_timer_start(abfit_ctx *ctx);
+int abfit_ctx_timer_stop(abfit_ctx *ctx, float *ms_out); /* records, synchronises, returns elapsed ms */
+int abfit_ctx_sync(abfit_ctx *ctx);
 /* FP64 peak micro-benchmark (independent DFMA chains on every SM); TFLOP/s, FMA = 2 */
 int abfit_measure_fp64_peak(abfit_ctx *ctx, double *tflops_out);
 

@@ -1,0 +1,132 @@
+// emul.cpp — HOST build of the device-side model / objective / Nelder-Mead state machine.
+//
+// TEST INFRASTRUCTURE ONLY (never loaded by the product package).  The per-lane device code of
+// alphabeta-rs_b200/csrc/abfit_model.cuh + abfit_nm.cuh has no cross-lane communication, so it
+// can be compiled for the CPU with a few shims and run one lane at a time.  That lets the
+// `-m "not gpu"` suite execute the SAME source the kernels are built from (micro-op program,
+// software-pipelined pair loop, NM phases) against the oracle, without a GPU.
+//
+//   see Makefile (g++, -ffp-contract=off, shims.h force-included into abfit_plan.cu built as C++)
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "shims.h"
+
+#include "../../alphabeta-rs_b200/csrc/abfit_plan.h"
+
+namespace abfit {
+static std::string g_err;
+void set_error(const std::string &m) { g_err = m; }
+int cuda_fail(cudaError_t, const char *) { return ABFIT_ERR_CUDA; }
+size_t smem_need(const DevProblem &pb, bool with_simplex, bool d_shared, int n_warps)
+{
+    size_t b = (size_t)n_warps * ((size_t)pb.n_lane + (with_simplex ? 25 : 0)) * 32 * 8;
+    if (d_shared) b += (((size_t)pb.n_pairs + 1) & ~(size_t)1) * 8;
+    b += (size_t)pb.n_offs * 4 + (size_t)pb.n_ops * 8 + (size_t)pb.n_events * 8 + 16;
+    return (b + 15) & ~(size_t)15;
+}
+}  // namespace abfit
+
+using namespace abfit;
+
+struct Staged {
+    HostPlan hp;
+    std::vector<double> lane_mem;  // (n_lane + 25) * 32
+    WarpCtx c;
+    LaneSimplex S;
+};
+
+static int stage(const abfit_problem *pb, Staged &s, int lane)
+{
+    if (int rc = compile_problems(pb, 1, s.hp)) return rc;
+    const DevProblem &d = s.hp.probs[0];
+    s.lane_mem.assign((size_t)(d.n_lane + 25) * 32, 0.0);
+    s.c.D = s.hp.D.data() + d.d_off;
+    s.c.offs = s.hp.offs.data() + d.offs_off;
+    s.c.ops = s.hp.ops.data() + d.ops_off;
+    s.c.events = s.hp.events.data() + d.ev_off;
+    s.c.lm = s.lane_mem.data();
+    s.c.n_pairs = d.n_pairs;
+    s.c.n_events = d.n_events;
+    s.c.tmax = d.tmax;
+    s.c.p_uu0 = d.p_uu0;
+    s.c.p_mm0 = d.p_mm0;
+    s.c.eqp = d.eqp;
+    s.c.penw = d.penw;
+    s.S.X = s.lane_mem.data() + (size_t)d.n_lane * 32 + lane;
+    s.S.C = s.S.X + 20 * 32;
+    return 0;
+}
+
+extern "C" {
+
+const char *emul_last_error(void) { return g_err.c_str(); }
+
+// objective of theta[B][4] on one problem; every theta runs on lane (i % 32)
+int emul_cost(const abfit_problem *pb, const double *theta, int B, double *cost, double *lse)
+{
+    Staged s;
+    if (int rc = stage(pb, s, 0)) return rc;
+    const DBroadcast Dat{s.c.D};
+    for (int i = 0; i < B; ++i) {
+        const double *t = theta + 4 * (size_t)i;
+        const int lane = i & 31;
+        cost[i] = objective(s.c, Dat, lane, t[0], t[1], t[2], t[3], true);
+        if (lse) lse[i] = objective(s.c, Dat, lane, t[0], t[1], t[2], t[3], false);
+    }
+    return 0;
+}
+
+// one Nelder-Mead run per simplex ([n][5][4]), the state machine driven exactly as the kernels drive it.
+// dstar: optional per-fit D* columns [n][n_pairs] (bootstrap replicates), else the problem's D.
+int emul_fit(const abfit_problem *pb, const double *simplices, int n, const double *dstar, int max_iters,
+             double sd_tol, uint32_t flags, abfit_fit *out)
+{
+    NMParams nm{max_iters, sd_tol, flags};
+    for (int f = 0; f < n; ++f) {
+        const int lane = f & 31;
+        Staged s;
+        if (int rc = stage(pb, s, lane)) return rc;
+        std::vector<double> tile;
+        if (dstar) {
+            tile.assign((size_t)s.c.n_pairs * 32, 0.0);
+            for (int i = 0; i < s.c.n_pairs; ++i) tile[(size_t)i * 32 + lane] = dstar[(size_t)f * s.c.n_pairs + i];
+        }
+        LaneNM L;
+        std::memset(&L, 0, sizeof L);
+        for (int q = 0; q < 20; ++q) s.S.X[q * 32] = simplices[(size_t)f * 20 + q];
+        nm_begin(L, s.S, f);
+        abfit_fit res;
+        std::memset(&res, 0, sizeof res);
+        for (;;) {
+            double v;
+            if (dstar) {
+                const DLaneColumn Dat{tile.data() + lane};
+                v = objective(s.c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
+            } else {
+                const DBroadcast Dat{s.c.D};
+                v = objective(s.c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
+            }
+            if (nm_advance(L, s.S, nm, v, res)) break;
+        }
+        out[f] = res;
+    }
+    return 0;
+}
+
+// plan statistics: per-lane doubles, micro-ops, events, chain length
+int emul_plan_stats(const abfit_problem *pb, int32_t out[6])
+{
+    HostPlan hp;
+    if (int rc = compile_problems(pb, 1, hp)) return rc;
+    out[0] = hp.probs[0].n_lane;
+    out[1] = hp.probs[0].n_ops;
+    out[2] = hp.probs[0].n_events;
+    out[3] = hp.probs[0].tmax;
+    out[4] = hp.n_triples[0];
+    out[5] = (int32_t)smem_need(hp.probs[0], true, true, 1);
+    return 0;
+}
+}
