@@ -366,7 +366,7 @@ int abfit_batch_run_fit(abfit_batch *b, int32_t max_iters, double sd_tol, uint32
     }
     ABFIT_CUDA(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->ctx->stream;
-    NMParams nm{max_iters, sd_tol, flags};
+    NMParams nm{max_iters, sd_tol, flags, nm_var_threshold(sd_tol)};
     // records of skipped (NaN) problems read back as status -1 / NaN
     ABFIT_CUDA(cudaMemsetAsync(b->d_all.p, 0xFF, (size_t)b->n_probs * b->n_starts * sizeof(abfit_fit), st));
     ABFIT_CUDA(cudaMemsetAsync(b->d_evals_fit.p, 0, (size_t)b->n_probs * 8, st));
@@ -462,7 +462,7 @@ int abfit_batch_run_boot(abfit_batch *b, int32_t max_iters, double sd_tol, uint3
     }
     ABFIT_CUDA(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->ctx->stream;
-    NMParams nm{max_iters, sd_tol, flags};
+    NMParams nm{max_iters, sd_tol, flags, nm_var_threshold(sd_tol)};
     ABFIT_CUDA(cudaMemsetAsync(b->d_rows.p, 0xFF, (size_t)b->n_probs * b->n_boot * 7 * 8, st));
     ABFIT_CUDA(cudaMemsetAsync(b->d_bootfits.p, 0xFF, (size_t)b->n_probs * b->n_boot * sizeof(abfit_fit), st));
     ABFIT_CUDA(cudaMemsetAsync(b->d_evals_boot.p, 0, (size_t)b->n_probs * 8, st));

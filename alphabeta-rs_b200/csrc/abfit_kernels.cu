@@ -157,12 +157,13 @@ k_fit_starts(DevicePools P, const WorkItem *__restrict__ items, const double *__
             }
         }
         const bool active = (L.phase != PH_IDLE);
-        if (!__any_sync(FULL, active)) break;
+        const unsigned amask = __ballot_sync(FULL, active);
+        if (!amask) break;
         if (active) {
             const double f =
                 objective(c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
             abfit_fit res;
-            if (nm_advance(L, S, nm, f, res)) {
+            if (nm_advance(L, S, nm, f, res, amask)) {
                 my_evals += (unsigned long long)res.evals;
                 store_fit(all_out + (size_t)it.prob * n_starts + res.start_id, res);
             }
@@ -311,12 +312,13 @@ k_fit_boot(DevicePools P, const WorkItem *__restrict__ items, int n_boot, const 
             next += __popc(m);
         }
         const bool active = (L.phase != PH_IDLE);
-        if (!__any_sync(FULL, active)) break;
+        const unsigned amask = __ballot_sync(FULL, active);
+        if (!amask) break;
         if (active) {
             const double f =
                 objective(c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
             abfit_fit res;
-            if (nm_advance(L, S, nm, f, res)) {
+            if (nm_advance(L, S, nm, f, res, amask)) {
                 my_evals += (unsigned long long)res.evals;
                 const size_t o = (size_t)it.prob * n_boot + res.start_id;
                 // src/boot_model.rs:86-91

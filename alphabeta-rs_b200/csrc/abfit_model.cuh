@@ -314,29 +314,25 @@ __device__ __forceinline__ double objective(const WarpCtx &c, const DAcc &Dat, i
     double t[4] = {0.0, 0.0, 0.0, 0.0};  // terms of the previous group (adding +0.0 first is exact)
 
     struct Grp {
-        double d[4], raw[4];
-        uint32_t off[4];
+        double d[4], v[4];
     };
-    // stage 1: loads of one group of four pairs.  The first dt of a group is always fetched, the
-    // others only where the (warp-uniform) triple changes inside the group.
+    // stage 1: loads of one group of four pairs (D, the four dt offsets, the four dt values).  All
+    // loads are unconditional: comparing offsets to skip repeated triples costs more issue slots
+    // than the shared-memory wavefronts it saves (ncu: the kernel is issue-bound, not LSU-bound).
     auto load = [&](int g, Grp &G) {
         Dat.load4(4 * g, G.d);
         const uint4 o = *reinterpret_cast<const uint4 *>(c.offs + 4 * g);
-        G.off[0] = o.x; G.off[1] = o.y; G.off[2] = o.z; G.off[3] = o.w;
-        G.raw[0] = *reinterpret_cast<const double *>(dtb + o.x);
-#pragma unroll
-        for (int q = 1; q < 4; ++q)
-            G.raw[q] = (G.off[q] != G.off[q - 1]) ? *reinterpret_cast<const double *>(dtb + G.off[q]) : 0.0;
+        G.v[0] = *reinterpret_cast<const double *>(dtb + o.x);
+        G.v[1] = *reinterpret_cast<const double *>(dtb + o.y);
+        G.v[2] = *reinterpret_cast<const double *>(dtb + o.z);
+        G.v[3] = *reinterpret_cast<const double *>(dtb + o.w);
     };
     // stage 2 + 3: residuals / squares of group G, then the sequential accumulate of the previous one
     auto step = [&](const Grp &G) {
-        double v[4], n[4];
-        v[0] = G.raw[0];
-#pragma unroll
-        for (int q = 1; q < 4; ++q) v[q] = (G.off[q] != G.off[q - 1]) ? G.raw[q] : v[q - 1];
+        double n[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const double res = G.d[q] - icpt - v[q];
+            const double res = G.d[q] - icpt - G.v[q];
             n[q] = res * res + pen;
         }
         sum += t[0];

@@ -105,16 +105,25 @@ struct NMParams {
     int max_iters;
     double sd_tol;
     uint32_t flags;
+    // largest y with sqrt(y) < sd_tol (host: nm_var_threshold).  IEEE sqrt is correctly rounded and
+    // therefore monotonic, so  sqrt(y) < sd_tol  <=>  y <= var_thr  and the kernels never take the root.
+    double var_thr;
 };
 
 // Consume the objective value f of the lane's current trial point and advance the
 // state machine to the next trial point.  Returns true when the fit has finished
 // (lane.phase == PH_IDLE, result in `res`).
+//
+// `amask` = lanes of the warp that are inside this call.  The phase switch is divergent by nature;
+// the sort / termination test / reflection that follows is common to every lane that completed an
+// iteration, so the lanes are re-converged before it (ncu: without the barrier the tail ran ~2.5x
+// per evaluation at ~5 active lanes).
 __device__ __forceinline__ bool nm_advance(LaneNM &L, const LaneSimplex &S, const NMParams &P, double f,
-                                           abfit_fit &res)
+                                           abfit_fit &res, unsigned amask)
 {
     bool iter_done = false;   // an NM iteration (or init) completed: sort + termination test follow
     bool finish = false;      // go to the final LSE evaluation
+    bool done = false;        // the fit has ended (result in `res`)
     switch (L.phase) {
         case PH_INIT: {
             // NOTE: written as "load vertex k+1 relative to k, then bump k" on purpose.  ptxas 12.9 folds
@@ -234,11 +243,13 @@ __device__ __forceinline__ bool nm_advance(LaneNM &L, const LaneSimplex &S, cons
             res.status = (res.cost != res.cost) ? ABFIT_FIT_NAN : L.status;
             res.start_id = L.fit_id;
             L.phase = PH_IDLE;
-            return true;
+            done = true;
+            break;
         }
         default: break;
     }
 
+    __syncwarp(amask);
     if (iter_done) {
         L.ord = sort5(S, L.ord);  // sort_param_vecs (stable)
         ++L.iters;
@@ -256,8 +267,8 @@ __device__ __forceinline__ bool nm_advance(LaneNM &L, const LaneSimplex &S, cons
             const double d = c[p] - c0;
             ss += d * d;
         }
-        const double sd = sqrt(1.0 / (5.0 - 1.0) * ss);
-        if (sd < P.sd_tol) {
+        // sd = sqrt(1/(n-1) * ss) < sd_tolerance, evaluated without the root (see NMParams::var_thr)
+        if (1.0 / (5.0 - 1.0) * ss <= P.var_thr) {
             L.status = ABFIT_TERM_SD;
             finish = true;
         } else if (L.iters >= P.max_iters) {
@@ -274,7 +285,7 @@ __device__ __forceinline__ bool nm_advance(LaneNM &L, const LaneSimplex &S, cons
         for (int j = 0; j < 4; ++j) L.xt[j] = S.x(b, j);
         L.phase = PH_LSE;
     }
-    return false;
+    return done;
 }
 
 // start a new fit on this lane from a 5x4 simplex in global memory

@@ -1,4 +1,7 @@
 // abfit_plan.cu — pedigree -> micro-op program (host).  O(pairs) bookkeeping; no numerics.
+#include <cfloat>
+#include <cstdlib>
+#include <cmath>
 #include <map>
 #include <set>
 #include <tuple>
@@ -189,6 +192,21 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
     return 0;
 }
 
+double nm_var_threshold(double sd_tol)
+{
+    if (!(sd_tol > 0.0)) return -1.0;  // sqrt(y) >= 0 is never below a tolerance <= 0 (or NaN)
+    if (std::isinf(sd_tol)) return DBL_MAX;
+    double y = sd_tol * sd_tol;
+    if (std::isinf(y)) y = DBL_MAX;
+    while (y > 0.0 && !(std::sqrt(y) < sd_tol)) y = std::nextafter(y, 0.0);
+    for (;;) {
+        const double up = std::nextafter(y, INFINITY);
+        if (std::isinf(up) || !(std::sqrt(up) < sd_tol)) break;
+        y = up;
+    }
+    return std::sqrt(y) < sd_tol ? y : -1.0;
+}
+
 int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm, int fits_per_prob, LaunchShape &out)
 {
     auto worst = [&](bool simplex, bool d_shared, int nw) {
@@ -199,9 +217,11 @@ int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm,
     // multi-start kernel: as many resident warps as shared memory allows (the register file allows 16)
     int best_w = -1;
     const int cand_nw[3] = {4, 2, 1};
+    const char *force = getenv("ABFIT_DEV_NWARPS");  // tuning experiments only
     for (int pass = 0; pass < 2; ++pass) {  // pass 0: D in shared memory; pass 1: D broadcast from L1/L2
         for (int nw : cand_nw) {
-            if (nw > 1 && fits_per_prob < 64 * nw) continue;  // too few fits for a multi-warp block
+            if (force && nw != atoi(force)) continue;
+            if (!force && nw > 1 && fits_per_prob < 64 * nw) continue;  // too few fits for a multi-warp block
             const size_t s = worst(true, pass == 0, nw);
             if (s > smem_cap) continue;
             int w = (int)std::min<size_t>(16, (smem_per_sm / (s + 1024)) * (size_t)nw);
@@ -241,6 +261,7 @@ std::vector<WorkItem> make_items(const HostPlan &hp, int count_per_prob, int n_s
     chunk = ((chunk + lanes - 1) / lanes) * lanes;
     if (chunk < 2 * lanes) chunk = 2 * lanes;
     if (chunk > count_per_prob) chunk = count_per_prob;
+    if (const char *fc = getenv("ABFIT_DEV_CHUNK")) chunk = std::max(1, std::min(atoi(fc), count_per_prob));
     const int n_chunks = (int)((count_per_prob + chunk - 1) / chunk);
     chunk = (count_per_prob + n_chunks - 1) / n_chunks;  // even split
     std::vector<WorkItem> items;

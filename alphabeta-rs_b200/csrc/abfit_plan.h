@@ -33,6 +33,10 @@ struct LaunchShape {
 };
 int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm, int fits_per_prob, LaunchShape &out);
 
+// largest y with sqrt(y) < sd_tol (-1 when no y >= 0 qualifies): lets the kernels evaluate argmin's
+// `sd < sd_tolerance` termination test without taking the square root (see NMParams::var_thr)
+double nm_var_threshold(double sd_tol);
+
 // chunks of `count_per_prob` fits per problem; every block gets at least 32 * n_warps * 2 fits when it can
 std::vector<WorkItem> make_items(const HostPlan &hp, int count_per_prob, int n_sm, int n_warps, bool skip_nan);
 

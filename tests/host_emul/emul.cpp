@@ -84,7 +84,7 @@ int emul_cost(const abfit_problem *pb, const double *theta, int B, double *cost,
 int emul_fit(const abfit_problem *pb, const double *simplices, int n, const double *dstar, int max_iters,
              double sd_tol, uint32_t flags, abfit_fit *out)
 {
-    NMParams nm{max_iters, sd_tol, flags};
+    NMParams nm{max_iters, sd_tol, flags, nm_var_threshold(sd_tol)};
     for (int f = 0; f < n; ++f) {
         const int lane = f & 31;
         Staged s;
@@ -109,7 +109,7 @@ int emul_fit(const abfit_problem *pb, const double *simplices, int n, const doub
                 const DBroadcast Dat{s.c.D};
                 v = objective(s.c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
             }
-            if (nm_advance(L, s.S, nm, v, res)) break;
+            if (nm_advance(L, s.S, nm, v, res, 1u << lane)) break;
         }
         out[f] = res;
     }
