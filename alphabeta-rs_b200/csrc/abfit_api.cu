@@ -73,7 +73,6 @@ struct abfit_batch {
     DevBuf<double> d_D;
     DevBuf<uint32_t> d_offs;
     DevBuf<OpWord> d_ops;
-    DevBuf<EvWord> d_events;
     DevicePools pools{};
     // fit
     int n_starts = 0;
@@ -298,17 +297,14 @@ int abfit_batch_create(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_pro
     if (int rc = b->d_D.ensure(hp.D.size())) return rc;
     if (int rc = b->d_offs.ensure(hp.offs.size())) return rc;
     if (int rc = b->d_ops.ensure(hp.ops.size())) return rc;
-    if (int rc = b->d_events.ensure(hp.events.size())) return rc;
     cudaStream_t st = ctx->stream;
     ABFIT_CUDA(cudaMemcpyAsync(b->d_probs.p, hp.probs.data(), hp.probs.size() * sizeof(DevProblem), cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaMemcpyAsync(b->d_D.p, hp.D.data(), hp.D.size() * 8, cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaMemcpyAsync(b->d_offs.p, hp.offs.data(), hp.offs.size() * 4, cudaMemcpyHostToDevice, st));
     if (!hp.ops.empty())
         ABFIT_CUDA(cudaMemcpyAsync(b->d_ops.p, hp.ops.data(), hp.ops.size() * sizeof(OpWord), cudaMemcpyHostToDevice, st));
-    if (!hp.events.empty())
-        ABFIT_CUDA(cudaMemcpyAsync(b->d_events.p, hp.events.data(), hp.events.size() * sizeof(EvWord), cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaStreamSynchronize(st));  // hp vectors are pageable: make the copies complete here
-    b->pools = DevicePools{b->d_probs.p, b->d_D.p, b->d_offs.p, b->d_ops.p, b->d_events.p};
+    b->pools = DevicePools{b->d_probs.p, b->d_D.p, b->d_offs.p, b->d_ops.p};
     for (auto &e : b->ev) ABFIT_CUDA(cudaEventCreate(&e));
     if (int rc = b->d_evals_fit.ensure(n_probs)) return rc;
     if (int rc = b->d_evals_boot.ensure(n_probs)) return rc;

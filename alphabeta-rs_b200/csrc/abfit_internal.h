@@ -24,7 +24,6 @@ struct DevicePools {  // device pointers of a compiled batch
     const double *D;
     const uint32_t *offs;
     const OpWord *ops;
-    const EvWord *events;
 };
 
 // dynamic shared memory of one block working on problem pb (matches carve_and_stage)

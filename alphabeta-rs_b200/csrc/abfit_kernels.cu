@@ -24,14 +24,14 @@ namespace abfit {
 
 // ---------------------------------------------------------------------------------
 // shared-memory carve-up
-//   [ per warp: (n_lane + 25) x 32 doubles ] [ D ] [ offs ] [ ops ] [ events ] [ queue ]
+//   [ per warp: (n_lane + 25) x 32 doubles ] [ D ] [ offs ] [ ops ] [ queue ]
 // ---------------------------------------------------------------------------------
 size_t smem_need(const DevProblem &pb, bool with_simplex, bool d_shared, int n_warps)
 {
     size_t b = (size_t)n_warps * ((size_t)pb.n_lane + (with_simplex ? 25 : 0)) * 32 * 8;
     if (d_shared) b += (((size_t)pb.n_pairs + 1) & ~(size_t)1) * 8;
     b += (size_t)pb.n_offs * 4;
-    b += (size_t)pb.n_ops * 8 + (size_t)pb.n_events * 8;
+    b += (size_t)pb.n_ops * 8;
     b += 16;
     return (b + 15) & ~(size_t)15;
 }
@@ -71,17 +71,13 @@ __device__ __forceinline__ Carved carve_and_stage(const DevProblem &pb, const De
     }
     uint32_t *offs = reinterpret_cast<uint32_t *>(p);  // 16-byte aligned; n_offs is a multiple of 4
     OpWord *ops = reinterpret_cast<OpWord *>(offs + pb.n_offs);
-    EvWord *evs = reinterpret_cast<EvWord *>(ops + pb.n_ops);
-    cv.queue = reinterpret_cast<int *>(evs + pb.n_events);
+    cv.queue = reinterpret_cast<int *>(ops + pb.n_ops);
     for (int i = tid; i < pb.n_offs; i += nthr) offs[i] = P.offs[pb.offs_off + i];
     for (int i = tid; i < pb.n_ops; i += nthr) ops[i] = P.ops[pb.ops_off + i];
-    for (int i = tid; i < pb.n_events; i += nthr) evs[i] = P.events[pb.ev_off + i];
     cv.ctx.offs = offs;
     cv.ctx.ops = ops;
-    cv.ctx.events = evs;
     cv.ctx.n_pairs = pb.n_pairs;
-    cv.ctx.n_events = pb.n_events;
-    cv.ctx.tmax = pb.tmax;
+    cv.ctx.n_ops = pb.n_ops;
     cv.ctx.p_uu0 = pb.p_uu0;
     cv.ctx.p_mm0 = pb.p_mm0;
     cv.ctx.eqp = pb.eqp;
@@ -122,7 +118,7 @@ __device__ __forceinline__ int queue_take(int *queue, unsigned m, int lane, int 
 // multi-start Nelder-Mead
 // ---------------------------------------------------------------------------------
 template <bool D_SHARED>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 k_fit_starts(DevicePools P, const WorkItem *__restrict__ items, const double *__restrict__ simplices,
              int n_starts, NMParams nm, abfit_fit *__restrict__ all_out,
              unsigned long long *__restrict__ evals_per_prob)

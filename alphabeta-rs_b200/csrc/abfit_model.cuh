@@ -37,12 +37,22 @@ constexpr unsigned FULL = 0xffffffffu;
 // Per-lane storage lives in shared memory as lane_mem[index * 32 + lane].
 // ---------------------------------------------------------------------------------
 enum MicroOp : uint32_t {
+    OP_STEP = 0,     // a = n                       R <- R.G, n times (matrix_power's chain, :27-29)
     OP_STORE_M = 1,  // a = dst                     lane_mem[dst..dst+8]  <- R  (= G^k)
     OP_CALC_S = 2,   // a = dst                     lane_mem[dst..dst+2]  <- sv0^T . R          (src/divergence.rs:55)
-    OP_D = 3,        // a = A source, b = B source  dreg <- conditional divergences of rows UU,UM,MM (:68-87)
-    OP_STORE_D = 4,  // a = dst                     lane_mem[dst..dst+2]  <- dreg
-    OP_LOAD_D = 5,   // a = src                     dreg <- lane_mem[src..src+2]
-    OP_DT = 6        // a = dst, b = s source       lane_mem[dst] <- s0*d_uu + s1*d_um + s2*d_mm (:89)
+    // dreg <- conditional divergences of rows UU,UM,MM for A = G^(t1-t0), B = G^(t2-t0) (:57-87).  The
+    // event fires at k = max(t1-t0, t2-t0), so one operand is always the chain's current power R; the
+    // variants name where the other one lives (no register copies, no source decoding):
+    OP_D_CC = 3,     //                             A = R,            B = R
+    OP_D_MC = 4,     // a = src                     A = lane_mem[src], B = R
+    OP_D_CM = 5,     // a = src                     A = R,            B = lane_mem[src]
+    OP_D_GC = 6,     //                             A = G,            B = R
+    OP_D_CG = 7,     //                             A = R,            B = G
+    OP_D_GEN = 10,   // a = A source, b = B source  an identity operand (t1 == t0 or t2 == t0) or anything else
+    OP_STORE_D = 11, // a = dst                     lane_mem[dst..dst+2]  <- dreg
+    OP_LOAD_D = 12,  // a = src                     dreg <- lane_mem[src..src+2]
+    OP_DT0 = 13,     // a = dst                     lane_mem[dst] <- sv0 . dreg   (t0 == 0: s = sv0^T . G^0)
+    OP_DT = 14       // a = dst, b = s source       lane_mem[dst] <- s0*d_uu + s1*d_um + s2*d_mm (:89)
 };
 // operand sources (16 bit); anything below SRC_SPECIAL is a lane_mem index
 constexpr uint32_t SRC_SPECIAL = 0xfff0;
@@ -54,21 +64,17 @@ constexpr uint32_t SRC_SV0 = 0xfff3;    // sv0^T . G^0
 struct OpWord {
     uint32_t x, y;
 };
-// event: x = k | n_ops << 8, y = first_op   (k ascending; k == 0 fires before the chain)
-struct EvWord {
-    uint32_t x, y;
-};
 
 struct DevProblem {
     int64_t d_off;     // into the D pool (even: 16-byte aligned)
     int64_t pair_off;  // into pred / resid (problems concatenated without padding)
     int64_t offs_off;  // into the pair-offset pool: u32 = 256 * lane_mem index of the pair's dt1t2
     int64_t ops_off;   // into the micro-op pool
-    int64_t ev_off;    // into the event pool
     int32_t n_pairs, n_offs;  // n_offs = n_pairs rounded up to 4
-    int32_t n_ops, n_events;
+    int32_t n_ops;
     int32_t n_lane;   // doubles of per-lane model storage
     int32_t tmax;     // last exponent the chain has to reach
+    int32_t pad_;
     double p_uu0, p_mm0;  // state at G0 (p0um = 0), src/ab_neutral.rs:23-24
     double eqp, penw;     // penw = eqp_weight * (double)n_pairs, src/structs.rs:210-211
 };
@@ -78,9 +84,8 @@ struct WarpCtx {
     const double *D;       // [n_pairs] shared (or global for very long pedigrees), 16-byte aligned
     const uint32_t *offs;  // shared, 16-byte aligned
     const OpWord *ops;     // shared
-    const EvWord *events;  // shared
     double *lm;            // this warp's lane_mem (lane NOT folded in)
-    int32_t n_pairs, n_events, tmax;
+    int32_t n_pairs, n_ops;
     double p_uu0, p_mm0, eqp, penw;
 };
 
@@ -171,15 +176,48 @@ __device__ __forceinline__ void fetch_matrix(uint32_t src, const double *lml, co
     }
 }
 
-// run the micro-ops of one event with R = G^k (all control flow here is warp-uniform)
-__device__ __forceinline__ void run_ops(const WarpCtx &c, double *lml, int first, int n, const double R[9],
-                                        const double G[9], const double sid[3], double sv0, double sv1, double sv2,
-                                        double dreg[3])
+// conditional divergences of the three rows, in the reference's order MM, UM, UU (:68-87)
+__device__ __forceinline__ void cond_div3(const double A[9], const double B[9], double dreg[3])
 {
-    for (int i = first; i < first + n; ++i) {
+    dreg[2] = cond_div(A + 6, B + 6);
+    dreg[1] = cond_div(A + 3, B + 3);
+    dreg[0] = cond_div(A, B);
+}
+
+__device__ __forceinline__ void load_matrix(const double *lml, uint32_t src, double M[9])
+{
+    const double *p = lml + src * 32;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) M[e] = p[e * 32];
+}
+
+// Power chain + per-triple theoretical divergence (src/divergence.rs:44-90): ONE flat loop over the
+// window's micro-ops.  The chain steps (OP_STEP) live in the same loop as the ops that read R on
+// purpose: with R loop-variant the compiler cannot hoist the pure cond_div3 variants out of the loop
+// and execute all of them speculatively (it did, for ~1000 FP64 instructions per evaluation, when
+// the ops of one exponent formed an inner loop).  All control flow here is warp-uniform.
+__device__ __forceinline__ void model_divergence(const WarpCtx &c, int lane, double alpha, double beta,
+                                                 double weight)
+{
+    double *lml = c.lm + lane;
+    double G[9], R[9], dreg[3] = {0.0, 0.0, 0.0};
+    genmatrix(alpha, beta, G);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = G[i];
+    // sv_gzero (src/divergence.rs:44) and its product with G^0
+    const double sv0 = c.p_uu0, sv1 = weight * c.p_mm0, sv2 = (1.0 - weight) * c.p_mm0;
+    const double I[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};
+    double sid[3];
+    vec_mat(sv0, sv1, sv2, I, sid);
+
+    for (int i = 0; i < c.n_ops; ++i) {
         const OpWord w = c.ops[i];
         const uint32_t op = w.x & 0xff, a = w.x >> 8, b = w.y;
         switch (op) {
+            case OP_STEP: {
+                for (uint32_t s = 0; s < a; ++s) mat3_step(R, G);
+                break;
+            }
             case OP_STORE_M: {
                 double *p = lml + a * 32;
 #pragma unroll
@@ -193,18 +231,26 @@ __device__ __forceinline__ void run_ops(const WarpCtx &c, double *lml, int first
                 p[0] = s[0]; p[32] = s[1]; p[64] = s[2];
                 break;
             }
-            case OP_D: {
+            case OP_D_CC: cond_div3(R, R, dreg); break;
+            case OP_D_MC: {
+                double M[9];
+                load_matrix(lml, a, M);
+                cond_div3(M, R, dreg);
+                break;
+            }
+            case OP_D_CM: {
+                double M[9];
+                load_matrix(lml, a, M);
+                cond_div3(R, M, dreg);
+                break;
+            }
+            case OP_D_GC: cond_div3(G, R, dreg); break;
+            case OP_D_CG: cond_div3(R, G, dreg); break;
+            case OP_D_GEN: {  // identity operands (t1 == t0 or t2 == t0) and anything unusual
                 double A[9], B[9];
                 fetch_matrix(a, lml, R, G, A);
-                if (b == a) {
-#pragma unroll
-                    for (int e = 0; e < 9; ++e) B[e] = A[e];
-                } else {
-                    fetch_matrix(b, lml, R, G, B);
-                }
-                dreg[2] = cond_div(A + 6, B + 6);  // MM, UM, UU in the reference's order (:68-87)
-                dreg[1] = cond_div(A + 3, B + 3);
-                dreg[0] = cond_div(A, B);
+                fetch_matrix(b, lml, R, G, B);
+                cond_div3(A, B, dreg);
                 break;
             }
             case OP_STORE_D: {
@@ -217,52 +263,16 @@ __device__ __forceinline__ void run_ops(const WarpCtx &c, double *lml, int first
                 dreg[0] = p[0]; dreg[1] = p[32]; dreg[2] = p[64];
                 break;
             }
+            case OP_DT0:
+                lml[a * 32] = sid[0] * dreg[0] + sid[1] * dreg[1] + sid[2] * dreg[2];  // src/divergence.rs:89
+                break;
             case OP_DT: {
-                double s0, s1, s2;
-                if (b == SRC_SV0) {
-                    s0 = sid[0]; s1 = sid[1]; s2 = sid[2];
-                } else {
-                    const double *p = lml + b * 32;
-                    s0 = p[0]; s1 = p[32]; s2 = p[64];
-                }
-                lml[a * 32] = s0 * dreg[0] + s1 * dreg[1] + s2 * dreg[2];  // src/divergence.rs:89
+                const double *p = lml + b * 32;
+                const double s0 = p[0], s1 = p[32], s2 = p[64];
+                lml[a * 32] = s0 * dreg[0] + s1 * dreg[1] + s2 * dreg[2];
                 break;
             }
             default: break;
-        }
-    }
-}
-
-// Power chain + per-triple theoretical divergence (src/divergence.rs:44-90).
-__device__ __forceinline__ void model_divergence(const WarpCtx &c, int lane, double alpha, double beta,
-                                                 double weight)
-{
-    double *lml = c.lm + lane;
-    double G[9], R[9], dreg[3] = {0.0, 0.0, 0.0};
-    genmatrix(alpha, beta, G);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = G[i];
-    // sv_gzero (src/divergence.rs:44) and its product with G^0
-    const double sv0 = c.p_uu0, sv1 = weight * c.p_mm0, sv2 = (1.0 - weight) * c.p_mm0;
-    double sid[3];
-    {
-        const double I[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};
-        vec_mat(sv0, sv1, sv2, I, sid);
-    }
-    const EvWord none = {0xffu, 0u};
-    int ei = 0;
-    EvWord ev = c.n_events > 0 ? c.events[0] : none;
-    if ((ev.x & 0xff) == 0) {  // exponent-0-only triples (t0 = t1 = t2)
-        run_ops(c, lml, (int)ev.y, (int)(ev.x >> 8), R, G, sid, sv0, sv1, sv2, dreg);
-        ++ei;
-        ev = ei < c.n_events ? c.events[ei] : none;
-    }
-    for (int k = 1; k <= c.tmax; ++k) {
-        if (k > 1) mat3_step(R, G);
-        if ((int)(ev.x & 0xff) == k) {  // warp-uniform
-            run_ops(c, lml, (int)ev.y, (int)(ev.x >> 8), R, G, sid, sv0, sv1, sv2, dreg);
-            ++ei;
-            ev = ei < c.n_events ? c.events[ei] : none;
         }
     }
 }

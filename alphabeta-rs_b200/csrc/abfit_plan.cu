@@ -54,7 +54,6 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
         hp.total_pairs += ap.n_pairs;
         dp.offs_off = (int64_t)hp.offs.size();
         dp.ops_off = (int64_t)hp.ops.size();
-        dp.ev_off = (int64_t)hp.events.size();
         dp.n_pairs = ap.n_pairs;
         dp.p_uu0 = ap.p0uu;
         dp.p_mm0 = 1.0 - ap.p0uu;               // src/ab_neutral.rs:23
@@ -135,15 +134,27 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
             if (e == 1) return SRC_G;
             return idx_M[e];
         };
+        auto op_d = [&](int a, int b, int k) -> OpWord {
+            const uint32_t sa = src_of(a, k), sb = src_of(b, k);
+            if (sa == SRC_CUR && sb == SRC_CUR) return mk_op(OP_D_CC, 0);
+            if (sb == SRC_CUR) {
+                if (sa == SRC_G) return mk_op(OP_D_GC, 0);
+                if (sa < SRC_SPECIAL) return mk_op(OP_D_MC, sa);
+            } else if (sa == SRC_CUR) {
+                if (sb == SRC_G) return mk_op(OP_D_CG, 0);
+                if (sb < SRC_SPECIAL) return mk_op(OP_D_CM, sb);
+            }
+            return mk_op(OP_D_GEN, sa, sb);
+        };
         for (auto &kv : by_ab) {
             const int a = kv.first.first, b = kv.first.second, k = std::max(a, b);
             Ev &ev = evs[k];
-            ev.body.push_back(mk_op(OP_D, src_of(a, k), src_of(b, k)));
+            ev.body.push_back(op_d(a, b, k));
             for (auto &t : kv.second) {
                 const int t0 = std::get<0>(t);
                 const uint32_t dst = dt_base + (uint32_t)tri_id[t];
                 if (t0 == 0)
-                    ev.body.push_back(mk_op(OP_DT, dst, SRC_SV0));
+                    ev.body.push_back(mk_op(OP_DT0, dst));
                 else if (t0 <= k)
                     ev.body.push_back(mk_op(OP_DT, dst, idx_S[t0]));
             }
@@ -161,21 +172,21 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
                     ev.tail.push_back(mk_op(OP_DT, dt_base + (uint32_t)tri_id[t], idx_S[lv.first]));
             }
         }
-        int tmax = 0;
+        // flatten: [exponent-0 ops] STEP ... ops(k1) STEP ... ops(k2) ...; the chain starts at R = G^1
+        int tmax = 0, cur_k = 1;
         for (auto &kv : evs) {
-            EvWord w;
-            const size_t first = hp.ops.size() - (size_t)dp.ops_off;
+            const int k = kv.first;
+            if (k > cur_k) {
+                hp.ops.push_back(mk_op(OP_STEP, (uint32_t)(k - cur_k)));
+                cur_k = k;
+            }
             for (auto &o : kv.second.head) hp.ops.push_back(o);
             for (auto &o : kv.second.body) hp.ops.push_back(o);
             for (auto &o : kv.second.tail) hp.ops.push_back(o);
-            const size_t n = hp.ops.size() - (size_t)dp.ops_off - first;
-            w.x = (uint32_t)kv.first | ((uint32_t)n << 8);
-            w.y = (uint32_t)first;
-            hp.events.push_back(w);
-            tmax = std::max(tmax, kv.first);
+            tmax = std::max(tmax, k);
         }
         dp.n_ops = (int32_t)(hp.ops.size() - (size_t)dp.ops_off);
-        dp.n_events = (int32_t)(hp.events.size() - (size_t)dp.ev_off);
+        dp.pad_ = 0;
         dp.n_lane = (int32_t)n_lane;
         dp.tmax = tmax;
 

@@ -10,7 +10,6 @@ struct HostPlan {
     std::vector<double> D;         // every problem padded to an even count (16-byte alignment)
     std::vector<uint32_t> offs;    // 256 * lane_mem index of each pair's dt1t2, padded to 4 per problem
     std::vector<OpWord> ops;
-    std::vector<EvWord> events;
     std::vector<double> flops;     // algorithmic FLOPs per objective evaluation
     std::vector<int32_t> n_triples, tmax;
     std::vector<uint8_t> d_has_nan;

@@ -24,7 +24,7 @@ size_t smem_need(const DevProblem &pb, bool with_simplex, bool d_shared, int n_w
 {
     size_t b = (size_t)n_warps * ((size_t)pb.n_lane + (with_simplex ? 25 : 0)) * 32 * 8;
     if (d_shared) b += (((size_t)pb.n_pairs + 1) & ~(size_t)1) * 8;
-    b += (size_t)pb.n_offs * 4 + (size_t)pb.n_ops * 8 + (size_t)pb.n_events * 8 + 16;
+    b += (size_t)pb.n_offs * 4 + (size_t)pb.n_ops * 8 + 16;
     return (b + 15) & ~(size_t)15;
 }
 }  // namespace abfit
@@ -46,11 +46,9 @@ static int stage(const abfit_problem *pb, Staged &s, int lane)
     s.c.D = s.hp.D.data() + d.d_off;
     s.c.offs = s.hp.offs.data() + d.offs_off;
     s.c.ops = s.hp.ops.data() + d.ops_off;
-    s.c.events = s.hp.events.data() + d.ev_off;
     s.c.lm = s.lane_mem.data();
     s.c.n_pairs = d.n_pairs;
-    s.c.n_events = d.n_events;
-    s.c.tmax = d.tmax;
+    s.c.n_ops = d.n_ops;
     s.c.p_uu0 = d.p_uu0;
     s.c.p_mm0 = d.p_mm0;
     s.c.eqp = d.eqp;
@@ -123,7 +121,7 @@ int emul_plan_stats(const abfit_problem *pb, int32_t out[6])
     if (int rc = compile_problems(pb, 1, hp)) return rc;
     out[0] = hp.probs[0].n_lane;
     out[1] = hp.probs[0].n_ops;
-    out[2] = hp.probs[0].n_events;
+    out[2] = 0;
     out[3] = hp.probs[0].tmax;
     out[4] = hp.n_triples[0];
     out[5] = (int32_t)smem_need(hp.probs[0], true, true, 1);

@@ -1,21 +1,21 @@
 #!/usr/bin/env python3
 """Summarise an ncu report of one kernel by source region (development aid).
 
-  python tools/ncu_regions.py gpurun_out/prof.ncu-rep k_fit_startsILb1 [csrc/abfit_kernels.cu]
+  python tools/ncu_regions.py gpurun_out/prof.ncu-rep k_fit_startsILb1 [libabfit.so that was profiled]
 
 Joins `ncu --page source --csv` (per-SASS-instruction samples / executed counts) with
-`nvdisasm --print-line-info` of the same source built with the Makefile's flags, and prints
+`nvdisasm --print-line-info` of the kernel cubin inside the profiled libabfit.so, and prints
 instruction share, stall-sample share and average active threads per region of the device code,
 plus the headline raw metrics.  Needs no GPU."""
 import collections, csv, os, re, subprocess, sys, tempfile
 
 rep, kern = sys.argv[1], sys.argv[2]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-src = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "alphabeta-rs_b200/csrc/abfit_kernels.cu")
+src = os.path.join(ROOT, "alphabeta-rs_b200/csrc/abfit_kernels.cu")
+lib = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "alphabeta-rs_b200/libabfit.so")
 tmp = tempfile.mkdtemp()
-cubin = os.path.join(tmp, "k.cubin")
-subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-lineinfo",
-                       "-fmad=false", "-O3", "-cubin", "-o", cubin, src], stderr=subprocess.DEVNULL)
+subprocess.check_call(["cuobjdump", "-xelf", "abfit_kernels.sm_100a.cubin", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
+cubin = os.path.join(tmp, "abfit_kernels.sm_100a.cubin")
 sass = subprocess.check_output(["nvdisasm", "--print-line-info", cubin], text=True).split("\n")
 start = next(i for i, l in enumerate(sass) if l.startswith(".text.") and kern in l)
 line_of, cur = {}, None
