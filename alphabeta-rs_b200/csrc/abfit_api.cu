@@ -76,7 +76,7 @@ struct abfit_batch {
     DevicePools pools{};
     // fit
     int n_starts = 0;
-    DevBuf<double> d_simplices;
+    DevBuf<double> d_simplices, d_xscratch;
     DevBuf<WorkItem> d_items;
     int n_items = 0;
     DevBuf<abfit_fit> d_all, d_best;
@@ -277,17 +277,19 @@ void abfit_gen_resample_idx(uint64_t seed, uint64_t problem_id, int32_t n_boot, 
 // ---------------------------------------------------------------------------------------
 // batches
 // ---------------------------------------------------------------------------------------
-int abfit_batch_create(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, abfit_batch **out)
+// (re)load a batch object with a new set of problems; device buffers only ever grow, so a batch that
+// is reused (the context's workspace behind the one-shot calls) stops paying cudaMalloc / cudaFree
+static int batch_load(abfit_batch *b, const abfit_problem *probs, int32_t n_probs)
 {
-    if (!ctx || !out) return ABFIT_ERR_ARG;
-    *out = nullptr;
-    ABFIT_CUDA(cudaSetDevice(ctx->device));
-    std::unique_ptr<abfit_batch> b(new abfit_batch());
-    b->ctx = ctx;
+    abfit_ctx *ctx = b->ctx;
     if (int rc = compile_problems(probs, n_probs, b->hp)) return rc;
     HostPlan &hp = b->hp;
     b->n_probs = n_probs;
     b->total_pairs = hp.total_pairs;
+    b->n_starts = b->n_boot = 0;
+    b->n_items = b->n_boot_items = 0;
+    b->fit_done = b->boot_uploaded = b->boot_done = false;
+    b->ev_fit = b->ev_boot = false;
     // aux kernels (select / cost / model divergence) only need the one-warp, simplex-free shape;
     // the fit shape is chosen in upload_starts / upload_boot when the number of fits is known
     if (int rc = choose_launch_shape(hp, (size_t)ctx->smem_optin, (size_t)ctx->prop.sharedMemPerMultiprocessor, 1,
@@ -305,13 +307,41 @@ int abfit_batch_create(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_pro
         ABFIT_CUDA(cudaMemcpyAsync(b->d_ops.p, hp.ops.data(), hp.ops.size() * sizeof(OpWord), cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaStreamSynchronize(st));  // hp vectors are pageable: make the copies complete here
     b->pools = DevicePools{b->d_probs.p, b->d_D.p, b->d_offs.p, b->d_ops.p};
-    for (auto &e : b->ev) ABFIT_CUDA(cudaEventCreate(&e));
+    if (!b->ev[0])
+        for (auto &e : b->ev) ABFIT_CUDA(cudaEventCreate(&e));
     if (int rc = b->d_evals_fit.ensure(n_probs)) return rc;
     if (int rc = b->d_evals_boot.ensure(n_probs)) return rc;
     ABFIT_CUDA(cudaMemsetAsync(b->d_evals_fit.p, 0, (size_t)n_probs * 8, st));
     ABFIT_CUDA(cudaMemsetAsync(b->d_evals_boot.p, 0, (size_t)n_probs * 8, st));
+    return 0;
+}
+
+int abfit_batch_create(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, abfit_batch **out)
+{
+    if (!ctx || !out) return ABFIT_ERR_ARG;
+    *out = nullptr;
+    ABFIT_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<abfit_batch> b(new abfit_batch());
+    b->ctx = ctx;
+    if (int rc = batch_load(b.get(), probs, n_probs)) {
+        abfit_batch_destroy(b.release());
+        return rc;
+    }
     *out = b.release();
     return 0;
+}
+
+// the context's reusable workspace for the one-shot host-buffer calls
+static int workspace(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, abfit_batch **out)
+{
+    if (!ctx) return ABFIT_ERR_ARG;
+    ABFIT_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->scratch) {
+        ctx->scratch = new abfit_batch();
+        ctx->scratch->ctx = ctx;
+    }
+    *out = ctx->scratch;
+    return batch_load(ctx->scratch, probs, n_probs);
 }
 
 void abfit_batch_destroy(abfit_batch *b)
@@ -344,6 +374,8 @@ int abfit_batch_upload_starts(abfit_batch *b, int32_t n_starts, const double *si
             ABFIT_CUDA(cudaMemcpyAsync(b->d_items.p, items.data(), items.size() * sizeof(WorkItem),
                                        cudaMemcpyHostToDevice, b->ctx->stream));
         ABFIT_CUDA(cudaStreamSynchronize(b->ctx->stream));
+        if (b->shape.x_global)
+            if (int rc = b->d_xscratch.ensure((size_t)std::max(b->n_items, 1) * b->shape.n_warps * 20 * 32)) return rc;
         if (int rc = b->d_all.ensure((size_t)b->n_probs * n_starts)) return rc;
         if (int rc = b->d_best.ensure(b->n_probs)) return rc;
         if (int rc = b->d_pred.ensure((size_t)b->total_pairs)) return rc;
@@ -369,7 +401,7 @@ int abfit_batch_run_fit(abfit_batch *b, int32_t max_iters, double sd_tol, uint32
     ABFIT_CUDA(cudaEventRecord(b->ev[0], st));
     if (int rc = launch_fit_starts(st, b->pools, b->d_items.p, b->n_items, b->shape.n_warps, b->d_simplices.p,
                                    b->n_starts, nm, b->d_all.p, b->d_evals_fit.p, b->shape.smem_fit,
-                                   b->shape.d_shared))
+                                   b->shape.d_shared, b->shape.x_global ? b->d_xscratch.p : nullptr))
         return rc;
     ABFIT_CUDA(cudaEventRecord(b->ev[1], st));
     if (int rc = launch_select(st, b->pools, b->n_probs, b->n_starts, b->d_all.p, b->d_best.p, b->d_pred.p,
@@ -538,21 +570,16 @@ int abfit_batch_flops_per_eval(abfit_batch *b, int32_t p, double *flops_out, int
 // ---------------------------------------------------------------------------------------
 // one-shot host-buffer entry points
 // ---------------------------------------------------------------------------------------
-struct BatchGuard {
-    abfit_batch *b = nullptr;
-    ~BatchGuard() { abfit_batch_destroy(b); }
-};
-
 int abfit_fit_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, int32_t n_starts,
                     const double *simplices, int32_t max_iters, double sd_tol, uint32_t flags,
                     abfit_fit *best_out, abfit_fit *all_out, double *pred_out, double *resid_out,
                     int32_t *prob_status_out)
 {
-    BatchGuard g;
-    if (int rc = abfit_batch_create(ctx, probs, n_probs, &g.b)) return rc;
-    if (int rc = abfit_batch_upload_starts(g.b, n_starts, simplices)) return rc;
-    if (int rc = abfit_batch_run_fit(g.b, max_iters, sd_tol, flags)) return rc;
-    return abfit_batch_download_fit(g.b, best_out, all_out, pred_out, resid_out, prob_status_out);
+    abfit_batch *b = nullptr;
+    if (int rc = workspace(ctx, probs, n_probs, &b)) return rc;
+    if (int rc = abfit_batch_upload_starts(b, n_starts, simplices)) return rc;
+    if (int rc = abfit_batch_run_fit(b, max_iters, sd_tol, flags)) return rc;
+    return abfit_batch_download_fit(b, best_out, all_out, pred_out, resid_out, prob_status_out);
 }
 
 int abfit_boot_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, const abfit_fit *best,
@@ -564,20 +591,19 @@ int abfit_boot_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs
         set_error("boot_batch: best, pred and resid are required");
         return ABFIT_ERR_ARG;
     }
-    BatchGuard g;
-    if (int rc = abfit_batch_create(ctx, probs, n_probs, &g.b)) return rc;
-    if (int rc = abfit_batch_upload_boot(g.b, n_boot, best, pred, resid, resample_idx, vary_vertices)) return rc;
-    if (int rc = abfit_batch_run_boot(g.b, max_iters, sd_tol, flags)) return rc;
-    return abfit_batch_download_boot(g.b, rows_out, fits_out);
+    abfit_batch *b = nullptr;
+    if (int rc = workspace(ctx, probs, n_probs, &b)) return rc;
+    if (int rc = abfit_batch_upload_boot(b, n_boot, best, pred, resid, resample_idx, vary_vertices)) return rc;
+    if (int rc = abfit_batch_run_boot(b, max_iters, sd_tol, flags)) return rc;
+    return abfit_batch_download_boot(b, rows_out, fits_out);
 }
 
 int abfit_cost_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, const int32_t *prob_of_theta,
                      const double *theta, int32_t B, double *cost_out, double *lse_out)
 {
     if (!theta || !cost_out || B <= 0) return ABFIT_ERR_ARG;
-    BatchGuard g;
-    if (int rc = abfit_batch_create(ctx, probs, n_probs, &g.b)) return rc;
-    abfit_batch *b = g.b;
+    abfit_batch *b = nullptr;
+    if (int rc = workspace(ctx, probs, n_probs, &b)) return rc;
     // group thetas by problem (stable), 32 per warp
     std::vector<int32_t> order(B);
     std::vector<std::vector<int32_t>> by_prob(n_probs);
@@ -631,16 +657,16 @@ int abfit_model_divergence(abfit_ctx *ctx, const abfit_problem *prob, const doub
                            double *p_uu_out)
 {
     if (!prob || !theta || !dt1t2_out) return ABFIT_ERR_ARG;
-    BatchGuard g;
-    if (int rc = abfit_batch_create(ctx, prob, 1, &g.b)) return rc;
+    abfit_batch *wb = nullptr;
+    if (int rc = workspace(ctx, prob, 1, &wb)) return rc;
     cudaStream_t st = ctx->stream;
     DevBuf<double> d_th, d_dt, d_puu;
     if (int rc = d_th.ensure(4)) return rc;
     if (int rc = d_dt.ensure(prob->n_pairs)) return rc;
     if (int rc = d_puu.ensure(1)) return rc;
     ABFIT_CUDA(cudaMemcpyAsync(d_th.p, theta, 32, cudaMemcpyHostToDevice, st));
-    if (int rc = launch_model_divergence(st, g.b->pools, d_th.p, d_dt.p, d_puu.p,
-                                         smem_need(g.b->hp.probs[0], false, false, 1)))
+    if (int rc = launch_model_divergence(st, wb->pools, d_th.p, d_dt.p, d_puu.p,
+                                         smem_need(wb->hp.probs[0], 0, false, 1)))
         return rc;
     ABFIT_CUDA(cudaMemcpyAsync(dt1t2_out, d_dt.p, (size_t)prob->n_pairs * 8, cudaMemcpyDeviceToHost, st));
     if (p_uu_out) ABFIT_CUDA(cudaMemcpyAsync(p_uu_out, d_puu.p, 8, cudaMemcpyDeviceToHost, st));

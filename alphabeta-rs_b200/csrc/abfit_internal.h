@@ -27,7 +27,8 @@ struct DevicePools {  // device pointers of a compiled batch
 };
 
 // dynamic shared memory of one block working on problem pb (matches carve_and_stage)
-size_t smem_need(const DevProblem &pb, bool with_simplex, bool d_shared, int n_warps);
+// simplex_doubles: 0 (no NM state), 25 (vertices + costs in shared) or 5 (costs only; vertices in global scratch)
+size_t smem_need(const DevProblem &pb, int simplex_doubles, bool d_shared, int n_warps);
 
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what);
@@ -40,7 +41,7 @@ int cuda_fail(cudaError_t e, const char *what);
 // ---- launchers (abfit_kernels.cu) ---------------------------------------------------
 int launch_fit_starts(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_warps,
                       const double *simplices, int n_starts, NMParams nm, abfit_fit *all_out,
-                      unsigned long long *evals_per_prob, size_t smem_bytes, bool d_in_shared);
+                      unsigned long long *evals_per_prob, size_t smem_bytes, bool d_in_shared, double *x_scratch);
 int launch_select(cudaStream_t st, const DevicePools &P, int n_probs, int n_starts, const abfit_fit *all,
                   abfit_fit *best_out, double *pred, double *resid, int32_t *prob_status, size_t smem_bytes,
                   bool d_in_shared);

@@ -24,11 +24,14 @@ namespace abfit {
 
 // ---------------------------------------------------------------------------------
 // shared-memory carve-up
-//   [ per warp: (n_lane + 25) x 32 doubles ] [ D ] [ offs ] [ ops ] [ queue ]
+//   [ per warp: (n_lane + simplex_doubles) x 32 doubles ] [ D ] [ offs ] [ ops ] [ queue ]
+// simplex_doubles: 0 = no Nelder-Mead state, 25 = vertices X (20) + costs C (5) in shared memory,
+// 5 = only the costs in shared memory, the vertices in a global (L2-resident) scratch area — they are
+// touched once per evaluation, and giving up their 5 KB per warp is what lets 16 warps share an SM.
 // ---------------------------------------------------------------------------------
-size_t smem_need(const DevProblem &pb, bool with_simplex, bool d_shared, int n_warps)
+size_t smem_need(const DevProblem &pb, int simplex_doubles, bool d_shared, int n_warps)
 {
-    size_t b = (size_t)n_warps * ((size_t)pb.n_lane + (with_simplex ? 25 : 0)) * 32 * 8;
+    size_t b = (size_t)n_warps * ((size_t)pb.n_lane + (size_t)simplex_doubles) * 32 * 8;
     if (d_shared) b += (((size_t)pb.n_pairs + 1) & ~(size_t)1) * 8;
     b += (size_t)pb.n_offs * 4;
     b += (size_t)pb.n_ops * 8;
@@ -43,18 +46,22 @@ struct Carved {
 };
 
 template <bool D_SHARED>
-__device__ __forceinline__ Carved carve_and_stage(const DevProblem &pb, const DevicePools &P, bool with_simplex)
+__device__ __forceinline__ Carved carve_and_stage(const DevProblem &pb, const DevicePools &P, int simplex_doubles,
+                                                  double *x_scratch = nullptr)
 {
     extern __shared__ double smem[];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, n_warps = nthr >> 5;
-    const int per_warp = (pb.n_lane + (with_simplex ? 25 : 0)) * 32;
+    const int per_warp = (pb.n_lane + simplex_doubles) * 32;
     Carved cv;
     double *mine = smem + (size_t)warp * per_warp;
     cv.ctx.lm = mine;
-    if (with_simplex) {
+    if (simplex_doubles == 25) {
         cv.simplex.X = mine + pb.n_lane * 32 + lane;
         cv.simplex.C = cv.simplex.X + 20 * 32;
+    } else if (simplex_doubles == 5) {
+        cv.simplex.X = x_scratch + ((size_t)blockIdx.x * n_warps + warp) * (20 * 32) + lane;
+        cv.simplex.C = mine + pb.n_lane * 32 + lane;
     } else {
         cv.simplex.X = nullptr;
         cv.simplex.C = nullptr;
@@ -117,16 +124,16 @@ __device__ __forceinline__ int queue_take(int *queue, unsigned m, int lane, int 
 // ---------------------------------------------------------------------------------
 // multi-start Nelder-Mead
 // ---------------------------------------------------------------------------------
-template <bool D_SHARED>
-__global__ void __launch_bounds__(128, 3)
+template <bool D_SHARED, bool X_GLOBAL>
+__global__ void __launch_bounds__(128, X_GLOBAL ? 4 : 3)
 k_fit_starts(DevicePools P, const WorkItem *__restrict__ items, const double *__restrict__ simplices,
              int n_starts, NMParams nm, abfit_fit *__restrict__ all_out,
-             unsigned long long *__restrict__ evals_per_prob)
+             unsigned long long *__restrict__ evals_per_prob, double *x_scratch)
 {
     const int lane = threadIdx.x & 31;
     const WorkItem it = items[blockIdx.x];
     const DevProblem pb = P.probs[it.prob];
-    Carved cv = carve_and_stage<D_SHARED>(pb, P, true);
+    Carved cv = carve_and_stage<D_SHARED>(pb, P, X_GLOBAL ? 5 : 25, x_scratch);
     if (threadIdx.x == 0) *cv.queue = it.first;
     __syncthreads();
     const WarpCtx &c = cv.ctx;
@@ -182,7 +189,7 @@ k_select(DevicePools P, int n_starts, const abfit_fit *__restrict__ all, abfit_f
     const int lane = threadIdx.x;
     const int p = blockIdx.x;
     const DevProblem pb = P.probs[p];
-    Carved cv = carve_and_stage<D_SHARED>(pb, P, false);
+    Carved cv = carve_and_stage<D_SHARED>(pb, P, 0);
     __syncwarp();
     const WarpCtx &c = cv.ctx;
 
@@ -261,7 +268,7 @@ k_fit_boot(DevicePools P, const WorkItem *__restrict__ items, int n_boot, const 
     const int lane = threadIdx.x;
     const WorkItem it = items[blockIdx.x];
     const DevProblem pb = P.probs[it.prob];
-    Carved cv = carve_and_stage<false>(pb, P, true);
+    Carved cv = carve_and_stage<false>(pb, P, 25);
     __syncwarp();
     const WarpCtx &c = cv.ctx;
     const LaneSimplex &S = cv.simplex;
@@ -346,7 +353,7 @@ k_cost_batch(DevicePools P, const WorkItem *__restrict__ items, const double *__
     const int lane = threadIdx.x;
     const WorkItem it = items[blockIdx.x];
     const DevProblem pb = P.probs[it.prob];
-    Carved cv = carve_and_stage<D_SHARED>(pb, P, false);
+    Carved cv = carve_and_stage<D_SHARED>(pb, P, 0);
     __syncwarp();
     const DBroadcast Dat{cv.ctx.D};
     if (lane < it.count) {
@@ -363,7 +370,7 @@ k_model_div(DevicePools P, const double *__restrict__ theta4, double *__restrict
 {
     const int lane = threadIdx.x;
     const DevProblem pb = P.probs[0];
-    Carved cv = carve_and_stage<false>(pb, P, false);
+    Carved cv = carve_and_stage<false>(pb, P, 0);
     __syncwarp();
     const WarpCtx &c = cv.ctx;
     model_divergence(c, lane, theta4[0], theta4[1], theta4[2]);
@@ -412,23 +419,39 @@ static int prep_kernel(K kernel, size_t smem_bytes)
     return 0;
 }
 
+template <bool D_SHARED, bool X_GLOBAL>
+static int launch_fit_starts_t(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_warps,
+                               const double *simplices, int n_starts, NMParams nm, abfit_fit *all_out,
+                               unsigned long long *evals_per_prob, size_t smem_bytes, double *x_scratch)
+{
+    if (int rc = prep_kernel(k_fit_starts<D_SHARED, X_GLOBAL>, smem_bytes)) return rc;
+    if (getenv("ABFIT_DEV_VERBOSE")) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fit_starts<D_SHARED, X_GLOBAL>, 32 * n_warps, smem_bytes);
+        fprintf(stderr, "[abfit] k_fit_starts<D_SHARED=%d,X_GLOBAL=%d>: %d blocks x %d warps, %zu B smem/block, %d blocks/SM\n",
+                (int)D_SHARED, (int)X_GLOBAL, n_items, n_warps, smem_bytes, nb);
+    }
+    k_fit_starts<D_SHARED, X_GLOBAL><<<n_items, 32 * n_warps, smem_bytes, st>>>(P, items, simplices, n_starts, nm,
+                                                                                 all_out, evals_per_prob, x_scratch);
+    ABFIT_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_fit_starts(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_warps,
                       const double *simplices, int n_starts, NMParams nm, abfit_fit *all_out,
-                      unsigned long long *evals_per_prob, size_t smem_bytes, bool d_in_shared)
+                      unsigned long long *evals_per_prob, size_t smem_bytes, bool d_in_shared, double *x_scratch)
 {
     if (n_items <= 0) return 0;
     if (const char *pad = getenv("ABFIT_DEV_SMEM_PAD")) smem_bytes += (size_t)atoi(pad);  // occupancy experiments
-    if (d_in_shared) {
-        if (int rc = prep_kernel(k_fit_starts<true>, smem_bytes)) return rc;
-        k_fit_starts<true><<<n_items, 32 * n_warps, smem_bytes, st>>>(P, items, simplices, n_starts, nm, all_out,
-                                                                      evals_per_prob);
-    } else {
-        if (int rc = prep_kernel(k_fit_starts<false>, smem_bytes)) return rc;
-        k_fit_starts<false><<<n_items, 32 * n_warps, smem_bytes, st>>>(P, items, simplices, n_starts, nm, all_out,
-                                                                       evals_per_prob);
-    }
-    ABFIT_CUDA(cudaGetLastError());
-    return 0;
+    if (d_in_shared)
+        return x_scratch ? launch_fit_starts_t<true, true>(st, P, items, n_items, n_warps, simplices, n_starts, nm, all_out,
+                                                           evals_per_prob, smem_bytes, x_scratch)
+                         : launch_fit_starts_t<true, false>(st, P, items, n_items, n_warps, simplices, n_starts, nm,
+                                                            all_out, evals_per_prob, smem_bytes, x_scratch);
+    return x_scratch ? launch_fit_starts_t<false, true>(st, P, items, n_items, n_warps, simplices, n_starts, nm, all_out,
+                                                        evals_per_prob, smem_bytes, x_scratch)
+                     : launch_fit_starts_t<false, false>(st, P, items, n_items, n_warps, simplices, n_starts, nm, all_out,
+                                                         evals_per_prob, smem_bytes, x_scratch);
 }
 
 int launch_select(cudaStream_t st, const DevicePools &P, int n_probs, int n_starts, const abfit_fit *all,

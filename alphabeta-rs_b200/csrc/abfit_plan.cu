@@ -220,39 +220,50 @@ double nm_var_threshold(double sd_tol)
 
 int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm, int fits_per_prob, LaunchShape &out)
 {
-    auto worst = [&](bool simplex, bool d_shared, int nw) {
+    auto worst = [&](int simplex_doubles, bool d_shared, int nw) {
         size_t m = 0;
-        for (auto &pb : hp.probs) m = std::max(m, smem_need(pb, simplex, d_shared, nw));
+        for (auto &pb : hp.probs) m = std::max(m, smem_need(pb, simplex_doubles, d_shared, nw));
         return m;
     };
-    // multi-start kernel: as many resident warps as shared memory allows (the register file allows 16)
+    // Multi-start kernel: as many resident warps as shared memory and registers allow.  With the
+    // vertices in shared memory the kernel is built for 3 blocks x 4 warps (168 registers); with the
+    // vertices in global scratch for 4 x 4 (128 registers).
     int best_w = -1;
     const int cand_nw[3] = {4, 2, 1};
     const char *force = getenv("ABFIT_DEV_NWARPS");  // tuning experiments only
+    const char *force_x = getenv("ABFIT_DEV_XGLOBAL");
     for (int pass = 0; pass < 2; ++pass) {  // pass 0: D in shared memory; pass 1: D broadcast from L1/L2
-        for (int nw : cand_nw) {
-            if (force && nw != atoi(force)) continue;
-            if (!force && nw > 1 && fits_per_prob < 64 * nw) continue;  // too few fits for a multi-warp block
-            const size_t s = worst(true, pass == 0, nw);
-            if (s > smem_cap) continue;
-            int w = (int)std::min<size_t>(16, (smem_per_sm / (s + 1024)) * (size_t)nw);
-            if (w > best_w) {
-                best_w = w;
-                out.n_warps = nw;
-                out.d_shared = pass == 0;
-                out.smem_fit = s;
+        for (int xg = 0; xg < 2; ++xg) {
+            if (force_x && xg != atoi(force_x)) continue;
+            for (int nw : cand_nw) {
+                if (force && nw != atoi(force)) continue;
+                if (!force && nw > 1 && fits_per_prob < 64 * nw) continue;  // too few fits for a multi-warp block
+                const size_t s = worst(xg ? 5 : 25, pass == 0, nw);
+                if (s > smem_cap) continue;
+                const int reg_warps = xg ? 16 : 12;
+                int w = (int)std::min<size_t>((size_t)reg_warps, (smem_per_sm / (s + 1024)) * (size_t)nw);
+                // measured on the C4 shape: 16 warps with the vertices in L2 are no faster than 12 with them
+                // in shared memory (the kernel is not latency-bound there), so the vertices only move out
+                // when shared memory would otherwise leave fewer than 8 resident warps
+                if (xg ? (best_w < 8 && w > best_w) : (w > best_w)) {
+                    best_w = w;
+                    out.n_warps = nw;
+                    out.d_shared = pass == 0;
+                    out.x_global = xg != 0;
+                    out.smem_fit = s;
+                }
             }
         }
         if (best_w >= 4) break;  // only give up the shared D column when occupancy would collapse
     }
     if (best_w <= 0) {
-        set_error("per-lane model state of one pedigree needs " + std::to_string(worst(true, false, 1)) +
+        set_error("per-lane model state of one pedigree needs " + std::to_string(worst(5, false, 1)) +
                   " B of shared memory (limit " + std::to_string(smem_cap) + "): too many distinct (t0,t1,t2) triples");
         return ABFIT_ERR_TOO_LARGE;
     }
-    out.smem_boot = worst(true, false, 1);
-    out.d_shared_aux = worst(false, true, 1) <= smem_cap / 2;
-    out.smem_aux = worst(false, out.d_shared_aux, 1);
+    out.smem_boot = worst(25, false, 1);
+    out.d_shared_aux = worst(0, true, 1) <= smem_cap / 2;
+    out.smem_aux = worst(0, out.d_shared_aux, 1);
     if (out.smem_boot > smem_cap || out.smem_aux > smem_cap) {
         set_error("pedigree too large for the shared-memory model state");
         return ABFIT_ERR_TOO_LARGE;

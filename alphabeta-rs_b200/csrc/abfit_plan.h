@@ -25,6 +25,7 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp);
 struct LaunchShape {
     int n_warps = 1;        // warps per block of the multi-start kernel
     bool d_shared = true;   // D column staged in shared memory (else broadcast from L1/L2)
+    bool x_global = false;  // simplex vertices in a global scratch area (20 * 32 doubles per warp) instead of shared
     size_t smem_fit = 0;    // k_fit_starts
     size_t smem_boot = 0;   // k_fit_boot (1 warp, D* comes from the scratch tile)
     size_t smem_aux = 0;    // k_select / k_cost_batch / k_model_div (1 warp, no simplex)

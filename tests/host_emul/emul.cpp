@@ -20,9 +20,9 @@ namespace abfit {
 static std::string g_err;
 void set_error(const std::string &m) { g_err = m; }
 int cuda_fail(cudaError_t, const char *) { return ABFIT_ERR_CUDA; }
-size_t smem_need(const DevProblem &pb, bool with_simplex, bool d_shared, int n_warps)
+size_t smem_need(const DevProblem &pb, int simplex_doubles, bool d_shared, int n_warps)
 {
-    size_t b = (size_t)n_warps * ((size_t)pb.n_lane + (with_simplex ? 25 : 0)) * 32 * 8;
+    size_t b = (size_t)n_warps * ((size_t)pb.n_lane + (size_t)simplex_doubles) * 32 * 8;
     if (d_shared) b += (((size_t)pb.n_pairs + 1) & ~(size_t)1) * 8;
     b += (size_t)pb.n_offs * 4 + (size_t)pb.n_ops * 8 + 16;
     return (b + 15) & ~(size_t)15;
@@ -124,7 +124,7 @@ int emul_plan_stats(const abfit_problem *pb, int32_t out[6])
     out[2] = 0;
     out[3] = hp.probs[0].tmax;
     out[4] = hp.n_triples[0];
-    out[5] = (int32_t)smem_need(hp.probs[0], true, true, 1);
+    out[5] = (int32_t)smem_need(hp.probs[0], 25, true, 1);
     return 0;
 }
 }
