@@ -13,8 +13,10 @@ import fails, and without a CUDA device every compute call raises ``AbfitError``
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
+import weakref
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -215,6 +217,19 @@ class FitResult:
     status: np.ndarray  # int32 [n_probs]
 
 
+_live_contexts = weakref.WeakSet()
+
+
+@atexit.register
+def _close_all():
+    # release device objects while the CUDA runtime is still loaded (not from __del__ during interpreter teardown)
+    for c in list(_live_contexts):
+        try:
+            c.close()
+        except Exception:
+            pass
+
+
 class Context:
     """One CUDA device + stream (abfit_ctx)."""
 
@@ -223,9 +238,14 @@ class Context:
         _check(_lib.abfit_ctx_create(device, C.byref(h)))
         self._h = h
         self.device = device
+        self._batches = weakref.WeakSet()
+        _live_contexts.add(self)
 
     def close(self):
+        """destroys the batches created on this context first (they hold device buffers and a pointer to it)"""
         if getattr(self, "_h", None):
+            for b in list(self._batches):
+                b.close()
             _lib.abfit_ctx_destroy(self._h)
             self._h = None
 
@@ -371,13 +391,14 @@ class Batch:
         h = C.c_void_p()
         _check(_lib.abfit_batch_create(ctx._h, arr, self.n_probs, C.byref(h)))
         self._h = h
+        ctx._batches.add(self)
         self.n_starts = 0
         self.n_boot = 0
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
             _lib.abfit_batch_destroy(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:

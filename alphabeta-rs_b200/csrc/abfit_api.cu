@@ -89,6 +89,7 @@ struct abfit_batch {
     DevBuf<int32_t> d_idx;
     DevBuf<double> d_vary, d_scratch, d_rows;
     DevBuf<abfit_fit> d_bootfits;
+    DevBuf<int> d_booterr;
     DevBuf<WorkItem> d_boot_items;
     int n_boot_items = 0;
     bool boot_uploaded = false, boot_done = false;
@@ -473,7 +474,9 @@ int abfit_batch_upload_boot(abfit_batch *b, int32_t n_boot, const abfit_fit *bes
             ABFIT_CUDA(cudaMemcpyAsync(b->d_boot_items.p, items.data(), items.size() * sizeof(WorkItem),
                                        cudaMemcpyHostToDevice, st));
         ABFIT_CUDA(cudaStreamSynchronize(st));
-        if (int rc = b->d_scratch.ensure((size_t)std::max(b->n_boot_items, 1) * b->hp.max_pairs * 32)) return rc;
+        // stored-D* tile: N x 32 doubles per block; index tile: ceil(N/4) x 32 x 8 bytes (+ one tile of slack for
+        // the L1 prefetch that runs 4 groups ahead)
+        if (int rc = b->d_scratch.ensure((size_t)(std::max(b->n_boot_items, 1) + 1) * b->hp.max_pairs * 32)) return rc;
         if (int rc = b->d_rows.ensure((size_t)b->n_probs * n_boot * 7)) return rc;
         if (int rc = b->d_bootfits.ensure((size_t)b->n_probs * n_boot)) return rc;
     }
@@ -495,7 +498,15 @@ int abfit_batch_run_boot(abfit_batch *b, int32_t max_iters, double sd_tol, uint3
     ABFIT_CUDA(cudaMemsetAsync(b->d_bootfits.p, 0xFF, (size_t)b->n_probs * b->n_boot * sizeof(abfit_fit), st));
     ABFIT_CUDA(cudaMemsetAsync(b->d_evals_boot.p, 0, (size_t)b->n_probs * 8, st));
     ABFIT_CUDA(cudaEventRecord(b->ev[3], st));
-    if (int rc = launch_fit_boot(st, b->pools, b->d_boot_items.p, b->n_boot_items, b->n_boot, b->d_best.p,
+    if (int rc = b->d_booterr.ensure(1)) return rc;
+    ABFIT_CUDA(cudaMemsetAsync(b->d_booterr.p, 0, sizeof(int), st));
+    if (b->shape.smem_boot_gather) {
+        if (int rc = launch_fit_boot_gather(st, b->pools, b->d_boot_items.p, b->n_boot_items, b->n_boot, b->d_best.p,
+                                            b->d_pred.p, b->d_resid.p, b->d_idx.p, b->d_vary.p, b->d_scratch.p,
+                                            (int64_t)((b->hp.max_pairs + 3) / 4) * 32, nm, b->d_rows.p, b->d_bootfits.p,
+                                            b->d_evals_boot.p, b->shape.smem_boot_gather, b->d_booterr.p))
+            return rc;
+    } else if (int rc = launch_fit_boot(st, b->pools, b->d_boot_items.p, b->n_boot_items, b->n_boot, b->d_best.p,
                                  b->d_pred.p, b->d_resid.p, b->d_idx.p, b->d_vary.p, b->d_scratch.p,
                                  (int64_t)b->hp.max_pairs * 32, nm, b->d_rows.p, b->d_bootfits.p,
                                  b->d_evals_boot.p, b->shape.smem_boot))
@@ -520,7 +531,13 @@ int abfit_batch_download_boot(abfit_batch *b, double *rows_out, abfit_fit *fits_
     if (fits_out)
         ABFIT_CUDA(cudaMemcpyAsync(fits_out, b->d_bootfits.p, (size_t)b->n_probs * b->n_boot * sizeof(abfit_fit),
                                    cudaMemcpyDeviceToHost, st));
+    int err = 0;
+    ABFIT_CUDA(cudaMemcpyAsync(&err, b->d_booterr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     ABFIT_CUDA(cudaStreamSynchronize(st));
+    if (err) {
+        set_error("resample_idx contains an index outside [0, n_pairs)");
+        return ABFIT_ERR_ARG;
+    }
     return 0;
 }
 

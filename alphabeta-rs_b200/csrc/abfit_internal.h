@@ -49,6 +49,13 @@ int launch_fit_boot(cudaStream_t st, const DevicePools &P, const WorkItem *items
                     const abfit_fit *best, const double *pred, const double *resid, const int32_t *resample_idx,
                     const double *vary, double *dstar_scratch, int64_t scratch_stride, NMParams nm,
                     double *rows_out, abfit_fit *fits_out, unsigned long long *evals_per_prob, size_t smem_bytes);
+// index-tile variant (n_pairs <= 8191): idx_scratch holds scratch_stride uint2 per block, scratch_stride >= 32 * ceil(N/4)
+size_t smem_need_boot_gather(const DevProblem &pb);
+int launch_fit_boot_gather(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_boot,
+                           const abfit_fit *best, const double *pred, const double *resid, const int32_t *resample_idx,
+                           const double *vary, void *idx_scratch, int64_t scratch_stride, NMParams nm,
+                           double *rows_out, abfit_fit *fits_out, unsigned long long *evals_per_prob, size_t smem_bytes,
+                           int *err_flag);
 int launch_cost_batch(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items,
                       const double *theta, double *cost_out, double *lse_out, size_t smem_bytes, bool d_in_shared);
 int launch_model_divergence(cudaStream_t st, const DevicePools &P, const double *theta4, double *dt_out,

@@ -37,30 +37,33 @@ constexpr unsigned FULL = 0xffffffffu;
 // Per-lane storage lives in shared memory as lane_mem[index * 32 + lane].
 // ---------------------------------------------------------------------------------
 enum MicroOp : uint32_t {
-    OP_STEP = 0,     // a = n                       R <- R.G, n times (matrix_power's chain, :27-29)
+    OP_NOP = 0,      //                             nothing (carries chain steps; also the end sentinel)
     OP_STORE_M = 1,  // a = dst                     lane_mem[dst..dst+8]  <- R  (= G^k)
     OP_CALC_S = 2,   // a = dst                     lane_mem[dst..dst+2]  <- sv0^T . R          (src/divergence.rs:55)
     // dreg <- conditional divergences of rows UU,UM,MM for A = G^(t1-t0), B = G^(t2-t0) (:57-87).  The
-    // event fires at k = max(t1-t0, t2-t0), so one operand is always the chain's current power R; the
-    // variants name where the other one lives (no register copies, no source decoding):
+    // op fires at k = max(t1-t0, t2-t0), so one operand is always the chain's current power R; the
+    // variants name where the other one lives (no register copies, no source decoding).  Fused tail:
+    //   c != NONE: lane_mem[c..c+2] <- dreg (kept for a triple whose t0 comes later)
+    //   b != NONE: lane_mem[b] <- sv0 . dreg  (the t0 == 0 triple of this exponent pair, :89)
     OP_D_CC = 3,     //                             A = R,            B = R
     OP_D_MC = 4,     // a = src                     A = lane_mem[src], B = R
     OP_D_CM = 5,     // a = src                     A = R,            B = lane_mem[src]
     OP_D_GC = 6,     //                             A = G,            B = R
     OP_D_CG = 7,     //                             A = R,            B = G
-    OP_D_GEN = 10,   // a = A source, b = B source  an identity operand (t1 == t0 or t2 == t0) or anything else
-    OP_STORE_D = 11, // a = dst                     lane_mem[dst..dst+2]  <- dreg
-    OP_LOAD_D = 12,  // a = src                     dreg <- lane_mem[src..src+2]
-    OP_DT0 = 13,     // a = dst                     lane_mem[dst] <- sv0 . dreg   (t0 == 0: s = sv0^T . G^0)
-    OP_DT = 14       // a = dst, b = s source       lane_mem[dst] <- s0*d_uu + s1*d_um + s2*d_mm (:89)
+    OP_D_GEN = 8,    // a = A source, b = B source  identity operands (t1 == t0 or t2 == t0); no fused tail
+    OP_STORE_D = 9,  // a = dst                     lane_mem[dst..dst+2]  <- dreg          (after OP_D_GEN)
+    OP_DT0 = 10,     // a = dst                     lane_mem[dst] <- sv0 . dreg            (after OP_D_GEN)
+    OP_DT = 11,      // a = dst, b = s source       lane_mem[dst] <- s0*d_uu + s1*d_um + s2*d_mm (:89)
+    OP_LDT = 12      // a = dst, b = s source, c = d source   dreg <- lane_mem[c..c+2], then OP_DT
 };
 // operand sources (16 bit); anything below SRC_SPECIAL is a lane_mem index
 constexpr uint32_t SRC_SPECIAL = 0xfff0;
 constexpr uint32_t SRC_CUR = 0xfff0;    // the chain's current power R = G^k
 constexpr uint32_t SRC_G = 0xfff1;      // G itself (exponent 1), always in registers
 constexpr uint32_t SRC_IDENT = 0xfff2;  // G^0 (src/divergence.rs:21-24)
-constexpr uint32_t SRC_SV0 = 0xfff3;    // sv0^T . G^0
-// op word: opcode | a << 8 (16 bit) ; second word: b (16 bit)
+constexpr uint32_t OP_NONE = 0xffff;    // absent b / c field
+// op word: x = opcode | n_step << 8 | a << 16,  y = b | c << 16.
+// n_step: chain steps R <- R.G (matrix_power's loop, :27-29) executed BEFORE the op.
 struct OpWord {
     uint32_t x, y;
 };
@@ -210,14 +213,16 @@ __device__ __forceinline__ void model_divergence(const WarpCtx &c, int lane, dou
     double sid[3];
     vec_mat(sv0, sv1, sv2, I, sid);
 
-    for (int i = 0; i < c.n_ops; ++i) {
-        const OpWord w = c.ops[i];
-        const uint32_t op = w.x & 0xff, a = w.x >> 8, b = w.y;
+    // The program ends with an OP_NOP sentinel, so the next word can always be fetched while the
+    // current op executes (the decode no longer waits on its own shared-memory load).
+    OpWord nxt = c.ops[0];
+    for (int i = 1; i < c.n_ops; ++i) {
+        const OpWord w = nxt;
+        nxt = c.ops[i];
+        const uint32_t op = w.x & 0xff, a = w.x >> 16, b = w.y & 0xffff, cc = w.y >> 16;
+        for (uint32_t s = (w.x >> 8) & 0xff; s > 0; --s) mat3_step(R, G);
+        bool d_tail = false;
         switch (op) {
-            case OP_STEP: {
-                for (uint32_t s = 0; s < a; ++s) mat3_step(R, G);
-                break;
-            }
             case OP_STORE_M: {
                 double *p = lml + a * 32;
 #pragma unroll
@@ -231,21 +236,23 @@ __device__ __forceinline__ void model_divergence(const WarpCtx &c, int lane, dou
                 p[0] = s[0]; p[32] = s[1]; p[64] = s[2];
                 break;
             }
-            case OP_D_CC: cond_div3(R, R, dreg); break;
+            case OP_D_CC: cond_div3(R, R, dreg); d_tail = true; break;
             case OP_D_MC: {
                 double M[9];
                 load_matrix(lml, a, M);
                 cond_div3(M, R, dreg);
+                d_tail = true;
                 break;
             }
             case OP_D_CM: {
                 double M[9];
                 load_matrix(lml, a, M);
                 cond_div3(R, M, dreg);
+                d_tail = true;
                 break;
             }
-            case OP_D_GC: cond_div3(G, R, dreg); break;
-            case OP_D_CG: cond_div3(R, G, dreg); break;
+            case OP_D_GC: cond_div3(G, R, dreg); d_tail = true; break;
+            case OP_D_CG: cond_div3(R, G, dreg); d_tail = true; break;
             case OP_D_GEN: {  // identity operands (t1 == t0 or t2 == t0) and anything unusual
                 double A[9], B[9];
                 fetch_matrix(a, lml, R, G, A);
@@ -258,14 +265,14 @@ __device__ __forceinline__ void model_divergence(const WarpCtx &c, int lane, dou
                 p[0] = dreg[0]; p[32] = dreg[1]; p[64] = dreg[2];
                 break;
             }
-            case OP_LOAD_D: {
-                const double *p = lml + a * 32;
-                dreg[0] = p[0]; dreg[1] = p[32]; dreg[2] = p[64];
-                break;
-            }
             case OP_DT0:
                 lml[a * 32] = sid[0] * dreg[0] + sid[1] * dreg[1] + sid[2] * dreg[2];  // src/divergence.rs:89
                 break;
+            case OP_LDT: {
+                const double *p = lml + cc * 32;
+                dreg[0] = p[0]; dreg[1] = p[32]; dreg[2] = p[64];
+            }
+            // fall through
             case OP_DT: {
                 const double *p = lml + b * 32;
                 const double s0 = p[0], s1 = p[32], s2 = p[64];
@@ -273,6 +280,13 @@ __device__ __forceinline__ void model_divergence(const WarpCtx &c, int lane, dou
                 break;
             }
             default: break;
+        }
+        if (d_tail) {
+            if (cc != OP_NONE) {
+                double *p = lml + cc * 32;
+                p[0] = dreg[0]; p[32] = dreg[1]; p[64] = dreg[2];
+            }
+            if (b != OP_NONE) lml[b * 32] = sid[0] * dreg[0] + sid[1] * dreg[1] + sid[2] * dreg[2];  // :89
         }
     }
 }
@@ -298,6 +312,37 @@ struct DLaneColumn {
         for (int q = 0; q < 4; ++q) d[q] = __ldcg(col + (size_t)(i + q) * 32);
     }
     __device__ __forceinline__ double operator()(int i) const { return __ldcg(col + (size_t)i * 32); }
+};
+
+// Bootstrap replicate (src/boot_model.rs:43-57): D*_i = pred_i + resid[idx_i], rebuilt on the fly from
+// the replicate's resample indices.  Only the indices are per-lane data: four u16 per lane and group of
+// four pairs in one coalesced 8-byte load from an L2-resident tile (a quarter of the bytes of a stored D*
+// column); pred is a shared-memory broadcast and resid a shared-memory gather.
+struct DGather {
+    const uint2 *tile;    // [group][32] (lane folded in): four u16 byte offsets into resid
+    const double *pred;   // shared, 16-byte aligned
+    const char *resid;    // shared, at the start of dynamic shared memory
+    __device__ __forceinline__ void load4(int i, double d[4]) const
+    {
+        const uint2 *p = tile + (size_t)(i >> 2) * 32;
+#ifdef __CUDA_ARCH__
+        // the tile streams from L2 once per evaluation: pull the line 4 groups ahead into L1
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 4 * 32));
+#endif
+        const uint2 w = *p;
+        const double2 a = *reinterpret_cast<const double2 *>(pred + i);
+        const double2 b = *reinterpret_cast<const double2 *>(pred + i + 2);
+        d[0] = a.x + *reinterpret_cast<const double *>(resid + (w.x & 0xffffu));
+        d[1] = a.y + *reinterpret_cast<const double *>(resid + (w.x >> 16));
+        d[2] = b.x + *reinterpret_cast<const double *>(resid + (w.y & 0xffffu));
+        d[3] = b.y + *reinterpret_cast<const double *>(resid + (w.y >> 16));
+    }
+    __device__ __forceinline__ double operator()(int i) const
+    {
+        const uint2 w = tile[(size_t)(i >> 2) * 32];
+        const uint32_t h = (i & 2) ? w.y : w.x;
+        return pred[i] + *reinterpret_cast<const double *>(resid + ((i & 1) ? (h >> 16) : (h & 0xffffu)));
+    }
 };
 
 // Objective (src/structs.rs:191-217).  penalty=false gives the penalty-free LSE of

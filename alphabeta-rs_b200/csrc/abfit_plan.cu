@@ -19,11 +19,11 @@ static inline int as_i8(double x)
     return (int)x;
 }
 
-static inline OpWord mk_op(uint32_t op, uint32_t a, uint32_t b = 0)
+static inline OpWord mk_op(uint32_t op, uint32_t a = 0, uint32_t b = OP_NONE, uint32_t c = OP_NONE)
 {
     OpWord w;
-    w.x = op | (a << 8);
-    w.y = b;
+    w.x = op | (a << 16);  // n_step (bits 8..15) is filled in when the program is flattened
+    w.y = b | (c << 16);
     return w;
 }
 
@@ -134,57 +134,57 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
             if (e == 1) return SRC_G;
             return idx_M[e];
         };
-        auto op_d = [&](int a, int b, int k) -> OpWord {
+        // the D op of exponent pair (a, b) with its fused tail: dt0 = dt slot of the t0 == 0 triple,
+        // keep = slot of the d-vector when a later t0 needs it
+        auto op_d = [&](int a, int b, int k, uint32_t dt0, uint32_t keep, std::vector<OpWord> &out) {
             const uint32_t sa = src_of(a, k), sb = src_of(b, k);
-            if (sa == SRC_CUR && sb == SRC_CUR) return mk_op(OP_D_CC, 0);
+            if (sa == SRC_CUR && sb == SRC_CUR) return out.push_back(mk_op(OP_D_CC, 0, dt0, keep));
             if (sb == SRC_CUR) {
-                if (sa == SRC_G) return mk_op(OP_D_GC, 0);
-                if (sa < SRC_SPECIAL) return mk_op(OP_D_MC, sa);
+                if (sa == SRC_G) return out.push_back(mk_op(OP_D_GC, 0, dt0, keep));
+                if (sa < SRC_SPECIAL) return out.push_back(mk_op(OP_D_MC, sa, dt0, keep));
             } else if (sa == SRC_CUR) {
-                if (sb == SRC_G) return mk_op(OP_D_CG, 0);
-                if (sb < SRC_SPECIAL) return mk_op(OP_D_CM, sb);
+                if (sb == SRC_G) return out.push_back(mk_op(OP_D_CG, 0, dt0, keep));
+                if (sb < SRC_SPECIAL) return out.push_back(mk_op(OP_D_CM, sb, dt0, keep));
             }
-            return mk_op(OP_D_GEN, sa, sb);
+            out.push_back(mk_op(OP_D_GEN, sa, sb));
+            if (keep != OP_NONE) out.push_back(mk_op(OP_STORE_D, keep));
+            if (dt0 != OP_NONE) out.push_back(mk_op(OP_DT0, dt0));
         };
         for (auto &kv : by_ab) {
             const int a = kv.first.first, b = kv.first.second, k = std::max(a, b);
             Ev &ev = evs[k];
-            ev.body.push_back(op_d(a, b, k));
+            uint32_t dt0 = OP_NONE;
+            for (auto &t : kv.second)
+                if (std::get<0>(t) == 0) dt0 = dt_base + (uint32_t)tri_id[t];
+            op_d(a, b, k, dt0, idx_D.count(kv.first) ? idx_D[kv.first] : OP_NONE, ev.body);
             for (auto &t : kv.second) {
                 const int t0 = std::get<0>(t);
-                const uint32_t dst = dt_base + (uint32_t)tri_id[t];
-                if (t0 == 0)
-                    ev.body.push_back(mk_op(OP_DT0, dst));
-                else if (t0 <= k)
-                    ev.body.push_back(mk_op(OP_DT, dst, idx_S[t0]));
+                if (t0 > 0 && t0 <= k) ev.body.push_back(mk_op(OP_DT, dt_base + (uint32_t)tri_id[t], idx_S[t0]));
             }
-            if (idx_D.count(kv.first)) ev.body.push_back(mk_op(OP_STORE_D, idx_D[kv.first]));
         }
         for (auto &kv : by_ab) {  // triples whose t0 comes after their exponent pair
             const int k = std::max(kv.first.first, kv.first.second);
-            std::map<int, std::vector<Tri>> late;
             for (auto &t : kv.second)
-                if (std::get<0>(t) > k) late[std::get<0>(t)].push_back(t);
-            for (auto &lv : late) {
-                Ev &ev = evs[lv.first];
-                ev.tail.push_back(mk_op(OP_LOAD_D, idx_D[kv.first]));
-                for (auto &t : lv.second)
-                    ev.tail.push_back(mk_op(OP_DT, dt_base + (uint32_t)tri_id[t], idx_S[lv.first]));
-            }
+                if (std::get<0>(t) > k)
+                    evs[std::get<0>(t)].tail.push_back(
+                        mk_op(OP_LDT, dt_base + (uint32_t)tri_id[t], idx_S[std::get<0>(t)], idx_D[kv.first]));
         }
-        // flatten: [exponent-0 ops] STEP ... ops(k1) STEP ... ops(k2) ...; the chain starts at R = G^1
+        // flatten; the chain starts at R = G^1 and the steps up to an exponent ride on its first op
         int tmax = 0, cur_k = 1;
         for (auto &kv : evs) {
             const int k = kv.first;
-            if (k > cur_k) {
-                hp.ops.push_back(mk_op(OP_STEP, (uint32_t)(k - cur_k)));
-                cur_k = k;
-            }
+            const size_t first = hp.ops.size();
             for (auto &o : kv.second.head) hp.ops.push_back(o);
             for (auto &o : kv.second.body) hp.ops.push_back(o);
             for (auto &o : kv.second.tail) hp.ops.push_back(o);
+            if (hp.ops.size() == first) continue;
+            if (k > cur_k) {
+                hp.ops[first].x |= (uint32_t)(k - cur_k) << 8;  // <= 127 by the time validation above
+                cur_k = k;
+            }
             tmax = std::max(tmax, k);
         }
+        hp.ops.push_back(mk_op(OP_NOP));  // end sentinel: the interpreter prefetches one word ahead
         dp.n_ops = (int32_t)(hp.ops.size() - (size_t)dp.ops_off);
         dp.pad_ = 0;
         dp.n_lane = (int32_t)n_lane;
@@ -262,6 +262,12 @@ int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm,
         return ABFIT_ERR_TOO_LARGE;
     }
     out.smem_boot = worst(25, false, 1);
+    out.smem_boot_gather = 0;
+    if (hp.max_pairs <= 8191) {  // u16 byte offsets into resid
+        size_t m = 0;
+        for (auto &pb : hp.probs) m = std::max(m, smem_need_boot_gather(pb));
+        if (m <= smem_cap / 4 && !getenv("ABFIT_DEV_BOOT_TILE")) out.smem_boot_gather = m;  // else: stored-D* kernel
+    }
     out.d_shared_aux = worst(0, true, 1) <= smem_cap / 2;
     out.smem_aux = worst(0, out.d_shared_aux, 1);
     if (out.smem_boot > smem_cap || out.smem_aux > smem_cap) {

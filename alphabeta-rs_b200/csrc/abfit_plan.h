@@ -28,6 +28,7 @@ struct LaunchShape {
     bool x_global = false;  // simplex vertices in a global scratch area (20 * 32 doubles per warp) instead of shared
     size_t smem_fit = 0;    // k_fit_starts
     size_t smem_boot = 0;   // k_fit_boot (1 warp, D* comes from the scratch tile)
+    size_t smem_boot_gather = 0;  // k_fit_boot_gather (1 warp + pred/resid of the window), 0 = not usable
     size_t smem_aux = 0;    // k_select / k_cost_batch / k_model_div (1 warp, no simplex)
     bool d_shared_aux = true;
 };

@@ -1,0 +1,120 @@
+"""The device-side model / objective / Nelder-Mead headers (alphabeta-rs_b200/csrc/abfit_model.cuh,
+abfit_nm.cuh) and the host pedigree compiler (abfit_plan.cu), built FOR THE CPU (tests/host_emul) and
+checked bit for bit against the oracle.  No GPU needed: this is how the `-m "not gpu"` suite covers
+the micro-op compiler, the software-pipelined pair loop and the NM state machine, and how a compiler
+problem on the GPU side is told apart from a source problem."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+EMUL_DIR = os.path.join(ROOT, "tests", "host_emul")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    subprocess.check_call(["make", "-C", EMUL_DIR, "-s", "-B", "libemul.so"])
+    return C.CDLL(os.path.join(EMUL_DIR, "libemul.so"))
+
+
+def emul_cost(emul, ab, ped, p0uu, eqp, w, theta):
+    arr = ab._pack_problems([ab.Problem(ped, p0uu, eqp, w)])
+    theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, 4)
+    cost, lse = np.empty(len(theta)), np.empty(len(theta))
+    rc = emul.emul_cost(arr, theta.ctypes.data_as(C.c_void_p), len(theta), cost.ctypes.data_as(C.c_void_p),
+                        lse.ctypes.data_as(C.c_void_p))
+    assert rc == 0, rc
+    return cost, lse
+
+
+def emul_fit(emul, ab, ped, p0uu, sx, max_iters=10000, flags=0, dstar=None):
+    arr = ab._pack_problems([ab.Problem(ped, p0uu, p0uu, 1.0)])
+    sx = np.ascontiguousarray(sx, dtype=np.float64)
+    n = sx.size // 20
+    out = np.zeros(n, dtype=ab.FIT_DTYPE)
+    dp = None if dstar is None else np.ascontiguousarray(dstar, dtype=np.float64).ctypes.data_as(C.c_void_p)
+    rc = emul.emul_fit(arr, sx.ctypes.data_as(C.c_void_p), n, dp, max_iters, C.c_double(ab.DBL_EPSILON), flags,
+                       out.ctypes.data_as(C.c_void_p))
+    assert rc == 0, rc
+    return out
+
+
+def random_pedigree(rng, n_pairs, tmax, style):
+    """time structures that exercise every micro-op: identity operands (t1 == t0, t2 == t0, all equal),
+    exponent 1 (G itself), stored powers, deferred d-vectors (t0 larger than both exponents)."""
+    rows = []
+    for _ in range(n_pairs):
+        if style == "lineage":  # (0, a, b), a <= b: the usual mutation-accumulation pedigree
+            a, b = sorted(rng.integers(0, tmax + 1, 2))
+            t0 = 0
+        elif style == "sibling":  # common ancestor late in the pedigree
+            t0 = int(rng.integers(0, tmax))
+            a, b = t0 + rng.integers(0, 3, 2)
+        else:  # anything valid, unsorted t1 / t2
+            t0 = int(rng.integers(0, tmax + 1))
+            a, b = rng.integers(t0, tmax + 1, 2)
+        rows.append([t0, a, b, rng.uniform(0, 0.3)])
+    return np.array(rows, dtype=np.float64)
+
+
+@pytest.mark.parametrize("style", ["lineage", "sibling", "any"])
+@pytest.mark.parametrize("tmax", [1, 4, 33, 127])
+def test_compiled_program_cost_is_bit_exact(emul, ab, oracle, style, tmax):
+    rng = np.random.default_rng(hash((style, tmax)) % 2**32)
+    for n_pairs in (1, 3, 4, 5, 37, 120):
+        ped = random_pedigree(rng, n_pairs, tmax, style)
+        B = 40
+        theta = np.stack([10 ** rng.uniform(-7, -1.5, B), 10 ** rng.uniform(-7, -1.5, B), rng.uniform(-0.1, 0.3, B),
+                          rng.uniform(0, 0.1, B)], axis=1)
+        theta[3] = [-2e-4, 3e-3, -0.2, 0.01]
+        cost, lse = emul_cost(emul, ab, ped, 0.8, 0.7, 1.3, theta)
+        pb = oracle.Problem(ped, 0.8, 0.7, 1.3)
+        for i in range(B):
+            assert cost[i] == oracle.cost(pb, theta[i]), (style, tmax, n_pairs, i)
+            assert lse[i] == oracle.lse(pb, theta[i], flags=oracle.FAST_DIVERGENCE), (style, tmax, n_pairs, i)
+
+
+def test_golden_cost_kat_through_the_device_headers(emul, ab, oracle):
+    ped = oracle.load_pedigree_file(os.path.join(GOLDEN, "pedigree.txt"))
+    cost, _ = emul_cost(emul, ab, ped, 0.75, 0.5, 0.7, [[0.0001179555, 0.0001180614, 0.03693534, 0.003023981]])
+    assert cost[0] == 0.0006700888539608879  # src/structs.rs:233
+
+
+@pytest.mark.parametrize("flags", [0, 1, 2])
+def test_nelder_mead_state_machine_matches_oracle(emul, ab, oracle, flags):
+    """flags: 0 = argmin 0.8.1 with stall early exit, 1 = shrink on failed contraction, 2 = literal (no early exit)"""
+    ped = oracle.load_pedigree_file(os.path.join(GOLDEN, "pedigree.txt"))
+    ped6 = np.loadtxt(os.path.join(GOLDEN, "pedigree_generated.txt"), skiprows=1)
+    max_iters = 400 if flags == 2 else 10000
+    oflags = oracle.FAST_DIVERGENCE | {0: oracle.EARLY_EXIT_ON_STALL, 1: oracle.SHRINK_ON_FAILED_CONTRACTION, 2: 0}[flags]
+    for p, u in ((ped, 0.8), (ped6, 0.655)):
+        sx = ab.gen_start_simplices(7, 3, 24, float(p[:, 3].max()))
+        g = emul_fit(emul, ab, p, u, sx, max_iters=max_iters, flags=flags)
+        rc, best, allr, pred, resid = oracle.ab_neutral(oracle.Problem(p, u, u, 1.0), sx, max_iters=max_iters, flags=oflags,
+                                                        n_threads=4)
+        assert rc == 0
+        for f in ("theta", "cost", "lse", "iters", "evals", "status"):
+            assert np.array_equal(g[f], allr[f]), (flags, f)
+
+
+def test_bootstrap_column_access_matches_oracle(emul, ab, oracle):
+    """per-lane D* columns (the bootstrap kernel's access pattern) through the same objective"""
+    ped = oracle.load_pedigree_file(os.path.join(GOLDEN, "pedigree.txt"))
+    u = 0.8
+    sx = ab.gen_start_simplices(1, 0, 16, float(ped[:, 3].max()))
+    rc, best, _, pred, resid = oracle.ab_neutral(oracle.Problem(ped, u, u, 1.0), sx,
+                                                 flags=oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, n_threads=4)
+    n_boot = 12
+    idx = ab.gen_resample_idx(5, 0, n_boot, len(ped))
+    vary = ab.gen_vary_vertices(5, 0, n_boot, best["theta"])
+    dstar = pred[None, :] + resid[idx]
+    simplices = np.concatenate([np.broadcast_to(best["theta"], (n_boot, 1, 4)), vary], axis=1)
+    g = emul_fit(emul, ab, ped, u, simplices, max_iters=1000, dstar=dstar)
+    rc, rows, fits = oracle.boot_model(oracle.Problem(ped, u, u, 1.0), best["theta"], pred, resid, idx, vary,
+                                       flags=oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, n_threads=4)
+    assert rc == 0
+    assert np.array_equal(g["theta"], fits["theta"]) and np.array_equal(g["evals"], fits["evals"])
