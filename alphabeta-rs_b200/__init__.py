@@ -105,6 +105,8 @@ def _load() -> C.CDLL:
         "abfit_batch_timing": (C.c_int, [vp, vp, vp, C.POINTER(i32)]),
         "abfit_batch_flops_per_eval": (C.c_int, [vp, i32, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i32)]),
         "abfit_analyze": (C.c_int, [vp, i32, vp]),
+        "abfit_window_counts": (C.c_int, [vp, vp]),
+        "abfit_place_sites": (C.c_int, [vp, i32, vp, i64, vp, vp, vp, i64, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
@@ -121,7 +123,7 @@ EXPORTED_SYMBOLS = (
     "abfit_model_divergence abfit_fit_batch abfit_boot_batch abfit_divergence abfit_batch_create "
     "abfit_batch_destroy abfit_batch_upload_starts abfit_batch_run_fit abfit_batch_download_fit "
     "abfit_batch_upload_boot abfit_batch_run_boot abfit_batch_download_boot abfit_batch_sync "
-    "abfit_batch_timing abfit_batch_flops_per_eval abfit_analyze"
+    "abfit_batch_timing abfit_batch_flops_per_eval abfit_analyze abfit_window_counts abfit_place_sites"
 ).split()
 
 
@@ -500,3 +502,64 @@ def analyze(rows) -> np.ndarray:
     out = np.empty(32)
     _check(_lib.abfit_analyze(_ptr(rows), rows.shape[0], _ptr(out)))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# site -> window assignment (host side of the metaprofile path)
+# ---------------------------------------------------------------------------------------------
+GENE_DTYPE = np.dtype([("chromosome", "<i4"), ("start", "<u4"), ("end", "<u4"), ("strand", "<i4")])
+SITE_DTYPE = GENE_DTYPE  # same layout: chromosome, start, end, strand (+1 / -1 / 0 = '*')
+
+
+class _WindowArgs(C.Structure):
+    _fields_ = [("window_size", C.c_uint32), ("window_step", C.c_uint32), ("cutoff", C.c_uint32),
+                ("max_gene_length", C.c_uint32), ("absolute", C.c_int32), ("cutoff_gene_length", C.c_int32)]
+
+
+def _window_args(window_size, window_step, cutoff, max_gene_length, absolute, cutoff_gene_length):
+    return _WindowArgs(window_size, window_step, cutoff, max_gene_length, int(bool(absolute)), int(bool(cutoff_gene_length)))
+
+
+def window_counts(window_size=5, window_step=0, cutoff=2048, max_gene_length=100, absolute=False,
+                  cutoff_gene_length=False):
+    """Windows::new (src/windows.rs:28-44) -> (n_upstream, n_gene, n_downstream)"""
+    a = _window_args(window_size, window_step, cutoff, max_gene_length, absolute, cutoff_gene_length)
+    out = (C.c_int32 * 3)()
+    _check(_lib.abfit_window_counts(C.byref(a), out))
+    return tuple(out)
+
+
+def place_sites(genes, sites, window_size=5, window_step=0, cutoff=2048, max_gene_length=100, absolute=False,
+                cutoff_gene_length=False, want_assignments=True):
+    """Windows::extract's placement loop + Windows::distribution (src/windows.rs:158-165,331-337,
+    src/methylation_site.rs:368-490) -> (distribution int32 [n_up+n_gene+n_down], assign_site int64, assign_window int32)"""
+    genes = np.ascontiguousarray(genes, dtype=GENE_DTYPE)
+    sites = np.ascontiguousarray(sites, dtype=SITE_DTYPE)
+    a = _window_args(window_size, window_step, cutoff, max_gene_length, absolute, cutoff_gene_length)
+    n = sum(window_counts(window_size, window_step, cutoff, max_gene_length, absolute, cutoff_gene_length))
+    dist = np.zeros(n, dtype=np.int32)
+    n_assign = C.c_int64()
+    _check(_lib.abfit_place_sites(_ptr(genes), len(genes), _ptr(sites), len(sites), C.byref(a), _ptr(dist),
+                                  C.byref(n_assign), 0, None, None))
+    if not want_assignments:
+        return dist, None, None
+    cap = n_assign.value
+    asite = np.empty(cap, dtype=np.int64)
+    awin = np.empty(cap, dtype=np.int32)
+    _check(_lib.abfit_place_sites(_ptr(genes), len(genes), _ptr(sites), len(sites), C.byref(a), _ptr(dist),
+                                  C.byref(n_assign), cap, _ptr(asite), _ptr(awin)))
+    return dist, asite, awin
+
+
+def segments_from_assignments(assign_site, assign_window, n_windows):
+    """(site, window) hits -> (gather order int64 [n_hits], seg_offsets int64 [n_windows+1]): sites of window w are
+    order[seg_offsets[w]:seg_offsets[w+1]], in file order (the order Windows::save writes them, src/windows.rs:259-285).
+    Gathering status / posteriorMax / rc.meth.lvl columns with `order` gives the [S][L] arrays abfit_divergence takes
+    with `seg_offsets` — every window of a metaprofile in one call instead of one directory per window."""
+    assign_site = np.asarray(assign_site, dtype=np.int64)
+    assign_window = np.asarray(assign_window, dtype=np.int64)
+    perm = np.argsort(assign_window, kind="stable")
+    counts = np.bincount(assign_window, minlength=n_windows).astype(np.int64)
+    seg = np.zeros(n_windows + 1, dtype=np.int64)
+    np.cumsum(counts, out=seg[1:])
+    return assign_site[perm], seg

@@ -29,16 +29,6 @@ namespace abfit {
 // 5 = only the costs in shared memory, the vertices in a global (L2-resident) scratch area — they are
 // touched once per evaluation, and giving up their 5 KB per warp is what lets 16 warps share an SM.
 // ---------------------------------------------------------------------------------
-size_t smem_need(const DevProblem &pb, int simplex_doubles, bool d_shared, int n_warps)
-{
-    size_t b = (size_t)n_warps * ((size_t)pb.n_lane + (size_t)simplex_doubles) * 32 * 8;
-    if (d_shared) b += (((size_t)pb.n_pairs + 1) & ~(size_t)1) * 8;
-    b += (size_t)pb.n_offs * 4;
-    b += (size_t)pb.n_ops * 8;
-    b += 16;
-    return (b + 15) & ~(size_t)15;
-}
-
 struct Carved {
     WarpCtx ctx;
     LaneSimplex simplex;
@@ -347,18 +337,6 @@ k_fit_boot(DevicePools P, const WorkItem *__restrict__ items, int n_boot, const 
 // u16 resample indices of its replicate in an L2-resident tile and gathers resid from shared memory
 // (see DGather).  Cuts the per-evaluation L2 traffic of k_fit_boot by 4x.
 // ---------------------------------------------------------------------------------
-// resid and pred sit at the very start of dynamic shared memory, so the gather address is just the
-// byte offset stored in the tile plus a link-time constant
-__host__ __device__ inline int boot_gather_lead(int n_pairs)
-{
-    const int npad = (n_pairs + 1) & ~1;
-    return (2 * npad + 31) & ~31;
-}
-size_t smem_need_boot_gather(const DevProblem &pb)
-{
-    return smem_need(pb, 25, false, 1) + (size_t)boot_gather_lead(pb.n_pairs) * 8;
-}
-
 __global__ void __launch_bounds__(32)
 k_fit_boot_gather(DevicePools P, const WorkItem *__restrict__ items, int n_boot, const abfit_fit *__restrict__ best,
                   const double *__restrict__ pred, const double *__restrict__ resid,

@@ -288,6 +288,14 @@ __device__ __forceinline__ bool nm_advance(LaneNM &L, const LaneSimplex &S, cons
     return done;
 }
 
+// Bootstrap index-tile kernel: resid and pred sit at the very start of dynamic shared memory (so the
+// gather address is the byte offset stored in the tile plus a link-time constant); doubles reserved.
+__host__ __device__ inline int boot_gather_lead(int n_pairs)
+{
+    const int npad = (n_pairs + 1) & ~1;
+    return (2 * npad + 31) & ~31;
+}
+
 // start a new fit on this lane from a 5x4 simplex in global memory
 __device__ __forceinline__ void nm_begin(LaneNM &L, const LaneSimplex &S, int fit_id)
 {

@@ -27,6 +27,22 @@ static inline OpWord mk_op(uint32_t op, uint32_t a = 0, uint32_t b = OP_NONE, ui
     return w;
 }
 
+// ---- shared-memory footprints (the carve-up itself is carve_and_stage in abfit_kernels.cu) ----------
+size_t smem_need(const DevProblem &pb, int simplex_doubles, bool d_shared, int n_warps)
+{
+    size_t b = (size_t)n_warps * ((size_t)pb.n_lane + (size_t)simplex_doubles) * 32 * 8;
+    if (d_shared) b += (((size_t)pb.n_pairs + 1) & ~(size_t)1) * 8;
+    b += (size_t)pb.n_offs * 4;
+    b += (size_t)pb.n_ops * 8;
+    b += 16;
+    return (b + 15) & ~(size_t)15;
+}
+
+size_t smem_need_boot_gather(const DevProblem &pb)
+{
+    return smem_need(pb, 25, false, 1) + (size_t)boot_gather_lead(pb.n_pairs) * 8;
+}
+
 int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
 {
     hp.clear();

@@ -238,7 +238,10 @@ def main():
     W, NS, NB = args.windows, args.starts, args.boots
     shape = load_shape()
     N = len(shape)
-    first = rank * W  # every rank fits its own windows (weak scaling; no data-path collective)
+    from alphabeta_rs_b200 import multi
+
+    first, _cnt = multi.window_shard(world * W, rank, world)  # every rank fits its own windows (weak scaling)
+    assert _cnt == W
     ctx = ab.Context(local)
     fp64_peak = ctx.measure_fp64_peak()  # TFLOP/s, DFMA = 2 FLOP
 

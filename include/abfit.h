@@ -204,6 +204,37 @@ int abfit_batch_timing(abfit_batch *b, float ms[3], int64_t evals[2], int32_t *l
 int abfit_batch_flops_per_eval(abfit_batch *b, int32_t p, double *flops_out, int32_t *n_triples_out,
                                int32_t *tmax_out);
 
+/* ---- site -> window assignment (host) ---------------------------------------
+ * Replaces MethylationSite::is_in_gene / find_gene / place_in_windows (src/methylation_site.rs:368-490),
+ * Windows::new (src/windows.rs:28-44), the gene-caching loop of Windows::extract (src/windows.rs:331-337)
+ * and Windows::distribution (src/windows.rs:158-165).  Integer and f64-compare logic, bit-exact.
+ * chromosome: Chromosome::Numbered(n) -> n, Mitochondrial -> 256, Chloroplast -> 257 (src/methylation_site.rs:49-68);
+ * strand: +1 Sense, -1 Antisense, 0 Unknown ('*', equal to anything: src/genes.rs:88-96). */
+typedef struct {
+    int32_t chromosome;
+    uint32_t start, end;
+    int32_t strand;
+} abfit_gene; /* `Gene` (src/genes.rs:117-125), annotation order */
+typedef struct {
+    int32_t chromosome;
+    uint32_t start, end;
+    int32_t strand;
+} abfit_cg_site; /* `MethylationSite` (src/methylation_site.rs:32-45), file order */
+typedef struct {
+    uint32_t window_size, window_step; /* step 0 = window_size (src/extract.rs:26-28) */
+    uint32_t cutoff;
+    uint32_t max_gene_length; /* 100 unless absolute (src/extract.rs:49-58) */
+    int32_t absolute, cutoff_gene_length;
+} abfit_window_args; /* the fields of `arguments::Windows` the placement reads (src/arguments.rs:14-55) */
+/* windows per region: upstream, gene, downstream (Windows::new) */
+int abfit_window_counts(const abfit_window_args *args, int32_t n_windows_out[3]);
+/* distribution_out [n_up + n_gene + n_down]: sites per window, upstream || gene || downstream;
+ * the optional assignment list (site index, flat window index) holds every (site, window) hit in site
+ * order — n_assign_out returns how many there are, at most assign_cap are written. */
+int abfit_place_sites(const abfit_gene *genes, int32_t n_genes, const abfit_cg_site *sites, int64_t n_sites,
+                      const abfit_window_args *args, int32_t *distribution_out, int64_t *n_assign_out,
+                      int64_t assign_cap, int64_t *assign_site, int32_t *assign_window);
+
 /* ---- post-processing ------------------------------------------------------ */
 /* Replaces RawAnalysis::analyze (src/analysis.rs:50-98). rows [n][7] -> out[32]: 8 means,
  * 8 sds (ddof 1), 8 (q0.025, q0.975) pairs, field order alpha, beta, beta/alpha, weight,

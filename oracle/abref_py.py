@@ -368,3 +368,163 @@ def load_pedigree_file(path: str) -> np.ndarray:
             continue
         rows.append([float(x) for x in line.split(" ")[:4]])
     return np.array(rows, dtype=np.float64)
+
+
+# ---------------------------------------------------------------------------------------------
+# site -> window assignment: literal Python restatement (small cases only; pure-Python loops)
+#   Gene::from_annotation_file_line   src/genes.rs:166-216
+#   Genome / GenesByStrand            src/genes.rs:24-57,127-163
+#   is_in_gene / find_gene / place_in_windows   src/methylation_site.rs:368-490
+#   Windows::new / extract loop / distribution  src/windows.rs:28-44,331-337,158-165
+# genes / sites are tuples (chromosome, start, end, strand) with strand +1 / -1 / 0 ('*').
+# ---------------------------------------------------------------------------------------------
+U32 = 0xFFFFFFFF
+
+
+def _strand_of(s: str):
+    return {"+": 1, "-": -1, "*": 0}.get(s)
+
+
+def _strand_eq(a: int, b: int) -> bool:  # src/genes.rs:88-96: Unknown equals anything
+    return not ((a > 0 and b < 0) or (a < 0 and b > 0))
+
+
+def chromosome_id(s: str):
+    """Chromosome::try_from (src/methylation_site.rs:57-68) -> Numbered(n) = n, M = 256, C = 257, else None"""
+    try:
+        c = _parse_chromosome(s)
+    except ValueError:
+        return None
+    return {"M": 256, "C": 257}.get(c, c)
+
+
+def parse_annotation_line(line: str, invert: bool = False):
+    """src/genes.rs:166-216: `chr start end name annotation strand` or `chr start end width strand name`"""
+    parts = line.replace("\t", " ").split(" ")
+    if len(parts) != 6:
+        return None
+    if _strand_of(parts[5]) is not None:
+        c, st, en, strand = parts[0], parts[1], parts[2], parts[5]
+    elif _strand_of(parts[4]) is not None:
+        c, st, en, strand = parts[0], parts[1], parts[2], parts[4]
+    else:
+        return None
+    cid = chromosome_id(c)
+    try:
+        a, b = _u32(st), _u32(en)
+    except ValueError:
+        return None
+    if cid is None:
+        return None
+    sd = _strand_of(strand)
+    return (cid, a, b, -sd if invert else sd)
+
+
+def window_counts(window_size, window_step, cutoff, max_gene_length, absolute):
+    step = window_step or window_size  # src/extract.rs:26-28
+    gene = (max_gene_length // step) if absolute else (100 // step)
+    updown = (cutoff // step) if absolute else (100 // step)
+    return updown, gene, updown
+
+
+def _gene_cutoff(g, cutoff, cutoff_gene_length):
+    return ((g[2] - g[1]) & U32) if cutoff_gene_length else cutoff
+
+
+def is_in_gene(site, g, cutoff, cutoff_gene_length=False):
+    c = _gene_cutoff(g, cutoff, cutoff_gene_length)
+    return (site[0] == g[0] and g[1] <= ((site[1] + c) & U32) and site[2] <= ((g[2] + c) & U32)
+            and _strand_eq(site[3], g[3]))
+
+
+def build_genome(genes):
+    genome = {}
+    for g in genes:
+        l = genome.setdefault(g[0], {"sense": [], "antisense": [], "combined": []})
+        l["combined"].append(g)
+        if g[3] > 0:
+            l["sense"].append(g)
+        if g[3] < 0:
+            l["antisense"].append(g)
+    for l in genome.values():
+        for k in l:
+            l[k].sort(key=lambda g: g[1])  # list.sort is stable, like Vec::sort_by
+    return genome
+
+
+def find_gene(site, genome, cutoff, cutoff_gene_length=False):
+    chrom = genome.get(site[0])
+    if chrom is None:
+        return None
+    strand = chrom["sense"] if site[3] > 0 else chrom["antisense"] if site[3] < 0 else chrom["combined"]
+    # slice::binary_search_by_key, Rust 1.52..1.81
+    size = len(strand)
+    left, right = 0, size
+    idx = None
+    while left < right:
+        mid = left + size // 2
+        key = (strand[mid][2] + _gene_cutoff(strand[mid], cutoff, cutoff_gene_length)) & U32
+        if key < site[1]:
+            left = mid + 1
+        elif key > site[1]:
+            right = mid
+        else:
+            idx = mid
+            break
+        size = right - left
+    if idx is None:
+        idx = left
+    if len(strand) < idx + 1:
+        return None
+    g = strand[idx]
+    return g if is_in_gene(site, g, cutoff, cutoff_gene_length) else None
+
+
+def place_in_windows(site, g, counts, window_size, window_step, cutoff, absolute):
+    """returns [(region, window index)] with region 0/1/2 = upstream/gene/downstream"""
+    E = 0.1
+    step = float(window_step or window_size)
+    size = float(window_size)
+    location, start, end = float(site[1]), float(g[1]), float(g[2])
+    cut = float(cutoff)
+    length = end - start
+    antisense = site[3] < 0  # Unknown is treated as Sense (:439-443)
+    offset = (end - location) if antisense else (location - start)
+    region = 0 if offset < 0.0 else 2 if offset > length else 1
+    if not antisense:
+        position = (location - start + cut, location - start, location - end)[region]
+    else:
+        position = (end - location + cut, end - location, start - location)[region]
+    if not absolute:
+        try:
+            position = position / length if region == 1 else position / cut
+        except ZeroDivisionError:
+            position = float("nan") if position == 0 else float("inf") * (1 if position > 0 else -1)
+        position *= 100.0
+    hits = []
+    for i in range(counts[region]):
+        lower = i * step - E
+        upper = lower + size + E
+        if position >= lower and position <= upper:
+            hits.append((region, i))
+    return hits
+
+
+def extract_windows(genes, sites, window_size=5, window_step=0, cutoff=2048, max_gene_length=100, absolute=False,
+                    cutoff_gene_length=False):
+    """Windows::extract placement loop -> (distribution list, [(site index, flat window index)])"""
+    counts = window_counts(window_size, window_step, cutoff, max_gene_length, absolute)
+    base = (0, counts[0], counts[0] + counts[1])
+    dist = [0] * sum(counts)
+    assign = []
+    genome = build_genome(genes)
+    last = None
+    for si, s in enumerate(sites):
+        if last is None or not is_in_gene(s, last, cutoff, cutoff_gene_length):
+            last = find_gene(s, genome, cutoff, cutoff_gene_length)
+        if last is None:
+            continue
+        for region, i in place_in_windows(s, last, counts, window_size, window_step, cutoff, absolute):
+            dist[base[region] + i] += 1
+            assign.append((si, base[region] + i))
+    return dist, assign

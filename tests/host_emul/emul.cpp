@@ -20,13 +20,6 @@ namespace abfit {
 static std::string g_err;
 void set_error(const std::string &m) { g_err = m; }
 int cuda_fail(cudaError_t, const char *) { return ABFIT_ERR_CUDA; }
-size_t smem_need(const DevProblem &pb, int simplex_doubles, bool d_shared, int n_warps)
-{
-    size_t b = (size_t)n_warps * ((size_t)pb.n_lane + (size_t)simplex_doubles) * 32 * 8;
-    if (d_shared) b += (((size_t)pb.n_pairs + 1) & ~(size_t)1) * 8;
-    b += (size_t)pb.n_offs * 4 + (size_t)pb.n_ops * 8 + 16;
-    return (b + 15) & ~(size_t)15;
-}
 }  // namespace abfit
 
 using namespace abfit;

@@ -289,3 +289,59 @@ def test_dmatrix_large_blocked(ab, ctx, oracle):
     b = ctx.dmatrix(status[:, cut:], post[:, cut:], meth[:, cut:], 0.99)
     assert np.array_equal(a["diff"] + b["diff"], out["diff"]) and np.array_equal(a["cnt"] + b["cnt"], out["cnt"])
     assert np.array_equal(a["nvalid"] + b["nvalid"], out["nvalid"])
+
+
+# ---------------------------------------------------------------------------------------------
+# C3: metaprofile windows -> observed divergence per window -> fit, all windows in one batch
+# ---------------------------------------------------------------------------------------------
+def test_metaprofile_chain_windows_to_fits(ab, ctx, oracle):
+    """data/methylome (4 samples x 500 CG sites, bp 6-1807 of chr 1) with a synthetic annotation whose genes
+    overlap those sites (the shipped annotation.bed starts at bp 23 121, so every real window is empty —
+    see test_windows.py).  Site -> window placement (host), per-window pairwise divergence + p0uu
+    (abfit_divergence with segment offsets) and the multi-start fits of all non-empty windows in ONE batch,
+    against the oracle doing the reference's per-window loop (src/cli/metaprofile.rs:50-72)."""
+    ped6, p6, info = oracle.build_pedigree(os.path.join(GOLDEN, "nodelist.txt"), os.path.join(GOLDEN, "edgelist.txt"), 0.99,
+                                           resolve_golden)
+    status, post, meth = info["status"], info["post"], info["meth"]
+    S, L = status.shape
+    # the four files list the same CG positions: read them once for the placement
+    sites = []
+    for line in open(os.path.join(GOLDEN, "methylome", "G0.txt")).read().split("\n")[1:]:
+        s = oracle.parse_methylome_line(line)
+        if s is not None:
+            sites.append((s["chromosome"], s["start"], s["end"], {"+": 1, "-": -1, "*": 0}[s["strand"]]))
+    assert len(sites) == L
+    genes = [(1, 200, 900, 1), (1, 700, 1500, -1), (1, 1400, 1700, 0)]
+    kw = dict(window_size=10, window_step=5, cutoff=150, max_gene_length=100, absolute=False)
+    dist, asite, awin = ab.place_sites(genes, sites, **kw)
+    want_dist, want_assign = oracle.extract_windows(genes, sites, **kw)
+    assert dist.tolist() == want_dist and list(zip(asite.tolist(), awin.tolist())) == want_assign
+    n_win = len(dist)
+    order, seg = ab.segments_from_assignments(asite, awin, n_win)
+    assert np.array_equal(np.diff(seg), dist)
+    out = ctx.dmatrix(status[:, order], post[:, order], meth[:, order], 0.99, seg_offsets=seg)
+
+    keep, probs, oprobs = [], [], []
+    for w in range(n_win):
+        cols = order[seg[w]:seg[w + 1]]
+        D, diff, cnt = oracle.dmatrix(status[:, cols], post[:, cols], 0.99)
+        assert np.array_equal(out["diff"][w], diff) and np.array_equal(out["cnt"][w], cnt)
+        assert np.array_equal(out["D"][w], D, equal_nan=True)
+        if len(cols) and not np.isnan(D).any():
+            want_p0 = oracle.p0uu(post[:, cols], meth[:, cols], 0.99)[0]
+            assert out["p0uu"][w] == want_p0
+            if D.max() > 0:
+                ped = ped6.copy()
+                ped[:, 3] = D  # same nodes and edges in every window (src/setup.rs:35-72): only D changes
+                keep.append(w)
+                probs.append(ab.Problem(ped, want_p0, want_p0, 1.0))
+                oprobs.append(oracle.Problem(ped, want_p0, want_p0, 1.0))
+    assert len(keep) >= 20
+    n_starts = 40
+    sx = np.stack([ab.gen_start_simplices(SEED, w, n_starts, float(p.pedigree[:, 3].max())) for w, p in zip(keep, probs)])
+    res = ctx.fit_batch(probs, sx, max_iters=10000)
+    off = 0
+    for i, w in enumerate(keep):
+        check_fit_against_oracle(ab, oracle, res, i, oprobs[i], sx[i], 10000,
+                                 oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, off, 6)
+        off += 6
