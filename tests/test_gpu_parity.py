@@ -295,7 +295,7 @@ def test_dmatrix_large_blocked(ab, ctx, oracle):
 # C3: metaprofile windows -> observed divergence per window -> fit, all windows in one batch
 # ---------------------------------------------------------------------------------------------
 def test_metaprofile_chain_windows_to_fits(ab, ctx, oracle):
-    """data/methylome (4 samples x 500 CG sites, bp 6-1807 of chr 1) with a synthetic annotation whose genes
+    """data/methylome (4 samples x 500 CG sites, bp 6-1807 of chr 1-5, C, M) with a synthetic annotation whose genes
     overlap those sites (the shipped annotation.bed starts at bp 23 121, so every real window is empty —
     see test_windows.py).  Site -> window placement (host), per-window pairwise divergence + p0uu
     (abfit_divergence with segment offsets) and the multi-start fits of all non-empty windows in ONE batch,
@@ -309,10 +309,13 @@ def test_metaprofile_chain_windows_to_fits(ab, ctx, oracle):
     for line in open(os.path.join(GOLDEN, "methylome", "G0.txt")).read().split("\n")[1:]:
         s = oracle.parse_methylome_line(line)
         if s is not None:
-            sites.append((s["chromosome"], s["start"], s["end"], {"+": 1, "-": -1, "*": 0}[s["strand"]]))
+            sites.append((oracle.chromosome_id(str(s["chromosome"])), s["start"], s["end"],
+                          {"+": 1, "-": -1, "*": 0}[s["strand"]]))
     assert len(sites) == L
-    genes = [(1, 200, 900, 1), (1, 700, 1500, -1), (1, 1400, 1700, 0)]
-    kw = dict(window_size=10, window_step=5, cutoff=150, max_gene_length=100, absolute=False)
+    genes = [(1, 300, 700, -1), (1, 250, 800, 1), (2, 1200, 1600, 1), (2, 1250, 1650, -1), (3, 600, 900, 0),
+             (4, 1200, 1550, -1), (4, 1150, 1600, 1), (5, 300, 900, 0), (257, 200, 900, 1), (257, 150, 950, -1),
+             (256, 200, 600, -1), (256, 150, 650, 1)]  # overlapping genes, both strands, unknown strand, chr C and M
+    kw = dict(window_size=10, window_step=5, cutoff=200, max_gene_length=100, absolute=False)
     dist, asite, awin = ab.place_sites(genes, sites, **kw)
     want_dist, want_assign = oracle.extract_windows(genes, sites, **kw)
     assert dist.tolist() == want_dist and list(zip(asite.tolist(), awin.tolist())) == want_assign
