@@ -88,6 +88,8 @@ def _load() -> C.CDLL:
         "abfit_gen_start_simplices": (None, [u64, u64, i32, dbl, vp]),
         "abfit_gen_vary_vertices": (None, [u64, u64, i32, vp, vp]),
         "abfit_gen_resample_idx": (None, [u64, u64, i32, i32, vp]),
+        "abfit_gen_vary_vertices_batch": (None, [u64, u64, i32, i32, vp, vp]),
+        "abfit_alphabeta_batch": (C.c_int, [vp, PP, i32, i32, vp, i32, vp, u64, u64, i32, i32, dbl, u32, vp, vp, vp, vp, vp, vp]),
         "abfit_cost_batch": (C.c_int, [vp, PP, i32, vp, vp, i32, vp, vp]),
         "abfit_model_divergence": (C.c_int, [vp, PP, vp, vp, vp]),
         "abfit_fit_batch": (C.c_int, [vp, PP, i32, i32, vp, i32, dbl, u32, vp, vp, vp, vp, vp]),
@@ -119,7 +121,8 @@ _lib = _load()
 EXPORTED_SYMBOLS = (
     "abfit_last_error abfit_version abfit_ctx_create abfit_ctx_destroy abfit_ctx_info abfit_measure_fp64_peak "
     "abfit_ctx_timer_start abfit_ctx_timer_stop abfit_ctx_sync "
-    "abfit_gen_start_simplices abfit_gen_vary_vertices abfit_gen_resample_idx abfit_cost_batch "
+    "abfit_gen_start_simplices abfit_gen_vary_vertices abfit_gen_vary_vertices_batch abfit_gen_resample_idx "
+    "abfit_alphabeta_batch abfit_cost_batch "
     "abfit_model_divergence abfit_fit_batch abfit_boot_batch abfit_divergence abfit_batch_create "
     "abfit_batch_destroy abfit_batch_upload_starts abfit_batch_run_fit abfit_batch_download_fit "
     "abfit_batch_upload_boot abfit_batch_run_boot abfit_batch_download_boot abfit_batch_sync "
@@ -337,6 +340,32 @@ class Context:
             _lib.abfit_boot_batch(self._h, arr, n_probs, _ptr(best), _ptr(pred), _ptr(resid), n_boot,
                                   _ptr(resample_idx), _ptr(vary_vertices), max_iters, sd_tol, flags, _ptr(rows), None)
         )
+
+    # -- alphabeta::run (fit + bootstrap), batched over windows -----------------------------------
+    def alphabeta_batch(self, probs, simplices, resample_idx, seed, first_problem_id=0, max_iters_fit=10000,
+                        max_iters_boot=1000, sd_tol=DBL_EPSILON, flags=0, best=None, pred=None, resid=None, status=None,
+                        rows=None, analysis=None, packed=None):
+        """alphabeta::run (src/alphabeta.rs:23-59) for every window in one call -> dict(best, pred, resid, status, rows,
+        analysis).  Output arrays may be passed in (e.g. pinned)."""
+        n_probs = len(probs)
+        simplices = _f64(simplices)
+        n_starts = simplices.size // (n_probs * 20)
+        idx = np.ascontiguousarray(resample_idx, dtype=np.int32)
+        total = sum(p.n_pairs for p in probs)
+        n_boot = idx.size // total
+        best = np.zeros(n_probs, dtype=FIT_DTYPE) if best is None else best
+        pred = np.empty(total) if pred is None else pred
+        resid = np.empty(total) if resid is None else resid
+        status = np.zeros(n_probs, dtype=np.int32) if status is None else status
+        rows = np.empty((n_probs, n_boot, 7)) if rows is None else rows
+        analysis = np.empty((n_probs, 32)) if analysis is None else analysis
+        arr = packed if packed is not None else _pack_problems(probs)
+        _check(
+            _lib.abfit_alphabeta_batch(self._h, arr, n_probs, n_starts, _ptr(simplices), n_boot, _ptr(idx), seed,
+                                       first_problem_id, max_iters_fit, max_iters_boot, sd_tol, flags, _ptr(best),
+                                       _ptr(pred), _ptr(resid), _ptr(status), _ptr(rows), _ptr(analysis))
+        )
+        return {"best": best, "pred": pred, "resid": resid, "status": status, "rows": rows, "analysis": analysis}
 
     # -- boot_model::run, batched over windows ---------------------------------------------------
     def boot_batch(self, probs: Sequence[Problem], best, pred, resid, resample_idx, vary_vertices, max_iters=1000,

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <thread>
 #include <tuple>
 
 #include "abfit_plan.h"
@@ -55,6 +56,8 @@ using namespace abfit;
 struct abfit_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of the bootstrap inputs while the multi-start kernel runs
+    cudaEvent_t copy_done = nullptr;
     cudaDeviceProp prop{};
     int smem_optin = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -99,6 +102,23 @@ struct abfit_batch {
     int launches_fit = 0, launches_boot = 0;
 };
 
+// run f(i) for i in [0, n) on the host's cores (input generation and statistics of large batches)
+template <class F>
+static void parallel_for(int32_t n, F f)
+{
+    const int nt = (int)std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)std::max(1, n / 64)));
+    if (nt <= 1) {
+        for (int32_t i = 0; i < n; ++i) f(i);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back([=]() {
+            for (int32_t i = t; i < n; i += nt) f(i);
+        });
+    for (auto &x : th) x.join();
+}
+
 extern "C" {
 
 const char *abfit_last_error(void) { return g_last_error.c_str(); }
@@ -131,6 +151,11 @@ int abfit_ctx_create(int device, abfit_ctx **out)
         delete c;
         return cuda_fail(cudaGetLastError(), "cudaStreamCreate");
     }
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming) != cudaSuccess) {
+        abfit_ctx_destroy(c);
+        return cuda_fail(cudaGetLastError(), "cudaStreamCreate (copy stream)");
+    }
     *out = c;
     return 0;
 }
@@ -142,6 +167,8 @@ void abfit_ctx_destroy(abfit_ctx *ctx)
     if (ctx->scratch) abfit_batch_destroy(ctx->scratch);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
+    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -439,6 +466,33 @@ int abfit_batch_download_fit(abfit_batch *b, abfit_fit *best_out, abfit_fit *all
     return 0;
 }
 
+// buffers and work items of a bootstrap with n_boot replicates per window (synchronises the stream when it
+// has to rebuild the items, so callers that overlap do this before they enqueue kernels)
+static int boot_alloc(abfit_batch *b, int32_t n_boot)
+{
+    cudaStream_t st = b->ctx->stream;
+    const size_t n_idx = (size_t)b->total_pairs * n_boot, n_vary = (size_t)b->n_probs * n_boot * 16;
+    if (int rc = b->d_idx.ensure(n_idx)) return rc;
+    if (int rc = b->d_vary.ensure(n_vary)) return rc;
+    if (n_boot != b->n_boot) {
+        b->n_boot = n_boot;
+        std::vector<WorkItem> items = make_items(b->hp, n_boot, b->ctx->prop.multiProcessorCount, 1, true);
+        b->n_boot_items = (int)items.size();
+        if (int rc = b->d_boot_items.ensure(items.size())) return rc;
+        if (!items.empty())
+            ABFIT_CUDA(cudaMemcpyAsync(b->d_boot_items.p, items.data(), items.size() * sizeof(WorkItem),
+                                       cudaMemcpyHostToDevice, st));
+        ABFIT_CUDA(cudaStreamSynchronize(st));
+        // stored-D* tile: N x 32 doubles per block; index tile: ceil(N/4) x 32 x 8 bytes (+ one tile of slack for
+        // the L1 prefetch that runs 4 groups ahead)
+        const size_t per_block = b->shape.smem_boot_gather ? (size_t)((b->hp.max_pairs + 3) / 4) * 32 : (size_t)b->hp.max_pairs * 32;
+        if (int rc = b->d_scratch.ensure((size_t)(std::max(b->n_boot_items, 1) + 1) * per_block)) return rc;
+        if (int rc = b->d_rows.ensure((size_t)b->n_probs * n_boot * 7)) return rc;
+        if (int rc = b->d_bootfits.ensure((size_t)b->n_probs * n_boot)) return rc;
+    }
+    return 0;
+}
+
 int abfit_batch_upload_boot(abfit_batch *b, int32_t n_boot, const abfit_fit *best, const double *pred,
                             const double *resid, const int32_t *resample_idx, const double *vary_vertices)
 {
@@ -460,26 +514,10 @@ int abfit_batch_upload_boot(abfit_batch *b, int32_t n_boot, const abfit_fit *bes
         set_error("upload_boot: no best model on the device (run_fit first or pass best/pred/resid)");
         return ABFIT_ERR_STATE;
     }
+    if (int rc = boot_alloc(b, n_boot)) return rc;
     const size_t n_idx = (size_t)b->total_pairs * n_boot, n_vary = (size_t)b->n_probs * n_boot * 16;
-    if (int rc = b->d_idx.ensure(n_idx)) return rc;
-    if (int rc = b->d_vary.ensure(n_vary)) return rc;
     ABFIT_CUDA(cudaMemcpyAsync(b->d_idx.p, resample_idx, n_idx * 4, cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaMemcpyAsync(b->d_vary.p, vary_vertices, n_vary * 8, cudaMemcpyHostToDevice, st));
-    if (n_boot != b->n_boot) {
-        b->n_boot = n_boot;
-        std::vector<WorkItem> items = make_items(b->hp, n_boot, b->ctx->prop.multiProcessorCount, 1, true);
-        b->n_boot_items = (int)items.size();
-        if (int rc = b->d_boot_items.ensure(items.size())) return rc;
-        if (!items.empty())
-            ABFIT_CUDA(cudaMemcpyAsync(b->d_boot_items.p, items.data(), items.size() * sizeof(WorkItem),
-                                       cudaMemcpyHostToDevice, st));
-        ABFIT_CUDA(cudaStreamSynchronize(st));
-        // stored-D* tile: N x 32 doubles per block; index tile: ceil(N/4) x 32 x 8 bytes (+ one tile of slack for
-        // the L1 prefetch that runs 4 groups ahead)
-        if (int rc = b->d_scratch.ensure((size_t)(std::max(b->n_boot_items, 1) + 1) * b->hp.max_pairs * 32)) return rc;
-        if (int rc = b->d_rows.ensure((size_t)b->n_probs * n_boot * 7)) return rc;
-        if (int rc = b->d_bootfits.ensure((size_t)b->n_probs * n_boot)) return rc;
-    }
     b->boot_uploaded = true;
     b->boot_done = false;
     return 0;
@@ -613,6 +651,55 @@ int abfit_boot_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs
     if (int rc = abfit_batch_upload_boot(b, n_boot, best, pred, resid, resample_idx, vary_vertices)) return rc;
     if (int rc = abfit_batch_run_boot(b, max_iters, sd_tol, flags)) return rc;
     return abfit_batch_download_boot(b, rows_out, fits_out);
+}
+
+void abfit_gen_vary_vertices_batch(uint64_t seed, uint64_t first_problem_id, int32_t n_probs, int32_t n_boot,
+                                   const abfit_fit *best, double *out)
+{
+    parallel_for(n_probs, [=](int32_t p) {
+        abfit_gen_vary_vertices(seed, first_problem_id + (uint64_t)p, n_boot, best[p].theta, out + (size_t)p * n_boot * 16);
+    });
+}
+
+int abfit_alphabeta_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, int32_t n_starts,
+                          const double *simplices, int32_t n_boot, const int32_t *resample_idx, uint64_t vary_seed,
+                          uint64_t first_problem_id, int32_t max_iters_fit, int32_t max_iters_boot, double sd_tol,
+                          uint32_t flags, abfit_fit *best_out, double *pred_out, double *resid_out,
+                          int32_t *prob_status_out, double *rows_out, double *analysis_out)
+{
+    if (!simplices || !resample_idx || n_starts <= 0 || n_boot <= 0 || !rows_out) return ABFIT_ERR_ARG;
+    abfit_batch *b = nullptr;
+    if (int rc = workspace(ctx, probs, n_probs, &b)) return rc;
+    if (int rc = boot_alloc(b, n_boot)) return rc;  // before any kernel is enqueued: it may synchronise
+    if (int rc = abfit_batch_upload_starts(b, n_starts, simplices)) return rc;
+    if (int rc = abfit_batch_run_fit(b, max_iters_fit, sd_tol, flags)) return rc;
+    // the resample indices (the bulk of the bootstrap's input) cross PCIe under the multi-start kernel
+    ABFIT_CUDA(cudaMemcpyAsync(b->d_idx.p, resample_idx, (size_t)b->total_pairs * n_boot * 4, cudaMemcpyHostToDevice,
+                               ctx->copy_stream));
+    ABFIT_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+    std::vector<abfit_fit> best_local;
+    if (!best_out) {
+        best_local.resize(n_probs);
+        best_out = best_local.data();
+    }
+    if (int rc = abfit_batch_download_fit(b, best_out, nullptr, pred_out, resid_out, prob_status_out)) return rc;
+    // Model::vary x 4 per replicate around each window's best model (src/boot_model.rs:69-75), drawn on the host
+    std::vector<double> vary((size_t)n_probs * n_boot * 16);
+    abfit_gen_vary_vertices_batch(vary_seed, first_problem_id, n_probs, n_boot, best_out, vary.data());
+    cudaStream_t st = ctx->stream;
+    ABFIT_CUDA(cudaMemcpyAsync(b->d_vary.p, vary.data(), vary.size() * 8, cudaMemcpyHostToDevice, st));
+    ABFIT_CUDA(cudaStreamWaitEvent(st, ctx->copy_done, 0));
+    b->boot_uploaded = true;
+    b->boot_done = false;
+    if (int rc = abfit_batch_run_boot(b, max_iters_boot, sd_tol, flags)) return rc;
+    if (int rc = abfit_batch_download_boot(b, rows_out, nullptr)) return rc;  // synchronises: `vary` may go out of scope
+    if (analysis_out) {
+        std::vector<int> rcs(n_probs, 0);
+        parallel_for(n_probs, [&](int32_t p) {
+            rcs[p] = abfit_analyze(rows_out + (size_t)p * n_boot * 7, n_boot, analysis_out + (size_t)p * 32);
+        });
+    }
+    return 0;
 }
 
 int abfit_cost_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, const int32_t *prob_of_theta,

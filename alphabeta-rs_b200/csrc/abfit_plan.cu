@@ -57,6 +57,10 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
     hp.d_has_nan.assign(n_probs, 0);
     typedef std::tuple<int, int, int> Tri;  // (t0, a = t1 - t0, b = t2 - t0)
     typedef std::pair<int, int> AB;
+    // Windows of one metaprofile share the pedigree's time structure (same nodes and edges, only D differs):
+    // a problem whose (t0,t1,t2) sequence equals the previous one's shares its program and offsets in the pools.
+    std::vector<uint32_t> key32, prev_key32;
+    int prev_p = -1;
     for (int p = 0; p < n_probs; ++p) {
         const abfit_problem &ap = probs[p];
         if (!ap.pedigree || ap.n_pairs <= 0) {
@@ -84,6 +88,7 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
         std::vector<Tri> key(ap.n_pairs);
         std::map<Tri, int> tri_id;
         int max_exp = 0;
+        key32.resize(ap.n_pairs);
         for (int i = 0; i < ap.n_pairs; ++i) {
             const double *row = ap.pedigree + 4 * (size_t)i;
             const int t0 = as_i8(row[0]), t1 = as_i8(row[1]), t2 = as_i8(row[2]);
@@ -93,11 +98,30 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
                 return ABFIT_ERR_TIME;
             }
             key[i] = Tri(t0, t1 - t0, t2 - t0);
-            tri_id.emplace(key[i], 0);
+            key32[i] = (uint32_t)t0 | ((uint32_t)(t1 - t0) << 8) | ((uint32_t)(t2 - t0) << 16);
             max_exp = std::max(max_exp, std::max(t0, std::max(t1 - t0, t2 - t0)));
             if (row[3] != row[3]) hp.d_has_nan[p] = 1;
             hp.D.push_back(row[3]);
         }
+        if (prev_p >= 0 && key32 == prev_key32) {
+            const DevProblem &q = hp.probs[prev_p];
+            dp.offs_off = q.offs_off;
+            dp.ops_off = q.ops_off;
+            dp.n_offs = q.n_offs;
+            dp.n_ops = q.n_ops;
+            dp.n_lane = q.n_lane;
+            dp.tmax = q.tmax;
+            dp.pad_ = 0;
+            hp.probs[p] = dp;
+            hp.tmax[p] = hp.tmax[prev_p];
+            hp.n_triples[p] = hp.n_triples[prev_p];
+            hp.flops[p] = hp.flops[prev_p];
+            hp.max_pairs = std::max(hp.max_pairs, ap.n_pairs);
+            continue;
+        }
+        prev_key32 = key32;
+        prev_p = p;
+        for (int i = 0; i < ap.n_pairs; ++i) tri_id.emplace(key[i], 0);
         int U = 0;
         for (auto &kv : tri_id) kv.second = U++;
 

@@ -11,9 +11,9 @@ ranks shard them with no data-path collective (weak scaling: every rank processe
 
 Printed JSON (one line, rank 0):
   value      fits/s with all inputs already resident in HBM (kernels only, CUDA events on the library stream)
-  e2e        fits/s through the host-buffer C-ABI calls (abfit_fit_batch + abfit_boot_batch): pinned host
-             inputs copied H2D and results D2H inside the timed region, incl. the host draw of the
-             bootstrap vary-vertices that depends on the fit result
+  e2e        fits/s through the host-buffer C-ABI call abfit_alphabeta_batch (= alphabeta::run per window): pinned
+             host inputs copied H2D and results D2H inside the timed region, incl. compiling the pedigrees, the host
+             draw of the bootstrap vary-vertices that depends on the fit result, and the bootstrap statistics
   roofline   dominant kernel k_fit_starts against the FP64 (DFMA) peak measured in the same run;
              achieved = executed objective evaluations x algorithmic FLOPs per evaluation / kernel time
   cpu_baseline  oracle port of the reference ("literal work": per-pair matrix_power, no early exit) on all
@@ -324,13 +324,16 @@ def main():
     rows_t = torch.empty((W, NB, 7), dtype=torch.float64, pin_memory=True)
     status_h = np.zeros(W, dtype=np.int32)
 
-    def e2e_step():
-        r = ctx.fit_batch_into(probs, sx, best_h, pred_t.numpy(), resid_t.numpy(), status_h)
-        gen_vary(best_h["theta"])
-        ctx.boot_batch_into(probs, best_h, pred_t.numpy(), resid_t.numpy(), idx, vary, rows_t.numpy())
-        return r
+    analysis_h = np.empty((W, 32))
+    packed = ab._pack_problems(probs)
 
-    h2d = sx.nbytes + idx.nbytes + vary.nbytes + peds.nbytes + best_h.nbytes + 2 * pred_t.numpy().nbytes
+    def e2e_step():
+        # abfit_alphabeta_batch = alphabeta::run for every window: fit, host draw of the vary vertices from the
+        # best-of-starts, bootstrap, statistics; host buffers in, host buffers out
+        ctx.alphabeta_batch(probs, sx, idx, SEED, first_problem_id=first, best=best_h, pred=pred_t.numpy(),
+                            resid=resid_t.numpy(), status=status_h, rows=rows_t.numpy(), analysis=analysis_h, packed=packed)
+
+    h2d = sx.nbytes + idx.nbytes + vary.nbytes + peds.nbytes
     d2h = best_h.nbytes + 2 * pred_t.numpy().nbytes + rows_t.numpy().nbytes + status_h.nbytes
     e2e_step()  # warm
     barrier()

@@ -114,6 +114,10 @@ void abfit_gen_start_simplices(uint64_t seed, uint64_t problem_id, int32_t n_sta
  * out [n_boot][4][4] */
 void abfit_gen_vary_vertices(uint64_t seed, uint64_t problem_id, int32_t n_boot, const double best_theta[4],
                              double *out);
+/* the same for n_probs windows (problem ids first_problem_id + p, theta of best[p]), on all host cores;
+ * out [n_probs][n_boot][4][4] */
+void abfit_gen_vary_vertices_batch(uint64_t seed, uint64_t first_problem_id, int32_t n_probs, int32_t n_boot,
+                                   const abfit_fit *best, double *out);
 /* residual resampling with replacement (src/boot_model.rs:43-48); out [n_boot][n_pairs] */
 void abfit_gen_resample_idx(uint64_t seed, uint64_t problem_id, int32_t n_boot, int32_t n_pairs, int32_t *out);
 
@@ -158,6 +162,20 @@ int abfit_boot_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs
                      const double *pred, const double *resid, int32_t n_boot, const int32_t *resample_idx,
                      const double *vary_vertices, int32_t max_iters, double sd_tol, uint32_t flags,
                      double *rows_out, abfit_fit *fits_out);
+
+/* Fit, then bootstrap, every window: replaces `alphabeta::run` (src/alphabeta.rs:23-59: ab_neutral::run :33-41
+ * followed by boot_model::run :42-54) for all windows of a metaprofile in one call (the reference loops the
+ * windows serially, src/cli/metaprofile.rs:50-72).  The vary vertices depend on each window's best model; they are
+ * drawn on the host (abfit_gen_vary_vertices, problem id = first_problem_id + window) once the best-of-starts
+ * are back, while the resample indices cross PCIe under the multi-start kernel.
+ *  rows_out      [n_probs][n_boot][7]   (required)
+ *  analysis_out  [n_probs][32]          RawAnalysis::analyze per window (may be NULL)
+ *  best_out, pred_out, resid_out, prob_status_out as in abfit_fit_batch (may be NULL) */
+int abfit_alphabeta_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, int32_t n_starts,
+                          const double *simplices, int32_t n_boot, const int32_t *resample_idx, uint64_t vary_seed,
+                          uint64_t first_problem_id, int32_t max_iters_fit, int32_t max_iters_boot, double sd_tol,
+                          uint32_t flags, abfit_fit *best_out, double *pred_out, double *resid_out,
+                          int32_t *prob_status_out, double *rows_out, double *analysis_out);
 
 /* Observed pairwise divergence + p0uu.  Replaces `DMatrix::from` (src/pedigree.rs:213-262)
  * and the per-sample statistics of `Pedigree::build` (src/pedigree.rs:159-183).

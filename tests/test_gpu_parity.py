@@ -348,3 +348,30 @@ def test_metaprofile_chain_windows_to_fits(ab, ctx, oracle):
         check_fit_against_oracle(ab, oracle, res, i, oprobs[i], sx[i], 10000,
                                  oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, off, 6)
         off += 6
+
+
+def test_alphabeta_batch_equals_fit_then_boot(ab, ctx, oracle, ped351, ped78):
+    """the combined call (alphabeta::run per window, overlapped uploads) against the two separate calls and the oracle"""
+    rng = np.random.default_rng(21)
+    cases = [synth_problem(rng, ped351) for _ in range(3)] + [ped78]
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    n_starts, n_boot, first_id = 48, 20, 1000
+    sx = np.stack([ab.gen_start_simplices(SEED, first_id + i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    idx = np.concatenate([ab.gen_resample_idx(SEED, first_id + i, n_boot, len(p)).ravel() for i, (p, u) in enumerate(cases)])
+    out = ctx.alphabeta_batch(probs, sx, idx, SEED, first_problem_id=first_id)
+    res = ctx.fit_batch(probs, sx, max_iters=10000)
+    assert np.array_equal(out["best"]["theta"], res.best["theta"]) and np.array_equal(out["pred"], res.pred)
+    assert np.array_equal(out["resid"], res.resid) and np.all(out["status"] == 0)
+    vary = np.stack([ab.gen_vary_vertices(SEED, first_id + i, n_boot, res.best[i]["theta"]) for i in range(len(cases))])
+    rows, _ = ctx.boot_batch(probs, res.best, res.pred, res.resid, idx, vary)
+    assert np.array_equal(out["rows"], rows)
+    off = 0
+    for i, (p, u) in enumerate(cases):
+        n = len(p)
+        flags = oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL
+        rc, orows, _ = oracle.boot_model(oracle.Problem(p, u, u, 1.0), res.best[i]["theta"], res.pred[off:off + n],
+                                         res.resid[off:off + n], idx[off * n_boot:(off + n) * n_boot].reshape(n_boot, n),
+                                         vary[i], flags=flags, n_threads=4)
+        assert rc == 0 and np.array_equal(out["rows"][i], orows)
+        assert np.array_equal(out["analysis"][i], oracle.analyze(orows), equal_nan=True)
+        off += n
