@@ -95,6 +95,7 @@ def _load() -> C.CDLL:
         "abfit_fit_batch": (C.c_int, [vp, PP, i32, i32, vp, i32, dbl, u32, vp, vp, vp, vp, vp]),
         "abfit_boot_batch": (C.c_int, [vp, PP, i32, vp, vp, vp, i32, vp, vp, i32, dbl, u32, vp, vp]),
         "abfit_divergence": (C.c_int, [vp, vp, vp, vp, i32, i64, vp, i32, dbl, vp, vp, vp, vp, vp, vp]),
+        "abfit_divergence_device": (C.c_int, [vp, vp, vp, vp, i32, i64, vp, i32, dbl, vp, vp, vp, vp, vp, vp, vp, vp]),
         "abfit_batch_create": (C.c_int, [vp, PP, i32, C.POINTER(vp)]),
         "abfit_batch_destroy": (None, [vp]),
         "abfit_batch_upload_starts": (C.c_int, [vp, i32, vp]),
@@ -123,7 +124,7 @@ EXPORTED_SYMBOLS = (
     "abfit_ctx_timer_start abfit_ctx_timer_stop abfit_ctx_sync "
     "abfit_gen_start_simplices abfit_gen_vary_vertices abfit_gen_vary_vertices_batch abfit_gen_resample_idx "
     "abfit_alphabeta_batch abfit_cost_batch "
-    "abfit_model_divergence abfit_fit_batch abfit_boot_batch abfit_divergence abfit_batch_create "
+    "abfit_model_divergence abfit_fit_batch abfit_boot_batch abfit_divergence abfit_divergence_device abfit_batch_create "
     "abfit_batch_destroy abfit_batch_upload_starts abfit_batch_run_fit abfit_batch_download_fit "
     "abfit_batch_upload_boot abfit_batch_run_boot abfit_batch_download_boot abfit_batch_sync "
     "abfit_batch_timing abfit_batch_flops_per_eval abfit_analyze abfit_window_counts abfit_place_sites"
@@ -404,6 +405,28 @@ class Context:
                                   _ptr(diff), _ptr(cnt), _ptr(p0uu), _ptr(methsum), _ptr(nvalid))
         )
         return {"D": D, "diff": diff, "cnt": cnt, "p0uu": p0uu, "methsum": methsum, "nvalid": nvalid}
+
+    def dmatrix_device(self, d_status: int, d_post: int, d_meth: int, S: int, L: int, thr=0.99, seg_offsets=None):
+        """abfit_divergence_device: the three [S][L] inputs are DEVICE pointers (ints); returns the dmatrix() dict plus
+        kernel_ms = (pack pass, pair pass) and launches"""
+        seg = None if seg_offsets is None else np.ascontiguousarray(seg_offsets, dtype=np.int64)
+        W = 1 if seg is None else len(seg) - 1
+        P = S * (S - 1) // 2
+        D = np.empty((W, P))
+        diff = np.empty((W, P), dtype=np.uint64)
+        cnt = np.empty((W, P), dtype=np.uint64)
+        p0uu = np.empty(W)
+        methsum = np.empty((W, S))
+        nvalid = np.empty((W, S), dtype=np.int64)
+        ms = (C.c_float * 2)()
+        launches = C.c_int32()
+        _check(
+            _lib.abfit_divergence_device(self._h, C.c_void_p(d_status), C.c_void_p(d_post), C.c_void_p(d_meth), S, L,
+                                         _ptr(seg), W, thr, _ptr(D), _ptr(diff), _ptr(cnt), _ptr(p0uu), _ptr(methsum),
+                                         _ptr(nvalid), C.cast(ms, C.c_void_p), C.cast(C.byref(launches), C.c_void_p))
+        )
+        return {"D": D, "diff": diff, "cnt": cnt, "p0uu": p0uu, "methsum": methsum, "nvalid": nvalid,
+                "kernel_ms": (ms[0], ms[1]), "launches": launches.value}
 
     def batch(self, probs: Sequence[Problem]) -> "Batch":
         return Batch(self, probs)

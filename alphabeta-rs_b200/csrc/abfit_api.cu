@@ -778,10 +778,10 @@ int abfit_model_divergence(abfit_ctx *ctx, const abfit_problem *prob, const doub
     return 0;
 }
 
-int abfit_divergence(abfit_ctx *ctx, const uint8_t *status, const double *posterior_max, const double *meth_lvl,
-                     int32_t S, int64_t L, const int64_t *seg_offsets, int32_t W, double thr, double *D_out,
-                     uint64_t *diff_out, uint64_t *cnt_out, double *p0uu_out, double *methsum_out,
-                     int64_t *nvalid_out)
+static int divergence_impl(abfit_ctx *ctx, bool device_inputs, const uint8_t *status, const double *posterior_max,
+                           const double *meth_lvl, int32_t S, int64_t L, const int64_t *seg_offsets, int32_t W,
+                           double thr, double *D_out, uint64_t *diff_out, uint64_t *cnt_out, double *p0uu_out,
+                           double *methsum_out, int64_t *nvalid_out, float *ms_out, int32_t *launches_out)
 {
     if (!ctx || !status || !posterior_max || !meth_lvl || S <= 0 || L < 0 || S > 65535) return ABFIT_ERR_ARG;
     int64_t whole[2] = {0, L};
@@ -802,24 +802,28 @@ int abfit_divergence(abfit_ctx *ctx, const uint8_t *status, const double *poster
     DevBuf<double> d_post, d_meth, d_D, d_methsum, d_p0uu;
     DevBuf<unsigned long long> d_diff, d_cnt;
     DevBuf<long long> d_nvalid;
-    if (int rc = d_status.ensure(n)) return rc;
-    if (int rc = d_post.ensure(n)) return rc;
-    if (int rc = d_meth.ensure(n)) return rc;
+    if (!device_inputs) {
+        if (int rc = d_status.ensure(n)) return rc;
+        if (int rc = d_post.ensure(n)) return rc;
+        if (int rc = d_meth.ensure(n)) return rc;
+    }
     if (int rc = d_D.ensure((size_t)W * P)) return rc;
     if (int rc = d_diff.ensure((size_t)W * P)) return rc;
     if (int rc = d_cnt.ensure((size_t)W * P)) return rc;
     if (int rc = d_methsum.ensure((size_t)W * S)) return rc;
     if (int rc = d_nvalid.ensure((size_t)W * S)) return rc;
     if (int rc = d_p0uu.ensure(W)) return rc;
-    if (n) {
+    if (n && !device_inputs) {
         ABFIT_CUDA(cudaMemcpyAsync(d_status.p, status, n, cudaMemcpyHostToDevice, st));
         ABFIT_CUDA(cudaMemcpyAsync(d_post.p, posterior_max, n * 8, cudaMemcpyHostToDevice, st));
         ABFIT_CUDA(cudaMemcpyAsync(d_meth.p, meth_lvl, n * 8, cudaMemcpyHostToDevice, st));
     }
     int launches = 0;
-    if (int rc = run_divergence(st, d_status.p, d_post.p, d_meth.p, S, L, seg_offsets, W, thr, d_D.p, d_diff.p,
-                                d_cnt.p, d_methsum.p, d_nvalid.p, d_p0uu.p, &launches))
+    if (int rc = run_divergence(st, device_inputs ? status : d_status.p, device_inputs ? posterior_max : d_post.p,
+                                device_inputs ? meth_lvl : d_meth.p, S, L, seg_offsets, W, thr, d_D.p, d_diff.p,
+                                d_cnt.p, d_methsum.p, d_nvalid.p, d_p0uu.p, &launches, ms_out))
         return rc;
+    if (launches_out) *launches_out = launches;
     if (D_out && P) ABFIT_CUDA(cudaMemcpyAsync(D_out, d_D.p, (size_t)W * P * 8, cudaMemcpyDeviceToHost, st));
     if (diff_out && P) ABFIT_CUDA(cudaMemcpyAsync(diff_out, d_diff.p, (size_t)W * P * 8, cudaMemcpyDeviceToHost, st));
     if (cnt_out && P) ABFIT_CUDA(cudaMemcpyAsync(cnt_out, d_cnt.p, (size_t)W * P * 8, cudaMemcpyDeviceToHost, st));
@@ -828,6 +832,24 @@ int abfit_divergence(abfit_ctx *ctx, const uint8_t *status, const double *poster
     if (nvalid_out) ABFIT_CUDA(cudaMemcpyAsync(nvalid_out, d_nvalid.p, (size_t)W * S * 8, cudaMemcpyDeviceToHost, st));
     ABFIT_CUDA(cudaStreamSynchronize(st));
     return 0;
+}
+
+int abfit_divergence(abfit_ctx *ctx, const uint8_t *status, const double *posterior_max, const double *meth_lvl,
+                     int32_t S, int64_t L, const int64_t *seg_offsets, int32_t W, double thr, double *D_out,
+                     uint64_t *diff_out, uint64_t *cnt_out, double *p0uu_out, double *methsum_out,
+                     int64_t *nvalid_out)
+{
+    return divergence_impl(ctx, false, status, posterior_max, meth_lvl, S, L, seg_offsets, W, thr, D_out, diff_out,
+                           cnt_out, p0uu_out, methsum_out, nvalid_out, nullptr, nullptr);
+}
+
+int abfit_divergence_device(abfit_ctx *ctx, const uint8_t *d_status, const double *d_posterior_max,
+                            const double *d_meth_lvl, int32_t S, int64_t L, const int64_t *seg_offsets, int32_t W,
+                            double thr, double *D_out, uint64_t *diff_out, uint64_t *cnt_out, double *p0uu_out,
+                            double *methsum_out, int64_t *nvalid_out, float kernel_ms[2], int32_t *launches_out)
+{
+    return divergence_impl(ctx, true, d_status, d_posterior_max, d_meth_lvl, S, L, seg_offsets, W, thr, D_out, diff_out,
+                           cnt_out, p0uu_out, methsum_out, nvalid_out, kernel_ms, launches_out);
 }
 
 // ---------------------------------------------------------------------------------------

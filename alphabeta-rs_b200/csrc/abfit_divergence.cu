@@ -17,7 +17,7 @@
 
 namespace abfit {
 
-constexpr int SB_WORDS = 256;          // words (64 sites) per super-block = one warp's share in k_pack
+constexpr int SB_WORDS = 64;           // words (64 sites) per super-block = one warp's share in k_pack
 constexpr int64_t EXACT_MAX = 65536;   // windows up to this many sites: sequential (bit-exact) methsum
 
 struct SuperBlock {
@@ -49,17 +49,28 @@ k_pack(const uint8_t *__restrict__ status, const double *__restrict__ post, cons
 
     double acc = 0.0;  // lane-local, in site order within the lane
     int nv = 0;
+    // Lane l owns the two adjacent sites 2l, 2l+1 of every 64-site word, so one 16-byte load per lane and
+    // array covers the word (512 contiguous bytes per warp request).  Bit b < 32 of a packed word is site 2b,
+    // bit 32 + b is site 2b + 1: any fixed permutation of the sites inside a word is as good as any other for
+    // the popcounts of pass 2, as long as every sample and plane uses the same one.
+    const bool vec = ((reinterpret_cast<uintptr_t>(po + sb.first_site) | reinterpret_cast<uintptr_t>(me + sb.first_site)) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(st + sb.first_site) & 1) == 0;
 #pragma unroll 4
     for (int w = 0; w < sb.n_words; ++w) {
-        const int64_t base = sb.first_site + (int64_t)w * 64;
-        const int64_t i0 = base + lane, i1 = base + 32 + lane;
+        const int64_t i0 = sb.first_site + (int64_t)w * 64 + 2 * lane, i1 = i0 + 1;
         const bool in0 = i0 < sb.end_site, in1 = i1 < sb.end_site;
-        const double p0 = in0 ? __ldcs(po + i0) : -1.0;
-        const double p1 = in1 ? __ldcs(po + i1) : -1.0;
-        const double m0 = in0 ? __ldcs(me + i0) : 0.0;
-        const double m1 = in1 ? __ldcs(me + i1) : 0.0;
-        const int s0 = in0 ? (int)__ldcs(st + i0) : 0;
-        const int s1 = in1 ? (int)__ldcs(st + i1) : 0;
+        double p0 = -1.0, p1 = -1.0, m0 = 0.0, m1 = 0.0;
+        int s0 = 0, s1 = 0;
+        if (vec && in1) {
+            const double2 pp = __ldcs(reinterpret_cast<const double2 *>(po + i0));
+            const double2 mm = __ldcs(reinterpret_cast<const double2 *>(me + i0));
+            const unsigned short ss = __ldcs(reinterpret_cast<const unsigned short *>(st + i0));
+            p0 = pp.x; p1 = pp.y; m0 = mm.x; m1 = mm.y;
+            s0 = ss & 0xff; s1 = ss >> 8;
+        } else {
+            if (in0) { p0 = __ldcs(po + i0); m0 = __ldcs(me + i0); s0 = (int)__ldcs(st + i0); }
+            if (in1) { p1 = __ldcs(po + i1); m1 = __ldcs(me + i1); s1 = (int)__ldcs(st + i1); }
+        }
         const bool v0 = in0 && (p0 >= thr), v1 = in1 && (p1 >= thr);
         const unsigned bv0 = __ballot_sync(FULL, v0), bv1 = __ballot_sync(FULL, v1);
         const unsigned b10 = __ballot_sync(FULL, s0 >= 1), b11 = __ballot_sync(FULL, s1 >= 1);
@@ -190,7 +201,7 @@ __global__ void k_p0uu(const double *__restrict__ methsum, const long long *__re
 int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_post, const double *d_meth, int S,
                    int64_t L, const int64_t *h_seg, int W, double thr, double *d_D, unsigned long long *d_diff,
                    unsigned long long *d_cnt, double *d_methsum, long long *d_nvalid, double *d_p0uu,
-                   int *launches)
+                   int *launches, float *ms)
 {
     // host-side segmentation tables
     std::vector<SuperBlock> sbs;
@@ -297,6 +308,11 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
         DV_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)W * P * 8, st));
     }
 
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (ms) {
+        for (auto &e : ev) DV_CUDA(cudaEventCreate(&e));
+        DV_CUDA(cudaEventRecord(ev[0], st));
+    }
     if (n_sb > 0) {
         dim3 grid((n_sb + 7) / 8, S);
         k_pack<<<grid, 256, 0, st>>>(d_status, d_post, d_meth, L, TW, d_sbs, n_sb, thr, d_V, d_T1, d_T2,
@@ -304,6 +320,7 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
         DV_CUDA(cudaGetLastError());
         ++*launches;
     }
+    if (ms) DV_CUDA(cudaEventRecord(ev[1], st));
     if (P > 0 && !items.empty()) {
         const size_t smem = (size_t)S * cw_max * 24;
         if (smem > 48 * 1024)
@@ -331,7 +348,13 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
             ++*launches;
         }
     }
+    if (ms) DV_CUDA(cudaEventRecord(ev[2], st));
     DV_CUDA(cudaStreamSynchronize(st));
+    if (ms) {  // ms[0] = k_pack (the HBM-bound pass), ms[1] = all-pairs popcount + finalisation
+        cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
+        cudaEventElapsedTime(&ms[1], ev[1], ev[2]);
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
     cleanup();
 #undef DV_CUDA
     return 0;

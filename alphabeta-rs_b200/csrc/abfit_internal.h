@@ -68,6 +68,6 @@ int max_dynamic_smem(int device);
 int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_post, const double *d_meth, int S,
                    int64_t L, const int64_t *h_seg, int W, double thr, double *d_D, unsigned long long *d_diff,
                    unsigned long long *d_cnt, double *d_methsum, long long *d_nvalid, double *d_p0uu,
-                   int *launches);
+                   int *launches, float *ms /* optional [2]: pack pass, pair pass + finalisation */);
 
 }  // namespace abfit

@@ -195,6 +195,15 @@ int abfit_divergence(abfit_ctx *ctx, const uint8_t *status, const double *poster
                      uint64_t *diff_out, uint64_t *cnt_out, double *p0uu_out, double *methsum_out,
                      int64_t *nvalid_out);
 
+/* The same with the three input arrays already in device memory (site tables that stay resident between
+ * calls; bench: HBM roofline of the packing pass).  seg_offsets and all outputs are host memory.
+ * kernel_ms[0] = device time of the packing pass (streams 17 B per sample-site), kernel_ms[1] = all-pairs
+ * popcounts + finalisation; launches_out = kernels launched.  Both may be NULL. */
+int abfit_divergence_device(abfit_ctx *ctx, const uint8_t *d_status, const double *d_posterior_max,
+                            const double *d_meth_lvl, int32_t S, int64_t L, const int64_t *seg_offsets, int32_t W,
+                            double thr, double *D_out, uint64_t *diff_out, uint64_t *cnt_out, double *p0uu_out,
+                            double *methsum_out, int64_t *nvalid_out, float kernel_ms[2], int32_t *launches_out);
+
 /* ---- staged, device-resident interface ------------------------------------
  * Same computation as abfit_fit_batch + abfit_boot_batch, split into upload /
  * run / download so a caller (bench.py, the metaprofile driver) can keep inputs
