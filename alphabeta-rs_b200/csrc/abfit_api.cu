@@ -80,6 +80,7 @@ struct abfit_batch {
     // fit
     int n_starts = 0;
     DevBuf<double> d_simplices, d_xscratch;
+    DevBuf<double> d_lm;  // lane state of the large-pedigree variants (shape.big)
     DevBuf<WorkItem> d_items;
     int n_items = 0;
     DevBuf<abfit_fit> d_all, d_best;
@@ -117,6 +118,20 @@ static void parallel_for(int32_t n, F f)
             for (int32_t i = t; i < n; i += nt) f(i);
         });
     for (auto &x : th) x.join();
+}
+
+// scratch of the large-pedigree kernels for `slots` warps (grows only); {nullptr} when the batch is not big
+static int big_scratch(abfit_batch *b, size_t slots, BigScratch &out)
+{
+    out = BigScratch();
+    if (!b->shape.big) return 0;
+    const size_t stride = (size_t)std::max(b->shape.n_lane_max, 1) * 32;
+    if (int rc = b->d_lm.ensure(slots * stride)) return rc;
+    if (int rc = b->d_xscratch.ensure(slots * 20 * 32)) return rc;
+    out.lm = b->d_lm.p;
+    out.lm_stride = stride;
+    out.x = b->d_xscratch.p;
+    return 0;
 }
 
 extern "C" {
@@ -402,7 +417,7 @@ int abfit_batch_upload_starts(abfit_batch *b, int32_t n_starts, const double *si
             ABFIT_CUDA(cudaMemcpyAsync(b->d_items.p, items.data(), items.size() * sizeof(WorkItem),
                                        cudaMemcpyHostToDevice, b->ctx->stream));
         ABFIT_CUDA(cudaStreamSynchronize(b->ctx->stream));
-        if (b->shape.x_global)
+        if (b->shape.x_global && !b->shape.big)
             if (int rc = b->d_xscratch.ensure((size_t)std::max(b->n_items, 1) * b->shape.n_warps * 20 * 32)) return rc;
         if (int rc = b->d_all.ensure((size_t)b->n_probs * n_starts)) return rc;
         if (int rc = b->d_best.ensure(b->n_probs)) return rc;
@@ -427,13 +442,15 @@ int abfit_batch_run_fit(abfit_batch *b, int32_t max_iters, double sd_tol, uint32
     ABFIT_CUDA(cudaMemsetAsync(b->d_all.p, 0xFF, (size_t)b->n_probs * b->n_starts * sizeof(abfit_fit), st));
     ABFIT_CUDA(cudaMemsetAsync(b->d_evals_fit.p, 0, (size_t)b->n_probs * 8, st));
     ABFIT_CUDA(cudaEventRecord(b->ev[0], st));
+    BigScratch big;
+    if (int rc = big_scratch(b, (size_t)std::max(std::max(b->n_items, 1) * b->shape.n_warps, b->n_probs), big)) return rc;
     if (int rc = launch_fit_starts(st, b->pools, b->d_items.p, b->n_items, b->shape.n_warps, b->d_simplices.p,
                                    b->n_starts, nm, b->d_all.p, b->d_evals_fit.p, b->shape.smem_fit,
-                                   b->shape.d_shared, b->shape.x_global ? b->d_xscratch.p : nullptr))
+                                   b->shape.d_shared, b->shape.x_global ? b->d_xscratch.p : nullptr, big))
         return rc;
     ABFIT_CUDA(cudaEventRecord(b->ev[1], st));
     if (int rc = launch_select(st, b->pools, b->n_probs, b->n_starts, b->d_all.p, b->d_best.p, b->d_pred.p,
-                               b->d_resid.p, b->d_status.p, b->shape.smem_aux, b->shape.d_shared_aux))
+                               b->d_resid.p, b->d_status.p, b->shape.smem_aux, b->shape.d_shared_aux, big))
         return rc;
     ABFIT_CUDA(cudaEventRecord(b->ev[2], st));
     b->ev_fit = true;
@@ -544,11 +561,15 @@ int abfit_batch_run_boot(abfit_batch *b, int32_t max_iters, double sd_tol, uint3
                                             (int64_t)((b->hp.max_pairs + 3) / 4) * 32, nm, b->d_rows.p, b->d_bootfits.p,
                                             b->d_evals_boot.p, b->shape.smem_boot_gather, b->d_booterr.p))
             return rc;
-    } else if (int rc = launch_fit_boot(st, b->pools, b->d_boot_items.p, b->n_boot_items, b->n_boot, b->d_best.p,
-                                 b->d_pred.p, b->d_resid.p, b->d_idx.p, b->d_vary.p, b->d_scratch.p,
-                                 (int64_t)b->hp.max_pairs * 32, nm, b->d_rows.p, b->d_bootfits.p,
-                                 b->d_evals_boot.p, b->shape.smem_boot))
-        return rc;
+    } else {
+        BigScratch big;
+        if (int rc = big_scratch(b, (size_t)std::max(b->n_boot_items, 1), big)) return rc;
+        if (int rc = launch_fit_boot(st, b->pools, b->d_boot_items.p, b->n_boot_items, b->n_boot, b->d_best.p,
+                                     b->d_pred.p, b->d_resid.p, b->d_idx.p, b->d_vary.p, b->d_scratch.p,
+                                     (int64_t)b->hp.max_pairs * 32, nm, b->d_rows.p, b->d_bootfits.p,
+                                     b->d_evals_boot.p, b->shape.smem_boot, big))
+            return rc;
+    }
     ABFIT_CUDA(cudaEventRecord(b->ev[4], st));
     b->ev_boot = true;
     b->boot_done = true;
@@ -743,8 +764,10 @@ int abfit_cost_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs
     if (int rc = d_items.ensure(items.size())) return rc;
     ABFIT_CUDA(cudaMemcpyAsync(d_th.p, th.data(), (size_t)B * 32, cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
+    BigScratch big;
+    if (int rc = big_scratch(b, std::max<size_t>(items.size(), 1), big)) return rc;
     if (int rc = launch_cost_batch(st, b->pools, d_items.p, (int)items.size(), d_th.p, d_cost.p, d_lse.p,
-                                   b->shape.smem_aux, b->shape.d_shared_aux))
+                                   b->shape.smem_aux, b->shape.d_shared_aux, big))
         return rc;
     std::vector<double> hc(B), hl(B);
     ABFIT_CUDA(cudaMemcpyAsync(hc.data(), d_cost.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
@@ -769,8 +792,10 @@ int abfit_model_divergence(abfit_ctx *ctx, const abfit_problem *prob, const doub
     if (int rc = d_dt.ensure(prob->n_pairs)) return rc;
     if (int rc = d_puu.ensure(1)) return rc;
     ABFIT_CUDA(cudaMemcpyAsync(d_th.p, theta, 32, cudaMemcpyHostToDevice, st));
+    BigScratch big;
+    if (int rc = big_scratch(wb, 1, big)) return rc;
     if (int rc = launch_model_divergence(st, wb->pools, d_th.p, d_dt.p, d_puu.p,
-                                         smem_need(wb->hp.probs[0], 0, false, 1)))
+                                         wb->shape.big ? wb->shape.smem_aux : smem_need(wb->hp.probs[0], 0, false, 1), big))
         return rc;
     ABFIT_CUDA(cudaMemcpyAsync(dt1t2_out, d_dt.p, (size_t)prob->n_pairs * 8, cudaMemcpyDeviceToHost, st));
     if (p_uu_out) ABFIT_CUDA(cudaMemcpyAsync(p_uu_out, d_puu.p, 8, cudaMemcpyDeviceToHost, st));

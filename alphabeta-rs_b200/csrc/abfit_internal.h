@@ -38,17 +38,26 @@ int cuda_fail(cudaError_t e, const char *what);
         if (e_ != cudaSuccess) return ::abfit::cuda_fail(e_, #call); \
     } while (0)
 
+// scratch of the large-pedigree variants (lane state in global memory); lm == nullptr: regular kernels
+struct BigScratch {
+    double *lm = nullptr;   // [slot][lm_stride] doubles, slot = block * warps + warp
+    size_t lm_stride = 0;   // n_lane_max * 32
+    double *x = nullptr;    // simplex vertices [slot][20 * 32]
+};
+
 // ---- launchers (abfit_kernels.cu) ---------------------------------------------------
 int launch_fit_starts(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_warps,
                       const double *simplices, int n_starts, NMParams nm, abfit_fit *all_out,
-                      unsigned long long *evals_per_prob, size_t smem_bytes, bool d_in_shared, double *x_scratch);
+                      unsigned long long *evals_per_prob, size_t smem_bytes, bool d_in_shared, double *x_scratch,
+                      const BigScratch &big);
 int launch_select(cudaStream_t st, const DevicePools &P, int n_probs, int n_starts, const abfit_fit *all,
                   abfit_fit *best_out, double *pred, double *resid, int32_t *prob_status, size_t smem_bytes,
-                  bool d_in_shared);
+                  bool d_in_shared, const BigScratch &big);
 int launch_fit_boot(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_boot,
                     const abfit_fit *best, const double *pred, const double *resid, const int32_t *resample_idx,
                     const double *vary, double *dstar_scratch, int64_t scratch_stride, NMParams nm,
-                    double *rows_out, abfit_fit *fits_out, unsigned long long *evals_per_prob, size_t smem_bytes);
+                    double *rows_out, abfit_fit *fits_out, unsigned long long *evals_per_prob, size_t smem_bytes,
+                    const BigScratch &big);
 // index-tile variant (n_pairs <= 8191): idx_scratch holds scratch_stride uint2 per block, scratch_stride >= 32 * ceil(N/4)
 size_t smem_need_boot_gather(const DevProblem &pb);
 int launch_fit_boot_gather(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_boot,
@@ -57,9 +66,10 @@ int launch_fit_boot_gather(cudaStream_t st, const DevicePools &P, const WorkItem
                            double *rows_out, abfit_fit *fits_out, unsigned long long *evals_per_prob, size_t smem_bytes,
                            int *err_flag);
 int launch_cost_batch(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items,
-                      const double *theta, double *cost_out, double *lse_out, size_t smem_bytes, bool d_in_shared);
+                      const double *theta, double *cost_out, double *lse_out, size_t smem_bytes, bool d_in_shared,
+                      const BigScratch &big);
 int launch_model_divergence(cudaStream_t st, const DevicePools &P, const double *theta4, double *dt_out,
-                            double *puu_out, size_t smem_bytes);
+                            double *puu_out, size_t smem_bytes, const BigScratch &big);
 int launch_fp64_peak(cudaStream_t st, int blocks, int threads, int iters, double *sink);
 int max_dynamic_smem(int device);
 

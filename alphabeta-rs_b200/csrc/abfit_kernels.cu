@@ -82,6 +82,42 @@ __device__ __forceinline__ Carved carve_and_stage(const DevProblem &pb, const De
     return cv;
 }
 
+// Pedigrees whose per-lane model state does not fit in shared memory (hundreds of distinct triples: C5's
+// 19 900-pair pedigree needs 836 doubles per lane): lane state, simplex vertices, D and the pair offsets all
+// live in global memory (an L2-resident scratch, [index][32 lanes] so every access is one coalesced 256-byte
+// request); only the simplex costs, the program and the queue stay in shared memory.  Same code, same bits —
+// just slower per evaluation.
+__device__ __forceinline__ Carved carve_big(const DevProblem &pb, const DevicePools &P, bool with_nm,
+                                            double *x_scratch, double *lm_scratch, size_t lm_stride)
+{
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, n_warps = nthr >> 5;
+    const size_t slot = (size_t)blockIdx.x * n_warps + warp;
+    Carved cv;
+    cv.ctx.lm = lm_scratch + slot * lm_stride;
+    if (with_nm) {
+        cv.simplex.X = x_scratch + slot * (20 * 32) + lane;
+        cv.simplex.C = smem + (size_t)warp * (5 * 32) + lane;
+    } else {
+        cv.simplex.X = nullptr;
+        cv.simplex.C = nullptr;
+    }
+    OpWord *ops = reinterpret_cast<OpWord *>(smem + (with_nm ? (size_t)n_warps * (5 * 32) : 0));
+    cv.queue = reinterpret_cast<int *>(ops + pb.n_ops);
+    for (int i = tid; i < pb.n_ops; i += nthr) ops[i] = P.ops[pb.ops_off + i];
+    cv.ctx.D = P.D + pb.d_off;
+    cv.ctx.offs = P.offs + pb.offs_off;
+    cv.ctx.ops = ops;
+    cv.ctx.n_pairs = pb.n_pairs;
+    cv.ctx.n_ops = pb.n_ops;
+    cv.ctx.p_uu0 = pb.p_uu0;
+    cv.ctx.p_mm0 = pb.p_mm0;
+    cv.ctx.eqp = pb.eqp;
+    cv.ctx.penw = pb.penw;
+    return cv;
+}
+
 __device__ __forceinline__ void store_fit(abfit_fit *dst, const abfit_fit &r)
 {
     // 64-byte record written as four 16-byte vector stores (dst is 64-byte aligned)
@@ -114,16 +150,18 @@ __device__ __forceinline__ int queue_take(int *queue, unsigned m, int lane, int 
 // ---------------------------------------------------------------------------------
 // multi-start Nelder-Mead
 // ---------------------------------------------------------------------------------
-template <bool D_SHARED, bool X_GLOBAL>
+template <bool D_SHARED, bool X_GLOBAL, bool BIG>
 __global__ void __launch_bounds__(128, X_GLOBAL ? 4 : 3)
 k_fit_starts(DevicePools P, const WorkItem *__restrict__ items, const double *__restrict__ simplices,
              int n_starts, NMParams nm, abfit_fit *__restrict__ all_out,
-             unsigned long long *__restrict__ evals_per_prob, double *x_scratch)
+             unsigned long long *__restrict__ evals_per_prob, double *x_scratch, double *lm_scratch,
+             size_t lm_stride)
 {
     const int lane = threadIdx.x & 31;
     const WorkItem it = items[blockIdx.x];
     const DevProblem pb = P.probs[it.prob];
-    Carved cv = carve_and_stage<D_SHARED>(pb, P, X_GLOBAL ? 5 : 25, x_scratch);
+    Carved cv = BIG ? carve_big(pb, P, true, x_scratch, lm_scratch, lm_stride)
+                    : carve_and_stage<D_SHARED>(pb, P, X_GLOBAL ? 5 : 25, x_scratch);
     if (threadIdx.x == 0) *cv.queue = it.first;
     __syncthreads();
     const WarpCtx &c = cv.ctx;
@@ -171,15 +209,16 @@ k_fit_starts(DevicePools P, const WorkItem *__restrict__ items, const double *__
 // ---------------------------------------------------------------------------------
 // best-of-starts (warp-shuffle argmin) + predicted divergence / residuals of the best
 // ---------------------------------------------------------------------------------
-template <bool D_SHARED>
+template <bool D_SHARED, bool BIG>
 __global__ void __launch_bounds__(32)
 k_select(DevicePools P, int n_starts, const abfit_fit *__restrict__ all, abfit_fit *__restrict__ best_out,
-         double *__restrict__ pred, double *__restrict__ resid, int32_t *__restrict__ prob_status)
+         double *__restrict__ pred, double *__restrict__ resid, int32_t *__restrict__ prob_status,
+         double *lm_scratch, size_t lm_stride)
 {
     const int lane = threadIdx.x;
     const int p = blockIdx.x;
     const DevProblem pb = P.probs[p];
-    Carved cv = carve_and_stage<D_SHARED>(pb, P, 0);
+    Carved cv = BIG ? carve_big(pb, P, false, nullptr, lm_scratch, lm_stride) : carve_and_stage<D_SHARED>(pb, P, 0);
     __syncwarp();
     const WarpCtx &c = cv.ctx;
 
@@ -247,18 +286,19 @@ k_select(DevicePools P, int n_starts, const abfit_fit *__restrict__ all, abfit_f
 // The column is built cooperatively by the warp into a [n_pairs][32] scratch tile
 // (coalesced on the lane axis), then read once per evaluation.
 // ---------------------------------------------------------------------------------
+template <bool BIG>
 __global__ void __launch_bounds__(32)
 k_fit_boot(DevicePools P, const WorkItem *__restrict__ items, int n_boot, const abfit_fit *__restrict__ best,
            const double *__restrict__ pred, const double *__restrict__ resid,
            const int32_t *__restrict__ resample_idx, const double *__restrict__ vary,
            double *__restrict__ dstar_scratch, long long scratch_stride, NMParams nm,
            double *__restrict__ rows_out, abfit_fit *__restrict__ fits_out,
-           unsigned long long *__restrict__ evals_per_prob)
+           unsigned long long *__restrict__ evals_per_prob, double *x_scratch, double *lm_scratch, size_t lm_stride)
 {
     const int lane = threadIdx.x;
     const WorkItem it = items[blockIdx.x];
     const DevProblem pb = P.probs[it.prob];
-    Carved cv = carve_and_stage<false>(pb, P, 25);
+    Carved cv = BIG ? carve_big(pb, P, true, x_scratch, lm_scratch, lm_stride) : carve_and_stage<false>(pb, P, 25);
     __syncwarp();
     const WarpCtx &c = cv.ctx;
     const LaneSimplex &S = cv.simplex;
@@ -435,15 +475,15 @@ k_fit_boot_gather(DevicePools P, const WorkItem *__restrict__ items, int n_boot,
 // ---------------------------------------------------------------------------------
 // objective only (test hook / CostFunction seam)
 // ---------------------------------------------------------------------------------
-template <bool D_SHARED>
+template <bool D_SHARED, bool BIG>
 __global__ void __launch_bounds__(32)
 k_cost_batch(DevicePools P, const WorkItem *__restrict__ items, const double *__restrict__ theta,
-             double *__restrict__ cost_out, double *__restrict__ lse_out)
+             double *__restrict__ cost_out, double *__restrict__ lse_out, double *lm_scratch, size_t lm_stride)
 {
     const int lane = threadIdx.x;
     const WorkItem it = items[blockIdx.x];
     const DevProblem pb = P.probs[it.prob];
-    Carved cv = carve_and_stage<D_SHARED>(pb, P, 0);
+    Carved cv = BIG ? carve_big(pb, P, false, nullptr, lm_scratch, lm_stride) : carve_and_stage<D_SHARED>(pb, P, 0);
     __syncwarp();
     const DBroadcast Dat{cv.ctx.D};
     if (lane < it.count) {
@@ -454,13 +494,14 @@ k_cost_batch(DevicePools P, const WorkItem *__restrict__ items, const double *__
     }
 }
 
+template <bool BIG>
 __global__ void __launch_bounds__(32)
 k_model_div(DevicePools P, const double *__restrict__ theta4, double *__restrict__ dt_out,
-            double *__restrict__ puu_out)
+            double *__restrict__ puu_out, double *lm_scratch, size_t lm_stride)
 {
     const int lane = threadIdx.x;
     const DevProblem pb = P.probs[0];
-    Carved cv = carve_and_stage<false>(pb, P, 0);
+    Carved cv = BIG ? carve_big(pb, P, false, nullptr, lm_scratch, lm_stride) : carve_and_stage<false>(pb, P, 0);
     __syncwarp();
     const WarpCtx &c = cv.ctx;
     model_divergence(c, lane, theta4[0], theta4[1], theta4[2]);
@@ -509,52 +550,58 @@ static int prep_kernel(K kernel, size_t smem_bytes)
     return 0;
 }
 
-template <bool D_SHARED, bool X_GLOBAL>
+template <bool D_SHARED, bool X_GLOBAL, bool BIG>
 static int launch_fit_starts_t(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_warps,
                                const double *simplices, int n_starts, NMParams nm, abfit_fit *all_out,
-                               unsigned long long *evals_per_prob, size_t smem_bytes, double *x_scratch)
+                               unsigned long long *evals_per_prob, size_t smem_bytes, double *x_scratch,
+                               const BigScratch &big)
 {
-    if (int rc = prep_kernel(k_fit_starts<D_SHARED, X_GLOBAL>, smem_bytes)) return rc;
+    if (int rc = prep_kernel(k_fit_starts<D_SHARED, X_GLOBAL, BIG>, smem_bytes)) return rc;
     if (getenv("ABFIT_DEV_VERBOSE")) {
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fit_starts<D_SHARED, X_GLOBAL>, 32 * n_warps, smem_bytes);
-        fprintf(stderr, "[abfit] k_fit_starts<D_SHARED=%d,X_GLOBAL=%d>: %d blocks x %d warps, %zu B smem/block, %d blocks/SM\n",
-                (int)D_SHARED, (int)X_GLOBAL, n_items, n_warps, smem_bytes, nb);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fit_starts<D_SHARED, X_GLOBAL, BIG>, 32 * n_warps, smem_bytes);
+        fprintf(stderr, "[abfit] k_fit_starts<D_SHARED=%d,X_GLOBAL=%d,BIG=%d>: %d blocks x %d warps, %zu B smem/block, %d blocks/SM\n",
+                (int)D_SHARED, (int)X_GLOBAL, (int)BIG, n_items, n_warps, smem_bytes, nb);
     }
-    k_fit_starts<D_SHARED, X_GLOBAL><<<n_items, 32 * n_warps, smem_bytes, st>>>(P, items, simplices, n_starts, nm,
-                                                                                 all_out, evals_per_prob, x_scratch);
+    k_fit_starts<D_SHARED, X_GLOBAL, BIG><<<n_items, 32 * n_warps, smem_bytes, st>>>(
+        P, items, simplices, n_starts, nm, all_out, evals_per_prob, x_scratch, big.lm, big.lm_stride);
     ABFIT_CUDA(cudaGetLastError());
     return 0;
 }
 
 int launch_fit_starts(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_warps,
                       const double *simplices, int n_starts, NMParams nm, abfit_fit *all_out,
-                      unsigned long long *evals_per_prob, size_t smem_bytes, bool d_in_shared, double *x_scratch)
+                      unsigned long long *evals_per_prob, size_t smem_bytes, bool d_in_shared, double *x_scratch,
+                      const BigScratch &big)
 {
     if (n_items <= 0) return 0;
     if (const char *pad = getenv("ABFIT_DEV_SMEM_PAD")) smem_bytes += (size_t)atoi(pad);  // occupancy experiments
-    if (d_in_shared)
-        return x_scratch ? launch_fit_starts_t<true, true>(st, P, items, n_items, n_warps, simplices, n_starts, nm, all_out,
-                                                           evals_per_prob, smem_bytes, x_scratch)
-                         : launch_fit_starts_t<true, false>(st, P, items, n_items, n_warps, simplices, n_starts, nm,
-                                                            all_out, evals_per_prob, smem_bytes, x_scratch);
-    return x_scratch ? launch_fit_starts_t<false, true>(st, P, items, n_items, n_warps, simplices, n_starts, nm, all_out,
-                                                        evals_per_prob, smem_bytes, x_scratch)
-                     : launch_fit_starts_t<false, false>(st, P, items, n_items, n_warps, simplices, n_starts, nm, all_out,
-                                                         evals_per_prob, smem_bytes, x_scratch);
+#define ABFIT_FS(DS, XG, BG)                                                                                         \
+    launch_fit_starts_t<DS, XG, BG>(st, P, items, n_items, n_warps, simplices, n_starts, nm, all_out, evals_per_prob, \
+                                    smem_bytes, x_scratch, big)
+    if (big.lm) return ABFIT_FS(false, true, true);
+    if (d_in_shared) return x_scratch ? ABFIT_FS(true, true, false) : ABFIT_FS(true, false, false);
+    return x_scratch ? ABFIT_FS(false, true, false) : ABFIT_FS(false, false, false);
+#undef ABFIT_FS
 }
 
 int launch_select(cudaStream_t st, const DevicePools &P, int n_probs, int n_starts, const abfit_fit *all,
                   abfit_fit *best_out, double *pred, double *resid, int32_t *prob_status, size_t smem_bytes,
-                  bool d_in_shared)
+                  bool d_in_shared, const BigScratch &big)
 {
     if (n_probs <= 0) return 0;
-    if (d_in_shared) {
-        if (int rc = prep_kernel(k_select<true>, smem_bytes)) return rc;
-        k_select<true><<<n_probs, 32, smem_bytes, st>>>(P, n_starts, all, best_out, pred, resid, prob_status);
+    if (big.lm) {
+        if (int rc = prep_kernel(k_select<false, true>, smem_bytes)) return rc;
+        k_select<false, true><<<n_probs, 32, smem_bytes, st>>>(P, n_starts, all, best_out, pred, resid, prob_status,
+                                                               big.lm, big.lm_stride);
+    } else if (d_in_shared) {
+        if (int rc = prep_kernel(k_select<true, false>, smem_bytes)) return rc;
+        k_select<true, false><<<n_probs, 32, smem_bytes, st>>>(P, n_starts, all, best_out, pred, resid, prob_status,
+                                                               nullptr, 0);
     } else {
-        if (int rc = prep_kernel(k_select<false>, smem_bytes)) return rc;
-        k_select<false><<<n_probs, 32, smem_bytes, st>>>(P, n_starts, all, best_out, pred, resid, prob_status);
+        if (int rc = prep_kernel(k_select<false, false>, smem_bytes)) return rc;
+        k_select<false, false><<<n_probs, 32, smem_bytes, st>>>(P, n_starts, all, best_out, pred, resid, prob_status,
+                                                                nullptr, 0);
     }
     ABFIT_CUDA(cudaGetLastError());
     return 0;
@@ -563,13 +610,21 @@ int launch_select(cudaStream_t st, const DevicePools &P, int n_probs, int n_star
 int launch_fit_boot(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_boot,
                     const abfit_fit *best, const double *pred, const double *resid, const int32_t *resample_idx,
                     const double *vary, double *dstar_scratch, int64_t scratch_stride, NMParams nm,
-                    double *rows_out, abfit_fit *fits_out, unsigned long long *evals_per_prob, size_t smem_bytes)
+                    double *rows_out, abfit_fit *fits_out, unsigned long long *evals_per_prob, size_t smem_bytes,
+                    const BigScratch &big)
 {
     if (n_items <= 0) return 0;
-    if (int rc = prep_kernel(k_fit_boot, smem_bytes)) return rc;
-    k_fit_boot<<<n_items, 32, smem_bytes, st>>>(P, items, n_boot, best, pred, resid, resample_idx, vary,
-                                                dstar_scratch, (long long)scratch_stride, nm, rows_out, fits_out,
-                                                evals_per_prob);
+    if (big.lm) {
+        if (int rc = prep_kernel(k_fit_boot<true>, smem_bytes)) return rc;
+        k_fit_boot<true><<<n_items, 32, smem_bytes, st>>>(P, items, n_boot, best, pred, resid, resample_idx, vary,
+                                                          dstar_scratch, (long long)scratch_stride, nm, rows_out,
+                                                          fits_out, evals_per_prob, big.x, big.lm, big.lm_stride);
+    } else {
+        if (int rc = prep_kernel(k_fit_boot<false>, smem_bytes)) return rc;
+        k_fit_boot<false><<<n_items, 32, smem_bytes, st>>>(P, items, n_boot, best, pred, resid, resample_idx, vary,
+                                                           dstar_scratch, (long long)scratch_stride, nm, rows_out,
+                                                           fits_out, evals_per_prob, nullptr, nullptr, 0);
+    }
     ABFIT_CUDA(cudaGetLastError());
     return 0;
 }
@@ -590,25 +645,34 @@ int launch_fit_boot_gather(cudaStream_t st, const DevicePools &P, const WorkItem
 }
 
 int launch_cost_batch(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items,
-                      const double *theta, double *cost_out, double *lse_out, size_t smem_bytes, bool d_in_shared)
+                      const double *theta, double *cost_out, double *lse_out, size_t smem_bytes, bool d_in_shared,
+                      const BigScratch &big)
 {
     if (n_items <= 0) return 0;
-    if (d_in_shared) {
-        if (int rc = prep_kernel(k_cost_batch<true>, smem_bytes)) return rc;
-        k_cost_batch<true><<<n_items, 32, smem_bytes, st>>>(P, items, theta, cost_out, lse_out);
+    if (big.lm) {
+        if (int rc = prep_kernel(k_cost_batch<false, true>, smem_bytes)) return rc;
+        k_cost_batch<false, true><<<n_items, 32, smem_bytes, st>>>(P, items, theta, cost_out, lse_out, big.lm, big.lm_stride);
+    } else if (d_in_shared) {
+        if (int rc = prep_kernel(k_cost_batch<true, false>, smem_bytes)) return rc;
+        k_cost_batch<true, false><<<n_items, 32, smem_bytes, st>>>(P, items, theta, cost_out, lse_out, nullptr, 0);
     } else {
-        if (int rc = prep_kernel(k_cost_batch<false>, smem_bytes)) return rc;
-        k_cost_batch<false><<<n_items, 32, smem_bytes, st>>>(P, items, theta, cost_out, lse_out);
+        if (int rc = prep_kernel(k_cost_batch<false, false>, smem_bytes)) return rc;
+        k_cost_batch<false, false><<<n_items, 32, smem_bytes, st>>>(P, items, theta, cost_out, lse_out, nullptr, 0);
     }
     ABFIT_CUDA(cudaGetLastError());
     return 0;
 }
 
 int launch_model_divergence(cudaStream_t st, const DevicePools &P, const double *theta4, double *dt_out,
-                            double *puu_out, size_t smem_bytes)
+                            double *puu_out, size_t smem_bytes, const BigScratch &big)
 {
-    if (int rc = prep_kernel(k_model_div, smem_bytes)) return rc;
-    k_model_div<<<1, 32, smem_bytes, st>>>(P, theta4, dt_out, puu_out);
+    if (big.lm) {
+        if (int rc = prep_kernel(k_model_div<true>, smem_bytes)) return rc;
+        k_model_div<true><<<1, 32, smem_bytes, st>>>(P, theta4, dt_out, puu_out, big.lm, big.lm_stride);
+    } else {
+        if (int rc = prep_kernel(k_model_div<false>, smem_bytes)) return rc;
+        k_model_div<false><<<1, 32, smem_bytes, st>>>(P, theta4, dt_out, puu_out, nullptr, 0);
+    }
     ABFIT_CUDA(cudaGetLastError());
     return 0;
 }

@@ -296,23 +296,38 @@ int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm,
         }
         if (best_w >= 4) break;  // only give up the shared D column when occupancy would collapse
     }
-    if (best_w <= 0) {
-        set_error("per-lane model state of one pedigree needs " + std::to_string(worst(5, false, 1)) +
-                  " B of shared memory (limit " + std::to_string(smem_cap) + "): too many distinct (t0,t1,t2) triples");
-        return ABFIT_ERR_TOO_LARGE;
+    out.n_lane_max = 0;
+    size_t max_ops = 0;
+    for (auto &pb : hp.probs) {
+        out.n_lane_max = std::max(out.n_lane_max, pb.n_lane);
+        max_ops = std::max(max_ops, (size_t)pb.n_ops);
     }
     out.smem_boot = worst(25, false, 1);
+    out.d_shared_aux = worst(0, true, 1) <= smem_cap / 2;
+    out.smem_aux = worst(0, out.d_shared_aux, 1);
+    out.big = best_w <= 0 || out.smem_boot > smem_cap || out.smem_aux > smem_cap || getenv("ABFIT_DEV_BIG");
+    if (out.big) {
+        // lane state, vertices, D and offsets in global scratch (carve_big): shared memory only holds the simplex
+        // costs, the program and the queue word
+        out.n_warps = (force ? atoi(force) : (fits_per_prob >= 256 ? 4 : 1));
+        out.d_shared = false;
+        out.x_global = true;
+        out.smem_fit = ((size_t)out.n_warps * 5 * 32 * 8 + max_ops * 8 + 16 + 15) & ~(size_t)15;
+        out.smem_boot = ((size_t)5 * 32 * 8 + max_ops * 8 + 16 + 15) & ~(size_t)15;
+        out.smem_aux = (max_ops * 8 + 16 + 15) & ~(size_t)15;
+        out.d_shared_aux = false;
+        out.smem_boot_gather = 0;
+        if (out.smem_fit > smem_cap) {
+            set_error("pedigree program too large for shared memory");
+            return ABFIT_ERR_TOO_LARGE;
+        }
+        return 0;
+    }
     out.smem_boot_gather = 0;
     if (hp.max_pairs <= 8191) {  // u16 byte offsets into resid
         size_t m = 0;
         for (auto &pb : hp.probs) m = std::max(m, smem_need_boot_gather(pb));
         if (m <= smem_cap / 4 && !getenv("ABFIT_DEV_BOOT_TILE")) out.smem_boot_gather = m;  // else: stored-D* kernel
-    }
-    out.d_shared_aux = worst(0, true, 1) <= smem_cap / 2;
-    out.smem_aux = worst(0, out.d_shared_aux, 1);
-    if (out.smem_boot > smem_cap || out.smem_aux > smem_cap) {
-        set_error("pedigree too large for the shared-memory model state");
-        return ABFIT_ERR_TOO_LARGE;
     }
     return 0;
 }

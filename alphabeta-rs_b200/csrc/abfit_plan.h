@@ -26,6 +26,8 @@ struct LaunchShape {
     int n_warps = 1;        // warps per block of the multi-start kernel
     bool d_shared = true;   // D column staged in shared memory (else broadcast from L1/L2)
     bool x_global = false;  // simplex vertices in a global scratch area (20 * 32 doubles per warp) instead of shared
+    bool big = false;       // per-lane model state does not fit in shared memory: everything per-lane in global scratch
+    int n_lane_max = 0;     // doubles of per-lane model state of the largest problem
     size_t smem_fit = 0;    // k_fit_starts
     size_t smem_boot = 0;   // k_fit_boot (1 warp, D* comes from the scratch tile)
     size_t smem_boot_gather = 0;  // k_fit_boot_gather (1 warp + pred/resid of the window), 0 = not usable

@@ -375,3 +375,63 @@ def test_alphabeta_batch_equals_fit_then_boot(ab, ctx, oracle, ped351, ped78):
         assert rc == 0 and np.array_equal(out["rows"][i], orows)
         assert np.array_equal(out["analysis"][i], oracle.analyze(orows), equal_nan=True)
         off += n
+
+
+# ---------------------------------------------------------------------------------------------
+# large pedigrees: per-lane state in global scratch (carve_big)
+# ---------------------------------------------------------------------------------------------
+def c5_pedigree(rng, lineages=10, generations=20):
+    """C5 shape: `lineages` independent lines sampled at generations 1..`generations` from a common G0"""
+    samples = [(l, g) for l in range(lineages) for g in range(1, generations + 1)]
+    rows = []
+    for i in range(len(samples)):
+        for j in range(i + 1, len(samples)):
+            (l1, g1), (l2, g2) = samples[i], samples[j]
+            rows.append([min(g1, g2) if l1 == l2 else 0, g1, g2, 0.0])
+    ped = np.array(rows, dtype=np.float64)
+    return ped
+
+
+def test_big_variant_is_bit_identical_on_small_problems(ab, ctx, oracle, ped351, monkeypatch):
+    """the global-scratch kernels forced onto the C4 pedigree give the same bits as the shared-memory ones"""
+    rng = np.random.default_rng(9)
+    cases = [synth_problem(rng, ped351) for _ in range(2)]
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    n_starts, n_boot = 300, 40
+    sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    idx = np.concatenate([ab.gen_resample_idx(SEED, i, n_boot, len(p)).ravel() for i, (p, u) in enumerate(cases)])
+    ref = ctx.alphabeta_batch(probs, sx, idx, SEED)
+    monkeypatch.setenv("ABFIT_DEV_BIG", "1")
+    big = ctx.alphabeta_batch(probs, sx, idx, SEED)
+    for k in ("pred", "resid", "rows", "status"):
+        assert np.array_equal(ref[k], big[k], equal_nan=True), k
+    assert np.array_equal(ref["best"]["theta"], big["best"]["theta"])
+    theta = np.stack([10 ** rng.uniform(-6, -2, 50), 10 ** rng.uniform(-6, -2, 50), rng.uniform(0, 0.1, 50), rng.uniform(0, 0.01, 50)], axis=1)
+    c_big, l_big = ctx.cost_batch(probs, theta, rng.integers(0, 2, 50).astype(np.int32))
+    monkeypatch.delenv("ABFIT_DEV_BIG")
+
+
+def test_c5_large_pedigree_fit(ab, ctx, oracle):
+    """BASELINE configs[4]: 200 samples -> 19 900 pairs, 590 distinct (t0,t1,t2) triples, 836 doubles of model state
+    per lane: does not fit in shared memory, runs through the global-scratch variant; bit-exact against the oracle"""
+    rng = np.random.default_rng(17)
+    ped = c5_pedigree(rng)
+    assert ped.shape == (19900, 4)
+    a, b, w, c, p0 = 2e-4, 1e-3, 0.04, 0.002, 0.75
+    pb_o = oracle.Problem(ped, p0, p0, 1.0)
+    dt, _ = oracle.divergence(pb_o, a, b, w, oracle.FAST_DIVERGENCE)
+    ped[:, 3] = np.maximum(c + dt + rng.normal(0, 5e-4, len(ped)), 0.0)
+    prob = ab.Problem(ped, p0, p0, 1.0)
+    theta = np.array([[a, b, w, c], [3e-4, 2e-3, 0.01, 0.0], [-1e-4, 1e-3, 0.2, 0.01]])
+    cost, lse = ctx.cost_batch([prob], theta)
+    for i in range(len(theta)):
+        assert cost[i] == oracle.cost(oracle.Problem(ped, p0, p0, 1.0), theta[i])
+    dtg, _ = ctx.divergence(prob, theta[0])
+    assert np.array_equal(dtg, dt)
+    n_starts = 40
+    sx = ab.gen_start_simplices(SEED, 0, n_starts, float(ped[:, 3].max()))
+    res = ctx.fit_batch([prob], sx[None], max_iters=10000)
+    assert res.status[0] == 0
+    check_fit_against_oracle(ab, oracle, res, 0, oracle.Problem(ped, p0, p0, 1.0), sx, 10000,
+                             oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, 0, len(ped))
+    assert 0.5 * a < res.best[0]["theta"][0] < 2 * a and 0.5 * b < res.best[0]["theta"][1] < 2 * b

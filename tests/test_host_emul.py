@@ -2,7 +2,7 @@
 abfit_nm.cuh) and the host pedigree compiler (abfit_plan.cu), built FOR THE CPU (tests/host_emul) and
 checked bit for bit against the oracle.  No GPU needed: this is how the `-m "not gpu"` suite covers
 the micro-op compiler, the software-pipelined pair loop and the NM state machine, and how a compiler
-problem on the GPU side (see DESIGN.md §2.7) is told apart from a source problem."""
+problem on the GPU side (see DESIGN.md §2.8) is told apart from a source problem."""
 import ctypes as C
 import os
 import subprocess
