@@ -435,3 +435,53 @@ def test_c5_large_pedigree_fit(ab, ctx, oracle):
     check_fit_against_oracle(ab, oracle, res, 0, oracle.Problem(ped, p0, p0, 1.0), sx, 10000,
                              oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, 0, len(ped))
     assert 0.5 * a < res.best[0]["theta"][0] < 2 * a and 0.5 * b < res.best[0]["theta"][1] < 2 * b
+
+
+# ---------------------------------------------------------------------------------------------
+# C4 at BASELINE.json's full size, through size-independent properties
+# ---------------------------------------------------------------------------------------------
+def test_c4_full_size_properties(ab, ctx, oracle, ped351):
+    """10 000 windows x (1000 starts + 100 bootstrap replicates) in one abfit_alphabeta_batch call (11 M fits).
+    Too large for the oracle, so: (1) every window fits; (2) sharding invariance — a slice of the windows run on its
+    own gives the same bits (what multi-GPU sharding relies on); (3) the oracle's best of the first 16 starts of a
+    few windows can never beat the GPU's best of 1000, and is reproduced exactly when the winner is among them;
+    (4) the bootstrap rows are internally consistent (equilibrium columns recomputed from alpha, beta)."""
+    import bench
+
+    W, NS, NB = 10000, 1000, 100
+    shape = bench.load_shape()
+    peds, p0uu = bench.synth_windows(W, 0, shape)
+    N = peds.shape[1]
+    probs = [ab.Problem(peds[i], float(p0uu[i]), float(p0uu[i]), 1.0) for i in range(W)]
+    sx = np.empty((W, NS, 5, 4))
+    idx = np.empty((W, NB, N), dtype=np.int32)
+    from concurrent.futures import ThreadPoolExecutor
+
+    def gen(i):
+        sx[i] = ab.gen_start_simplices(SEED, i, NS, float(peds[i, :, 3].max()))
+        idx[i] = ab.gen_resample_idx(SEED, i, NB, N)
+
+    with ThreadPoolExecutor(16) as ex:
+        list(ex.map(gen, range(W)))
+    out = ctx.alphabeta_batch(probs, sx, idx, SEED)
+    assert np.all(out["status"] == 0) and np.all(out["best"]["status"] > 0)
+    assert np.all(np.isfinite(out["rows"])) and np.all(np.isfinite(out["analysis"][:, :16]))
+    # (2) a slice on its own
+    lo, hi = 4321, 4337
+    sub = ctx.alphabeta_batch(probs[lo:hi], sx[lo:hi], idx[lo:hi], SEED, first_problem_id=lo)
+    assert np.array_equal(sub["best"]["theta"], out["best"]["theta"][lo:hi])
+    assert np.array_equal(sub["best"]["start_id"], out["best"]["start_id"][lo:hi])
+    assert np.array_equal(sub["rows"], out["rows"][lo:hi]) and np.array_equal(sub["pred"], out["pred"][lo * N:hi * N])
+    # (3) oracle on the first 16 starts of three windows
+    for w in (0, 777, 9999):
+        rc, best, _, _, _ = oracle.ab_neutral(oracle.Problem(peds[w], p0uu[w], p0uu[w], 1.0), sx[w, :16],
+                                              flags=oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, n_threads=8)
+        assert rc == 0 and out["best"][w]["lse"] <= best["lse"]
+        if out["best"][w]["start_id"] < 16:
+            assert np.array_equal(out["best"][w]["theta"], best["theta"])
+    # (4) est_mm / est_um / est_uu columns (src/structs.rs:146-158) from the fitted alpha, beta
+    a, b = out["rows"][..., 0], out["rows"][..., 1]
+    den = (a + b) * ((a + b - 1.0) ** 2 - 2.0)
+    assert np.allclose(out["rows"][..., 4], a * ((1 - a) ** 2 - (1 - b) ** 2 - 1.0) / den, rtol=1e-12, atol=0)
+    assert np.allclose(out["rows"][..., 6], b * ((1 - b) ** 2 - (1 - a) ** 2 - 1.0) / den, rtol=1e-12, atol=0)
+    assert np.allclose(out["rows"][..., 4:7].sum(axis=-1), 1.0, atol=1e-9)
