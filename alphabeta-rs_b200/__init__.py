@@ -108,6 +108,13 @@ def _load() -> C.CDLL:
         "abfit_batch_timing": (C.c_int, [vp, vp, vp, C.POINTER(i32)]),
         "abfit_batch_flops_per_eval": (C.c_int, [vp, i32, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i32)]),
         "abfit_analyze": (C.c_int, [vp, i32, vp]),
+        "abfit_format_f64": (C.c_int, [dbl, C.c_char_p, i32]),
+        "abfit_steady_state": (dbl, [dbl, dbl]),
+        "abfit_write_pedigree": (C.c_int, [C.c_char_p, vp, i32]),
+        "abfit_write_analysis": (C.c_int, [C.c_char_p, vp]),
+        "abfit_format_analysis": (C.c_int, [vp, C.c_char_p, i32]),
+        "abfit_write_npy_f64": (C.c_int, [C.c_char_p, vp, i32, vp]),
+        "abfit_write_metaprofile_results": (C.c_int, [C.c_char_p, C.c_char_p, i32, vp, vp, vp, vp, vp]),
         "abfit_window_counts": (C.c_int, [vp, vp]),
         "abfit_place_sites": (C.c_int, [vp, i32, vp, i64, vp, vp, vp, i64, vp, vp]),
     }
@@ -127,7 +134,9 @@ EXPORTED_SYMBOLS = (
     "abfit_model_divergence abfit_fit_batch abfit_boot_batch abfit_divergence abfit_divergence_device abfit_batch_create "
     "abfit_batch_destroy abfit_batch_upload_starts abfit_batch_run_fit abfit_batch_download_fit "
     "abfit_batch_upload_boot abfit_batch_run_boot abfit_batch_download_boot abfit_batch_sync "
-    "abfit_batch_timing abfit_batch_flops_per_eval abfit_analyze abfit_window_counts abfit_place_sites"
+    "abfit_batch_timing abfit_batch_flops_per_eval abfit_analyze abfit_window_counts abfit_place_sites "
+    "abfit_format_f64 abfit_steady_state abfit_write_pedigree abfit_write_analysis abfit_format_analysis "
+    "abfit_write_npy_f64 abfit_write_metaprofile_results"
 ).split()
 
 
@@ -615,3 +624,59 @@ def segments_from_assignments(assign_site, assign_window, n_windows):
     seg = np.zeros(n_windows + 1, dtype=np.int64)
     np.cumsum(counts, out=seg[1:])
     return assign_site[perm], seg
+
+
+# ---------------------------------------------------------------------------------------------
+# result files (byte-for-byte the reference's formats)
+# ---------------------------------------------------------------------------------------------
+def format_f64(v: float) -> str:
+    """f64 as Rust's `{}` prints it"""
+    buf = C.create_string_buffer(512)
+    n = _lib.abfit_format_f64(float(v), buf, 512)
+    if n < 0:
+        raise AbfitError(n, "format_f64")
+    return buf.value.decode()
+
+
+def steady_state(alpha: float, beta: float) -> float:
+    """steady_state (src/alphabeta.rs:71-79)"""
+    return _lib.abfit_steady_state(float(alpha), float(beta))
+
+
+def write_pedigree(path: str, pedigree) -> None:
+    """Pedigree::to_file (src/pedigree.rs:81-90)"""
+    ped = _f64(pedigree).reshape(-1, 4)
+    _check(_lib.abfit_write_pedigree(os.fsencode(path), _ptr(ped), ped.shape[0]))
+
+
+def write_analysis(path: str, analysis) -> None:
+    """Analysis::to_file (src/analysis.rs:102-144) from analyze()'s 32 values"""
+    a = _f64(analysis, (32,))
+    _check(_lib.abfit_write_analysis(os.fsencode(path), _ptr(a)))
+
+
+def format_analysis(analysis) -> str:
+    a = _f64(analysis, (32,))
+    buf = C.create_string_buffer(8192)
+    n = _lib.abfit_format_analysis(_ptr(a), buf, 8192)
+    if n < 0:
+        raise AbfitError(n, "format_analysis")
+    return buf.value.decode()
+
+
+def write_npy(path: str, array) -> None:
+    """write_npy of raw.npy (src/cli/alphabeta.rs:34-35)"""
+    a = _f64(array)
+    shape = np.asarray(a.shape, dtype=np.int64)
+    _check(_lib.abfit_write_npy_f64(os.fsencode(path), _ptr(a), a.ndim, _ptr(shape)))
+
+
+def write_metaprofile_results(path: str, run_name: str, cg_count, region, best, analysis, obs_steady_state) -> None:
+    """results.txt of `metaprofile ... alphabeta` (src/cli/metaprofile.rs:74-99)"""
+    cg = np.ascontiguousarray(cg_count, dtype=np.int32)
+    rg = np.ascontiguousarray(region, dtype=np.int32)
+    best = np.ascontiguousarray(best, dtype=FIT_DTYPE)
+    an = _f64(analysis).reshape(-1, 32)
+    obs = _f64(obs_steady_state)
+    _check(_lib.abfit_write_metaprofile_results(os.fsencode(path), run_name.encode(), len(cg), _ptr(cg), _ptr(rg), _ptr(best),
+                                                _ptr(an), _ptr(obs)))

@@ -270,6 +270,7 @@ int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm,
     // vertices in global scratch for 4 x 4 (128 registers).
     int best_w = -1;
     const int cand_nw[3] = {4, 2, 1};
+    const int64_t total_fits = (int64_t)hp.probs.size() * fits_per_prob;
     const char *force = getenv("ABFIT_DEV_NWARPS");  // tuning experiments only
     const char *force_x = getenv("ABFIT_DEV_XGLOBAL");
     for (int pass = 0; pass < 2; ++pass) {  // pass 0: D in shared memory; pass 1: D broadcast from L1/L2
@@ -278,6 +279,8 @@ int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm,
             for (int nw : cand_nw) {
                 if (force && nw != atoi(force)) continue;
                 if (!force && nw > 1 && fits_per_prob < 64 * nw) continue;  // too few fits for a multi-warp block
+                // a small batch (one pedigree x 1000 starts) is spread over as many SMs as it has warps
+                if (!force && nw > 1 && total_fits < (int64_t)148 * 64 * nw) continue;
                 const size_t s = worst(xg ? 5 : 25, pass == 0, nw);
                 if (s > smem_cap) continue;
                 const int reg_warps = xg ? 16 : 12;
@@ -309,7 +312,7 @@ int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm,
     if (out.big) {
         // lane state, vertices, D and offsets in global scratch (carve_big): shared memory only holds the simplex
         // costs, the program and the queue word
-        out.n_warps = (force ? atoi(force) : (fits_per_prob >= 256 ? 4 : 1));
+        out.n_warps = (force ? atoi(force) : (fits_per_prob >= 256 && total_fits >= (int64_t)148 * 64 * 4 ? 4 : 1));
         out.d_shared = false;
         out.x_global = true;
         out.smem_fit = ((size_t)out.n_warps * 5 * 32 * 8 + max_ops * 8 + 16 + 15) & ~(size_t)15;
@@ -342,7 +345,9 @@ std::vector<WorkItem> make_items(const HostPlan &hp, int count_per_prob, int n_s
     const int64_t total = (int64_t)n_probs * count_per_prob;
     int64_t chunk = (total + target_blocks - 1) / target_blocks;
     chunk = ((chunk + lanes - 1) / lanes) * lanes;
-    if (chunk < 2 * lanes) chunk = 2 * lanes;
+    // at least two fits per lane so that the queue can even out the run lengths — unless the whole batch is
+    // smaller than the machine, where one fit per lane on more SMs finishes sooner
+    if (chunk < 2 * lanes && total >= (int64_t)n_sm * 2 * lanes) chunk = 2 * lanes;
     if (chunk > count_per_prob) chunk = count_per_prob;
     if (const char *fc = getenv("ABFIT_DEV_CHUNK")) chunk = std::max(1, std::min(atoi(fc), count_per_prob));
     const int n_chunks = (int)((count_per_prob + chunk - 1) / chunk);

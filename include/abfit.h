@@ -268,6 +268,25 @@ int abfit_place_sites(const abfit_gene *genes, int32_t n_genes, const abfit_cg_s
  * intercept, pr_mm, pr_um, pr_uu. Host only (O(n) per window). */
 int abfit_analyze(const double *rows, int32_t n, double out[32]);
 
+/* ---- result files of the reference, byte for byte (host) ------------------------
+ * f64 exactly as Rust's `{}` prints it (shortest round-trip digits, never scientific, "1" not "1.0", "NaN", "inf");
+ * returns the length or ABFIT_ERR_ARG when buf is too small */
+int abfit_format_f64(double v, char *buf, int32_t cap);
+/* steady_state (src/alphabeta.rs:71-79) */
+double abfit_steady_state(double alpha, double beta);
+/* Pedigree::to_file (src/pedigree.rs:81-90): "time0\ttime1\ttime2\tD.value" + one row per pair */
+int abfit_write_pedigree(const char *path, const double *pedigree, int32_t n_pairs);
+/* Analysis::to_file / Display (src/analysis.rs:102-187) from abfit_analyze's out[32] */
+int abfit_write_analysis(const char *path, const double analysis[32]);
+int abfit_format_analysis(const double analysis[32], char *buf, int32_t cap);
+/* write_npy of raw.npy (src/cli/alphabeta.rs:34-35; 3-D in src/cli/metaprofile.rs:110-111): NPY v1.0, '<f8', C order */
+int abfit_write_npy_f64(const char *path, const double *data, int32_t ndim, const int64_t *shape);
+/* results.txt of `metaprofile ... alphabeta` (src/cli/metaprofile.rs:74-99); region 0/1/2 = upstream/gene/downstream,
+ * analysis [n_windows][32] from abfit_analyze / abfit_alphabeta_batch */
+int abfit_write_metaprofile_results(const char *path, const char *run_name, int32_t n_windows, const int32_t *cg_count,
+                                    const int32_t *region, const abfit_fit *best, const double *analysis,
+                                    const double *obs_steady_state);
+
 #ifdef __cplusplus
 }
 #endif

@@ -528,3 +528,59 @@ def extract_windows(genes, sites, window_size=5, window_step=0, cutoff=2048, max
             dist[base[region] + i] += 1
             assign.append((si, base[region] + i))
     return dist, assign
+
+
+# ---------------------------------------------------------------------------------------------
+# result files: literal restatement of the reference's writers
+# ---------------------------------------------------------------------------------------------
+def rust_f64(v: float) -> str:
+    """`format!("{}", v)` for an f64: shortest round-trip digits (Python's repr has the same digits), positional"""
+    import math
+    from decimal import Decimal
+
+    if math.isnan(v):
+        return "NaN"
+    if math.isinf(v):
+        return "-inf" if v < 0 else "inf"
+    s = format(Decimal(repr(float(v))), "f")
+    if "." in s:
+        s = s.rstrip("0").rstrip(".")
+    if s in ("-", ""):
+        s += "0"
+    if v == 0 and math.copysign(1.0, v) < 0 and not s.startswith("-"):
+        s = "-" + s
+    return s
+
+
+def pedigree_file_text(ped) -> str:
+    """Pedigree::to_file (src/pedigree.rs:81-90)"""
+    out = "time0\ttime1\ttime2\tD.value\n"
+    for r in np.asarray(ped, dtype=np.float64).reshape(-1, 4):
+        out += "\t".join(rust_f64(x) for x in r) + "\n"
+    return out
+
+
+def analysis_file_text(a) -> str:
+    """Analysis::to_file (src/analysis.rs:102-144); a = analyze() output (8 means, 8 sds, 8 CI pairs)"""
+    names = ["Alpha", "Beta", "AlphaBeta", "Weight", "Intercept", "PrMM", "PrUM", "PrUU"]
+    out = "".join(f"{n}\t{rust_f64(a[i])}\n" for i, n in enumerate(names))
+    out += "".join(f"SD{n}\t{rust_f64(a[8 + i])}\n" for i, n in enumerate(names))
+    out += "".join(f"CI{n}\t{rust_f64(a[16 + 2 * i])}-{rust_f64(a[17 + 2 * i])}\n" for i, n in enumerate(names))
+    return out
+
+
+def steady_state(alpha, beta) -> float:
+    return float(lib().abref_steady_state(C.c_double(alpha), C.c_double(beta)))
+
+
+def metaprofile_results_text(run_name, cg_count, region, best_theta, analysis, obs) -> str:
+    """src/cli/metaprofile.rs:74-99"""
+    out = ("run;window;cg_count;region;alpha;beta;1/2*(alpha+beta);pred_steady_state;obs_steady_state;sd_alpha;sd_beta;"
+           "ci_alpha_0.025;ci_alpha_0.975;ci_beta_0.025;ci_beta_0.975\n")
+    reg = ["upstream", "gene", "downstream"]
+    for i in range(len(cg_count)):
+        a, b = float(best_theta[i][0]), float(best_theta[i][1])
+        an = analysis[i]
+        vals = [a, b, 0.5 * (a + b), steady_state(a, b), obs[i], an[8], an[9], an[16], an[17], an[18], an[19]]
+        out += f"{run_name};{i};{int(cg_count[i])};{reg[region[i]]};" + ";".join(rust_f64(float(x)) for x in vals) + "\n"
+    return out
