@@ -269,7 +269,7 @@ int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm,
     // vertices in shared memory the kernel is built for 3 blocks x 4 warps (168 registers); with the
     // vertices in global scratch for 4 x 4 (128 registers).
     int best_w = -1;
-    const int cand_nw[3] = {4, 2, 1};
+    const int cand_nw[4] = {4, 3, 2, 1};
     const int64_t total_fits = (int64_t)hp.probs.size() * fits_per_prob;
     const char *force = getenv("ABFIT_DEV_NWARPS");  // tuning experiments only
     const char *force_x = getenv("ABFIT_DEV_XGLOBAL");
@@ -288,7 +288,8 @@ int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm,
                 // measured on the C4 shape: 16 warps with the vertices in L2 are no faster than 12 with them
                 // in shared memory (the kernel is not latency-bound there), so the vertices only move out
                 // when shared memory would otherwise leave fewer than 8 resident warps
-                if (xg ? (best_w < 8 && w > best_w) : (w > best_w)) {
+                // equal residency: fewer warps per block = more fits per lane of a window's queue (shorter tails)
+                if (xg ? (best_w < 8 && w > best_w) : (w > best_w || (w == best_w && !out.x_global && nw < out.n_warps))) {
                     best_w = w;
                     out.n_warps = nw;
                     out.d_shared = pass == 0;
