@@ -148,6 +148,139 @@ __device__ __forceinline__ int queue_take(int *queue, unsigned m, int lane, int 
 }
 
 // ---------------------------------------------------------------------------------
+// Tail hand-off.  Once a block's queue is drained its warps thin out: Nelder-Mead run lengths spread 4x, so
+// a warp keeps executing full-width instructions for a handful of long fits (simulation on the C4 shape:
+// 89 % of the issued lanes do useful work with 3 warps per block, 95 % with hand-off).  A warp with few
+// active lanes therefore hands them to a sibling warp of the same block that has room, and exits.
+//
+// Mailbox protocol (one shared int `mb`, one published active-lane count per warp; all offers are
+// targeted, every take goes through a CAS, only the donor withdraws):
+//   donor     drained, 0 < active <= HANDOFF_MAX, mb == 0, a live sibling r with nact[r] + active <= 32:
+//             CAS mb 0 -> OFFER(donor, r, count); park the lane states in its own (now idle) lane_mem;
+//             fence; wait: mb == 0 -> taken, exit;  nact[r] < 0 (r has exited) -> CAS OFFER -> 0, resume.
+//   receiver  sees OFFER targeted at it (every loop trip, and once more after announcing its exit):
+//             CAS OFFER -> TAKING; idle lanes load the parked states and copy the simplices; mb = 0.
+// Active-lane counts only fall after the drain, so the room the donor saw is still there when the receiver
+// looks.  The moved state is the complete LaneNM + simplex, so results are unchanged bit for bit.
+// ---------------------------------------------------------------------------------
+constexpr int HANDOFF_MAX = 16;
+constexpr int MB_OFFER = 1 << 30, MB_TAKING = 1 << 29;
+__device__ __forceinline__ int mb_offer(int donor, int target, int count) { return MB_OFFER | donor | (target << 4) | (count << 8); }
+
+struct HandoffCtx {
+    volatile int *mb;            // mailbox word
+    volatile signed char *nact;  // [n_warps] published active-lane counts (-1: exited)
+    double *lm_base;             // shared: start of warp 0's per-warp region
+    int per_warp;                // doubles per warp region
+    int n_lane;                  // doubles of lane state (simplex X follows)
+};
+
+__device__ __forceinline__ void handoff_park(const LaneNM &L, double *ent, int lane)
+{
+    ent[0] = L.xt[0]; ent[1] = L.xt[1]; ent[2] = L.xt[2]; ent[3] = L.xt[3];
+    ent[4] = L.fr;
+    ent[5] = __hiloint2double(L.phase, L.k);
+    ent[6] = __hiloint2double((int)L.ord, L.iters);
+    ent[7] = __hiloint2double(L.evals, L.status);
+    ent[8] = __hiloint2double(L.fit_id, lane);
+}
+__device__ __forceinline__ int handoff_unpark(LaneNM &L, const double *ent)
+{
+    L.xt[0] = ent[0]; L.xt[1] = ent[1]; L.xt[2] = ent[2]; L.xt[3] = ent[3];
+    L.fr = ent[4];
+    L.phase = __double2hiint(ent[5]); L.k = __double2loint(ent[5]);
+    L.ord = (uint32_t)__double2hiint(ent[6]); L.iters = __double2loint(ent[6]);
+    L.evals = __double2hiint(ent[7]); L.status = __double2loint(ent[7]);
+    L.fit_id = __double2hiint(ent[8]);
+    return __double2loint(ent[8]);  // the donor lane that owns the simplex
+}
+
+// receiver side: returns true when lanes were taken over
+__device__ __forceinline__ bool handoff_try_take(const HandoffCtx &H, int warp, int lane, LaneNM &L, const LaneSimplex &S)
+{
+    const unsigned idle = __ballot_sync(FULL, L.phase == PH_IDLE);
+    int v = 0;
+    if (lane == 0) {
+        v = *H.mb;
+        if (!((v & MB_OFFER) && ((v >> 4) & 15) == warp && ((v >> 8) & 63) <= __popc(idle) &&
+              atomicCAS(const_cast<int *>(H.mb), v, MB_TAKING) == v))
+            v = 0;
+    }
+    v = __shfl_sync(FULL, v, 0);
+    if (!v) return false;
+    __threadfence_block();
+    const int donor = v & 15, count = (v >> 8) & 63;
+    const int rank = __popc(idle & ((1u << lane) - 1u));
+    if (L.phase == PH_IDLE && rank < count) {
+        const double *dbase = H.lm_base + (size_t)donor * H.per_warp;
+        const int dl = handoff_unpark(L, dbase + rank * 16);
+        const double *dX = dbase + H.n_lane * 32 + dl;  // donor lane's simplex: X[20], C[5] at stride 32
+#pragma unroll
+        for (int q = 0; q < 20; ++q) S.X[q * 32] = dX[q * 32];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) S.C[q * 32] = dX[(20 + q) * 32];
+    }
+    const unsigned now = __ballot_sync(FULL, L.phase != PH_IDLE);
+    if (lane == 0) {
+        H.nact[warp] = (signed char)__popc(now);  // published before the mailbox is released: the next donor sees it
+        __threadfence_block();
+        *H.mb = 0;
+    }
+    return true;
+}
+
+// donor side: returns true when the lanes were taken (the warp is empty now), false when it keeps them
+__device__ __forceinline__ bool handoff_try_give(const HandoffCtx &H, int warp, int n_warps, int lane, LaneNM &L,
+                                                 unsigned amask, double *my_lm)
+{
+    const int n_act = __popc(amask);
+    int offer = 0;
+    if (lane == 0 && *H.mb == 0) {
+        int target = -1, best = 0;
+        for (int r = 0; r < n_warps; ++r) {
+            const int a = H.nact[r];
+            if (r != warp && a > best && a + n_act <= 32) {
+                best = a;
+                target = r;
+            }
+        }
+        if (target >= 0) {
+            offer = mb_offer(warp, target, n_act);
+            if (atomicCAS(const_cast<int *>(H.mb), 0, MB_TAKING) != 0) offer = 0;  // reserved while the states are parked
+            else H.nact[warp] = 0;  // not a target for anybody while it is giving its lanes away
+        }
+    }
+    offer = __shfl_sync(FULL, offer, 0);
+    if (!offer) return false;
+    if (L.phase != PH_IDLE) handoff_park(L, my_lm + __popc(amask & ((1u << lane) - 1u)) * 16, lane);
+    __syncwarp();
+    __threadfence_block();
+    const int target = (offer >> 4) & 15;
+    int taken = 0;  // 1 taken, 2 withdrawn
+    if (lane == 0) {
+        atomicExch(const_cast<int *>(H.mb), offer);
+        for (;;) {
+            const int v = *H.mb;
+            if (v == 0) {
+                taken = 1;
+                break;
+            }
+            if (v == offer && H.nact[target] < 0 && atomicCAS(const_cast<int *>(H.mb), offer, 0) == offer) {
+                taken = 2;
+                break;
+            }
+            __nanosleep(256);
+        }
+    }
+    taken = __shfl_sync(FULL, taken, 0);
+    if (taken == 1) {
+        L.phase = PH_IDLE;  // the fits live on in the receiver
+        return true;
+    }
+    return false;  // withdrawn: registers still hold the states
+}
+
+// ---------------------------------------------------------------------------------
 // multi-start Nelder-Mead
 // ---------------------------------------------------------------------------------
 template <bool D_SHARED, bool X_GLOBAL, bool BIG>
@@ -157,16 +290,27 @@ k_fit_starts(DevicePools P, const WorkItem *__restrict__ items, const double *__
              unsigned long long *__restrict__ evals_per_prob, double *x_scratch, double *lm_scratch,
              size_t lm_stride)
 {
-    const int lane = threadIdx.x & 31;
+    constexpr bool HANDOFF = !X_GLOBAL && !BIG;  // the simplex of a moved lane is copied between shared regions
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const WorkItem it = items[blockIdx.x];
     const DevProblem pb = P.probs[it.prob];
     Carved cv = BIG ? carve_big(pb, P, true, x_scratch, lm_scratch, lm_stride)
                     : carve_and_stage<D_SHARED>(pb, P, X_GLOBAL ? 5 : 25, x_scratch);
-    if (threadIdx.x == 0) *cv.queue = it.first;
+    if (threadIdx.x == 0) {
+        cv.queue[0] = it.first;
+        cv.queue[1] = 0;           // mailbox
+        cv.queue[2] = 0x20202020;  // published active-lane counts: everybody full
+    }
     __syncthreads();
     const WarpCtx &c = cv.ctx;
     const LaneSimplex &S = cv.simplex;
     const DBroadcast Dat{c.D};
+    HandoffCtx H;
+    H.mb = cv.queue + 1;
+    H.nact = reinterpret_cast<volatile signed char *>(cv.queue + 2);
+    H.per_warp = (pb.n_lane + 25) * 32;
+    H.lm_base = c.lm - (size_t)warp * H.per_warp;
+    H.n_lane = pb.n_lane;
 
     LaneNM L;
     lane_nm_reset(L);
@@ -187,9 +331,26 @@ k_fit_starts(DevicePools P, const WorkItem *__restrict__ items, const double *__
                 nm_begin(L, S, idx);
             }
         }
+        unsigned amask = __ballot_sync(FULL, L.phase != PH_IDLE);
+        if (HANDOFF && drained && n_warps > 1 && pb.n_lane * 32 >= HANDOFF_MAX * 16) {
+            if (lane == 0) H.nact[warp] = (signed char)__popc(amask);
+            if (amask != FULL && handoff_try_take(H, warp, lane, L, S)) {
+                amask = __ballot_sync(FULL, L.phase != PH_IDLE);
+            } else if (amask && __popc(amask) <= HANDOFF_MAX && handoff_try_give(H, warp, n_warps, lane, L, amask, c.lm)) {
+                amask = 0;
+            }
+        }
+        if (!amask) {
+            if (HANDOFF && n_warps > 1 && pb.n_lane * 32 >= HANDOFF_MAX * 16) {
+                // announce the exit, then look once more: an offer posted in between is either taken here or
+                // withdrawn by its donor (whoever wins the CAS)
+                if (lane == 0) H.nact[warp] = -1;
+                __threadfence_block();
+                if (handoff_try_take(H, warp, lane, L, S)) continue;
+            }
+            break;
+        }
         const bool active = (L.phase != PH_IDLE);
-        const unsigned amask = __ballot_sync(FULL, active);
-        if (!amask) break;
         if (active) {
             const double f =
                 objective(c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
