@@ -108,6 +108,12 @@ def _load() -> C.CDLL:
         "abfit_batch_timing": (C.c_int, [vp, vp, vp, C.POINTER(i32)]),
         "abfit_batch_flops_per_eval": (C.c_int, [vp, i32, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i32)]),
         "abfit_analyze": (C.c_int, [vp, i32, vp]),
+        "abfit_parse_methylome_line": (C.c_int, [C.c_char_p, i32, vp, vp, vp, vp]),
+        "abfit_pedigree_build": (C.c_int, [vp, C.c_char_p, C.c_char_p, dbl, C.POINTER(vp)]),
+        "abfit_pedigree_info": (C.c_int, [vp, vp, vp, vp, vp]),
+        "abfit_pedigree_rows": (vp, [vp]),
+        "abfit_pedigree_warnings": (C.c_char_p, [vp]),
+        "abfit_pedigree_free": (None, [vp]),
         "abfit_format_f64": (C.c_int, [dbl, C.c_char_p, i32]),
         "abfit_steady_state": (dbl, [dbl, dbl]),
         "abfit_write_pedigree": (C.c_int, [C.c_char_p, vp, i32]),
@@ -135,7 +141,8 @@ EXPORTED_SYMBOLS = (
     "abfit_batch_destroy abfit_batch_upload_starts abfit_batch_run_fit abfit_batch_download_fit "
     "abfit_batch_upload_boot abfit_batch_run_boot abfit_batch_download_boot abfit_batch_sync "
     "abfit_batch_timing abfit_batch_flops_per_eval abfit_analyze abfit_window_counts abfit_place_sites "
-    "abfit_format_f64 abfit_steady_state abfit_write_pedigree abfit_write_analysis abfit_format_analysis "
+    "abfit_parse_methylome_line abfit_pedigree_build abfit_pedigree_info abfit_pedigree_rows abfit_pedigree_warnings "
+    "abfit_pedigree_free abfit_format_f64 abfit_steady_state abfit_write_pedigree abfit_write_analysis abfit_format_analysis "
     "abfit_write_npy_f64 abfit_write_metaprofile_results"
 ).split()
 
@@ -680,3 +687,36 @@ def write_metaprofile_results(path: str, run_name: str, cg_count, region, best, 
     obs = _f64(obs_steady_state)
     _check(_lib.abfit_write_metaprofile_results(os.fsencode(path), run_name.encode(), len(cg), _ptr(cg), _ptr(rg), _ptr(best),
                                                 _ptr(an), _ptr(obs)))
+
+
+# ---------------------------------------------------------------------------------------------
+# input files
+# ---------------------------------------------------------------------------------------------
+def parse_methylome_line(line: str, invert_strand: bool = False):
+    """MethylationSite::from_methylome_file_line (src/methylation_site.rs:146-362) -> dict or None"""
+    site = np.zeros(1, dtype=SITE_DTYPE)
+    post, lvl, status = C.c_double(), C.c_double(), C.c_int32()
+    rc = _lib.abfit_parse_methylome_line(line.encode(), int(invert_strand), _ptr(site), C.cast(C.byref(post), C.c_void_p),
+                                         C.cast(C.byref(status), C.c_void_p), C.cast(C.byref(lvl), C.c_void_p))
+    if rc == 1:
+        return None
+    _check(rc)
+    return {"chromosome": int(site[0]["chromosome"]), "start": int(site[0]["start"]), "end": int(site[0]["end"]),
+            "strand": int(site[0]["strand"]), "posteriormax": post.value, "status": status.value, "meth_lvl": lvl.value}
+
+
+def build_pedigree(ctx: Context, nodelist: str, edgelist: str, posterior_max_filter: float = 0.99):
+    """Pedigree::build (src/pedigree.rs:92-193): (pedigree [n,4], p0uu, info dict).  File names inside the nodelist are
+    relative to the current directory, as in the reference."""
+    h = C.c_void_p()
+    _check(_lib.abfit_pedigree_build(ctx._h, os.fsencode(nodelist), os.fsencode(edgelist), posterior_max_filter, C.byref(h)))
+    try:
+        n, p0, ns, nl = C.c_int32(), C.c_double(), C.c_int32(), C.c_int64()
+        _check(_lib.abfit_pedigree_info(h, C.cast(C.byref(n), C.c_void_p), C.cast(C.byref(p0), C.c_void_p),
+                                        C.cast(C.byref(ns), C.c_void_p), C.cast(C.byref(nl), C.c_void_p)))
+        rows = np.ctypeslib.as_array(C.cast(_lib.abfit_pedigree_rows(h), C.POINTER(C.c_double)), shape=(max(n.value, 1), 4))[:n.value].copy() \
+            if n.value else np.zeros((0, 4))
+        warn = (_lib.abfit_pedigree_warnings(h) or b"").decode()
+    finally:
+        _lib.abfit_pedigree_free(h)
+    return rows, p0.value, {"n_samples": ns.value, "n_sites": nl.value, "warnings": warn}

@@ -1,0 +1,381 @@
+// abfit_inputs.cu — the input side of `alphabeta` (host): nodelist / edgelist / methylome parsing and
+// the pedigree builder, restated from the reference so that real files can be fed end to end
+// (SURVEY.md §8f rank 2).  The O(S^2 L) part — the observed pairwise divergence — runs on the GPU
+// (abfit_divergence); everything here is O(input) text handling and a shortest-path search on a graph
+// of a few hundred nodes.
+//
+//   MethylationSite::from_methylome_file_line   src/methylation_site.rs:146-362
+//   Chromosome::try_from                        src/methylation_site.rs:57-68
+//   Pedigree::build                             src/pedigree.rs:92-193
+//   DMatrix::convert (shortest path, t0 rule)   src/pedigree.rs:264-337
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <queue>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "abfit_internal.h"
+
+namespace {
+
+std::vector<std::string> split_any(const std::string &s, const char *seps)
+{
+    std::vector<std::string> out;
+    std::string cur;
+    for (char ch : s) {
+        if (std::strchr(seps, ch)) {
+            out.push_back(cur);
+            cur.clear();
+        } else {
+            cur += ch;
+        }
+    }
+    out.push_back(cur);
+    return out;
+}
+
+// <u32 as FromStr>: optional '+', ASCII digits, no overflow
+bool parse_u32(const std::string &s, uint32_t &v)
+{
+    size_t i = (!s.empty() && s[0] == '+') ? 1 : 0;
+    if (i >= s.size()) return false;
+    uint64_t acc = 0;
+    for (; i < s.size(); ++i) {
+        if (s[i] < '0' || s[i] > '9') return false;
+        acc = acc * 10 + (uint64_t)(s[i] - '0');
+        if (acc > 0xFFFFFFFFull) return false;
+    }
+    v = (uint32_t)acc;
+    return true;
+}
+
+// <f64 as FromStr>: [+-] (digits [. digits] | . digits) [e[+-]digits] | inf | infinity | nan  (case-insensitive words)
+bool parse_f64(const std::string &s, double &v)
+{
+    size_t i = 0;
+    if (i < s.size() && (s[i] == '+' || s[i] == '-')) ++i;
+    std::string w;
+    for (size_t k = i; k < s.size(); ++k) w += (char)std::tolower((unsigned char)s[k]);
+    if (w == "inf" || w == "infinity" || w == "nan") {
+        v = std::strtod(s.c_str(), nullptr);
+        return true;
+    }
+    size_t nd = 0;
+    while (i < s.size() && std::isdigit((unsigned char)s[i])) ++i, ++nd;
+    if (i < s.size() && s[i] == '.') {
+        ++i;
+        while (i < s.size() && std::isdigit((unsigned char)s[i])) ++i, ++nd;
+    }
+    if (nd == 0) return false;
+    if (i < s.size() && (s[i] == 'e' || s[i] == 'E')) {
+        ++i;
+        if (i < s.size() && (s[i] == '+' || s[i] == '-')) ++i;
+        size_t ne = 0;
+        while (i < s.size() && std::isdigit((unsigned char)s[i])) ++i, ++ne;
+        if (ne == 0) return false;
+    }
+    if (i != s.size()) return false;
+    v = std::strtod(s.c_str(), nullptr);  // glibc: correctly rounded, like Rust's
+    return true;
+}
+
+// Chromosome::try_from: Numbered(n) -> n, Mitochondrial -> 256, Chloroplast -> 257
+bool parse_chromosome(std::string s, int32_t &c)
+{
+    while (s.rfind("chr", 0) == 0) s = s.substr(3);  // trim_start_matches("chr")
+    if (s == "M") { c = 256; return true; }
+    if (s == "C") { c = 257; return true; }
+    uint32_t v;
+    if (!parse_u32(s, v) || v > 255) return false;
+    c = (int32_t)v;
+    return true;
+}
+
+struct Site {
+    int32_t chromosome;
+    uint32_t start, end;
+    int32_t strand;
+    double posteriormax, meth_lvl;
+    uint8_t status;
+};
+
+uint8_t status_of(char c) { return c == 'M' ? 2 : c == 'I' ? 1 : 0; }  // anything else parses as U (with a warning)
+
+bool cg_fields(const std::vector<std::string> &f, size_t i_chr, const std::string &start, const std::string *end,
+               size_t i_strand, size_t i_cm, size_t i_ct, size_t i_post, size_t i_status, size_t i_lvl, bool invert, Site &o)
+{
+    uint32_t cm, ct;
+    if (!parse_chromosome(f[i_chr], o.chromosome)) return false;
+    if (!parse_u32(start, o.start)) return false;
+    if (end) {
+        if (!parse_u32(*end, o.end)) return false;
+    } else {
+        o.end = o.start + 1;
+    }
+    o.strand = ((f[i_strand] == "+") ^ invert) ? 1 : -1;
+    if (!parse_u32(f[i_cm], cm) || !parse_u32(f[i_ct], ct)) return false;
+    if (!parse_f64(f[i_post], o.posteriormax)) return false;
+    if (f[i_status].empty()) return false;
+    o.status = status_of(f[i_status][0]);
+    if (!parse_f64(f[i_lvl], o.meth_lvl)) return false;
+    return true;
+}
+
+// the six formats, tried in the reference's order; 4-field lines all end in the chromatin-state reading
+bool parse_methylome_line(const std::string &line, bool invert, Site &o)
+{
+    const std::vector<std::string> f = split_any(line, "\t");
+    if (f.size() == 9 && f[3] == "CG" && cg_fields(f, 0, f[1], nullptr, 2, 4, 5, 6, 7, 8, invert, o)) return true;
+    if (f.size() == 10 && f[3] == "CG" && cg_fields(f, 0, f[1], nullptr, 2, 4, 5, 6, 7, 8, invert, o)) return true;
+    if (f.size() == 11 && f[3] == "CG" && cg_fields(f, 0, f[1], &f[2], 5, 6, 7, 8, 9, 10, invert, o)) return true;
+    const std::vector<std::string> g = split_any(line, "\t ");
+    if (g.size() == 4) {
+        if (parse_chromosome(g[0], o.chromosome) && parse_u32(g[1], o.start) && parse_u32(g[2], o.end)) {
+            o.strand = 0;
+            o.posteriormax = 0.0;
+            o.meth_lvl = 0.0;
+            o.status = 0;
+            return true;
+        }
+    }
+    return false;
+}
+
+bool read_file(const char *path, std::string &out)
+{
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    std::ostringstream ss;
+    ss << f.rdbuf();
+    out = ss.str();
+    return true;
+}
+
+struct Node {
+    size_t id;
+    std::string file, name;
+    uint32_t generation;
+    bool meth;
+};
+
+}  // namespace
+
+struct abfit_pedigree {
+    std::vector<double> rows;  // [n_pairs][4]
+    double p0uu = 0.0;
+    int32_t n_samples = 0;
+    int64_t n_sites = 0;
+    std::string warnings;
+};
+
+extern "C" {
+
+int abfit_parse_methylome_line(const char *line, int32_t invert_strand, abfit_cg_site *site_out, double *posterior_max_out,
+                               int32_t *status_out, double *meth_lvl_out)
+{
+    if (!line) return ABFIT_ERR_ARG;
+    Site s;
+    if (!parse_methylome_line(line, invert_strand != 0, s)) return 1;  // not a site (header, other context, malformed)
+    if (site_out) {
+        site_out->chromosome = s.chromosome;
+        site_out->start = s.start;
+        site_out->end = s.end;
+        site_out->strand = s.strand;
+    }
+    if (posterior_max_out) *posterior_max_out = s.posteriormax;
+    if (status_out) *status_out = s.status;
+    if (meth_lvl_out) *meth_lvl_out = s.meth_lvl;
+    return 0;
+}
+
+int abfit_pedigree_build(abfit_ctx *ctx, const char *nodelist_path, const char *edgelist_path, double posterior_max_filter,
+                         abfit_pedigree **out)
+{
+    if (!ctx || !nodelist_path || !edgelist_path || !out) return ABFIT_ERR_ARG;
+    *out = nullptr;
+    std::string ntext, etext;
+    if (!read_file(nodelist_path, ntext) || !read_file(edgelist_path, etext)) {
+        abfit::set_error("cannot read the nodelist or the edgelist");
+        return ABFIT_ERR_ARG;
+    }
+    // nodes: split on \n and \r, skip the header, id = index after the header (src/pedigree.rs:99-116)
+    std::vector<Node> nodes;
+    {
+        const std::vector<std::string> lines = split_any(ntext, "\n\r");
+        for (size_t li = 1; li < lines.size(); ++li) {
+            const std::vector<std::string> e = split_any(lines[li], ",\t ");
+            uint32_t gen;
+            if (e.size() < 4 || !parse_u32(e[2], gen)) continue;
+            nodes.push_back(Node{li - 1, e[0], e[1], gen, e[3] == "Y"});
+        }
+    }
+    if (nodes.empty()) {
+        abfit::set_error("No nodes could be parsed from the nodelist");
+        return ABFIT_ERR_ARG;
+    }
+    struct Edge {
+        const Node *from, *to;
+    };
+    std::vector<Edge> edges;  // src/pedigree.rs:123-135
+    {
+        const std::vector<std::string> lines = split_any(etext, "\n\r");
+        for (size_t li = 1; li < lines.size(); ++li) {
+            const std::vector<std::string> e = split_any(lines[li], "\t ,");
+            if (e.size() < 2) continue;
+            const Node *a = nullptr, *b = nullptr;
+            for (auto &n : nodes)
+                if (!a && n.name == e[0]) a = &n;
+            for (auto &n : nodes)
+                if (!b && n.name == e[1]) b = &n;
+            if (a && b) edges.push_back(Edge{a, b});
+        }
+    }
+    // measured nodes and their site tables (src/pedigree.rs:137-177); node.file is relative to the CWD
+    std::vector<const Node *> meas;
+    for (auto &n : nodes)
+        if (n.meth) meas.push_back(&n);
+    const int S = (int)meas.size();
+    std::vector<std::vector<uint8_t>> st(S);
+    std::vector<std::vector<double>> po(S), me(S);
+    for (int s = 0; s < S; ++s) {
+        std::ifstream f(meas[s]->file);
+        if (!f) {
+            abfit::set_error("Could not open node file: " + meas[s]->file);
+            return ABFIT_ERR_ARG;
+        }
+        std::string line;
+        Site site;
+        while (std::getline(f, line)) {
+            if (!line.empty() && line.back() == '\r') line.pop_back();  // BufRead::lines strips \r\n
+            if (!parse_methylome_line(line, false, site)) continue;
+            st[s].push_back(site.status);
+            po[s].push_back(site.posteriormax);
+            me[s].push_back(site.meth_lvl);
+        }
+    }
+    std::unique_ptr<abfit_pedigree> ped(new abfit_pedigree());
+    ped->n_samples = S;
+    // observed divergence + per-sample methylation level on the GPU, one call per group of samples with equally long
+    // site lists (pairs of unequal length get D = 0 with a warning, src/pedigree.rs:222-230)
+    std::vector<double> Dfull((size_t)S * S, 0.0);  // [i][j] for i < j
+    std::vector<double> rc(S, 0.0);
+    std::map<size_t, std::vector<int>> by_len;
+    for (int s = 0; s < S; ++s) by_len[st[s].size()].push_back(s);
+    if (by_len.size() > 1) ped->warnings += "Lengths do not match, all bets are off: pairs of samples with different site counts get D = 0\n";
+    for (auto &kv : by_len) {
+        const std::vector<int> &grp = kv.second;
+        const int G = (int)grp.size();
+        const int64_t L = (int64_t)kv.first;
+        ped->n_sites = std::max(ped->n_sites, L);
+        std::vector<uint8_t> gs((size_t)G * L);
+        std::vector<double> gp((size_t)G * L), gm((size_t)G * L);
+        for (int g = 0; g < G; ++g) {
+            std::copy(st[grp[g]].begin(), st[grp[g]].end(), gs.begin() + (size_t)g * L);
+            std::copy(po[grp[g]].begin(), po[grp[g]].end(), gp.begin() + (size_t)g * L);
+            std::copy(me[grp[g]].begin(), me[grp[g]].end(), gm.begin() + (size_t)g * L);
+        }
+        const size_t P = (size_t)G * (G - 1) / 2;
+        std::vector<double> D(std::max<size_t>(P, 1)), methsum(G);
+        std::vector<int64_t> nvalid(G);
+        if (int rc2 = abfit_divergence(ctx, gs.data(), gp.data(), gm.data(), G, L, nullptr, 1, posterior_max_filter, D.data(),
+                                       nullptr, nullptr, nullptr, methsum.data(), nvalid.data()))
+            return rc2;
+        size_t p = 0;
+        for (int a = 0; a < G; ++a) {
+            rc[grp[a]] = methsum[a] / (double)nvalid[a];  // src/pedigree.rs:171-172 (0/0 = NaN)
+            for (int b = a + 1; b < G; ++b) {
+                const int i = std::min(grp[a], grp[b]), j = std::max(grp[a], grp[b]);
+                Dfull[(size_t)i * S + j] = D[p++];
+            }
+        }
+    }
+    {
+        double acc = 0.0;  // src/pedigree.rs:179-183
+        for (int s = 0; s < S; ++s) acc += 1.0 - rc[s];
+        ped->p0uu = acc / (double)S;
+    }
+    // DMatrix::convert: undirected graph, edge weight |generation difference|, shortest path, t0 = smallest
+    // generation on the path (src/pedigree.rs:264-337).  petgraph's astar with a zero heuristic is Dijkstra;
+    // pedigrees are trees, so the path is unique.
+    std::map<size_t, std::vector<std::pair<size_t, uint64_t>>> adj;
+    std::map<size_t, uint32_t> gen_of;
+    for (auto &e : edges) {
+        const uint64_t w = e.from->generation > e.to->generation ? e.from->generation - e.to->generation
+                                                                 : e.to->generation - e.from->generation;
+        adj[e.from->id].push_back({e.to->id, w});
+        adj[e.to->id].push_back({e.from->id, w});
+        gen_of.emplace(e.from->id, e.from->generation);
+        gen_of.emplace(e.to->id, e.to->generation);
+    }
+    for (int i = 0; i < S; ++i)
+        for (int j = i + 1; j < S; ++j) {
+            const size_t src = meas[i]->id, dst = meas[j]->id;
+            if (!adj.count(src)) continue;
+            std::map<size_t, uint64_t> dist;
+            std::map<size_t, size_t> prev;
+            typedef std::pair<uint64_t, size_t> QE;
+            std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
+            dist[src] = 0;
+            pq.push({0, src});
+            bool found = false;
+            while (!pq.empty()) {
+                const QE top = pq.top();
+                pq.pop();
+                if (top.second == dst) {
+                    found = true;
+                    break;
+                }
+                if (top.first > dist[top.second]) continue;
+                for (auto &nb : adj[top.second]) {
+                    const uint64_t nd = top.first + nb.second;
+                    auto it = dist.find(nb.first);
+                    if (it == dist.end() || nd < it->second) {
+                        dist[nb.first] = nd;
+                        prev[nb.first] = top.second;
+                        pq.push({nd, nb.first});
+                    }
+                }
+            }
+            if (!found) continue;
+            uint32_t t0 = gen_of[dst];
+            for (size_t u = dst;;) {
+                t0 = std::min(t0, gen_of[u]);
+                auto it = prev.find(u);
+                if (u == src || it == prev.end()) break;
+                u = it->second;
+            }
+            const double t1 = (double)meas[i]->generation, t2 = (double)meas[j]->generation;
+            if ((double)dist[dst] != t1 - (double)t0 + t2 - (double)t0) {
+                abfit::set_error("pedigree graph: path length does not match the generation times (the reference asserts here)");
+                return ABFIT_ERR_ARG;
+            }
+            ped->rows.push_back((double)t0);
+            ped->rows.push_back(t1);
+            ped->rows.push_back(t2);
+            ped->rows.push_back(Dfull[(size_t)i * S + j]);
+        }
+    *out = ped.release();
+    return 0;
+}
+
+int abfit_pedigree_info(const abfit_pedigree *p, int32_t *n_pairs, double *p0uu, int32_t *n_samples, int64_t *n_sites)
+{
+    if (!p) return ABFIT_ERR_ARG;
+    if (n_pairs) *n_pairs = (int32_t)(p->rows.size() / 4);
+    if (p0uu) *p0uu = p->p0uu;
+    if (n_samples) *n_samples = p->n_samples;
+    if (n_sites) *n_sites = p->n_sites;
+    return 0;
+}
+
+const double *abfit_pedigree_rows(const abfit_pedigree *p) { return p ? p->rows.data() : nullptr; }
+const char *abfit_pedigree_warnings(const abfit_pedigree *p) { return p ? p->warnings.c_str() : ""; }
+void abfit_pedigree_free(abfit_pedigree *p) { delete p; }
+
+}  // extern "C"

@@ -268,6 +268,21 @@ int abfit_place_sites(const abfit_gene *genes, int32_t n_genes, const abfit_cg_s
  * intercept, pr_mm, pr_um, pr_uu. Host only (O(n) per window). */
 int abfit_analyze(const double *rows, int32_t n, double out[32]);
 
+/* ---- input files (host parsing; the observed divergence of the pedigree runs on the GPU) ------------
+ * MethylationSite::from_methylome_file_line (src/methylation_site.rs:146-362): 0 = parsed, 1 = not a site
+ * (header, non-CG context, malformed), < 0 = error.  status_out: 0 U / 1 I / 2 M. */
+int abfit_parse_methylome_line(const char *line, int32_t invert_strand, abfit_cg_site *site_out, double *posterior_max_out,
+                               int32_t *status_out, double *meth_lvl_out);
+/* Pedigree::build (src/pedigree.rs:92-193) + DMatrix::convert (:264-337): nodelist + edgelist + the methylome files the
+ * nodelist names (relative to the CWD, as in the reference) -> pedigree rows [t0, t1, t2, D] and p0uu. */
+typedef struct abfit_pedigree abfit_pedigree;
+int abfit_pedigree_build(abfit_ctx *ctx, const char *nodelist_path, const char *edgelist_path, double posterior_max_filter,
+                         abfit_pedigree **out);
+int abfit_pedigree_info(const abfit_pedigree *p, int32_t *n_pairs, double *p0uu, int32_t *n_samples, int64_t *n_sites);
+const double *abfit_pedigree_rows(const abfit_pedigree *p); /* [n_pairs][4] */
+const char *abfit_pedigree_warnings(const abfit_pedigree *p);
+void abfit_pedigree_free(abfit_pedigree *p);
+
 /* ---- result files of the reference, byte for byte (host) ------------------------
  * f64 exactly as Rust's `{}` prints it (shortest round-trip digits, never scientific, "1" not "1.0", "NaN", "inf");
  * returns the length or ABFIT_ERR_ARG when buf is too small */

@@ -199,6 +199,21 @@ def _u32(s: str) -> int:
     return v
 
 
+_F64_RE = None
+
+
+def _f64_rust(s: str) -> float:
+    """<f64 as FromStr>::from_str: no surrounding whitespace, no underscores, no hex; inf / infinity / nan in any case"""
+    global _F64_RE
+    import re
+
+    if _F64_RE is None:
+        _F64_RE = re.compile(r"^[+-]?((\d+\.?\d*|\.\d+)([eE][+-]?\d+)?|(?i:inf|infinity|nan))$")
+    if not (s.isascii() and _F64_RE.match(s)):
+        raise ValueError("f64")
+    return float(s)
+
+
 def _status(s: str) -> int:
     """src/methylation_site.rs:101-115,130-136: U=0, I=1, M=2; anything else parses as U"""
     if not s:
@@ -216,7 +231,7 @@ def parse_methylome_line(line: str, invert_strand: bool = False):
             "chromosome": _parse_chromosome(chrom), "start": start, "end": end,
             "strand": ("+" if ((strand == "+") ^ invert_strand) else "-"),
             "count_methylated": _u32(cm), "count_total": _u32(ct),
-            "posteriormax": float(post), "status": _status(status), "meth_lvl": float(lvl), "original": line,
+            "posteriormax": _f64_rust(post), "status": _status(status), "meth_lvl": _f64_rust(lvl), "original": line,
         }
 
     try:
