@@ -350,8 +350,13 @@ def main():
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------
     achieved = evals_fit * fl["flops"] / (fit_ms * 1e-3) / 1e12  # TFLOP/s, algorithmic
+    # DRAM bytes of one k_fit_starts launch at the default configuration, from an ncu capture of this command
+    # (profiles/r01_dram_traffic_bench_default.csv: 1.784 GB read + 0.780 GB written = the start simplices in and the
+    # fit records out; the kernel never re-reads HBM).  Other configurations were not captured.
+    traffic = 1784302336 + 779979008 if (W, NS, NB) == (10000, 1000, 100) else None
     roofline = {"bound": "fp64", "kernel": "k_fit_starts", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": achieved / fp64_peak, "traffic": None,
+                "frac": achieved / fp64_peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)",
+                "bound_note": "FP64 vector pipe (BASELINE.json: % FP64 peak); no tensor cores, HBM traffic is 2.6 GB per 2.3 s launch",
                 "peak_source": "DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure; nominal 37.2)",
                 "flops_per_eval": fl["flops"], "evals_per_launch": evals_fit / args.steps,
                 "kernel_ms": fit_ms / args.steps, "kernel_share_of_step": fit_ms / total_ms,
