@@ -485,3 +485,27 @@ def test_c4_full_size_properties(ab, ctx, oracle, ped351):
     assert np.allclose(out["rows"][..., 4], a * ((1 - a) ** 2 - (1 - b) ** 2 - 1.0) / den, rtol=1e-12, atol=0)
     assert np.allclose(out["rows"][..., 6], b * ((1 - b) ** 2 - (1 - a) ** 2 - 1.0) / den, rtol=1e-12, atol=0)
     assert np.allclose(out["rows"][..., 4:7].sum(axis=-1), 1.0, atol=1e-9)
+
+
+@pytest.mark.parametrize("env", [{"ABFIT_DEV_NWARPS": "4"}, {"ABFIT_DEV_NWARPS": "2"}, {"ABFIT_DEV_NWARPS": "1"},
+                                 {"ABFIT_DEV_XGLOBAL": "1"}, {"ABFIT_DEV_BOOT_TILE": "1"}, {"ABFIT_DEV_CHUNK": "40"},
+                                 {"ABFIT_DEV_BIG": "1"}])
+def test_kernel_variants_are_bit_identical(ab, ctx, ped351, monkeypatch, env):
+    """every launch shape the library can choose (warps per block, queue chunking with tail hand-off, simplex vertices
+    in shared / global memory, stored-D* / index-tile bootstrap, global-scratch lane state) returns the same bits"""
+    rng = np.random.default_rng(33)
+    cases = [synth_problem(rng, ped351) for _ in range(3)]
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    n_starts, n_boot = 400, 48
+    sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    idx = np.concatenate([ab.gen_resample_idx(SEED, i, n_boot, len(p)).ravel() for i, (p, u) in enumerate(cases)])
+    ref = ctx.alphabeta_batch(probs, sx, idx, SEED)
+    ref_all = ctx.fit_batch(probs, sx).all
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = ctx.alphabeta_batch(probs, sx, idx, SEED)
+    got_all = ctx.fit_batch(probs, sx).all
+    for k in ("pred", "resid", "rows", "status", "analysis"):
+        assert np.array_equal(ref[k], got[k], equal_nan=True), k
+    for f in ("theta", "cost", "lse", "iters", "evals", "status", "start_id"):
+        assert np.array_equal(ref_all[f], got_all[f]), f
