@@ -111,6 +111,8 @@ def _load() -> C.CDLL:
         "abfit_parse_methylome_line": (C.c_int, [C.c_char_p, i32, vp, vp, vp, vp]),
         "abfit_pedigree_build": (C.c_int, [vp, C.c_char_p, C.c_char_p, dbl, C.POINTER(vp)]),
         "abfit_pedigree_info": (C.c_int, [vp, vp, vp, vp, vp]),
+        "abfit_pedigree_graph": (C.c_int, [C.c_char_p, C.c_char_p, vp, C.c_char_p, i32, vp, vp, i32]),
+        "abfit_parse_annotation_line": (C.c_int, [C.c_char_p, i32, vp]),
         "abfit_pedigree_rows": (vp, [vp]),
         "abfit_pedigree_warnings": (C.c_char_p, [vp]),
         "abfit_pedigree_free": (None, [vp]),
@@ -141,7 +143,7 @@ EXPORTED_SYMBOLS = (
     "abfit_batch_destroy abfit_batch_upload_starts abfit_batch_run_fit abfit_batch_download_fit "
     "abfit_batch_upload_boot abfit_batch_run_boot abfit_batch_download_boot abfit_batch_sync "
     "abfit_batch_timing abfit_batch_flops_per_eval abfit_analyze abfit_window_counts abfit_place_sites "
-    "abfit_parse_methylome_line abfit_pedigree_build abfit_pedigree_info abfit_pedigree_rows abfit_pedigree_warnings "
+    "abfit_parse_methylome_line abfit_parse_annotation_line abfit_pedigree_graph abfit_pedigree_build abfit_pedigree_info abfit_pedigree_rows abfit_pedigree_warnings "
     "abfit_pedigree_free abfit_format_f64 abfit_steady_state abfit_write_pedigree abfit_write_analysis abfit_format_analysis "
     "abfit_write_npy_f64 abfit_write_metaprofile_results"
 ).split()
@@ -720,3 +722,23 @@ def build_pedigree(ctx: Context, nodelist: str, edgelist: str, posterior_max_fil
     finally:
         _lib.abfit_pedigree_free(h)
     return rows, p0.value, {"n_samples": ns.value, "n_sites": nl.value, "warnings": warn}
+
+
+def parse_annotation_line(line: str, invert_strand: bool = False):
+    """Gene::from_annotation_file_line (src/genes.rs:166-216) -> (chromosome, start, end, strand) or None"""
+    g = np.zeros(1, dtype=GENE_DTYPE)
+    rc = _lib.abfit_parse_annotation_line(line.encode(), int(invert_strand), _ptr(g))
+    if rc == 1:
+        return None
+    _check(rc)
+    return (int(g[0]["chromosome"]), int(g[0]["start"]), int(g[0]["end"]), int(g[0]["strand"]))
+
+
+def pedigree_graph(nodelist: str, edgelist: str):
+    """nodelist + edgelist -> (measured files [S], pairs float64 [n_pairs, 5] = i, j, t0, t1, t2)"""
+    ns, npairs = C.c_int32(), C.c_int32()
+    files = C.create_string_buffer(1 << 20)
+    pairs = np.zeros((1 << 16, 5))
+    _check(_lib.abfit_pedigree_graph(os.fsencode(nodelist), os.fsencode(edgelist), C.cast(C.byref(ns), C.c_void_p), files,
+                                     1 << 20, C.cast(C.byref(npairs), C.c_void_p), _ptr(pairs), 1 << 16))
+    return files.value.decode().split("\n")[:-1], pairs[:npairs.value].copy()

@@ -1,0 +1,424 @@
+// metaprofile — front end with the flags of the reference's `metaprofile` binary (src/cli/metaprofile.rs:14-114,
+// src/arguments.rs:9-62, src/extract.rs:17-155) on top of libabfit, FUSED: sites are binned once in memory, the observed
+// divergence of every window is one abfit_divergence call (segment offsets) and all windows are fitted by one
+// abfit_alphabeta_batch call — instead of one directory of re-written methylome files and one serial alphabeta::run
+// per window (src/cli/metaprofile.rs:50-72).
+//
+//   metaprofile -m <methylome dir> -g <annotation> [-w 5] [-s 0] [-o .] [-a] [-c 2048] [-i] [--name N]
+//               [--cutoff-gene-length] [--iterations 100] [--seed N] [--device 0]
+//               [alphabeta --nodes <nodelist> --edges <edgelist>]
+//
+// Files written (formats of the reference): distribution_<file>, distributions.txt, steady_state_methylation.txt,
+// all_steady_state_methylation.txt and, with the sub-command, results.txt and raw.npy (iterations x 7 x windows).
+// Deliberate differences: no per-window directories / methylome copies and no metaplot.png; methylome files are
+// processed in name order (the reference uses the directory's own order); every window is fitted on ITS OWN sites
+// (the reference only does that when the nodelist holds absolute, tab-separated paths: src/setup.rs:48-58), the
+// measured nodes being matched to the methylome files by file name; the windows looped over are those of
+// Windows::new (the reference's loop `(0..max).step_by(step)` can run one directory past them); seeded RNG.
+// Like the reference, a window that cannot be fitted prints an error and is skipped, and results.txt pairs the
+// i-th fitted window with the i-th distribution entry (src/cli/metaprofile.rs:76-77).
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dirent.h>
+#include <fstream>
+#include <map>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+#include "../../include/abfit.h"
+
+static std::string f64s(double v)
+{
+    char buf[512];
+    abfit_format_f64(v, buf, sizeof buf);
+    return buf;
+}
+static bool exists(const std::string &p)
+{
+    struct stat st;
+    return stat(p.c_str(), &st) == 0;
+}
+static std::string base_name(const std::string &p)
+{
+    const size_t k = p.find_last_of('/');
+    return k == std::string::npos ? p : p.substr(k + 1);
+}
+static int write_text(const std::string &path, const std::string &c)
+{
+    FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) return 1;
+    std::fwrite(c.data(), 1, c.size(), f);
+    std::fclose(f);
+    return 0;
+}
+
+struct Sample {
+    std::string name;
+    std::vector<abfit_cg_site> sites;
+    std::vector<uint8_t> status;
+    std::vector<double> post, meth;
+    std::vector<int32_t> dist;
+    std::vector<int64_t> order, seg;  // sites of window w: order[seg[w] .. seg[w+1]) (file order)
+};
+
+int main(int argc, char **argv)
+{
+    std::string methylome, genome, output = ".", name, nodes, edges;
+    uint32_t window_size = 5, window_step = 0, cutoff = 2048;
+    bool absolute = false, invert = false, cutoff_gene_length = false, sub = false;
+    long iterations = 100;
+    unsigned long long seed = 0xAB0B200ull;
+    int device = 0;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto val = [&]() -> const char * {
+            if (i + 1 >= argc) {
+                std::fprintf(stderr, "error: a value is required for '%s'\n", a.c_str());
+                std::exit(2);
+            }
+            return argv[++i];
+        };
+        if (a == "alphabeta") sub = true;
+        else if (sub && (a == "-n" || a == "--nodes")) nodes = val();
+        else if (sub && (a == "-e" || a == "--edges")) edges = val();
+        else if (sub && (a == "-i" || a == "--iterations" || a == "-p" || a == "--posterior-max-filter" || a == "-o" || a == "--output")) val();  // parsed and ignored, like the reference (src/arguments.rs:142-152)
+        else if (a == "-m" || a == "--methylome") methylome = val();
+        else if (a == "-g" || a == "--genome") genome = val();
+        else if (a == "-w" || a == "--window-size") window_size = (uint32_t)std::strtoul(val(), nullptr, 10);
+        else if (a == "-s" || a == "--window-step") window_step = (uint32_t)std::strtoul(val(), nullptr, 10);
+        else if (a == "-o" || a == "--output-dir") output = val();
+        else if (a == "-a" || a == "--absolute") absolute = true;
+        else if (a == "-c" || a == "--cutoff") cutoff = (uint32_t)std::strtoul(val(), nullptr, 10);
+        else if (a == "-i" || a == "--invert") invert = true;
+        else if (a == "--name") name = val();
+        else if (a == "-f" || a == "--force") {}
+        else if (a == "--cutoff-gene-length") cutoff_gene_length = true;
+        else if (a == "--iterations") iterations = std::atol(val());
+        else if (a == "--seed") seed = std::strtoull(val(), nullptr, 0);
+        else if (a == "--device") device = std::atoi(val());
+        else {
+            std::fprintf(stderr, "error: unexpected argument '%s' found\n", a.c_str());
+            return 2;
+        }
+    }
+    if (methylome.empty() || genome.empty()) {
+        std::fprintf(stderr, "error: the following required arguments were not provided:\n  --methylome <METHYLOME>\n  --genome <GENOME>\n");
+        return 2;
+    }
+    std::printf("Starting run %s\n", name.c_str());
+    if (window_step == 0) window_step = window_size;  // src/cli/metaprofile.rs:18-20
+    if (window_step == 0 || iterations <= 0) {
+        std::printf("Error: window size / step and iterations must be positive\n");
+        return 1;
+    }
+
+    // ---- extract (src/extract.rs:17-155) -----------------------------------------------------------------------
+    std::vector<std::string> files;  // load_methylome (src/files.rs:23-38)
+    if (DIR *d = opendir(methylome.c_str())) {
+        while (dirent *e = readdir(d)) {
+            const std::string fn = e->d_name;
+            const size_t dot = fn.find_last_of('.');
+            if (fn == "." || fn == ".." || dot == std::string::npos || dot == 0) continue;
+            const std::string ext = fn.substr(dot + 1);
+            if (ext.find("tsv") != std::string::npos || ext.find("fn") != std::string::npos) continue;
+            files.push_back(fn);
+        }
+        closedir(d);
+    }
+    if (files.empty()) {
+        std::printf("Error: Could not find any files in the methylome directory. Please check your input. Files with .tsv or .fn extensions are ignored.\n");
+        return 1;
+    }
+    std::sort(files.begin(), files.end());
+    std::vector<abfit_gene> genes;
+    {
+        std::ifstream f(genome);
+        if (!f) {
+            std::printf("Error: Error while reading genome annotation file: %s\n", genome.c_str());
+            return 1;
+        }
+        std::string line;
+        abfit_gene g;
+        while (std::getline(f, line)) {
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            if (abfit_parse_annotation_line(line.c_str(), invert, &g) == 0) genes.push_back(g);
+        }
+    }
+    if (genes.empty()) {
+        std::printf("Error: Could not parse a single annotation from the annotation file. Please check your input or add a parser implemenation for your data format.\n");
+        return 1;
+    }
+    uint32_t max_gene_length = 100;  // src/extract.rs:49-58
+    if (absolute) {
+        max_gene_length = 0;
+        for (auto &g : genes) max_gene_length = std::max(max_gene_length, (uint32_t)(g.end - g.start));
+        std::printf("The maximum gene length is %u bp\n", max_gene_length);
+    }
+    if (!exists(output)) {
+        std::printf("Error: output directory %s does not exist\n", output.c_str());
+        return 1;
+    }
+    abfit_window_args wa{window_size, window_step, cutoff, max_gene_length, absolute ? 1 : 0, cutoff_gene_length ? 1 : 0};
+    int32_t nwin[3];
+    if (abfit_window_counts(&wa, nwin)) {
+        std::printf("Error: %s\n", abfit_last_error());
+        return 1;
+    }
+    const int n_total = nwin[0] + nwin[1] + nwin[2];
+
+    std::vector<Sample> samples(files.size());
+    for (size_t fi = 0; fi < files.size(); ++fi) {
+        Sample &S = samples[fi];
+        S.name = files[fi];
+        std::ifstream f(methylome + "/" + files[fi]);
+        std::string line;
+        bool first = true;
+        abfit_cg_site site;
+        double post, lvl;
+        int32_t status;
+        while (std::getline(f, line)) {
+            if (first) {  // Windows::extract skips the header row (src/windows.rs:322)
+                first = false;
+                continue;
+            }
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            if (abfit_parse_methylome_line(line.c_str(), invert, &site, &post, &status, &lvl) != 0) continue;
+            S.sites.push_back(site);
+            S.status.push_back((uint8_t)status);
+            S.post.push_back(post);
+            S.meth.push_back(lvl);
+        }
+        S.dist.assign(n_total, 0);
+        int64_t n_assign = 0;
+        abfit_place_sites(genes.data(), (int32_t)genes.size(), S.sites.data(), (int64_t)S.sites.size(), &wa, S.dist.data(), &n_assign, 0,
+                          nullptr, nullptr);
+        std::vector<int64_t> asite((size_t)n_assign);
+        std::vector<int32_t> awin((size_t)n_assign);
+        abfit_place_sites(genes.data(), (int32_t)genes.size(), S.sites.data(), (int64_t)S.sites.size(), &wa, S.dist.data(), &n_assign,
+                          n_assign, asite.data(), awin.data());
+        if (invert) {
+            // Windows::inverse (src/windows.rs:87-92), quirk included: upstream <- reversed downstream, gene reversed,
+            // downstream <- reversed NEW upstream = the old downstream
+            auto remap = [&](int32_t w) -> std::vector<int32_t> {
+                std::vector<int32_t> out;
+                if (w >= nwin[0] && w < nwin[0] + nwin[1]) out.push_back(nwin[0] + (nwin[1] - 1 - (w - nwin[0])));
+                if (w >= nwin[0] + nwin[1]) {
+                    const int i = w - nwin[0] - nwin[1];
+                    out.push_back(nwin[0] - 1 - i);        // new upstream
+                    out.push_back(nwin[0] + nwin[1] + i);  // new downstream = old downstream
+                }
+                return out;  // old upstream sites are dropped
+            };
+            std::vector<int64_t> a2;
+            std::vector<int32_t> w2;
+            for (int64_t q = 0; q < n_assign; ++q)
+                for (int32_t nw : remap(awin[q])) {
+                    a2.push_back(asite[q]);
+                    w2.push_back(nw);
+                }
+            asite.swap(a2);
+            awin.swap(w2);
+            std::fill(S.dist.begin(), S.dist.end(), 0);
+            for (int32_t w : awin) ++S.dist[w];
+        }
+        // stable counting sort of the hits by window: file order inside every window
+        S.seg.assign(n_total + 1, 0);
+        for (int32_t w : awin) ++S.seg[w + 1];
+        for (int w = 0; w < n_total; ++w) S.seg[w + 1] += S.seg[w];
+        S.order.resize(asite.size());
+        std::vector<int64_t> cur(S.seg.begin(), S.seg.end() - 1);
+        for (size_t q = 0; q < asite.size(); ++q) S.order[(size_t)cur[awin[q]]++] = asite[q];
+    }
+    // distribution / steady-state files (src/extract.rs:100-151, src/windows.rs:94-176,245-257)
+    std::vector<std::vector<double>> ss(samples.size(), std::vector<double>(n_total));
+    for (size_t fi = 0; fi < samples.size(); ++fi)
+        for (int w = 0; w < n_total; ++w) {
+            double acc = 0.0;
+            for (int64_t q = samples[fi].seg[w]; q < samples[fi].seg[w + 1]; ++q) acc = acc + samples[fi].meth[(size_t)samples[fi].order[q]];
+            ss[fi][w] = acc / (double)(samples[fi].seg[w + 1] - samples[fi].seg[w]);
+        }
+    std::vector<double> avg(n_total, 0.0);
+    for (size_t fi = 0; fi < samples.size(); ++fi)
+        for (int w = 0; w < n_total; ++w) avg[w] += ss[fi][w] / (double)samples.size();
+    std::string all_d, all_s, avg_s;
+    for (size_t fi = 0; fi < samples.size(); ++fi) {
+        std::string one;
+        all_d += samples[fi].name + ";";
+        all_s += samples[fi].name + ";";
+        for (int w = 0; w < n_total; ++w) {
+            one += std::to_string(samples[fi].dist[w]) + "\n";
+            all_d += std::to_string(samples[fi].dist[w]) + ";";
+            all_s += f64s(ss[fi][w]) + ";";
+        }
+        all_d += "\n";
+        all_s += "\n";
+        write_text(output + "/distribution_" + samples[fi].name, one);
+    }
+    for (int w = 0; w < n_total; ++w) avg_s += f64s(avg[w]) + "\n";
+    write_text(output + "/steady_state_methylation.txt", avg_s);
+    write_text(output + "/all_steady_state_methylation.txt", all_s);
+    write_text(output + "/distributions.txt", all_d);
+    if (!sub) {
+        std::printf("Done\n");
+        return 0;
+    }
+
+    // ---- alphabeta_multiple (src/cli/metaprofile.rs:33-114), fused ----------------------------------------------
+    if (nodes.empty() || edges.empty()) {
+        std::printf("Error: the alphabeta sub-command needs --nodes and --edges\n");
+        return 1;
+    }
+    int32_t S = 0, n_pairs = 0;
+    std::vector<char> fbuf(1 << 20);
+    std::vector<double> pairs(5 * 65536);
+    if (abfit_pedigree_graph(nodes.c_str(), edges.c_str(), &S, fbuf.data(), (int32_t)fbuf.size(), &n_pairs, pairs.data(), 65536)) {
+        std::printf("Error: Error while building pedigree: %s\n", abfit_last_error());
+        return 1;
+    }
+    std::vector<int> sample_of(S, -1);  // measured node -> methylome file, by file name
+    {
+        std::string all(fbuf.data());
+        size_t pos = 0;
+        for (int s = 0; s < S; ++s) {
+            const size_t e = all.find('\n', pos);
+            const std::string bn = base_name(all.substr(pos, e - pos));
+            pos = e + 1;
+            for (size_t fi = 0; fi < samples.size(); ++fi)
+                if (samples[fi].name == bn) sample_of[s] = (int)fi;
+            if (sample_of[s] < 0) {
+                std::printf("Error: Error while building pedigree: Could not open node file: %s\n", bn.c_str());
+                return 1;
+            }
+        }
+    }
+    abfit_ctx *ctx = nullptr;
+    if (abfit_ctx_create(device, &ctx)) {
+        std::printf("Error: %s\n", abfit_last_error());
+        return 1;
+    }
+    // windows whose samples all list the same number of sites go into one divergence call
+    std::vector<int> usable;
+    std::vector<int64_t> seg{0};
+    for (int w = 0; w < n_total; ++w) {
+        const int64_t len = samples[sample_of[0]].seg[w + 1] - samples[sample_of[0]].seg[w];
+        bool same = len > 0;
+        for (int s = 1; s < S; ++s) same &= samples[sample_of[s]].seg[w + 1] - samples[sample_of[s]].seg[w] == len;
+        if (!same) {
+            std::printf("Error: Model failed: window %d is empty or its samples list different numbers of sites\n", w);
+            continue;
+        }
+        usable.push_back(w);
+        seg.push_back(seg.back() + len);
+    }
+    const int64_t L = seg.back();
+    const int W = (int)usable.size();
+    const size_t P = (size_t)S * (S - 1) / 2;
+    std::vector<uint8_t> st((size_t)S * L);
+    std::vector<double> po((size_t)S * L), me((size_t)S * L);
+    for (int s = 0; s < S; ++s) {
+        const Sample &A = samples[sample_of[s]];
+        int64_t o = 0;
+        for (int w : usable)
+            for (int64_t q = A.seg[w]; q < A.seg[w + 1]; ++q, ++o) {
+                st[(size_t)s * L + o] = A.status[(size_t)A.order[q]];
+                po[(size_t)s * L + o] = A.post[(size_t)A.order[q]];
+                me[(size_t)s * L + o] = A.meth[(size_t)A.order[q]];
+            }
+    }
+    std::vector<double> D((size_t)std::max(W, 1) * std::max<size_t>(P, 1)), p0uu(std::max(W, 1));
+    if (W > 0 && abfit_divergence(ctx, st.data(), po.data(), me.data(), S, L, seg.data(), W, 0.99, D.data(), nullptr, nullptr, p0uu.data(),
+                                  nullptr, nullptr)) {
+        std::printf("Error: %s\n", abfit_last_error());
+        return 1;
+    }
+    // one problem per window whose pedigree has no NaN (the reference panics on those, src/ab_neutral.rs:28)
+    std::vector<int> fitted;
+    std::vector<std::vector<double>> peds;
+    for (int k = 0; k < W; ++k) {
+        std::vector<double> ped((size_t)n_pairs * 4);
+        bool ok = n_pairs > 0 && p0uu[k] == p0uu[k];
+        for (int r = 0; r < n_pairs; ++r) {
+            const int i = (int)pairs[5 * r], j = (int)pairs[5 * r + 1];
+            const size_t p = (size_t)i * S - (size_t)i * (i + 1) / 2 + (size_t)(j - i - 1);
+            ped[4 * r + 0] = pairs[5 * r + 2];
+            ped[4 * r + 1] = pairs[5 * r + 3];
+            ped[4 * r + 2] = pairs[5 * r + 4];
+            ped[4 * r + 3] = D[(size_t)k * P + p];
+            ok &= ped[4 * r + 3] == ped[4 * r + 3];
+        }
+        if (!ok) {
+            std::printf("Error: Model failed: window %d has too few valid sites (NaN divergence)\n", usable[k]);
+            continue;
+        }
+        fitted.push_back(k);
+        peds.push_back(std::move(ped));
+    }
+    const int F = (int)fitted.size();
+    const int n = (int)iterations;
+    std::vector<abfit_problem> probs(F);
+    std::vector<double> simplices((size_t)F * n * 20), rows((size_t)F * n * 7), analysis((size_t)F * 32);
+    std::vector<int32_t> idx((size_t)F * n * n_pairs), status(F);
+    std::vector<abfit_fit> best(F);
+    for (int f = 0; f < F; ++f) {
+        const int k = fitted[f];
+        probs[f] = abfit_problem{peds[f].data(), n_pairs, p0uu[k], p0uu[k], 1.0};
+        double max_div = peds[f][3];
+        for (int r = 1; r < n_pairs; ++r) max_div = std::max(max_div, peds[f][4 * r + 3]);
+        abfit_gen_start_simplices(seed, (uint64_t)usable[k], n, max_div, simplices.data() + (size_t)f * n * 20);
+        abfit_gen_resample_idx(seed, (uint64_t)usable[k], n, n_pairs, idx.data() + (size_t)f * n * n_pairs);
+    }
+    // NB: the vary vertices are keyed by (seed, position in the batch); a window's result therefore depends on which
+    // windows precede it only through that key, never through their data
+    if (F > 0 && abfit_alphabeta_batch(ctx, probs.data(), F, n, simplices.data(), n, idx.data(), seed, 0, 10000, 1000, DBL_EPSILON, 0,
+                                       best.data(), nullptr, nullptr, status.data(), rows.data(), analysis.data())) {
+        std::printf("Error: %s\n", abfit_last_error());
+        return 1;
+    }
+    std::vector<int32_t> cg, region;
+    std::vector<abfit_fit> rbest;
+    std::vector<double> ranalysis, robs, raw;
+    std::vector<int> keep;
+    for (int f = 0; f < F; ++f) {
+        if (status[f] != 0) {
+            std::printf("Error: Model failed: window %d\n", usable[fitted[f]]);
+            continue;
+        }
+        keep.push_back(f);
+    }
+    const int R = (int)keep.size();
+    for (int q = 0; q < R; ++q) {
+        const int f = keep[q], w = usable[fitted[f]];
+        cg.push_back(samples[0].dist[(size_t)q]);  // the i-th result meets the i-th distribution entry (src/cli/metaprofile.rs:76-77)
+        region.push_back(w < nwin[0] ? 0 : w < nwin[0] + nwin[1] ? 1 : 2);
+        rbest.push_back(best[f]);
+        ranalysis.insert(ranalysis.end(), analysis.begin() + (size_t)f * 32, analysis.begin() + (size_t)f * 32 + 32);
+        robs.push_back(1.0 - p0uu[fitted[f]]);
+    }
+    raw.resize((size_t)n * 7 * R);  // [iteration][column][window]
+    for (int q = 0; q < R; ++q)
+        for (int it = 0; it < n; ++it)
+            for (int c = 0; c < 7; ++c) raw[((size_t)it * 7 + c) * R + q] = rows[((size_t)keep[q] * n + it) * 7 + c];
+    const std::string rp = output + "/results.txt";
+    if (abfit_write_metaprofile_results(rp.c_str(), name.c_str(), R, cg.data(), region.data(), rbest.data(), ranalysis.data(), robs.data())) {
+        std::printf("Error: %s\n", abfit_last_error());
+        return 1;
+    }
+    {
+        std::ifstream f(rp);
+        std::string line;
+        while (std::getline(f, line)) std::printf("%s\n", line.c_str());
+        std::printf("\n");
+    }
+    const int64_t shape[3] = {n, 7, R};
+    if (abfit_write_npy_f64((output + "/raw.npy").c_str(), raw.data(), 3, shape)) {
+        std::printf("Error: %s\n", abfit_last_error());
+        return 1;
+    }
+    abfit_ctx_destroy(ctx);
+    return 0;
+}

@@ -164,41 +164,19 @@ struct Node {
     bool meth;
 };
 
-}  // namespace
 
-struct abfit_pedigree {
-    std::vector<double> rows;  // [n_pairs][4]
-    double p0uu = 0.0;
-    int32_t n_samples = 0;
-    int64_t n_sites = 0;
-    std::string warnings;
+// nodelist + edgelist -> measured nodes and, for every pair of them connected in the pedigree graph, (i, j, t0, t1, t2)
+struct PedGraph {
+    std::vector<Node> meas;
+    struct Pair {
+        int i, j;
+        double t0, t1, t2;
+    };
+    std::vector<Pair> pairs;
 };
 
-extern "C" {
-
-int abfit_parse_methylome_line(const char *line, int32_t invert_strand, abfit_cg_site *site_out, double *posterior_max_out,
-                               int32_t *status_out, double *meth_lvl_out)
+int build_graph(const char *nodelist_path, const char *edgelist_path, PedGraph &g)
 {
-    if (!line) return ABFIT_ERR_ARG;
-    Site s;
-    if (!parse_methylome_line(line, invert_strand != 0, s)) return 1;  // not a site (header, other context, malformed)
-    if (site_out) {
-        site_out->chromosome = s.chromosome;
-        site_out->start = s.start;
-        site_out->end = s.end;
-        site_out->strand = s.strand;
-    }
-    if (posterior_max_out) *posterior_max_out = s.posteriormax;
-    if (status_out) *status_out = s.status;
-    if (meth_lvl_out) *meth_lvl_out = s.meth_lvl;
-    return 0;
-}
-
-int abfit_pedigree_build(abfit_ctx *ctx, const char *nodelist_path, const char *edgelist_path, double posterior_max_filter,
-                         abfit_pedigree **out)
-{
-    if (!ctx || !nodelist_path || !edgelist_path || !out) return ABFIT_ERR_ARG;
-    *out = nullptr;
     std::string ntext, etext;
     if (!read_file(nodelist_path, ntext) || !read_file(edgelist_path, etext)) {
         abfit::set_error("cannot read the nodelist or the edgelist");
@@ -236,70 +214,9 @@ int abfit_pedigree_build(abfit_ctx *ctx, const char *nodelist_path, const char *
             if (a && b) edges.push_back(Edge{a, b});
         }
     }
-    // measured nodes and their site tables (src/pedigree.rs:137-177); node.file is relative to the CWD
-    std::vector<const Node *> meas;
     for (auto &n : nodes)
-        if (n.meth) meas.push_back(&n);
-    const int S = (int)meas.size();
-    std::vector<std::vector<uint8_t>> st(S);
-    std::vector<std::vector<double>> po(S), me(S);
-    for (int s = 0; s < S; ++s) {
-        std::ifstream f(meas[s]->file);
-        if (!f) {
-            abfit::set_error("Could not open node file: " + meas[s]->file);
-            return ABFIT_ERR_ARG;
-        }
-        std::string line;
-        Site site;
-        while (std::getline(f, line)) {
-            if (!line.empty() && line.back() == '\r') line.pop_back();  // BufRead::lines strips \r\n
-            if (!parse_methylome_line(line, false, site)) continue;
-            st[s].push_back(site.status);
-            po[s].push_back(site.posteriormax);
-            me[s].push_back(site.meth_lvl);
-        }
-    }
-    std::unique_ptr<abfit_pedigree> ped(new abfit_pedigree());
-    ped->n_samples = S;
-    // observed divergence + per-sample methylation level on the GPU, one call per group of samples with equally long
-    // site lists (pairs of unequal length get D = 0 with a warning, src/pedigree.rs:222-230)
-    std::vector<double> Dfull((size_t)S * S, 0.0);  // [i][j] for i < j
-    std::vector<double> rc(S, 0.0);
-    std::map<size_t, std::vector<int>> by_len;
-    for (int s = 0; s < S; ++s) by_len[st[s].size()].push_back(s);
-    if (by_len.size() > 1) ped->warnings += "Lengths do not match, all bets are off: pairs of samples with different site counts get D = 0\n";
-    for (auto &kv : by_len) {
-        const std::vector<int> &grp = kv.second;
-        const int G = (int)grp.size();
-        const int64_t L = (int64_t)kv.first;
-        ped->n_sites = std::max(ped->n_sites, L);
-        std::vector<uint8_t> gs((size_t)G * L);
-        std::vector<double> gp((size_t)G * L), gm((size_t)G * L);
-        for (int g = 0; g < G; ++g) {
-            std::copy(st[grp[g]].begin(), st[grp[g]].end(), gs.begin() + (size_t)g * L);
-            std::copy(po[grp[g]].begin(), po[grp[g]].end(), gp.begin() + (size_t)g * L);
-            std::copy(me[grp[g]].begin(), me[grp[g]].end(), gm.begin() + (size_t)g * L);
-        }
-        const size_t P = (size_t)G * (G - 1) / 2;
-        std::vector<double> D(std::max<size_t>(P, 1)), methsum(G);
-        std::vector<int64_t> nvalid(G);
-        if (int rc2 = abfit_divergence(ctx, gs.data(), gp.data(), gm.data(), G, L, nullptr, 1, posterior_max_filter, D.data(),
-                                       nullptr, nullptr, nullptr, methsum.data(), nvalid.data()))
-            return rc2;
-        size_t p = 0;
-        for (int a = 0; a < G; ++a) {
-            rc[grp[a]] = methsum[a] / (double)nvalid[a];  // src/pedigree.rs:171-172 (0/0 = NaN)
-            for (int b = a + 1; b < G; ++b) {
-                const int i = std::min(grp[a], grp[b]), j = std::max(grp[a], grp[b]);
-                Dfull[(size_t)i * S + j] = D[p++];
-            }
-        }
-    }
-    {
-        double acc = 0.0;  // src/pedigree.rs:179-183
-        for (int s = 0; s < S; ++s) acc += 1.0 - rc[s];
-        ped->p0uu = acc / (double)S;
-    }
+        if (n.meth) g.meas.push_back(n);
+    const int S = (int)g.meas.size();
     // DMatrix::convert: undirected graph, edge weight |generation difference|, shortest path, t0 = smallest
     // generation on the path (src/pedigree.rs:264-337).  petgraph's astar with a zero heuristic is Dijkstra;
     // pedigrees are trees, so the path is unique.
@@ -315,7 +232,7 @@ int abfit_pedigree_build(abfit_ctx *ctx, const char *nodelist_path, const char *
     }
     for (int i = 0; i < S; ++i)
         for (int j = i + 1; j < S; ++j) {
-            const size_t src = meas[i]->id, dst = meas[j]->id;
+            const size_t src = g.meas[i].id, dst = g.meas[j].id;
             if (!adj.count(src)) continue;
             std::map<size_t, uint64_t> dist;
             std::map<size_t, size_t> prev;
@@ -350,17 +267,168 @@ int abfit_pedigree_build(abfit_ctx *ctx, const char *nodelist_path, const char *
                 if (u == src || it == prev.end()) break;
                 u = it->second;
             }
-            const double t1 = (double)meas[i]->generation, t2 = (double)meas[j]->generation;
+            const double t1 = (double)g.meas[i].generation, t2 = (double)g.meas[j].generation;
             if ((double)dist[dst] != t1 - (double)t0 + t2 - (double)t0) {
                 abfit::set_error("pedigree graph: path length does not match the generation times (the reference asserts here)");
                 return ABFIT_ERR_ARG;
             }
-            ped->rows.push_back((double)t0);
-            ped->rows.push_back(t1);
-            ped->rows.push_back(t2);
-            ped->rows.push_back(Dfull[(size_t)i * S + j]);
+            g.pairs.push_back(PedGraph::Pair{i, j, (double)t0, t1, t2});
         }
+    return 0;
+}
+
+}  // namespace
+
+struct abfit_pedigree {
+    std::vector<double> rows;  // [n_pairs][4]
+    double p0uu = 0.0;
+    int32_t n_samples = 0;
+    int64_t n_sites = 0;
+    std::string warnings;
+};
+
+extern "C" {
+
+int abfit_parse_methylome_line(const char *line, int32_t invert_strand, abfit_cg_site *site_out, double *posterior_max_out,
+                               int32_t *status_out, double *meth_lvl_out)
+{
+    if (!line) return ABFIT_ERR_ARG;
+    Site s;
+    if (!parse_methylome_line(line, invert_strand != 0, s)) return 1;  // not a site (header, other context, malformed)
+    if (site_out) {
+        site_out->chromosome = s.chromosome;
+        site_out->start = s.start;
+        site_out->end = s.end;
+        site_out->strand = s.strand;
+    }
+    if (posterior_max_out) *posterior_max_out = s.posteriormax;
+    if (status_out) *status_out = s.status;
+    if (meth_lvl_out) *meth_lvl_out = s.meth_lvl;
+    return 0;
+}
+
+int abfit_pedigree_build(abfit_ctx *ctx, const char *nodelist_path, const char *edgelist_path, double posterior_max_filter,
+                         abfit_pedigree **out)
+{
+    if (!ctx || !nodelist_path || !edgelist_path || !out) return ABFIT_ERR_ARG;
+    *out = nullptr;
+    PedGraph g;
+    if (int rc = build_graph(nodelist_path, edgelist_path, g)) return rc;
+    // measured nodes and their site tables (src/pedigree.rs:137-177); node.file is relative to the CWD
+    const int S = (int)g.meas.size();
+    std::vector<std::vector<uint8_t>> st(S);
+    std::vector<std::vector<double>> po(S), me(S);
+    for (int s = 0; s < S; ++s) {
+        std::ifstream f(g.meas[s].file);
+        if (!f) {
+            abfit::set_error("Could not open node file: " + g.meas[s].file);
+            return ABFIT_ERR_ARG;
+        }
+        std::string line;
+        Site site;
+        while (std::getline(f, line)) {
+            if (!line.empty() && line.back() == '\r') line.pop_back();  // BufRead::lines strips \r\n
+            if (!parse_methylome_line(line, false, site)) continue;
+            st[s].push_back(site.status);
+            po[s].push_back(site.posteriormax);
+            me[s].push_back(site.meth_lvl);
+        }
+    }
+    std::unique_ptr<abfit_pedigree> ped(new abfit_pedigree());
+    ped->n_samples = S;
+    // observed divergence + per-sample methylation level on the GPU, one call per group of samples with equally long
+    // site lists (pairs of unequal length get D = 0 with a warning, src/pedigree.rs:222-230)
+    std::vector<double> Dfull((size_t)S * S, 0.0);  // [i][j] for i < j
+    std::vector<double> rc(S, 0.0);
+    std::map<size_t, std::vector<int>> by_len;
+    for (int s = 0; s < S; ++s) by_len[st[s].size()].push_back(s);
+    if (by_len.size() > 1) ped->warnings += "Lengths do not match, all bets are off: pairs of samples with different site counts get D = 0\n";
+    for (auto &kv : by_len) {
+        const std::vector<int> &grp = kv.second;
+        const int G = (int)grp.size();
+        const int64_t L = (int64_t)kv.first;
+        ped->n_sites = std::max(ped->n_sites, L);
+        std::vector<uint8_t> gs((size_t)G * L);
+        std::vector<double> gp((size_t)G * L), gm((size_t)G * L);
+        for (int q = 0; q < G; ++q) {
+            std::copy(st[grp[q]].begin(), st[grp[q]].end(), gs.begin() + (size_t)q * L);
+            std::copy(po[grp[q]].begin(), po[grp[q]].end(), gp.begin() + (size_t)q * L);
+            std::copy(me[grp[q]].begin(), me[grp[q]].end(), gm.begin() + (size_t)q * L);
+        }
+        const size_t P = (size_t)G * (G - 1) / 2;
+        std::vector<double> D(std::max<size_t>(P, 1)), methsum(G);
+        std::vector<int64_t> nvalid(G);
+        if (int rc2 = abfit_divergence(ctx, gs.data(), gp.data(), gm.data(), G, L, nullptr, 1, posterior_max_filter, D.data(),
+                                       nullptr, nullptr, nullptr, methsum.data(), nvalid.data()))
+            return rc2;
+        size_t p = 0;
+        for (int a = 0; a < G; ++a) {
+            rc[grp[a]] = methsum[a] / (double)nvalid[a];  // src/pedigree.rs:171-172 (0/0 = NaN)
+            for (int b = a + 1; b < G; ++b) {
+                const int i = std::min(grp[a], grp[b]), j = std::max(grp[a], grp[b]);
+                Dfull[(size_t)i * S + j] = D[p++];
+            }
+        }
+    }
+    {
+        double acc = 0.0;  // src/pedigree.rs:179-183
+        for (int s = 0; s < S; ++s) acc += 1.0 - rc[s];
+        ped->p0uu = acc / (double)S;
+    }
+    for (auto &pr : g.pairs) {
+        ped->rows.push_back(pr.t0);
+        ped->rows.push_back(pr.t1);
+        ped->rows.push_back(pr.t2);
+        ped->rows.push_back(Dfull[(size_t)pr.i * S + pr.j]);
+    }
     *out = ped.release();
+    return 0;
+}
+
+// The graph part alone (metaprofile: the same nodes and edges for every window, only D changes).
+//   files_out: the measured nodes' file names, '\n'-separated, in nodelist order (caller-owned buffer of files_cap bytes)
+//   pairs_out [n_pairs][5]: i, j (sample indices, i < j), t0, t1, t2 in pedigree row order; D of row r is D[pair index of (i, j)]
+int abfit_pedigree_graph(const char *nodelist_path, const char *edgelist_path, int32_t *n_samples_out, char *files_out,
+                         int32_t files_cap, int32_t *n_pairs_out, double *pairs_out, int32_t pairs_cap)
+{
+    if (!nodelist_path || !edgelist_path) return ABFIT_ERR_ARG;
+    PedGraph g;
+    if (int rc = build_graph(nodelist_path, edgelist_path, g)) return rc;
+    if (n_samples_out) *n_samples_out = (int32_t)g.meas.size();
+    if (n_pairs_out) *n_pairs_out = (int32_t)g.pairs.size();
+    if (files_out) {
+        std::string all;
+        for (auto &n : g.meas) all += n.file + "\n";
+        if ((int32_t)all.size() + 1 > files_cap) return ABFIT_ERR_ARG;
+        std::memcpy(files_out, all.c_str(), all.size() + 1);
+    }
+    if (pairs_out) {
+        if ((int32_t)g.pairs.size() > pairs_cap) return ABFIT_ERR_ARG;
+        for (size_t r = 0; r < g.pairs.size(); ++r) {
+            pairs_out[5 * r + 0] = g.pairs[r].i;
+            pairs_out[5 * r + 1] = g.pairs[r].j;
+            pairs_out[5 * r + 2] = g.pairs[r].t0;
+            pairs_out[5 * r + 3] = g.pairs[r].t1;
+            pairs_out[5 * r + 4] = g.pairs[r].t2;
+        }
+    }
+    return 0;
+}
+
+// Gene::from_annotation_file_line (src/genes.rs:166-216): `chr start end name annotation strand` or
+// `chr start end width strand name`, separated by blanks or tabs.  0 = parsed, 1 = not a gene line.
+int abfit_parse_annotation_line(const char *line, int32_t invert_strand, abfit_gene *gene_out)
+{
+    if (!line || !gene_out) return ABFIT_ERR_ARG;
+    const std::vector<std::string> f = split_any(line, " \t");
+    if (f.size() != 6) return 1;
+    auto strand_of = [](const std::string &s) { return s == "+" ? 1 : s == "-" ? -1 : s == "*" ? 0 : 2; };
+    int sd = strand_of(f[5]);
+    if (sd == 2) sd = strand_of(f[4]);
+    if (sd == 2) return 1;
+    if (!parse_chromosome(f[0], gene_out->chromosome) || !parse_u32(f[1], gene_out->start) || !parse_u32(f[2], gene_out->end))
+        return 1;
+    gene_out->strand = invert_strand ? -sd : sd;
     return 0;
 }
 

@@ -280,6 +280,12 @@ int abfit_pedigree_build(abfit_ctx *ctx, const char *nodelist_path, const char *
                          abfit_pedigree **out);
 int abfit_pedigree_info(const abfit_pedigree *p, int32_t *n_pairs, double *p0uu, int32_t *n_samples, int64_t *n_sites);
 const double *abfit_pedigree_rows(const abfit_pedigree *p); /* [n_pairs][4] */
+/* The graph part alone (metaprofile: same nodes and edges for every window, only D changes): the measured nodes' file
+ * names ('\n'-separated, nodelist order) and per pedigree row (i, j, t0, t1, t2), i < j sample indices. */
+int abfit_pedigree_graph(const char *nodelist_path, const char *edgelist_path, int32_t *n_samples_out, char *files_out,
+                         int32_t files_cap, int32_t *n_pairs_out, double *pairs_out /*[n_pairs][5]*/, int32_t pairs_cap);
+/* Gene::from_annotation_file_line (src/genes.rs:166-216): 0 = parsed, 1 = not a gene line */
+int abfit_parse_annotation_line(const char *line, int32_t invert_strand, abfit_gene *gene_out);
 const char *abfit_pedigree_warnings(const abfit_pedigree *p);
 void abfit_pedigree_free(abfit_pedigree *p);
 

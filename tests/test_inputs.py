@@ -106,3 +106,93 @@ def test_alphabeta_cli_end_to_end(ab, ctx, oracle, tmp_path):
         "Estimated steady state %s\nObserved steady state methylation %s\n##########\n" % (
             oracle.rust_f64(oracle.steady_state(best["theta"][0], best["theta"][1])), oracle.rust_f64(1.0 - p0uu))
     assert want_block in r.stdout
+
+
+def test_metaprofile_extraction_files_match_the_reference_output(tmp_path):
+    """C3 on the shipped data: `metaprofile -m data/methylome -g data/annotation.bed -w 5` -> data/output_metaplot/*
+    (no GPU involved: binning, distributions and steady-state files are host work)"""
+    exe = os.path.join(ROOT, "alphabeta-rs_b200", "metaprofile")
+    r = subprocess.run([exe, "-m", os.path.join(GOLDEN, "methylome"), "-g", os.path.join(GOLDEN, "annotation.bed"), "-w", "5",
+                        "-o", str(tmp_path), "--name", "t"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "Done" in r.stdout, r.stdout + r.stderr
+    gold = os.path.join(GOLDEN, "output_metaplot")
+    for f in ("distribution_G0.txt", "steady_state_methylation.txt"):
+        assert open(os.path.join(tmp_path, f), "rb").read() == open(os.path.join(gold, f), "rb").read(), f
+    # distributions.txt lists the files in directory order in the reference, in name order here
+    assert sorted(open(os.path.join(tmp_path, "distributions.txt")).read().split("\n")) == \
+        sorted(open(os.path.join(gold, "distributions.txt")).read().split("\n"))
+
+
+@pytest.mark.gpu
+def test_metaprofile_cli_fused_pipeline(ab, ctx, oracle, tmp_path):
+    """`metaprofile ... alphabeta` on the example methylomes with an annotation that covers them: results.txt and raw.npy
+    equal the reference's per-window loop restated with the oracle (same seeds)"""
+    ann = os.path.join(tmp_path, "ann.bed")
+    genes = [(1, 300, 700, "-"), (1, 250, 800, "+"), (2, 1200, 1600, "+"), (2, 1250, 1650, "-"), (3, 600, 900, "*"),
+             (4, 1200, 1550, "-"), (4, 1150, 1600, "+"), (5, 300, 900, "*"), ("C", 200, 900, "+"), ("C", 150, 950, "-"),
+             ("M", 200, 600, "-"), ("M", 150, 650, "+")]
+    open(ann, "w").write("".join(f"{c}\t{s}\t{e}\tg{i}\tgbM\t{sd}\n" for i, (c, s, e, sd) in enumerate(genes)))
+    out = os.path.join(tmp_path, "out")
+    os.makedirs(out)
+    exe = os.path.join(ROOT, "alphabeta-rs_b200", "metaprofile")
+    n_it, seed = 60, 777
+    r = subprocess.run([exe, "-m", os.path.join(GOLDEN, "methylome"), "-g", ann, "-w", "10", "-s", "5", "-c", "200", "-o", out,
+                        "--name", "run7", "--iterations", str(n_it), "--seed", str(seed), "alphabeta",
+                        "--nodes", os.path.join(GOLDEN, "nodelist.txt"), "--edges", os.path.join(GOLDEN, "edgelist.txt")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # ---- the reference's flow, restated: per window, pedigree from that window's sites, fit, bootstrap -------------
+    ped6, _, info = oracle.build_pedigree(os.path.join(GOLDEN, "nodelist.txt"), os.path.join(GOLDEN, "edgelist.txt"), 0.99, resolve_golden)
+    og = [(oracle.chromosome_id(str(c)), s, e, STRAND[sd]) for c, s, e, sd in genes]
+    # every sample's file is binned on its own (Windows::extract per file); the files list the same CG positions in
+    # different orders, so a window holds different rows of each file
+    per_sample = []
+    for node in info["nodes"]:
+        path = resolve_golden(node["file"])
+        sites, st, po, me = [], [], [], []
+        for line in open(path).read().split("\n")[1:]:
+            q = oracle.parse_methylome_line(line)
+            if q is not None:
+                sites.append((oracle.chromosome_id(str(q["chromosome"])), q["start"], q["end"], STRAND[q["strand"]]))
+                st.append(q["status"]); po.append(q["posteriormax"]); me.append(q["meth_lvl"])
+        d, assign = oracle.extract_windows(og, sites, window_size=10, window_step=5, cutoff=200)
+        per_sample.append((d, assign, np.array(st, dtype=np.uint8), np.array(po), np.array(me)))
+    dist = per_sample[0][0]  # G0.txt: first node and first file in name order
+    flags = oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL
+    results, raws = [], []
+    f = 0
+    for w in range(len(dist)):
+        cols = [[si for si, ww in ps[1] if ww == w] for ps in per_sample]
+        if not cols[0] or len({len(c) for c in cols}) != 1:
+            continue
+        status = np.stack([ps[2][c] for ps, c in zip(per_sample, cols)])
+        post = np.stack([ps[3][c] for ps, c in zip(per_sample, cols)])
+        meth = np.stack([ps[4][c] for ps, c in zip(per_sample, cols)])
+        D, _, _ = oracle.dmatrix(status, post, 0.99)
+        p0 = oracle.p0uu(post, meth, 0.99)[0]
+        if np.isnan(D).any() or np.isnan(p0):
+            continue
+        ped = ped6.copy()
+        ped[:, 3] = D
+        pb = oracle.Problem(ped, p0, p0, 1.0)
+        sx = ab.gen_start_simplices(seed, w, n_it, float(D.max()))
+        rc, best, _, pred, resid = oracle.ab_neutral(pb, sx, flags=flags, n_threads=8)
+        assert rc == 0
+        idx = ab.gen_resample_idx(seed, w, n_it, len(ped))
+        vary = ab.gen_vary_vertices(seed, f, n_it, best["theta"])  # keyed by the position in the batch
+        rc2, rows, _ = oracle.boot_model(pb, best["theta"], pred, resid, idx, vary, flags=flags, n_threads=8)
+        assert rc2 == 0
+        region = 0 if w < 20 else 1 if w < 40 else 2
+        results.append((region, best["theta"].copy(), oracle.analyze(rows), 1.0 - p0))
+        raws.append(rows)
+        f += 1
+    assert len(results) >= 20
+    want = oracle.metaprofile_results_text("run7", dist[:len(results)], [r_[0] for r_ in results], [r_[1] for r_ in results],
+                                           [r_[2] for r_ in results], [r_[3] for r_ in results])
+    if os.environ.get("ABFIT_TEST_DUMP"):
+        open(os.path.join(os.environ["ABFIT_TEST_DUMP"], "mp_want.txt"), "w").write(want)
+        open(os.path.join(os.environ["ABFIT_TEST_DUMP"], "mp_got.txt"), "w").write(open(os.path.join(out, "results.txt")).read())
+        open(os.path.join(os.environ["ABFIT_TEST_DUMP"], "mp_stdout.txt"), "w").write(r.stdout)
+    assert open(os.path.join(out, "results.txt")).read() == want
+    raw = np.load(os.path.join(out, "raw.npy"))
+    assert raw.shape == (n_it, 7, len(results)) and np.array_equal(raw, np.stack(raws, axis=2))
