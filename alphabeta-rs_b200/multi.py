@@ -77,3 +77,30 @@ def combine_site_shards(diff: Sequence[np.ndarray], cnt: Sequence[np.ndarray], m
     for s in range(S):  # src/pedigree.rs:179-183: sequential sum over samples, then / S
         p0uu = p0uu + (1.0 - rc[..., s])
     return D, p0uu / float(S), d, c
+
+
+def start_shard(n_starts: int, rank: int, world: int) -> Tuple[int, int]:
+    """contiguous block of START ids for `rank` — the sharding of one huge problem (the C5 fit is
+    1 window x 1000 starts).  The seeded start generator is keyed by the global start id, so rank r fits
+    simplices[first : first + count] of the same array a single process would use."""
+    return window_shard(n_starts, rank, world)
+
+
+def best_of_shards(cands: np.ndarray, first_start: Sequence[int]) -> Tuple[int, np.ndarray]:
+    """Final argmin over the per-rank winners of a start-sharded fit (one `abfit_fit` record per rank, in rank
+    order; `first_start[r]` = first global start id of rank r).  Same rule as one process: smallest penalty-free
+    LSE wins and the lowest start id breaks ties (stable sort, src/ab_neutral.rs:83-101); a NaN LSE is the
+    reference's panic (`partial_cmp().unwrap()`, :100).  Returns (winning rank, its record with the GLOBAL start id)."""
+    cands = np.asarray(cands)
+    if len(cands) == 0 or len(cands) != len(first_start):
+        raise ValueError("one candidate and one first_start per rank")
+    if np.isnan(cands["lse"]).any() or (cands["status"] < 0).any():
+        raise FloatingPointError("a shard returned a failed fit / NaN LSE (the reference panics here)")
+    gid = cands["start_id"].astype(np.int64) + np.asarray(first_start, dtype=np.int64)
+    win = 0
+    for r in range(1, len(cands)):
+        if cands["lse"][r] < cands["lse"][win] or (cands["lse"][r] == cands["lse"][win] and gid[r] < gid[win]):
+            win = r
+    rec = cands[win].copy()
+    rec["start_id"] = gid[win]
+    return win, rec

@@ -65,7 +65,22 @@ def _worker(rank, world, port, out_dir):
         methsum = np.array([meth[s, f0:f0 + n][valid[s]].sum() for s in range(S)])
         nvalid = valid.sum(axis=1).astype(np.int64)
         parts = [multi.gather_to_root(np.asarray(x)[None]) for x in (diff, cnt, methsum, nvalid)]
+        # ---- ONE problem, its starts sharded over ranks (the C5 fit) -----------------------------
+        n_big = 9
+        sx_all = ab.gen_start_simplices(seed, 77, n_big, float(peds[0][:, 3].max()))
+        s0, sc = multi.start_shard(n_big, rank, world)
+        rc, best, _, pred, resid = o.ab_neutral(o.Problem(peds[0], 0.7, 0.7, 1.0), sx_all[s0:s0 + sc],
+                                                flags=o.FAST_DIVERGENCE | o.EARLY_EXIT_ON_STALL)
+        assert rc == 0
+        mine = np.zeros(1, dtype=ab.FIT_DTYPE)
+        for f in ("theta", "cost", "lse", "iters", "evals", "status", "start_id"):
+            mine[0][f] = best[f]
+        cands = multi.gather_to_root(mine)
+        firsts = multi.gather_to_root(np.array([s0], dtype=np.int64))
+        preds = multi.gather_to_root(np.asarray(pred)[None])
         if rank == 0:
+            win, rec = multi.best_of_shards(cands, firsts)
+            np.savez(os.path.join(out_dir, "bigfit.npz"), rec=rec, pred=preds[win], win=win)
             np.save(os.path.join(out_dir, "fits.npy"), allw)
             D, p0uu, d, c = multi.combine_site_shards(*parts)
             np.savez(os.path.join(out_dir, "div.npz"), D=D, p0uu=p0uu, d=d, c=c)
@@ -91,6 +106,23 @@ def test_window_and_site_shards_cover_everything_once():
             assert sum(c for _, c in spans) == L and all(f % 64 == 0 or c == 0 for f, c in spans)
 
 
+def test_best_of_shards_rule(ab):
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("abfit_multi", os.path.join(ROOT, "alphabeta-rs_b200", "multi.py"))
+    multi = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(multi)
+    c = np.zeros(3, dtype=ab.FIT_DTYPE)
+    c["lse"] = [2.0, 1.0, 1.0]
+    c["start_id"] = [0, 5, 1]
+    win, rec = multi.best_of_shards(c, [0, 10, 3])  # global ids 0, 15, 4: the tie goes to id 4
+    assert win == 2 and int(rec["start_id"]) == 4
+    assert [multi.start_shard(1000, r, 8) for r in (0, 7)] == [(0, 125), (875, 125)]
+    c["lse"][0] = np.nan
+    with pytest.raises(FloatingPointError):
+        multi.best_of_shards(c, [0, 10, 3])
+
+
 @pytest.mark.timeout(300)
 def test_two_gloo_ranks_equal_one_process(tmp_path, oracle, ab):
     import torch.multiprocessing as mp
@@ -109,6 +141,13 @@ def test_two_gloo_ranks_equal_one_process(tmp_path, oracle, ab):
         rc, best, _, _, _ = oracle.ab_neutral(oracle.Problem(peds[w], 0.7, 0.7, 1.0), sx,
                                               flags=oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL)
         assert np.array_equal(got[w]["theta"], best["theta"]) and got[w]["start_id"] == best["start_id"]
+    # one problem, starts sharded: same winner (global start id), same prediction as one process
+    sx_all = ab.gen_start_simplices(seed, 77, 9, float(peds[0][:, 3].max()))
+    rc, best, _, pred, _ = oracle.ab_neutral(oracle.Problem(peds[0], 0.7, 0.7, 1.0), sx_all,
+                                             flags=oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL)
+    z = np.load(os.path.join(tmp_path, "bigfit.npz"))
+    assert int(z["rec"]["start_id"]) == int(best["start_id"]) and np.array_equal(z["rec"]["theta"], best["theta"])
+    assert z["rec"]["lse"] == best["lse"] and np.array_equal(z["pred"], pred)
     S, L = 4, 1000
     rs = np.random.default_rng(5)
     status = rs.integers(0, 3, (S, L)).astype(np.uint8)
