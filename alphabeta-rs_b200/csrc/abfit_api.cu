@@ -76,6 +76,7 @@ struct abfit_batch {
     DevBuf<double> d_D;
     DevBuf<uint32_t> d_offs;
     DevBuf<OpWord> d_ops;
+    DevBuf<uint32_t> d_wtrip, d_wtid;
     DevicePools pools{};
     // fit
     int n_starts = 0;
@@ -342,14 +343,18 @@ static int batch_load(abfit_batch *b, const abfit_problem *probs, int32_t n_prob
     if (int rc = b->d_D.ensure(hp.D.size())) return rc;
     if (int rc = b->d_offs.ensure(hp.offs.size())) return rc;
     if (int rc = b->d_ops.ensure(hp.ops.size())) return rc;
+    if (int rc = b->d_wtrip.ensure(hp.wtrip.size())) return rc;
+    if (int rc = b->d_wtid.ensure(hp.wtid.size())) return rc;
     cudaStream_t st = ctx->stream;
     ABFIT_CUDA(cudaMemcpyAsync(b->d_probs.p, hp.probs.data(), hp.probs.size() * sizeof(DevProblem), cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaMemcpyAsync(b->d_D.p, hp.D.data(), hp.D.size() * 8, cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaMemcpyAsync(b->d_offs.p, hp.offs.data(), hp.offs.size() * 4, cudaMemcpyHostToDevice, st));
     if (!hp.ops.empty())
         ABFIT_CUDA(cudaMemcpyAsync(b->d_ops.p, hp.ops.data(), hp.ops.size() * sizeof(OpWord), cudaMemcpyHostToDevice, st));
+    ABFIT_CUDA(cudaMemcpyAsync(b->d_wtrip.p, hp.wtrip.data(), hp.wtrip.size() * 4, cudaMemcpyHostToDevice, st));
+    ABFIT_CUDA(cudaMemcpyAsync(b->d_wtid.p, hp.wtid.data(), hp.wtid.size() * 4, cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaStreamSynchronize(st));  // hp vectors are pageable: make the copies complete here
-    b->pools = DevicePools{b->d_probs.p, b->d_D.p, b->d_offs.p, b->d_ops.p};
+    b->pools = DevicePools{b->d_probs.p, b->d_D.p, b->d_offs.p, b->d_ops.p, b->d_wtrip.p, b->d_wtid.p};
     if (!b->ev[0])
         for (auto &e : b->ev) ABFIT_CUDA(cudaEventCreate(&e));
     if (int rc = b->d_evals_fit.ensure(n_probs)) return rc;
@@ -410,7 +415,8 @@ int abfit_batch_upload_starts(abfit_batch *b, int32_t n_starts, const double *si
                                          (size_t)b->ctx->prop.sharedMemPerMultiprocessor, n_starts, b->shape))
             return rc;
         std::vector<WorkItem> items =
-            make_items(b->hp, n_starts, b->ctx->prop.multiProcessorCount, b->shape.n_warps, true);
+            b->shape.wide ? make_items_wide(b->hp, n_starts, b->ctx->prop.multiProcessorCount, true)
+                          : make_items(b->hp, n_starts, b->ctx->prop.multiProcessorCount, b->shape.n_warps, true);
         b->n_items = (int)items.size();
         if (int rc = b->d_items.ensure(items.size())) return rc;
         if (!items.empty())
@@ -444,9 +450,13 @@ int abfit_batch_run_fit(abfit_batch *b, int32_t max_iters, double sd_tol, uint32
     ABFIT_CUDA(cudaEventRecord(b->ev[0], st));
     BigScratch big;
     if (int rc = big_scratch(b, (size_t)std::max(std::max(b->n_items, 1) * b->shape.n_warps, b->n_probs), big)) return rc;
-    if (int rc = launch_fit_starts(st, b->pools, b->d_items.p, b->n_items, b->shape.n_warps, b->d_simplices.p,
-                                   b->n_starts, nm, b->d_all.p, b->d_evals_fit.p, b->shape.smem_fit,
-                                   b->shape.d_shared, b->shape.x_global ? b->d_xscratch.p : nullptr, big))
+    if (b->shape.wide) {
+        if (int rc = launch_fit_starts_wide(st, b->pools, b->d_items.p, b->n_items, b->d_simplices.p, b->n_starts, nm,
+                                            b->d_all.p, b->d_evals_fit.p, b->shape.smem_wide))
+            return rc;
+    } else if (int rc = launch_fit_starts(st, b->pools, b->d_items.p, b->n_items, b->shape.n_warps, b->d_simplices.p,
+                                          b->n_starts, nm, b->d_all.p, b->d_evals_fit.p, b->shape.smem_fit,
+                                          b->shape.d_shared, b->shape.x_global ? b->d_xscratch.p : nullptr, big))
         return rc;
     ABFIT_CUDA(cudaEventRecord(b->ev[1], st));
     if (int rc = launch_select(st, b->pools, b->n_probs, b->n_starts, b->d_all.p, b->d_best.p, b->d_pred.p,
@@ -493,7 +503,9 @@ static int boot_alloc(abfit_batch *b, int32_t n_boot)
     if (int rc = b->d_vary.ensure(n_vary)) return rc;
     if (n_boot != b->n_boot) {
         b->n_boot = n_boot;
-        std::vector<WorkItem> items = make_items(b->hp, n_boot, b->ctx->prop.multiProcessorCount, 1, true);
+        std::vector<WorkItem> items = b->shape.wide
+                                          ? make_items_wide(b->hp, n_boot, b->ctx->prop.multiProcessorCount, true)
+                                          : make_items(b->hp, n_boot, b->ctx->prop.multiProcessorCount, 1, true);
         b->n_boot_items = (int)items.size();
         if (int rc = b->d_boot_items.ensure(items.size())) return rc;
         if (!items.empty())
@@ -502,7 +514,9 @@ static int boot_alloc(abfit_batch *b, int32_t n_boot)
         ABFIT_CUDA(cudaStreamSynchronize(st));
         // stored-D* tile: N x 32 doubles per block; index tile: ceil(N/4) x 32 x 8 bytes (+ one tile of slack for
         // the L1 prefetch that runs 4 groups ahead)
-        const size_t per_block = b->shape.smem_boot_gather ? (size_t)((b->hp.max_pairs + 3) / 4) * 32 : (size_t)b->hp.max_pairs * 32;
+        const size_t per_block = b->shape.wide ? (size_t)((b->hp.max_pairs + 1) & ~1)  // one D* row per warp
+                                 : b->shape.smem_boot_gather ? (size_t)((b->hp.max_pairs + 3) / 4) * 32
+                                                             : (size_t)b->hp.max_pairs * 32;
         if (int rc = b->d_scratch.ensure((size_t)(std::max(b->n_boot_items, 1) + 1) * per_block)) return rc;
         if (int rc = b->d_rows.ensure((size_t)b->n_probs * n_boot * 7)) return rc;
         if (int rc = b->d_bootfits.ensure((size_t)b->n_probs * n_boot)) return rc;
@@ -555,7 +569,13 @@ int abfit_batch_run_boot(abfit_batch *b, int32_t max_iters, double sd_tol, uint3
     ABFIT_CUDA(cudaEventRecord(b->ev[3], st));
     if (int rc = b->d_booterr.ensure(1)) return rc;
     ABFIT_CUDA(cudaMemsetAsync(b->d_booterr.p, 0, sizeof(int), st));
-    if (b->shape.smem_boot_gather) {
+    if (b->shape.wide) {
+        if (int rc = launch_fit_boot_wide(st, b->pools, b->d_boot_items.p, b->n_boot_items, b->n_boot, b->d_best.p,
+                                          b->d_pred.p, b->d_resid.p, b->d_idx.p, b->d_vary.p, b->d_scratch.p,
+                                          (int64_t)((b->hp.max_pairs + 1) & ~1), nm, b->d_rows.p, b->d_bootfits.p,
+                                          b->d_evals_boot.p, b->shape.smem_wide, b->d_booterr.p))
+            return rc;
+    } else if (b->shape.smem_boot_gather) {
         if (int rc = launch_fit_boot_gather(st, b->pools, b->d_boot_items.p, b->n_boot_items, b->n_boot, b->d_best.p,
                                             b->d_pred.p, b->d_resid.p, b->d_idx.p, b->d_vary.p, b->d_scratch.p,
                                             (int64_t)((b->hp.max_pairs + 3) / 4) * 32, nm, b->d_rows.p, b->d_bootfits.p,

@@ -24,6 +24,8 @@ struct DevicePools {  // device pointers of a compiled batch
     const double *D;
     const uint32_t *offs;
     const OpWord *ops;
+    const uint32_t *wtrip;
+    const uint32_t *wtid;
 };
 
 // dynamic shared memory of one block working on problem pb (matches carve_and_stage)
@@ -65,6 +67,15 @@ int launch_fit_boot_gather(cudaStream_t st, const DevicePools &P, const WorkItem
                            const double *vary, void *idx_scratch, int64_t scratch_stride, NMParams nm,
                            double *rows_out, abfit_fit *fits_out, unsigned long long *evals_per_prob, size_t smem_bytes,
                            int *err_flag);
+// warp-per-fit variants (abfit_wide.cuh): one warp per block; dstar_scratch holds scratch_stride doubles per block
+int launch_fit_starts_wide(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items,
+                           const double *simplices, int n_starts, NMParams nm, abfit_fit *all_out,
+                           unsigned long long *evals_per_prob, size_t smem_bytes);
+int launch_fit_boot_wide(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_boot,
+                         const abfit_fit *best, const double *pred, const double *resid, const int32_t *resample_idx,
+                         const double *vary, double *dstar_scratch, int64_t scratch_stride, NMParams nm,
+                         double *rows_out, abfit_fit *fits_out, unsigned long long *evals_per_prob, size_t smem_bytes,
+                         int *err_flag);
 int launch_cost_batch(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items,
                       const double *theta, double *cost_out, double *lse_out, size_t smem_bytes, bool d_in_shared,
                       const BigScratch &big);

@@ -19,6 +19,7 @@
 #include <cstdlib>
 
 #include "abfit_internal.h"
+#include "abfit_wide.cuh"
 
 namespace abfit {
 
@@ -634,6 +635,111 @@ k_fit_boot_gather(DevicePools P, const WorkItem *__restrict__ items, int n_boot,
 }
 
 // ---------------------------------------------------------------------------------
+// warp-per-fit Nelder-Mead (abfit_wide.cuh) for pedigrees with thousands of pairs: one block = one
+// warp = one fit at a time.  Every lane carries the same Nelder-Mead state (the state machine of
+// abfit_nm.cuh run redundantly, so the control flow is warp-uniform by construction) and the
+// 32 lanes share the work of each objective evaluation.  BOOT: bootstrap replicates
+// (src/boot_model.rs:41-100) — the warp first materialises D*_i = pred_i + resid[idx_i] as a row of
+// the scratch area, then fits it like an observed column.
+// ---------------------------------------------------------------------------------
+struct WideBoot {
+    const abfit_fit *best;
+    const double *pred, *resid;
+    const int32_t *resample_idx;
+    const double *vary;
+    double *dstar;  // [block][stride]
+    long long stride;
+    double *rows_out;
+    int *err_flag;
+};
+
+template <bool BOOT>
+__global__ void __launch_bounds__(32)
+k_fit_wide(DevicePools P, const WorkItem *__restrict__ items, const double *__restrict__ simplices, int n_per_prob,
+           NMParams nm, abfit_fit *__restrict__ fits_out, unsigned long long *__restrict__ evals_per_prob, WideBoot B)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x;
+    const WorkItem it = items[blockIdx.x];
+    const DevProblem pb = P.probs[it.prob];
+    WideCtx c;
+    double *after = wide_carve(c, smem, pb.tmax, pb.n_trip);
+    LaneSimplex S;
+    S.X = after + lane;
+    S.C = S.X + 20 * 32;
+    uint32_t *trip = reinterpret_cast<uint32_t *>(after + 25 * 32);
+    for (int i = lane; i < pb.n_trip; i += 32) trip[i] = P.wtrip[pb.wtrip_off + i];
+    c.trip = trip;
+    c.tid = P.wtid + pb.wtid_off;
+    c.D = P.D + pb.d_off;
+    c.n_pairs = pb.n_pairs;
+    c.n_trip = pb.n_trip;
+    c.tmax = pb.tmax;
+    c.p_uu0 = pb.p_uu0;
+    c.p_mm0 = pb.p_mm0;
+    c.eqp = pb.eqp;
+    c.penw = pb.penw;
+    __syncwarp();
+    double *drow = BOOT ? B.dstar + (size_t)blockIdx.x * (size_t)B.stride : nullptr;
+    unsigned long long my_evals = 0;
+
+    for (int f = it.first; f < it.first + it.count; ++f) {
+        if (BOOT) {
+            const int32_t *ib = B.resample_idx + (size_t)pb.pair_off * n_per_prob + (size_t)f * pb.n_pairs;
+            const double *predp = B.pred + pb.pair_off, *residp = B.resid + pb.pair_off;
+            for (int i = lane; i < pb.n_pairs; i += 32) {
+                uint32_t ix = (uint32_t)ib[i];
+                if (ix >= (uint32_t)pb.n_pairs) {  // reported by download_boot; keeps the gather in bounds
+                    ix = 0u;
+                    *B.err_flag = 1;
+                }
+                drow[i] = predp[i] + residp[ix];  // src/boot_model.rs:50-57
+            }
+            c.D = drow;
+            // simplex = [best, vary x 4]  (src/boot_model.rs:69-75)
+            const abfit_fit bm = B.best[it.prob];
+            const double *vv = B.vary + ((size_t)it.prob * n_per_prob + f) * 16;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) S.X[q * 32] = bm.theta[q];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) S.X[(4 + q) * 32] = vv[q];
+        } else {
+            const double *sx = simplices + ((size_t)it.prob * n_per_prob + f) * 20;
+#pragma unroll
+            for (int q = 0; q < 20; ++q) S.X[q * 32] = sx[q];
+        }
+        __syncwarp();
+        LaneNM L;
+        lane_nm_reset(L);
+        nm_begin(L, S, f);
+        for (;;) {
+            const double v = objective_wide(c, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
+            abfit_fit res;
+            if (nm_advance(L, S, nm, v, res, FULL)) {
+                if (lane == 0) {
+                    my_evals += (unsigned long long)res.evals;
+                    const size_t o = (size_t)it.prob * n_per_prob + res.start_id;
+                    if (BOOT) {
+                        double *row = B.rows_out + o * 7;  // src/boot_model.rs:86-91
+                        row[0] = res.theta[0];
+                        row[1] = res.theta[1];
+                        row[2] = res.theta[2];
+                        row[3] = res.theta[3];
+                        row[4] = p_mm_est(res.theta[0], res.theta[1]);
+                        row[5] = p_um_est(res.theta[0], res.theta[1]);
+                        row[6] = p_uu_est(res.theta[0], res.theta[1]);
+                    }
+                    if (fits_out) store_fit(fits_out + o, res);
+                }
+                break;
+            }
+        }
+        __syncwarp();  // every lane is done with this replicate's D* row and simplex
+    }
+    if (lane == 0 && evals_per_prob && my_evals) atomicAdd(evals_per_prob + it.prob, my_evals);
+}
+
+// ---------------------------------------------------------------------------------
 // objective only (test hook / CostFunction seam)
 // ---------------------------------------------------------------------------------
 template <bool D_SHARED, bool BIG>
@@ -701,13 +807,15 @@ int max_dynamic_smem(int device)
 }
 
 template <class K>
-static int prep_kernel(K kernel, size_t smem_bytes)
+static int prep_kernel(K kernel, size_t smem_bytes, bool max_shared = true)
 {
     if (smem_bytes > 48 * 1024)
         ABFIT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    // prefer the largest shared-memory carve-out: these kernels keep all per-lane state in shared
-    ABFIT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    cudaSharedmemCarveoutMaxShared));
+    // prefer the largest shared-memory carve-out: these kernels keep all per-lane state in shared (the
+    // warp-per-fit kernels stream D and the triple ids through L1 instead and leave the split to the driver)
+    if (max_shared)
+        ABFIT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
     return 0;
 }
 
@@ -801,6 +909,36 @@ int launch_fit_boot_gather(cudaStream_t st, const DevicePools &P, const WorkItem
     k_fit_boot_gather<<<n_items, 32, smem_bytes, st>>>(P, items, n_boot, best, pred, resid, resample_idx, vary,
                                                        static_cast<uint2 *>(idx_scratch), (long long)scratch_stride, nm,
                                                        rows_out, fits_out, evals_per_prob, err_flag);
+    ABFIT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_fit_starts_wide(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items,
+                           const double *simplices, int n_starts, NMParams nm, abfit_fit *all_out,
+                           unsigned long long *evals_per_prob, size_t smem_bytes)
+{
+    if (n_items <= 0) return 0;
+    if (int rc = prep_kernel(k_fit_wide<false>, smem_bytes, false)) return rc;
+    if (getenv("ABFIT_DEV_VERBOSE"))
+        fprintf(stderr, "[abfit] k_fit_wide<starts>: %d blocks x 1 warp, %zu B smem/block\n", n_items, smem_bytes);
+    k_fit_wide<false><<<n_items, 32, smem_bytes, st>>>(P, items, simplices, n_starts, nm, all_out, evals_per_prob,
+                                                       WideBoot{});
+    ABFIT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_fit_boot_wide(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_boot,
+                         const abfit_fit *best, const double *pred, const double *resid, const int32_t *resample_idx,
+                         const double *vary, double *dstar_scratch, int64_t scratch_stride, NMParams nm,
+                         double *rows_out, abfit_fit *fits_out, unsigned long long *evals_per_prob, size_t smem_bytes,
+                         int *err_flag)
+{
+    if (n_items <= 0) return 0;
+    if (int rc = prep_kernel(k_fit_wide<true>, smem_bytes, false)) return rc;
+    if (getenv("ABFIT_DEV_VERBOSE"))
+        fprintf(stderr, "[abfit] k_fit_wide<boot>: %d blocks x 1 warp, %zu B smem/block\n", n_items, smem_bytes);
+    WideBoot B{best, pred, resid, resample_idx, vary, dstar_scratch, (long long)scratch_stride, rows_out, err_flag};
+    k_fit_wide<true><<<n_items, 32, smem_bytes, st>>>(P, items, nullptr, n_boot, nm, fits_out, evals_per_prob, B);
     ABFIT_CUDA(cudaGetLastError());
     return 0;
 }

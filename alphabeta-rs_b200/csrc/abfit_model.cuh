@@ -77,7 +77,9 @@ struct DevProblem {
     int32_t n_ops;
     int32_t n_lane;   // doubles of per-lane model storage
     int32_t tmax;     // last exponent the chain has to reach
-    int32_t pad_;
+    int32_t n_trip;   // distinct (t0,t1,t2) triples
+    int64_t wtrip_off;  // into the triple pool (u32 per triple: t0 | (t1-t0) << 8 | (t2-t0) << 16), see abfit_wide.cuh
+    int64_t wtid_off;   // into the per-pair triple-id pool
     double p_uu0, p_mm0;  // state at G0 (p0um = 0), src/ab_neutral.rs:23-24
     double eqp, penw;     // penw = eqp_weight * (double)n_pairs, src/structs.rs:210-211
 };

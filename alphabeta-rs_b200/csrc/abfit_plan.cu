@@ -7,6 +7,7 @@
 #include <tuple>
 
 #include "abfit_plan.h"
+#include "abfit_wide.cuh"
 
 namespace abfit {
 
@@ -36,6 +37,11 @@ size_t smem_need(const DevProblem &pb, int simplex_doubles, bool d_shared, int n
     b += (size_t)pb.n_ops * 8;
     b += 16;
     return (b + 15) & ~(size_t)15;
+}
+
+size_t smem_need_wide(const DevProblem &pb)
+{
+    return ((size_t)wide_warp_doubles(pb.tmax, pb.n_trip) * 8 + (size_t)pb.n_trip * 4 + 15) & ~(size_t)15;
 }
 
 size_t smem_need_boot_gather(const DevProblem &pb)
@@ -74,6 +80,8 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
         hp.total_pairs += ap.n_pairs;
         dp.offs_off = (int64_t)hp.offs.size();
         dp.ops_off = (int64_t)hp.ops.size();
+        dp.wtrip_off = (int64_t)hp.wtrip.size();
+        dp.wtid_off = (int64_t)hp.wtid.size();
         dp.n_pairs = ap.n_pairs;
         dp.p_uu0 = ap.p0uu;
         dp.p_mm0 = 1.0 - ap.p0uu;               // src/ab_neutral.rs:23
@@ -111,7 +119,9 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
             dp.n_ops = q.n_ops;
             dp.n_lane = q.n_lane;
             dp.tmax = q.tmax;
-            dp.pad_ = 0;
+            dp.n_trip = q.n_trip;
+            dp.wtrip_off = q.wtrip_off;
+            dp.wtid_off = q.wtid_off;
             hp.probs[p] = dp;
             hp.tmax[p] = hp.tmax[prev_p];
             hp.n_triples[p] = hp.n_triples[prev_p];
@@ -226,9 +236,13 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
         }
         hp.ops.push_back(mk_op(OP_NOP));  // end sentinel: the interpreter prefetches one word ahead
         dp.n_ops = (int32_t)(hp.ops.size() - (size_t)dp.ops_off);
-        dp.pad_ = 0;
         dp.n_lane = (int32_t)n_lane;
         dp.tmax = tmax;
+        dp.n_trip = U;
+        for (auto &kv : tri_id)  // map order == id order
+            hp.wtrip.push_back((uint32_t)std::get<0>(kv.first) | ((uint32_t)std::get<1>(kv.first) << 8) |
+                               ((uint32_t)std::get<2>(kv.first) << 16));
+        for (int i = 0; i < ap.n_pairs; ++i) hp.wtid.push_back((uint32_t)tri_id[key[i]]);
 
         for (int i = 0; i < ap.n_pairs; ++i) hp.offs.push_back(256u * (dt_base + (uint32_t)tri_id[key[i]]));
         while (hp.offs.size() & 3) hp.offs.push_back(256u * dt_base);
@@ -310,6 +324,17 @@ int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm,
     out.d_shared_aux = worst(0, true, 1) <= smem_cap / 2;
     out.smem_aux = worst(0, out.d_shared_aux, 1);
     out.big = best_w <= 0 || out.smem_boot > smem_cap || out.smem_aux > smem_cap || getenv("ABFIT_DEV_BIG");
+    out.wide = false;
+    out.smem_wide = 0;
+    {
+        size_t m = 0;
+        for (auto &pb : hp.probs) m = std::max(m, smem_need_wide(pb));
+        const char *fw = getenv("ABFIT_DEV_WIDE");  // tests: force the warp-per-fit kernels on (1) or off (0)
+        if (m <= smem_cap && (fw ? atoi(fw) != 0 : out.big)) {
+            out.wide = true;
+            out.smem_wide = m;
+        }
+    }
     if (out.big) {
         // lane state, vertices, D and offsets in global scratch (carve_big): shared memory only holds the simplex
         // costs, the program and the queue word
@@ -334,6 +359,31 @@ int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm,
         if (m <= smem_cap / 4 && !getenv("ABFIT_DEV_BOOT_TILE")) out.smem_boot_gather = m;  // else: stored-D* kernel
     }
     return 0;
+}
+
+std::vector<WorkItem> make_items_wide(const HostPlan &hp, int count_per_prob, int n_sm, bool skip_nan)
+{
+    // one warp per block, one fit at a time per warp: the kernel is bound by the latency of the sequential pair
+    // sum, so the batch is cut into about three waves of 14 warps per SM (more do not add throughput: 14 chains
+    // saturate the FP64 pipe) and a batch smaller than that gets one fit per warp
+    const int n_probs = (int)hp.probs.size();
+    const int64_t total = (int64_t)n_probs * count_per_prob;
+    const int64_t target_blocks = (int64_t)n_sm * 14 * 3;
+    int64_t chunk = std::max<int64_t>(1, (total + target_blocks - 1) / target_blocks);
+    chunk = std::min<int64_t>(chunk, count_per_prob);
+    std::vector<WorkItem> items;
+    for (int p = 0; p < n_probs; ++p) {
+        if (skip_nan && hp.d_has_nan[p]) continue;
+        for (int f = 0; f < count_per_prob; f += (int)chunk) {
+            WorkItem it;
+            it.prob = p;
+            it.first = f;
+            it.count = std::min<int>((int)chunk, count_per_prob - f);
+            it.pad = 0;
+            items.push_back(it);
+        }
+    }
+    return items;
 }
 
 std::vector<WorkItem> make_items(const HostPlan &hp, int count_per_prob, int n_sm, int n_warps, bool skip_nan)

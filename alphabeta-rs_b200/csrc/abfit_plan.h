@@ -10,6 +10,8 @@ struct HostPlan {
     std::vector<double> D;         // every problem padded to an even count (16-byte alignment)
     std::vector<uint32_t> offs;    // 256 * lane_mem index of each pair's dt1t2, padded to 4 per problem
     std::vector<OpWord> ops;
+    std::vector<uint32_t> wtrip;   // distinct triples of each program (warp-per-fit kernels, abfit_wide.cuh)
+    std::vector<uint32_t> wtid;    // triple id of every pair
     std::vector<double> flops;     // algorithmic FLOPs per objective evaluation
     std::vector<int32_t> n_triples, tmax;
     std::vector<uint8_t> d_has_nan;
@@ -33,7 +35,13 @@ struct LaunchShape {
     size_t smem_boot_gather = 0;  // k_fit_boot_gather (1 warp + pred/resid of the window), 0 = not usable
     size_t smem_aux = 0;    // k_select / k_cost_batch / k_model_div (1 warp, no simplex)
     bool d_shared_aux = true;
+    // warp-per-fit kernels (abfit_wide.cuh) replace the global-scratch variant of the Nelder-Mead kernels whenever
+    // their per-warp tables fit in shared memory: one block = one warp
+    bool wide = false;
+    size_t smem_wide = 0;
 };
+size_t smem_need_wide(const DevProblem &pb);
+std::vector<WorkItem> make_items_wide(const HostPlan &hp, int count_per_prob, int n_sm, bool skip_nan);
 int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm, int fits_per_prob, LaunchShape &out);
 
 // largest y with sqrt(y) < sd_tol (-1 when no y >= 0 qualifies): lets the kernels evaluate argmin's

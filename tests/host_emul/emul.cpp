@@ -15,6 +15,7 @@
 #include "shims.h"
 
 #include "../../alphabeta-rs_b200/csrc/abfit_plan.h"
+#include "../../alphabeta-rs_b200/csrc/abfit_wide.cuh"
 
 namespace abfit {
 static std::string g_err;
@@ -101,6 +102,71 @@ int emul_fit(const abfit_problem *pb, const double *simplices, int n, const doub
                 v = objective(s.c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
             }
             if (nm_advance(L, s.S, nm, v, res, 1u << lane)) break;
+        }
+        out[f] = res;
+    }
+    return 0;
+}
+
+// ---- warp-per-fit formulation (abfit_wide.cuh), run with a "warp" of ONE lane (ABFIT_WIDE_WIDTH=1): same
+// tables, same chunked pair sum, same Nelder-Mead driver as k_fit_wide
+struct StagedWide {
+    HostPlan hp;
+    std::vector<double> mem;
+    WideCtx c;
+    LaneSimplex S;
+};
+
+static int stage_wide(const abfit_problem *pb, StagedWide &s)
+{
+    if (int rc = compile_problems(pb, 1, s.hp)) return rc;
+    const DevProblem &d = s.hp.probs[0];
+    s.mem.assign(wide_warp_doubles(d.tmax, d.n_trip), 0.0);
+    double *after = wide_carve(s.c, s.mem.data(), d.tmax, d.n_trip);
+    s.S.X = after;
+    s.S.C = after + 20 * 32;
+    s.c.trip = s.hp.wtrip.data() + d.wtrip_off;
+    s.c.tid = s.hp.wtid.data() + d.wtid_off;
+    s.c.D = s.hp.D.data() + d.d_off;
+    s.c.n_pairs = d.n_pairs;
+    s.c.n_trip = d.n_trip;
+    s.c.tmax = d.tmax;
+    s.c.p_uu0 = d.p_uu0;
+    s.c.p_mm0 = d.p_mm0;
+    s.c.eqp = d.eqp;
+    s.c.penw = d.penw;
+    return 0;
+}
+
+int emul_cost_wide(const abfit_problem *pb, const double *theta, int B, double *cost, double *lse)
+{
+    StagedWide s;
+    if (int rc = stage_wide(pb, s)) return rc;
+    for (int i = 0; i < B; ++i) {
+        const double *t = theta + 4 * (size_t)i;
+        cost[i] = objective_wide(s.c, 0, t[0], t[1], t[2], t[3], true);
+        if (lse) lse[i] = objective_wide(s.c, 0, t[0], t[1], t[2], t[3], false);
+    }
+    return 0;
+}
+
+int emul_fit_wide(const abfit_problem *pb, const double *simplices, int n, const double *dstar, int max_iters,
+                  double sd_tol, uint32_t flags, abfit_fit *out)
+{
+    NMParams nm{max_iters, sd_tol, flags, nm_var_threshold(sd_tol)};
+    StagedWide s;
+    if (int rc = stage_wide(pb, s)) return rc;
+    for (int f = 0; f < n; ++f) {
+        if (dstar) s.c.D = dstar + (size_t)f * s.c.n_pairs;
+        LaneNM L;
+        std::memset(&L, 0, sizeof L);
+        for (int q = 0; q < 20; ++q) s.S.X[q * 32] = simplices[(size_t)f * 20 + q];
+        nm_begin(L, s.S, f);
+        abfit_fit res;
+        std::memset(&res, 0, sizeof res);
+        for (;;) {
+            const double v = objective_wide(s.c, 0, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
+            if (nm_advance(L, s.S, nm, v, res, 1u)) break;
         }
         out[f] = res;
     }

@@ -402,6 +402,7 @@ def test_big_variant_is_bit_identical_on_small_problems(ab, ctx, oracle, ped351,
     idx = np.concatenate([ab.gen_resample_idx(SEED, i, n_boot, len(p)).ravel() for i, (p, u) in enumerate(cases)])
     ref = ctx.alphabeta_batch(probs, sx, idx, SEED)
     monkeypatch.setenv("ABFIT_DEV_BIG", "1")
+    monkeypatch.setenv("ABFIT_DEV_WIDE", "0")  # the lane-per-fit global-scratch kernels, not the warp-per-fit ones
     big = ctx.alphabeta_batch(probs, sx, idx, SEED)
     for k in ("pred", "resid", "rows", "status"):
         assert np.array_equal(ref[k], big[k], equal_nan=True), k
@@ -409,11 +410,13 @@ def test_big_variant_is_bit_identical_on_small_problems(ab, ctx, oracle, ped351,
     theta = np.stack([10 ** rng.uniform(-6, -2, 50), 10 ** rng.uniform(-6, -2, 50), rng.uniform(0, 0.1, 50), rng.uniform(0, 0.01, 50)], axis=1)
     c_big, l_big = ctx.cost_batch(probs, theta, rng.integers(0, 2, 50).astype(np.int32))
     monkeypatch.delenv("ABFIT_DEV_BIG")
+    monkeypatch.delenv("ABFIT_DEV_WIDE")
 
 
 def test_c5_large_pedigree_fit(ab, ctx, oracle):
     """BASELINE configs[4]: 200 samples -> 19 900 pairs, 590 distinct (t0,t1,t2) triples, 836 doubles of model state
-    per lane: does not fit in shared memory, runs through the global-scratch variant; bit-exact against the oracle"""
+    per lane: does not fit in shared memory.  The Nelder-Mead kernels run warp-per-fit (abfit_wide.cuh), cost /
+    divergence / selection through the global-scratch lane-per-fit variant; all bit-exact against the oracle"""
     rng = np.random.default_rng(17)
     ped = c5_pedigree(rng)
     assert ped.shape == (19900, 4)
@@ -435,6 +438,17 @@ def test_c5_large_pedigree_fit(ab, ctx, oracle):
     check_fit_against_oracle(ab, oracle, res, 0, oracle.Problem(ped, p0, p0, 1.0), sx, 10000,
                              oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, 0, len(ped))
     assert 0.5 * a < res.best[0]["theta"][0] < 2 * a and 0.5 * b < res.best[0]["theta"][1] < 2 * b
+    # bootstrap of the same pedigree (warp-per-fit, D* rows materialised per replicate)
+    n_boot = 6
+    idx = ab.gen_resample_idx(SEED, 0, n_boot, len(ped))
+    vary = ab.gen_vary_vertices(SEED, 0, n_boot, res.best[0]["theta"])[None]
+    rows, fits = ctx.boot_batch([prob], res.best, res.pred, res.resid, idx.ravel(), vary, max_iters=1000)
+    rc, orows, ofits = oracle.boot_model(oracle.Problem(ped, p0, p0, 1.0), res.best[0]["theta"], res.pred, res.resid,
+                                         idx, vary[0], max_iters=1000,
+                                         flags=oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, n_threads=8)
+    assert rc == 0 and np.array_equal(rows[0], orows)
+    for f in ("theta", "cost", "iters", "evals", "status"):
+        assert np.array_equal(fits[0][f], ofits[f]), f
 
 
 # ---------------------------------------------------------------------------------------------
@@ -489,10 +503,11 @@ def test_c4_full_size_properties(ab, ctx, oracle, ped351):
 
 @pytest.mark.parametrize("env", [{"ABFIT_DEV_NWARPS": "4"}, {"ABFIT_DEV_NWARPS": "2"}, {"ABFIT_DEV_NWARPS": "1"},
                                  {"ABFIT_DEV_XGLOBAL": "1"}, {"ABFIT_DEV_BOOT_TILE": "1"}, {"ABFIT_DEV_CHUNK": "40"},
-                                 {"ABFIT_DEV_BIG": "1"}])
+                                 {"ABFIT_DEV_BIG": "1", "ABFIT_DEV_WIDE": "0"}, {"ABFIT_DEV_WIDE": "1"}])
 def test_kernel_variants_are_bit_identical(ab, ctx, ped351, monkeypatch, env):
     """every launch shape the library can choose (warps per block, queue chunking with tail hand-off, simplex vertices
-    in shared / global memory, stored-D* / index-tile bootstrap, global-scratch lane state) returns the same bits"""
+    in shared / global memory, stored-D* / index-tile bootstrap, global-scratch lane state, warp-per-fit) returns the
+    same bits"""
     rng = np.random.default_rng(33)
     cases = [synth_problem(rng, ped351) for _ in range(3)]
     probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]

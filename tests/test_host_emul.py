@@ -21,23 +21,23 @@ def emul():
     return C.CDLL(os.path.join(EMUL_DIR, "libemul.so"))
 
 
-def emul_cost(emul, ab, ped, p0uu, eqp, w, theta):
+def emul_cost(emul, ab, ped, p0uu, eqp, w, theta, wide=False):
     arr = ab._pack_problems([ab.Problem(ped, p0uu, eqp, w)])
     theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, 4)
     cost, lse = np.empty(len(theta)), np.empty(len(theta))
-    rc = emul.emul_cost(arr, theta.ctypes.data_as(C.c_void_p), len(theta), cost.ctypes.data_as(C.c_void_p),
+    rc = (emul.emul_cost_wide if wide else emul.emul_cost)(arr, theta.ctypes.data_as(C.c_void_p), len(theta), cost.ctypes.data_as(C.c_void_p),
                         lse.ctypes.data_as(C.c_void_p))
     assert rc == 0, rc
     return cost, lse
 
 
-def emul_fit(emul, ab, ped, p0uu, sx, max_iters=10000, flags=0, dstar=None):
+def emul_fit(emul, ab, ped, p0uu, sx, max_iters=10000, flags=0, dstar=None, wide=False):
     arr = ab._pack_problems([ab.Problem(ped, p0uu, p0uu, 1.0)])
     sx = np.ascontiguousarray(sx, dtype=np.float64)
     n = sx.size // 20
     out = np.zeros(n, dtype=ab.FIT_DTYPE)
     dp = None if dstar is None else np.ascontiguousarray(dstar, dtype=np.float64).ctypes.data_as(C.c_void_p)
-    rc = emul.emul_fit(arr, sx.ctypes.data_as(C.c_void_p), n, dp, max_iters, C.c_double(ab.DBL_EPSILON), flags,
+    rc = (emul.emul_fit_wide if wide else emul.emul_fit)(arr, sx.ctypes.data_as(C.c_void_p), n, dp, max_iters, C.c_double(ab.DBL_EPSILON), flags,
                        out.ctypes.data_as(C.c_void_p))
     assert rc == 0, rc
     return out
@@ -65,22 +65,25 @@ def random_pedigree(rng, n_pairs, tmax, style):
 @pytest.mark.parametrize("tmax", [1, 4, 33, 127])
 def test_compiled_program_cost_is_bit_exact(emul, ab, oracle, style, tmax):
     rng = np.random.default_rng(hash((style, tmax)) % 2**32)
-    for n_pairs in (1, 3, 4, 5, 37, 120):
+    for n_pairs in (1, 3, 4, 5, 37, 120, 131, 260):
         ped = random_pedigree(rng, n_pairs, tmax, style)
         B = 40
         theta = np.stack([10 ** rng.uniform(-7, -1.5, B), 10 ** rng.uniform(-7, -1.5, B), rng.uniform(-0.1, 0.3, B),
                           rng.uniform(0, 0.1, B)], axis=1)
         theta[3] = [-2e-4, 3e-3, -0.2, 0.01]
         cost, lse = emul_cost(emul, ab, ped, 0.8, 0.7, 1.3, theta)
+        wcost, wlse = emul_cost(emul, ab, ped, 0.8, 0.7, 1.3, theta, wide=True)  # warp-per-fit formulation
         pb = oracle.Problem(ped, 0.8, 0.7, 1.3)
         for i in range(B):
             assert cost[i] == oracle.cost(pb, theta[i]), (style, tmax, n_pairs, i)
             assert lse[i] == oracle.lse(pb, theta[i], flags=oracle.FAST_DIVERGENCE), (style, tmax, n_pairs, i)
+        assert np.array_equal(wcost, cost, equal_nan=True) and np.array_equal(wlse, lse, equal_nan=True)
 
 
-def test_golden_cost_kat_through_the_device_headers(emul, ab, oracle):
+@pytest.mark.parametrize("wide", [False, True])
+def test_golden_cost_kat_through_the_device_headers(emul, ab, oracle, wide):
     ped = oracle.load_pedigree_file(os.path.join(GOLDEN, "pedigree.txt"))
-    cost, _ = emul_cost(emul, ab, ped, 0.75, 0.5, 0.7, [[0.0001179555, 0.0001180614, 0.03693534, 0.003023981]])
+    cost, _ = emul_cost(emul, ab, ped, 0.75, 0.5, 0.7, [[0.0001179555, 0.0001180614, 0.03693534, 0.003023981]], wide=wide)
     assert cost[0] == 0.0006700888539608879  # src/structs.rs:233
 
 
@@ -94,11 +97,13 @@ def test_nelder_mead_state_machine_matches_oracle(emul, ab, oracle, flags):
     for p, u in ((ped, 0.8), (ped6, 0.655)):
         sx = ab.gen_start_simplices(7, 3, 24, float(p[:, 3].max()))
         g = emul_fit(emul, ab, p, u, sx, max_iters=max_iters, flags=flags)
+        gw = emul_fit(emul, ab, p, u, sx, max_iters=max_iters, flags=flags, wide=True)
         rc, best, allr, pred, resid = oracle.ab_neutral(oracle.Problem(p, u, u, 1.0), sx, max_iters=max_iters, flags=oflags,
                                                         n_threads=4)
         assert rc == 0
         for f in ("theta", "cost", "lse", "iters", "evals", "status"):
             assert np.array_equal(g[f], allr[f]), (flags, f)
+            assert np.array_equal(gw[f], allr[f]), ("wide", flags, f)
 
 
 def test_bootstrap_column_access_matches_oracle(emul, ab, oracle):
@@ -114,6 +119,8 @@ def test_bootstrap_column_access_matches_oracle(emul, ab, oracle):
     dstar = pred[None, :] + resid[idx]
     simplices = np.concatenate([np.broadcast_to(best["theta"], (n_boot, 1, 4)), vary], axis=1)
     g = emul_fit(emul, ab, ped, u, simplices, max_iters=1000, dstar=dstar)
+    gw = emul_fit(emul, ab, ped, u, simplices, max_iters=1000, dstar=dstar, wide=True)
+    assert np.array_equal(gw["theta"], g["theta"]) and np.array_equal(gw["evals"], g["evals"])
     rc, rows, fits = oracle.boot_model(oracle.Problem(ped, u, u, 1.0), best["theta"], pred, resid, idx, vary,
                                        flags=oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, n_threads=4)
     assert rc == 0

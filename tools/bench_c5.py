@@ -25,7 +25,10 @@ bt.upload_starts(sx[None])
 for rep in range(2):
     bt.run_fit(); tm = bt.timing()
     print("fit 1000 starts: %.1f ms, evals/fit %.0f, %.2f TFLOP/s" % (tm["fit_ms"], tm["evals_fit"] / NS, tm["evals_fit"] * fl["flops"] / tm["fit_ms"] / 1e9))
-res = bt.download_fit()
+res = bt.download_fit(want_all=True)
+ev = np.sort(res.all[0]["evals"])
+print("evals per fit: median %d, p90 %d, p99 %d, max %d -> %.1f us per evaluation on the longest fit's warp" %
+      (ev[len(ev) // 2], ev[int(0.9 * len(ev))], ev[int(0.99 * len(ev))], ev[-1], tm["fit_ms"] * 1e3 / ev[-1]))
 vary = ab.gen_vary_vertices(1, 0, NB, res.best[0]["theta"])
 bt.upload_boot(idx, vary[None])
 bt.run_boot(); tm = bt.timing()
