@@ -504,12 +504,14 @@ def test_c4_full_size_properties(ab, ctx, oracle, ped351):
 @pytest.mark.parametrize("env", [{"ABFIT_DEV_NWARPS": "4"}, {"ABFIT_DEV_NWARPS": "2"}, {"ABFIT_DEV_NWARPS": "1"},
                                  {"ABFIT_DEV_XGLOBAL": "1"}, {"ABFIT_DEV_BOOT_TILE": "1"}, {"ABFIT_DEV_CHUNK": "40"},
                                  {"ABFIT_DEV_BIG": "1", "ABFIT_DEV_WIDE": "0"}, {"ABFIT_DEV_WIDE": "1"}])
-def test_kernel_variants_are_bit_identical(ab, ctx, ped351, monkeypatch, env):
+def test_kernel_variants_are_bit_identical(ab, ctx, ped351, ped78, monkeypatch, env):
     """every launch shape the library can choose (warps per block, queue chunking with tail hand-off, simplex vertices
     in shared / global memory, stored-D* / index-tile bootstrap, global-scratch lane state, warp-per-fit) returns the
     same bits"""
     rng = np.random.default_rng(33)
-    cases = [synth_problem(rng, ped351) for _ in range(3)]
+    ped6 = np.loadtxt(os.path.join(GOLDEN, "pedigree_generated.txt"), skiprows=1)
+    # different pedigrees in one batch: 351 pairs (two share a program), 78 pairs, 6 pairs (shorter than one chunk)
+    cases = [synth_problem(rng, ped351) for _ in range(2)] + [ped78, (ped6, 0.655), synth_problem(rng, ped351, n_keep=200)]
     probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
     n_starts, n_boot = 400, 48
     sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
