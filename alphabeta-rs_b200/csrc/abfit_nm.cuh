@@ -124,7 +124,66 @@ __device__ __forceinline__ bool nm_advance(LaneNM &L, const LaneSimplex &S, cons
     bool iter_done = false;   // an NM iteration (or init) completed: sort + termination test follow
     bool finish = false;      // go to the final LSE evaluation
     bool done = false;        // the fit has ended (result in `res`)
-    switch (L.phase) {
+    const int ph = L.phase;
+    // ---- reflect / expand / contract: ~99 % of all evaluations --------------------------------------
+    // The lanes of a warp are spread over these three phases and their outcomes.  Written as ONE region with
+    // per-lane predicates (instead of one switch arm per phase and outcome) so that the lanes share its
+    // instruction stream: one centroid, one vertex replacement, one next trial point — whoever needs them.
+    if (ph == PH_REFLECT || ph == PH_EXPAND || ph == PH_CONTRACT) {
+        ++L.evals;
+        const int w = ord_at(L.ord, 4);
+        const bool is_r = ph == PH_REFLECT, is_e = ph == PH_EXPAND, is_c = ph == PH_CONTRACT;
+        const double c0 = S.c(ord_at(L.ord, 0)), c3 = S.c(ord_at(L.ord, 3)), cw = S.c(w);
+        const bool r_accept = is_r && (f < c3 && f >= c0);              // Action::Reflection
+        const bool r_expand = is_r && !r_accept && (f < c0);            // Action::Expansion
+        const bool r_contract = is_r && !r_accept && !r_expand && (f >= c3);  // Action::ContractionInside
+        const bool r_nan = is_r && !r_accept && !r_expand && !r_contract;     // NaN reflection cost: Action::Shrink
+        const bool e_take = is_e && (f < L.fr);
+        const bool e_keep = is_e && !e_take;  // keep the reflection point (recomputed from the untouched simplex: same bits)
+        const bool c_take = is_c && (f < cw);
+        const bool c_fail = is_c && !c_take;
+        double x0[4] = {0.0, 0.0, 0.0, 0.0};
+        if (r_expand || r_contract || e_keep) centroid(S, L.ord, x0);
+        if (r_accept || e_take || c_take || e_keep) {  // replace the worst vertex
+            double v[4], cost = e_keep ? L.fr : f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double xr = x0[j] + (x0[j] - S.x(w, j)) * 1.0;  // NelderMead::reflect
+                v[j] = e_keep ? xr : L.xt[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) S.x(w, j) = v[j];
+            S.c(w) = cost;
+            iter_done = true;
+        }
+        if (r_expand || r_contract) {
+            // xe = x0 + (xr - x0) * 2   /   xc = x0 + (x[4] - x0) * 0.5
+            const double coef = r_expand ? 2.0 : 0.5;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double from = r_expand ? L.xt[j] : S.x(w, j);
+                L.xt[j] = x0[j] + (from - x0[j]) * coef;
+            }
+            if (r_expand) L.fr = f;
+            L.phase = r_expand ? PH_EXPAND : PH_CONTRACT;
+        }
+        if (r_nan || (c_fail && (P.flags & ABFIT_SHRINK_ON_FAILED_CONTRACTION))) {
+            L.k = 1;
+            shrink_point(S, L.ord, 1, L.xt);
+            L.phase = PH_SHRINK;
+        } else if (c_fail) {
+            if (P.flags & ABFIT_NO_EARLY_EXIT_ON_STALL) {
+                iter_done = true;  // argmin 0.8.1: nothing replaced, iteration counted
+            } else {
+                // Simplex unchanged and next_iter is a pure function of it: all remaining
+                // iterations repeat this one.  Same best vertex as after max_iters.
+                L.iters = P.max_iters;
+                L.status = ABFIT_TERM_STALLED;
+                finish = true;
+            }
+        }
+    }
+    switch (ph) {
         case PH_INIT: {
             // NOTE: written as "load vertex k+1 relative to k, then bump k" on purpose.  ptxas 12.9 folds
             // `++k; load x[k]` into an LDS with the +1 in the immediate offset AND reads the already
@@ -142,76 +201,6 @@ __device__ __forceinline__ bool nm_advance(LaneNM &L, const LaneSimplex &S, cons
             } else {
                 iter_done = true;  // sort + termination test of the Executor's first loop pass
                 L.iters = -1;      // the shared tail below counts an iteration; init is not one
-            }
-            break;
-        }
-        case PH_REFLECT: {
-            ++L.evals;
-            const double c0 = S.c(ord_at(L.ord, 0)), c3 = S.c(ord_at(L.ord, 3));
-            if (f < c3 && f >= c0) {  // Action::Reflection
-                const int w = ord_at(L.ord, 4);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) S.x(w, j) = L.xt[j];
-                S.c(w) = f;
-                iter_done = true;
-            } else if (f < c0) {  // Action::Expansion: xe = x0 + (xr - x0) * 2
-                double x0[4];
-                centroid(S, L.ord, x0);
-                L.fr = f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) L.xt[j] = x0[j] + (L.xt[j] - x0[j]) * 2.0;
-                L.phase = PH_EXPAND;
-            } else if (f >= c3) {  // Action::ContractionInside: xc = x0 + (x[4] - x0) * 0.5
-                double x0[4];
-                centroid(S, L.ord, x0);
-                const int w = ord_at(L.ord, 4);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) L.xt[j] = x0[j] + (S.x(w, j) - x0[j]) * 0.5;
-                L.phase = PH_CONTRACT;
-            } else {  // NaN reflection cost: Action::Shrink
-                L.k = 1;
-                shrink_point(S, L.ord, 1, L.xt);
-                L.phase = PH_SHRINK;
-            }
-            break;
-        }
-        case PH_EXPAND: {
-            ++L.evals;
-            const int w = ord_at(L.ord, 4);
-            if (f < L.fr) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) S.x(w, j) = L.xt[j];
-                S.c(w) = f;
-            } else {  // keep the reflection point (recomputed from the untouched simplex: same bits)
-                double xr[4];
-                reflect_point(S, L.ord, xr);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) S.x(w, j) = xr[j];
-                S.c(w) = L.fr;
-            }
-            iter_done = true;
-            break;
-        }
-        case PH_CONTRACT: {
-            ++L.evals;
-            const int w = ord_at(L.ord, 4);
-            if (f < S.c(w)) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) S.x(w, j) = L.xt[j];
-                S.c(w) = f;
-                iter_done = true;
-            } else if (P.flags & ABFIT_SHRINK_ON_FAILED_CONTRACTION) {
-                L.k = 1;
-                shrink_point(S, L.ord, 1, L.xt);
-                L.phase = PH_SHRINK;
-            } else if (P.flags & ABFIT_NO_EARLY_EXIT_ON_STALL) {
-                iter_done = true;  // argmin 0.8.1: nothing replaced, iteration counted
-            } else {
-                // Simplex unchanged and next_iter is a pure function of it: all remaining
-                // iterations repeat this one.  Same best vertex as after max_iters.
-                L.iters = P.max_iters;
-                L.status = ABFIT_TERM_STALLED;
-                finish = true;
             }
             break;
         }
