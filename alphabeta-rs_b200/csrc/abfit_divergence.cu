@@ -9,7 +9,8 @@
 //                       valid = post >= thr, t1 = status >= 1, t2 = status >= 2 (thermometer code,
 //                       |a-b| = popc(t1a^t1b) + popc(t2a^t2b)) — plus blocked partial sums of
 //                       meth_lvl over valid sites.  3 bits/site leave HBM again (2 % of the input).
-//   pass 2  k_pairs     all-pairs popcount over the bit-planes staged in shared memory; exact u64
+//   pass 2  k_pairs     all-pairs popcount over the bit-planes staged in shared memory, 4 x 4 sample tiles
+//                       in registers (POPC-bound); exact u64
 //                       sums, so D = diff / (2 cnt) is bit-identical to the reference for any
 //                       sharding of the site axis.
 //   pass 3  k_finalize  D = diff/(2 cnt), per-sample methsum / nvalid, p0uu per window.
@@ -104,43 +105,101 @@ struct PairItem {
     int32_t pad;
 };
 
-__global__ void __launch_bounds__(256)
+// Register-tiled all-pairs popcount.  A thread owns up to two 4 x 4 tiles of the (i, j) sample matrix (16 pairs
+// each, upper triangle incl. the diagonal blocks): per 64-site word it reads the three bit-planes of its 4 row
+// samples (6 x 16-byte loads, a broadcast inside a warp, whose lanes share the row block) and of its 4 column
+// samples, and updates 16 packed counters (cnt << 16 | diff: an item has at most 256 words, so diff <= 32 768 and
+// cnt <= 16 384).  0.75 shared-memory loads per pair and word instead of 6, and one atomic per pair and item of
+// up to 256 words instead of one per 34 words: the pass is bound by the POPC pipe, not by the LSU.
+// Shared layout: plane[w * Sp + s] (word-major: the samples of a tile are adjacent), Sp = padded S + 2.
+constexpr int PAIR_ITEM_WORDS = 256;
+constexpr int PAIR_THREADS_MAX = 640;
+
+__global__ void __launch_bounds__(PAIR_THREADS_MAX)
 k_pairs(const unsigned long long *__restrict__ V, const unsigned long long *__restrict__ T1,
         const unsigned long long *__restrict__ T2, int64_t total_words, int S, int P,
-        const PairItem *__restrict__ items, const ushort2 *__restrict__ pairtab,
+        const PairItem *__restrict__ items, const ushort2 *__restrict__ tiletab, int n_tiles, int Sp, int sw,
         unsigned long long *__restrict__ diff, unsigned long long *__restrict__ cnt)
 {
     extern __shared__ unsigned long long sh[];
     const PairItem it = items[blockIdx.x];
-    const int nw = it.n_words;
-    unsigned long long *sV = sh, *sA = sh + (size_t)S * nw, *sB = sh + (size_t)2 * S * nw;
-    for (int q = threadIdx.x; q < S * nw; q += blockDim.x) {
-        const int s = q / nw, w = q - s * nw;
-        const size_t g = (size_t)s * total_words + it.first_word + w;
-        sV[q] = V[g];
-        sA[q] = T1[g];
-        sB[q] = T2[g];
-    }
-    __syncthreads();
+    const size_t plane = (size_t)sw * Sp;
+    unsigned long long *sV = sh, *sA = sh + plane, *sB = sh + 2 * plane;
+    // rows S .. Sp-1 stay zero: valid = 0, they add nothing
+    for (size_t q = threadIdx.x; q < 3 * plane; q += blockDim.x) sh[q] = 0ull;
     unsigned long long *dw = diff + (size_t)it.window * P, *cw = cnt + (size_t)it.window * P;
-    for (int p = threadIdx.x; p < P; p += blockDim.x) {
-        const ushort2 ij = pairtab[p];
-        const unsigned long long *vi = sV + (size_t)ij.x * nw, *vj = sV + (size_t)ij.y * nw;
-        const unsigned long long *ai = sA + (size_t)ij.x * nw, *aj = sA + (size_t)ij.y * nw;
-        const unsigned long long *bi = sB + (size_t)ij.x * nw, *bj = sB + (size_t)ij.y * nw;
-        unsigned d = 0, c = 0;  // <= 64 * 2 * nw, nw <= 2^20: fits
-        for (int w = 0; w < nw; ++w) {
-            const unsigned long long m = vi[w] & vj[w];
-            c += __popcll(m);
-            d += __popcll((ai[w] ^ aj[w]) & m) + __popcll((bi[w] ^ bj[w]) & m);
+    const int nthr = blockDim.x;
+    for (int pass = 0; pass < n_tiles; pass += 2 * nthr) {
+        const int ta = pass + threadIdx.x, tb = ta + nthr;
+        const bool has_a = ta < n_tiles, has_b = tb < n_tiles;
+        const ushort2 A = has_a ? tiletab[ta] : make_ushort2(0, 0), B = has_b ? tiletab[tb] : make_ushort2(0, 0);
+        unsigned acc_a[16], acc_b[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc_a[k] = acc_b[k] = 0u;
+        for (int w0 = 0; w0 < it.n_words; w0 += sw) {
+            const int nw = min(sw, it.n_words - w0);
+            __syncthreads();  // the previous sub-chunk has been consumed (and the zero fill is complete)
+            // coalesced on the word axis in global memory
+            for (int q = threadIdx.x; q < S * nw; q += nthr) {
+                const int s = q / nw, w = q - s * nw;
+                const size_t g = (size_t)s * total_words + it.first_word + w0 + w;
+                sV[(size_t)w * Sp + s] = V[g];
+                sA[(size_t)w * Sp + s] = T1[g];
+                sB[(size_t)w * Sp + s] = T2[g];
+            }
+            __syncthreads();
+            auto tile = [&](const ushort2 T, unsigned acc[16]) {
+                for (int w = 0; w < nw; ++w) {
+                    const size_t r = (size_t)w * Sp + 4 * T.x, c = (size_t)w * Sp + 4 * T.y;
+                    unsigned long long vi[4], ai[4], bi[4];
+                    {
+                        const ulonglong2 v0 = *reinterpret_cast<const ulonglong2 *>(sV + r), v1 = *reinterpret_cast<const ulonglong2 *>(sV + r + 2);
+                        const ulonglong2 a0 = *reinterpret_cast<const ulonglong2 *>(sA + r), a1 = *reinterpret_cast<const ulonglong2 *>(sA + r + 2);
+                        const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(sB + r), b1 = *reinterpret_cast<const ulonglong2 *>(sB + r + 2);
+                        vi[0] = v0.x; vi[1] = v0.y; vi[2] = v1.x; vi[3] = v1.y;
+                        ai[0] = a0.x; ai[1] = a0.y; ai[2] = a1.x; ai[3] = a1.y;
+                        bi[0] = b0.x; bi[1] = b0.y; bi[2] = b1.x; bi[3] = b1.y;
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {  // two column samples per 16-byte load
+                        const ulonglong2 vj = *reinterpret_cast<const ulonglong2 *>(sV + c + 2 * h);
+                        const ulonglong2 aj = *reinterpret_cast<const ulonglong2 *>(sA + c + 2 * h);
+                        const ulonglong2 bj = *reinterpret_cast<const ulonglong2 *>(sB + c + 2 * h);
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            const unsigned long long m0 = vi[a] & vj.x, m1 = vi[a] & vj.y;
+                            acc[4 * a + 2 * h] += ((unsigned)__popcll(m0) << 16) + (unsigned)__popcll((ai[a] ^ aj.x) & m0) +
+                                                  (unsigned)__popcll((bi[a] ^ bj.x) & m0);
+                            acc[4 * a + 2 * h + 1] += ((unsigned)__popcll(m1) << 16) + (unsigned)__popcll((ai[a] ^ aj.y) & m1) +
+                                                      (unsigned)__popcll((bi[a] ^ bj.y) & m1);
+                        }
+                    }
+                }
+            };
+            if (has_a) tile(A, acc_a);
+            if (has_b) tile(B, acc_b);
         }
-        if (it.single) {
-            dw[p] = d;
-            cw[p] = c;
-        } else {
-            atomicAdd(dw + p, (unsigned long long)d);
-            atomicAdd(cw + p, (unsigned long long)c);
-        }
+        auto flush = [&](const ushort2 T, const unsigned acc[16]) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int i = 4 * T.x + a, j = 4 * T.y + b;
+                    if (i < j && j < S) {
+                        const size_t p = (size_t)i * S - (size_t)i * (i + 1) / 2 + (size_t)(j - i - 1);
+                        const unsigned long long d = acc[4 * a + b] & 0xffffu, c = acc[4 * a + b] >> 16;
+                        if (it.single) {
+                            dw[p] = d;
+                            cw[p] = c;
+                        } else {
+                            atomicAdd(dw + p, d);
+                            atomicAdd(cw + p, c);
+                        }
+                    }
+                }
+        };
+        if (has_a) flush(A, acc_a);
+        if (has_b) flush(B, acc_b);
     }
 }
 
@@ -232,32 +291,49 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
     const int P = S * (S - 1) / 2;
     *launches = 0;
 
-    // pair chunks: as many words per block as fit next to S samples in shared memory
-    const size_t smem_cap = 160 * 1024;
-    int64_t cw_max = (int64_t)(smem_cap / ((size_t)S * 24));
-    if (cw_max < 1) {
+    // pair pass: items of at most PAIR_ITEM_WORDS words (packed 16-bit counters), staged through shared memory
+    // `sw` words at a time; 4 x 4 sample tiles, two per thread
+    const int Sp = ((S + 3) & ~3) + 2;  // even (16-byte loads), and w * Sp walks through 8 different bank pairs
+    const int nb = (S + 3) / 4;
+    const int n_tiles = nb * (nb + 1) / 2;
+    const size_t smem_cap = 200 * 1024;
+    int sw = (int)std::min<size_t>(32, smem_cap / ((size_t)Sp * 24));
+    if (sw < 1) {
         set_error("too many samples for the shared-memory pair kernel");
         return ABFIT_ERR_TOO_LARGE;
     }
-    if (cw_max > 64) cw_max = 64;
+    const int pair_threads = std::min(PAIR_THREADS_MAX, std::max(32, (((n_tiles + 1) / 2) + 31) & ~31));
+    int n_sm = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
     std::vector<PairItem> items;
+    // enough items to give every SM a block, never more than PAIR_ITEM_WORDS words each
+    const int64_t chunk_target = std::max<int64_t>(8, std::min<int64_t>(PAIR_ITEM_WORDS, (TW + n_sm - 1) / n_sm));
     for (int w = 0; w < W; ++w) {
         const int64_t nw = woff[w + 1] - woff[w];
-        for (int64_t f = 0; f < nw; f += cw_max) {
+        if (nw <= 0) continue;
+        int64_t n_chunks = (nw + chunk_target - 1) / chunk_target;
+        // one long window (a whole methylome): whole waves of one block per SM
+        if (W == 1 && n_chunks > n_sm / 2) n_chunks = ((n_chunks + n_sm - 1) / n_sm) * n_sm;
+        const int64_t chunk = (nw + n_chunks - 1) / n_chunks;
+        for (int64_t f = 0; f < nw; f += chunk) {
             PairItem it;
             it.window = w;
-            it.n_words = (int32_t)std::min<int64_t>(cw_max, nw - f);
+            it.n_words = (int32_t)std::min<int64_t>(chunk, nw - f);
             it.first_word = woff[w] + f;
-            it.single = nw <= cw_max;
+            it.single = nw <= chunk;
             it.pad = 0;
             items.push_back(it);
         }
     }
-    std::vector<ushort2> pairtab((size_t)P);
+    std::vector<ushort2> pairtab((size_t)n_tiles);  // tile -> (row block, column block), row-major: a warp shares its rows
     {
-        size_t p = 0;
-        for (int i = 0; i < S; ++i)
-            for (int j = i + 1; j < S; ++j) pairtab[p++] = make_ushort2((unsigned short)i, (unsigned short)j);
+        size_t t = 0;
+        for (int i = 0; i < nb; ++i)
+            for (int j = i; j < nb; ++j) pairtab[t++] = make_ushort2((unsigned short)i, (unsigned short)j);
     }
 
     // device scratch
@@ -322,11 +398,11 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
     }
     if (ms) DV_CUDA(cudaEventRecord(ev[1], st));
     if (P > 0 && !items.empty()) {
-        const size_t smem = (size_t)S * cw_max * 24;
+        const size_t smem = (size_t)sw * Sp * 24;
         if (smem > 48 * 1024)
             DV_CUDA(cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_pairs<<<(unsigned)items.size(), 256, smem, st>>>(d_V, d_T1, d_T2, TW, S, P, d_items, d_pairtab, d_diff,
-                                                          d_cnt);
+        k_pairs<<<(unsigned)items.size(), pair_threads, smem, st>>>(d_V, d_T1, d_T2, TW, S, P, d_items, d_pairtab,
+                                                                   n_tiles, Sp, sw, d_diff, d_cnt);
         DV_CUDA(cudaGetLastError());
         ++*launches;
     }
