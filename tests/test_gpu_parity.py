@@ -291,6 +291,29 @@ def test_dmatrix_large_blocked(ab, ctx, oracle):
     assert np.array_equal(a["nvalid"] + b["nvalid"], out["nvalid"])
 
 
+@pytest.mark.parametrize("S,L,segs", [(2, 130, None), (3, 64, None), (5, 1, None), (210, 40_000, None),
+                                      (37, 5_000, [0, 0, 63, 64, 700, 700, 4_999, 5_000]),
+                                      (5, 2_600_000, [0, 1_300_000, 2_600_000])])
+def test_dmatrix_pair_tiles_shapes(ab, ctx, oracle, S, L, segs):
+    """the register-tiled pair pass: sample counts that are not multiples of the 4 x 4 tile, more tiles than one
+    pass of the block covers (210 samples -> 1431 tiles), items of several hundred words that flush their packed
+    counters, windows of 0 / 1 / 63 / 64 sites"""
+    rng = np.random.default_rng(1000 * S + L)
+    status, post, meth = synth_methylomes(rng, S, L)
+    if segs is None:
+        out = ctx.dmatrix(status, post, meth, 0.99)
+        D, diff, cnt = oracle.dmatrix(status, post, 0.99)
+        assert np.array_equal(out["diff"][0], diff) and np.array_equal(out["cnt"][0], cnt)
+        assert np.array_equal(out["D"][0], D, equal_nan=True)
+    else:
+        out = ctx.dmatrix(status, post, meth, 0.99, seg_offsets=segs)
+        for w in range(len(segs) - 1):
+            a, b = segs[w], segs[w + 1]
+            D, diff, cnt = oracle.dmatrix(status[:, a:b], post[:, a:b], 0.99)
+            assert np.array_equal(out["diff"][w], diff) and np.array_equal(out["cnt"][w], cnt), w
+            assert np.array_equal(out["D"][w], D, equal_nan=True), w
+
+
 # ---------------------------------------------------------------------------------------------
 # C3: metaprofile windows -> observed divergence per window -> fit, all windows in one batch
 # ---------------------------------------------------------------------------------------------
