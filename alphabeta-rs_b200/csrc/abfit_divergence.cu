@@ -126,7 +126,15 @@ k_pairs(const unsigned long long *__restrict__ V, const unsigned long long *__re
     const size_t plane = (size_t)sw * Sp;
     unsigned long long *sV = sh, *sA = sh + plane, *sB = sh + 2 * plane;
     // rows S .. Sp-1 stay zero: valid = 0, they add nothing
-    for (size_t q = threadIdx.x; q < 3 * plane; q += blockDim.x) sh[q] = 0ull;
+    {
+        const int npad = Sp - S;
+        for (int q = threadIdx.x; q < sw * npad; q += blockDim.x) {
+            const size_t o = (size_t)(q / npad) * Sp + S + (q % npad);
+            sV[o] = 0ull;
+            sA[o] = 0ull;
+            sB[o] = 0ull;
+        }
+    }
     unsigned long long *dw = diff + (size_t)it.window * P, *cw = cnt + (size_t)it.window * P;
     const int nthr = blockDim.x;
     for (int pass = 0; pass < n_tiles; pass += 2 * nthr) {
@@ -328,6 +336,11 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
             it.pad = 0;
             items.push_back(it);
         }
+    }
+    {
+        int32_t longest = 1;
+        for (auto &it : items) longest = std::max(longest, it.n_words);
+        sw = std::min(sw, (int)longest);  // thousands of one-word windows: a block stages one word, not 32
     }
     std::vector<ushort2> pairtab((size_t)n_tiles);  // tile -> (row block, column block), row-major: a warp shares its rows
     {
