@@ -1,7 +1,9 @@
 // abfit_plan.cu — pedigree -> micro-op program (host).  O(pairs) bookkeeping; no numerics.
 #include <cfloat>
 #include <cstdlib>
+#include <cstring>
 #include <cmath>
+#include <thread>
 #include <map>
 #include <set>
 #include <tuple>
@@ -49,6 +51,24 @@ size_t smem_need_boot_gather(const DevProblem &pb)
     return smem_need(pb, 25, false, 1) + (size_t)boot_gather_lead(pb.n_pairs) * 8;
 }
 
+// run f(p) for p in [0, n) on the host's cores (row scans of large batches; small ones stay on the caller's thread)
+template <class F>
+static void scan_parallel(int n, F f)
+{
+    const unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), (unsigned)(n / 512));
+    if (nt <= 1) {
+        for (int p = 0; p < n; ++p) f(p);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+        th.emplace_back([=]() {
+            const int lo = (int)((int64_t)n * t / nt), hi = (int)((int64_t)n * (t + 1) / nt);
+            for (int p = lo; p < hi; ++p) f(p);
+        });
+    for (auto &x : th) x.join();
+}
+
 int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
 {
     hp.clear();
@@ -63,21 +83,55 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
     hp.d_has_nan.assign(n_probs, 0);
     typedef std::tuple<int, int, int> Tri;  // (t0, a = t1 - t0, b = t2 - t0)
     typedef std::pair<int, int> AB;
-    // Windows of one metaprofile share the pedigree's time structure (same nodes and edges, only D differs):
-    // a problem whose (t0,t1,t2) sequence equals the previous one's shares its program and offsets in the pools.
-    std::vector<uint32_t> key32, prev_key32;
-    int prev_p = -1;
+
+    // ---- pass 1: pool layout, then one scan of every pedigree row (parallel over problems) ------------
+    std::vector<int64_t> d_off(n_probs), pair_off(n_probs);
+    int64_t d_total = 0;
     for (int p = 0; p < n_probs; ++p) {
-        const abfit_problem &ap = probs[p];
-        if (!ap.pedigree || ap.n_pairs <= 0) {
+        if (!probs[p].pedigree || probs[p].n_pairs <= 0) {
             set_error("problem " + std::to_string(p) + ": empty pedigree");
             return ABFIT_ERR_ARG;
         }
+        d_off[p] = d_total;  // even: 16-byte aligned columns
+        pair_off[p] = hp.total_pairs;
+        d_total += ((int64_t)probs[p].n_pairs + 1) & ~(int64_t)1;
+        hp.total_pairs += probs[p].n_pairs;
+        hp.max_pairs = std::max(hp.max_pairs, probs[p].n_pairs);
+    }
+    hp.D.assign((size_t)d_total, 0.0);
+    std::vector<uint32_t> keys((size_t)hp.total_pairs);  // t0 | (t1 - t0) << 8 | (t2 - t0) << 16 per row
+    std::vector<int32_t> bad_row(n_probs, -1), max_exp_of(n_probs, 0);
+    scan_parallel(n_probs, [&](int p) {
+        const abfit_problem &ap = probs[p];
+        uint32_t *k = keys.data() + pair_off[p];
+        double *Dp = hp.D.data() + d_off[p];
+        int mx = 0;
+        uint8_t nan = 0;
+        for (int i = 0; i < ap.n_pairs; ++i) {
+            const double *row = ap.pedigree + 4 * (size_t)i;
+            const int t0 = as_i8(row[0]), t1 = as_i8(row[1]), t2 = as_i8(row[2]);
+            if (t0 < 0 || t1 < t0 || t2 < t0) {
+                bad_row[p] = i;
+                return;
+            }
+            k[i] = (uint32_t)t0 | ((uint32_t)(t1 - t0) << 8) | ((uint32_t)(t2 - t0) << 16);
+            mx = std::max(mx, std::max(t0, std::max(t1 - t0, t2 - t0)));
+            nan |= (uint8_t)(row[3] != row[3]);
+            Dp[i] = row[3];
+        }
+        max_exp_of[p] = mx;
+        hp.d_has_nan[p] = nan;
+    });
+
+    // ---- pass 2: programs ------------------------------------------------------------------------------
+    // Windows of one metaprofile share the pedigree's time structure (same nodes and edges, only D differs):
+    // a problem whose (t0,t1,t2) sequence equals the previous one's shares its program and offsets in the pools.
+    int prev_p = -1;
+    for (int p = 0; p < n_probs; ++p) {
+        const abfit_problem &ap = probs[p];
         DevProblem dp;
-        if (hp.D.size() & 1) hp.D.push_back(0.0);
-        dp.d_off = (int64_t)hp.D.size();
-        dp.pair_off = hp.total_pairs;
-        hp.total_pairs += ap.n_pairs;
+        dp.d_off = d_off[p];
+        dp.pair_off = pair_off[p];
         dp.offs_off = (int64_t)hp.offs.size();
         dp.ops_off = (int64_t)hp.ops.size();
         dp.wtrip_off = (int64_t)hp.wtrip.size();
@@ -89,29 +143,17 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
             set_error("problem " + std::to_string(p) + ": p0mm + p0uu + p0um != 1");
             return ABFIT_ERR_NAN;
         }
+        if (bad_row[p] >= 0) {
+            set_error("problem " + std::to_string(p) + " row " + std::to_string(bad_row[p]) +
+                      ": needs 0 <= t0 <= t1,t2 <= 127 (the reference would invert the matrix)");
+            return ABFIT_ERR_TIME;
+        }
         dp.eqp = ap.eqp;
         dp.penw = ap.eqp_weight * (double)ap.n_pairs;  // src/structs.rs:210-211
-
-        // ---- distinct triples --------------------------------------------------------------
-        std::vector<Tri> key(ap.n_pairs);
-        std::map<Tri, int> tri_id;
-        int max_exp = 0;
-        key32.resize(ap.n_pairs);
-        for (int i = 0; i < ap.n_pairs; ++i) {
-            const double *row = ap.pedigree + 4 * (size_t)i;
-            const int t0 = as_i8(row[0]), t1 = as_i8(row[1]), t2 = as_i8(row[2]);
-            if (t0 < 0 || t1 < t0 || t2 < t0) {
-                set_error("problem " + std::to_string(p) + " row " + std::to_string(i) +
-                          ": needs 0 <= t0 <= t1,t2 <= 127 (the reference would invert the matrix)");
-                return ABFIT_ERR_TIME;
-            }
-            key[i] = Tri(t0, t1 - t0, t2 - t0);
-            key32[i] = (uint32_t)t0 | ((uint32_t)(t1 - t0) << 8) | ((uint32_t)(t2 - t0) << 16);
-            max_exp = std::max(max_exp, std::max(t0, std::max(t1 - t0, t2 - t0)));
-            if (row[3] != row[3]) hp.d_has_nan[p] = 1;
-            hp.D.push_back(row[3]);
-        }
-        if (prev_p >= 0 && key32 == prev_key32) {
+        const uint32_t *key32 = keys.data() + pair_off[p];
+        const int max_exp = max_exp_of[p];
+        if (prev_p >= 0 && probs[prev_p].n_pairs == ap.n_pairs &&
+            std::memcmp(key32, keys.data() + pair_off[prev_p], (size_t)ap.n_pairs * 4) == 0) {
             const DevProblem &q = hp.probs[prev_p];
             dp.offs_off = q.offs_off;
             dp.ops_off = q.ops_off;
@@ -126,11 +168,14 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
             hp.tmax[p] = hp.tmax[prev_p];
             hp.n_triples[p] = hp.n_triples[prev_p];
             hp.flops[p] = hp.flops[prev_p];
-            hp.max_pairs = std::max(hp.max_pairs, ap.n_pairs);
             continue;
         }
-        prev_key32 = key32;
         prev_p = p;
+        // ---- distinct triples --------------------------------------------------------------
+        std::vector<Tri> key(ap.n_pairs);
+        std::map<Tri, int> tri_id;
+        for (int i = 0; i < ap.n_pairs; ++i)
+            key[i] = Tri((int)(key32[i] & 0xff), (int)((key32[i] >> 8) & 0xff), (int)((key32[i] >> 16) & 0xff));
         for (int i = 0; i < ap.n_pairs; ++i) tri_id.emplace(key[i], 0);
         int U = 0;
         for (auto &kv : tri_id) kv.second = U++;
@@ -252,7 +297,6 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
         hp.tmax[p] = max_exp;
         hp.n_triples[p] = U;
         hp.flops[p] = 45.0 * (max_exp > 1 ? max_exp - 1 : 0) + 56.0 * U + 5.0 * ap.n_pairs + 40.0;
-        hp.max_pairs = std::max(hp.max_pairs, ap.n_pairs);
     }
     return 0;
 }
