@@ -576,10 +576,15 @@ int abfit_batch_run_boot(abfit_batch *b, int32_t max_iters, double sd_tol, uint3
                                           b->d_evals_boot.p, b->shape.smem_wide, b->d_booterr.p))
             return rc;
     } else if (b->shape.smem_boot_gather) {
+        double *bx = nullptr;
+        if (b->shape.boot_x_global) {
+            if (int rc = b->d_xscratch.ensure((size_t)std::max(b->n_boot_items, 1) * 20 * 32)) return rc;
+            bx = b->d_xscratch.p;
+        }
         if (int rc = launch_fit_boot_gather(st, b->pools, b->d_boot_items.p, b->n_boot_items, b->n_boot, b->d_best.p,
                                             b->d_pred.p, b->d_resid.p, b->d_idx.p, b->d_vary.p, b->d_scratch.p,
                                             (int64_t)((b->hp.max_pairs + 3) / 4) * 32, nm, b->d_rows.p, b->d_bootfits.p,
-                                            b->d_evals_boot.p, b->shape.smem_boot_gather, b->d_booterr.p))
+                                            b->d_evals_boot.p, b->shape.smem_boot_gather, b->d_booterr.p, bx))
             return rc;
     } else {
         BigScratch big;

@@ -545,12 +545,12 @@ k_fit_boot_gather(DevicePools P, const WorkItem *__restrict__ items, int n_boot,
                   const int32_t *__restrict__ resample_idx, const double *__restrict__ vary,
                   uint2 *__restrict__ idx_scratch, long long scratch_stride, NMParams nm,
                   double *__restrict__ rows_out, abfit_fit *__restrict__ fits_out,
-                  unsigned long long *__restrict__ evals_per_prob, int *__restrict__ err_flag)
+                  unsigned long long *__restrict__ evals_per_prob, int *__restrict__ err_flag, double *x_scratch)
 {
     const int lane = threadIdx.x;
     const WorkItem it = items[blockIdx.x];
     const DevProblem pb = P.probs[it.prob];
-    Carved cv = carve_and_stage<false>(pb, P, 25, nullptr, boot_gather_lead(pb.n_pairs));
+    Carved cv = carve_and_stage<false>(pb, P, x_scratch ? 5 : 25, x_scratch, boot_gather_lead(pb.n_pairs));
     // resid / pred of this window at the start of shared memory
     extern __shared__ double smem_lead[];
     const int npad = (pb.n_pairs + 1) & ~1;
@@ -902,13 +902,13 @@ int launch_fit_boot_gather(cudaStream_t st, const DevicePools &P, const WorkItem
                            const abfit_fit *best, const double *pred, const double *resid, const int32_t *resample_idx,
                            const double *vary, void *idx_scratch, int64_t scratch_stride, NMParams nm,
                            double *rows_out, abfit_fit *fits_out, unsigned long long *evals_per_prob, size_t smem_bytes,
-                           int *err_flag)
+                           int *err_flag, double *x_scratch)
 {
     if (n_items <= 0) return 0;
     if (int rc = prep_kernel(k_fit_boot_gather, smem_bytes)) return rc;
     k_fit_boot_gather<<<n_items, 32, smem_bytes, st>>>(P, items, n_boot, best, pred, resid, resample_idx, vary,
                                                        static_cast<uint2 *>(idx_scratch), (long long)scratch_stride, nm,
-                                                       rows_out, fits_out, evals_per_prob, err_flag);
+                                                       rows_out, fits_out, evals_per_prob, err_flag, x_scratch);
     ABFIT_CUDA(cudaGetLastError());
     return 0;
 }

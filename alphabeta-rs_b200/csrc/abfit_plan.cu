@@ -46,9 +46,9 @@ size_t smem_need_wide(const DevProblem &pb)
     return ((size_t)wide_warp_doubles(pb.tmax, pb.n_trip) * 8 + (size_t)pb.n_trip * 4 + 15) & ~(size_t)15;
 }
 
-size_t smem_need_boot_gather(const DevProblem &pb)
+size_t smem_need_boot_gather(const DevProblem &pb, int simplex_doubles)
 {
-    return smem_need(pb, 25, false, 1) + (size_t)boot_gather_lead(pb.n_pairs) * 8;
+    return smem_need(pb, simplex_doubles, false, 1) + (size_t)boot_gather_lead(pb.n_pairs) * 8;
 }
 
 // run f(p) for p in [0, n) on the host's cores (row scans of large batches; small ones stay on the caller's thread)
@@ -397,10 +397,21 @@ int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm,
         return 0;
     }
     out.smem_boot_gather = 0;
+    out.boot_x_global = false;
     if (hp.max_pairs <= 8191) {  // u16 byte offsets into resid
-        size_t m = 0;
-        for (auto &pb : hp.probs) m = std::max(m, smem_need_boot_gather(pb));
-        if (m <= smem_cap / 4 && !getenv("ABFIT_DEV_BOOT_TILE")) out.smem_boot_gather = m;  // else: stored-D* kernel
+        size_t m25 = 0, m5 = 0;
+        for (auto &pb : hp.probs) {
+            m25 = std::max(m25, smem_need_boot_gather(pb, 25));
+            m5 = std::max(m5, smem_need_boot_gather(pb, 5));
+        }
+        if (m25 <= smem_cap / 4 && !getenv("ABFIT_DEV_BOOT_TILE")) {  // else: stored-D* kernel
+            // one-warp blocks, 158 registers: at most 12 fit on an SM.  The simplex vertices move to a global scratch
+            // area when that buys resident warps (measured on the C4 shape: 8 -> 11 warps per SM, bootstrap -4 %)
+            const size_t b25 = std::min<size_t>(12, smem_per_sm / (m25 + 1024)), b5 = std::min<size_t>(12, smem_per_sm / (m5 + 1024));
+            const char *fx = getenv("ABFIT_DEV_BOOT_XGLOBAL");
+            out.boot_x_global = fx ? atoi(fx) != 0 : b5 > b25;
+            out.smem_boot_gather = out.boot_x_global ? m5 : m25;
+        }
     }
     return 0;
 }

@@ -33,6 +33,7 @@ struct LaunchShape {
     size_t smem_fit = 0;    // k_fit_starts
     size_t smem_boot = 0;   // k_fit_boot (1 warp, D* comes from the scratch tile)
     size_t smem_boot_gather = 0;  // k_fit_boot_gather (1 warp + pred/resid of the window), 0 = not usable
+    bool boot_x_global = false;   // k_fit_boot_gather keeps the simplex vertices in global scratch (more resident warps)
     size_t smem_aux = 0;    // k_select / k_cost_batch / k_model_div (1 warp, no simplex)
     bool d_shared_aux = true;
     // warp-per-fit kernels (abfit_wide.cuh) replace the global-scratch variant of the Nelder-Mead kernels whenever

@@ -526,7 +526,8 @@ def test_c4_full_size_properties(ab, ctx, oracle, ped351):
 
 @pytest.mark.parametrize("env", [{"ABFIT_DEV_NWARPS": "4"}, {"ABFIT_DEV_NWARPS": "2"}, {"ABFIT_DEV_NWARPS": "1"},
                                  {"ABFIT_DEV_XGLOBAL": "1"}, {"ABFIT_DEV_BOOT_TILE": "1"}, {"ABFIT_DEV_CHUNK": "40"},
-                                 {"ABFIT_DEV_BIG": "1", "ABFIT_DEV_WIDE": "0"}, {"ABFIT_DEV_WIDE": "1"}])
+                                 {"ABFIT_DEV_BIG": "1", "ABFIT_DEV_WIDE": "0"}, {"ABFIT_DEV_WIDE": "1"},
+                                 {"ABFIT_DEV_BOOT_XGLOBAL": "0"}, {"ABFIT_DEV_BOOT_XGLOBAL": "1"}])
 def test_kernel_variants_are_bit_identical(ab, ctx, ped351, ped78, monkeypatch, env):
     """every launch shape the library can choose (warps per block, queue chunking with tail hand-off, simplex vertices
     in shared / global memory, stored-D* / index-tile bootstrap, global-scratch lane state, warp-per-fit) returns the
