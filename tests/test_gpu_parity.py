@@ -133,6 +133,31 @@ def test_fit_c1_real_pedigrees_bitwise(ab, ctx, oracle, ped78):
     assert abs(res.best[1]["theta"][1] - 0.00655710970515347) < 0.1 * 0.00655710970515347
 
 
+@pytest.mark.parametrize("n_starts,n_boot", [(1, 1), (33, 31), (97, 100), (257, 7)])
+def test_ragged_start_and_replicate_counts(ab, ctx, oracle, ped78, ped351, n_starts, n_boot):
+    """start / replicate counts that do not fill warps, queues or hand-off groups evenly; three different pedigrees
+    in one batch; every start and every bootstrap row bit-identical to the oracle"""
+    rng = np.random.default_rng(100 * n_starts + n_boot)
+    cases = [ped78, synth_problem(rng, ped351), synth_problem(rng, ped351, n_keep=37)]
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    res = ctx.fit_batch(probs, sx, max_iters=10000)
+    idx = np.concatenate([ab.gen_resample_idx(SEED, i, n_boot, len(p)).ravel() for i, (p, u) in enumerate(cases)])
+    vary = np.stack([ab.gen_vary_vertices(SEED, i, n_boot, res.best[i]["theta"]) for i in range(len(cases))])
+    rows, fits = ctx.boot_batch(probs, res.best, res.pred, res.resid, idx, vary, max_iters=1000)
+    off = 0
+    flags = oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL
+    for i, (p, u) in enumerate(cases):
+        n = len(p)
+        check_fit_against_oracle(ab, oracle, res, i, oracle.Problem(p, u, u, 1.0), sx[i], 10000, flags, off, n)
+        rc, orows, ofits = oracle.boot_model(oracle.Problem(p, u, u, 1.0), res.best[i]["theta"], res.pred[off:off + n],
+                                             res.resid[off:off + n], idx[off * n_boot:(off + n) * n_boot].reshape(n_boot, n),
+                                             vary[i], max_iters=1000, flags=flags, n_threads=8)
+        assert rc == 0 and np.array_equal(rows[i], orows)
+        assert np.array_equal(fits[i]["evals"], ofits["evals"])
+        off += n
+
+
 def test_fit_synthetic_windows_bitwise(ab, ctx, oracle, ped351):
     """C4-shaped windows (N=351, U=10, Tmax=32) + ragged ones; every start of every window bit-identical"""
     rng = np.random.default_rng(42)
