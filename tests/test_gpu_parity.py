@@ -499,6 +499,43 @@ def test_c5_large_pedigree_fit(ab, ctx, oracle):
         assert np.array_equal(fits[0][f], ofits[f]), f
 
 
+def test_c5_chain_methylomes_to_fit(ab, ctx, oracle):
+    """BASELINE configs[4] end to end at a reduced site count: 200 simulated methylomes (10 lineages x 20 generations
+    from one founder) -> observed divergence of all 19 900 pairs + p0uu on the GPU -> pedigree -> ABneutral fit with
+    the warp-per-fit kernels; every stage against the oracle on the same inputs"""
+    rng = np.random.default_rng(2024)
+    lineages, generations, L = 10, 20, 20_000
+    founder = rng.choice(np.array([0, 2], dtype=np.uint8), size=L, p=[0.7, 0.3])
+    rows = []
+    for _ in range(lineages):
+        cur = founder.copy()
+        for _g in range(generations):
+            r = rng.random(L)
+            cur = np.where((cur == 0) & (r < 4e-3), 2, np.where((cur == 2) & (r < 1.5e-2), 0, cur)).astype(np.uint8)
+            rows.append(cur.copy())
+    status = np.stack(rows)
+    S = len(status)
+    post = np.where(rng.random((S, L)) < 0.9, 0.9999, rng.uniform(0.5, 0.99, (S, L)))
+    meth = np.clip(status / 2.0 + rng.normal(0, 0.05, (S, L)), 0, 1)
+    out = ctx.dmatrix(status, post, meth, 0.99)
+    D, diff, cnt = oracle.dmatrix(status, post, 0.99)
+    assert np.array_equal(out["diff"][0], diff) and np.array_equal(out["cnt"][0], cnt) and np.array_equal(out["D"][0], D)
+    p0, _, _ = oracle.p0uu(post, meth, 0.99)
+    assert abs(out["p0uu"][0] - p0) <= 1e-12 * abs(p0)
+    ped = c5_pedigree(rng, lineages, generations)
+    ped[:, 3] = out["D"][0]
+    p0uu = float(out["p0uu"][0])
+    n_starts = 12
+    sx = ab.gen_start_simplices(SEED, 0, n_starts, float(ped[:, 3].max()))
+    res = ctx.fit_batch([ab.Problem(ped, p0uu, p0uu, 1.0)], sx[None], max_iters=10000)
+    assert res.status[0] == 0
+    check_fit_against_oracle(ab, oracle, res, 0, oracle.Problem(ped, p0uu, p0uu, 1.0), sx, 10000,
+                             oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, 0, len(ped))
+    # the simulated rates are recovered to within a factor of two
+    a, b = res.best[0]["theta"][:2]
+    assert 2e-3 < a < 8e-3 and 7e-3 < b < 3e-2, (a, b)
+
+
 # ---------------------------------------------------------------------------------------------
 # C4 at BASELINE.json's full size, through size-independent properties
 # ---------------------------------------------------------------------------------------------
