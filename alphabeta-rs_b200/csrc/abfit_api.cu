@@ -64,6 +64,11 @@ struct abfit_ctx {
     // workspace of the one-shot host-buffer calls: device buffers are kept between calls
     // (cudaMalloc/cudaFree of multi-GB buffers costs more than the kernels of a small batch)
     abfit_batch *scratch = nullptr;
+    // observed divergence: pass-to-pass scratch and result buffers, kept between calls
+    DivArena div_arena;
+    DevBuf<double> dv_D, dv_methsum, dv_p0uu;
+    DevBuf<unsigned long long> dv_diff, dv_cnt;
+    DevBuf<long long> dv_nvalid;
 };
 
 struct abfit_batch {
@@ -181,6 +186,7 @@ void abfit_ctx_destroy(abfit_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->scratch) abfit_batch_destroy(ctx->scratch);
+    if (ctx->div_arena.p) cudaFree(ctx->div_arena.p);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
@@ -848,10 +854,11 @@ static int divergence_impl(abfit_ctx *ctx, bool device_inputs, const uint8_t *st
     cudaStream_t st = ctx->stream;
     const size_t n = (size_t)S * (size_t)L;
     const size_t P = (size_t)S * (S - 1) / 2;
-    DevBuf<uint8_t> d_status;
-    DevBuf<double> d_post, d_meth, d_D, d_methsum, d_p0uu;
-    DevBuf<unsigned long long> d_diff, d_cnt;
-    DevBuf<long long> d_nvalid;
+    DevBuf<uint8_t> d_status;  // host-input path: freed at the end of the call (whole methylomes can be many GB)
+    DevBuf<double> d_post, d_meth;
+    DevBuf<double> &d_D = ctx->dv_D, &d_methsum = ctx->dv_methsum, &d_p0uu = ctx->dv_p0uu;
+    DevBuf<unsigned long long> &d_diff = ctx->dv_diff, &d_cnt = ctx->dv_cnt;
+    DevBuf<long long> &d_nvalid = ctx->dv_nvalid;
     if (!device_inputs) {
         if (int rc = d_status.ensure(n)) return rc;
         if (int rc = d_post.ensure(n)) return rc;
@@ -871,7 +878,7 @@ static int divergence_impl(abfit_ctx *ctx, bool device_inputs, const uint8_t *st
     int launches = 0;
     if (int rc = run_divergence(st, device_inputs ? status : d_status.p, device_inputs ? posterior_max : d_post.p,
                                 device_inputs ? meth_lvl : d_meth.p, S, L, seg_offsets, W, thr, d_D.p, d_diff.p,
-                                d_cnt.p, d_methsum.p, d_nvalid.p, d_p0uu.p, &launches, ms_out))
+                                d_cnt.p, d_methsum.p, d_nvalid.p, d_p0uu.p, &launches, ms_out, &ctx->div_arena))
         return rc;
     if (launches_out) *launches_out = launches;
     if (D_out && P) ABFIT_CUDA(cudaMemcpyAsync(D_out, d_D.p, (size_t)W * P * 8, cudaMemcpyDeviceToHost, st));

@@ -268,7 +268,7 @@ __global__ void k_p0uu(const double *__restrict__ methsum, const long long *__re
 int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_post, const double *d_meth, int S,
                    int64_t L, const int64_t *h_seg, int W, double thr, double *d_D, unsigned long long *d_diff,
                    unsigned long long *d_cnt, double *d_methsum, long long *d_nvalid, double *d_p0uu,
-                   int *launches, float *ms)
+                   int *launches, float *ms, DivArena *arena)
 {
     // host-side segmentation tables
     std::vector<SuperBlock> sbs;
@@ -349,7 +349,7 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
             for (int j = i; j < nb; ++j) pairtab[t++] = make_ushort2((unsigned short)i, (unsigned short)j);
     }
 
-    // device scratch
+    // device scratch: one arena, carved at 256-byte boundaries
     unsigned long long *d_V = nullptr, *d_T1 = nullptr, *d_T2 = nullptr;
     double *d_methpart = nullptr;
     long long *d_nvpart = nullptr;
@@ -359,9 +359,10 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
     PairItem *d_items = nullptr;
     ushort2 *d_pairtab = nullptr;
     int rc = 0;
+    DivArena local_arena;
+    DivArena *ar = arena ? arena : &local_arena;
     auto cleanup = [&]() {
-        cudaFree(d_V); cudaFree(d_T1); cudaFree(d_T2); cudaFree(d_methpart); cudaFree(d_nvpart);
-        cudaFree(d_sbs); cudaFree(d_sbfirst); cudaFree(d_seg); cudaFree(d_items); cudaFree(d_pairtab);
+        if (!arena && local_arena.p) cudaFree(local_arena.p);
     };
 #define DV_CUDA(call)                                   \
     do {                                                \
@@ -373,16 +374,40 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
         }                                               \
     } while (0)
     const size_t plane = (size_t)S * (size_t)std::max<int64_t>(TW, 1) * 8;
-    DV_CUDA(cudaMalloc(&d_V, plane));
-    DV_CUDA(cudaMalloc(&d_T1, plane));
-    DV_CUDA(cudaMalloc(&d_T2, plane));
-    DV_CUDA(cudaMalloc(&d_methpart, (size_t)S * std::max(n_sb, 1) * 8));
-    DV_CUDA(cudaMalloc(&d_nvpart, (size_t)S * std::max(n_sb, 1) * 8));
-    DV_CUDA(cudaMalloc(&d_sbs, std::max<size_t>(sbs.size(), 1) * sizeof(SuperBlock)));
-    DV_CUDA(cudaMalloc(&d_sbfirst, (size_t)(W + 1) * 4));
-    DV_CUDA(cudaMalloc(&d_seg, (size_t)(W + 1) * 8));
-    DV_CUDA(cudaMalloc(&d_items, std::max<size_t>(items.size(), 1) * sizeof(PairItem)));
-    DV_CUDA(cudaMalloc(&d_pairtab, std::max<size_t>(pairtab.size(), 1) * sizeof(ushort2)));
+    {
+        size_t off = 0;
+        auto take = [&](size_t bytes) {
+            const size_t o = off;
+            off += (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+            return o;
+        };
+        const size_t o_V = take(plane), o_T1 = take(plane), o_T2 = take(plane);
+        const size_t o_mp = take((size_t)S * std::max(n_sb, 1) * 8), o_nv = take((size_t)S * std::max(n_sb, 1) * 8);
+        const size_t o_sbs = take(sbs.size() * sizeof(SuperBlock)), o_sbf = take((size_t)(W + 1) * 4);
+        const size_t o_seg = take((size_t)(W + 1) * 8), o_it = take(items.size() * sizeof(PairItem));
+        const size_t o_pt = take(pairtab.size() * sizeof(ushort2));
+        if (off > ar->cap) {
+            if (ar->p) {
+                DV_CUDA(cudaStreamSynchronize(st));  // earlier work on this stream may still read the old arena
+                DV_CUDA(cudaFree(ar->p));
+                ar->p = nullptr;
+                ar->cap = 0;
+            }
+            DV_CUDA(cudaMalloc(&ar->p, off));
+            ar->cap = off;
+        }
+        char *base = static_cast<char *>(ar->p);
+        d_V = reinterpret_cast<unsigned long long *>(base + o_V);
+        d_T1 = reinterpret_cast<unsigned long long *>(base + o_T1);
+        d_T2 = reinterpret_cast<unsigned long long *>(base + o_T2);
+        d_methpart = reinterpret_cast<double *>(base + o_mp);
+        d_nvpart = reinterpret_cast<long long *>(base + o_nv);
+        d_sbs = reinterpret_cast<SuperBlock *>(base + o_sbs);
+        d_sbfirst = reinterpret_cast<int32_t *>(base + o_sbf);
+        d_seg = reinterpret_cast<int64_t *>(base + o_seg);
+        d_items = reinterpret_cast<PairItem *>(base + o_it);
+        d_pairtab = reinterpret_cast<ushort2 *>(base + o_pt);
+    }
     if (!sbs.empty())
         DV_CUDA(cudaMemcpyAsync(d_sbs, sbs.data(), sbs.size() * sizeof(SuperBlock), cudaMemcpyHostToDevice, st));
     DV_CUDA(cudaMemcpyAsync(d_sbfirst, sb_first.data(), (size_t)(W + 1) * 4, cudaMemcpyHostToDevice, st));

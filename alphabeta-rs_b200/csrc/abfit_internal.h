@@ -85,10 +85,17 @@ int launch_fp64_peak(cudaStream_t st, int blocks, int threads, int iters, double
 int max_dynamic_smem(int device);
 
 // ---- divergence (abfit_divergence.cu) -------------------------------------------------
+// grow-only device arena for the pass-to-pass scratch (bit-planes, tables): owned by the context, so repeated
+// calls stop paying cudaMalloc / cudaFree (tens of milliseconds against a few milliseconds of kernels)
+struct DivArena {
+    void *p = nullptr;
+    size_t cap = 0;
+};
 // h_seg is a HOST array [W+1]; every other pointer is device memory. d_p0uu [W] may be null.
 int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_post, const double *d_meth, int S,
                    int64_t L, const int64_t *h_seg, int W, double thr, double *d_D, unsigned long long *d_diff,
                    unsigned long long *d_cnt, double *d_methsum, long long *d_nvalid, double *d_p0uu,
-                   int *launches, float *ms /* optional [2]: pack pass, pair pass + finalisation */);
+                   int *launches, float *ms /* optional [2]: pack pass, pair pass + finalisation */,
+                   DivArena *arena = nullptr /* null: allocate and free inside the call */);
 
 }  // namespace abfit
