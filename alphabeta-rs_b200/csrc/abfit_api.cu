@@ -268,23 +268,6 @@ int abfit_measure_fp64_peak(abfit_ctx *ctx, double *tflops_out)
 // ---------------------------------------------------------------------------------------
 // input generators (host; counter-based so shards can be produced independently)
 // ---------------------------------------------------------------------------------------
-static inline uint64_t mix64(uint64_t z)
-{
-    z += 0x9e3779b97f4a7c15ull;
-    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-    return z ^ (z >> 31);
-}
-static inline double u01(uint64_t seed, uint64_t stream, uint64_t problem, uint64_t item, uint64_t sub)
-{
-    uint64_t h = mix64(seed ^ (stream * 0xd1342543de82ef95ull));
-    h = mix64(h ^ problem);
-    h = mix64(h ^ item);
-    h = mix64(h ^ sub);
-    return (double)(h >> 11) * (1.0 / 9007199254740992.0);  // [0,1)
-}
-static inline double uniform(double lo, double hi, double u) { return lo + (hi - lo) * u; }
-
 void abfit_gen_start_simplices(uint64_t seed, uint64_t problem_id, int32_t n_starts, double max_divergence,
                                double *out)
 {
@@ -306,11 +289,7 @@ void abfit_gen_vary_vertices(uint64_t seed, uint64_t problem_id, int32_t n_boot,
     for (int32_t b = 0; b < n_boot; ++b)
         for (int v = 0; v < 4; ++v)
             for (int j = 0; j < 4; ++j) {
-                double n = best_theta[j];
-                if (n == 0.0) n = 0.1;  // src/structs.rs:105-108
-                double lo = n - std::fabs(n) * 0.1, hi = n + std::fabs(n) * 0.1;
-                if (lo >= hi) std::swap(lo, hi);  // src/structs.rs:113-115
-                out[((size_t)b * 4 + v) * 4 + j] = uniform(lo, hi, u01(seed, 2, problem_id, (uint64_t)b, v * 4 + j));
+                out[((size_t)b * 4 + v) * 4 + j] = vary_coordinate(seed, problem_id, (uint64_t)b, v, j, best_theta[j]);
             }
 }
 
@@ -408,13 +387,16 @@ void abfit_batch_destroy(abfit_batch *b)
     delete b;
 }
 
-int abfit_batch_upload_starts(abfit_batch *b, int32_t n_starts, const double *simplices)
+// simplices == nullptr: the caller has already put them into b->d_simplices (abfit_alphabeta_batch starts that
+// copy before the pedigrees are compiled)
+static int upload_starts_impl(abfit_batch *b, int32_t n_starts, const double *simplices)
 {
-    if (!b || !simplices || n_starts <= 0) return ABFIT_ERR_ARG;
     ABFIT_CUDA(cudaSetDevice(b->ctx->device));
     const size_t n = (size_t)b->n_probs * n_starts * 20;
-    if (int rc = b->d_simplices.ensure(n)) return rc;
-    ABFIT_CUDA(cudaMemcpyAsync(b->d_simplices.p, simplices, n * 8, cudaMemcpyHostToDevice, b->ctx->stream));
+    if (simplices) {
+        if (int rc = b->d_simplices.ensure(n)) return rc;
+        ABFIT_CUDA(cudaMemcpyAsync(b->d_simplices.p, simplices, n * 8, cudaMemcpyHostToDevice, b->ctx->stream));
+    }
     if (n_starts != b->n_starts) {
         b->n_starts = n_starts;
         if (int rc = choose_launch_shape(b->hp, (size_t)b->ctx->smem_optin,
@@ -439,6 +421,12 @@ int abfit_batch_upload_starts(abfit_batch *b, int32_t n_starts, const double *si
     }
     b->fit_done = false;
     return 0;
+}
+
+int abfit_batch_upload_starts(abfit_batch *b, int32_t n_starts, const double *simplices)
+{
+    if (!b || !simplices || n_starts <= 0) return ABFIT_ERR_ARG;
+    return upload_starts_impl(b, n_starts, simplices);
 }
 
 int abfit_batch_run_fit(abfit_batch *b, int32_t max_iters, double sd_tol, uint32_t flags)
@@ -720,31 +708,54 @@ int abfit_alphabeta_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_
                           int32_t *prob_status_out, double *rows_out, double *analysis_out)
 {
     if (!simplices || !resample_idx || n_starts <= 0 || n_boot <= 0 || !rows_out) return ABFIT_ERR_ARG;
-    abfit_batch *b = nullptr;
+    if (!ctx || n_probs <= 0) return ABFIT_ERR_ARG;
+    ABFIT_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->scratch) {
+        ctx->scratch = new abfit_batch();
+        ctx->scratch->ctx = ctx;
+    }
+    abfit_batch *b = ctx->scratch;
+    cudaStream_t st = ctx->stream;
+    // the start simplices (the bulk of the fit's input) cross PCIe while the host compiles the pedigrees
+    const size_t n_sx = (size_t)n_probs * n_starts * 20;
+    if (b->d_simplices.n < n_sx || !b->d_simplices.p) {
+        ABFIT_CUDA(cudaStreamSynchronize(st));  // the buffer is about to be reallocated
+        if (int rc = b->d_simplices.ensure(n_sx)) return rc;
+    }
+    ABFIT_CUDA(cudaMemcpyAsync(b->d_simplices.p, simplices, n_sx * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    ABFIT_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
     if (int rc = workspace(ctx, probs, n_probs, &b)) return rc;
     if (int rc = boot_alloc(b, n_boot)) return rc;  // before any kernel is enqueued: it may synchronise
-    if (int rc = abfit_batch_upload_starts(b, n_starts, simplices)) return rc;
+    if (int rc = upload_starts_impl(b, n_starts, nullptr)) return rc;
+    ABFIT_CUDA(cudaStreamWaitEvent(st, ctx->copy_done, 0));
     if (int rc = abfit_batch_run_fit(b, max_iters_fit, sd_tol, flags)) return rc;
     // the resample indices (the bulk of the bootstrap's input) cross PCIe under the multi-start kernel
     ABFIT_CUDA(cudaMemcpyAsync(b->d_idx.p, resample_idx, (size_t)b->total_pairs * n_boot * 4, cudaMemcpyHostToDevice,
                                ctx->copy_stream));
     ABFIT_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
-    std::vector<abfit_fit> best_local;
-    if (!best_out) {
-        best_local.resize(n_probs);
-        best_out = best_local.data();
-    }
-    if (int rc = abfit_batch_download_fit(b, best_out, nullptr, pred_out, resid_out, prob_status_out)) return rc;
-    // Model::vary x 4 per replicate around each window's best model (src/boot_model.rs:69-75), drawn on the host
-    std::vector<double> vary((size_t)n_probs * n_boot * 16);
-    abfit_gen_vary_vertices_batch(vary_seed, first_problem_id, n_probs, n_boot, best_out, vary.data());
-    cudaStream_t st = ctx->stream;
-    ABFIT_CUDA(cudaMemcpyAsync(b->d_vary.p, vary.data(), vary.size() * 8, cudaMemcpyHostToDevice, st));
+    // Model::vary x 4 per replicate around each window's best model (src/boot_model.rs:69-75): drawn on the device
+    // right behind the selection kernel — the same numbers abfit_gen_vary_vertices gives on the host — so the
+    // bootstrap starts without a round trip through the host
+    if (int rc = launch_gen_vary(st, vary_seed, first_problem_id, n_probs, n_boot, b->d_best.p, b->d_vary.p)) return rc;
     ABFIT_CUDA(cudaStreamWaitEvent(st, ctx->copy_done, 0));
     b->boot_uploaded = true;
     b->boot_done = false;
     if (int rc = abfit_batch_run_boot(b, max_iters_boot, sd_tol, flags)) return rc;
-    if (int rc = abfit_batch_download_boot(b, rows_out, nullptr)) return rc;  // synchronises: `vary` may go out of scope
+    // results of the fit come back while the bootstrap runs (copy stream, behind the selection kernel's event)
+    {
+        ABFIT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, b->ev[2], 0));
+        cudaStream_t cs = ctx->copy_stream;
+        if (best_out)
+            ABFIT_CUDA(cudaMemcpyAsync(best_out, b->d_best.p, (size_t)n_probs * sizeof(abfit_fit), cudaMemcpyDeviceToHost, cs));
+        if (pred_out)
+            ABFIT_CUDA(cudaMemcpyAsync(pred_out, b->d_pred.p, (size_t)b->total_pairs * 8, cudaMemcpyDeviceToHost, cs));
+        if (resid_out)
+            ABFIT_CUDA(cudaMemcpyAsync(resid_out, b->d_resid.p, (size_t)b->total_pairs * 8, cudaMemcpyDeviceToHost, cs));
+        if (prob_status_out)
+            ABFIT_CUDA(cudaMemcpyAsync(prob_status_out, b->d_status.p, (size_t)n_probs * 4, cudaMemcpyDeviceToHost, cs));
+        ABFIT_CUDA(cudaStreamSynchronize(cs));
+    }
+    if (int rc = abfit_batch_download_boot(b, rows_out, nullptr)) return rc;
     if (analysis_out) {
         std::vector<int> rcs(n_probs, 0);
         parallel_for(n_probs, [&](int32_t p) {

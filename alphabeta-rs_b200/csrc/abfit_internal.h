@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "abfit_nm.cuh"
+#include "abfit_rng.h"
 
 namespace abfit {
 
@@ -81,6 +82,10 @@ int launch_cost_batch(cudaStream_t st, const DevicePools &P, const WorkItem *ite
                       const BigScratch &big);
 int launch_model_divergence(cudaStream_t st, const DevicePools &P, const double *theta4, double *dt_out,
                             double *puu_out, size_t smem_bytes, const BigScratch &big);
+// vary vertices of every (window, replicate) drawn on the device from the best fits (same numbers as
+// abfit_gen_vary_vertices): out[n_probs][n_boot][4][4]
+int launch_gen_vary(cudaStream_t st, uint64_t seed, uint64_t first_problem_id, int n_probs, int n_boot,
+                    const abfit_fit *best, double *out);
 int launch_fp64_peak(cudaStream_t st, int blocks, int threads, int iters, double *sink);
 int max_dynamic_smem(int device);
 

@@ -780,6 +780,19 @@ k_model_div(DevicePools P, const double *__restrict__ theta4, double *__restrict
 // ---------------------------------------------------------------------------------
 // FP64 roofline micro-benchmark: 8 independent DFMA chains per thread
 // ---------------------------------------------------------------------------------
+// Model::vary x 4 per bootstrap replicate (src/boot_model.rs:69-75, src/structs.rs:100-128), one thread per coordinate
+__global__ void k_gen_vary(uint64_t seed, uint64_t first_problem_id, int n_probs, int n_boot,
+                           const abfit_fit *__restrict__ best, double *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t per_prob = (size_t)n_boot * 16;
+    if (i >= (size_t)n_probs * per_prob) return;
+    const int p = (int)(i / per_prob);
+    const size_t r = i - (size_t)p * per_prob;
+    const int b = (int)(r >> 4), v = (int)((r >> 2) & 3), j = (int)(r & 3);
+    out[i] = vary_coordinate(seed, first_problem_id + (uint64_t)p, (uint64_t)b, v, j, best[p].theta[j]);
+}
+
 __global__ void k_fp64_peak(int iters, double *sink)
 {
     double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-9, a2 = a0 + 2e-9, a3 = a0 + 3e-9;
@@ -972,6 +985,16 @@ int launch_model_divergence(cudaStream_t st, const DevicePools &P, const double 
         if (int rc = prep_kernel(k_model_div<false>, smem_bytes)) return rc;
         k_model_div<false><<<1, 32, smem_bytes, st>>>(P, theta4, dt_out, puu_out, nullptr, 0);
     }
+    ABFIT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_gen_vary(cudaStream_t st, uint64_t seed, uint64_t first_problem_id, int n_probs, int n_boot,
+                    const abfit_fit *best, double *out)
+{
+    const size_t n = (size_t)n_probs * n_boot * 16;
+    if (n == 0) return 0;
+    k_gen_vary<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(seed, first_problem_id, n_probs, n_boot, best, out);
     ABFIT_CUDA(cudaGetLastError());
     return 0;
 }

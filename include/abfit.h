@@ -166,8 +166,10 @@ int abfit_boot_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs
 /* Fit, then bootstrap, every window: replaces `alphabeta::run` (src/alphabeta.rs:23-59: ab_neutral::run :33-41
  * followed by boot_model::run :42-54) for all windows of a metaprofile in one call (the reference loops the
  * windows serially, src/cli/metaprofile.rs:50-72).  The vary vertices depend on each window's best model; they are
- * drawn on the host (abfit_gen_vary_vertices, problem id = first_problem_id + window) once the best-of-starts
- * are back, while the resample indices cross PCIe under the multi-start kernel.
+ * the numbers abfit_gen_vary_vertices(vary_seed, first_problem_id + window, ...) returns, drawn on the device right
+ * behind the best-of-starts selection (same counter-based generator, same bits), so the bootstrap starts without a
+ * round trip through the host.  The start simplices cross PCIe while the host compiles the pedigrees, the resample
+ * indices under the multi-start kernel, and the fit results come back under the bootstrap kernel.
  *  rows_out      [n_probs][n_boot][7]   (required)
  *  analysis_out  [n_probs][32]          RawAnalysis::analyze per window (may be NULL)
  *  best_out, pred_out, resid_out, prob_status_out as in abfit_fit_batch (may be NULL) */
