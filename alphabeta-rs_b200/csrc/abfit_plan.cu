@@ -409,7 +409,9 @@ int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm,
             // area when that buys resident warps (measured on the C4 shape: 8 -> 11 warps per SM, bootstrap -4 %)
             const size_t b25 = std::min<size_t>(12, smem_per_sm / (m25 + 1024)), b5 = std::min<size_t>(12, smem_per_sm / (m5 + 1024));
             const char *fx = getenv("ABFIT_DEV_BOOT_XGLOBAL");
-            out.boot_x_global = fx ? atoi(fx) != 0 : b5 > b25;
+            // ... and only when there are more blocks than resident slots (one block per window and ~128 replicates):
+            // a batch that is resident all at once gains nothing and pays the global-memory vertices
+            out.boot_x_global = fx ? atoi(fx) != 0 : (b5 > b25 && hp.probs.size() > (size_t)148 * b25);
             out.smem_boot_gather = out.boot_x_global ? m5 : m25;
         }
     }
