@@ -14,7 +14,8 @@ a, b, w, c, p0 = 2e-4, 1e-3, 0.04, 0.002, 0.75
 dt, _ = o.divergence(o.Problem(ped, p0, p0, 1.0), a, b, w, o.FAST_DIVERGENCE)
 ped[:, 3] = np.maximum(c + dt + rng.normal(0, 5e-4, len(ped)), 0.0)
 prob = ab.Problem(ped, p0, p0, 1.0)
-NS, NB = 1000, 100
+NS = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+NB = 100
 sx = ab.gen_start_simplices(1, 0, NS, float(ped[:, 3].max()))
 idx = ab.gen_resample_idx(1, 0, NB, len(ped))
 ctx = ab.Context(0)
@@ -22,9 +23,9 @@ bt = ctx.batch([prob])
 fl = bt.flops_per_eval(0)
 print("C5 pedigree:", ped.shape, fl)
 bt.upload_starts(sx[None])
-for rep in range(2):
+for rep in range(2 if NS <= 4000 else 1):
     bt.run_fit(); tm = bt.timing()
-    print("fit 1000 starts: %.1f ms, evals/fit %.0f, %.2f TFLOP/s" % (tm["fit_ms"], tm["evals_fit"] / NS, tm["evals_fit"] * fl["flops"] / tm["fit_ms"] / 1e9))
+    print("fit %d starts: %.1f ms, evals/fit %.0f, %.2f TFLOP/s" % (NS, tm["fit_ms"], tm["evals_fit"] / NS, tm["evals_fit"] * fl["flops"] / tm["fit_ms"] / 1e9))
 res = bt.download_fit(want_all=True)
 ev = np.sort(res.all[0]["evals"])
 print("evals per fit: median %d, p90 %d, p99 %d, max %d -> %.1f us per evaluation on the longest fit's warp" %
