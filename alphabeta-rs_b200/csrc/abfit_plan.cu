@@ -458,7 +458,11 @@ std::vector<WorkItem> make_items(const HostPlan &hp, int count_per_prob, int n_s
     if (chunk < 2 * lanes && total >= (int64_t)n_sm * 2 * lanes) chunk = 2 * lanes;
     if (chunk > count_per_prob) chunk = count_per_prob;
     if (const char *fc = getenv("ABFIT_DEV_CHUNK")) chunk = std::max(1, std::min(atoi(fc), count_per_prob));
-    const int n_chunks = (int)((count_per_prob + chunk - 1) / chunk);
+    // nearest, not ceiling: 1000 starts against a chunk of 960 are one block, not two halves (longer queues per
+    // block even out the run lengths better than a few more blocks do)
+    // (only when a block's queue is deep: with one or two fits per lane an extra fit doubles a lane's work)
+    const int n_chunks = chunk >= 4 * lanes ? (int)std::max<int64_t>(1, (count_per_prob + chunk / 2) / chunk)
+                                            : (int)((count_per_prob + chunk - 1) / chunk);
     chunk = (count_per_prob + n_chunks - 1) / n_chunks;  // even split
     std::vector<WorkItem> items;
     for (int p = 0; p < n_probs; ++p) {

@@ -173,6 +173,27 @@ int emul_fit_wide(const abfit_problem *pb, const double *simplices, int n, const
     return 0;
 }
 
+// launch shape the library would choose on a B200 (227 KB opt-in shared memory per block, 228 KB per SM)
+int emul_launch_shape(const abfit_problem *pb, int n_probs, int fits_per_prob, int64_t out[10])
+{
+    HostPlan hp;
+    if (int rc = compile_problems(pb, n_probs, hp)) return rc;
+    LaunchShape sh;
+    if (int rc = choose_launch_shape(hp, 227 * 1024, 228 * 1024, fits_per_prob, sh)) return rc;
+    out[0] = sh.n_warps;
+    out[1] = sh.d_shared;
+    out[2] = sh.x_global;
+    out[3] = sh.big;
+    out[4] = sh.wide;
+    out[5] = sh.boot_x_global;
+    out[6] = (int64_t)sh.smem_fit;
+    out[7] = (int64_t)sh.smem_wide;
+    out[8] = (int64_t)sh.smem_boot_gather;
+    out[9] = (int64_t)(sh.wide ? make_items_wide(hp, fits_per_prob, 148, true).size()
+                               : make_items(hp, fits_per_prob, 148, sh.n_warps, true).size());
+    return 0;
+}
+
 // plan statistics: per-lane doubles, micro-ops, events, chain length
 int emul_plan_stats(const abfit_problem *pb, int32_t out[6])
 {

@@ -125,3 +125,37 @@ def test_bootstrap_column_access_matches_oracle(emul, ab, oracle):
                                        flags=oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, n_threads=4)
     assert rc == 0
     assert np.array_equal(g["theta"], fits["theta"]) and np.array_equal(g["evals"], fits["evals"])
+
+
+def emul_shape(emul, ab, peds, fits_per_prob):
+    arr = ab._pack_problems([ab.Problem(p, 0.8, 0.8, 1.0) for p in peds])
+    out = (C.c_int64 * 10)()
+    rc = emul.emul_launch_shape(arr, len(peds), fits_per_prob, out)
+    assert rc == 0, rc
+    keys = ("n_warps", "d_shared", "x_global", "big", "wide", "boot_x_global", "smem_fit", "smem_wide", "smem_boot_gather", "n_items")
+    return dict(zip(keys, [int(v) for v in out]))
+
+
+def test_launch_shapes_for_the_baseline_configs(emul, ab, oracle, monkeypatch):
+    """host-side choice of kernel variant and block shape (abfit_plan.cu) for the shapes of BASELINE.json"""
+    for k in ("ABFIT_DEV_NWARPS", "ABFIT_DEV_XGLOBAL", "ABFIT_DEV_BIG", "ABFIT_DEV_WIDE", "ABFIT_DEV_BOOT_XGLOBAL",
+              "ABFIT_DEV_BOOT_TILE", "ABFIT_DEV_CHUNK"):
+        monkeypatch.delenv(k, raising=False)
+    ped351 = oracle.load_pedigree_file(os.path.join(GOLDEN, "pedigree.txt"))
+    # C4: thousands of windows sharing one program -> 3-warp blocks, 4 per SM, one block per window; bootstrap with
+    # the vertices in global scratch because there are more windows than resident bootstrap blocks
+    c4 = emul_shape(emul, ab, [ped351] * 2000, 1000)
+    assert (c4["n_warps"], c4["d_shared"], c4["x_global"], c4["big"], c4["wide"]) == (3, 1, 0, 0, 0)
+    assert 4 * (c4["smem_fit"] + 1024) <= 228 * 1024 < 5 * (c4["smem_fit"] + 1024)
+    assert c4["n_items"] == 2000 and c4["boot_x_global"] == 1 and 0 < c4["smem_boot_gather"] < 21 * 1024
+    # a few windows: resident all at once, the bootstrap keeps its vertices in shared memory
+    assert emul_shape(emul, ab, [ped351] * 500, 1000)["boot_x_global"] == 0
+    # C1 / C2: one small pedigree x 1000 starts -> one-warp blocks spread over the SMs
+    ped6 = np.loadtxt(os.path.join(GOLDEN, "pedigree_generated.txt"), skiprows=1)
+    c1 = emul_shape(emul, ab, [ped6], 1000)
+    assert c1["n_warps"] == 1 and c1["big"] == 0 and c1["n_items"] == 32
+    # C5: 19 900 pairs, 590 triples -> per-lane state does not fit; warp-per-fit, one fit per block
+    samples = [(l, g) for l in range(10) for g in range(1, 21)]
+    rows = [[min(g1, g2) if l1 == l2 else 0, g1, g2, 0.1] for i, (l1, g1) in enumerate(samples) for (l2, g2) in samples[i + 1:]]
+    c5 = emul_shape(emul, ab, [np.array(rows, dtype=np.float64)], 1000)
+    assert c5["big"] == 1 and c5["wide"] == 1 and c5["n_items"] == 1000 and c5["smem_wide"] < 24 * 1024
