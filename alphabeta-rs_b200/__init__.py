@@ -107,6 +107,7 @@ def _load() -> C.CDLL:
         "abfit_batch_sync": (C.c_int, [vp]),
         "abfit_batch_timing": (C.c_int, [vp, vp, vp, C.POINTER(i32)]),
         "abfit_batch_flops_per_eval": (C.c_int, [vp, i32, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i32)]),
+        "abfit_batch_fp64_instr_per_eval": (C.c_int, [vp, i32, C.POINTER(dbl)]),
         "abfit_analyze": (C.c_int, [vp, i32, vp]),
         "abfit_parse_methylome_line": (C.c_int, [C.c_char_p, i32, vp, vp, vp, vp]),
         "abfit_pedigree_build": (C.c_int, [vp, C.c_char_p, C.c_char_p, dbl, C.POINTER(vp)]),
@@ -142,7 +143,7 @@ EXPORTED_SYMBOLS = (
     "abfit_model_divergence abfit_fit_batch abfit_boot_batch abfit_divergence abfit_divergence_device abfit_batch_create "
     "abfit_batch_destroy abfit_batch_upload_starts abfit_batch_run_fit abfit_batch_download_fit "
     "abfit_batch_upload_boot abfit_batch_run_boot abfit_batch_download_boot abfit_batch_sync "
-    "abfit_batch_timing abfit_batch_flops_per_eval abfit_analyze abfit_window_counts abfit_place_sites "
+    "abfit_batch_timing abfit_batch_flops_per_eval abfit_batch_fp64_instr_per_eval abfit_analyze abfit_window_counts abfit_place_sites "
     "abfit_parse_methylome_line abfit_parse_annotation_line abfit_pedigree_graph abfit_pedigree_build abfit_pedigree_info abfit_pedigree_rows abfit_pedigree_warnings "
     "abfit_pedigree_free abfit_format_f64 abfit_steady_state abfit_write_pedigree abfit_write_analysis abfit_format_analysis "
     "abfit_write_npy_f64 abfit_write_metaprofile_results"
@@ -535,7 +536,9 @@ class Batch:
     def flops_per_eval(self, p: int = 0):
         f, u, t = C.c_double(), C.c_int32(), C.c_int32()
         _check(_lib.abfit_batch_flops_per_eval(self._h, p, C.byref(f), C.byref(u), C.byref(t)))
-        return {"flops": f.value, "n_triples": u.value, "tmax": t.value}
+        n = C.c_double()
+        _check(_lib.abfit_batch_fp64_instr_per_eval(self._h, p, C.byref(n)))
+        return {"flops": f.value, "n_triples": u.value, "tmax": t.value, "fp64_instr": n.value}
 
 
 # ---------------------------------------------------------------------------------------------

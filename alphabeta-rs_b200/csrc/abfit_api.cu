@@ -586,7 +586,7 @@ int abfit_batch_run_boot(abfit_batch *b, int32_t max_iters, double sd_tol, uint3
         if (int rc = launch_fit_boot(st, b->pools, b->d_boot_items.p, b->n_boot_items, b->n_boot, b->d_best.p,
                                      b->d_pred.p, b->d_resid.p, b->d_idx.p, b->d_vary.p, b->d_scratch.p,
                                      (int64_t)b->hp.max_pairs * 32, nm, b->d_rows.p, b->d_bootfits.p,
-                                     b->d_evals_boot.p, b->shape.smem_boot, big))
+                                     b->d_evals_boot.p, b->shape.smem_boot, b->d_booterr.p, big))
             return rc;
     }
     ABFIT_CUDA(cudaEventRecord(b->ev[4], st));
@@ -659,6 +659,13 @@ int abfit_batch_flops_per_eval(abfit_batch *b, int32_t p, double *flops_out, int
     if (flops_out) *flops_out = b->hp.flops[p];
     if (n_triples_out) *n_triples_out = b->hp.n_triples[p];
     if (tmax_out) *tmax_out = b->hp.tmax[p];
+    return 0;
+}
+
+int abfit_batch_fp64_instr_per_eval(abfit_batch *b, int32_t p, double *instr_out)
+{
+    if (!b || p < 0 || p >= b->n_probs || !instr_out) return ABFIT_ERR_ARG;
+    *instr_out = b->hp.fp64_instr[p];
     return 0;
 }
 

@@ -60,7 +60,7 @@ int launch_fit_boot(cudaStream_t st, const DevicePools &P, const WorkItem *items
                     const abfit_fit *best, const double *pred, const double *resid, const int32_t *resample_idx,
                     const double *vary, double *dstar_scratch, int64_t scratch_stride, NMParams nm,
                     double *rows_out, abfit_fit *fits_out, unsigned long long *evals_per_prob, size_t smem_bytes,
-                    const BigScratch &big);
+                    int *err_flag, const BigScratch &big);
 // index-tile variant (n_pairs <= 8191): idx_scratch holds scratch_stride uint2 per block, scratch_stride >= 32 * ceil(N/4)
 size_t smem_need_boot_gather(const DevProblem &pb, int simplex_doubles);
 int launch_fit_boot_gather(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_boot,

@@ -455,7 +455,8 @@ k_fit_boot(DevicePools P, const WorkItem *__restrict__ items, int n_boot, const 
            const int32_t *__restrict__ resample_idx, const double *__restrict__ vary,
            double *__restrict__ dstar_scratch, long long scratch_stride, NMParams nm,
            double *__restrict__ rows_out, abfit_fit *__restrict__ fits_out,
-           unsigned long long *__restrict__ evals_per_prob, double *x_scratch, double *lm_scratch, size_t lm_stride)
+           unsigned long long *__restrict__ evals_per_prob, int *__restrict__ err_flag, double *x_scratch,
+           double *lm_scratch, size_t lm_stride)
 {
     const int lane = threadIdx.x;
     const WorkItem it = items[blockIdx.x];
@@ -491,8 +492,14 @@ k_fit_boot(DevicePools P, const WorkItem *__restrict__ items, int n_boot, const 
                 tm &= tm - 1;
                 const int b = __shfl_sync(FULL, idx, tl);
                 const int32_t *ib = idxp + (size_t)b * pb.n_pairs;
-                for (int i = lane; i < pb.n_pairs; i += 32)
-                    tile[(size_t)i * 32 + tl] = predp[i] + residp[ib[i]];
+                for (int i = lane; i < pb.n_pairs; i += 32) {
+                    uint32_t ix = (uint32_t)ib[i];
+                    if (ix >= (uint32_t)pb.n_pairs) {  // reported by download_boot; keeps the gather in bounds
+                        ix = 0u;
+                        *err_flag = 1;
+                    }
+                    tile[(size_t)i * 32 + tl] = predp[i] + residp[ix];
+                }
             }
             __syncwarp();
             if (take) {
@@ -893,19 +900,19 @@ int launch_fit_boot(cudaStream_t st, const DevicePools &P, const WorkItem *items
                     const abfit_fit *best, const double *pred, const double *resid, const int32_t *resample_idx,
                     const double *vary, double *dstar_scratch, int64_t scratch_stride, NMParams nm,
                     double *rows_out, abfit_fit *fits_out, unsigned long long *evals_per_prob, size_t smem_bytes,
-                    const BigScratch &big)
+                    int *err_flag, const BigScratch &big)
 {
     if (n_items <= 0) return 0;
     if (big.lm) {
         if (int rc = prep_kernel(k_fit_boot<true>, smem_bytes)) return rc;
         k_fit_boot<true><<<n_items, 32, smem_bytes, st>>>(P, items, n_boot, best, pred, resid, resample_idx, vary,
                                                           dstar_scratch, (long long)scratch_stride, nm, rows_out,
-                                                          fits_out, evals_per_prob, big.x, big.lm, big.lm_stride);
+                                                          fits_out, evals_per_prob, err_flag, big.x, big.lm, big.lm_stride);
     } else {
         if (int rc = prep_kernel(k_fit_boot<false>, smem_bytes)) return rc;
         k_fit_boot<false><<<n_items, 32, smem_bytes, st>>>(P, items, n_boot, best, pred, resid, resample_idx, vary,
                                                            dstar_scratch, (long long)scratch_stride, nm, rows_out,
-                                                           fits_out, evals_per_prob, nullptr, nullptr, 0);
+                                                           fits_out, evals_per_prob, err_flag, nullptr, nullptr, 0);
     }
     ABFIT_CUDA(cudaGetLastError());
     return 0;

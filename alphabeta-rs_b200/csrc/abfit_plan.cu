@@ -78,6 +78,7 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
     }
     hp.probs.resize(n_probs);
     hp.flops.resize(n_probs);
+    hp.fp64_instr.resize(n_probs);
     hp.tmax.resize(n_probs);
     hp.n_triples.resize(n_probs);
     hp.d_has_nan.assign(n_probs, 0);
@@ -168,6 +169,7 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
             hp.tmax[p] = hp.tmax[prev_p];
             hp.n_triples[p] = hp.n_triples[prev_p];
             hp.flops[p] = hp.flops[prev_p];
+            hp.fp64_instr[p] = hp.fp64_instr[prev_p];
             continue;
         }
         prev_p = p;
@@ -297,6 +299,22 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
         hp.tmax[p] = max_exp;
         hp.n_triples[p] = U;
         hp.flops[p] = 45.0 * (max_exp > 1 ? max_exp - 1 : 0) + 56.0 * U + 5.0 * ap.n_pairs + 40.0;
+        // FP64 instructions per evaluation and lane as the kernels execute them (FMA = one instruction): 27 per chain
+        // step, 36 per conditional-divergence op, 9 per sv0.G^t0, 5 per dt1t2, 5 per pair, 48 for genmatrix / sv0 /
+        // sv0.I / p_uu_est / penalty.  The DFMA peak is one such instruction per lane and slot, so
+        // fp64_instr / (flops / 2) is the factor by which the bit-exact formulation (FMA only in the 3x3 dots)
+        // stays below the FMA roofline even with a perfectly busy pipe.
+        {
+            double n = 48.0 + 5.0 * ap.n_pairs;
+            for (size_t i = (size_t)dp.ops_off; i < hp.ops.size(); ++i) {
+                const uint32_t op = hp.ops[i].x & 0xff, steps = (hp.ops[i].x >> 8) & 0xff, bb = hp.ops[i].y & 0xffff;
+                n += 27.0 * steps;
+                if (op >= OP_D_CC && op <= OP_D_GEN) n += 36.0 + ((op != OP_D_GEN && bb != OP_NONE) ? 5.0 : 0.0);
+                else if (op == OP_CALC_S) n += 9.0;
+                else if (op == OP_DT0 || op == OP_DT || op == OP_LDT) n += 5.0;
+            }
+            hp.fp64_instr[p] = n;
+        }
     }
     return 0;
 }

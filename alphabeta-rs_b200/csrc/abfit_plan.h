@@ -13,6 +13,7 @@ struct HostPlan {
     std::vector<uint32_t> wtrip;   // distinct triples of each program (warp-per-fit kernels, abfit_wide.cuh)
     std::vector<uint32_t> wtid;    // triple id of every pair
     std::vector<double> flops;     // algorithmic FLOPs per objective evaluation
+    std::vector<double> fp64_instr;  // FP64 instructions one lane executes per objective evaluation (program-derived)
     std::vector<int32_t> n_triples, tmax;
     std::vector<uint8_t> d_has_nan;
     int32_t max_pairs = 0;

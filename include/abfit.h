@@ -232,6 +232,10 @@ int abfit_batch_timing(abfit_batch *b, float ms[3], int64_t evals[2], int32_t *l
  * 45(Tmax-1) + 56 U + 5 N + 40 */
 int abfit_batch_flops_per_eval(abfit_batch *b, int32_t p, double *flops_out, int32_t *n_triples_out,
                                int32_t *tmax_out);
+/* FP64 instructions one fit executes per objective evaluation of problem p (an FMA counts once).  Under the
+ * bit-exact arithmetic contract only the 3x3 products are FMAs, so this is larger than flops / 2; the ratio is
+ * the ceiling of the FMA-roofline fraction (bench.py: roofline.pipe_frac). */
+int abfit_batch_fp64_instr_per_eval(abfit_batch *b, int32_t p, double *instr_out);
 
 /* ---- site -> window assignment (host) ---------------------------------------
  * Replaces MethylationSite::is_in_gene / find_gene / place_in_windows (src/methylation_site.rs:368-490),

@@ -473,6 +473,58 @@ static void start_task(void *c, int i)
     free(copy);
 }
 
+/* src/ab_neutral.rs:83-101, literally: `results.sort_by(|a, b| { let pedigree = pedigree.clone();
+ * divergence(a); divergence(b); lse_a.partial_cmp(&lse_b).unwrap() })` — slice::sort_by is a stable
+ * merge sort (insertion sort on short runs); ~ n log2 n comparisons, two objective evaluations each.
+ * The comparison count of this top-down merge sort (runs of <= 20 by insertion) is within a few
+ * per cent of Rust's; the ORDER it produces is the same (any stable sort gives one order). */
+typedef struct {
+    const abref_problem *pb;
+    abref_fit *fits;
+    int flags;
+    int nan;
+    long n_cmp;
+} literal_sort_ctx;
+
+static int literal_less(literal_sort_ctx *c, int a, int b)
+{
+    /* let pedigree = pedigree.clone(); */
+    abref_problem local = *c->pb;
+    size_t bytes = sizeof(double) * 4 * (size_t)local.n;
+    double *copy = (double *)malloc(bytes);
+    memcpy(copy, c->pb->ped, bytes);
+    local.ped = copy;
+    double la = abref_lse(&local, c->fits[a].theta, c->flags);
+    double lb = abref_lse(&local, c->fits[b].theta, c->flags);
+    free(copy);
+    ++c->n_cmp;
+    if (la != la || lb != lb) c->nan = 1; /* partial_cmp().unwrap() panics */
+    return la < lb;
+}
+
+static void literal_merge_sort(literal_sort_ctx *c, int *v, int *tmp, int lo, int hi)
+{
+    if (hi - lo <= 20) {
+        for (int i = lo + 1; i < hi; ++i) {
+            int x = v[i], j = i;
+            while (j > lo && literal_less(c, x, v[j - 1])) {
+                v[j] = v[j - 1];
+                --j;
+            }
+            v[j] = x;
+        }
+        return;
+    }
+    int mid = lo + (hi - lo) / 2;
+    literal_merge_sort(c, v, tmp, lo, mid);
+    literal_merge_sort(c, v, tmp, mid, hi);
+    int i = lo, j = mid, k = lo;
+    while (i < mid && j < hi) tmp[k++] = literal_less(c, v[j], v[i]) ? v[j++] : v[i++]; /* stable */
+    while (i < mid) tmp[k++] = v[i++];
+    while (j < hi) tmp[k++] = v[j++];
+    memcpy(v + lo, tmp + lo, sizeof(int) * (size_t)(hi - lo));
+}
+
 int abref_ab_neutral(const abref_problem *pb, int n_starts, const double *simplices, int max_iters,
                      double sd_tol, int flags, int n_threads, abref_fit *best, abref_fit *all_out,
                      double *pred, double *resid)
@@ -491,7 +543,24 @@ int abref_ab_neutral(const abref_problem *pb, int n_starts, const double *simpli
     /* :83-101 stable sort by penalty-free LSE, first element wins; the reference
      * re-evaluates divergence() inside the comparator, the value is the same.
      * Result order in the reference is completion order; here: start id. */
-    int rc = 0, arg = -1;
+    int rc = 0, arg = -1, literal_first = -1;
+    if (flags & ABREF_LITERAL_SORT) {
+        /* the reference's own work: a stable merge sort whose comparator clones the pedigree and
+         * evaluates divergence() + the LSE sum for BOTH operands of every comparison (serial). */
+        for (int i = 0; i < n_starts; ++i)
+            if (fits[i].status < 0) rc = ABREF_ERR_NAN;
+        if (rc == 0) {
+            int *ord = (int *)malloc(sizeof(int) * (size_t)n_starts);
+            int *tmp = (int *)malloc(sizeof(int) * (size_t)n_starts);
+            for (int i = 0; i < n_starts; ++i) ord[i] = i;
+            literal_sort_ctx lc = {pb, fits, flags, 0, 0};
+            literal_merge_sort(&lc, ord, tmp, 0, n_starts);
+            if (lc.nan) rc = ABREF_ERR_NAN;
+            literal_first = ord[0];
+            free(ord);
+            free(tmp);
+        }
+    }
     for (int i = 0; i < n_starts; ++i) {
         if (fits[i].status < 0) {
             rc = ABREF_ERR_NAN; /* :64,66 expect()/unwrap() panic */
@@ -501,6 +570,7 @@ int abref_ab_neutral(const abref_problem *pb, int n_starts, const double *simpli
         if (fits[i].lse != fits[i].lse) rc = ABREF_ERR_NAN; /* :100 unwrap panic */
         if (arg < 0 || fits[i].lse < fits[arg].lse) arg = i;
     }
+    if (rc == 0 && literal_first >= 0 && literal_first != arg) return ABREF_ERR_TIME - 100; /* cannot happen: both are the stable minimum */
     if (rc == 0 && arg >= 0) {
         *best = fits[arg];
         /* :108-135 */

@@ -45,7 +45,10 @@ typedef struct {
 enum {
     ABREF_NM_SHRINK_ON_FAILED_CONTRACTION = 1, /* later-argmin semantics; default off = 0.8.1 */
     ABREF_NM_EARLY_EXIT_ON_STALL = 2,          /* result-identical short-cut, see abref_nelder_mead */
-    ABREF_FAST_DIVERGENCE = 4                  /* power table + same chain: bit-identical, less work */
+    ABREF_FAST_DIVERGENCE = 4,                 /* power table + same chain: bit-identical, less work */
+    ABREF_LITERAL_SORT = 8                     /* best-of-starts by the reference's own sort_by whose comparator
+                                                  re-evaluates divergence() twice per comparison (src/ab_neutral.rs:83-101);
+                                                  same winner, the reference's serial tail is paid */
 };
 
 enum {

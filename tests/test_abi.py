@@ -79,3 +79,33 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "abref" not in txt and "oracle/" not in txt.replace("oracle/.", ""), os.path.join(dirpath, f)
+
+
+def test_python_twin_of_the_seeded_generators_is_bit_identical(ab):
+    """oracle/gen_py.py feeds the reference arm of bench.py (so that process never maps libabfit.so); the same seeds
+    must give the same doubles / indices as the C generators the GPU arm uses (north_star: identical inputs)"""
+    from oracle import gen_py as g
+
+    for pid in (0, 5, 9999, 12345678901):
+        for md in (0.0123, 0.0, -1.0):
+            assert ab.gen_start_simplices(0xAB0B200, pid, 130, md).tobytes() == g.gen_start_simplices(0xAB0B200, pid, 130, md).tobytes()
+        for n in (6, 351):
+            assert ab.gen_resample_idx(0xAB0B200, pid, 33, n).tobytes() == g.gen_resample_idx(0xAB0B200, pid, 33, n).tobytes()
+        for th in ([1e-4, 2e-3, 0.05, 0.01], [-1e-4, 0.0, -0.3, 0.0]):
+            assert ab.gen_vary_vertices(0xAB0B200, pid, 21, th).tobytes() == g.gen_vary_vertices(0xAB0B200, pid, 21, th).tobytes()
+
+
+def test_literal_sort_picks_the_same_winner(oracle):
+    """ABREF_LITERAL_SORT (the reference's sort_by with the re-evaluating comparator, src/ab_neutral.rs:83-101) and the
+    direct stable argmin agree on the winner; the flag only adds the reference's serial work"""
+    import os
+    from conftest import GOLDEN
+    from oracle import gen_py as g
+
+    ped = oracle.load_pedigree_file(os.path.join(GOLDEN, "pedigree.txt"))
+    pb = oracle.Problem(ped, 0.8, 0.8, 1.0)
+    sx = g.gen_start_simplices(7, 0, 45, float(ped[:, 3].max()))
+    fl = oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL
+    a = oracle.ab_neutral(pb, sx, flags=fl, n_threads=4)
+    b = oracle.ab_neutral(pb, sx, flags=fl | oracle.LITERAL_SORT, n_threads=4)
+    assert a[0] == b[0] == 0 and a[1]["start_id"] == b[1]["start_id"] and np.array_equal(a[3], b[3])

@@ -133,6 +133,37 @@ def test_fit_c1_real_pedigrees_bitwise(ab, ctx, oracle, ped78):
     assert abs(res.best[1]["theta"][1] - 0.00655710970515347) < 0.1 * 0.00655710970515347
 
 
+def test_c1_c2_default_counts_bitwise(ab, ctx, oracle, ped78):
+    """BASELINE configs[0..1] at their own sizes: the repo's example pedigree (6 pairs) and the desired_output one
+    (78 pairs), 1000 starts (the `alphabeta` default, src/arguments.rs:98-99) and 1000 bootstrap replicates, every
+    start and every replicate bit-identical to the oracle"""
+    ped6, p6, _ = oracle.build_pedigree(os.path.join(GOLDEN, "nodelist.txt"), os.path.join(GOLDEN, "edgelist.txt"), 0.99,
+                                        resolve_golden)
+    cases = [(ped6, p6), ped78]
+    n_starts = n_boot = 1000
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    idx = np.concatenate([ab.gen_resample_idx(SEED, i, n_boot, len(p)).ravel() for i, (p, u) in enumerate(cases)])
+    out = ctx.alphabeta_batch(probs, sx, idx, SEED)
+    res = ctx.fit_batch(probs, sx, max_iters=10000)
+    assert np.all(res.status == 0) and np.array_equal(out["best"]["theta"], res.best["theta"])
+    flags = oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL
+    off = 0
+    for i, (p, u) in enumerate(cases):
+        n = len(p)
+        check_fit_against_oracle(ab, oracle, res, i, oracle.Problem(p, u, u, 1.0), sx[i], 10000, flags, off, n)
+        vary = ab.gen_vary_vertices(SEED, i, n_boot, res.best[i]["theta"])
+        rc, orows, _ = oracle.boot_model(oracle.Problem(p, u, u, 1.0), res.best[i]["theta"], res.pred[off:off + n],
+                                         res.resid[off:off + n], idx[off * n_boot:(off + n) * n_boot].reshape(n_boot, n),
+                                         vary, max_iters=1000, flags=flags, n_threads=8)
+        assert rc == 0 and np.array_equal(out["rows"][i], orows)
+        assert np.array_equal(out["analysis"][i], oracle.analyze(orows), equal_nan=True)
+        off += n
+    # R original within 10 % (src/macros.rs:25-34)
+    assert abs(res.best[1]["theta"][0] - 5.7985750419976e-05) < 0.1 * 5.7985750419976e-05
+    assert abs(res.best[1]["theta"][1] - 0.00655710970515347) < 0.1 * 0.00655710970515347
+
+
 @pytest.mark.parametrize("n_starts,n_boot", [(1, 1), (33, 31), (97, 100), (257, 7)])
 def test_ragged_start_and_replicate_counts(ab, ctx, oracle, ped78, ped351, n_starts, n_boot):
     """start / replicate counts that do not fill warps, queues or hand-off groups evenly; three different pedigrees
@@ -456,9 +487,15 @@ def test_big_variant_is_bit_identical_on_small_problems(ab, ctx, oracle, ped351,
         assert np.array_equal(ref[k], big[k], equal_nan=True), k
     assert np.array_equal(ref["best"]["theta"], big["best"]["theta"])
     theta = np.stack([10 ** rng.uniform(-6, -2, 50), 10 ** rng.uniform(-6, -2, 50), rng.uniform(0, 0.1, 50), rng.uniform(0, 0.01, 50)], axis=1)
-    c_big, l_big = ctx.cost_batch(probs, theta, rng.integers(0, 2, 50).astype(np.int32))
+    pot = rng.integers(0, 2, 50).astype(np.int32)
+    c_big, l_big = ctx.cost_batch(probs, theta, pot)
     monkeypatch.delenv("ABFIT_DEV_BIG")
     monkeypatch.delenv("ABFIT_DEV_WIDE")
+    c_ref, l_ref = ctx.cost_batch(probs, theta, pot)
+    assert np.array_equal(c_big, c_ref) and np.array_equal(l_big, l_ref)
+    for i in range(50):
+        pb_o = oracle.Problem(cases[pot[i]][0], cases[pot[i]][1], cases[pot[i]][1], 1.0)
+        assert c_big[i] == oracle.cost(pb_o, theta[i]) and l_big[i] == oracle.lse(pb_o, theta[i]), i
 
 
 def test_c5_large_pedigree_fit(ab, ctx, oracle):
@@ -499,12 +536,15 @@ def test_c5_large_pedigree_fit(ab, ctx, oracle):
         assert np.array_equal(fits[0][f], ofits[f]), f
 
 
-def test_c5_chain_methylomes_to_fit(ab, ctx, oracle):
+@pytest.mark.parametrize("L", [20_000, 70_001])
+def test_c5_chain_methylomes_to_fit(ab, ctx, oracle, L):
     """BASELINE configs[4] end to end at a reduced site count: 200 simulated methylomes (10 lineages x 20 generations
     from one founder) -> observed divergence of all 19 900 pairs + p0uu on the GPU -> pedigree -> ABneutral fit with
-    the warp-per-fit kernels; every stage against the oracle on the same inputs"""
+    the warp-per-fit kernels; every stage against the oracle on the same inputs.  L = 70 001 is a window longer than
+    65 536 sites: the GPU's p0uu comes from the blocked sum (<= 1e-12 from the oracle's sequential one), and the two
+    CHAINS are compared — oracle p0uu -> oracle fit against GPU p0uu -> GPU fit — at the north-star tolerances."""
     rng = np.random.default_rng(2024)
-    lineages, generations, L = 10, 20, 20_000
+    lineages, generations = 10, 20
     founder = rng.choice(np.array([0, 2], dtype=np.uint8), size=L, p=[0.7, 0.3])
     rows = []
     for _ in range(lineages):
@@ -534,6 +574,18 @@ def test_c5_chain_methylomes_to_fit(ab, ctx, oracle):
     # the simulated rates are recovered to within a factor of two
     a, b = res.best[0]["theta"][:2]
     assert 2e-3 < a < 8e-3 and 7e-3 < b < 3e-2, (a, b)
+    # chain against chain: the oracle side uses ITS OWN p0uu (p_uu0 and eqp of the objective) and its own D
+    ped_o = ped.copy()
+    ped_o[:, 3] = D
+    rc, obest, _, opred, _ = oracle.ab_neutral(oracle.Problem(ped_o, p0, p0, 1.0), sx, max_iters=10000,
+                                               flags=oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, n_threads=8)
+    assert rc == 0
+    gb = res.best[0]
+    assert abs(gb["lse"] - obest["lse"]) <= 1e-9 * obest["lse"]              # best-fit RSS
+    assert rel(gb["theta"][:2], obest["theta"][:2]) <= 1e-6                  # fitted alpha, beta
+    assert rel(res.pred, opred) <= 1e-9
+    if L <= 65_536:
+        assert out["p0uu"][0] == p0 and np.array_equal(gb["theta"], obest["theta"])
 
 
 # ---------------------------------------------------------------------------------------------
@@ -612,3 +664,74 @@ def test_kernel_variants_are_bit_identical(ab, ctx, ped351, ped78, monkeypatch, 
         assert np.array_equal(ref[k], got[k], equal_nan=True), k
     for f in ("theta", "cost", "lse", "iters", "evals", "status", "start_id"):
         assert np.array_equal(ref_all[f], got_all[f]), f
+
+
+@pytest.mark.parametrize("n_starts", [33, 61, 97])
+def test_tail_handoff_stress(ab, ctx, oracle, ped351, monkeypatch, n_starts):
+    """the lock-free tail hand-off (mailbox word, CAS, targeted offers) at the shapes that maximise it: 3-warp blocks
+    whose queue holds 33-97 starts, i.e. it is drained almost at once and every warp thins out; 60 repetitions, all
+    fit records compared bit for bit each time (a lost or duplicated lane state changes them or hangs the launch)"""
+    rng = np.random.default_rng(7000 + n_starts)
+    cases = [synth_problem(rng, ped351) for _ in range(6)]
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    monkeypatch.setenv("ABFIT_DEV_NWARPS", "1")   # one warp per block: no hand-off, the reference bits
+    ref = ctx.fit_batch(probs, sx, max_iters=10000).all
+    flags = oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL
+    rc, _, allr, _, _ = oracle.ab_neutral(oracle.Problem(cases[0][0], cases[0][1], cases[0][1], 1.0), sx[0], max_iters=10000,
+                                          flags=flags, n_threads=8)
+    assert rc == 0 and np.array_equal(ref[0]["theta"], allr["theta"]) and np.array_equal(ref[0]["evals"], allr["evals"])
+    monkeypatch.setenv("ABFIT_DEV_NWARPS", "3")
+    monkeypatch.setenv("ABFIT_DEV_CHUNK", str(n_starts))
+    b = ctx.batch(probs)
+    b.upload_starts(sx)
+    for rep in range(60):
+        b.run_fit()
+        got = b.download_fit(want_all=True).all
+        assert got.tobytes() == ref.tobytes(), rep
+    b.close()
+
+
+@pytest.mark.parametrize("env", [{}, {"ABFIT_DEV_BOOT_TILE": "1"}, {"ABFIT_DEV_WIDE": "1"},
+                                 {"ABFIT_DEV_BIG": "1", "ABFIT_DEV_WIDE": "0"}])
+def test_resample_index_out_of_range_is_an_error_in_every_boot_kernel(ab, ctx, ped351, monkeypatch, env):
+    """contract of abfit_boot_batch: a resample index outside [0, n_pairs) -> ABFIT_ERR_ARG, whichever bootstrap kernel
+    the planner picks (index tile, stored D* tile, warp-per-fit, global-scratch lane state); never an out-of-bounds read"""
+    rng = np.random.default_rng(77)
+    p, u = synth_problem(rng, ped351, n_keep=90)
+    prob = [ab.Problem(p, u, u, 1.0)]
+    sx = ab.gen_start_simplices(SEED, 0, 32, float(p[:, 3].max()))[None]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    res = ctx.fit_batch(prob, sx)
+    n_boot = 40
+    idx = ab.gen_resample_idx(SEED, 0, n_boot, len(p))
+    vary = ab.gen_vary_vertices(SEED, 0, n_boot, res.best[0]["theta"])[None]
+    rows, _ = ctx.boot_batch(prob, res.best, res.pred, res.resid, idx.ravel(), vary)
+    assert np.all(np.isfinite(rows))
+    for bad in (len(p), -1, 2 ** 30):
+        idx2 = idx.copy()
+        idx2[17, 5] = bad
+        with pytest.raises(ab.AbfitError) as e:
+            ctx.boot_batch(prob, res.best, res.pred, res.resid, idx2.ravel(), vary)
+        assert e.value.code == ab.ERR_ARG
+
+
+def test_resample_index_check_large_pedigree(ab, ctx):
+    """same contract on a pedigree with more than 8191 pairs (u16 index tile not applicable)"""
+    rng = np.random.default_rng(78)
+    ped = c5_pedigree(rng, lineages=10, generations=13)  # 130 samples -> 8385 pairs
+    assert len(ped) > 8191
+    ped[:, 3] = 0.002 + 1e-4 * ped[:, 1] + 1e-4 * ped[:, 2] + rng.normal(0, 1e-4, len(ped))
+    prob = [ab.Problem(ped, 0.8, 0.8, 1.0)]
+    sx = ab.gen_start_simplices(SEED, 0, 4, float(ped[:, 3].max()))[None]
+    res = ctx.fit_batch(prob, sx, max_iters=200)
+    n_boot = 3
+    idx = ab.gen_resample_idx(SEED, 0, n_boot, len(ped))
+    vary = ab.gen_vary_vertices(SEED, 0, n_boot, res.best[0]["theta"])[None]
+    rows, _ = ctx.boot_batch(prob, res.best, res.pred, res.resid, idx.ravel(), vary, max_iters=50)
+    assert np.all(np.isfinite(rows))
+    idx[1, 8000] = len(ped)
+    with pytest.raises(ab.AbfitError) as e:
+        ctx.boot_batch(prob, res.best, res.pred, res.resid, idx.ravel(), vary, max_iters=50)
+    assert e.value.code == ab.ERR_ARG
