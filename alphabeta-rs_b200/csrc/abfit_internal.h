@@ -12,23 +12,6 @@
 
 namespace abfit {
 
-// chunk of consecutive starts / replicates / thetas of one problem, processed by one block
-struct WorkItem {
-    int32_t prob;
-    int32_t first;
-    int32_t count;
-    int32_t pad;
-};
-
-struct DevicePools {  // device pointers of a compiled batch
-    const DevProblem *probs;
-    const double *D;
-    const uint32_t *offs;
-    const OpWord *ops;
-    const uint32_t *wtrip;
-    const uint32_t *wtid;
-};
-
 // dynamic shared memory of one block working on problem pb (matches carve_and_stage)
 // simplex_doubles: 0 (no NM state), 25 (vertices + costs in shared) or 5 (costs only; vertices in global scratch)
 size_t smem_need(const DevProblem &pb, int simplex_doubles, bool d_shared, int n_warps);

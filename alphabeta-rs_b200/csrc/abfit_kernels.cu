@@ -19,271 +19,25 @@
 #include <cstdlib>
 
 #include "abfit_internal.h"
+#include "abfit_fitkernels.cuh"
 #include "abfit_wide.cuh"
 
 namespace abfit {
 
 // ---------------------------------------------------------------------------------
-// shared-memory carve-up
-//   [ per warp: (n_lane + simplex_doubles) x 32 doubles ] [ D ] [ offs ] [ ops ] [ queue ]
-// simplex_doubles: 0 = no Nelder-Mead state, 25 = vertices X (20) + costs C (5) in shared memory,
-// 5 = only the costs in shared memory, the vertices in a global (L2-resident) scratch area — they are
-// touched once per evaluation, and giving up their 5 KB per warp is what lets 16 warps share an SM.
+// the generic objective: interprets the window's micro-op program (abfit_model.cuh)
 // ---------------------------------------------------------------------------------
-struct Carved {
-    WarpCtx ctx;
-    LaneSimplex simplex;
-    int *queue;
+struct InterpObjective {
+    static constexpr int N_LANE = -1;
+    static constexpr bool NEEDS_PROGRAM = true;
+    template <class DAcc>
+    static __device__ __forceinline__ double eval(const WarpCtx &c, const DAcc &Dat, int lane, double alpha,
+                                                  double beta, double weight, double icpt, bool penalty)
+    {
+        return objective(c, Dat, lane, alpha, beta, weight, icpt, penalty);
+    }
 };
 
-template <bool D_SHARED>
-__device__ __forceinline__ Carved carve_and_stage(const DevProblem &pb, const DevicePools &P, int simplex_doubles,
-                                                  double *x_scratch = nullptr, int lead_doubles = 0)
-{
-    extern __shared__ double smem[];
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int warp = tid >> 5, lane = tid & 31, n_warps = nthr >> 5;
-    const int per_warp = (pb.n_lane + simplex_doubles) * 32;
-    Carved cv;
-    double *mine = smem + lead_doubles + (size_t)warp * per_warp;  // lead_doubles: multiple of 32
-    cv.ctx.lm = mine;
-    if (simplex_doubles == 25) {
-        cv.simplex.X = mine + pb.n_lane * 32 + lane;
-        cv.simplex.C = cv.simplex.X + 20 * 32;
-    } else if (simplex_doubles == 5) {
-        cv.simplex.X = x_scratch + ((size_t)blockIdx.x * n_warps + warp) * (20 * 32) + lane;
-        cv.simplex.C = mine + pb.n_lane * 32 + lane;
-    } else {
-        cv.simplex.X = nullptr;
-        cv.simplex.C = nullptr;
-    }
-    double *p = smem + lead_doubles + (size_t)n_warps * per_warp;  // multiple of 256 bytes
-    const double *Dg = P.D + pb.d_off;
-    if (D_SHARED) {
-        double *Ds = p;
-        p += (pb.n_pairs + 1) & ~1;
-        for (int i = tid; i < pb.n_pairs; i += nthr) Ds[i] = Dg[i];
-        cv.ctx.D = Ds;
-    } else {
-        cv.ctx.D = Dg;  // pool offsets are even: 16-byte aligned
-    }
-    uint32_t *offs = reinterpret_cast<uint32_t *>(p);  // 16-byte aligned; n_offs is a multiple of 4
-    OpWord *ops = reinterpret_cast<OpWord *>(offs + pb.n_offs);
-    cv.queue = reinterpret_cast<int *>(ops + pb.n_ops);
-    for (int i = tid; i < pb.n_offs; i += nthr) offs[i] = P.offs[pb.offs_off + i];
-    for (int i = tid; i < pb.n_ops; i += nthr) ops[i] = P.ops[pb.ops_off + i];
-    cv.ctx.offs = offs;
-    cv.ctx.ops = ops;
-    cv.ctx.n_pairs = pb.n_pairs;
-    cv.ctx.n_ops = pb.n_ops;
-    cv.ctx.p_uu0 = pb.p_uu0;
-    cv.ctx.p_mm0 = pb.p_mm0;
-    cv.ctx.eqp = pb.eqp;
-    cv.ctx.penw = pb.penw;
-    return cv;
-}
-
-// Pedigrees whose per-lane model state does not fit in shared memory (hundreds of distinct triples: C5's
-// 19 900-pair pedigree needs 836 doubles per lane): lane state, simplex vertices, D and the pair offsets all
-// live in global memory (an L2-resident scratch, [index][32 lanes] so every access is one coalesced 256-byte
-// request); only the simplex costs, the program and the queue stay in shared memory.  Same code, same bits —
-// just slower per evaluation.
-__device__ __forceinline__ Carved carve_big(const DevProblem &pb, const DevicePools &P, bool with_nm,
-                                            double *x_scratch, double *lm_scratch, size_t lm_stride)
-{
-    extern __shared__ double smem[];
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int warp = tid >> 5, lane = tid & 31, n_warps = nthr >> 5;
-    const size_t slot = (size_t)blockIdx.x * n_warps + warp;
-    Carved cv;
-    cv.ctx.lm = lm_scratch + slot * lm_stride;
-    if (with_nm) {
-        cv.simplex.X = x_scratch + slot * (20 * 32) + lane;
-        cv.simplex.C = smem + (size_t)warp * (5 * 32) + lane;
-    } else {
-        cv.simplex.X = nullptr;
-        cv.simplex.C = nullptr;
-    }
-    OpWord *ops = reinterpret_cast<OpWord *>(smem + (with_nm ? (size_t)n_warps * (5 * 32) : 0));
-    cv.queue = reinterpret_cast<int *>(ops + pb.n_ops);
-    for (int i = tid; i < pb.n_ops; i += nthr) ops[i] = P.ops[pb.ops_off + i];
-    cv.ctx.D = P.D + pb.d_off;
-    cv.ctx.offs = P.offs + pb.offs_off;
-    cv.ctx.ops = ops;
-    cv.ctx.n_pairs = pb.n_pairs;
-    cv.ctx.n_ops = pb.n_ops;
-    cv.ctx.p_uu0 = pb.p_uu0;
-    cv.ctx.p_mm0 = pb.p_mm0;
-    cv.ctx.eqp = pb.eqp;
-    cv.ctx.penw = pb.penw;
-    return cv;
-}
-
-__device__ __forceinline__ void store_fit(abfit_fit *dst, const abfit_fit &r)
-{
-    // 64-byte record written as four 16-byte vector stores (dst is 64-byte aligned)
-    double2 *d = reinterpret_cast<double2 *>(dst);
-    d[0] = make_double2(r.theta[0], r.theta[1]);
-    d[1] = make_double2(r.theta[2], r.theta[3]);
-    d[2] = make_double2(r.cost, r.lse);
-    d[3] = make_double2(__hiloint2double(r.evals, r.iters), __hiloint2double(r.start_id, r.status));
-}
-
-__device__ __forceinline__ void lane_nm_reset(LaneNM &L)
-{
-    L.phase = PH_IDLE;
-    L.k = 0; L.ord = 0; L.iters = 0; L.evals = 0; L.status = 0; L.fit_id = -1; L.fr = 0.0;
-    L.xt[0] = L.xt[1] = L.xt[2] = L.xt[3] = 0.0;
-}
-
-// take `count` consecutive fit ids for the idle lanes in mask m; returns this lane's id (or >= end)
-__device__ __forceinline__ int queue_take(int *queue, unsigned m, int lane, int end, bool &drained)
-{
-    int base = end;
-    if (!drained) {
-        if (lane == 0) base = atomicAdd(queue, __popc(m));
-        base = __shfl_sync(FULL, base, 0);
-        if (base >= end) drained = true;  // warp-uniform
-    }
-    return base + __popc(m & ((1u << lane) - 1u));
-}
-
-// ---------------------------------------------------------------------------------
-// Tail hand-off.  Once a block's queue is drained its warps thin out: Nelder-Mead run lengths spread 4x, so
-// a warp keeps executing full-width instructions for a handful of long fits (simulation on the C4 shape:
-// 89 % of the issued lanes do useful work with 3 warps per block, 95 % with hand-off).  A warp with few
-// active lanes therefore hands them to a sibling warp of the same block that has room, and exits.
-//
-// Mailbox protocol (one shared int `mb`, one published active-lane count per warp; all offers are
-// targeted, every take goes through a CAS, only the donor withdraws):
-//   donor     drained, 0 < active <= HANDOFF_MAX, mb == 0, a live sibling r with nact[r] + active <= 32:
-//             CAS mb 0 -> OFFER(donor, r, count); park the lane states in its own (now idle) lane_mem;
-//             fence; wait: mb == 0 -> taken, exit;  nact[r] < 0 (r has exited) -> CAS OFFER -> 0, resume.
-//   receiver  sees OFFER targeted at it (every loop trip, and once more after announcing its exit):
-//             CAS OFFER -> TAKING; idle lanes load the parked states and copy the simplices; mb = 0.
-// Active-lane counts only fall after the drain, so the room the donor saw is still there when the receiver
-// looks.  The moved state is the complete LaneNM + simplex, so results are unchanged bit for bit.
-// ---------------------------------------------------------------------------------
-constexpr int HANDOFF_MAX = 16;
-constexpr int MB_OFFER = 1 << 30, MB_TAKING = 1 << 29;
-__device__ __forceinline__ int mb_offer(int donor, int target, int count) { return MB_OFFER | donor | (target << 4) | (count << 8); }
-
-struct HandoffCtx {
-    volatile int *mb;            // mailbox word
-    volatile signed char *nact;  // [n_warps] published active-lane counts (-1: exited)
-    double *lm_base;             // shared: start of warp 0's per-warp region
-    int per_warp;                // doubles per warp region
-    int n_lane;                  // doubles of lane state (simplex X follows)
-};
-
-__device__ __forceinline__ void handoff_park(const LaneNM &L, double *ent, int lane)
-{
-    ent[0] = L.xt[0]; ent[1] = L.xt[1]; ent[2] = L.xt[2]; ent[3] = L.xt[3];
-    ent[4] = L.fr;
-    ent[5] = __hiloint2double(L.phase, L.k);
-    ent[6] = __hiloint2double((int)L.ord, L.iters);
-    ent[7] = __hiloint2double(L.evals, L.status);
-    ent[8] = __hiloint2double(L.fit_id, lane);
-}
-__device__ __forceinline__ int handoff_unpark(LaneNM &L, const double *ent)
-{
-    L.xt[0] = ent[0]; L.xt[1] = ent[1]; L.xt[2] = ent[2]; L.xt[3] = ent[3];
-    L.fr = ent[4];
-    L.phase = __double2hiint(ent[5]); L.k = __double2loint(ent[5]);
-    L.ord = (uint32_t)__double2hiint(ent[6]); L.iters = __double2loint(ent[6]);
-    L.evals = __double2hiint(ent[7]); L.status = __double2loint(ent[7]);
-    L.fit_id = __double2hiint(ent[8]);
-    return __double2loint(ent[8]);  // the donor lane that owns the simplex
-}
-
-// receiver side: returns true when lanes were taken over
-__device__ __forceinline__ bool handoff_try_take(const HandoffCtx &H, int warp, int lane, LaneNM &L, const LaneSimplex &S)
-{
-    const unsigned idle = __ballot_sync(FULL, L.phase == PH_IDLE);
-    int v = 0;
-    if (lane == 0) {
-        v = *H.mb;
-        if (!((v & MB_OFFER) && ((v >> 4) & 15) == warp && ((v >> 8) & 63) <= __popc(idle) &&
-              atomicCAS(const_cast<int *>(H.mb), v, MB_TAKING) == v))
-            v = 0;
-    }
-    v = __shfl_sync(FULL, v, 0);
-    if (!v) return false;
-    __threadfence_block();
-    const int donor = v & 15, count = (v >> 8) & 63;
-    const int rank = __popc(idle & ((1u << lane) - 1u));
-    if (L.phase == PH_IDLE && rank < count) {
-        const double *dbase = H.lm_base + (size_t)donor * H.per_warp;
-        const int dl = handoff_unpark(L, dbase + rank * 16);
-        const double *dX = dbase + H.n_lane * 32 + dl;  // donor lane's simplex: X[20], C[5] at stride 32
-#pragma unroll
-        for (int q = 0; q < 20; ++q) S.X[q * 32] = dX[q * 32];
-#pragma unroll
-        for (int q = 0; q < 5; ++q) S.C[q * 32] = dX[(20 + q) * 32];
-    }
-    const unsigned now = __ballot_sync(FULL, L.phase != PH_IDLE);
-    if (lane == 0) {
-        H.nact[warp] = (signed char)__popc(now);  // published before the mailbox is released: the next donor sees it
-        __threadfence_block();
-        *H.mb = 0;
-    }
-    return true;
-}
-
-// donor side: returns true when the lanes were taken (the warp is empty now), false when it keeps them
-__device__ __forceinline__ bool handoff_try_give(const HandoffCtx &H, int warp, int n_warps, int lane, LaneNM &L,
-                                                 unsigned amask, double *my_lm)
-{
-    const int n_act = __popc(amask);
-    int offer = 0;
-    if (lane == 0 && *H.mb == 0) {
-        int target = -1, best = 0;
-        for (int r = 0; r < n_warps; ++r) {
-            const int a = H.nact[r];
-            if (r != warp && a > best && a + n_act <= 32) {
-                best = a;
-                target = r;
-            }
-        }
-        if (target >= 0) {
-            offer = mb_offer(warp, target, n_act);
-            if (atomicCAS(const_cast<int *>(H.mb), 0, MB_TAKING) != 0) offer = 0;  // reserved while the states are parked
-            else H.nact[warp] = 0;  // not a target for anybody while it is giving its lanes away
-        }
-    }
-    offer = __shfl_sync(FULL, offer, 0);
-    if (!offer) return false;
-    if (L.phase != PH_IDLE) handoff_park(L, my_lm + __popc(amask & ((1u << lane) - 1u)) * 16, lane);
-    __syncwarp();
-    __threadfence_block();
-    const int target = (offer >> 4) & 15;
-    int taken = 0;  // 1 taken, 2 withdrawn
-    if (lane == 0) {
-        atomicExch(const_cast<int *>(H.mb), offer);
-        for (;;) {
-            const int v = *H.mb;
-            if (v == 0) {
-                taken = 1;
-                break;
-            }
-            if (v == offer && H.nact[target] < 0 && atomicCAS(const_cast<int *>(H.mb), offer, 0) == offer) {
-                taken = 2;
-                break;
-            }
-            __nanosleep(256);
-        }
-    }
-    taken = __shfl_sync(FULL, taken, 0);
-    if (taken == 1) {
-        L.phase = PH_IDLE;  // the fits live on in the receiver
-        return true;
-    }
-    return false;  // withdrawn: registers still hold the states
-}
-
-// ---------------------------------------------------------------------------------
-// multi-start Nelder-Mead
-// ---------------------------------------------------------------------------------
 template <bool D_SHARED, bool X_GLOBAL, bool BIG>
 __global__ void __launch_bounds__(128, X_GLOBAL ? 4 : 3)
 k_fit_starts(DevicePools P, const WorkItem *__restrict__ items, const double *__restrict__ simplices,
@@ -291,81 +45,20 @@ k_fit_starts(DevicePools P, const WorkItem *__restrict__ items, const double *__
              unsigned long long *__restrict__ evals_per_prob, double *x_scratch, double *lm_scratch,
              size_t lm_stride)
 {
-    constexpr bool HANDOFF = !X_GLOBAL && !BIG;  // the simplex of a moved lane is copied between shared regions
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const WorkItem it = items[blockIdx.x];
-    const DevProblem pb = P.probs[it.prob];
-    Carved cv = BIG ? carve_big(pb, P, true, x_scratch, lm_scratch, lm_stride)
-                    : carve_and_stage<D_SHARED>(pb, P, X_GLOBAL ? 5 : 25, x_scratch);
-    if (threadIdx.x == 0) {
-        cv.queue[0] = it.first;
-        cv.queue[1] = 0;           // mailbox
-        cv.queue[2] = 0x20202020;  // published active-lane counts: everybody full
-    }
-    __syncthreads();
-    const WarpCtx &c = cv.ctx;
-    const LaneSimplex &S = cv.simplex;
-    const DBroadcast Dat{c.D};
-    HandoffCtx H;
-    H.mb = cv.queue + 1;
-    H.nact = reinterpret_cast<volatile signed char *>(cv.queue + 2);
-    H.per_warp = (pb.n_lane + 25) * 32;
-    H.lm_base = c.lm - (size_t)warp * H.per_warp;
-    H.n_lane = pb.n_lane;
+    fit_starts_body<InterpObjective, D_SHARED, X_GLOBAL, BIG>(P, items, simplices, n_starts, nm, all_out, evals_per_prob,
+                                                             x_scratch, lm_scratch, lm_stride);
+}
 
-    LaneNM L;
-    lane_nm_reset(L);
-    const int end = it.first + it.count;
-    bool drained = false;
-    unsigned long long my_evals = 0;
-
-    for (;;) {
-        // ---- refill idle lanes from the block's chunk ----
-        const bool need = (L.phase == PH_IDLE);
-        const unsigned m = __ballot_sync(FULL, need);
-        if (m && !drained) {
-            const int idx = queue_take(cv.queue, m, lane, end, drained);
-            if (need && idx < end) {
-                const double *sx = simplices + ((size_t)it.prob * n_starts + idx) * 20;
-#pragma unroll
-                for (int q = 0; q < 20; ++q) S.X[q * 32] = sx[q];
-                nm_begin(L, S, idx);
-            }
-        }
-        unsigned amask = __ballot_sync(FULL, L.phase != PH_IDLE);
-        if (HANDOFF && drained && n_warps > 1 && pb.n_lane * 32 >= HANDOFF_MAX * 16) {
-            if (lane == 0) H.nact[warp] = (signed char)__popc(amask);
-            if (amask != FULL && handoff_try_take(H, warp, lane, L, S)) {
-                amask = __ballot_sync(FULL, L.phase != PH_IDLE);
-            } else if (amask && __popc(amask) <= HANDOFF_MAX && handoff_try_give(H, warp, n_warps, lane, L, amask, c.lm)) {
-                amask = 0;
-            }
-        }
-        if (!amask) {
-            if (HANDOFF && n_warps > 1 && pb.n_lane * 32 >= HANDOFF_MAX * 16) {
-                // announce the exit, then look once more: an offer posted in between is either taken here or
-                // withdrawn by its donor (whoever wins the CAS)
-                if (lane == 0) H.nact[warp] = -1;
-                __threadfence_block();
-                if (handoff_try_take(H, warp, lane, L, S)) continue;
-            }
-            break;
-        }
-        const bool active = (L.phase != PH_IDLE);
-        if (active) {
-            const double f =
-                objective(c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
-            abfit_fit res;
-            if (nm_advance(L, S, nm, f, res, amask)) {
-                my_evals += (unsigned long long)res.evals;
-                store_fit(all_out + (size_t)it.prob * n_starts + res.start_id, res);
-            }
-        }
-    }
-    // FLOP accounting: objective evaluations actually executed (excludes the LSE pass)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_down_sync(FULL, my_evals, o);
-    if (lane == 0 && evals_per_prob) atomicAdd(evals_per_prob + it.prob, my_evals);
+__global__ void __launch_bounds__(32)
+k_fit_boot_gather(DevicePools P, const WorkItem *__restrict__ items, int n_boot, const abfit_fit *__restrict__ best,
+                  const double *__restrict__ pred, const double *__restrict__ resid,
+                  const int32_t *__restrict__ resample_idx, const double *__restrict__ vary,
+                  uint2 *__restrict__ idx_scratch, long long scratch_stride, NMParams nm,
+                  double *__restrict__ rows_out, abfit_fit *__restrict__ fits_out,
+                  unsigned long long *__restrict__ evals_per_prob, int *__restrict__ err_flag, double *x_scratch)
+{
+    fit_boot_gather_body<InterpObjective>(P, items, n_boot, best, pred, resid, resample_idx, vary, idx_scratch,
+                                          scratch_stride, nm, rows_out, fits_out, evals_per_prob, err_flag, x_scratch);
 }
 
 // ---------------------------------------------------------------------------------
@@ -380,7 +73,7 @@ k_select(DevicePools P, int n_starts, const abfit_fit *__restrict__ all, abfit_f
     const int lane = threadIdx.x;
     const int p = blockIdx.x;
     const DevProblem pb = P.probs[p];
-    Carved cv = BIG ? carve_big(pb, P, false, nullptr, lm_scratch, lm_stride) : carve_and_stage<D_SHARED>(pb, P, 0);
+    Carved cv = BIG ? carve_big(pb, P, false, nullptr, lm_scratch, lm_stride) : carve_and_stage<InterpObjective, D_SHARED>(pb, P, 0);
     __syncwarp();
     const WarpCtx &c = cv.ctx;
 
@@ -461,7 +154,7 @@ k_fit_boot(DevicePools P, const WorkItem *__restrict__ items, int n_boot, const 
     const int lane = threadIdx.x;
     const WorkItem it = items[blockIdx.x];
     const DevProblem pb = P.probs[it.prob];
-    Carved cv = BIG ? carve_big(pb, P, true, x_scratch, lm_scratch, lm_stride) : carve_and_stage<false>(pb, P, 25);
+    Carved cv = BIG ? carve_big(pb, P, true, x_scratch, lm_scratch, lm_stride) : carve_and_stage<InterpObjective, false>(pb, P, 25);
     __syncwarp();
     const WarpCtx &c = cv.ctx;
     const LaneSimplex &S = cv.simplex;
@@ -503,106 +196,6 @@ k_fit_boot(DevicePools P, const WorkItem *__restrict__ items, int n_boot, const 
             }
             __syncwarp();
             if (take) {
-                // simplex = [best, vary x 4]  (src/boot_model.rs:69-75)
-                const double *vv = vary + ((size_t)it.prob * n_boot + idx) * 16;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) S.X[q * 32] = bm.theta[q];
-#pragma unroll
-                for (int q = 0; q < 16; ++q) S.X[(4 + q) * 32] = vv[q];
-                nm_begin(L, S, idx);
-            }
-            next += __popc(m);
-        }
-        const bool active = (L.phase != PH_IDLE);
-        const unsigned amask = __ballot_sync(FULL, active);
-        if (!amask) break;
-        if (active) {
-            const double f =
-                objective(c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
-            abfit_fit res;
-            if (nm_advance(L, S, nm, f, res, amask)) {
-                my_evals += (unsigned long long)res.evals;
-                const size_t o = (size_t)it.prob * n_boot + res.start_id;
-                // src/boot_model.rs:86-91
-                double *row = rows_out + o * 7;
-                row[0] = res.theta[0];
-                row[1] = res.theta[1];
-                row[2] = res.theta[2];
-                row[3] = res.theta[3];
-                row[4] = p_mm_est(res.theta[0], res.theta[1]);
-                row[5] = p_um_est(res.theta[0], res.theta[1]);
-                row[6] = p_uu_est(res.theta[0], res.theta[1]);
-                if (fits_out) store_fit(fits_out + o, res);
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_down_sync(FULL, my_evals, o);
-    if (lane == 0 && evals_per_prob) atomicAdd(evals_per_prob + it.prob, my_evals);
-}
-
-// ---------------------------------------------------------------------------------
-// bootstrap refits, index-tile variant (n_pairs <= 8191): D* is never materialised; each lane keeps the
-// u16 resample indices of its replicate in an L2-resident tile and gathers resid from shared memory
-// (see DGather).  Cuts the per-evaluation L2 traffic of k_fit_boot by 4x.
-// ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
-k_fit_boot_gather(DevicePools P, const WorkItem *__restrict__ items, int n_boot, const abfit_fit *__restrict__ best,
-                  const double *__restrict__ pred, const double *__restrict__ resid,
-                  const int32_t *__restrict__ resample_idx, const double *__restrict__ vary,
-                  uint2 *__restrict__ idx_scratch, long long scratch_stride, NMParams nm,
-                  double *__restrict__ rows_out, abfit_fit *__restrict__ fits_out,
-                  unsigned long long *__restrict__ evals_per_prob, int *__restrict__ err_flag, double *x_scratch)
-{
-    const int lane = threadIdx.x;
-    const WorkItem it = items[blockIdx.x];
-    const DevProblem pb = P.probs[it.prob];
-    Carved cv = carve_and_stage<false>(pb, P, x_scratch ? 5 : 25, x_scratch, boot_gather_lead(pb.n_pairs));
-    // resid / pred of this window at the start of shared memory
-    extern __shared__ double smem_lead[];
-    const int npad = (pb.n_pairs + 1) & ~1;
-    double *sresid = smem_lead;
-    double *spred = smem_lead + npad;
-    for (int i = lane; i < pb.n_pairs; i += 32) {
-        spred[i] = pred[pb.pair_off + i];
-        sresid[i] = resid[pb.pair_off + i];
-    }
-    __syncwarp();
-    const WarpCtx &c = cv.ctx;
-    const LaneSimplex &S = cv.simplex;
-    uint2 *tile = idx_scratch + (size_t)blockIdx.x * (size_t)scratch_stride + lane;
-    const DGather Dat{tile, spred, reinterpret_cast<const char *>(sresid)};
-    const int32_t *idxp = resample_idx + (size_t)pb.pair_off * n_boot;  // [n_boot][n_pairs] of this problem
-    const abfit_fit bm = best[it.prob];
-    const int ng4 = (pb.n_pairs + 3) >> 2;
-
-    LaneNM L;
-    lane_nm_reset(L);
-    int next = it.first;
-    const int end = it.first + it.count;
-    unsigned long long my_evals = 0;
-
-    for (;;) {
-        const bool need = (L.phase == PH_IDLE);
-        const unsigned m = __ballot_sync(FULL, need);
-        if (m && next < end) {
-            const int idx = next + __popc(m & ((1u << lane) - 1u));
-            if (need && idx < end) {
-                // pack this replicate's indices into the lane's tile column (read back by this lane only)
-                const int32_t *ib = idxp + (size_t)idx * pb.n_pairs;
-                for (int g = 0; g < ng4; ++g) {
-                    uint32_t v[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        v[q] = (4 * g + q < pb.n_pairs) ? (uint32_t)ib[4 * g + q] : 0u;
-                        if (v[q] >= (uint32_t)pb.n_pairs) {  // reported by download_boot; keeps the gather in bounds
-                            v[q] = 0u;
-                            *err_flag = 1;
-                        }
-                        v[q] *= 8u;  // byte offset into resid (n_pairs <= 8191)
-                    }
-                    tile[(size_t)g * 32] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
-                }
                 // simplex = [best, vary x 4]  (src/boot_model.rs:69-75)
                 const double *vv = vary + ((size_t)it.prob * n_boot + idx) * 16;
 #pragma unroll
@@ -757,7 +350,7 @@ k_cost_batch(DevicePools P, const WorkItem *__restrict__ items, const double *__
     const int lane = threadIdx.x;
     const WorkItem it = items[blockIdx.x];
     const DevProblem pb = P.probs[it.prob];
-    Carved cv = BIG ? carve_big(pb, P, false, nullptr, lm_scratch, lm_stride) : carve_and_stage<D_SHARED>(pb, P, 0);
+    Carved cv = BIG ? carve_big(pb, P, false, nullptr, lm_scratch, lm_stride) : carve_and_stage<InterpObjective, D_SHARED>(pb, P, 0);
     __syncwarp();
     const DBroadcast Dat{cv.ctx.D};
     if (lane < it.count) {
@@ -775,7 +368,7 @@ k_model_div(DevicePools P, const double *__restrict__ theta4, double *__restrict
 {
     const int lane = threadIdx.x;
     const DevProblem pb = P.probs[0];
-    Carved cv = BIG ? carve_big(pb, P, false, nullptr, lm_scratch, lm_stride) : carve_and_stage<false>(pb, P, 0);
+    Carved cv = BIG ? carve_big(pb, P, false, nullptr, lm_scratch, lm_stride) : carve_and_stage<InterpObjective, false>(pb, P, 0);
     __syncwarp();
     const WarpCtx &c = cv.ctx;
     model_divergence(c, lane, theta4[0], theta4[1], theta4[2]);

@@ -13,10 +13,17 @@
 // Compile with -fmad=false: the only fused operations are the explicit __fma_rn
 // chains of the 3x3 products (the pattern that reproduces the reference's cost KAT).
 #pragma once
+#ifdef __CUDACC_RTC__
+// run-time build (abfit_jit.cu): NVRTC has the CUDA built-ins; the fixed-width integer types and the C ABI structs
+// come from in-memory headers
+#include "abfit_rtc_prelude.h"
+#include "abfit.h"
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/abfit.h"
+#endif
 
 namespace abfit {
 
@@ -84,6 +91,23 @@ struct DevProblem {
     double eqp, penw;     // penw = eqp_weight * (double)n_pairs, src/structs.rs:210-211
 };
 
+// chunk of consecutive starts / replicates / thetas of one problem, processed by one block
+struct WorkItem {
+    int32_t prob;
+    int32_t first;
+    int32_t count;
+    int32_t pad;
+};
+
+struct DevicePools {  // device pointers of a compiled batch
+    const DevProblem *probs;
+    const double *D;
+    const uint32_t *offs;
+    const OpWord *ops;
+    const uint32_t *wtrip;
+    const uint32_t *wtid;
+};
+
 // per-warp view of the staged problem
 struct WarpCtx {
     const double *D;       // [n_pairs] shared (or global for very long pedigrees), 16-byte aligned
@@ -126,6 +150,21 @@ __device__ __forceinline__ void mat3_step(double R[9], const double G[9])
         }
 #pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = n[i];
+}
+
+// the same step into a second matrix, N = R.G: lets a rolled loop ping-pong between two register sets instead of
+// copying nine values per step (specialised objectives, abfit_jit.cu)
+__device__ __forceinline__ void mat3_to(const double R[9], const double G[9], double N[9])
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double acc = R[3 * i] * G[j];
+            acc = __fma_rn(R[3 * i + 1], G[3 + j], acc);
+            acc = __fma_rn(R[3 * i + 2], G[6 + j], acc);
+            N[3 * i + j] = acc;
+        }
 }
 
 // src/alphabeta.rs:62-65

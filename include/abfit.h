@@ -25,7 +25,9 @@
  */
 #ifndef ABFIT_H
 #define ABFIT_H
+#ifndef __CUDACC_RTC__ /* the library's run-time kernel build supplies the fixed-width types itself */
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -236,6 +238,15 @@ int abfit_batch_flops_per_eval(abfit_batch *b, int32_t p, double *flops_out, int
  * bit-exact arithmetic contract only the 3x3 products are FMAs, so this is larger than flops / 2; the ratio is
  * the ceiling of the FMA-roofline fraction (bench.py: roofline.pipe_frac). */
 int abfit_batch_fp64_instr_per_eval(abfit_batch *b, int32_t p, double *instr_out);
+/* 1 when the batch's Nelder-Mead kernels are the run-time specialised ones (a batch whose windows all share one
+ * pedigree time structure — every metaprofile — gets its micro-op program compiled to straight-line code with
+ * NVRTC; policy and environment switches: csrc/abfit_api.cu::decide_jit), 0 for the interpreter kernels.  Results
+ * are bit-identical either way. */
+int abfit_batch_uses_specialised_kernels(abfit_batch *b);
+/* Diagnostic (no GPU needed): writes the CUDA C++ source specialised for `prob`'s pedigree to source_path and, when
+ * cubin_path is not NULL, compiles it with NVRTC for sm_100a and writes the cubin (tests build the same source
+ * for the host and compare it with the oracle; cuobjdump -sass on the cubin shows what the GPU runs). */
+int abfit_jit_dump(const abfit_problem *prob, const char *source_path, const char *cubin_path, double *compile_seconds);
 
 /* ---- site -> window assignment (host) ---------------------------------------
  * Replaces MethylationSite::is_in_gene / find_gene / place_in_windows (src/methylation_site.rs:368-490),

@@ -194,6 +194,8 @@ int emul_launch_shape(const abfit_problem *pb, int n_probs, int fits_per_prob, i
     return 0;
 }
 
+double emul_var_threshold(double sd_tol) { return nm_var_threshold(sd_tol); }
+
 // plan statistics: per-lane doubles, micro-ops, events, chain length
 int emul_plan_stats(const abfit_problem *pb, int32_t out[6])
 {

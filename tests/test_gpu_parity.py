@@ -735,3 +735,65 @@ def test_resample_index_check_large_pedigree(ab, ctx):
     with pytest.raises(ab.AbfitError) as e:
         ctx.boot_batch(prob, res.best, res.pred, res.resid, idx.ravel(), vary, max_iters=50)
     assert e.value.code == ab.ERR_ARG
+
+
+@pytest.mark.parametrize("env", [{}, {"ABFIT_DEV_NWARPS": "3", "ABFIT_DEV_CHUNK": "150"}, {"ABFIT_DEV_NWARPS": "4"}])
+def test_specialised_kernels_are_bit_identical(ab, ctx, oracle, ped351, ped78, monkeypatch, env):
+    """run-time specialised kernels (csrc/abfit_jit.cu: the batch's one micro-op program compiled to straight-line
+    code by NVRTC) against the interpreter kernels and the oracle: every start, every bootstrap row, same bits —
+    one-warp blocks, 3-warp blocks with queue + tail hand-off, 4-warp blocks"""
+    rng = np.random.default_rng(55)
+    for shape_ped, n_keep in ((ped351, None), (ped351, 123), (ped78[0], None)):
+        base, u0 = synth_problem(rng, shape_ped, n_keep=n_keep)
+        cases = []
+        for _ in range(5):  # same time structure (one program), different D and p0uu: a metaprofile's windows
+            p = base.copy()
+            p[:, 3] = np.maximum(base[:, 3] * rng.uniform(0.7, 1.3) + rng.normal(0, 3e-4, len(base)), 0.0)
+            cases.append((p, float(rng.uniform(0.6, 0.95))))
+        probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+        n_starts, n_boot = 300, 40
+        sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+        idx = np.concatenate([ab.gen_resample_idx(SEED, i, n_boot, len(p)).ravel() for i, (p, u) in enumerate(cases)])
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        monkeypatch.setenv("ABFIT_JIT", "0")
+        ref = ctx.alphabeta_batch(probs, sx, idx, SEED)
+        b0 = ctx.batch(probs)
+        b0.upload_starts(sx)
+        assert not b0.uses_specialised_kernels()
+        b0.run_fit()
+        ref_all = b0.download_fit(want_all=True).all
+        b0.close()
+        monkeypatch.setenv("ABFIT_JIT", "1")
+        got = ctx.alphabeta_batch(probs, sx, idx, SEED)
+        b1 = ctx.batch(probs)
+        b1.upload_starts(sx)
+        assert b1.uses_specialised_kernels()
+        b1.run_fit()
+        got_all = b1.download_fit(want_all=True).all
+        b1.close()
+        for k in ("pred", "resid", "rows", "status", "analysis"):
+            assert np.array_equal(ref[k], got[k], equal_nan=True), k
+        assert got_all.tobytes() == ref_all.tobytes()
+        p, u = cases[2]
+        rc, best, allr, pred, resid = oracle.ab_neutral(oracle.Problem(p, u, u, 1.0), sx[2], max_iters=10000,
+                                                        flags=oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL, n_threads=8)
+        assert rc == 0
+        for f in ("theta", "cost", "lse", "iters", "evals", "status", "start_id"):
+            assert np.array_equal(got_all[2][f], allr[f]), f
+        monkeypatch.delenv("ABFIT_JIT")
+
+
+def test_specialised_kernels_mixed_batch_falls_back_to_interpreter(ab, ctx, ped351, ped78, monkeypatch):
+    """a batch that mixes pedigree programs is not specialised (one kernel per program would be needed); same API"""
+    rng = np.random.default_rng(56)
+    cases = [synth_problem(rng, ped351), ped78]
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    sx = np.stack([ab.gen_start_simplices(SEED, i, 64, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    monkeypatch.setenv("ABFIT_JIT", "1")
+    b = ctx.batch(probs)
+    b.upload_starts(sx)
+    assert not b.uses_specialised_kernels()
+    b.run_fit()
+    assert np.all(b.download_fit().status == 0)
+    b.close()

@@ -159,3 +159,102 @@ def test_launch_shapes_for_the_baseline_configs(emul, ab, oracle, monkeypatch):
     rows = [[min(g1, g2) if l1 == l2 else 0, g1, g2, 0.1] for i, (l1, g1) in enumerate(samples) for (l2, g2) in samples[i + 1:]]
     c5 = emul_shape(emul, ab, [np.array(rows, dtype=np.float64)], 1000)
     assert c5["big"] == 1 and c5["wide"] == 1 and c5["n_items"] == 1000 and c5["smem_wide"] < 24 * 1024
+
+
+# ---------------------------------------------------------------------------------------------
+# run-time specialised objective (csrc/abfit_jit.cu): the GENERATED source, built for the CPU
+# ---------------------------------------------------------------------------------------------
+def build_spec(ab, ped, tmp_path, tag):
+    """abfit_jit_dump -> generated CUDA C++ -> g++ (shims, -ffp-contract=off) -> ctypes"""
+    src = os.path.join(str(tmp_path), f"spec_{tag}.cu")
+    so = os.path.join(str(tmp_path), f"libspec_{tag}.so")
+    ab.jit_dump(ab.Problem(ped, 0.8, 0.8, 1.0), source_path=src)
+    csrc = os.path.join(ROOT, "alphabeta-rs_b200", "csrc")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
+                           "-I/usr/local/cuda/include", "-I" + csrc, "-I" + EMUL_DIR, "-Wno-attributes", "-Wno-unknown-pragmas",
+                           f'-DSPEC_SOURCE="{src}"', "-include", os.path.join(EMUL_DIR, "shims.h"), "-o", so,
+                           os.path.join(EMUL_DIR, "emul_spec.cpp")])
+    return C.CDLL(so)
+
+
+def spec_cost(lib, ab, ped, p0uu, eqp, w, theta):
+    arr = ab._pack_problems([ab.Problem(ped, p0uu, eqp, w)])
+    theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, 4)
+    cost, lse = np.empty(len(theta)), np.empty(len(theta))
+    assert lib.spec_cost(arr, theta.ctypes.data_as(C.c_void_p), len(theta), cost.ctypes.data_as(C.c_void_p),
+                         lse.ctypes.data_as(C.c_void_p)) == 0
+    return cost, lse
+
+
+def spec_fit(lib, ab, emul, ped, p0uu, sx, max_iters=10000, flags=0, dstar=None):
+    arr = ab._pack_problems([ab.Problem(ped, p0uu, p0uu, 1.0)])
+    sx = np.ascontiguousarray(sx, dtype=np.float64)
+    n = sx.size // 20
+    out = np.zeros(n, dtype=ab.FIT_DTYPE)
+    dp = None if dstar is None else np.ascontiguousarray(dstar, dtype=np.float64).ctypes.data_as(C.c_void_p)
+    emul.emul_var_threshold.restype = C.c_double
+    thr = emul.emul_var_threshold(C.c_double(ab.DBL_EPSILON))
+    assert lib.spec_fit(arr, sx.ctypes.data_as(C.c_void_p), n, dp, max_iters, C.c_double(ab.DBL_EPSILON), flags,
+                        C.c_double(thr), out.ctypes.data_as(C.c_void_p)) == 0
+    return out
+
+
+@pytest.mark.parametrize("style,tmax,n_pairs", [("lineage", 33, 131), ("sibling", 33, 120), ("any", 4, 37), ("any", 127, 260),
+                                                ("sibling", 1, 5), ("lineage", 4, 3)])
+def test_specialised_objective_source_is_bit_exact(emul, ab, oracle, tmp_path, style, tmax, n_pairs):
+    """the code generator against the oracle on time structures that exercise every micro-op (identity operands,
+    G itself, stored powers, deferred d-vectors), pair counts that are not multiples of 4, negative / NaN thetas"""
+    rng = np.random.default_rng(hash((style, tmax, n_pairs)) % 2**32)
+    ped = random_pedigree(rng, n_pairs, tmax, style)
+    lib = build_spec(ab, ped, tmp_path, f"{style}{tmax}_{n_pairs}")
+    B = 60
+    theta = np.stack([10 ** rng.uniform(-7, -1.5, B), 10 ** rng.uniform(-7, -1.5, B), rng.uniform(-0.1, 0.3, B),
+                      rng.uniform(0, 0.1, B)], axis=1)
+    theta[3] = [-2e-4, 3e-3, -0.2, 0.01]
+    theta[4] = [0.0, 0.0, 0.0, 0.0]  # 0/0 in p_uu_est: NaN cost, finite LSE
+    cost, lse = spec_cost(lib, ab, ped, 0.8, 0.7, 1.3, theta)
+    pb = oracle.Problem(ped, 0.8, 0.7, 1.3)
+    for i in range(B):
+        wc = oracle.cost(pb, theta[i])
+        assert cost[i] == wc or (np.isnan(cost[i]) and np.isnan(wc)), (style, tmax, n_pairs, i)
+        assert lse[i] == oracle.lse(pb, theta[i], flags=oracle.FAST_DIVERGENCE), (style, tmax, n_pairs, i)
+    icost, ilse = emul_cost(emul, ab, ped, 0.8, 0.7, 1.3, theta)  # and == the interpreter it replaces
+    assert np.array_equal(icost, cost, equal_nan=True) and np.array_equal(ilse, lse)
+
+
+def test_specialised_objective_golden_kat_and_fits(emul, ab, oracle, tmp_path):
+    """the C4 pedigree (data/pedigree.txt): cost KAT of src/structs.rs:233, whole Nelder-Mead runs and bootstrap
+    replicates through the generated objective, all bit-identical to the oracle"""
+    ped = oracle.load_pedigree_file(os.path.join(GOLDEN, "pedigree.txt"))
+    lib = build_spec(ab, ped, tmp_path, "c4")
+    cost, _ = spec_cost(lib, ab, ped, 0.75, 0.5, 0.7, [[0.0001179555, 0.0001180614, 0.03693534, 0.003023981]])
+    assert cost[0] == 0.0006700888539608879
+    u = 0.8
+    sx = ab.gen_start_simplices(7, 3, 24, float(ped[:, 3].max()))
+    fl = oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL
+    g = spec_fit(lib, ab, emul, ped, u, sx)
+    rc, best, allr, pred, resid = oracle.ab_neutral(oracle.Problem(ped, u, u, 1.0), sx, flags=fl, n_threads=4)
+    assert rc == 0
+    for f in ("theta", "cost", "lse", "iters", "evals", "status"):
+        assert np.array_equal(g[f], allr[f]), f
+    n_boot = 10
+    idx = ab.gen_resample_idx(5, 0, n_boot, len(ped))
+    vary = ab.gen_vary_vertices(5, 0, n_boot, best["theta"])
+    simplices = np.concatenate([np.broadcast_to(best["theta"], (n_boot, 1, 4)), vary], axis=1)
+    gb = spec_fit(lib, ab, emul, ped, u, simplices, max_iters=1000, dstar=pred[None, :] + resid[idx])
+    rc, rows, fits = oracle.boot_model(oracle.Problem(ped, u, u, 1.0), best["theta"], pred, resid, idx, vary, flags=fl,
+                                       n_threads=4)
+    assert rc == 0 and np.array_equal(gb["theta"], fits["theta"]) and np.array_equal(gb["evals"], fits["evals"])
+
+
+def test_specialised_kernels_compile_for_sm_100a_without_a_gpu(ab, oracle, tmp_path, monkeypatch):
+    """NVRTC cross-compiles the generated source + the embedded device headers here; the cubin holds both kernels"""
+    monkeypatch.setenv("ABFIT_CACHE_DIR", str(tmp_path / "cache"))
+    ped = oracle.load_pedigree_file(os.path.join(GOLDEN, "pedigree.txt"))
+    cubin = str(tmp_path / "spec.cubin")
+    secs = ab.jit_dump(ab.Problem(ped, 0.8, 0.8, 1.0), cubin_path=cubin)
+    assert secs > 0 and os.path.getsize(cubin) > 10000
+    blob = open(cubin, "rb").read()
+    assert b"abfit_jit_fit_starts" in blob and b"abfit_jit_fit_boot_gather" in blob
+    # second request: served from the disk cache
+    assert ab.jit_dump(ab.Problem(ped, 0.8, 0.8, 1.0), cubin_path=cubin) == 0.0

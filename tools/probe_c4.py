@@ -30,7 +30,9 @@ if __name__ == "__main__":
     b = ctx.batch(probs)
     fl = b.flops_per_eval(0)
     print("flops/eval", fl)
+    t = time.time()
     b.upload_starts(sx)
+    print("upload_starts %.2f s; specialised kernels: %s" % (time.time() - t, b.uses_specialised_kernels()))
     for rep in range(3):
         b.run_fit()
         tm = b.timing()
