@@ -110,6 +110,7 @@ def _load() -> C.CDLL:
         "abfit_batch_fp64_instr_per_eval": (C.c_int, [vp, i32, C.POINTER(dbl)]),
         "abfit_batch_uses_specialised_kernels": (C.c_int, [vp]),
         "abfit_jit_dump": (C.c_int, [vp, C.c_char_p, C.c_char_p, C.POINTER(dbl)]),
+        "abfit_jit_last_error": (C.c_char_p, []),
         "abfit_analyze": (C.c_int, [vp, i32, vp]),
         "abfit_parse_methylome_line": (C.c_int, [C.c_char_p, i32, vp, vp, vp, vp]),
         "abfit_pedigree_build": (C.c_int, [vp, C.c_char_p, C.c_char_p, dbl, C.POINTER(vp)]),
@@ -145,7 +146,7 @@ EXPORTED_SYMBOLS = (
     "abfit_model_divergence abfit_fit_batch abfit_boot_batch abfit_divergence abfit_divergence_device abfit_batch_create "
     "abfit_batch_destroy abfit_batch_upload_starts abfit_batch_run_fit abfit_batch_download_fit "
     "abfit_batch_upload_boot abfit_batch_run_boot abfit_batch_download_boot abfit_batch_sync "
-    "abfit_batch_timing abfit_batch_flops_per_eval abfit_batch_fp64_instr_per_eval abfit_batch_uses_specialised_kernels abfit_jit_dump abfit_analyze abfit_window_counts abfit_place_sites "
+    "abfit_batch_timing abfit_batch_flops_per_eval abfit_batch_fp64_instr_per_eval abfit_batch_uses_specialised_kernels abfit_jit_dump abfit_jit_last_error abfit_analyze abfit_window_counts abfit_place_sites "
     "abfit_parse_methylome_line abfit_parse_annotation_line abfit_pedigree_graph abfit_pedigree_build abfit_pedigree_info abfit_pedigree_rows abfit_pedigree_warnings "
     "abfit_pedigree_free abfit_format_f64 abfit_steady_state abfit_write_pedigree abfit_write_analysis abfit_format_analysis "
     "abfit_write_npy_f64 abfit_write_metaprofile_results"
@@ -233,6 +234,10 @@ def _pack_problems(probs: Sequence[Problem]):
         arr[i].eqp = p.eqp
         arr[i].eqp_weight = p.eqp_weight
     return arr
+
+
+def jit_last_error() -> str:
+    return (_lib.abfit_jit_last_error() or b"").decode()
 
 
 def jit_dump(prob: "Problem", source_path: Optional[str] = None, cubin_path: Optional[str] = None) -> float:

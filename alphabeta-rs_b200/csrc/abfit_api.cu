@@ -107,6 +107,8 @@ struct abfit_batch {
     // specialised kernels of this batch's program (abfit_jit.cu); nullptr: interpreter kernels
     const JitModule *jit = nullptr;
     bool jit_decided = false;
+    DevBuf<int> d_cursor;  // item cursors of the continuous-scheduling kernels: [0] multi-start, [1] bootstrap
+    int jit_warps_fit = 0, jit_warps_boot = 0;  // resident warps = grid of a full machine
     // timing
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_fit = false, ev_boot = false;
@@ -444,9 +446,17 @@ static int upload_starts_impl(abfit_batch *b, int32_t n_starts, const double *si
             return rc;
         b->jit_decided = false;
         decide_jit(b, n_starts);
-        std::vector<WorkItem> items =
-            b->shape.wide ? make_items_wide(b->hp, n_starts, b->ctx->prop.multiProcessorCount, true)
-                          : make_items(b->hp, n_starts, b->ctx->prop.multiProcessorCount, b->shape.n_warps, true);
+        const int n_sm = b->ctx->prop.multiProcessorCount;
+        std::vector<WorkItem> items;
+        if (b->jit && b->jit->sched == 2) {
+            if (int rc = b->d_cursor.ensure(2)) return rc;
+            b->jit_warps_fit = jit_resident_warps(b->jit, false, b->hp.probs[0], n_sm);
+            if (b->jit_warps_fit <= 0) return cuda_fail(cudaGetLastError(), "occupancy of the specialised multi-start kernel");
+            items = make_items_guided(b->hp, n_starts, b->jit_warps_fit, 256, true);
+        } else {
+            items = b->shape.wide ? make_items_wide(b->hp, n_starts, n_sm, true)
+                                  : make_items(b->hp, n_starts, n_sm, b->shape.n_warps, true);
+        }
         b->n_items = (int)items.size();
         if (int rc = b->d_items.ensure(items.size())) return rc;
         if (!items.empty())
@@ -489,6 +499,12 @@ int abfit_batch_run_fit(abfit_batch *b, int32_t max_iters, double sd_tol, uint32
     if (b->shape.wide) {
         if (int rc = launch_fit_starts_wide(st, b->pools, b->d_items.p, b->n_items, b->d_simplices.p, b->n_starts, nm,
                                             b->d_all.p, b->d_evals_fit.p, b->shape.smem_wide))
+            return rc;
+    } else if (b->jit && b->jit->sched == 2) {
+        if (int rc = jit_launch_fit_starts_v2(b->jit, st, b->pools, b->d_items.p, b->n_items,
+                                              (int64_t)b->n_probs * b->n_starts, b->jit_warps_fit, b->d_cursor.p,
+                                              b->d_simplices.p, b->n_starts, nm, b->d_all.p, b->d_evals_fit.p,
+                                              jit_smem_fit_v2(b->hp.probs[0])))
             return rc;
     } else if (b->jit) {
         if (int rc = jit_launch_fit_starts(b->jit, st, b->pools, b->d_items.p, b->n_items, b->shape.n_warps,
@@ -545,9 +561,17 @@ static int boot_alloc(abfit_batch *b, int32_t n_boot)
     decide_jit(b, n_boot);  // a bootstrap-only batch has not been through upload_starts
     if (n_boot != b->n_boot) {
         b->n_boot = n_boot;
-        std::vector<WorkItem> items = b->shape.wide
-                                          ? make_items_wide(b->hp, n_boot, b->ctx->prop.multiProcessorCount, true)
-                                          : make_items(b->hp, n_boot, b->ctx->prop.multiProcessorCount, 1, true);
+        const bool v2 = b->jit && b->jit->sched == 2 && b->shape.smem_boot_gather;
+        std::vector<WorkItem> items;
+        if (v2) {
+            if (int rc = b->d_cursor.ensure(2)) return rc;
+            b->jit_warps_boot = jit_resident_warps(b->jit, true, b->hp.probs[0], b->ctx->prop.multiProcessorCount);
+            if (b->jit_warps_boot <= 0) return cuda_fail(cudaGetLastError(), "occupancy of the specialised bootstrap kernel");
+            items = make_items_guided(b->hp, n_boot, b->jit_warps_boot, 256, true);
+        } else {
+            items = b->shape.wide ? make_items_wide(b->hp, n_boot, b->ctx->prop.multiProcessorCount, true)
+                                  : make_items(b->hp, n_boot, b->ctx->prop.multiProcessorCount, 1, true);
+        }
         b->n_boot_items = (int)items.size();
         if (int rc = b->d_boot_items.ensure(items.size())) return rc;
         if (!items.empty())
@@ -559,7 +583,9 @@ static int boot_alloc(abfit_batch *b, int32_t n_boot)
         const size_t per_block = b->shape.wide ? (size_t)((b->hp.max_pairs + 1) & ~1)  // one D* row per warp
                                  : b->shape.smem_boot_gather ? (size_t)((b->hp.max_pairs + 3) / 4) * 32
                                                              : (size_t)b->hp.max_pairs * 32;
-        if (int rc = b->d_scratch.ensure((size_t)(std::max(b->n_boot_items, 1) + 1) * per_block)) return rc;
+        // (continuous scheduling: one index tile per persistent warp)
+        const size_t n_tiles = v2 ? (size_t)b->jit_warps_boot : (size_t)std::max(b->n_boot_items, 1);
+        if (int rc = b->d_scratch.ensure((n_tiles + 1) * per_block)) return rc;
         if (int rc = b->d_rows.ensure((size_t)b->n_probs * n_boot * 7)) return rc;
         if (int rc = b->d_bootfits.ensure((size_t)b->n_probs * n_boot)) return rc;
     }
@@ -616,6 +642,14 @@ int abfit_batch_run_boot(abfit_batch *b, int32_t max_iters, double sd_tol, uint3
                                           b->d_pred.p, b->d_resid.p, b->d_idx.p, b->d_vary.p, b->d_scratch.p,
                                           (int64_t)((b->hp.max_pairs + 1) & ~1), nm, b->d_rows.p, b->d_bootfits.p,
                                           b->d_evals_boot.p, b->shape.smem_wide, b->d_booterr.p))
+            return rc;
+    } else if (b->shape.smem_boot_gather && b->jit && b->jit->sched == 2) {
+        if (int rc = jit_launch_fit_boot_gather_v2(b->jit, st, b->pools, b->d_boot_items.p, b->n_boot_items,
+                                                   (int64_t)b->n_probs * b->n_boot, b->jit_warps_boot, b->d_cursor.p + 1,
+                                                   b->n_boot, b->d_best.p, b->d_pred.p, b->d_resid.p, b->d_idx.p,
+                                                   b->d_vary.p, b->d_scratch.p, (int64_t)((b->hp.max_pairs + 3) / 4) * 32,
+                                                   nm, b->d_rows.p, b->d_bootfits.p, b->d_evals_boot.p,
+                                                   jit_smem_boot_v2(b->hp.probs[0]), b->d_booterr.p))
             return rc;
     } else if (b->shape.smem_boot_gather && b->jit) {
         // specialised index-tile kernel: 33 doubles of shared memory per lane, the simplex always fits
@@ -723,7 +757,7 @@ int abfit_jit_dump(const abfit_problem *prob, const char *source_path, const cha
     if (!prob) return ABFIT_ERR_ARG;
     HostPlan hp;
     if (int rc = compile_problems(prob, 1, hp)) return rc;
-    const std::string src = jit_generate_source(hp, 0);
+    const std::string src = jit_generate_source(hp, 0, jit_default_sched());
     if (source_path) {
         FILE *f = fopen(source_path, "wb");
         if (!f) {
@@ -755,6 +789,13 @@ int abfit_jit_dump(const abfit_problem *prob, const char *source_path, const cha
 int abfit_batch_uses_specialised_kernels(abfit_batch *b)
 {
     return b && b->jit ? 1 : 0;
+}
+
+const char *abfit_jit_last_error(void)
+{
+    static thread_local std::string s;
+    s = jit_last_note();
+    return s.c_str();
 }
 
 int abfit_batch_fp64_instr_per_eval(abfit_batch *b, int32_t p, double *instr_out)

@@ -20,6 +20,7 @@
 // warps of the block share the staged pedigree and every warp runs a perfectly uniform objective on 32 different
 // thetas.  Lanes that finish a fit pull the next start of the chunk from a block-wide counter.
 #pragma once
+#include "abfit_fitkernels_host.h"
 #include "abfit_nm.cuh"
 
 namespace abfit {
@@ -484,6 +485,270 @@ __device__ __forceinline__ void fit_boot_gather_body(const DevicePools &P, const
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_down_sync(FULL, my_evals, o);
     if (lane == 0 && evals_per_prob) atomicAdd(evals_per_prob + it.prob, my_evals);
+}
+
+// ---------------------------------------------------------------------------------
+// Continuous lane scheduling ("v2" bodies; specialised objectives, batches whose windows share one program).
+//
+// The block-per-item bodies above keep a whole block on ONE window: when its queue drains the warps thin out
+// (a handful of long fits keep full-width instructions issuing; the hand-off only consolidates them), and a batch
+// with few windows per SM slot ends in a ragged last wave — at 1 250 windows per GPU (10 000 sharded over 8) the
+// multi-start kernel ran 15-20 % below its large-batch rate; the bootstrap's 100 replicates per window left
+// 21.5 of 32 lanes busy.  Here a block is ONE warp that lives for the whole launch (grid = resident warps):
+//
+//   * work items are chunks of one window's fits, opened one after the other from a global cursor; their
+//     sizes follow guided self-scheduling on the host (large first, 32 at the end: make_items_guided), so all
+//     warps run out of work within about one fit of each other;
+//   * a lane that finishes a fit takes the next fit of the open item AT ONCE, even when the item belongs to
+//     another window than the fits still running on its neighbours: a warp keeps two window slots in shared
+//     memory (D column + the window's scalars), every lane points at the slot of its own window.  The objective
+//     is the same instruction stream for every lane — only the broadcast loads of D become two-address loads
+//     while two windows overlap;
+//   * a new item is opened into the slot that has no running fits (its predecessor's last fits have finished by
+//     then: an item lasts several fits per lane).
+//
+// No block-wide synchronisation, no inter-block waiting (the cursor is only ever incremented).  A fit's arithmetic
+// does not depend on which lane, warp or slot runs it: same bits as the block-per-item kernels.
+// ---------------------------------------------------------------------------------
+
+__device__ __forceinline__ WarpCtx v2_ctx(const double *D, const double *scal, int n_pairs)
+{
+    WarpCtx c;
+    c.D = D;
+    c.offs = nullptr;
+    c.ops = nullptr;
+    c.lm = nullptr;
+    c.n_pairs = n_pairs;
+    c.n_ops = 0;
+    c.p_uu0 = scal[0];
+    c.p_mm0 = scal[1];
+    c.eqp = scal[2];
+    c.penw = scal[3];
+    return c;
+}
+
+// warp-uniform bookkeeping of the open item
+struct V2Queue {
+    int cur = -1;       // slot being filled from (-1: none yet)
+    int next = 0, end = 0, prob = 0;
+    bool exhausted = false;
+};
+
+// Opens the next item when the current one is used up.  Returns false when idle lanes have to wait (the other
+// slot still has running fits) or no items are left.  `users_other` = lanes running on the slot to be reused.
+template <class STAGE>
+__device__ __forceinline__ bool v2_open_next(V2Queue &q, const WorkItem *__restrict__ items, int n_items, int *cursor,
+                                             int lane, unsigned users_other, STAGE stage)
+{
+    if (q.exhausted) return false;
+    const int other = q.cur < 0 ? 0 : (q.cur ^ 1);
+    if (q.cur >= 0 && users_other) return false;
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(cursor, 1);
+    idx = __shfl_sync(FULL, idx, 0);
+    if (idx >= n_items) {
+        q.exhausted = true;
+        return false;
+    }
+    const WorkItem it = items[idx];
+    q.cur = other;
+    q.next = it.first;
+    q.end = it.first + it.count;
+    q.prob = it.prob;
+    stage(other, it.prob);
+    return true;
+}
+
+template <class OBJ>
+__device__ __forceinline__ void fit_starts_body_v2(const DevicePools &P, const WorkItem *__restrict__ items, int n_items,
+                                                   int *cursor, const double *__restrict__ simplices, int n_starts,
+                                                   const NMParams &nm, abfit_fit *__restrict__ all_out,
+                                                   unsigned long long *__restrict__ evals_per_prob)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x;  // one warp per block
+    LaneSimplex S;
+    S.X = smem + lane;
+    S.C = S.X + 20 * 32;
+    const int n_pairs = P.probs[items[0].prob].n_pairs;  // one program for the whole batch (host: jit_eligible)
+    const int npad = (n_pairs + 1) & ~1;
+    const int slot_doubles = v2_fit_slot_doubles(n_pairs);
+    double *slots = smem + 25 * 32;
+    auto stage = [&](int slot, int prob) {
+        const DevProblem pb = P.probs[prob];
+        double *sl = slots + slot * slot_doubles;
+        const double *Dg = P.D + pb.d_off;
+        for (int i = lane; i < pb.n_pairs; i += 32) sl[i] = Dg[i];
+        if (lane == 0) {
+            sl[npad] = pb.p_uu0;
+            sl[npad + 1] = pb.p_mm0;
+            sl[npad + 2] = pb.eqp;
+            sl[npad + 3] = pb.penw;
+        }
+        __syncwarp();
+    };
+
+    LaneNM L;
+    lane_nm_reset(L);
+    int my_slot = 0, my_prob = 0;
+    V2Queue q;
+    for (;;) {
+        __syncwarp();
+        unsigned idle = __ballot_sync(FULL, L.phase == PH_IDLE);
+        while (idle) {
+            if (q.next >= q.end) {
+                const unsigned users_other = __ballot_sync(FULL, L.phase != PH_IDLE && my_slot != q.cur);
+                if (!v2_open_next(q, items, n_items, cursor, lane, users_other, stage)) break;
+            }
+            const int take = min(__popc(idle), q.end - q.next);
+            const int rank = __popc(idle & ((1u << lane) - 1u));
+            if (((idle >> lane) & 1u) && rank < take) {
+                const int id = q.next + rank;
+                const double *sx = simplices + ((size_t)q.prob * n_starts + id) * 20;
+#pragma unroll
+                for (int k = 0; k < 20; ++k) S.X[k * 32] = sx[k];
+                nm_begin(L, S, id);
+                my_slot = q.cur;
+                my_prob = q.prob;
+            }
+            q.next += take;
+            idle = __ballot_sync(FULL, L.phase == PH_IDLE);
+        }
+        const bool active = (L.phase != PH_IDLE);
+        const unsigned amask = __ballot_sync(FULL, active);
+        if (!amask) break;  // nothing runs and nothing could be started: the launch's work is done
+        if (active) {
+            const double *sl = slots + my_slot * slot_doubles;
+            const WarpCtx c = v2_ctx(sl, sl + npad, n_pairs);
+            const DBroadcast Dat{sl};
+            const double f = OBJ::eval(c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
+            abfit_fit res;
+            if (nm_advance(L, S, nm, f, res, amask)) {
+                store_fit(all_out + (size_t)my_prob * n_starts + res.start_id, res);
+                // FLOP accounting: objective evaluations actually executed (excludes the LSE pass)
+                if (evals_per_prob) atomicAdd(evals_per_prob + my_prob, (unsigned long long)res.evals);
+            }
+        }
+    }
+}
+
+// bootstrap refits (src/boot_model.rs:41-100), index-tile formulation (see DGather): a slot holds the window's
+// residuals, predictions, scalars and best model; the lane's resample indices are packed as SHARED-MEMORY BYTE
+// OFFSETS of the residuals in the lane's slot, so the gather address is again "tile value + link-time constant".
+template <class OBJ>
+__device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, const WorkItem *__restrict__ items, int n_items,
+                                                        int *cursor, int n_boot, const abfit_fit *__restrict__ best,
+                                                        const double *__restrict__ pred, const double *__restrict__ resid,
+                                                        const int32_t *__restrict__ resample_idx,
+                                                        const double *__restrict__ vary, uint2 *__restrict__ idx_scratch,
+                                                        long long scratch_stride, const NMParams &nm,
+                                                        double *__restrict__ rows_out, abfit_fit *__restrict__ fits_out,
+                                                        unsigned long long *__restrict__ evals_per_prob,
+                                                        int *__restrict__ err_flag)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x;  // one warp per block
+    LaneSimplex S;
+    S.X = smem + lane;
+    S.C = S.X + 20 * 32;
+    const int n_pairs = P.probs[items[0].prob].n_pairs;
+    const int npad = (n_pairs + 1) & ~1;
+    const int slot_doubles = v2_boot_slot_doubles(n_pairs);
+    double *slots = smem + 25 * 32;
+    const int ng4 = (n_pairs + 3) >> 2;
+    uint2 *tile = idx_scratch + (size_t)blockIdx.x * (size_t)scratch_stride + lane;
+    // slot: [resid npad][pred npad][p_uu0, p_mm0, eqp, penw][best theta 4]
+    auto stage = [&](int slot, int prob) {
+        const DevProblem pb = P.probs[prob];
+        double *sl = slots + slot * slot_doubles;
+        for (int i = lane; i < pb.n_pairs; i += 32) {
+            sl[i] = resid[pb.pair_off + i];
+            sl[npad + i] = pred[pb.pair_off + i];
+        }
+        if (lane == 0) {
+            const abfit_fit bm = best[prob];
+            sl[2 * npad] = pb.p_uu0;
+            sl[2 * npad + 1] = pb.p_mm0;
+            sl[2 * npad + 2] = pb.eqp;
+            sl[2 * npad + 3] = pb.penw;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sl[2 * npad + 4 + k] = bm.theta[k];
+        }
+        __syncwarp();
+    };
+
+    LaneNM L;
+    lane_nm_reset(L);
+    int my_slot = 0, my_prob = 0;
+    V2Queue q;
+    for (;;) {
+        __syncwarp();
+        unsigned idle = __ballot_sync(FULL, L.phase == PH_IDLE);
+        while (idle) {
+            if (q.next >= q.end) {
+                const unsigned users_other = __ballot_sync(FULL, L.phase != PH_IDLE && my_slot != q.cur);
+                if (!v2_open_next(q, items, n_items, cursor, lane, users_other, stage)) break;
+            }
+            const int take = min(__popc(idle), q.end - q.next);
+            const int rank = __popc(idle & ((1u << lane) - 1u));
+            if (((idle >> lane) & 1u) && rank < take) {
+                const int id = q.next + rank;
+                const DevProblem pb = P.probs[q.prob];
+                const double *sl = slots + q.cur * slot_doubles;
+                // this replicate's resample indices -> byte offsets of its residuals in shared memory
+                const uint32_t base = (uint32_t)((const char *)sl - (const char *)smem);
+                const int32_t *ib = resample_idx + (size_t)pb.pair_off * n_boot + (size_t)id * pb.n_pairs;
+                for (int g = 0; g < ng4; ++g) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        v[k] = (4 * g + k < pb.n_pairs) ? (uint32_t)ib[4 * g + k] : 0u;
+                        if (v[k] >= (uint32_t)pb.n_pairs) {  // reported by download_boot; keeps the gather in bounds
+                            v[k] = 0u;
+                            *err_flag = 1;
+                        }
+                        v[k] = base + v[k] * 8u;  // < 64 KB: the host checks the footprint
+                    }
+                    tile[(size_t)g * 32] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+                }
+                // simplex = [best, vary x 4]  (src/boot_model.rs:69-75)
+                const double *vv = vary + ((size_t)q.prob * n_boot + id) * 16;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) S.X[k * 32] = sl[2 * npad + 4 + k];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) S.X[(4 + k) * 32] = vv[k];
+                nm_begin(L, S, id);
+                my_slot = q.cur;
+                my_prob = q.prob;
+            }
+            q.next += take;
+            idle = __ballot_sync(FULL, L.phase == PH_IDLE);
+        }
+        const bool active = (L.phase != PH_IDLE);
+        const unsigned amask = __ballot_sync(FULL, active);
+        if (!amask) break;
+        if (active) {
+            const double *sl = slots + my_slot * slot_doubles;
+            const WarpCtx c = v2_ctx(nullptr, sl + 2 * npad, n_pairs);
+            const DGather Dat{tile, sl + npad, reinterpret_cast<const char *>(smem)};
+            const double f = OBJ::eval(c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
+            abfit_fit res;
+            if (nm_advance(L, S, nm, f, res, amask)) {
+                if (evals_per_prob) atomicAdd(evals_per_prob + my_prob, (unsigned long long)res.evals);
+                const size_t o = (size_t)my_prob * n_boot + res.start_id;
+                // src/boot_model.rs:86-91
+                double *row = rows_out + o * 7;
+                row[0] = res.theta[0];
+                row[1] = res.theta[1];
+                row[2] = res.theta[2];
+                row[3] = res.theta[3];
+                row[4] = p_mm_est(res.theta[0], res.theta[1]);
+                row[5] = p_um_est(res.theta[0], res.theta[1]);
+                row[6] = p_uu_est(res.theta[0], res.theta[1]);
+                if (fits_out) store_fit(fits_out + o, res);
+            }
+        }
+    }
 }
 
 }  // namespace abfit

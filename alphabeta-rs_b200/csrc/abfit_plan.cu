@@ -461,6 +461,37 @@ std::vector<WorkItem> make_items_wide(const HostPlan &hp, int count_per_prob, in
     return items;
 }
 
+std::vector<WorkItem> make_items_guided(const HostPlan &hp, int count_per_prob, int resident_warps, int max_chunk,
+                                        bool skip_nan)
+{
+    const int n_probs = (int)hp.probs.size();
+    int64_t remaining = 0;
+    for (int p = 0; p < n_probs; ++p)
+        if (!(skip_nan && hp.d_has_nan[p])) remaining += count_per_prob;
+    const int64_t P2 = 2 * (int64_t)std::max(resident_warps, 1);
+    if (const char *fc = getenv("ABFIT_DEV_CHUNK")) max_chunk = std::max(1, atoi(fc));
+    std::vector<WorkItem> items;
+    for (int p = 0; p < n_probs; ++p) {
+        if (skip_nan && hp.d_has_nan[p]) continue;
+        for (int f = 0; f < count_per_prob;) {
+            int64_t chunk = remaining / P2;
+            chunk = std::min<int64_t>(std::max<int64_t>(chunk, 32), max_chunk);
+            chunk = (chunk / 32) * 32 > 0 ? (chunk / 32) * 32 : chunk;  // whole rounds of a warp
+            int c = (int)std::min<int64_t>(chunk, count_per_prob - f);
+            if (count_per_prob - f - c < 16 && count_per_prob - f - c > 0) c = count_per_prob - f;  // no crumbs
+            WorkItem it;
+            it.prob = p;
+            it.first = f;
+            it.count = c;
+            it.pad = 0;
+            items.push_back(it);
+            f += c;
+            remaining -= c;
+        }
+    }
+    return items;
+}
+
 std::vector<WorkItem> make_items(const HostPlan &hp, int count_per_prob, int n_sm, int n_warps, bool skip_nan)
 {
     // One block per item.  Enough blocks to fill the machine several times over, but chunks as

@@ -53,4 +53,11 @@ double nm_var_threshold(double sd_tol);
 // chunks of `count_per_prob` fits per problem; every block gets at least 32 * n_warps * 2 fits when it can
 std::vector<WorkItem> make_items(const HostPlan &hp, int count_per_prob, int n_sm, int n_warps, bool skip_nan);
 
+// Items of the continuous-scheduling kernels (persistent warps pulling from a global cursor): guided self-scheduling —
+// an item takes 1/(2 P) of the fits that are still unassigned (P = resident warps), at most `max_chunk` and one
+// window, at least 32 — so the bulk of a batch runs in long items and the warps run out of work within about one
+// fit of each other.
+std::vector<WorkItem> make_items_guided(const HostPlan &hp, int count_per_prob, int resident_warps, int max_chunk,
+                                        bool skip_nan);
+
 }  // namespace abfit

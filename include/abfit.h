@@ -243,6 +243,9 @@ int abfit_batch_fp64_instr_per_eval(abfit_batch *b, int32_t p, double *instr_out
  * NVRTC; policy and environment switches: csrc/abfit_api.cu::decide_jit), 0 for the interpreter kernels.  Results
  * are bit-identical either way. */
 int abfit_batch_uses_specialised_kernels(abfit_batch *b);
+/* why the last attempt to build or load specialised kernels failed in this process ("" if none did); the batch
+ * concerned ran on the interpreter kernels */
+const char *abfit_jit_last_error(void);
 /* Diagnostic (no GPU needed): writes the CUDA C++ source specialised for `prob`'s pedigree to source_path and, when
  * cubin_path is not NULL, compiles it with NVRTC for sm_100a and writes the cubin (tests build the same source
  * for the host and compare it with the oracle; cuobjdump -sass on the cubin shows what the GPU runs). */

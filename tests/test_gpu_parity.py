@@ -737,11 +737,15 @@ def test_resample_index_check_large_pedigree(ab, ctx):
     assert e.value.code == ab.ERR_ARG
 
 
-@pytest.mark.parametrize("env", [{}, {"ABFIT_DEV_NWARPS": "3", "ABFIT_DEV_CHUNK": "150"}, {"ABFIT_DEV_NWARPS": "4"}])
+@pytest.mark.parametrize("env", [{}, {"ABFIT_DEV_CHUNK": "40"}, {"ABFIT_DEV_CHUNK": "7"},
+                                 {"ABFIT_DEV_SCHED": "1", "ABFIT_DEV_NWARPS": "3", "ABFIT_DEV_CHUNK": "150"},
+                                 {"ABFIT_DEV_SCHED": "1", "ABFIT_DEV_NWARPS": "4"}, {"ABFIT_DEV_SCHED": "1"}])
 def test_specialised_kernels_are_bit_identical(ab, ctx, oracle, ped351, ped78, monkeypatch, env):
     """run-time specialised kernels (csrc/abfit_jit.cu: the batch's one micro-op program compiled to straight-line
-    code by NVRTC) against the interpreter kernels and the oracle: every start, every bootstrap row, same bits —
-    one-warp blocks, 3-warp blocks with queue + tail hand-off, 4-warp blocks"""
+    code by NVRTC) against the interpreter kernels and the oracle: every start, every bootstrap row, same bits.
+    Default = continuous lane scheduling (persistent warps, two window slots per warp; small chunks force constant
+    slot switching and waiting for stragglers); ABFIT_DEV_SCHED=1 = the block-per-item bodies on the specialised
+    objective (one-warp blocks, 3-warp blocks with queue + tail hand-off, 4-warp blocks)"""
     rng = np.random.default_rng(55)
     for shape_ped, n_keep in ((ped351, None), (ped351, 123), (ped78[0], None)):
         base, u0 = synth_problem(rng, shape_ped, n_keep=n_keep)
@@ -768,7 +772,7 @@ def test_specialised_kernels_are_bit_identical(ab, ctx, oracle, ped351, ped78, m
         got = ctx.alphabeta_batch(probs, sx, idx, SEED)
         b1 = ctx.batch(probs)
         b1.upload_starts(sx)
-        assert b1.uses_specialised_kernels()
+        assert b1.uses_specialised_kernels(), ab.jit_last_error()
         b1.run_fit()
         got_all = b1.download_fit(want_all=True).all
         b1.close()
@@ -782,6 +786,57 @@ def test_specialised_kernels_are_bit_identical(ab, ctx, oracle, ped351, ped78, m
         for f in ("theta", "cost", "lse", "iters", "evals", "status", "start_id"):
             assert np.array_equal(got_all[2][f], allr[f]), f
         monkeypatch.delenv("ABFIT_JIT")
+
+
+@pytest.mark.parametrize("n_starts,n_boot", [(1, 1), (33, 31), (97, 100), (257, 7)])
+def test_specialised_kernels_ragged_counts(ab, ctx, oracle, ped351, monkeypatch, n_starts, n_boot):
+    """continuous lane scheduling with start / replicate counts that fill neither warps nor items; three windows of
+    one program; every start and every bootstrap row bit-identical to the oracle"""
+    rng = np.random.default_rng(900 + n_starts)
+    base, _ = synth_problem(rng, ped351, n_keep=77)
+    cases = []
+    for _ in range(3):
+        p = base.copy()
+        p[:, 3] = np.maximum(base[:, 3] * rng.uniform(0.7, 1.3) + rng.normal(0, 3e-4, len(base)), 0.0)
+        cases.append((p, float(rng.uniform(0.6, 0.95))))
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    idx = np.concatenate([ab.gen_resample_idx(SEED, i, n_boot, len(p)).ravel() for i, (p, u) in enumerate(cases)])
+    monkeypatch.setenv("ABFIT_JIT", "1")
+    b = ctx.batch(probs)
+    b.upload_starts(sx)
+    assert b.uses_specialised_kernels(), ab.jit_last_error()
+    b.run_fit()
+    res = b.download_fit(want_all=True)
+    vary = np.stack([ab.gen_vary_vertices(SEED, i, n_boot, res.best[i]["theta"]) for i in range(len(cases))])
+    b.upload_boot(idx, vary)
+    b.run_boot()
+    rows, fits = b.download_boot(want_fits=True)
+    b.close()
+    flags = oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL
+    off = 0
+    for i, (p, u) in enumerate(cases):
+        n = len(p)
+        check_fit_against_oracle(ab, oracle, res, i, oracle.Problem(p, u, u, 1.0), sx[i], 10000, flags, off, n)
+        rc, orows, ofits = oracle.boot_model(oracle.Problem(p, u, u, 1.0), res.best[i]["theta"], res.pred[off:off + n],
+                                             res.resid[off:off + n], idx[off * n_boot:(off + n) * n_boot].reshape(n_boot, n),
+                                             vary[i], max_iters=1000, flags=flags, n_threads=8)
+        assert rc == 0 and np.array_equal(rows[i], orows)
+        assert np.array_equal(fits[i]["evals"], ofits["evals"])
+        off += n
+    # an out-of-range resample index is reported by the specialised bootstrap kernel too
+    if n_boot > 1:
+        bad = idx.copy()
+        bad[5] = len(cases[0][0])
+        b = ctx.batch(probs)
+        b.upload_starts(sx)
+        b.run_fit()
+        b.upload_boot(bad, vary)
+        b.run_boot()
+        with pytest.raises(ab.AbfitError) as e:
+            b.download_boot()
+        assert e.value.code == ab.ERR_ARG
+        b.close()
 
 
 def test_specialised_kernels_mixed_batch_falls_back_to_interpreter(ab, ctx, ped351, ped78, monkeypatch):
