@@ -489,7 +489,7 @@ int abfit_batch_run_fit(abfit_batch *b, int32_t max_iters, double sd_tol, uint32
     }
     ABFIT_CUDA(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->ctx->stream;
-    NMParams nm{max_iters, sd_tol, flags, nm_var_threshold(sd_tol)};
+    const NMParams nm = nm_params(max_iters, sd_tol, flags);
     // records of skipped (NaN) problems read back as status -1 / NaN
     ABFIT_CUDA(cudaMemsetAsync(b->d_all.p, 0xFF, (size_t)b->n_probs * b->n_starts * sizeof(abfit_fit), st));
     ABFIT_CUDA(cudaMemsetAsync(b->d_evals_fit.p, 0, (size_t)b->n_probs * 8, st));
@@ -504,7 +504,7 @@ int abfit_batch_run_fit(abfit_batch *b, int32_t max_iters, double sd_tol, uint32
         if (int rc = jit_launch_fit_starts_v2(b->jit, st, b->pools, b->d_items.p, b->n_items,
                                               (int64_t)b->n_probs * b->n_starts, b->jit_warps_fit, b->d_cursor.p,
                                               b->d_simplices.p, b->n_starts, nm, b->d_all.p, b->d_evals_fit.p,
-                                              jit_smem_fit_v2(b->hp.probs[0])))
+                                              jit_smem_fit_v2(b->jit, b->hp.probs[0])))
             return rc;
     } else if (b->jit) {
         if (int rc = jit_launch_fit_starts(b->jit, st, b->pools, b->d_items.p, b->n_items, b->shape.n_warps,
@@ -630,7 +630,7 @@ int abfit_batch_run_boot(abfit_batch *b, int32_t max_iters, double sd_tol, uint3
     }
     ABFIT_CUDA(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->ctx->stream;
-    NMParams nm{max_iters, sd_tol, flags, nm_var_threshold(sd_tol)};
+    const NMParams nm = nm_params(max_iters, sd_tol, flags);
     ABFIT_CUDA(cudaMemsetAsync(b->d_rows.p, 0xFF, (size_t)b->n_probs * b->n_boot * 7 * 8, st));
     ABFIT_CUDA(cudaMemsetAsync(b->d_bootfits.p, 0xFF, (size_t)b->n_probs * b->n_boot * sizeof(abfit_fit), st));
     ABFIT_CUDA(cudaMemsetAsync(b->d_evals_boot.p, 0, (size_t)b->n_probs * 8, st));
@@ -649,7 +649,7 @@ int abfit_batch_run_boot(abfit_batch *b, int32_t max_iters, double sd_tol, uint3
                                                    b->n_boot, b->d_best.p, b->d_pred.p, b->d_resid.p, b->d_idx.p,
                                                    b->d_vary.p, b->d_scratch.p, (int64_t)((b->hp.max_pairs + 3) / 4) * 32,
                                                    nm, b->d_rows.p, b->d_bootfits.p, b->d_evals_boot.p,
-                                                   jit_smem_boot_v2(b->hp.probs[0]), b->d_booterr.p))
+                                                   jit_smem_boot_v2(b->jit, b->hp.probs[0]), b->d_booterr.p))
             return rc;
     } else if (b->shape.smem_boot_gather && b->jit) {
         // specialised index-tile kernel: 33 doubles of shared memory per lane, the simplex always fits

@@ -500,12 +500,12 @@ __device__ __forceinline__ void fit_boot_gather_body(const DevicePools &P, const
 //     sizes follow guided self-scheduling on the host (large first, 32 at the end: make_items_guided), so all
 //     warps run out of work within about one fit of each other;
 //   * a lane that finishes a fit takes the next fit of the open item AT ONCE, even when the item belongs to
-//     another window than the fits still running on its neighbours: a warp keeps two window slots in shared
+//     another window than the fits still running on its neighbours: a warp keeps V2_SLOTS window slots in shared
 //     memory (D column + the window's scalars), every lane points at the slot of its own window.  The objective
-//     is the same instruction stream for every lane — only the broadcast loads of D become two-address loads
-//     while two windows overlap;
-//   * a new item is opened into the slot that has no running fits (its predecessor's last fits have finished by
-//     then: an item lasts several fits per lane).
+//     is the same instruction stream for every lane — only the broadcast loads of D become multi-address loads
+//     while windows overlap;
+//   * a new item is opened into a slot that has no running fits; with four slots even an item of one fit per
+//     lane finds one (measured with two: mid-sized items kept idle lanes waiting for a predecessor's long fits).
 //
 // No block-wide synchronisation, no inter-block waiting (the cursor is only ever incremented).  A fit's arithmetic
 // does not depend on which lane, warp or slot runs it: same bits as the block-per-item kernels.
@@ -529,20 +529,20 @@ __device__ __forceinline__ WarpCtx v2_ctx(const double *D, const double *scal, i
 
 // warp-uniform bookkeeping of the open item
 struct V2Queue {
-    int cur = -1;       // slot being filled from (-1: none yet)
+    int cur = 0;  // slot being filled from
     int next = 0, end = 0, prob = 0;
     bool exhausted = false;
 };
 
-// Opens the next item when the current one is used up.  Returns false when idle lanes have to wait (the other
-// slot still has running fits) or no items are left.  `users_other` = lanes running on the slot to be reused.
+// Opens the next item when the current one is used up.  Returns false when idle lanes have to wait (every slot
+// still has running fits) or no items are left.  `busy`: bit s set = slot s has running fits.
 template <class STAGE>
 __device__ __forceinline__ bool v2_open_next(V2Queue &q, const WorkItem *__restrict__ items, int n_items, int *cursor,
-                                             int lane, unsigned users_other, STAGE stage)
+                                             int lane, unsigned busy, STAGE stage)
 {
     if (q.exhausted) return false;
-    const int other = q.cur < 0 ? 0 : (q.cur ^ 1);
-    if (q.cur >= 0 && users_other) return false;
+    const int slot = __ffs(~busy) - 1;  // first slot without running fits
+    if (slot >= V2_SLOTS) return false;
     int idx = 0;
     if (lane == 0) idx = atomicAdd(cursor, 1);
     idx = __shfl_sync(FULL, idx, 0);
@@ -551,12 +551,21 @@ __device__ __forceinline__ bool v2_open_next(V2Queue &q, const WorkItem *__restr
         return false;
     }
     const WorkItem it = items[idx];
-    q.cur = other;
+    q.cur = slot;
     q.next = it.first;
     q.end = it.first + it.count;
     q.prob = it.prob;
-    stage(other, it.prob);
+    stage(slot, it.prob);
     return true;
+}
+
+// bit s = some lane runs a fit on slot s
+__device__ __forceinline__ unsigned v2_busy_slots(bool active, int my_slot)
+{
+    unsigned busy = 0;
+#pragma unroll
+    for (int s = 0; s < V2_SLOTS; ++s) busy |= (__ballot_sync(FULL, active && my_slot == s) ? 1u : 0u) << s;
+    return busy;
 }
 
 template <class OBJ>
@@ -597,8 +606,7 @@ __device__ __forceinline__ void fit_starts_body_v2(const DevicePools &P, const W
         unsigned idle = __ballot_sync(FULL, L.phase == PH_IDLE);
         while (idle) {
             if (q.next >= q.end) {
-                const unsigned users_other = __ballot_sync(FULL, L.phase != PH_IDLE && my_slot != q.cur);
-                if (!v2_open_next(q, items, n_items, cursor, lane, users_other, stage)) break;
+                if (!v2_open_next(q, items, n_items, cursor, lane, v2_busy_slots(L.phase != PH_IDLE, my_slot), stage)) break;
             }
             const int take = min(__popc(idle), q.end - q.next);
             const int rank = __popc(idle & ((1u << lane) - 1u));
@@ -633,7 +641,7 @@ __device__ __forceinline__ void fit_starts_body_v2(const DevicePools &P, const W
 }
 
 // bootstrap refits (src/boot_model.rs:41-100), index-tile formulation (see DGather): a slot holds the window's
-// residuals, predictions, scalars and best model; the lane's resample indices are packed as SHARED-MEMORY BYTE
+// residuals, scalars and best model; the lane's resample indices are packed as SHARED-MEMORY BYTE
 // OFFSETS of the residuals in the lane's slot, so the gather address is again "tile value + link-time constant".
 template <class OBJ>
 __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, const WorkItem *__restrict__ items, int n_items,
@@ -657,22 +665,20 @@ __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, co
     double *slots = smem + 25 * 32;
     const int ng4 = (n_pairs + 3) >> 2;
     uint2 *tile = idx_scratch + (size_t)blockIdx.x * (size_t)scratch_stride + lane;
-    // slot: [resid npad][pred npad][p_uu0, p_mm0, eqp, penw][best theta 4]
+    // slot: [resid npad][p_uu0, p_mm0, eqp, penw][best theta 4]; the window's predictions stay in global memory and
+    // are read through L1 (the same address for every lane of a window), which keeps four slots within 12 KB
     auto stage = [&](int slot, int prob) {
         const DevProblem pb = P.probs[prob];
         double *sl = slots + slot * slot_doubles;
-        for (int i = lane; i < pb.n_pairs; i += 32) {
-            sl[i] = resid[pb.pair_off + i];
-            sl[npad + i] = pred[pb.pair_off + i];
-        }
+        for (int i = lane; i < pb.n_pairs; i += 32) sl[i] = resid[pb.pair_off + i];
         if (lane == 0) {
             const abfit_fit bm = best[prob];
-            sl[2 * npad] = pb.p_uu0;
-            sl[2 * npad + 1] = pb.p_mm0;
-            sl[2 * npad + 2] = pb.eqp;
-            sl[2 * npad + 3] = pb.penw;
+            sl[npad] = pb.p_uu0;
+            sl[npad + 1] = pb.p_mm0;
+            sl[npad + 2] = pb.eqp;
+            sl[npad + 3] = pb.penw;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) sl[2 * npad + 4 + k] = bm.theta[k];
+            for (int k = 0; k < 4; ++k) sl[npad + 4 + k] = bm.theta[k];
         }
         __syncwarp();
     };
@@ -680,20 +686,21 @@ __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, co
     LaneNM L;
     lane_nm_reset(L);
     int my_slot = 0, my_prob = 0;
+    const double *my_pred = pred;
     V2Queue q;
     for (;;) {
         __syncwarp();
         unsigned idle = __ballot_sync(FULL, L.phase == PH_IDLE);
         while (idle) {
             if (q.next >= q.end) {
-                const unsigned users_other = __ballot_sync(FULL, L.phase != PH_IDLE && my_slot != q.cur);
-                if (!v2_open_next(q, items, n_items, cursor, lane, users_other, stage)) break;
+                if (!v2_open_next(q, items, n_items, cursor, lane, v2_busy_slots(L.phase != PH_IDLE, my_slot), stage)) break;
             }
             const int take = min(__popc(idle), q.end - q.next);
             const int rank = __popc(idle & ((1u << lane) - 1u));
             if (((idle >> lane) & 1u) && rank < take) {
                 const int id = q.next + rank;
                 const DevProblem pb = P.probs[q.prob];
+                my_pred = pred + pb.pair_off;
                 const double *sl = slots + q.cur * slot_doubles;
                 // this replicate's resample indices -> byte offsets of its residuals in shared memory
                 const uint32_t base = (uint32_t)((const char *)sl - (const char *)smem);
@@ -714,7 +721,7 @@ __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, co
                 // simplex = [best, vary x 4]  (src/boot_model.rs:69-75)
                 const double *vv = vary + ((size_t)q.prob * n_boot + id) * 16;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) S.X[k * 32] = sl[2 * npad + 4 + k];
+                for (int k = 0; k < 4; ++k) S.X[k * 32] = sl[npad + 4 + k];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) S.X[(4 + k) * 32] = vv[k];
                 nm_begin(L, S, id);
@@ -729,8 +736,8 @@ __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, co
         if (!amask) break;
         if (active) {
             const double *sl = slots + my_slot * slot_doubles;
-            const WarpCtx c = v2_ctx(nullptr, sl + 2 * npad, n_pairs);
-            const DGather Dat{tile, sl + npad, reinterpret_cast<const char *>(smem)};
+            const WarpCtx c = v2_ctx(nullptr, sl + npad, n_pairs);
+            const DGatherL1 Dat{tile, my_pred, reinterpret_cast<const char *>(smem)};
             const double f = OBJ::eval(c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
             abfit_fit res;
             if (nm_advance(L, S, nm, f, res, amask)) {

@@ -7,8 +7,14 @@ namespace abfit {
 #else
 #define ABFIT_HD_INLINE inline
 #endif
+// window slots per warp: a lane starts a fit of the open item's window while its neighbours finish fits of up to
+// V2_SLOTS - 1 earlier windows; with four, an item as short as one fit per lane is reopened without waiting
+#ifndef ABFIT_V2_SLOTS
+#define ABFIT_V2_SLOTS 4
+#endif
+constexpr int V2_SLOTS = ABFIT_V2_SLOTS;  // (a generated source may define another count: occupancy experiments)
 // multi-start slot: [D npad][p_uu0, p_mm0, eqp, penw]
 ABFIT_HD_INLINE int v2_fit_slot_doubles(int n_pairs) { return ((n_pairs + 1) & ~1) + 4; }
-// bootstrap slot: [resid npad][pred npad][p_uu0, p_mm0, eqp, penw][best theta 4]
-ABFIT_HD_INLINE int v2_boot_slot_doubles(int n_pairs) { return 2 * ((n_pairs + 1) & ~1) + 8; }
+// bootstrap slot: [resid npad][p_uu0, p_mm0, eqp, penw][best theta 4]  (the predictions are read through L1)
+ABFIT_HD_INLINE int v2_boot_slot_doubles(int n_pairs) { return ((n_pairs + 1) & ~1) + 8; }
 }  // namespace abfit

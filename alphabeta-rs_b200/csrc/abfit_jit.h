@@ -10,7 +10,7 @@ namespace abfit {
 
 constexpr int JIT_SPEC_NLANE = 8;    // per-lane shared doubles of a specialised kernel: the hand-off's parking area
 constexpr int JIT_MAX_PAIRS = 1024;  // unrolled pair loop: ~5.5 instructions per pair
-constexpr int JIT_MAX_SLOTS = 96;    // per-lane values of the program, all kept in registers
+constexpr int JIT_MAX_SLOTS = 160;   // per-lane values of the program, all kept in registers
 
 struct EmbeddedSource {
     const char *name;
@@ -21,6 +21,7 @@ struct JitModule {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t fit_starts = nullptr;
     cudaKernel_t fit_boot_gather = nullptr;
+    int slots = 4;  // window slots per warp (sched 2)
     int sched = 2;  // 1: block-per-item bodies, 2: continuous lane scheduling (persistent one-warp blocks)
     double compile_seconds = 0.0;
     bool from_disk_cache = false;
@@ -50,8 +51,8 @@ int jit_launch_fit_boot_gather(const JitModule *m, cudaStream_t st, DevicePools 
                                unsigned long long *evals_per_prob, size_t smem_bytes, int *err_flag, double *x_scratch);
 
 // continuous lane scheduling: persistent one-warp blocks, items opened from a global cursor (cursor: device int)
-size_t jit_smem_fit_v2(const DevProblem &pb);
-size_t jit_smem_boot_v2(const DevProblem &pb);
+size_t jit_smem_fit_v2(const JitModule *m, const DevProblem &pb);
+size_t jit_smem_boot_v2(const JitModule *m, const DevProblem &pb);
 int jit_resident_warps(const JitModule *m, bool boot, const DevProblem &pb, int n_sm);  // grid of a full machine
 int jit_launch_fit_starts_v2(const JitModule *m, cudaStream_t st, DevicePools P, const WorkItem *items, int n_items,
                              int64_t n_fits, int grid_max, int *cursor, const double *simplices, int n_starts, NMParams nm,

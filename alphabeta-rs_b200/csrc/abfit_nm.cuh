@@ -41,10 +41,14 @@ __device__ __forceinline__ int ord_at(uint32_t ord, int p) { return (ord >> (3 *
 
 // stable insertion sort of the five vertices by cost (sort_by(partial_cmp().unwrap_or(Equal)))
 // written as a fixed compare-exchange sequence; with strict '<' it performs exactly the
-// swaps the insertion sort would, NaNs included.
-__device__ __forceinline__ uint32_t sort5(const LaneSimplex &S, uint32_t ord)
+// swaps the insertion sort would, NaNs included.  The sorted costs are returned in c[].
+//
+// FULL = false: only the vertex at sorted position 4 (the one an iteration replaces) may be out of place.  The
+// first four come out of an earlier call, i.e. no adjacent pair of them satisfies c[j] < c[j-1], so the six
+// compare-exchanges of insertion steps 1..3 would not swap anything: only step 4 is executed.  Same result.
+template <bool FULL>
+__device__ __forceinline__ uint32_t sort5(const LaneSimplex &S, uint32_t ord, double c[5])
 {
-    double c[5];
     int o[5];
 #pragma unroll
     for (int p = 0; p < 5; ++p) {
@@ -52,7 +56,7 @@ __device__ __forceinline__ uint32_t sort5(const LaneSimplex &S, uint32_t ord)
         c[p] = S.c(o[p]);
     }
 #pragma unroll
-    for (int i = 1; i < 5; ++i)
+    for (int i = FULL ? 1 : 4; i < 5; ++i)
 #pragma unroll
         for (int j = i; j >= 1; --j) {
             const bool sw = c[j] < c[j - 1];
@@ -108,6 +112,11 @@ struct NMParams {
     // largest y with sqrt(y) < sd_tol (host: nm_var_threshold).  IEEE sqrt is correctly rounded and
     // therefore monotonic, so  sqrt(y) < sd_tol  <=>  y <= var_thr  and the kernels never take the root.
     double var_thr;
+    // Quick reject of the termination test (host: nm_range_threshold): when the spread of the sorted costs,
+    // c[4] - c[0], exceeds this, 0.25 * ss > var_thr is certain — whatever the mean rounds to, one of the two
+    // extreme costs is at least half the spread away from it — and the exact test (a division and ~25 dependent
+    // FP64 operations per iteration) is skipped.  The decision is the same as the exact test's, always.
+    double range_thr;
 };
 
 // Consume the objective value f of the lane's current trial point and advance the
@@ -122,6 +131,7 @@ __device__ __forceinline__ bool nm_advance(LaneNM &L, const LaneSimplex &S, cons
                                            abfit_fit &res, unsigned amask)
 {
     bool iter_done = false;   // an NM iteration (or init) completed: sort + termination test follow
+    bool full_sort = false;   // ... and more than the worst vertex changed (init, shrink)
     bool finish = false;      // go to the final LSE evaluation
     bool done = false;        // the fit has ended (result in `res`)
     const int ph = L.phase;
@@ -200,6 +210,7 @@ __device__ __forceinline__ bool nm_advance(LaneNM &L, const LaneSimplex &S, cons
                 L.xt[3] = nx[224];
             } else {
                 iter_done = true;  // sort + termination test of the Executor's first loop pass
+                full_sort = true;
                 L.iters = -1;      // the shared tail below counts an iteration; init is not one
             }
             break;
@@ -216,6 +227,7 @@ __device__ __forceinline__ bool nm_advance(LaneNM &L, const LaneSimplex &S, cons
                 shrink_point(S, L.ord, k + 1, L.xt);
             } else {
                 iter_done = true;
+                full_sort = true;
             }
             break;
         }
@@ -240,24 +252,26 @@ __device__ __forceinline__ bool nm_advance(LaneNM &L, const LaneSimplex &S, cons
 
     __syncwarp(amask);
     if (iter_done) {
-        L.ord = sort5(S, L.ord);  // sort_param_vecs (stable)
+        double c[5];
+        L.ord = full_sort ? sort5<true>(S, L.ord, c) : sort5<false>(S, L.ord, c);  // sort_param_vecs (stable)
         ++L.iters;
         // Executor: terminate_internal at the top of the next iteration
-        double c[5];
+        bool sd_small = false;
+        if (!(c[4] - c[0] > P.range_thr)) {  // else: certainly not converged (NMParams::range_thr)
+            double sum = 0.0;
 #pragma unroll
-        for (int p = 0; p < 5; ++p) c[p] = S.c(ord_at(L.ord, p));
-        double sum = 0.0;
+            for (int p = 0; p < 5; ++p) sum += c[p];
+            const double c0 = sum / 5.0;
+            double ss = 0.0;
 #pragma unroll
-        for (int p = 0; p < 5; ++p) sum += c[p];
-        const double c0 = sum / 5.0;
-        double ss = 0.0;
-#pragma unroll
-        for (int p = 0; p < 5; ++p) {
-            const double d = c[p] - c0;
-            ss += d * d;
+            for (int p = 0; p < 5; ++p) {
+                const double d = c[p] - c0;
+                ss += d * d;
+            }
+            // sd = sqrt(1/(n-1) * ss) < sd_tolerance, evaluated without the root (see NMParams::var_thr)
+            sd_small = 1.0 / (5.0 - 1.0) * ss <= P.var_thr;
         }
-        // sd = sqrt(1/(n-1) * ss) < sd_tolerance, evaluated without the root (see NMParams::var_thr)
-        if (1.0 / (5.0 - 1.0) * ss <= P.var_thr) {
+        if (sd_small) {
             L.status = ABFIT_TERM_SD;
             finish = true;
         } else if (L.iters >= P.max_iters) {

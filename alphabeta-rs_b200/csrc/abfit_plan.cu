@@ -334,6 +334,26 @@ double nm_var_threshold(double sd_tol)
     return std::sqrt(y) < sd_tol ? y : -1.0;
 }
 
+double nm_range_threshold(double var_thr)
+{
+    if (var_thr < 0.0) return -1.0;  // the sd test can never fire: every spread (>= 0) rejects, NaN costs take the exact path
+    const double t = 8.0 * std::sqrt(var_thr);  // 4 sqrt(var_thr) suffices in exact arithmetic; the factor 2 covers every rounding
+    // spreads whose square is not a normal double are left to the exact test
+    if (!(t >= 1e-140) || std::isinf(t)) return INFINITY;
+    return t;
+}
+
+NMParams nm_params(int max_iters, double sd_tol, uint32_t flags)
+{
+    NMParams nm;
+    nm.max_iters = max_iters;
+    nm.sd_tol = sd_tol;
+    nm.flags = flags;
+    nm.var_thr = nm_var_threshold(sd_tol);
+    nm.range_thr = nm_range_threshold(nm.var_thr);
+    return nm;
+}
+
 int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm, int fits_per_prob, LaunchShape &out)
 {
     auto worst = [&](int simplex_doubles, bool d_shared, int nw) {

@@ -49,6 +49,9 @@ int choose_launch_shape(const HostPlan &hp, size_t smem_cap, size_t smem_per_sm,
 // largest y with sqrt(y) < sd_tol (-1 when no y >= 0 qualifies): lets the kernels evaluate argmin's
 // `sd < sd_tolerance` termination test without taking the square root (see NMParams::var_thr)
 double nm_var_threshold(double sd_tol);
+// spread of the sorted simplex costs above which the termination test certainly fails (NMParams::range_thr)
+double nm_range_threshold(double var_thr);
+NMParams nm_params(int max_iters, double sd_tol, uint32_t flags);
 
 // chunks of `count_per_prob` fits per problem; every block gets at least 32 * n_warps * 2 fits when it can
 std::vector<WorkItem> make_items(const HostPlan &hp, int count_per_prob, int n_sm, int n_warps, bool skip_nan);

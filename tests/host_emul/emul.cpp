@@ -76,7 +76,7 @@ int emul_cost(const abfit_problem *pb, const double *theta, int B, double *cost,
 int emul_fit(const abfit_problem *pb, const double *simplices, int n, const double *dstar, int max_iters,
              double sd_tol, uint32_t flags, abfit_fit *out)
 {
-    NMParams nm{max_iters, sd_tol, flags, nm_var_threshold(sd_tol)};
+    const NMParams nm = nm_params(max_iters, sd_tol, flags);
     for (int f = 0; f < n; ++f) {
         const int lane = f & 31;
         Staged s;
@@ -153,7 +153,7 @@ int emul_cost_wide(const abfit_problem *pb, const double *theta, int B, double *
 int emul_fit_wide(const abfit_problem *pb, const double *simplices, int n, const double *dstar, int max_iters,
                   double sd_tol, uint32_t flags, abfit_fit *out)
 {
-    NMParams nm{max_iters, sd_tol, flags, nm_var_threshold(sd_tol)};
+    const NMParams nm = nm_params(max_iters, sd_tol, flags);
     StagedWide s;
     if (int rc = stage_wide(pb, s)) return rc;
     for (int f = 0; f < n; ++f) {
@@ -195,6 +195,7 @@ int emul_launch_shape(const abfit_problem *pb, int n_probs, int fits_per_prob, i
 }
 
 double emul_var_threshold(double sd_tol) { return nm_var_threshold(sd_tol); }
+double emul_range_threshold(double var_thr) { return nm_range_threshold(var_thr); }
 
 // plan statistics: per-lane doubles, micro-ops, events, chain length
 int emul_plan_stats(const abfit_problem *pb, int32_t out[6])

@@ -51,11 +51,11 @@ int spec_cost(const abfit_problem *pb, const double *theta, int B, double *cost,
 // one Nelder-Mead run per simplex, the state machine driven as the kernels drive it; dstar: optional per-fit D*
 // columns [n][n_pairs] read through the per-lane column accessor (bootstrap replicates)
 int spec_fit(const abfit_problem *pb, const double *simplices, int n, const double *dstar, int max_iters, double sd_tol,
-             uint32_t flags, double var_thr, abfit_fit *out)
+             uint32_t flags, double var_thr, double range_thr, abfit_fit *out)
 {
     std::vector<double> D;
     const WarpCtx c = make_ctx(pb, D);
-    NMParams nm{max_iters, sd_tol, flags, var_thr};
+    NMParams nm{max_iters, sd_tol, flags, var_thr, range_thr};
     std::vector<double> simplex(25 * 32), tile;
     for (int f = 0; f < n; ++f) {
         const int lane = f & 31;

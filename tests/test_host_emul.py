@@ -194,8 +194,10 @@ def spec_fit(lib, ab, emul, ped, p0uu, sx, max_iters=10000, flags=0, dstar=None)
     dp = None if dstar is None else np.ascontiguousarray(dstar, dtype=np.float64).ctypes.data_as(C.c_void_p)
     emul.emul_var_threshold.restype = C.c_double
     thr = emul.emul_var_threshold(C.c_double(ab.DBL_EPSILON))
+    emul.emul_range_threshold.restype = C.c_double
+    rthr = emul.emul_range_threshold(C.c_double(thr))
     assert lib.spec_fit(arr, sx.ctypes.data_as(C.c_void_p), n, dp, max_iters, C.c_double(ab.DBL_EPSILON), flags,
-                        C.c_double(thr), out.ctypes.data_as(C.c_void_p)) == 0
+                        C.c_double(thr), C.c_double(rthr), out.ctypes.data_as(C.c_void_p)) == 0
     return out
 
 
