@@ -89,6 +89,9 @@ def _load() -> C.CDLL:
         "abfit_gen_vary_vertices": (None, [u64, u64, i32, vp, vp]),
         "abfit_gen_resample_idx": (None, [u64, u64, i32, i32, vp]),
         "abfit_gen_vary_vertices_batch": (None, [u64, u64, i32, i32, vp, vp]),
+        "abfit_device_count": (C.c_int, []),
+        "abfit_alphabeta_batch_multi": (C.c_int, [vp, i32, vp, i32, i32, vp, i32, vp, u64, u64, vp, i32, i32, dbl, u32, vp, vp, vp, vp, vp, vp]),
+        "abfit_divergence_multi": (C.c_int, [vp, i32, vp, vp, vp, i32, i64, vp, i32, dbl, vp, vp, vp, vp, vp, vp]),
         "abfit_alphabeta_batch": (C.c_int, [vp, PP, i32, i32, vp, i32, vp, u64, u64, i32, i32, dbl, u32, vp, vp, vp, vp, vp, vp]),
         "abfit_cost_batch": (C.c_int, [vp, PP, i32, vp, vp, i32, vp, vp]),
         "abfit_model_divergence": (C.c_int, [vp, PP, vp, vp, vp]),
@@ -104,6 +107,8 @@ def _load() -> C.CDLL:
         "abfit_batch_upload_boot": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
         "abfit_batch_run_boot": (C.c_int, [vp, i32, dbl, u32]),
         "abfit_batch_download_boot": (C.c_int, [vp, vp, vp]),
+        "abfit_batch_run_pipelined": (C.c_int, [vp, i32, i32, dbl, u32]),
+        "abfit_batch_pipes": (C.c_int, [vp]),
         "abfit_batch_sync": (C.c_int, [vp]),
         "abfit_batch_timing": (C.c_int, [vp, vp, vp, C.POINTER(i32)]),
         "abfit_batch_flops_per_eval": (C.c_int, [vp, i32, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i32)]),
@@ -143,9 +148,9 @@ EXPORTED_SYMBOLS = (
     "abfit_ctx_timer_start abfit_ctx_timer_stop abfit_ctx_sync "
     "abfit_gen_start_simplices abfit_gen_vary_vertices abfit_gen_vary_vertices_batch abfit_gen_resample_idx "
     "abfit_alphabeta_batch abfit_cost_batch "
-    "abfit_model_divergence abfit_fit_batch abfit_boot_batch abfit_divergence abfit_divergence_device abfit_batch_create "
+    "abfit_device_count abfit_model_divergence abfit_fit_batch abfit_boot_batch abfit_alphabeta_batch_multi abfit_divergence abfit_divergence_multi abfit_divergence_device abfit_batch_create "
     "abfit_batch_destroy abfit_batch_upload_starts abfit_batch_run_fit abfit_batch_download_fit "
-    "abfit_batch_upload_boot abfit_batch_run_boot abfit_batch_download_boot abfit_batch_sync "
+    "abfit_batch_upload_boot abfit_batch_run_boot abfit_batch_download_boot abfit_batch_run_pipelined abfit_batch_pipes abfit_batch_sync "
     "abfit_batch_timing abfit_batch_flops_per_eval abfit_batch_fp64_instr_per_eval abfit_batch_uses_specialised_kernels abfit_jit_dump abfit_jit_last_error abfit_analyze abfit_window_counts abfit_place_sites "
     "abfit_parse_methylome_line abfit_parse_annotation_line abfit_pedigree_graph abfit_pedigree_build abfit_pedigree_info abfit_pedigree_rows abfit_pedigree_warnings "
     "abfit_pedigree_free abfit_format_f64 abfit_steady_state abfit_write_pedigree abfit_write_analysis abfit_format_analysis "
@@ -248,6 +253,49 @@ def jit_dump(prob: "Problem", source_path: Optional[str] = None, cubin_path: Opt
     _check(_lib.abfit_jit_dump(arr, None if source_path is None else source_path.encode(),
                                None if cubin_path is None else cubin_path.encode(), C.byref(secs)))
     return secs.value
+
+
+def device_count() -> int:
+    return int(_lib.abfit_device_count())
+
+
+def alphabeta_batch_multi(ctxs: Sequence["Context"], probs, simplices, resample_idx, seed, first_problem_id=0,
+                          problem_ids=None, max_iters_fit=10000, max_iters_boot=1000, sd_tol=DBL_EPSILON, flags=0):
+    """abfit_alphabeta_batch_multi: alphabeta::run for every window, windows sharded over the contexts' GPUs (one host
+    thread per device, no collective) -> the dict Context.alphabeta_batch returns, in window order."""
+    n_probs = len(probs)
+    simplices = _f64(simplices)
+    n_starts = simplices.size // (n_probs * 20)
+    idx = np.ascontiguousarray(resample_idx, dtype=np.int32)
+    total = sum(p.n_pairs for p in probs)
+    n_boot = idx.size // total
+    best = np.zeros(n_probs, dtype=FIT_DTYPE)
+    pred, resid = np.empty(total), np.empty(total)
+    status = np.zeros(n_probs, dtype=np.int32)
+    rows, analysis = np.empty((n_probs, n_boot, 7)), np.empty((n_probs, 32))
+    ids = None if problem_ids is None else np.ascontiguousarray(problem_ids, dtype=np.uint64)
+    hs = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    _check(_lib.abfit_alphabeta_batch_multi(hs, len(ctxs), _pack_problems(probs), n_probs, n_starts, _ptr(simplices), n_boot,
+                                            _ptr(idx), seed, first_problem_id, _ptr(ids), max_iters_fit, max_iters_boot, sd_tol,
+                                            flags, _ptr(best), _ptr(pred), _ptr(resid), _ptr(status), _ptr(rows), _ptr(analysis)))
+    return {"best": best, "pred": pred, "resid": resid, "status": status, "rows": rows, "analysis": analysis}
+
+
+def dmatrix_multi(ctxs: Sequence["Context"], status, posterior_max, meth_lvl, thr=0.99, seg_offsets=None):
+    """abfit_divergence_multi: windows (or, for one window, the site axis) sharded over the contexts' GPUs"""
+    status = np.ascontiguousarray(status, dtype=np.uint8)
+    post, meth = _f64(posterior_max), _f64(meth_lvl)
+    S, L = status.shape
+    seg = None if seg_offsets is None else np.ascontiguousarray(seg_offsets, dtype=np.int64)
+    W = 1 if seg is None else len(seg) - 1
+    P = S * (S - 1) // 2
+    D = np.empty((W, P))
+    diff, cnt = np.empty((W, P), dtype=np.uint64), np.empty((W, P), dtype=np.uint64)
+    p0uu, methsum, nvalid = np.empty(W), np.empty((W, S)), np.empty((W, S), dtype=np.int64)
+    hs = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    _check(_lib.abfit_divergence_multi(hs, len(ctxs), _ptr(status), _ptr(post), _ptr(meth), S, L, _ptr(seg), W, thr, _ptr(D),
+                                       _ptr(diff), _ptr(cnt), _ptr(p0uu), _ptr(methsum), _ptr(nvalid)))
+    return {"D": D, "diff": diff, "cnt": cnt, "p0uu": p0uu, "methsum": methsum, "nvalid": nvalid}
 
 
 @dataclass
@@ -532,6 +580,13 @@ class Batch:
 
     def run_boot(self, max_iters=1000, sd_tol=DBL_EPSILON, flags=0):
         _check(_lib.abfit_batch_run_boot(self._h, max_iters, sd_tol, flags))
+
+    def run_pipelined(self, max_iters_fit=10000, max_iters_boot=1000, sd_tol=DBL_EPSILON, flags=0):
+        """run_fit + run_boot as one pipelined pass over sub-batches of windows (abfit_batch_run_pipelined)"""
+        _check(_lib.abfit_batch_run_pipelined(self._h, max_iters_fit, max_iters_boot, sd_tol, flags))
+
+    def pipes(self) -> int:
+        return int(_lib.abfit_batch_pipes(self._h))
 
     def download_boot(self, want_fits=False, rows=None):
         rows = np.empty((self.n_probs, self.n_boot, 7)) if rows is None else rows

@@ -5,7 +5,7 @@
 // per window (src/cli/metaprofile.rs:50-72).
 //
 //   metaprofile -m <methylome dir> -g <annotation> [-w 5] [-s 0] [-o .] [-a] [-c 2048] [-i] [--name N]
-//               [--cutoff-gene-length] [--iterations 100] [--seed N] [--device 0]
+//               [--cutoff-gene-length] [--iterations 100] [--seed N] [--device 0 | --devices 0-7]
 //               [alphabeta --nodes <nodelist> --edges <edgelist>]
 //
 // Files written (formats of the reference): distribution_<file>, distributions.txt, steady_state_methylation.txt,
@@ -74,6 +74,7 @@ int main(int argc, char **argv)
     long iterations = 100;
     unsigned long long seed = 0xAB0B200ull;
     int device = 0;
+    std::vector<int> devices;  // --devices 0-7 / 0,2,5: windows sharded over several GPUs (abfit_alphabeta_batch_multi)
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto val = [&]() -> const char * {
@@ -101,6 +102,19 @@ int main(int argc, char **argv)
         else if (a == "--iterations") iterations = std::atol(val());
         else if (a == "--seed") seed = std::strtoull(val(), nullptr, 0);
         else if (a == "--device") device = std::atoi(val());
+        else if (a == "--devices") {
+            const std::string v = val();
+            size_t pos = 0;
+            while (pos < v.size()) {
+                size_t e = v.find(',', pos);
+                if (e == std::string::npos) e = v.size();
+                const std::string tok = v.substr(pos, e - pos);
+                const size_t dash = tok.find('-');
+                const int lo = std::atoi(tok.c_str()), hi = dash == std::string::npos ? lo : std::atoi(tok.c_str() + dash + 1);
+                for (int d = lo; d <= hi; ++d) devices.push_back(d);
+                pos = e + 1;
+            }
+        }
         else {
             std::fprintf(stderr, "error: unexpected argument '%s' found\n", a.c_str());
             return 2;
@@ -296,11 +310,17 @@ int main(int argc, char **argv)
             }
         }
     }
-    abfit_ctx *ctx = nullptr;
-    if (abfit_ctx_create(device, &ctx)) {
-        std::printf("Error: %s\n", abfit_last_error());
+    if (S <= 0 || n_pairs <= 0) {  // the reference fails here too: nothing to compare (src/pedigree.rs:92-193)
+        std::printf("Error: Error while building pedigree: the nodelist has fewer than two measured samples\n");
         return 1;
     }
+    if (devices.empty()) devices.push_back(device);
+    std::vector<abfit_ctx *> ctxs(devices.size(), nullptr);
+    for (size_t d = 0; d < devices.size(); ++d)
+        if (abfit_ctx_create(devices[d], &ctxs[d])) {
+            std::printf("Error: %s\n", abfit_last_error());
+            return 1;
+        }
     // windows whose samples all list the same number of sites go into one divergence call
     std::vector<int> usable;
     std::vector<int64_t> seg{0};
@@ -331,8 +351,8 @@ int main(int argc, char **argv)
             }
     }
     std::vector<double> D((size_t)std::max(W, 1) * std::max<size_t>(P, 1)), p0uu(std::max(W, 1));
-    if (W > 0 && abfit_divergence(ctx, st.data(), po.data(), me.data(), S, L, seg.data(), W, 0.99, D.data(), nullptr, nullptr, p0uu.data(),
-                                  nullptr, nullptr)) {
+    if (W > 0 && abfit_divergence_multi(ctxs.data(), (int32_t)ctxs.size(), st.data(), po.data(), me.data(), S, L, seg.data(), W, 0.99,
+                                        D.data(), nullptr, nullptr, p0uu.data(), nullptr, nullptr)) {
         std::printf("Error: %s\n", abfit_last_error());
         return 1;
     }
@@ -364,18 +384,21 @@ int main(int argc, char **argv)
     std::vector<double> simplices((size_t)F * n * 20), rows((size_t)F * n * 7), analysis((size_t)F * 32);
     std::vector<int32_t> idx((size_t)F * n * n_pairs), status(F);
     std::vector<abfit_fit> best(F);
+    std::vector<uint64_t> ids(F);  // every window's generator key is its position in the genome-wide window list
     for (int f = 0; f < F; ++f) {
         const int k = fitted[f];
+        ids[f] = (uint64_t)usable[k];
         probs[f] = abfit_problem{peds[f].data(), n_pairs, p0uu[k], p0uu[k], 1.0};
         double max_div = peds[f][3];
         for (int r = 1; r < n_pairs; ++r) max_div = std::max(max_div, peds[f][4 * r + 3]);
         abfit_gen_start_simplices(seed, (uint64_t)usable[k], n, max_div, simplices.data() + (size_t)f * n * 20);
         abfit_gen_resample_idx(seed, (uint64_t)usable[k], n, n_pairs, idx.data() + (size_t)f * n * n_pairs);
     }
-    // NB: the vary vertices are keyed by (seed, position in the batch); a window's result therefore depends on which
-    // windows precede it only through that key, never through their data
-    if (F > 0 && abfit_alphabeta_batch(ctx, probs.data(), F, n, simplices.data(), n, idx.data(), seed, 0, 10000, 1000, DBL_EPSILON, 0,
-                                       best.data(), nullptr, nullptr, status.data(), rows.data(), analysis.data())) {
+    // start simplices, resample indices and vary vertices of a window are all keyed by (seed, window id): its result
+    // does not depend on which other windows are fitted with it, nor on how the windows are sharded over the GPUs
+    if (F > 0 && abfit_alphabeta_batch_multi(ctxs.data(), (int32_t)ctxs.size(), probs.data(), F, n, simplices.data(), n, idx.data(), seed,
+                                             0, ids.data(), 10000, 1000, DBL_EPSILON, 0, best.data(), nullptr, nullptr,
+                                             status.data(), rows.data(), analysis.data())) {
         std::printf("Error: %s\n", abfit_last_error());
         return 1;
     }
@@ -419,6 +442,6 @@ int main(int argc, char **argv)
         std::printf("Error: %s\n", abfit_last_error());
         return 1;
     }
-    abfit_ctx_destroy(ctx);
+    for (abfit_ctx *c : ctxs) abfit_ctx_destroy(c);
     return 0;
 }

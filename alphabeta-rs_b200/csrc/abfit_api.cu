@@ -62,6 +62,11 @@ struct abfit_ctx {
     cudaDeviceProp prop{};
     int smem_optin = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    // pipelined fit -> bootstrap (run_pipelined): one stream per sub-batch of windows
+    static constexpr int MAX_PIPES = 8;
+    cudaStream_t pipe_stream[MAX_PIPES] = {};
+    cudaEvent_t pipe_done[MAX_PIPES] = {};
+    cudaEvent_t pipe_start = nullptr, idx_done = nullptr;
     // workspace of the one-shot host-buffer calls: device buffers are kept between calls
     // (cudaMalloc/cudaFree of multi-GB buffers costs more than the kernels of a small batch)
     abfit_batch *scratch = nullptr;
@@ -107,8 +112,20 @@ struct abfit_batch {
     // specialised kernels of this batch's program (abfit_jit.cu); nullptr: interpreter kernels
     const JitModule *jit = nullptr;
     bool jit_decided = false;
+    int64_t jit_fits_seen = 0;
+    bool boot_items_v2 = false;  // the bootstrap items were built for the continuous-scheduling kernel
+    DevBuf<unsigned long long> d_ids;  // per-window generator keys of abfit_alphabeta_batch_multi
     DevBuf<int> d_cursor;  // item cursors of the continuous-scheduling kernels: [0] multi-start, [1] bootstrap
     int jit_warps_fit = 0, jit_warps_boot = 0;  // resident warps = grid of a full machine
+    // pipelined fit -> select -> bootstrap: sub-batches of windows, each with its own guided item lists and cursors
+    struct Pipe {
+        int p0 = 0, n = 0, fit_item0 = 0, fit_items = 0, boot_item0 = 0, boot_items = 0;
+    };
+    std::vector<Pipe> pipes;
+    DevBuf<WorkItem> d_pipe_items;
+    DevBuf<int> d_pipe_cursor;
+    int pipes_n_starts = -1, pipes_n_boot = -1;
+    bool pipelined_timing = false;
     // timing
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_fit = false, ev_boot = false;
@@ -152,8 +169,10 @@ static int big_scratch(abfit_batch *b, size_t slots, BigScratch &out)
 // (default 2 000 000; a compilation takes a few seconds, the specialised kernels save ~25 % of 0.25 us per fit).
 static void decide_jit(abfit_batch *b, int64_t fits_per_prob)
 {
-    if (b->jit_decided) return;
+    // decided once per loaded batch; a later request with more fits per window may still turn specialisation ON
+    if (b->jit_decided && (b->jit || fits_per_prob <= b->jit_fits_seen)) return;
     b->jit_decided = true;
+    b->jit_fits_seen = fits_per_prob;
     b->jit = nullptr;
     const char *env = getenv("ABFIT_JIT");
     if (env && atoi(env) == 0) return;
@@ -184,6 +203,16 @@ extern "C" {
 
 const char *abfit_last_error(void) { return g_last_error.c_str(); }
 const char *abfit_version(void) { return "abfit-b200 0.1 (sm_100a)"; }
+
+int abfit_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
 
 int abfit_ctx_create(int device, abfit_ctx **out)
 {
@@ -229,6 +258,12 @@ void abfit_ctx_destroy(abfit_ctx *ctx)
     if (ctx->div_arena.p) cudaFree(ctx->div_arena.p);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
+    for (int k = 0; k < abfit_ctx::MAX_PIPES; ++k) {
+        if (ctx->pipe_stream[k]) cudaStreamDestroy(ctx->pipe_stream[k]);
+        if (ctx->pipe_done[k]) cudaEventDestroy(ctx->pipe_done[k]);
+    }
+    if (ctx->pipe_start) cudaEventDestroy(ctx->pipe_start);
+    if (ctx->idx_done) cudaEventDestroy(ctx->idx_done);
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -361,6 +396,10 @@ static int batch_load(abfit_batch *b, const abfit_problem *probs, int32_t n_prob
     b->ev_fit = b->ev_boot = false;
     b->jit = nullptr;
     b->jit_decided = false;
+    b->jit_fits_seen = 0;
+    b->pipes.clear();
+    b->pipes_n_starts = b->pipes_n_boot = -1;
+    b->pipelined_timing = false;
     // aux kernels (select / cost / model divergence) only need the one-warp, simplex-free shape;
     // the fit shape is chosen in upload_starts / upload_boot when the number of fits is known
     if (int rc = choose_launch_shape(hp, (size_t)ctx->smem_optin, (size_t)ctx->prop.sharedMemPerMultiprocessor, 1,
@@ -444,7 +483,6 @@ static int upload_starts_impl(abfit_batch *b, int32_t n_starts, const double *si
         if (int rc = choose_launch_shape(b->hp, (size_t)b->ctx->smem_optin,
                                          (size_t)b->ctx->prop.sharedMemPerMultiprocessor, n_starts, b->shape))
             return rc;
-        b->jit_decided = false;
         decide_jit(b, n_starts);
         const int n_sm = b->ctx->prop.multiProcessorCount;
         std::vector<WorkItem> items;
@@ -522,6 +560,7 @@ int abfit_batch_run_fit(abfit_batch *b, int32_t max_iters, double sd_tol, uint32
     ABFIT_CUDA(cudaEventRecord(b->ev[2], st));
     b->ev_fit = true;
     b->fit_done = true;
+    b->pipelined_timing = false;
     b->launches_fit = (b->n_items > 0 ? 1 : 0) + 1;
     return 0;
 }
@@ -559,9 +598,12 @@ static int boot_alloc(abfit_batch *b, int32_t n_boot)
     if (int rc = b->d_idx.ensure(n_idx)) return rc;
     if (int rc = b->d_vary.ensure(n_vary)) return rc;
     decide_jit(b, n_boot);  // a bootstrap-only batch has not been through upload_starts
-    if (n_boot != b->n_boot) {
+    const bool want_v2 = b->jit && b->jit->sched == 2 && b->shape.smem_boot_gather;
+    if (n_boot != b->n_boot || want_v2 != b->boot_items_v2) {
         b->n_boot = n_boot;
-        const bool v2 = b->jit && b->jit->sched == 2 && b->shape.smem_boot_gather;
+        b->boot_items_v2 = want_v2;
+        b->pipes_n_boot = -1;
+        const bool v2 = want_v2;
         std::vector<WorkItem> items;
         if (v2) {
             if (int rc = b->d_cursor.ensure(2)) return rc;
@@ -630,6 +672,7 @@ int abfit_batch_run_boot(abfit_batch *b, int32_t max_iters, double sd_tol, uint3
     }
     ABFIT_CUDA(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->ctx->stream;
+    if (int rc = boot_alloc(b, b->n_boot)) return rc;  // no-op unless the kernel family changed since the upload
     const NMParams nm = nm_params(max_iters, sd_tol, flags);
     ABFIT_CUDA(cudaMemsetAsync(b->d_rows.p, 0xFF, (size_t)b->n_probs * b->n_boot * 7 * 8, st));
     ABFIT_CUDA(cudaMemsetAsync(b->d_bootfits.p, 0xFF, (size_t)b->n_probs * b->n_boot * sizeof(abfit_fit), st));
@@ -686,6 +729,144 @@ int abfit_batch_run_boot(abfit_batch *b, int32_t max_iters, double sd_tol, uint3
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// pipelined fit -> select -> bootstrap
+//
+// A multi-start launch cannot end before its longest fit does, and among a million fits some run for thousands of
+// iterations: ~30 ms at the end of every launch during which the machine drains (measured: launch time =
+// 0.162 ms x windows + 32 ms).  Only a window's OWN best-of-starts gates its bootstrap, so the batch is cut into
+// sub-batches of windows, each a fit -> select -> (vary) -> bootstrap chain on its own stream: while the last long
+// fits of one sub-batch finish, the freed warps already run the next sub-batch's fits, and the bootstraps fill what
+// is left.  Same kernels, same items-to-fits mapping inside a sub-batch: same bits.
+// ---------------------------------------------------------------------------------------
+static int plan_pipes(abfit_batch *b)
+{
+    abfit_ctx *ctx = b->ctx;
+    const bool v2 = b->jit && b->jit->sched == 2 && b->shape.smem_boot_gather && !b->shape.wide && !b->shape.big;
+    if (!v2 || b->n_starts <= 0 || b->n_boot <= 0) {
+        b->pipes.clear();
+        return 0;
+    }
+    if (b->pipes_n_starts == b->n_starts && b->pipes_n_boot == b->n_boot && !b->pipes.empty()) return 0;
+    int K = std::max(1, std::min<int>(abfit_ctx::MAX_PIPES, (b->n_probs + 300) / 600));
+    if (const char *e = getenv("ABFIT_DEV_PIPES")) K = std::max(1, std::min<int>(abfit_ctx::MAX_PIPES, atoi(e)));
+    K = std::min(K, b->n_probs);
+    b->pipes.assign(K, abfit_batch::Pipe());
+    std::vector<WorkItem> all;
+    for (int k = 0; k < K; ++k) {
+        abfit_batch::Pipe &pp = b->pipes[k];
+        pp.p0 = (int)((int64_t)b->n_probs * k / K);
+        pp.n = (int)((int64_t)b->n_probs * (k + 1) / K) - pp.p0;
+        std::vector<WorkItem> it = make_items_guided(b->hp, b->n_starts, b->jit_warps_fit, 256, true, pp.p0, pp.p0 + pp.n);
+        pp.fit_item0 = (int)all.size();
+        pp.fit_items = (int)it.size();
+        all.insert(all.end(), it.begin(), it.end());
+    }
+    for (int k = 0; k < K; ++k) {
+        abfit_batch::Pipe &pp = b->pipes[k];
+        std::vector<WorkItem> it = make_items_guided(b->hp, b->n_boot, b->jit_warps_boot, 256, true, pp.p0, pp.p0 + pp.n);
+        pp.boot_item0 = (int)all.size();
+        pp.boot_items = (int)it.size();
+        all.insert(all.end(), it.begin(), it.end());
+    }
+    if (int rc = b->d_pipe_items.ensure(all.size())) return rc;
+    if (int rc = b->d_pipe_cursor.ensure(2 * abfit_ctx::MAX_PIPES)) return rc;
+    if (!all.empty())
+        ABFIT_CUDA(cudaMemcpyAsync(b->d_pipe_items.p, all.data(), all.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, ctx->stream));
+    ABFIT_CUDA(cudaStreamSynchronize(ctx->stream));  // `all` is pageable host memory
+    for (int k = 0; k < K; ++k) {
+        if (!ctx->pipe_stream[k]) ABFIT_CUDA(cudaStreamCreateWithFlags(&ctx->pipe_stream[k], cudaStreamNonBlocking));
+        if (!ctx->pipe_done[k]) ABFIT_CUDA(cudaEventCreateWithFlags(&ctx->pipe_done[k], cudaEventDisableTiming));
+    }
+    if (!ctx->pipe_start) ABFIT_CUDA(cudaEventCreateWithFlags(&ctx->pipe_start, cudaEventDisableTiming));
+    b->pipes_n_starts = b->n_starts;
+    b->pipes_n_boot = b->n_boot;
+    return 0;
+}
+
+// gen_vary: draw the vary vertices on the device behind each sub-batch's selection (abfit_alphabeta_batch), else the
+// uploaded ones are used.  before_boot: optional event the bootstraps have to wait for (the resample indices' H2D copy).
+static int run_pipelined_impl(abfit_batch *b, int32_t max_iters_fit, int32_t max_iters_boot, double sd_tol, uint32_t flags,
+                              bool gen_vary, uint64_t vary_seed, uint64_t first_problem_id, const unsigned long long *d_ids,
+                              cudaEvent_t before_boot)
+{
+    abfit_ctx *ctx = b->ctx;
+    if (int rc = plan_pipes(b)) return rc;
+    cudaStream_t st = ctx->stream;
+    if (b->pipes.size() <= 1) {  // nothing to overlap (or not the continuous-scheduling kernels): one after the other
+        if (int rc = abfit_batch_run_fit(b, max_iters_fit, sd_tol, flags)) return rc;
+        if (gen_vary)
+            if (int rc = launch_gen_vary(st, vary_seed, first_problem_id, d_ids, b->n_probs, b->n_boot, b->d_best.p, b->d_vary.p))
+                return rc;
+        if (before_boot) ABFIT_CUDA(cudaStreamWaitEvent(st, before_boot, 0));
+        b->boot_uploaded = true;
+        return abfit_batch_run_boot(b, max_iters_boot, sd_tol, flags);
+    }
+    const NMParams nm_fit = nm_params(max_iters_fit, sd_tol, flags), nm_boot = nm_params(max_iters_boot, sd_tol, flags);
+    ABFIT_CUDA(cudaMemsetAsync(b->d_all.p, 0xFF, (size_t)b->n_probs * b->n_starts * sizeof(abfit_fit), st));
+    ABFIT_CUDA(cudaMemsetAsync(b->d_evals_fit.p, 0, (size_t)b->n_probs * 8, st));
+    ABFIT_CUDA(cudaMemsetAsync(b->d_rows.p, 0xFF, (size_t)b->n_probs * b->n_boot * 7 * 8, st));
+    ABFIT_CUDA(cudaMemsetAsync(b->d_bootfits.p, 0xFF, (size_t)b->n_probs * b->n_boot * sizeof(abfit_fit), st));
+    ABFIT_CUDA(cudaMemsetAsync(b->d_evals_boot.p, 0, (size_t)b->n_probs * 8, st));
+    if (int rc = b->d_booterr.ensure(1)) return rc;
+    ABFIT_CUDA(cudaMemsetAsync(b->d_booterr.p, 0, sizeof(int), st));
+    ABFIT_CUDA(cudaEventRecord(b->ev[0], st));
+    ABFIT_CUDA(cudaEventRecord(ctx->pipe_start, st));
+    BigScratch none;
+    const DevProblem &pb0 = b->hp.probs[0];
+    const int64_t tile_stride = (int64_t)((b->hp.max_pairs + 3) / 4) * 32;
+    // every sub-batch's bootstrap kernel gets its own range of index tiles
+    if (int rc = b->d_scratch.ensure(((size_t)b->jit_warps_boot * b->pipes.size() + 1) * (size_t)tile_stride)) return rc;
+    for (size_t k = 0; k < b->pipes.size(); ++k) {
+        const abfit_batch::Pipe &pp = b->pipes[k];
+        cudaStream_t ps = ctx->pipe_stream[k];
+        ABFIT_CUDA(cudaStreamWaitEvent(ps, ctx->pipe_start, 0));
+        if (int rc = jit_launch_fit_starts_v2(b->jit, ps, b->pools, b->d_pipe_items.p + pp.fit_item0, pp.fit_items,
+                                              (int64_t)pp.n * b->n_starts, b->jit_warps_fit, b->d_pipe_cursor.p + 2 * k,
+                                              b->d_simplices.p, b->n_starts, nm_fit, b->d_all.p, b->d_evals_fit.p,
+                                              jit_smem_fit_v2(b->jit, pb0)))
+            return rc;
+        if (int rc = launch_select(ps, b->pools, pp.n, b->n_starts, b->d_all.p, b->d_best.p, b->d_pred.p, b->d_resid.p,
+                                   b->d_status.p, b->shape.smem_aux, b->shape.d_shared_aux, none, pp.p0))
+            return rc;
+        if (gen_vary)
+            if (int rc = launch_gen_vary(ps, vary_seed, first_problem_id + (uint64_t)pp.p0, d_ids ? d_ids + pp.p0 : nullptr, pp.n,
+                                         b->n_boot, b->d_best.p + pp.p0, b->d_vary.p + (size_t)pp.p0 * b->n_boot * 16))
+                return rc;
+        if (before_boot) ABFIT_CUDA(cudaStreamWaitEvent(ps, before_boot, 0));
+        if (int rc = jit_launch_fit_boot_gather_v2(
+                b->jit, ps, b->pools, b->d_pipe_items.p + pp.boot_item0, pp.boot_items, (int64_t)pp.n * b->n_boot,
+                b->jit_warps_boot, b->d_pipe_cursor.p + 2 * k + 1, b->n_boot, b->d_best.p, b->d_pred.p, b->d_resid.p, b->d_idx.p,
+                b->d_vary.p, reinterpret_cast<uint2 *>(b->d_scratch.p) + (size_t)k * b->jit_warps_boot * tile_stride, tile_stride,
+                nm_boot, b->d_rows.p, b->d_bootfits.p, b->d_evals_boot.p, jit_smem_boot_v2(b->jit, pb0), b->d_booterr.p))
+            return rc;
+        ABFIT_CUDA(cudaEventRecord(ctx->pipe_done[k], ps));
+        ABFIT_CUDA(cudaStreamWaitEvent(st, ctx->pipe_done[k], 0));
+    }
+    for (int e = 1; e <= 4; ++e) ABFIT_CUDA(cudaEventRecord(b->ev[e], st));
+    b->ev_fit = b->ev_boot = true;
+    b->pipelined_timing = true;
+    b->fit_done = b->boot_done = b->boot_uploaded = true;
+    b->launches_fit = 2 * (int)b->pipes.size();
+    b->launches_boot = (int)b->pipes.size() * (gen_vary ? 2 : 1);
+    return 0;
+}
+
+int abfit_batch_run_pipelined(abfit_batch *b, int32_t max_iters_fit, int32_t max_iters_boot, double sd_tol, uint32_t flags)
+{
+    if (!b || b->n_starts <= 0 || !b->boot_uploaded) {
+        set_error("run_pipelined: upload_starts and upload_boot first");
+        return ABFIT_ERR_STATE;
+    }
+    ABFIT_CUDA(cudaSetDevice(b->ctx->device));
+    return run_pipelined_impl(b, max_iters_fit, max_iters_boot, sd_tol, flags, false, 0, 0, nullptr, nullptr);
+}
+
+int abfit_batch_pipes(abfit_batch *b)
+{
+    return b ? (int)std::max<size_t>(1, b->pipes.size()) : 0;
+}
+
 int abfit_batch_download_boot(abfit_batch *b, double *rows_out, abfit_fit *fits_out)
 {
     if (!b || !b->boot_done) {
@@ -724,11 +905,14 @@ int abfit_batch_timing(abfit_batch *b, float ms[3], int64_t evals[2], int32_t *l
     ABFIT_CUDA(cudaStreamSynchronize(b->ctx->stream));
     if (ms) {
         ms[0] = ms[1] = ms[2] = 0.f;
-        if (b->ev_fit) {
+        if (b->pipelined_timing) {
+            // the sub-batches' kernels overlap: only the whole span is meaningful, reported as ms[0]
+            ABFIT_CUDA(cudaEventElapsedTime(&ms[0], b->ev[0], b->ev[4]));
+        } else if (b->ev_fit) {
             ABFIT_CUDA(cudaEventElapsedTime(&ms[0], b->ev[0], b->ev[1]));
             ABFIT_CUDA(cudaEventElapsedTime(&ms[1], b->ev[1], b->ev[2]));
         }
-        if (b->ev_boot) ABFIT_CUDA(cudaEventElapsedTime(&ms[2], b->ev[3], b->ev[4]));
+        if (b->ev_boot && !b->pipelined_timing) ABFIT_CUDA(cudaEventElapsedTime(&ms[2], b->ev[3], b->ev[4]));
     }
     if (evals) {
         std::vector<unsigned long long> h(b->n_probs);
@@ -844,11 +1028,11 @@ void abfit_gen_vary_vertices_batch(uint64_t seed, uint64_t first_problem_id, int
     });
 }
 
-int abfit_alphabeta_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, int32_t n_starts,
+static int alphabeta_impl(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, int32_t n_starts,
                           const double *simplices, int32_t n_boot, const int32_t *resample_idx, uint64_t vary_seed,
-                          uint64_t first_problem_id, int32_t max_iters_fit, int32_t max_iters_boot, double sd_tol,
-                          uint32_t flags, abfit_fit *best_out, double *pred_out, double *resid_out,
-                          int32_t *prob_status_out, double *rows_out, double *analysis_out)
+                          uint64_t first_problem_id, const uint64_t *problem_ids, int32_t max_iters_fit,
+                          int32_t max_iters_boot, double sd_tol, uint32_t flags, abfit_fit *best_out, double *pred_out,
+                          double *resid_out, int32_t *prob_status_out, double *rows_out, double *analysis_out)
 {
     if (!simplices || !resample_idx || n_starts <= 0 || n_boot <= 0 || !rows_out) return ABFIT_ERR_ARG;
     if (!ctx || n_probs <= 0) return ABFIT_ERR_ARG;
@@ -868,36 +1052,37 @@ int abfit_alphabeta_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_
     ABFIT_CUDA(cudaMemcpyAsync(b->d_simplices.p, simplices, n_sx * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
     ABFIT_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
     if (int rc = workspace(ctx, probs, n_probs, &b)) return rc;
-    if (int rc = boot_alloc(b, n_boot)) return rc;  // before any kernel is enqueued: it may synchronise
-    if (int rc = upload_starts_impl(b, n_starts, nullptr)) return rc;
+    decide_jit(b, (int64_t)n_starts + n_boot);  // one decision for both phases of this batch
+    if (int rc = upload_starts_impl(b, n_starts, nullptr)) return rc;  // before any kernel is enqueued: these may synchronise
+    if (int rc = boot_alloc(b, n_boot)) return rc;
     ABFIT_CUDA(cudaStreamWaitEvent(st, ctx->copy_done, 0));
-    if (int rc = abfit_batch_run_fit(b, max_iters_fit, sd_tol, flags)) return rc;
-    // the resample indices (the bulk of the bootstrap's input) cross PCIe under the multi-start kernel
+    // the resample indices (the bulk of the bootstrap's input) cross PCIe under the multi-start kernels
+    if (!ctx->idx_done) ABFIT_CUDA(cudaEventCreateWithFlags(&ctx->idx_done, cudaEventDisableTiming));
     ABFIT_CUDA(cudaMemcpyAsync(b->d_idx.p, resample_idx, (size_t)b->total_pairs * n_boot * 4, cudaMemcpyHostToDevice,
                                ctx->copy_stream));
-    ABFIT_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
-    // Model::vary x 4 per replicate around each window's best model (src/boot_model.rs:69-75): drawn on the device
-    // right behind the selection kernel — the same numbers abfit_gen_vary_vertices gives on the host — so the
-    // bootstrap starts without a round trip through the host
-    if (int rc = launch_gen_vary(st, vary_seed, first_problem_id, n_probs, n_boot, b->d_best.p, b->d_vary.p)) return rc;
-    ABFIT_CUDA(cudaStreamWaitEvent(st, ctx->copy_done, 0));
+    ABFIT_CUDA(cudaEventRecord(ctx->idx_done, ctx->copy_stream));
+    const unsigned long long *d_ids = nullptr;
+    if (problem_ids) {  // every window keeps its own key, whatever its position in this batch
+        if (int rc = b->d_ids.ensure(n_probs)) return rc;
+        ABFIT_CUDA(cudaMemcpyAsync(b->d_ids.p, problem_ids, (size_t)n_probs * 8, cudaMemcpyHostToDevice, st));
+        d_ids = b->d_ids.p;
+    }
+    // fit -> select -> Model::vary x 4 per replicate around each window's best model (src/boot_model.rs:69-75: drawn on
+    // the device right behind the selection kernel — the same numbers abfit_gen_vary_vertices gives on the host — so
+    // the bootstrap starts without a round trip through the host) -> bootstrap, pipelined over sub-batches of windows
     b->boot_uploaded = true;
     b->boot_done = false;
-    if (int rc = abfit_batch_run_boot(b, max_iters_boot, sd_tol, flags)) return rc;
-    // results of the fit come back while the bootstrap runs (copy stream, behind the selection kernel's event)
-    {
-        ABFIT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, b->ev[2], 0));
-        cudaStream_t cs = ctx->copy_stream;
-        if (best_out)
-            ABFIT_CUDA(cudaMemcpyAsync(best_out, b->d_best.p, (size_t)n_probs * sizeof(abfit_fit), cudaMemcpyDeviceToHost, cs));
-        if (pred_out)
-            ABFIT_CUDA(cudaMemcpyAsync(pred_out, b->d_pred.p, (size_t)b->total_pairs * 8, cudaMemcpyDeviceToHost, cs));
-        if (resid_out)
-            ABFIT_CUDA(cudaMemcpyAsync(resid_out, b->d_resid.p, (size_t)b->total_pairs * 8, cudaMemcpyDeviceToHost, cs));
-        if (prob_status_out)
-            ABFIT_CUDA(cudaMemcpyAsync(prob_status_out, b->d_status.p, (size_t)n_probs * 4, cudaMemcpyDeviceToHost, cs));
-        ABFIT_CUDA(cudaStreamSynchronize(cs));
-    }
+    if (int rc = run_pipelined_impl(b, max_iters_fit, max_iters_boot, sd_tol, flags, true, vary_seed, first_problem_id, d_ids,
+                                    ctx->idx_done))
+        return rc;
+    if (best_out)
+        ABFIT_CUDA(cudaMemcpyAsync(best_out, b->d_best.p, (size_t)n_probs * sizeof(abfit_fit), cudaMemcpyDeviceToHost, st));
+    if (pred_out)
+        ABFIT_CUDA(cudaMemcpyAsync(pred_out, b->d_pred.p, (size_t)b->total_pairs * 8, cudaMemcpyDeviceToHost, st));
+    if (resid_out)
+        ABFIT_CUDA(cudaMemcpyAsync(resid_out, b->d_resid.p, (size_t)b->total_pairs * 8, cudaMemcpyDeviceToHost, st));
+    if (prob_status_out)
+        ABFIT_CUDA(cudaMemcpyAsync(prob_status_out, b->d_status.p, (size_t)n_probs * 4, cudaMemcpyDeviceToHost, st));
     if (int rc = abfit_batch_download_boot(b, rows_out, nullptr)) return rc;
     if (analysis_out) {
         std::vector<int> rcs(n_probs, 0);
@@ -905,6 +1090,65 @@ int abfit_alphabeta_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_
             rcs[p] = abfit_analyze(rows_out + (size_t)p * n_boot * 7, n_boot, analysis_out + (size_t)p * 32);
         });
     }
+    return 0;
+}
+
+int abfit_alphabeta_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs, int32_t n_starts,
+                          const double *simplices, int32_t n_boot, const int32_t *resample_idx, uint64_t vary_seed,
+                          uint64_t first_problem_id, int32_t max_iters_fit, int32_t max_iters_boot, double sd_tol,
+                          uint32_t flags, abfit_fit *best_out, double *pred_out, double *resid_out,
+                          int32_t *prob_status_out, double *rows_out, double *analysis_out)
+{
+    return alphabeta_impl(ctx, probs, n_probs, n_starts, simplices, n_boot, resample_idx, vary_seed, first_problem_id,
+                          nullptr, max_iters_fit, max_iters_boot, sd_tol, flags, best_out, pred_out, resid_out,
+                          prob_status_out, rows_out, analysis_out);
+}
+
+// contiguous, balanced block of `n` units for shard r of `world`
+static void shard_range(int64_t n, int r, int world, int64_t &first, int64_t &count)
+{
+    const int64_t base = n / world, extra = n % world;
+    first = (int64_t)r * base + std::min<int64_t>(r, extra);
+    count = base + (r < extra ? 1 : 0);
+}
+
+int abfit_alphabeta_batch_multi(abfit_ctx *const *ctxs, int32_t n_ctx, const abfit_problem *probs, int32_t n_probs,
+                                int32_t n_starts, const double *simplices, int32_t n_boot, const int32_t *resample_idx,
+                                uint64_t vary_seed, uint64_t first_problem_id, const uint64_t *problem_ids,
+                                int32_t max_iters_fit, int32_t max_iters_boot, double sd_tol, uint32_t flags,
+                                abfit_fit *best_out, double *pred_out, double *resid_out, int32_t *prob_status_out,
+                                double *rows_out, double *analysis_out)
+{
+    if (!ctxs || n_ctx <= 0 || !probs || n_probs <= 0 || !simplices || !resample_idx || !rows_out) return ABFIT_ERR_ARG;
+    for (int r = 0; r < n_ctx; ++r)
+        if (!ctxs[r]) return ABFIT_ERR_ARG;
+    const int world = std::min<int>(n_ctx, n_probs);
+    std::vector<int64_t> pair_off((size_t)n_probs + 1, 0);
+    for (int p = 0; p < n_probs; ++p) pair_off[p + 1] = pair_off[p] + std::max(probs[p].n_pairs, 0);
+    std::vector<int> rcs(world, 0);
+    std::vector<std::string> errs(world);
+    auto work = [&](int r) {
+        int64_t first, count;
+        shard_range(n_probs, r, world, first, count);
+        const int64_t po = pair_off[first];
+        rcs[r] = alphabeta_impl(ctxs[r], probs + first, (int32_t)count, n_starts, simplices + (size_t)first * n_starts * 20,
+                                n_boot, resample_idx + (size_t)po * n_boot, vary_seed, first_problem_id + (uint64_t)first,
+                                problem_ids ? problem_ids + first : nullptr, max_iters_fit, max_iters_boot, sd_tol, flags,
+                                best_out ? best_out + first : nullptr, pred_out ? pred_out + po : nullptr,
+                                resid_out ? resid_out + po : nullptr, prob_status_out ? prob_status_out + first : nullptr,
+                                rows_out + (size_t)first * n_boot * 7, analysis_out ? analysis_out + (size_t)first * 32 : nullptr);
+        if (rcs[r]) errs[r] = g_last_error;  // thread-local: carry it over to the caller's thread
+    };
+    // one host thread + context per device; the shards never exchange data
+    std::vector<std::thread> th;
+    for (int r = 1; r < world; ++r) th.emplace_back(work, r);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int r = 0; r < world; ++r)
+        if (rcs[r]) {
+            set_error("device shard " + std::to_string(r) + ": " + errs[r]);
+            return rcs[r];
+        }
     return 0;
 }
 
@@ -988,10 +1232,12 @@ int abfit_model_divergence(abfit_ctx *ctx, const abfit_problem *prob, const doub
     return 0;
 }
 
+// pitch: row stride (in sites) of the three HOST arrays when they are column slices of wider matrices (0: L)
 static int divergence_impl(abfit_ctx *ctx, bool device_inputs, const uint8_t *status, const double *posterior_max,
                            const double *meth_lvl, int32_t S, int64_t L, const int64_t *seg_offsets, int32_t W,
                            double thr, double *D_out, uint64_t *diff_out, uint64_t *cnt_out, double *p0uu_out,
-                           double *methsum_out, int64_t *nvalid_out, float *ms_out, int32_t *launches_out)
+                           double *methsum_out, int64_t *nvalid_out, float *ms_out, int32_t *launches_out,
+                           int64_t pitch = 0)
 {
     if (!ctx || !status || !posterior_max || !meth_lvl || S <= 0 || L < 0 || S > 65535) return ABFIT_ERR_ARG;
     int64_t whole[2] = {0, L};
@@ -1025,9 +1271,17 @@ static int divergence_impl(abfit_ctx *ctx, bool device_inputs, const uint8_t *st
     if (int rc = d_nvalid.ensure((size_t)W * S)) return rc;
     if (int rc = d_p0uu.ensure(W)) return rc;
     if (n && !device_inputs) {
-        ABFIT_CUDA(cudaMemcpyAsync(d_status.p, status, n, cudaMemcpyHostToDevice, st));
-        ABFIT_CUDA(cudaMemcpyAsync(d_post.p, posterior_max, n * 8, cudaMemcpyHostToDevice, st));
-        ABFIT_CUDA(cudaMemcpyAsync(d_meth.p, meth_lvl, n * 8, cudaMemcpyHostToDevice, st));
+        if (pitch > L) {  // a site range of wider host matrices: row by row into dense device matrices
+            ABFIT_CUDA(cudaMemcpy2DAsync(d_status.p, (size_t)L, status, (size_t)pitch, (size_t)L, S, cudaMemcpyHostToDevice, st));
+            ABFIT_CUDA(cudaMemcpy2DAsync(d_post.p, (size_t)L * 8, posterior_max, (size_t)pitch * 8, (size_t)L * 8, S,
+                                         cudaMemcpyHostToDevice, st));
+            ABFIT_CUDA(cudaMemcpy2DAsync(d_meth.p, (size_t)L * 8, meth_lvl, (size_t)pitch * 8, (size_t)L * 8, S,
+                                         cudaMemcpyHostToDevice, st));
+        } else {
+            ABFIT_CUDA(cudaMemcpyAsync(d_status.p, status, n, cudaMemcpyHostToDevice, st));
+            ABFIT_CUDA(cudaMemcpyAsync(d_post.p, posterior_max, n * 8, cudaMemcpyHostToDevice, st));
+            ABFIT_CUDA(cudaMemcpyAsync(d_meth.p, meth_lvl, n * 8, cudaMemcpyHostToDevice, st));
+        }
     }
     int launches = 0;
     if (int rc = run_divergence(st, device_inputs ? status : d_status.p, device_inputs ? posterior_max : d_post.p,
@@ -1052,6 +1306,103 @@ int abfit_divergence(abfit_ctx *ctx, const uint8_t *status, const double *poster
 {
     return divergence_impl(ctx, false, status, posterior_max, meth_lvl, S, L, seg_offsets, W, thr, D_out, diff_out,
                            cnt_out, p0uu_out, methsum_out, nvalid_out, nullptr, nullptr);
+}
+
+int abfit_divergence_multi(abfit_ctx *const *ctxs, int32_t n_ctx, const uint8_t *status, const double *posterior_max,
+                           const double *meth_lvl, int32_t S, int64_t L, const int64_t *seg_offsets, int32_t W, double thr,
+                           double *D_out, uint64_t *diff_out, uint64_t *cnt_out, double *p0uu_out, double *methsum_out,
+                           int64_t *nvalid_out)
+{
+    if (!ctxs || n_ctx <= 0 || !status || !posterior_max || !meth_lvl || S <= 0 || L < 0) return ABFIT_ERR_ARG;
+    for (int r = 0; r < n_ctx; ++r)
+        if (!ctxs[r]) return ABFIT_ERR_ARG;
+    const size_t P = (size_t)S * (S - 1) / 2;
+    if (seg_offsets && W > 1) {
+        // windows are independent: every device takes a contiguous block of windows (and the site range they cover);
+        // results are per window, so this is the single-device result bit for bit
+        const int world = std::min<int>(n_ctx, W);
+        std::vector<int> rcs(world, 0);
+        std::vector<std::string> errs(world);
+        auto work = [&](int r) {
+            int64_t w0, wc;
+            shard_range(W, r, world, w0, wc);
+            const int64_t a = seg_offsets[w0], b = seg_offsets[w0 + wc];
+            std::vector<int64_t> seg((size_t)wc + 1);
+            for (int64_t k = 0; k <= wc; ++k) seg[k] = seg_offsets[w0 + k] - a;
+            rcs[r] = divergence_impl(ctxs[r], false, status + a, posterior_max + a, meth_lvl + a, S, b - a, seg.data(), (int32_t)wc,
+                                     thr, D_out ? D_out + (size_t)w0 * P : nullptr, diff_out ? diff_out + (size_t)w0 * P : nullptr,
+                                     cnt_out ? cnt_out + (size_t)w0 * P : nullptr, p0uu_out ? p0uu_out + w0 : nullptr,
+                                     methsum_out ? methsum_out + (size_t)w0 * S : nullptr,
+                                     nvalid_out ? nvalid_out + (size_t)w0 * S : nullptr, nullptr, nullptr, L);
+            if (rcs[r]) errs[r] = g_last_error;
+        };
+        std::vector<std::thread> th;
+        for (int r = 1; r < world; ++r) th.emplace_back(work, r);
+        work(0);
+        for (auto &t : th) t.join();
+        for (int r = 0; r < world; ++r)
+            if (rcs[r]) {
+                set_error("device shard " + std::to_string(r) + ": " + errs[r]);
+                return rcs[r];
+            }
+        return 0;
+    }
+    // one window = all sites (whole methylomes, BASELINE configs[4]): the SITE axis is sharded in 64-site words; the
+    // integer partial sums add up exactly, so D = diff / (2 cnt) (src/pedigree.rs:257) does not depend on the number
+    // of devices; the per-sample methylation sums are added in device order (p0uu within 1e-12 of one device)
+    const int64_t a0 = seg_offsets ? seg_offsets[0] : 0, b0 = seg_offsets ? seg_offsets[1] : L;
+    if (a0 < 0 || b0 > L || b0 < a0) {
+        set_error("seg_offsets outside [0, L]");
+        return ABFIT_ERR_ARG;
+    }
+    const int64_t words = (b0 - a0 + 63) / 64;
+    const int world = (int)std::max<int64_t>(1, std::min<int64_t>(n_ctx, words));
+    std::vector<std::vector<uint64_t>> pd(world, std::vector<uint64_t>(P)), pc(world, std::vector<uint64_t>(P));
+    std::vector<std::vector<double>> pm(world, std::vector<double>(S));
+    std::vector<std::vector<int64_t>> pn(world, std::vector<int64_t>(S));
+    std::vector<int> rcs(world, 0);
+    std::vector<std::string> errs(world);
+    auto work = [&](int r) {
+        int64_t w0, wc;
+        shard_range(words, r, world, w0, wc);
+        const int64_t a = std::min(a0 + w0 * 64, b0), b = std::min(a0 + (w0 + wc) * 64, b0);
+        rcs[r] = divergence_impl(ctxs[r], false, status + a, posterior_max + a, meth_lvl + a, S, b - a, nullptr, 1, thr, nullptr,
+                                 pd[r].data(), pc[r].data(), nullptr, pm[r].data(), pn[r].data(), nullptr, nullptr, L);
+        if (rcs[r]) errs[r] = g_last_error;
+    };
+    std::vector<std::thread> th;
+    for (int r = 1; r < world; ++r) th.emplace_back(work, r);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int r = 0; r < world; ++r)
+        if (rcs[r]) {
+            set_error("device shard " + std::to_string(r) + ": " + errs[r]);
+            return rcs[r];
+        }
+    for (size_t p = 0; p < P; ++p) {
+        uint64_t d = 0, c = 0;
+        for (int r = 0; r < world; ++r) {
+            d += pd[r][p];
+            c += pc[r][p];
+        }
+        if (diff_out) diff_out[p] = d;
+        if (cnt_out) cnt_out[p] = c;
+        if (D_out) D_out[p] = (double)d / (2.0 * (double)c);  // src/pedigree.rs:257 (0/0 -> NaN)
+    }
+    double acc = 0.0;
+    for (int s = 0; s < S; ++s) {
+        double m = 0.0;
+        int64_t nv = 0;
+        for (int r = 0; r < world; ++r) {
+            m += pm[r][s];
+            nv += pn[r][s];
+        }
+        if (methsum_out) methsum_out[s] = m;
+        if (nvalid_out) nvalid_out[s] = nv;
+        acc += 1.0 - m / (double)nv;  // src/pedigree.rs:179-183
+    }
+    if (p0uu_out) *p0uu_out = acc / (double)S;
+    return 0;
 }
 
 int abfit_divergence_device(abfit_ctx *ctx, const uint8_t *d_status, const double *d_posterior_max,

@@ -536,13 +536,13 @@ struct V2Queue {
 
 // Opens the next item when the current one is used up.  Returns false when idle lanes have to wait (every slot
 // still has running fits) or no items are left.  `busy`: bit s set = slot s has running fits.
-template <class STAGE>
+template <int NSLOTS, class STAGE>
 __device__ __forceinline__ bool v2_open_next(V2Queue &q, const WorkItem *__restrict__ items, int n_items, int *cursor,
                                              int lane, unsigned busy, STAGE stage)
 {
     if (q.exhausted) return false;
     const int slot = __ffs(~busy) - 1;  // first slot without running fits
-    if (slot >= V2_SLOTS) return false;
+    if (slot >= NSLOTS) return false;
     int idx = 0;
     if (lane == 0) idx = atomicAdd(cursor, 1);
     idx = __shfl_sync(FULL, idx, 0);
@@ -560,11 +560,12 @@ __device__ __forceinline__ bool v2_open_next(V2Queue &q, const WorkItem *__restr
 }
 
 // bit s = some lane runs a fit on slot s
+template <int NSLOTS>
 __device__ __forceinline__ unsigned v2_busy_slots(bool active, int my_slot)
 {
     unsigned busy = 0;
 #pragma unroll
-    for (int s = 0; s < V2_SLOTS; ++s) busy |= (__ballot_sync(FULL, active && my_slot == s) ? 1u : 0u) << s;
+    for (int s = 0; s < NSLOTS; ++s) busy |= (__ballot_sync(FULL, active && my_slot == s) ? 1u : 0u) << s;
     return busy;
 }
 
@@ -606,7 +607,7 @@ __device__ __forceinline__ void fit_starts_body_v2(const DevicePools &P, const W
         unsigned idle = __ballot_sync(FULL, L.phase == PH_IDLE);
         while (idle) {
             if (q.next >= q.end) {
-                if (!v2_open_next(q, items, n_items, cursor, lane, v2_busy_slots(L.phase != PH_IDLE, my_slot), stage)) break;
+                if (!v2_open_next<V2_SLOTS>(q, items, n_items, cursor, lane, v2_busy_slots<V2_SLOTS>(L.phase != PH_IDLE, my_slot), stage)) break;
             }
             const int take = min(__popc(idle), q.end - q.next);
             const int rank = __popc(idle & ((1u << lane) - 1u));
@@ -641,7 +642,7 @@ __device__ __forceinline__ void fit_starts_body_v2(const DevicePools &P, const W
 }
 
 // bootstrap refits (src/boot_model.rs:41-100), index-tile formulation (see DGather): a slot holds the window's
-// residuals, scalars and best model; the lane's resample indices are packed as SHARED-MEMORY BYTE
+// residuals, predictions, scalars and best model; the lane's resample indices are packed as SHARED-MEMORY BYTE
 // OFFSETS of the residuals in the lane's slot, so the gather address is again "tile value + link-time constant".
 template <class OBJ>
 __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, const WorkItem *__restrict__ items, int n_items,
@@ -665,20 +666,22 @@ __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, co
     double *slots = smem + 25 * 32;
     const int ng4 = (n_pairs + 3) >> 2;
     uint2 *tile = idx_scratch + (size_t)blockIdx.x * (size_t)scratch_stride + lane;
-    // slot: [resid npad][p_uu0, p_mm0, eqp, penw][best theta 4]; the window's predictions stay in global memory and
-    // are read through L1 (the same address for every lane of a window), which keeps four slots within 12 KB
+    // slot: [resid npad][pred npad][p_uu0, p_mm0, eqp, penw][best theta 4]
     auto stage = [&](int slot, int prob) {
         const DevProblem pb = P.probs[prob];
         double *sl = slots + slot * slot_doubles;
-        for (int i = lane; i < pb.n_pairs; i += 32) sl[i] = resid[pb.pair_off + i];
+        for (int i = lane; i < pb.n_pairs; i += 32) {
+            sl[i] = resid[pb.pair_off + i];
+            sl[npad + i] = pred[pb.pair_off + i];
+        }
         if (lane == 0) {
             const abfit_fit bm = best[prob];
-            sl[npad] = pb.p_uu0;
-            sl[npad + 1] = pb.p_mm0;
-            sl[npad + 2] = pb.eqp;
-            sl[npad + 3] = pb.penw;
+            sl[2 * npad] = pb.p_uu0;
+            sl[2 * npad + 1] = pb.p_mm0;
+            sl[2 * npad + 2] = pb.eqp;
+            sl[2 * npad + 3] = pb.penw;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) sl[npad + 4 + k] = bm.theta[k];
+            for (int k = 0; k < 4; ++k) sl[2 * npad + 4 + k] = bm.theta[k];
         }
         __syncwarp();
     };
@@ -686,21 +689,19 @@ __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, co
     LaneNM L;
     lane_nm_reset(L);
     int my_slot = 0, my_prob = 0;
-    const double *my_pred = pred;
     V2Queue q;
     for (;;) {
         __syncwarp();
         unsigned idle = __ballot_sync(FULL, L.phase == PH_IDLE);
         while (idle) {
             if (q.next >= q.end) {
-                if (!v2_open_next(q, items, n_items, cursor, lane, v2_busy_slots(L.phase != PH_IDLE, my_slot), stage)) break;
+                if (!v2_open_next<V2_BOOT_SLOTS>(q, items, n_items, cursor, lane, v2_busy_slots<V2_BOOT_SLOTS>(L.phase != PH_IDLE, my_slot), stage)) break;
             }
             const int take = min(__popc(idle), q.end - q.next);
             const int rank = __popc(idle & ((1u << lane) - 1u));
             if (((idle >> lane) & 1u) && rank < take) {
                 const int id = q.next + rank;
                 const DevProblem pb = P.probs[q.prob];
-                my_pred = pred + pb.pair_off;
                 const double *sl = slots + q.cur * slot_doubles;
                 // this replicate's resample indices -> byte offsets of its residuals in shared memory
                 const uint32_t base = (uint32_t)((const char *)sl - (const char *)smem);
@@ -721,7 +722,7 @@ __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, co
                 // simplex = [best, vary x 4]  (src/boot_model.rs:69-75)
                 const double *vv = vary + ((size_t)q.prob * n_boot + id) * 16;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) S.X[k * 32] = sl[npad + 4 + k];
+                for (int k = 0; k < 4; ++k) S.X[k * 32] = sl[2 * npad + 4 + k];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) S.X[(4 + k) * 32] = vv[k];
                 nm_begin(L, S, id);
@@ -736,8 +737,8 @@ __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, co
         if (!amask) break;
         if (active) {
             const double *sl = slots + my_slot * slot_doubles;
-            const WarpCtx c = v2_ctx(nullptr, sl + npad, n_pairs);
-            const DGatherL1 Dat{tile, my_pred, reinterpret_cast<const char *>(smem)};
+            const WarpCtx c = v2_ctx(nullptr, sl + 2 * npad, n_pairs);
+            const DGather Dat{tile, sl + npad, reinterpret_cast<const char *>(smem)};
             const double f = OBJ::eval(c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
             abfit_fit res;
             if (nm_advance(L, S, nm, f, res, amask)) {

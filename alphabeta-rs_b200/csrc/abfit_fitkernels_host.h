@@ -15,6 +15,9 @@ namespace abfit {
 constexpr int V2_SLOTS = ABFIT_V2_SLOTS;  // (a generated source may define another count: occupancy experiments)
 // multi-start slot: [D npad][p_uu0, p_mm0, eqp, penw]
 ABFIT_HD_INLINE int v2_fit_slot_doubles(int n_pairs) { return ((n_pairs + 1) & ~1) + 4; }
-// bootstrap slot: [resid npad][p_uu0, p_mm0, eqp, penw][best theta 4]  (the predictions are read through L1)
-ABFIT_HD_INLINE int v2_boot_slot_doubles(int n_pairs) { return ((n_pairs + 1) & ~1) + 8; }
+// bootstrap slot: [resid npad][pred npad][p_uu0, p_mm0, eqp, penw][best theta 4]; two slots (an item is a whole
+// window's replicates; measured: four slots with the predictions read through L1 instead were 5 % slower — the
+// kernel is bound by the load/store unit, and 12 resident warps need the slots to stay within 12 KB)
+constexpr int V2_BOOT_SLOTS = 2;
+ABFIT_HD_INLINE int v2_boot_slot_doubles(int n_pairs) { return 2 * ((n_pairs + 1) & ~1) + 8; }
 }  // namespace abfit

@@ -38,7 +38,7 @@ int launch_fit_starts(cudaStream_t st, const DevicePools &P, const WorkItem *ite
                       const BigScratch &big);
 int launch_select(cudaStream_t st, const DevicePools &P, int n_probs, int n_starts, const abfit_fit *all,
                   abfit_fit *best_out, double *pred, double *resid, int32_t *prob_status, size_t smem_bytes,
-                  bool d_in_shared, const BigScratch &big);
+                  bool d_in_shared, const BigScratch &big, int p_base = 0);  // windows [p_base, p_base + n_probs)
 int launch_fit_boot(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_boot,
                     const abfit_fit *best, const double *pred, const double *resid, const int32_t *resample_idx,
                     const double *vary, double *dstar_scratch, int64_t scratch_stride, NMParams nm,
@@ -67,8 +67,9 @@ int launch_model_divergence(cudaStream_t st, const DevicePools &P, const double 
                             double *puu_out, size_t smem_bytes, const BigScratch &big);
 // vary vertices of every (window, replicate) drawn on the device from the best fits (same numbers as
 // abfit_gen_vary_vertices): out[n_probs][n_boot][4][4]
-int launch_gen_vary(cudaStream_t st, uint64_t seed, uint64_t first_problem_id, int n_probs, int n_boot,
-                    const abfit_fit *best, double *out);
+// (ids: optional device array of per-window generator keys, else first_problem_id + window)
+int launch_gen_vary(cudaStream_t st, uint64_t seed, uint64_t first_problem_id, const unsigned long long *ids, int n_probs,
+                    int n_boot, const abfit_fit *best, double *out);
 int launch_fp64_peak(cudaStream_t st, int blocks, int threads, int iters, double *sink);
 int max_dynamic_smem(int device);
 

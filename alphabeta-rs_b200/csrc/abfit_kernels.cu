@@ -66,12 +66,12 @@ k_fit_boot_gather(DevicePools P, const WorkItem *__restrict__ items, int n_boot,
 // ---------------------------------------------------------------------------------
 template <bool D_SHARED, bool BIG>
 __global__ void __launch_bounds__(32)
-k_select(DevicePools P, int n_starts, const abfit_fit *__restrict__ all, abfit_fit *__restrict__ best_out,
+k_select(DevicePools P, int p_base, int n_starts, const abfit_fit *__restrict__ all, abfit_fit *__restrict__ best_out,
          double *__restrict__ pred, double *__restrict__ resid, int32_t *__restrict__ prob_status,
          double *lm_scratch, size_t lm_stride)
 {
     const int lane = threadIdx.x;
-    const int p = blockIdx.x;
+    const int p = p_base + blockIdx.x;
     const DevProblem pb = P.probs[p];
     Carved cv = BIG ? carve_big(pb, P, false, nullptr, lm_scratch, lm_stride) : carve_and_stage<InterpObjective, D_SHARED>(pb, P, 0);
     __syncwarp();
@@ -381,8 +381,8 @@ k_model_div(DevicePools P, const double *__restrict__ theta4, double *__restrict
 // FP64 roofline micro-benchmark: 8 independent DFMA chains per thread
 // ---------------------------------------------------------------------------------
 // Model::vary x 4 per bootstrap replicate (src/boot_model.rs:69-75, src/structs.rs:100-128), one thread per coordinate
-__global__ void k_gen_vary(uint64_t seed, uint64_t first_problem_id, int n_probs, int n_boot,
-                           const abfit_fit *__restrict__ best, double *__restrict__ out)
+__global__ void k_gen_vary(uint64_t seed, uint64_t first_problem_id, const unsigned long long *__restrict__ ids,
+                           int n_probs, int n_boot, const abfit_fit *__restrict__ best, double *__restrict__ out)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t per_prob = (size_t)n_boot * 16;
@@ -390,7 +390,8 @@ __global__ void k_gen_vary(uint64_t seed, uint64_t first_problem_id, int n_probs
     const int p = (int)(i / per_prob);
     const size_t r = i - (size_t)p * per_prob;
     const int b = (int)(r >> 4), v = (int)((r >> 2) & 3), j = (int)(r & 3);
-    out[i] = vary_coordinate(seed, first_problem_id + (uint64_t)p, (uint64_t)b, v, j, best[p].theta[j]);
+    const uint64_t key = ids ? (uint64_t)ids[p] : first_problem_id + (uint64_t)p;
+    out[i] = vary_coordinate(seed, key, (uint64_t)b, v, j, best[p].theta[j]);
 }
 
 __global__ void k_fp64_peak(int iters, double *sink)
@@ -469,20 +470,20 @@ int launch_fit_starts(cudaStream_t st, const DevicePools &P, const WorkItem *ite
 
 int launch_select(cudaStream_t st, const DevicePools &P, int n_probs, int n_starts, const abfit_fit *all,
                   abfit_fit *best_out, double *pred, double *resid, int32_t *prob_status, size_t smem_bytes,
-                  bool d_in_shared, const BigScratch &big)
+                  bool d_in_shared, const BigScratch &big, int p_base)
 {
     if (n_probs <= 0) return 0;
     if (big.lm) {
         if (int rc = prep_kernel(k_select<false, true>, smem_bytes)) return rc;
-        k_select<false, true><<<n_probs, 32, smem_bytes, st>>>(P, n_starts, all, best_out, pred, resid, prob_status,
+        k_select<false, true><<<n_probs, 32, smem_bytes, st>>>(P, p_base, n_starts, all, best_out, pred, resid, prob_status,
                                                                big.lm, big.lm_stride);
     } else if (d_in_shared) {
         if (int rc = prep_kernel(k_select<true, false>, smem_bytes)) return rc;
-        k_select<true, false><<<n_probs, 32, smem_bytes, st>>>(P, n_starts, all, best_out, pred, resid, prob_status,
+        k_select<true, false><<<n_probs, 32, smem_bytes, st>>>(P, p_base, n_starts, all, best_out, pred, resid, prob_status,
                                                                nullptr, 0);
     } else {
         if (int rc = prep_kernel(k_select<false, false>, smem_bytes)) return rc;
-        k_select<false, false><<<n_probs, 32, smem_bytes, st>>>(P, n_starts, all, best_out, pred, resid, prob_status,
+        k_select<false, false><<<n_probs, 32, smem_bytes, st>>>(P, p_base, n_starts, all, best_out, pred, resid, prob_status,
                                                                 nullptr, 0);
     }
     ABFIT_CUDA(cudaGetLastError());
@@ -589,12 +590,12 @@ int launch_model_divergence(cudaStream_t st, const DevicePools &P, const double 
     return 0;
 }
 
-int launch_gen_vary(cudaStream_t st, uint64_t seed, uint64_t first_problem_id, int n_probs, int n_boot,
-                    const abfit_fit *best, double *out)
+int launch_gen_vary(cudaStream_t st, uint64_t seed, uint64_t first_problem_id, const unsigned long long *ids, int n_probs,
+                    int n_boot, const abfit_fit *best, double *out)
 {
     const size_t n = (size_t)n_probs * n_boot * 16;
     if (n == 0) return 0;
-    k_gen_vary<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(seed, first_problem_id, n_probs, n_boot, best, out);
+    k_gen_vary<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(seed, first_problem_id, ids, n_probs, n_boot, best, out);
     ABFIT_CUDA(cudaGetLastError());
     return 0;
 }

@@ -386,35 +386,6 @@ struct DGather {
     }
 };
 
-// The same with the predictions in global memory (continuous-scheduling bootstrap kernel): every lane of a window
-// reads the same address, so the loads are L1 broadcasts; pred + pair_off is only 8-byte aligned.
-struct DGatherL1 {
-    const uint2 *tile;   // [group][32] (lane folded in): four u16 shared-memory byte offsets of the residuals
-    const double *pred;  // global: predictions of the lane's window
-    const char *smem;    // base of dynamic shared memory
-    __device__ __forceinline__ void load4(int i, double d[4]) const
-    {
-        const uint2 *p = tile + (size_t)(i >> 2) * 32;
-#ifdef __CUDA_ARCH__
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 4 * 32));
-        const double p0 = __ldg(pred + i), p1 = __ldg(pred + i + 1), p2 = __ldg(pred + i + 2), p3 = __ldg(pred + i + 3);
-#else
-        const double p0 = pred[i], p1 = pred[i + 1], p2 = pred[i + 2], p3 = pred[i + 3];
-#endif
-        const uint2 w = *p;
-        d[0] = p0 + *reinterpret_cast<const double *>(smem + (w.x & 0xffffu));
-        d[1] = p1 + *reinterpret_cast<const double *>(smem + (w.x >> 16));
-        d[2] = p2 + *reinterpret_cast<const double *>(smem + (w.y & 0xffffu));
-        d[3] = p3 + *reinterpret_cast<const double *>(smem + (w.y >> 16));
-    }
-    __device__ __forceinline__ double operator()(int i) const
-    {
-        const uint2 w = tile[(size_t)(i >> 2) * 32];
-        const uint32_t h = (i & 2) ? w.y : w.x;
-        return pred[i] + *reinterpret_cast<const double *>(smem + ((i & 1) ? (h >> 16) : (h & 0xffffu)));
-    }
-};
-
 // Objective (src/structs.rs:191-217).  penalty=false gives the penalty-free LSE of
 // src/ab_neutral.rs:88-93 (r*r + 0.0 == r*r, so one loop serves both).
 //

@@ -482,16 +482,16 @@ std::vector<WorkItem> make_items_wide(const HostPlan &hp, int count_per_prob, in
 }
 
 std::vector<WorkItem> make_items_guided(const HostPlan &hp, int count_per_prob, int resident_warps, int max_chunk,
-                                        bool skip_nan)
+                                        bool skip_nan, int p_first, int p_end)
 {
-    const int n_probs = (int)hp.probs.size();
+    const int n_probs = p_end < 0 ? (int)hp.probs.size() : p_end;
     int64_t remaining = 0;
-    for (int p = 0; p < n_probs; ++p)
+    for (int p = p_first; p < n_probs; ++p)
         if (!(skip_nan && hp.d_has_nan[p])) remaining += count_per_prob;
     const int64_t P2 = 2 * (int64_t)std::max(resident_warps, 1);
     if (const char *fc = getenv("ABFIT_DEV_CHUNK")) max_chunk = std::max(1, atoi(fc));
     std::vector<WorkItem> items;
-    for (int p = 0; p < n_probs; ++p) {
+    for (int p = p_first; p < n_probs; ++p) {
         if (skip_nan && hp.d_has_nan[p]) continue;
         for (int f = 0; f < count_per_prob;) {
             int64_t chunk = remaining / P2;

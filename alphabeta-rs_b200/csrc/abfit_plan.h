@@ -61,6 +61,6 @@ std::vector<WorkItem> make_items(const HostPlan &hp, int count_per_prob, int n_s
 // window, at least 32 — so the bulk of a batch runs in long items and the warps run out of work within about one
 // fit of each other.
 std::vector<WorkItem> make_items_guided(const HostPlan &hp, int count_per_prob, int resident_warps, int max_chunk,
-                                        bool skip_nan);
+                                        bool skip_nan, int p_first = 0, int p_end = -1 /* windows [p_first, p_end) */);
 
 }  // namespace abfit

@@ -92,6 +92,8 @@ const char *abfit_last_error(void);
 const char *abfit_version(void);
 
 /* ---- context ------------------------------------------------------------ */
+/* CUDA devices visible to this process (0 without a driver) */
+int abfit_device_count(void);
 int abfit_ctx_create(int device, abfit_ctx **out);
 void abfit_ctx_destroy(abfit_ctx *ctx);
 /* device properties the bench reports: sm count, max SM clock (kHz), HBM bytes */
@@ -181,6 +183,19 @@ int abfit_alphabeta_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_
                           uint32_t flags, abfit_fit *best_out, double *pred_out, double *resid_out,
                           int32_t *prob_status_out, double *rows_out, double *analysis_out);
 
+/* The same over several GPUs of one box (the reference's window loop src/cli/metaprofile.rs:50-72 is
+ * serial): one context per device (ctxs[0..n_ctx)), one host thread per context, contiguous balanced blocks of windows;
+ * every shard writes its windows' results straight into the caller's arrays, in window order.  The shards never
+ * exchange data — no collective.  Window p of the call keeps its generator key whatever the sharding:
+ * problem_ids[p] when given (e.g. the window's position in the genome, so that dropping an empty window does not
+ * change its neighbours' bootstrap), else first_problem_id + p.  Bit-identical to one device. */
+int abfit_alphabeta_batch_multi(abfit_ctx *const *ctxs, int32_t n_ctx, const abfit_problem *probs, int32_t n_probs,
+                                int32_t n_starts, const double *simplices, int32_t n_boot, const int32_t *resample_idx,
+                                uint64_t vary_seed, uint64_t first_problem_id, const uint64_t *problem_ids,
+                                int32_t max_iters_fit, int32_t max_iters_boot, double sd_tol, uint32_t flags,
+                                abfit_fit *best_out, double *pred_out, double *resid_out, int32_t *prob_status_out,
+                                double *rows_out, double *analysis_out);
+
 /* Observed pairwise divergence + p0uu.  Replaces `DMatrix::from` (src/pedigree.rs:213-262)
  * and the per-sample statistics of `Pedigree::build` (src/pedigree.rs:159-183).
  *  status        [S][L] u8: 0 = U, 1 = I, 2 = M (src/methylation_site.rs:130-136)
@@ -198,6 +213,15 @@ int abfit_divergence(abfit_ctx *ctx, const uint8_t *status, const double *poster
                      int32_t S, int64_t L, const int64_t *seg_offsets, int32_t W, double thr, double *D_out,
                      uint64_t *diff_out, uint64_t *cnt_out, double *p0uu_out, double *methsum_out,
                      int64_t *nvalid_out);
+
+/* abfit_divergence over several GPUs (one context per device).  W > 1: the WINDOWS are sharded (results are per
+ * window: bit-identical to one device).  One window = whole methylomes (src/pedigree.rs:213-262 at 200 x 5 M sites):
+ * the SITE axis is sharded; the exact integer sums of every shard are added on the host, so D is bit-identical for any
+ * number of devices, and p0uu agrees within 1e-12 (per-sample sums added in device order). */
+int abfit_divergence_multi(abfit_ctx *const *ctxs, int32_t n_ctx, const uint8_t *status, const double *posterior_max,
+                           const double *meth_lvl, int32_t S, int64_t L, const int64_t *seg_offsets, int32_t W, double thr,
+                           double *D_out, uint64_t *diff_out, uint64_t *cnt_out, double *p0uu_out, double *methsum_out,
+                           int64_t *nvalid_out);
 
 /* The same with the three input arrays already in device memory (site tables that stay resident between
  * calls; bench: HBM roofline of the packing pass).  seg_offsets and all outputs are host memory.
@@ -224,6 +248,13 @@ int abfit_batch_upload_boot(abfit_batch *b, int32_t n_boot, const abfit_fit *bes
                             const double *resid, const int32_t *resample_idx, const double *vary_vertices);
 int abfit_batch_run_boot(abfit_batch *b, int32_t max_iters, double sd_tol, uint32_t flags);
 int abfit_batch_download_boot(abfit_batch *b, double *rows_out, abfit_fit *fits_out);
+/* run_fit + run_boot of an uploaded batch as ONE pipelined pass: the windows are cut into sub-batches, each a
+ * fit -> select -> bootstrap chain on its own stream, so that the long fits that end every multi-start launch and the
+ * bootstraps overlap with the next sub-batch's fits (what abfit_alphabeta_batch does internally).  Same results as
+ * run_fit followed by run_boot.  abfit_batch_timing then reports the whole span as ms[0]. */
+int abfit_batch_run_pipelined(abfit_batch *b, int32_t max_iters_fit, int32_t max_iters_boot, double sd_tol, uint32_t flags);
+/* sub-batches abfit_batch_run_pipelined uses for this batch (1: no overlap possible) */
+int abfit_batch_pipes(abfit_batch *b);
 int abfit_batch_sync(abfit_batch *b);
 /* device times of the last run_fit / run_boot (ms, CUDA events on the context stream):
  * ms[0] multi-start NM kernel, ms[1] best-of-starts select, ms[2] bootstrap NM kernel;

@@ -737,7 +737,8 @@ def test_resample_index_check_large_pedigree(ab, ctx):
     assert e.value.code == ab.ERR_ARG
 
 
-@pytest.mark.parametrize("env", [{}, {"ABFIT_DEV_CHUNK": "40"}, {"ABFIT_DEV_CHUNK": "7"},
+@pytest.mark.parametrize("env", [{}, {"ABFIT_DEV_CHUNK": "40"}, {"ABFIT_DEV_CHUNK": "7"}, {"ABFIT_DEV_PIPES": "2"},
+                                 {"ABFIT_DEV_PIPES": "5", "ABFIT_DEV_CHUNK": "40"},
                                  {"ABFIT_DEV_SCHED": "1", "ABFIT_DEV_NWARPS": "3", "ABFIT_DEV_CHUNK": "150"},
                                  {"ABFIT_DEV_SCHED": "1", "ABFIT_DEV_NWARPS": "4"}, {"ABFIT_DEV_SCHED": "1"}])
 def test_specialised_kernels_are_bit_identical(ab, ctx, oracle, ped351, ped78, monkeypatch, env):
@@ -839,6 +840,47 @@ def test_specialised_kernels_ragged_counts(ab, ctx, oracle, ped351, monkeypatch,
         b.close()
 
 
+def test_pipelined_pass_equals_fit_then_boot(ab, ctx, ped351, monkeypatch):
+    """abfit_batch_run_pipelined (sub-batches of windows as overlapping fit -> select -> bootstrap chains on their own
+    streams) gives the bytes of run_fit followed by run_boot; repeated, because the overlap is scheduling-dependent"""
+    rng = np.random.default_rng(57)
+    base, _ = synth_problem(rng, ped351, n_keep=101)
+    cases = []
+    for _ in range(9):
+        p = base.copy()
+        p[:, 3] = np.maximum(base[:, 3] * rng.uniform(0.7, 1.3) + rng.normal(0, 3e-4, len(base)), 0.0)
+        cases.append((p, float(rng.uniform(0.6, 0.95))))
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    n_starts, n_boot = 150, 37
+    sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    idx = np.concatenate([ab.gen_resample_idx(SEED, i, n_boot, len(p)).ravel() for i, (p, u) in enumerate(cases)])
+    monkeypatch.setenv("ABFIT_JIT", "1")
+    monkeypatch.setenv("ABFIT_DEV_PIPES", "4")
+    b = ctx.batch(probs)
+    b.upload_starts(sx)
+    b.run_fit()
+    res = b.download_fit(want_all=True)
+    vary = np.stack([ab.gen_vary_vertices(SEED, i, n_boot, res.best[i]["theta"]) for i in range(len(cases))])
+    b.upload_boot(idx, vary)
+    b.run_boot()
+    rows, fits = b.download_boot(want_fits=True)
+    t_seq = b.timing()
+    for rep in range(5):
+        b.run_pipelined()
+        assert b.pipes() == 4
+        res2 = b.download_fit(want_all=True)
+        rows2, fits2 = b.download_boot(want_fits=True)
+        assert res2.all.tobytes() == res.all.tobytes() and res2.best.tobytes() == res.best.tobytes(), rep
+        assert np.array_equal(res2.pred, res.pred) and np.array_equal(res2.resid, res.resid)
+        assert rows2.tobytes() == rows.tobytes() and fits2.tobytes() == fits.tobytes(), rep
+        t = b.timing()
+        assert t["evals_fit"] == t_seq["evals_fit"] and t["evals_boot"] == t_seq["evals_boot"] and t["launches"] == 12
+    b.close()
+    # the one-shot call takes the same pipelined path (vary vertices drawn on the device per sub-batch)
+    out = ctx.alphabeta_batch(probs, sx, idx, SEED)
+    assert np.array_equal(out["rows"], rows) and np.array_equal(out["best"]["theta"], res.best["theta"])
+
+
 def test_specialised_kernels_mixed_batch_falls_back_to_interpreter(ab, ctx, ped351, ped78, monkeypatch):
     """a batch that mixes pedigree programs is not specialised (one kernel per program would be needed); same API"""
     rng = np.random.default_rng(56)
@@ -852,3 +894,70 @@ def test_specialised_kernels_mixed_batch_falls_back_to_interpreter(ab, ctx, ped3
     b.run_fit()
     assert np.all(b.download_fit().status == 0)
     b.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-GPU inside the product: one context + host thread per device, windows (or sites) sharded
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ctx_pool(ab):
+    """one context per visible device; on a one-GPU box three contexts on device 0 (the sharding, threading and
+    gathering logic is the same, only the devices coincide)"""
+    n = ab.device_count()
+    devs = list(range(n)) if n >= 2 else [0, 0, 0]
+    pool = [ab.Context(d) for d in devs]
+    yield pool
+    for c in pool:
+        c.close()
+
+
+def test_multi_device_alphabeta_equals_single_device(ab, ctx, ctx_pool, ped351, ped78):
+    """abfit_alphabeta_batch_multi (windows sharded over the contexts, ragged pedigrees so the shards' offsets into
+    the concatenated arrays differ) returns the single-device bytes; and with per-window generator keys a window's
+    result does not change when another window is dropped from the batch"""
+    rng = np.random.default_rng(71)
+    cases = [synth_problem(rng, ped351, n_keep=k) for k in (60, 60, 33, 90, 60, 17, 45)]
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    ids = np.array([3, 4, 9, 10, 11, 40, 41], dtype=np.uint64)  # window ids with gaps (empty windows were dropped)
+    n_starts, n_boot = 64, 24
+    sx = np.stack([ab.gen_start_simplices(SEED, int(i), n_starts, float(p[:, 3].max())) for i, (p, u) in zip(ids, cases)])
+    idx = np.concatenate([ab.gen_resample_idx(SEED, int(i), n_boot, len(p)).ravel() for i, (p, u) in zip(ids, cases)])
+    one = ab.alphabeta_batch_multi([ctx], probs, sx, idx, SEED, problem_ids=ids)
+    many = ab.alphabeta_batch_multi(ctx_pool, probs, sx, idx, SEED, problem_ids=ids)
+    for k in ("best", "pred", "resid", "status", "rows", "analysis"):
+        assert one[k].tobytes() == many[k].tobytes(), k
+    # consecutive keys: the single-context entry point gives the same bytes
+    idx2 = np.concatenate([ab.gen_resample_idx(SEED, 100 + i, n_boot, len(p)).ravel() for i, (p, u) in enumerate(cases)])
+    sx2 = np.stack([ab.gen_start_simplices(SEED, 100 + i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    a = ctx.alphabeta_batch(probs, sx2, idx2, SEED, first_problem_id=100)
+    b = ab.alphabeta_batch_multi(ctx_pool, probs, sx2, idx2, SEED, first_problem_id=100)
+    for k in ("best", "pred", "resid", "status", "rows", "analysis"):
+        assert a[k].tobytes() == b[k].tobytes(), k
+    # drop window 2: everybody else keeps its results (ADVICE r1: vary vertices used to be keyed by batch position)
+    keep = [0, 1, 3, 4, 5, 6]
+    offs = np.concatenate([[0], np.cumsum([len(p) for p, u in cases])])
+    idx_k = np.concatenate([idx[offs[i] * n_boot:offs[i + 1] * n_boot] for i in keep])
+    sub = ab.alphabeta_batch_multi(ctx_pool, [probs[i] for i in keep], sx[keep], idx_k, SEED, problem_ids=ids[keep])
+    assert np.array_equal(sub["rows"], many["rows"][keep]) and np.array_equal(sub["best"]["theta"], many["best"]["theta"][keep])
+
+
+def test_multi_device_divergence(ab, ctx, ctx_pool, oracle):
+    """abfit_divergence_multi: window-sharded = single device bit for bit; site-sharded whole methylomes: integer sums
+    and D exact, p0uu within 1e-12 (north_star)"""
+    rng = np.random.default_rng(72)
+    S, L = 11, 40_000
+    status, post, meth = synth_methylomes(rng, S, L)
+    seg = np.array([0, 100, 100, 1000, 7777, 7778, 20000, 39999, 40000], dtype=np.int64)
+    one = ctx.dmatrix(status, post, meth, 0.99, seg)
+    many = ab.dmatrix_multi(ctx_pool, status, post, meth, 0.99, seg)
+    for k in ("diff", "cnt", "nvalid"):
+        assert np.array_equal(one[k], many[k]), k
+    for k in ("D", "p0uu", "methsum"):
+        assert np.array_equal(one[k], many[k], equal_nan=True), k
+    whole1 = ctx.dmatrix(status, post, meth, 0.99)
+    whole = ab.dmatrix_multi(ctx_pool, status, post, meth, 0.99)
+    D, diff, cnt = oracle.dmatrix(status, post, 0.99)
+    assert np.array_equal(whole["diff"][0], diff) and np.array_equal(whole["cnt"][0], cnt) and np.array_equal(whole["D"][0], D)
+    assert np.array_equal(whole["nvalid"], whole1["nvalid"])
+    p0 = oracle.p0uu(post, meth, 0.99)[0]
+    assert abs(whole["p0uu"][0] - p0) <= 1e-12 * abs(p0)

@@ -179,7 +179,7 @@ def test_metaprofile_cli_fused_pipeline(ab, ctx, oracle, tmp_path):
         rc, best, _, pred, resid = oracle.ab_neutral(pb, sx, flags=flags, n_threads=8)
         assert rc == 0
         idx = ab.gen_resample_idx(seed, w, n_it, len(ped))
-        vary = ab.gen_vary_vertices(seed, f, n_it, best["theta"])  # keyed by the position in the batch
+        vary = ab.gen_vary_vertices(seed, w, n_it, best["theta"])  # keyed by the window id, like the starts and the resamples
         rc2, rows, _ = oracle.boot_model(pb, best["theta"], pred, resid, idx, vary, flags=flags, n_threads=8)
         assert rc2 == 0
         region = 0 if w < 20 else 1 if w < 40 else 2
