@@ -1,7 +1,7 @@
 // alphabeta — command-line front end with the flags, console block and output files of the reference's
 // `alphabeta` binary (src/cli/alphabeta.rs:8-38, src/arguments.rs:96-114, src/alphabeta.rs:23-59), on top of libabfit.
 //
-//   alphabeta -n nodelist.txt -e edgelist.txt [-i 1000] [-p 0.99] [-o .] [--seed N] [--device 0]
+//   alphabeta -n nodelist.txt -e edgelist.txt [-i 1000] [-p 0.99] [-o .] [--seed N] [--device 0 | --devices 0-7]
 //
 // Differences that are deliberate: the random starts / resamples come from a seed (default 0xAB0B200,
 // `--seed` is an extra flag; the reference uses an unseeded thread_rng), there are no progress bars and
@@ -52,6 +52,7 @@ int main(int argc, char **argv)
         else if (a == "-o" || a == "--output") output = val("--output");
         else if (a == "--seed") seed = std::strtoull(val("--seed"), nullptr, 0);
         else if (a == "--device") device = std::atoi(val("--device"));
+        else if (a == "--devices") device = std::atoi(val("--devices"));  // one pedigree = one window: its starts and replicates stay on the first listed GPU
         else if (a == "-h" || a == "--help") {
             std::printf("Usage: alphabeta [OPTIONS]\n\nOptions:\n"
                         "  -i, --iterations <ITERATIONS>  Number of iterations to run for Nelder-Mead optimization [default: 1000]\n"

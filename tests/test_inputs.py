@@ -196,3 +196,16 @@ def test_metaprofile_cli_fused_pipeline(ab, ctx, oracle, tmp_path):
     assert open(os.path.join(out, "results.txt")).read() == want
     raw = np.load(os.path.join(out, "raw.npy"))
     assert raw.shape == (n_it, 7, len(results)) and np.array_equal(raw, np.stack(raws, axis=2))
+    # --devices: windows sharded over several GPUs (all visible ones; on a one-GPU box three contexts on device 0) give
+    # the same files byte for byte
+    out2 = os.path.join(tmp_path, "out_multi")
+    os.makedirs(out2)
+    nd = ab.device_count()
+    devs = f"0-{nd - 1}" if nd >= 2 else "0,0,0"
+    r2 = subprocess.run([exe, "-m", os.path.join(GOLDEN, "methylome"), "-g", ann, "-w", "10", "-s", "5", "-c", "200", "-o", out2,
+                         "--name", "run7", "--iterations", str(n_it), "--seed", str(seed), "--devices", devs, "alphabeta",
+                         "--nodes", os.path.join(GOLDEN, "nodelist.txt"), "--edges", os.path.join(GOLDEN, "edgelist.txt")],
+                        capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0, r2.stdout + r2.stderr
+    for fn in ("results.txt", "raw.npy", "distributions.txt", "steady_state_methylation.txt"):
+        assert open(os.path.join(out2, fn), "rb").read() == open(os.path.join(out, fn), "rb").read(), fn
