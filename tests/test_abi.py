@@ -109,3 +109,10 @@ def test_literal_sort_picks_the_same_winner(oracle):
     a = oracle.ab_neutral(pb, sx, flags=fl, n_threads=4)
     b = oracle.ab_neutral(pb, sx, flags=fl | oracle.LITERAL_SORT, n_threads=4)
     assert a[0] == b[0] == 0 and a[1]["start_id"] == b[1]["start_id"] and np.array_equal(a[3], b[3])
+
+
+def test_rust_sys_crate_names_only_declared_entry_points():
+    """rust/abfit-sys (untested courtesy binding: no Rust toolchain here) must at least name real entry points"""
+    src = open(os.path.join(ROOT, "rust", "abfit-sys", "src", "lib.rs")).read()
+    rust = set(re.findall(r"pub fn (abfit_[a-z0-9_]+)\s*\(", src))
+    assert len(rust) >= 20 and rust <= set(declared_symbols()), sorted(rust - set(declared_symbols()))
