@@ -5,12 +5,14 @@
 // per window (src/cli/metaprofile.rs:50-72).
 //
 //   metaprofile -m <methylome dir> -g <annotation> [-w 5] [-s 0] [-o .] [-a] [-c 2048] [-i] [--name N]
-//               [--cutoff-gene-length] [--iterations 100] [--seed N] [--device 0 | --devices 0-7]
+//               [--cutoff-gene-length] [--iterations 100] [--seed N] [--device 0 | --devices 0-7] [--write-windows]
 //               [alphabeta --nodes <nodelist> --edges <edgelist>]
 //
 // Files written (formats of the reference): distribution_<file>, distributions.txt, steady_state_methylation.txt,
 // all_steady_state_methylation.txt and, with the sub-command, results.txt and raw.npy (iterations x 7 x windows).
-// Deliberate differences: no per-window directories / methylome copies and no metaplot.png; methylome files are
+// --write-windows additionally writes the reference's per-window directory tree ({region}/{window * step}/{file},
+// nodelist.txt / edgelist.txt per directory; src/setup.rs:5-74, src/windows.rs:259-285) — the fused pipeline does not
+// read it.  Deliberate differences: no metaplot.png; methylome files are
 // processed in name order (the reference uses the directory's own order); every window is fitted on ITS OWN sites
 // (the reference only does that when the nodelist holds absolute, tab-separated paths: src/setup.rs:48-58), the
 // measured nodes being matched to the methylome files by file name; the windows looped over are those of
@@ -26,6 +28,7 @@
 #include <dirent.h>
 #include <fstream>
 #include <map>
+#include <sstream>
 #include <string>
 #include <sys/stat.h>
 #include <vector>
@@ -48,6 +51,12 @@ static std::string base_name(const std::string &p)
     const size_t k = p.find_last_of('/');
     return k == std::string::npos ? p : p.substr(k + 1);
 }
+static void mkdirs(const std::string &path)  // fs::create_dir_all
+{
+    for (size_t i = 1; i <= path.size(); ++i)
+        if (i == path.size() || path[i] == '/') mkdir(path.substr(0, i).c_str(), 0755);
+}
+
 static int write_text(const std::string &path, const std::string &c)
 {
     FILE *f = std::fopen(path.c_str(), "wb");
@@ -64,13 +73,14 @@ struct Sample {
     std::vector<double> post, meth;
     std::vector<int32_t> dist;
     std::vector<int64_t> order, seg;  // sites of window w: order[seg[w] .. seg[w+1]) (file order)
+    std::vector<std::string> original;  // --write-windows: the parsed lines as read (MethylationSite::original)
 };
 
 int main(int argc, char **argv)
 {
     std::string methylome, genome, output = ".", name, nodes, edges;
     uint32_t window_size = 5, window_step = 0, cutoff = 2048;
-    bool absolute = false, invert = false, cutoff_gene_length = false, sub = false;
+    bool absolute = false, invert = false, cutoff_gene_length = false, sub = false, write_windows = false;
     long iterations = 100;
     unsigned long long seed = 0xAB0B200ull;
     int device = 0;
@@ -102,6 +112,7 @@ int main(int argc, char **argv)
         else if (a == "--iterations") iterations = std::atol(val());
         else if (a == "--seed") seed = std::strtoull(val(), nullptr, 0);
         else if (a == "--device") device = std::atoi(val());
+        else if (a == "--write-windows") write_windows = true;
         else if (a == "--devices") {
             const std::string v = val();
             size_t pos = 0;
@@ -203,6 +214,7 @@ int main(int argc, char **argv)
             if (!line.empty() && line.back() == '\r') line.pop_back();
             if (abfit_parse_methylome_line(line.c_str(), invert, &site, &post, &status, &lvl) != 0) continue;
             S.sites.push_back(site);
+            if (write_windows) S.original.push_back(line);
             S.status.push_back((uint8_t)status);
             S.post.push_back(post);
             S.meth.push_back(lvl);
@@ -277,6 +289,70 @@ int main(int argc, char **argv)
     write_text(output + "/steady_state_methylation.txt", avg_s);
     write_text(output + "/all_steady_state_methylation.txt", all_s);
     write_text(output + "/distributions.txt", all_d);
+    if (write_windows) {
+        // The per-window directory tree of the reference (setup_output_dir src/setup.rs:5-74, Windows::save
+        // src/windows.rs:259-285): {output}/{upstream,gene,downstream}/{window * step}/{methylome file} holding the
+        // header row and the window's original lines; with the sub-command every directory also gets the edgelist and
+        // the nodelist, whose '/'-led tab-separated lines are re-pathed into the directory (src/setup.rs:48-58).  The
+        // fused pipeline below does not read any of it — this is for tools that consume the reference's layout.
+        static const char *HEADER = "seqnames\tstart\tstrand\tcontext\tcounts.methylated\tcounts.total\tposteriorMax\tstatus\trc.meth.lvl\tcontext.trinucleotide\n";
+        const char *side_name[3] = {"upstream", "gene", "downstream"};
+        const uint32_t side_max[3] = {absolute ? cutoff : 100u, absolute ? max_gene_length : 100u, absolute ? cutoff : 100u};
+        std::string nodes_text, edges_text;
+        if (sub) {
+            std::ifstream fn(nodes), fe(edges);
+            std::stringstream a, b;
+            a << fn.rdbuf();
+            b << fe.rdbuf();
+            nodes_text = a.str();
+            edges_text = b.str();
+        }
+        for (int side = 0; side < 3; ++side)
+            for (uint32_t window = 0; window < side_max[side]; window += window_step) {
+                const std::string dir = output + "/" + side_name[side] + "/" + std::to_string(window);
+                mkdirs(dir);
+                if (!sub) continue;
+                std::string nodelist;
+                size_t pos = 0;
+                for (;;) {  // nodes.split('\n'): a trailing newline yields a last empty piece, which also gets its "\n"
+                    const size_t e = nodes_text.find('\n', pos);
+                    std::string line = nodes_text.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
+                    if (!line.empty() && line[0] == '/') {
+                        const std::string old_file = line.substr(0, line.find('\t'));
+                        const std::string fname = old_file.substr(old_file.find_last_of('/') + 1);
+                        const std::string repl = dir + "/" + fname;
+                        std::string out;
+                        size_t q = 0;
+                        for (;;) {  // str::replace: every occurrence
+                            const size_t h = line.find(old_file, q);
+                            if (h == std::string::npos) break;
+                            out += line.substr(q, h - q) + repl;
+                            q = h + old_file.size();
+                        }
+                        line = out + line.substr(q);
+                    }
+                    nodelist += line + "\n";
+                    if (e == std::string::npos) break;
+                    pos = e + 1;
+                }
+                write_text(dir + "/nodelist.txt", nodelist);
+                write_text(dir + "/edgelist.txt", edges_text);
+            }
+        for (const Sample &A : samples) {
+            int w = 0;
+            for (int side = 0; side < 3; ++side)
+                for (int i = 0; i < nwin[side]; ++i, ++w) {
+                    const std::string dir = output + "/" + side_name[side] + "/" + std::to_string((uint64_t)i * window_step);
+                    mkdirs(dir);
+                    std::string text = HEADER;
+                    for (int64_t q = A.seg[w]; q < A.seg[w + 1]; ++q) {
+                        if (q > A.seg[w]) text += "\n";
+                        text += A.original[(size_t)A.order[(size_t)q]];
+                    }
+                    write_text(dir + "/" + A.name, text);
+                }
+        }
+    }
     if (!sub) {
         std::printf("Done\n");
         return 0;

@@ -209,3 +209,48 @@ def test_metaprofile_cli_fused_pipeline(ab, ctx, oracle, tmp_path):
     assert r2.returncode == 0, r2.stdout + r2.stderr
     for fn in ("results.txt", "raw.npy", "distributions.txt", "steady_state_methylation.txt"):
         assert open(os.path.join(out2, fn), "rb").read() == open(os.path.join(out, fn), "rb").read(), fn
+
+
+def test_metaprofile_write_windows_layout(oracle, tmp_path):
+    """--write-windows: the reference's per-window tree (Windows::save src/windows.rs:259-285, setup_output_dir
+    src/setup.rs:5-74).  No GPU involved: extraction only, plus the nodelist / edgelist copies of the sub-command's
+    set-up checked through a run that stops at the missing device."""
+    ann = os.path.join(tmp_path, "ann.bed")
+    genes = [(1, 300, 700, "-"), (1, 250, 800, "+"), (2, 1200, 1600, "+"), (3, 600, 900, "*")]
+    open(ann, "w").write("".join(f"{c}\t{s}\t{e}\tg{i}\tgbM\t{sd}\n" for i, (c, s, e, sd) in enumerate(genes)))
+    out = os.path.join(tmp_path, "out")
+    os.makedirs(out)
+    exe = os.path.join(ROOT, "alphabeta-rs_b200", "metaprofile")
+    r = subprocess.run([exe, "-m", os.path.join(GOLDEN, "methylome"), "-g", ann, "-w", "10", "-s", "5", "-c", "200", "-o", out,
+                        "--write-windows"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    header = ("seqnames\tstart\tstrand\tcontext\tcounts.methylated\tcounts.total\tposteriorMax\tstatus\trc.meth.lvl\t"
+              "context.trinucleotide\n")
+    og = [(oracle.chromosome_id(str(c)), s, e, STRAND[sd]) for c, s, e, sd in genes]
+    for fn in sorted(os.listdir(os.path.join(GOLDEN, "methylome"))):
+        lines, sites = [], []
+        for line in open(os.path.join(GOLDEN, "methylome", fn)).read().split("\n")[1:]:
+            q = oracle.parse_methylome_line(line)
+            if q is not None:
+                lines.append(line)
+                sites.append((oracle.chromosome_id(str(q["chromosome"])), q["start"], q["end"], STRAND[q["strand"]]))
+        dist, assign = oracle.extract_windows(og, sites, window_size=10, window_step=5, cutoff=200)
+        assert len(dist) == 60 and sum(dist) > 0
+        for w in range(60):
+            region, i = ("upstream", w) if w < 20 else ("gene", w - 20) if w < 40 else ("downstream", w - 40)
+            want = header + "\n".join(lines[si] for si, ww in assign if ww == w)
+            assert open(os.path.join(out, region, str(i * 5), fn)).read() == want, (fn, w)
+    assert sorted(os.listdir(os.path.join(out, "gene")), key=int) == [str(5 * i) for i in range(20)]
+    # set-up of the sub-command: every directory gets the edgelist and the nodelist, '/'-led tab-separated lines re-pathed
+    nl = os.path.join(tmp_path, "nodes.tsv")
+    open(nl, "w").write("filename\tnode\tgen\tmeth\n/abs/dir/G0.txt\t0_0\t0\tY\n./rel/G1_2.txt\t1_2\t1\tY\nx\t1_0\t1\tN\n")
+    el = os.path.join(tmp_path, "edges.tsv")
+    open(el, "w").write("from\tto\n0_0\t1_0\n1_0\t1_2\n")
+    out2 = os.path.join(tmp_path, "out2")
+    os.makedirs(out2)
+    subprocess.run([exe, "-m", os.path.join(GOLDEN, "methylome"), "-g", ann, "-w", "10", "-s", "50", "-o", out2, "--write-windows",
+                    "--device", "99", "alphabeta", "--nodes", nl, "--edges", el], capture_output=True, text=True, timeout=300)
+    d = os.path.join(out2, "downstream", "50")
+    assert open(os.path.join(d, "edgelist.txt")).read() == open(el).read()
+    assert open(os.path.join(d, "nodelist.txt")).read() == (
+        f"filename\tnode\tgen\tmeth\n{d}/G0.txt\t0_0\t0\tY\n./rel/G1_2.txt\t1_2\t1\tY\nx\t1_0\t1\tN\n\n")
