@@ -575,14 +575,15 @@ __device__ __forceinline__ void fit_starts_body_v2(const DevicePools &P, const W
                                                    const NMParams &nm, abfit_fit *__restrict__ all_out,
                                                    unsigned long long *__restrict__ evals_per_prob)
 {
-    extern __shared__ double smem[];
-    const int lane = threadIdx.x;  // one warp per block
-    LaneSimplex S;
-    S.X = smem + lane;
-    S.C = S.X + 20 * 32;
+    extern __shared__ double smem_block[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_pairs = P.probs[items[0].prob].n_pairs;  // one program for the whole batch (host: jit_eligible)
     const int npad = (n_pairs + 1) & ~1;
     const int slot_doubles = v2_fit_slot_doubles(n_pairs);
+    double *smem = smem_block + (size_t)warp * (25 * 32 + V2_SLOTS * slot_doubles);  // this warp's own region
+    LaneSimplex S;
+    S.X = smem + lane;
+    S.C = S.X + 20 * 32;
     double *slots = smem + 25 * 32;
     auto stage = [&](int slot, int prob) {
         const DevProblem pb = P.probs[prob];
@@ -603,7 +604,9 @@ __device__ __forceinline__ void fit_starts_body_v2(const DevicePools &P, const W
     int my_slot = 0, my_prob = 0;
     V2Queue q;
     for (;;) {
-        __syncwarp();
+        // warps of a block stay in phase (shared instruction-cache lines); a warp that has left the loop has exited
+        if (V2_WARPS > 1) __syncthreads();
+        else __syncwarp();
         unsigned idle = __ballot_sync(FULL, L.phase == PH_IDLE);
         while (idle) {
             if (q.next >= q.end) {
@@ -655,17 +658,18 @@ __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, co
                                                         unsigned long long *__restrict__ evals_per_prob,
                                                         int *__restrict__ err_flag)
 {
-    extern __shared__ double smem[];
-    const int lane = threadIdx.x;  // one warp per block
-    LaneSimplex S;
-    S.X = smem + lane;
-    S.C = S.X + 20 * 32;
+    extern __shared__ double smem_block[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_pairs = P.probs[items[0].prob].n_pairs;
     const int npad = (n_pairs + 1) & ~1;
     const int slot_doubles = v2_boot_slot_doubles(n_pairs);
+    double *smem = smem_block + (size_t)warp * (25 * 32 + V2_BOOT_SLOTS * slot_doubles);  // this warp's own region
+    LaneSimplex S;
+    S.X = smem + lane;
+    S.C = S.X + 20 * 32;
     double *slots = smem + 25 * 32;
     const int ng4 = (n_pairs + 3) >> 2;
-    uint2 *tile = idx_scratch + (size_t)blockIdx.x * (size_t)scratch_stride + lane;
+    uint2 *tile = idx_scratch + ((size_t)blockIdx.x * V2_WARPS + warp) * (size_t)scratch_stride + lane;
     // slot: [resid npad][pred npad][p_uu0, p_mm0, eqp, penw][best theta 4]
     auto stage = [&](int slot, int prob) {
         const DevProblem pb = P.probs[prob];
@@ -691,7 +695,9 @@ __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, co
     int my_slot = 0, my_prob = 0;
     V2Queue q;
     for (;;) {
-        __syncwarp();
+        // warps of a block stay in phase (shared instruction-cache lines); a warp that has left the loop has exited
+        if (V2_WARPS > 1) __syncthreads();
+        else __syncwarp();
         unsigned idle = __ballot_sync(FULL, L.phase == PH_IDLE);
         while (idle) {
             if (q.next >= q.end) {
@@ -704,7 +710,7 @@ __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, co
                 const DevProblem pb = P.probs[q.prob];
                 const double *sl = slots + q.cur * slot_doubles;
                 // this replicate's resample indices -> byte offsets of its residuals in shared memory
-                const uint32_t base = (uint32_t)((const char *)sl - (const char *)smem);
+                const uint32_t base = (uint32_t)((const char *)sl - (const char *)smem_block);
                 const int32_t *ib = resample_idx + (size_t)pb.pair_off * n_boot + (size_t)id * pb.n_pairs;
                 for (int g = 0; g < ng4; ++g) {
                     uint32_t v[4];
@@ -738,7 +744,7 @@ __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, co
         if (active) {
             const double *sl = slots + my_slot * slot_doubles;
             const WarpCtx c = v2_ctx(nullptr, sl + 2 * npad, n_pairs);
-            const DGather Dat{tile, sl + npad, reinterpret_cast<const char *>(smem)};
+            const DGather Dat{tile, sl + npad, reinterpret_cast<const char *>(smem_block)};
             const double f = OBJ::eval(c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
             abfit_fit res;
             if (nm_advance(L, S, nm, f, res, amask)) {

@@ -19,5 +19,12 @@ ABFIT_HD_INLINE int v2_fit_slot_doubles(int n_pairs) { return ((n_pairs + 1) & ~
 // window's replicates; measured: four slots with the predictions read through L1 instead were 5 % slower — the
 // kernel is bound by the load/store unit, and 12 resident warps need the slots to stay within 12 KB)
 constexpr int V2_BOOT_SLOTS = 2;
+// warps per block of the continuous-scheduling kernels.  The warps of a block are independent (own queue state, own
+// slots); a block-wide barrier at the top of every evaluation only keeps them in PHASE, so that they walk through the
+// (tens of KB of straight-line) objective code together and share its instruction-cache lines.
+#ifndef ABFIT_V2_WARPS
+#define ABFIT_V2_WARPS 1
+#endif
+constexpr int V2_WARPS = ABFIT_V2_WARPS;
 ABFIT_HD_INLINE int v2_boot_slot_doubles(int n_pairs) { return 2 * ((n_pairs + 1) & ~1) + 8; }
 }  // namespace abfit

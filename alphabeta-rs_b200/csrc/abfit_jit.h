@@ -22,6 +22,7 @@ struct JitModule {
     cudaKernel_t fit_starts = nullptr;
     cudaKernel_t fit_boot_gather = nullptr;
     int slots = 4;  // window slots per warp (sched 2)
+    int warps = 1;  // warps per block (sched 2): independent warps kept in phase by a block barrier per evaluation
     int sched = 2;  // 1: block-per-item bodies, 2: continuous lane scheduling (persistent one-warp blocks)
     double compile_seconds = 0.0;
     bool from_disk_cache = false;
