@@ -200,8 +200,9 @@ def run_reference_arm(args):
 
     o.build()
     threads = o.hw_threads()
-    # bounded sample: ~ 8 fits per thread and step (literal reference work is ~1.3 s per fit and core)
-    ns = max(8, 8 * threads)
+    # bounded sample: ~ 4 fits per thread and step (literal reference work is ~1.3 s per fit and core, plus the serial
+    # sort_by tail), so that 25 steps and the one full window below end within a few minutes
+    ns = max(8, 4 * threads)
     nb = max(2, ns // 10)
     vals = []
     for i in range(args.warmup + args.steps):
