@@ -256,7 +256,7 @@ void abfit_ctx_destroy(abfit_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->scratch) abfit_batch_destroy(ctx->scratch);
-    if (ctx->div_arena.p) cudaFree(ctx->div_arena.p);
+    div_arena_release(ctx->div_arena);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     for (int k = 0; k < abfit_ctx::MAX_PIPES; ++k) {

@@ -32,14 +32,16 @@ struct SuperBlock {
 // pass 1 ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_pack(const uint8_t *__restrict__ status, const double *__restrict__ post, const double *__restrict__ meth,
-       int64_t L, int64_t total_words, const SuperBlock *__restrict__ sbs, int n_sb, double thr,
-       unsigned long long *__restrict__ V, unsigned long long *__restrict__ T1,
+       int64_t L, int64_t total_words, const SuperBlock *__restrict__ sbs, int n_sb, int sb_first, int sb_end,
+       double thr, unsigned long long *__restrict__ V, unsigned long long *__restrict__ T1,
        unsigned long long *__restrict__ T2, double *__restrict__ methpart, long long *__restrict__ nvpart)
 {
+    // super-blocks [sb_first, sb_end) of the n_sb of this call: the site axis is packed in chunks so that the pair
+    // pass of one chunk runs while the next chunk is being packed (run_divergence)
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int warp = sb_first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int s = blockIdx.y;
-    if (warp >= n_sb) return;
+    if (warp >= sb_end) return;
     const SuperBlock sb = sbs[warp];
     const uint8_t *st = status + (size_t)s * L;
     const double *po = post + (size_t)s * L;
@@ -115,7 +117,9 @@ struct PairItem {
 constexpr int PAIR_ITEM_WORDS = 256;
 constexpr int PAIR_THREADS_MAX = 640;
 
-__global__ void __launch_bounds__(PAIR_THREADS_MAX)
+// 80 registers (instead of the 96 a 640-thread launch bound allows): 51 K of the SM's 64 K registers, so that one
+// 256-thread block of k_pack (52 registers) fits beside a block of this kernel and the two passes overlap
+__global__ void __maxnreg__(80)
 k_pairs(const unsigned long long *__restrict__ V, const unsigned long long *__restrict__ T1,
         const unsigned long long *__restrict__ T2, int64_t total_words, int S, int P,
         const PairItem *__restrict__ items, const ushort2 *__restrict__ tiletab, int n_tiles, int Sp, int sw,
@@ -286,6 +290,17 @@ __global__ void k_p0uu(const double *__restrict__ methsum, const long long *__re
     p0uu[w] = acc / (double)S;
 }
 
+void div_arena_release(DivArena &a)
+{
+    if (a.p) cudaFree(a.p);
+    if (a.st2) cudaStreamDestroy(a.st2);
+    if (a.ev_start) cudaEventDestroy(a.ev_start);
+    if (a.ev_pack_end) cudaEventDestroy(a.ev_pack_end);
+    for (auto &e : a.ev_pack)
+        if (e) cudaEventDestroy(e);
+    a = DivArena();
+}
+
 // -------------------------------------------------------------------------------------
 int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_post, const double *d_meth, int S,
                    int64_t L, const int64_t *h_seg, int W, double thr, double *d_D, unsigned long long *d_diff,
@@ -384,7 +399,7 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
     DivArena local_arena;
     DivArena *ar = arena ? arena : &local_arena;
     auto cleanup = [&]() {
-        if (!arena && local_arena.p) cudaFree(local_arena.p);
+        if (!arena) div_arena_release(local_arena);
     };
 #define DV_CUDA(call)                                   \
     do {                                                \
@@ -444,27 +459,93 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
         DV_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)W * P * 8, st));
     }
 
+    // ---- pass 1 and pass 2, overlapped ---------------------------------------------------------------------------
+    // k_pack is bound by HBM, k_pairs by the POPC pipe: run back to back they leave each other's resource idle (2.9 +
+    // 2.5 ms on the C5 shape).  A long site axis is therefore cut into chunks (whole pair items / whole super-blocks):
+    // chunk c's pair pass runs on the main stream while chunk c+1 is packed on a second stream, the two kernels sharing
+    // every SM (k_pairs: 640 threads x 80 registers, k_pack: 128-thread blocks in the register space that is left).
+    int n_chunks = 1;
+    if (P > 0 && !items.empty() && n_sb > 0 && TW >= 8192) n_chunks = (int)std::min<int64_t>(DivArena::MAX_CHUNKS, TW / 4096);
+    if (const char *e = getenv("ABFIT_DEV_DIV_CHUNKS")) n_chunks = std::max(1, std::min(DivArena::MAX_CHUNKS, atoi(e)));
+    n_chunks = (int)std::min<size_t>((size_t)std::max(n_chunks, 1), std::max<size_t>(items.size(), 1));
+    if (P == 0 || items.empty() || n_sb == 0) n_chunks = 1;
+    cudaStream_t st2 = st;
+    cudaEvent_t ev_start = nullptr, ev_pack[DivArena::MAX_CHUNKS] = {};
+    if (n_chunks > 1) {
+        if (!ar->st2) {
+            DV_CUDA(cudaStreamCreateWithFlags(&ar->st2, cudaStreamNonBlocking));
+            DV_CUDA(cudaEventCreateWithFlags(&ar->ev_start, cudaEventDisableTiming));
+            for (auto &e : ar->ev_pack) DV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            DV_CUDA(cudaEventCreate(&ar->ev_pack_end));
+        }
+        st2 = ar->st2;
+        ev_start = ar->ev_start;
+        for (int c = 0; c < n_chunks; ++c) ev_pack[c] = ar->ev_pack[c];
+    }
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     if (ms) {
         for (auto &e : ev) DV_CUDA(cudaEventCreate(&e));
         DV_CUDA(cudaEventRecord(ev[0], st));
     }
-    if (n_sb > 0) {
-        dim3 grid((n_sb + 7) / 8, S);
-        k_pack<<<grid, 256, 0, st>>>(d_status, d_post, d_meth, L, TW, d_sbs, n_sb, thr, d_V, d_T1, d_T2,
-                                     d_methpart, d_nvpart);
-        DV_CUDA(cudaGetLastError());
-        ++*launches;
-    }
-    if (ms) DV_CUDA(cudaEventRecord(ev[1], st));
-    if (P > 0 && !items.empty()) {
-        const size_t smem = (size_t)sw * Sp * 24;
-        if (smem > 48 * 1024)
-            DV_CUDA(cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_pairs<<<(unsigned)items.size(), pair_threads, smem, st>>>(d_V, d_T1, d_T2, TW, S, P, d_items, d_pairtab,
-                                                                   n_tiles, Sp, sw, d_diff, d_cnt);
-        DV_CUDA(cudaGetLastError());
-        ++*launches;
+    const size_t pair_smem = (size_t)sw * Sp * 24;
+    if (P > 0 && !items.empty() && pair_smem > 48 * 1024)
+        DV_CUDA(cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem));
+    if (n_chunks == 1) {
+        if (n_sb > 0) {
+            dim3 grid((n_sb + 7) / 8, S);
+            k_pack<<<grid, 256, 0, st>>>(d_status, d_post, d_meth, L, TW, d_sbs, n_sb, 0, n_sb, thr, d_V, d_T1, d_T2,
+                                         d_methpart, d_nvpart);
+            DV_CUDA(cudaGetLastError());
+            ++*launches;
+        }
+        if (ms) DV_CUDA(cudaEventRecord(ev[1], st));
+        if (P > 0 && !items.empty()) {
+            k_pairs<<<(unsigned)items.size(), pair_threads, pair_smem, st>>>(d_V, d_T1, d_T2, TW, S, P, d_items, d_pairtab,
+                                                                            n_tiles, Sp, sw, d_diff, d_cnt);
+            DV_CUDA(cudaGetLastError());
+            ++*launches;
+        }
+    } else {
+        // chunk c = items [i0, i1) and every super-block that starts before the chunk's last word
+        DV_CUDA(cudaEventRecord(ev_start, st));
+        DV_CUDA(cudaStreamWaitEvent(st2, ev_start, 0));
+        std::vector<int> item_end(n_chunks), sb_end(n_chunks);
+        for (int c = 0; c < n_chunks; ++c) {
+            // whole waves of one pair block per SM where the item count allows
+            int64_t e = (int64_t)items.size() * (c + 1) / n_chunks;
+            if (c + 1 < n_chunks && e > n_sm) e = (e / n_sm) * n_sm;
+            item_end[c] = (int)e;
+        }
+        item_end[n_chunks - 1] = (int)items.size();
+        for (int c = 0, q = 0; c < n_chunks; ++c) {
+            const int64_t last_word = c + 1 < n_chunks ? items[(size_t)item_end[c]].first_word : TW;
+            while (q < n_sb && sbs[(size_t)q].first_word < last_word) ++q;
+            sb_end[c] = c + 1 < n_chunks ? q : n_sb;
+        }
+        const int pack_threads = 128;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int s0 = c ? sb_end[c - 1] : 0, s1 = sb_end[c];
+            if (s1 > s0) {
+                dim3 grid((s1 - s0 + pack_threads / 32 - 1) / (pack_threads / 32), S);
+                k_pack<<<grid, pack_threads, 0, st2>>>(d_status, d_post, d_meth, L, TW, d_sbs, n_sb, s0, s1, thr, d_V, d_T1, d_T2,
+                                                        d_methpart, d_nvpart);
+                DV_CUDA(cudaGetLastError());
+                ++*launches;
+            }
+            DV_CUDA(cudaEventRecord(ev_pack[c], st2));
+        }
+        if (ms) DV_CUDA(cudaEventRecord(ar->ev_pack_end, st2));
+        for (int c = 0; c < n_chunks; ++c) {
+            const int i0 = c ? item_end[c - 1] : 0, i1 = item_end[c];
+            DV_CUDA(cudaStreamWaitEvent(st, ev_pack[c], 0));
+            if (i1 > i0) {
+                k_pairs<<<(unsigned)(i1 - i0), pair_threads, pair_smem, st>>>(d_V, d_T1, d_T2, TW, S, P, d_items + i0, d_pairtab,
+                                                                            n_tiles, Sp, sw, d_diff, d_cnt);
+                DV_CUDA(cudaGetLastError());
+                ++*launches;
+            }
+        }
+        if (ms) DV_CUDA(cudaEventRecord(ev[1], st));  // end of the pair pass (the packing ended earlier, on st2)
     }
     if (P > 0) {
         const int64_t n = (int64_t)W * P;
@@ -486,9 +567,19 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
     }
     if (ms) DV_CUDA(cudaEventRecord(ev[2], st));
     DV_CUDA(cudaStreamSynchronize(st));
-    if (ms) {  // ms[0] = k_pack (the HBM-bound pass), ms[1] = all-pairs popcount + finalisation
-        cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
-        cudaEventElapsedTime(&ms[1], ev[1], ev[2]);
+    if (ms) {
+        // one chunk: ms[0] = k_pack (the HBM-bound pass), ms[1] = all-pairs popcount + finalisation.
+        // overlapped: ms[0] = until the last chunk was packed, ms[1] = the rest (pair pass of the last chunks +
+        // finalisation); ms[0] + ms[1] is the duration of the call's kernels either way
+        if (n_chunks > 1) {
+            float total = 0.f;
+            cudaEventElapsedTime(&ms[0], ev[0], ar->ev_pack_end);
+            cudaEventElapsedTime(&total, ev[0], ev[2]);
+            ms[1] = total - ms[0];
+        } else {
+            cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
+            cudaEventElapsedTime(&ms[1], ev[1], ev[2]);
+        }
         for (auto &e : ev) cudaEventDestroy(e);
     }
     cleanup();

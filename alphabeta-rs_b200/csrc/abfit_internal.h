@@ -79,7 +79,13 @@ int max_dynamic_smem(int device);
 struct DivArena {
     void *p = nullptr;
     size_t cap = 0;
+    // second stream + events of the overlapped pack / pair passes (created at first use)
+    static constexpr int MAX_CHUNKS = 16;
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_pack_end = nullptr;
+    cudaEvent_t ev_pack[MAX_CHUNKS] = {};
 };
+void div_arena_release(DivArena &a);
 // h_seg is a HOST array [W+1]; every other pointer is device memory. d_p0uu [W] may be null.
 int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_post, const double *d_meth, int S,
                    int64_t L, const int64_t *h_seg, int W, double thr, double *d_D, unsigned long long *d_diff,

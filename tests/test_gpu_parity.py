@@ -962,3 +962,29 @@ def test_multi_device_divergence(ab, ctx, ctx_pool, oracle):
     assert np.array_equal(whole["nvalid"], whole1["nvalid"])
     p0 = oracle.p0uu(post, meth, 0.99)[0]
     assert abs(whole["p0uu"][0] - p0) <= 1e-12 * abs(p0)
+
+
+@pytest.mark.parametrize("chunks", ["2", "5", "16"])
+def test_dmatrix_overlapped_chunks(ab, ctx, oracle, monkeypatch, chunks):
+    """the pack pass and the pair pass overlapped chunk by chunk on two streams (run_divergence): same integers, same D,
+    same per-sample sums as the back-to-back passes and as the oracle — whole methylomes and windowed"""
+    rng = np.random.default_rng(300 + int(chunks))
+    S, L = 23, 330_007
+    status, post, meth = synth_methylomes(rng, S, L)
+    monkeypatch.setenv("ABFIT_DEV_DIV_CHUNKS", "1")
+    ref = ctx.dmatrix(status, post, meth, 0.99)
+    seg = np.array([0, 5, 64_000, 64_001, 200_000, 200_000, 330_000, 330_007], dtype=np.int64)
+    ref_w = ctx.dmatrix(status, post, meth, 0.99, seg)
+    monkeypatch.setenv("ABFIT_DEV_DIV_CHUNKS", chunks)
+    for rep in range(3):
+        got = ctx.dmatrix(status, post, meth, 0.99)
+        got_w = ctx.dmatrix(status, post, meth, 0.99, seg)
+        for k in ("diff", "cnt", "nvalid"):
+            assert np.array_equal(ref[k], got[k]) and np.array_equal(ref_w[k], got_w[k]), (k, rep)
+        for k in ("D", "p0uu", "methsum"):
+            assert np.array_equal(ref[k], got[k], equal_nan=True) and np.array_equal(ref_w[k], got_w[k], equal_nan=True), (k, rep)
+    D, diff, cnt = oracle.dmatrix(status, post, 0.99)
+    assert np.array_equal(got["diff"][0], diff) and np.array_equal(got["cnt"][0], cnt) and np.array_equal(got["D"][0], D)
+    monkeypatch.delenv("ABFIT_DEV_DIV_CHUNKS")
+    big = ctx.dmatrix(np.tile(status, (1, 2)), np.tile(post, (1, 2)), np.tile(meth, (1, 2)), 0.99)  # default: chunked (> 8192 words)
+    assert np.array_equal(big["diff"][0], 2 * diff) and np.array_equal(big["cnt"][0], 2 * cnt)
