@@ -30,18 +30,25 @@ struct SuperBlock {
 };
 
 // pass 1 ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// 56 registers: two 128-thread blocks fit in the 14 K registers a k_pairs block leaves free on an SM
+__global__ void __maxnreg__(56)
 k_pack(const uint8_t *__restrict__ status, const double *__restrict__ post, const double *__restrict__ meth,
-       int64_t L, int64_t total_words, const SuperBlock *__restrict__ sbs, int n_sb, int sb_first, int sb_end,
+       int64_t L, int64_t total_words, const SuperBlock *__restrict__ sbs, int n_sb, int sb_first, int sb_end, int S,
        double thr, unsigned long long *__restrict__ V, unsigned long long *__restrict__ T1,
        unsigned long long *__restrict__ T2, double *__restrict__ methpart, long long *__restrict__ nvpart)
 {
-    // super-blocks [sb_first, sb_end) of the n_sb of this call: the site axis is packed in chunks so that the pair
-    // pass of one chunk runs while the next chunk is being packed (run_divergence)
+    // Work unit = one super-block of one sample; units of this launch: super-blocks [sb_first, sb_end) x S samples,
+    // unit u = sample u / n_sbc, super-block sb_first + u % n_sbc (consecutive warps read consecutive memory).  A
+    // launch either has a warp per unit, or — the overlapped mode of run_divergence, where the pair pass of one chunk
+    // of sites runs while the next chunk is being packed — a fixed number of blocks per SM that loop over the units,
+    // so that the packing never takes more of an SM than the registers the pair kernel leaves free.
     const int lane = threadIdx.x & 31;
-    const int warp = sb_first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int s = blockIdx.y;
-    if (warp >= sb_end) return;
+    const int n_sbc = sb_end - sb_first;
+    const long long n_units = (long long)n_sbc * S;
+    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long u = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < n_units; u += n_warps) {
+    const int s = (int)(u / n_sbc);
+    const int warp = sb_first + (int)(u - (long long)s * n_sbc);
     const SuperBlock sb = sbs[warp];
     const uint8_t *st = status + (size_t)s * L;
     const double *po = post + (size_t)s * L;
@@ -96,6 +103,7 @@ k_pack(const uint8_t *__restrict__ status, const double *__restrict__ post, cons
         methpart[(size_t)s * n_sb + warp] = acc;
         nvpart[(size_t)s * n_sb + warp] = nv;
     }
+    }  // units
 }
 
 // pass 2 ------------------------------------------------------------------------------
@@ -465,7 +473,9 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
     // chunk c's pair pass runs on the main stream while chunk c+1 is packed on a second stream, the two kernels sharing
     // every SM (k_pairs: 640 threads x 80 registers, k_pack: 128-thread blocks in the register space that is left).
     int n_chunks = 1;
-    if (P > 0 && !items.empty() && n_sb > 0 && TW >= 8192) n_chunks = (int)std::min<int64_t>(DivArena::MAX_CHUNKS, TW / 4096);
+    // (only whole methylomes of millions of sites: measured on 625 000 sites and on 10 000 windows of 1000 sites the
+    // plain sequence is faster)
+    if (P > 0 && !items.empty() && n_sb > 0 && W == 1 && TW >= 32768) n_chunks = 8;
     if (const char *e = getenv("ABFIT_DEV_DIV_CHUNKS")) n_chunks = std::max(1, std::min(DivArena::MAX_CHUNKS, atoi(e)));
     n_chunks = (int)std::min<size_t>((size_t)std::max(n_chunks, 1), std::max<size_t>(items.size(), 1));
     if (P == 0 || items.empty() || n_sb == 0) n_chunks = 1;
@@ -492,9 +502,9 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
         DV_CUDA(cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem));
     if (n_chunks == 1) {
         if (n_sb > 0) {
-            dim3 grid((n_sb + 7) / 8, S);
-            k_pack<<<grid, 256, 0, st>>>(d_status, d_post, d_meth, L, TW, d_sbs, n_sb, 0, n_sb, thr, d_V, d_T1, d_T2,
-                                         d_methpart, d_nvpart);
+            const long long units = (long long)n_sb * S;
+            k_pack<<<(unsigned)((units + 7) / 8), 256, 0, st>>>(d_status, d_post, d_meth, L, TW, d_sbs, n_sb, 0, n_sb, S, thr,
+                                                                d_V, d_T1, d_T2, d_methpart, d_nvpart);
             DV_CUDA(cudaGetLastError());
             ++*launches;
         }
@@ -522,12 +532,16 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
             while (q < n_sb && sbs[(size_t)q].first_word < last_word) ++q;
             sb_end[c] = c + 1 < n_chunks ? q : n_sb;
         }
+        // two 128-thread blocks per SM (2 x 4 warps x 56 registers = the 14 K registers a k_pairs block leaves free)
         const int pack_threads = 128;
+        int pack_blocks = 2 * n_sm;
+        if (const char *e = getenv("ABFIT_DEV_DIV_PACK_BLOCKS")) pack_blocks = std::max(1, atoi(e)) * n_sm;
         for (int c = 0; c < n_chunks; ++c) {
             const int s0 = c ? sb_end[c - 1] : 0, s1 = sb_end[c];
             if (s1 > s0) {
-                dim3 grid((s1 - s0 + pack_threads / 32 - 1) / (pack_threads / 32), S);
-                k_pack<<<grid, pack_threads, 0, st2>>>(d_status, d_post, d_meth, L, TW, d_sbs, n_sb, s0, s1, thr, d_V, d_T1, d_T2,
+                const long long units = (long long)(s1 - s0) * S;
+                const unsigned grid = (unsigned)std::min<long long>(pack_blocks, (units + pack_threads / 32 - 1) / (pack_threads / 32));
+                k_pack<<<grid, pack_threads, 0, st2>>>(d_status, d_post, d_meth, L, TW, d_sbs, n_sb, s0, s1, S, thr, d_V, d_T1, d_T2,
                                                         d_methpart, d_nvpart);
                 DV_CUDA(cudaGetLastError());
                 ++*launches;
