@@ -475,7 +475,7 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
     int n_chunks = 1;
     // (only whole methylomes of millions of sites: measured on 625 000 sites and on 10 000 windows of 1000 sites the
     // plain sequence is faster)
-    if (P > 0 && !items.empty() && n_sb > 0 && W == 1 && TW >= 32768) n_chunks = 8;
+    if (P > 0 && !items.empty() && n_sb > 0 && W == 1 && TW >= 32768) n_chunks = 4;
     if (const char *e = getenv("ABFIT_DEV_DIV_CHUNKS")) n_chunks = std::max(1, std::min(DivArena::MAX_CHUNKS, atoi(e)));
     n_chunks = (int)std::min<size_t>((size_t)std::max(n_chunks, 1), std::max<size_t>(items.size(), 1));
     if (P == 0 || items.empty() || n_sb == 0) n_chunks = 1;
@@ -532,10 +532,13 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
             while (q < n_sb && sbs[(size_t)q].first_word < last_word) ++q;
             sb_end[c] = c + 1 < n_chunks ? q : n_sb;
         }
-        // two 128-thread blocks per SM (2 x 4 warps x 56 registers = the 14 K registers a k_pairs block leaves free)
+        // 128-thread blocks (4 warps x 56 registers) slip into the registers a k_pairs block leaves free.  Measured on
+        // the C5 shape: a warp per unit 5.02 ms for both passes (4 chunks; 5.40 back to back); a FIXED number of looping
+        // blocks per SM, which would guarantee the pair kernel its room, starves the packing instead — it needs
+        // ~64 resident warps per SM to stream at HBM speed (2 / 4 blocks per SM: 8.4 / 4.7 ms for the packing alone).
         const int pack_threads = 128;
-        int pack_blocks = 2 * n_sm;
-        if (const char *e = getenv("ABFIT_DEV_DIV_PACK_BLOCKS")) pack_blocks = std::max(1, atoi(e)) * n_sm;
+        long long pack_blocks = 1ll << 40;
+        if (const char *e = getenv("ABFIT_DEV_DIV_PACK_BLOCKS")) pack_blocks = (long long)std::max(1, atoi(e)) * n_sm;
         for (int c = 0; c < n_chunks; ++c) {
             const int s0 = c ? sb_end[c - 1] : 0, s1 = sb_end[c];
             if (s1 > s0) {
