@@ -475,7 +475,7 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
     int n_chunks = 1;
     // (only whole methylomes of millions of sites: measured on 625 000 sites and on 10 000 windows of 1000 sites the
     // plain sequence is faster)
-    if (P > 0 && !items.empty() && n_sb > 0 && W == 1 && TW >= 32768) n_chunks = 4;
+    if (P > 0 && !items.empty() && n_sb > 0 && W == 1 && TW >= 65536) n_chunks = 4;
     if (const char *e = getenv("ABFIT_DEV_DIV_CHUNKS")) n_chunks = std::max(1, std::min(DivArena::MAX_CHUNKS, atoi(e)));
     n_chunks = (int)std::min<size_t>((size_t)std::max(n_chunks, 1), std::max<size_t>(items.size(), 1));
     if (P == 0 || items.empty() || n_sb == 0) n_chunks = 1;
