@@ -988,3 +988,34 @@ def test_dmatrix_overlapped_chunks(ab, ctx, oracle, monkeypatch, chunks):
     monkeypatch.delenv("ABFIT_DEV_DIV_CHUNKS")
     big = ctx.dmatrix(np.tile(status, (1, 2)), np.tile(post, (1, 2)), np.tile(meth, (1, 2)), 0.99)  # default: chunked (> 8192 words)
     assert np.array_equal(big["diff"][0], 2 * diff) and np.array_equal(big["cnt"][0], 2 * cnt)
+
+
+@pytest.mark.parametrize("S,L,seg", [(23, 330_007, None), (2, 70_001, None), (5, 65_537, None), (200, 140_000, None),
+                                     (37, 400_000, [3, 399_990]), (4, 1_000_003, [65, 1_000_003]), (9, 66_000, [1, 66_000])])
+def test_dmatrix_fused_kernel(ab, ctx, oracle, monkeypatch, S, L, seg):
+    """k_fused (bulk-copy packer warps + all-pairs popcount warps in one persistent kernel, whole methylomes): integers
+    and D exact against the oracle and against the two-kernel path, per-sample sums within 1e-12 (its own fixed
+    blocking), run-to-run identical; odd L (rows that are not 16-byte aligned), windows that start and end inside the
+    rows, partial last words and groups, more packer warps than samples"""
+    rng = np.random.default_rng(7000 + S + L)
+    status, post, meth = synth_methylomes(rng, S, L)
+    a, b = (0, L) if seg is None else seg
+    import torch
+    d_st, d_po, d_me = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (status, post, meth))
+    run = lambda: ctx.dmatrix_device(d_st.data_ptr(), d_po.data_ptr(), d_me.data_ptr(), S, L, 0.99, seg_offsets=seg)
+    monkeypatch.setenv("ABFIT_DEV_DIV_FUSED", "0")
+    ref = run()
+    assert ref["launches"] > 4
+    monkeypatch.setenv("ABFIT_DEV_DIV_FUSED", "1")
+    got = [run() for _ in range(3)]
+    D, diff, cnt = oracle.dmatrix(status[:, a:b], post[:, a:b], 0.99)
+    p0, rc, nv = oracle.p0uu(post[:, a:b], meth[:, a:b], 0.99)
+    for g in got:
+        assert g["launches"] <= 4, "the fused path did not run"
+        assert np.array_equal(g["diff"][0], diff) and np.array_equal(g["cnt"][0], cnt) and np.array_equal(g["D"][0], D)
+        assert np.array_equal(g["diff"], ref["diff"]) and np.array_equal(g["cnt"], ref["cnt"])
+        assert np.array_equal(g["nvalid"][0], nv) and np.array_equal(g["nvalid"], ref["nvalid"])
+        assert abs(g["p0uu"][0] - p0) <= 1e-12 * abs(p0)
+        assert np.allclose(g["methsum"], ref["methsum"], rtol=1e-12, atol=0)
+        for k in ("methsum", "p0uu"):
+            assert np.array_equal(g[k], got[0][k]), k
