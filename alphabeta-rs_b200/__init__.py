@@ -132,6 +132,8 @@ def _load() -> C.CDLL:
         "abfit_format_analysis": (C.c_int, [vp, C.c_char_p, i32]),
         "abfit_write_npy_f64": (C.c_int, [C.c_char_p, vp, i32, vp]),
         "abfit_write_metaprofile_results": (C.c_int, [C.c_char_p, C.c_char_p, i32, vp, vp, vp, vp, vp]),
+        "abfit_plot_metaplot": (C.c_int, [C.c_char_p, i32, vp, vp, vp, vp, vp, vp]),
+        "abfit_plot_bootstrap": (C.c_int, [C.c_char_p, vp, vp, i32]),
         "abfit_window_counts": (C.c_int, [vp, vp]),
         "abfit_place_sites": (C.c_int, [vp, i32, vp, i64, vp, vp, vp, i64, vp, vp]),
     }
@@ -154,7 +156,7 @@ EXPORTED_SYMBOLS = (
     "abfit_batch_timing abfit_batch_flops_per_eval abfit_batch_fp64_instr_per_eval abfit_batch_uses_specialised_kernels abfit_jit_dump abfit_jit_last_error abfit_analyze abfit_window_counts abfit_place_sites "
     "abfit_parse_methylome_line abfit_parse_annotation_line abfit_pedigree_graph abfit_pedigree_build abfit_pedigree_info abfit_pedigree_rows abfit_pedigree_warnings "
     "abfit_pedigree_free abfit_format_f64 abfit_steady_state abfit_write_pedigree abfit_write_analysis abfit_format_analysis "
-    "abfit_write_npy_f64 abfit_write_metaprofile_results"
+    "abfit_write_npy_f64 abfit_write_metaprofile_results abfit_plot_metaplot abfit_plot_bootstrap"
 ).split()
 
 
@@ -767,6 +769,21 @@ def write_metaprofile_results(path: str, run_name: str, cg_count, region, best, 
     obs = _f64(obs_steady_state)
     _check(_lib.abfit_write_metaprofile_results(os.fsencode(path), run_name.encode(), len(cg), _ptr(cg), _ptr(rg), _ptr(best),
                                                 _ptr(an), _ptr(obs)))
+
+
+def plot_metaplot(path: str, alpha, beta, ci_alpha=None, ci_beta=None) -> None:
+    """metaplot.png (src/plot.rs:6-82): alpha / beta per window, ci_* = (lo[n], hi[n]) 95 % bands"""
+    a, b = _f64(alpha), _f64(beta)
+    cal, cah = (None, None) if ci_alpha is None else (_f64(ci_alpha[0], a.shape), _f64(ci_alpha[1], a.shape))
+    cbl, cbh = (None, None) if ci_beta is None else (_f64(ci_beta[0], a.shape), _f64(ci_beta[1], a.shape))
+    _check(_lib.abfit_plot_metaplot(os.fsencode(path), len(a), _ptr(a), _ptr(b), _ptr(cal), _ptr(cah), _ptr(cbl), _ptr(cbh)))
+
+
+def plot_bootstrap(path: str, alphas, betas) -> None:
+    """bootstrap.png (src/plot.rs:84-137): box plots of the bootstrap alphas and betas"""
+    a = _f64(alphas)
+    b = _f64(betas, a.shape)
+    _check(_lib.abfit_plot_bootstrap(os.fsencode(path), _ptr(a), _ptr(b), len(a)))
 
 
 # ---------------------------------------------------------------------------------------------

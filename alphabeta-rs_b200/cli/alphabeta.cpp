@@ -4,8 +4,10 @@
 //   alphabeta -n nodelist.txt -e edgelist.txt [-i 1000] [-p 0.99] [-o .] [--seed N] [--device 0 | --devices 0-7]
 //
 // Differences that are deliberate: the random starts / resamples come from a seed (default 0xAB0B200,
-// `--seed` is an extra flag; the reference uses an unseeded thread_rng), there are no progress bars and
-// no bootstrap.png, and a window on which the reference panics reports an error instead.
+// `--seed` is an extra flag; the reference uses an unseeded thread_rng), the two progress bars advance per stage
+// of the batched call instead of per start (cli/progress.h), bootstrap.png is drawn by the library's own rasteriser
+// (same content as src/plot.rs:84-137, not the same pixels), and a window on which the reference panics reports an
+// error instead.
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
@@ -15,6 +17,7 @@
 #include <vector>
 
 #include "../../include/abfit.h"
+#include "progress.h"
 
 static bool exists(const std::string &p)
 {
@@ -114,12 +117,16 @@ int main(int argc, char **argv)
     abfit_problem prob{rows, n_pairs, p0uu, p0uu, 1.0};  // eqp = p0uu, eqp_weight = 1 (src/alphabeta.rs:33-37)
     abfit_fit best;
     int32_t status = 0;
+    progress::Bar pb_neutral("ABNeutral", (unsigned long long)n, false), pb_boot("BootModel", (unsigned long long)n, false);  // src/progress.rs:5-23
+    pb_neutral.tick();
     const int rc = abfit_alphabeta_batch(ctx, &prob, 1, n, simplices.data(), n, idx.data(), seed, 0, 10000, 1000, DBL_EPSILON, 0,
                                          &best, pred.data(), resid.data(), &status, rows_out.data(), analysis.data());
     if (rc || status) {
         std::printf("Error: Model failed: %s\n", rc ? abfit_last_error() : "NaN in the pedigree or in every fit (the reference panics here)");
         return 1;
     }
+    pb_neutral.finish();
+    pb_boot.finish();
     char text[8192];
     abfit_format_analysis(analysis.data(), text, sizeof text);
     std::printf("##########\nResults:\n\n");
@@ -137,6 +144,17 @@ int main(int argc, char **argv)
         abfit_write_npy_f64(rp.c_str(), rows_out.data(), 2, shape)) {
         std::printf("Error: %s\n", abfit_last_error());
         return 1;
+    }
+    {  // plot::bootstrap(results.column(0), results.column(1), output_dir)  (src/boot_model.rs:105-109)
+        std::vector<double> alphas(n), betas(n);
+        for (int i = 0; i < n; ++i) {
+            alphas[i] = rows_out[(size_t)i * 7];
+            betas[i] = rows_out[(size_t)i * 7 + 1];
+        }
+        if (abfit_plot_bootstrap((output + "/bootstrap.png").c_str(), alphas.data(), betas.data(), n)) {
+            std::printf("Error: %s\n", abfit_last_error());
+            return 1;
+        }
     }
     abfit_pedigree_free(ped);
     abfit_ctx_destroy(ctx);

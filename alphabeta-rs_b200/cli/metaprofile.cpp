@@ -9,11 +9,13 @@
 //               [alphabeta --nodes <nodelist> --edges <edgelist>]
 //
 // Files written (formats of the reference): distribution_<file>, distributions.txt, steady_state_methylation.txt,
-// all_steady_state_methylation.txt and, with the sub-command, results.txt and raw.npy (iterations x 7 x windows).
+// all_steady_state_methylation.txt and, with the sub-command, results.txt, raw.npy (iterations x 7 x windows) and
+// metaplot.png (src/plot.rs:6-82: same series, colours and ranges, own rasteriser); a progress bar on stderr when it
+// is a terminal (cli/progress.h).
 // --write-windows additionally writes the reference's per-window directory tree ({region}/{window * step}/{file},
 // nodelist.txt / edgelist.txt per directory; src/setup.rs:5-74, src/windows.rs:259-285) — the fused pipeline does not
-// read it.  Deliberate differences: no metaplot.png; methylome files are
-// processed in name order (the reference uses the directory's own order); every window is fitted on ITS OWN sites
+// read it; with the sub-command every window directory also gets its bootstrap.png (src/boot_model.rs:105-109).
+// Deliberate differences: methylome files are processed in name order (the reference uses the directory's own order); every window is fitted on ITS OWN sites
 // (the reference only does that when the nodelist holds absolute, tab-separated paths: src/setup.rs:48-58), the
 // measured nodes being matched to the methylome files by file name; the windows looped over are those of
 // Windows::new (the reference's loop `(0..max).step_by(step)` can run one directory past them); seeded RNG.
@@ -34,6 +36,7 @@
 #include <vector>
 
 #include "../../include/abfit.h"
+#include "progress.h"
 
 static std::string f64s(double v)
 {
@@ -472,12 +475,17 @@ int main(int argc, char **argv)
     }
     // start simplices, resample indices and vary vertices of a window are all keyed by (seed, window id): its result
     // does not depend on which other windows are fitted with it, nor on how the windows are sharded over the GPUs
+    // progress::multi(total_steps) (src/cli/metaprofile.rs:46): one step per window; the windows are fitted in one batched
+    // call, so the bar stands at the windows prepared so far while the GPUs work and jumps to the end afterwards
+    progress::Bar pb("Progress ", (unsigned long long)n_total, true);
+    pb.set((unsigned long long)(n_total - F));
     if (F > 0 && abfit_alphabeta_batch_multi(ctxs.data(), (int32_t)ctxs.size(), probs.data(), F, n, simplices.data(), n, idx.data(), seed,
                                              0, ids.data(), 10000, 1000, DBL_EPSILON, 0, best.data(), nullptr, nullptr,
                                              status.data(), rows.data(), analysis.data())) {
         std::printf("Error: %s\n", abfit_last_error());
         return 1;
     }
+    pb.finish();
     std::vector<int32_t> cg, region;
     std::vector<abfit_fit> rbest;
     std::vector<double> ranalysis, robs, raw;
@@ -517,6 +525,36 @@ int main(int argc, char **argv)
     if (abfit_write_npy_f64((output + "/raw.npy").c_str(), raw.data(), 3, shape)) {
         std::printf("Error: %s\n", abfit_last_error());
         return 1;
+    }
+    if (write_windows) {  // boot_model::run draws bootstrap.png into every window's own directory (src/boot_model.rs:105-109)
+        const char *side_name[3] = {"upstream", "gene", "downstream"};
+        std::vector<double> al(n), be(n);
+        for (int q = 0; q < R; ++q) {
+            const int f = keep[q], w = usable[fitted[f]];
+            const int side = w < nwin[0] ? 0 : w < nwin[0] + nwin[1] ? 1 : 2;
+            const int i = w - (side == 0 ? 0 : side == 1 ? nwin[0] : nwin[0] + nwin[1]);
+            for (int it = 0; it < n; ++it) {
+                al[it] = rows[((size_t)f * n + it) * 7];
+                be[it] = rows[((size_t)f * n + it) * 7 + 1];
+            }
+            const std::string png = output + "/" + side_name[side] + "/" + std::to_string((uint64_t)i * window_step) + "/bootstrap.png";
+            if (abfit_plot_bootstrap(png.c_str(), al.data(), be.data(), n)) std::printf("Error: %s\n", abfit_last_error());
+        }
+    }
+    {  // plot::metaplot(&analyses, &args) (src/cli/metaprofile.rs:113): alpha, beta and their 95 % intervals per fitted window
+        std::vector<double> al(R), be(R), al_lo(R), al_hi(R), be_lo(R), be_hi(R);
+        for (int q = 0; q < R; ++q) {
+            al[q] = rbest[q].theta[0];
+            be[q] = rbest[q].theta[1];
+            al_lo[q] = ranalysis[(size_t)q * 32 + 16];
+            al_hi[q] = ranalysis[(size_t)q * 32 + 17];
+            be_lo[q] = ranalysis[(size_t)q * 32 + 18];
+            be_hi[q] = ranalysis[(size_t)q * 32 + 19];
+        }
+        if (abfit_plot_metaplot((output + "/metaplot.png").c_str(), R, al.data(), be.data(), al_lo.data(), al_hi.data(), be_lo.data(), be_hi.data())) {
+            std::printf("Error: %s\n", abfit_last_error());
+            return 1;
+        }
     }
     for (abfit_ctx *c : ctxs) abfit_ctx_destroy(c);
     return 0;

@@ -371,10 +371,10 @@ k_fused(const FusedArgs a)
 
     if (tid >= a.n_cons) {
         // ------------------------------------------------------------------ packer warp
-        // units of this warp: for every group of the CTA, the samples pw, pw + PACK_WARPS, ...; unit u lives in ring
-        // slot u % RING.  Two cursors walk the same sequence: the copy cursor runs RING units ahead of the work cursor.
+        // The units (group, sample) of the CTA, numbered group-major, are dealt to the packer warps round robin: this
+        // warp's k-th unit lives in ring slot k % RING.  Two cursors walk the same sequence: the copy cursor runs RING
+        // units ahead of the work cursor.
         const int pw = (tid - a.n_cons) >> 5;
-        const int ns_w = pw < a.S ? (a.S - pw + FUSED_PACK_WARPS - 1) / FUSED_PACK_WARPS : 0;
         unsigned char *ring = raw + (size_t)pw * FUSED_RING * FUSED_SLOT;
         uint64_t *rbar = bar_raw + pw * FUSED_RING;
         const unsigned lo_post = (unsigned)(reinterpret_cast<uintptr_t>(a.post) >> 3) & 1u;   // in elements, mod 2
@@ -382,11 +382,15 @@ k_fused(const FusedArgs a)
         const unsigned lo_st = (unsigned)reinterpret_cast<uintptr_t>(a.status) & 15u;
         const int64_t site_first = a.site0 + g0 * (int64_t)(FUSED_GW * 64);
 
-        int c_gl = 0, c_si = 0, c_slot = 0;   // copy cursor
-        int64_t c_site = site_first;
+        int c_gl = 0, c_s = pw, c_slot = 0;   // copy cursor: group, sample, ring slot
+        while (c_s >= a.S) {
+            c_s -= a.S;
+            ++c_gl;
+        }
         // start the copies of the unit under the copy cursor and advance it (all lanes call it; lane 0 issues)
         auto issue = [&]() {
-            const int sm = pw + FUSED_PACK_WARPS * c_si;
+            const int sm = c_s;
+            const int64_t c_site = site_first + (int64_t)c_gl * (FUSED_GW * 64);
             const int nsites = (int)min((int64_t)(FUSED_GW * 64), a.end_site - c_site);
             const int64_t off = (int64_t)sm * a.L + c_site;   // element index of the unit's first site
             unsigned char *slot = ring + c_slot * FUSED_SLOT;
@@ -418,17 +422,16 @@ k_fused(const FusedArgs a)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar);
             }
-            if (++c_si == ns_w) {
-                c_si = 0;
+            c_s += FUSED_PACK_WARPS;
+            while (c_s >= a.S) {
+                c_s -= a.S;
                 ++c_gl;
-                c_site += FUSED_GW * 64;
             }
             if (++c_slot == FUSED_RING) c_slot = 0;
         };
-        if (ns_w > 0)
-            for (int q = 0; q < FUSED_RING && c_gl < n_gl; ++q) issue();
+        for (int q = 0; q < FUSED_RING && c_gl < n_gl; ++q) issue();
 
-        int w_slot = 0;
+        int w_slot = 0, w_s = pw;   // work cursor: ring slot, sample (the group is the loop variable)
         unsigned w_par = 0;
         int64_t site = site_first;
         for (int gl = 0; gl < n_gl; ++gl, site += FUSED_GW * 64) {
@@ -439,8 +442,8 @@ k_fused(const FusedArgs a)
             unsigned short *sV = reinterpret_cast<unsigned short *>(stage0 + (size_t)b * stage_words);
             unsigned short *sA = sV + 4 * FUSED_GW * a.Sp, *sB = sA + 4 * FUSED_GW * a.Sp;   // planes, in 16-bit pieces
             mbar_wait(bar_empty + b, ((gl >> 1) & 1) ^ 1);   // the consumers are done with this stage
-            for (int si = 0; si < ns_w; ++si) {
-                const int sm = pw + FUSED_PACK_WARPS * si;
+            for (; w_s < a.S; w_s += FUSED_PACK_WARPS) {
+                const int sm = w_s;
                 const unsigned char *slot = ring + w_slot * FUSED_SLOT;
                 const int64_t off = (int64_t)sm * a.L + site;
                 const unsigned op = ((lo_post + (unsigned)off) & 1u) * 8u, om = ((lo_meth + (unsigned)off) & 1u) * 8u;
@@ -522,8 +525,9 @@ k_fused(const FusedArgs a)
                     w_par ^= 1u;
                 }
             }
+            w_s -= a.S;
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_full + b);   // this warp's samples of the group are in the stage
+            if (lane == 0) mbar_arrive(bar_full + b);   // this warp's units of the group are in the stage
         }
     } else {
         // ------------------------------------------------------------------ consumer warps
@@ -553,30 +557,36 @@ k_fused(const FusedArgs a)
     }
 }
 
-// per sample: sum of the group partials of k_fused.  Lane l adds its contiguous share of the groups in order, then the
-// fixed shuffle tree: the order depends on the number of groups only.
-__global__ void __launch_bounds__(32 * FIN_WARPS)
+// per sample: sum of the group partials of k_fused.  One block per sample; thread t adds its contiguous share of the
+// groups in order, then a fixed tree over the 256 threads: the order depends on the number of groups only.
+constexpr int FING_THREADS = 256;
+__global__ void __launch_bounds__(FING_THREADS)
 k_finalize_grouped(const double *__restrict__ methpart, const int32_t *__restrict__ nvpart, int64_t n_groups, int S,
                    double *__restrict__ methsum, long long *__restrict__ nvalid)
 {
-    const int lane = threadIdx.x & 31;
-    const int s = blockIdx.x * FIN_WARPS + (threadIdx.x >> 5);
-    if (s >= S) return;
-    const int64_t per = (n_groups + 31) / 32, q0 = min(n_groups, per * lane), q1 = min(n_groups, q0 + per);
+    __shared__ double sacc[FING_THREADS];
+    __shared__ long long snv[FING_THREADS];
+    const int s = blockIdx.x, t = threadIdx.x;
+    const int64_t per = (n_groups + FING_THREADS - 1) / FING_THREADS, q0 = min(n_groups, per * t), q1 = min(n_groups, q0 + per);
     double acc = 0.0;
     long long nv = 0;
     for (int64_t q = q0; q < q1; ++q) {
         acc += methpart[(size_t)s * n_groups + q];
         nv += nvpart[(size_t)s * n_groups + q];
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        acc += __shfl_down_sync(FULL, acc, o);
-        nv += __shfl_down_sync(FULL, nv, o);
+    sacc[t] = acc;
+    snv[t] = nv;
+    __syncthreads();
+    for (int o = FING_THREADS / 2; o > 0; o >>= 1) {
+        if (t < o) {
+            sacc[t] += sacc[t + o];
+            snv[t] += snv[t + o];
+        }
+        __syncthreads();
     }
-    if (lane == 0) {
-        methsum[s] = acc;
-        nvalid[s] = nv;
+    if (t == 0) {
+        methsum[s] = sacc[0];
+        nvalid[s] = snv[0];
     }
 }
 
@@ -750,7 +760,7 @@ static int run_fused(cudaStream_t st, const uint8_t *d_status, const double *d_p
     if (ms) ABFIT_CUDA(cudaEventRecord(ev[1], st));
     k_finalize_pairs<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(d_diff, d_cnt, P, d_D);
     ABFIT_CUDA(cudaGetLastError());
-    k_finalize_grouped<<<(S + FIN_WARPS - 1) / FIN_WARPS, 32 * FIN_WARPS, 0, st>>>(a.methpart, a.nvpart, NG, S, d_methsum, d_nvalid);
+    k_finalize_grouped<<<S, FING_THREADS, 0, st>>>(a.methpart, a.nvpart, NG, S, d_methsum, d_nvalid);
     ABFIT_CUDA(cudaGetLastError());
     *launches += 2;
     if (d_p0uu) {
@@ -825,7 +835,7 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
         const int nb_f = (S + 3) / 4, n_tiles_f = nb_f * (nb_f + 1) / 2;
         const bool can = W == 1 && P > 0 && h_seg[1] - h_seg[0] > EXACT_MAX && n_tiles_f <= 2 * PAIR_THREADS_MAX &&
                          fused_smem(S, pack_warps, ring) <= (size_t)smem_optin;
-        bool fused = can && TW >= 32768;
+        bool fused = can;
         if (const char *e = getenv("ABFIT_DEV_DIV_FUSED")) fused = atoi(e) != 0 && can;
         if (fused) {
             DivArena local;

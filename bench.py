@@ -393,7 +393,10 @@ def large_case_c5(ab, multi, ctx, torch, dist, rank, world, local, L, n_starts, 
           "p0uu": p0uu, "best": {"alpha": float(best["theta"][0]), "beta": float(best["theta"][1]),
                                  "lse": float(best["lse"]), "start_id": int(best["start_id"]), "rank": int(win)}}
     kern_ms = float(pk_ms + pr_ms)
-    droof = {"bound": "hbm", "kernels": "k_pack + k_pairs (+ finalisation)", "algorithmic_bytes": alg_bytes,
+    fused = out["launches"] <= 4  # k_fused + the three finalisation kernels (the two-pass path has >= 5 launches)
+    droof = {"bound": "hbm", "kernels": "k_fused (bulk-copy packer warps + all-pairs popcount warps in one persistent "
+             "kernel) + finalisation" if fused else "k_pack + k_pairs (+ finalisation)", "fused": bool(fused),
+             "algorithmic_bytes": alg_bytes,
              "bytes_formula": "17 S L + 24 P (SURVEY.md §8d): posteriorMax f64 + rc.meth.lvl f64 + status u8 read once, "
                               "D / diff / cnt written once", "S": S, "L": L, "P": P, "n_gpus": world,
              "pack_kernel_ms": float(pk_ms), "pair_kernel_ms": float(pr_ms),
@@ -401,8 +404,10 @@ def large_case_c5(ab, multi, ctx, torch, dist, rank, world, local, L, n_starts, 
              "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / peak if kern_ms > 0 else None,
              "pack_frac": 17.0 * S * L / (pk_ms * 1e-3) / 1e9 / peak if pk_ms > 0 else None,
              "peak_source": hbm_src + (f" x {world} GPUs" if world > 1 else ""),
-             "note": "per-rank kernel times (CUDA events inside the library), max over ranks; k_pack is HBM-bound, "
-                     "k_pairs is bound by the POPC pipe (3 x popc64 per pair and 64 sites)"}
+             "note": ("per-rank kernel times (CUDA events inside the library), max over ranks; pack_kernel_ms = k_fused (streams the "
+                      "17 B per sample-site once; the bit-planes stay in shared memory), pair_kernel_ms = finalisation" if fused else
+                      "per-rank kernel times (CUDA events inside the library), max over ranks; k_pack is HBM-bound, "
+                      "k_pairs is bound by the POPC pipe (3 x popc64 per pair and 64 sites)")}
     return c5, droof
 
 

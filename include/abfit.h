@@ -359,6 +359,18 @@ int abfit_write_metaprofile_results(const char *path, const char *run_name, int3
                                     const int32_t *region, const abfit_fit *best, const double *analysis,
                                     const double *obs_steady_state);
 
+/* ---- the reference's pictures (host; src/plot.rs) ------------------------------------
+ * 1280 x 960 PNG files with the reference's series, colours, axis ranges and captions (not its pixels: own
+ * rasteriser and bitmap font, see csrc/abfit_plot.cu).
+ * metaplot.png of `metaprofile ... alphabeta` (src/plot.rs:6-82, called at src/cli/metaprofile.rs:113): alpha (red)
+ * and beta (blue) per window, x = 0..300, y = 0..0.01, 95 % bands from ci_*_lo / ci_*_hi (any of the four may be NULL) */
+int abfit_plot_metaplot(const char *path, int32_t n_windows, const double *alpha, const double *beta,
+                        const double *ci_alpha_lo, const double *ci_alpha_hi, const double *ci_beta_lo,
+                        const double *ci_beta_hi);
+/* bootstrap.png of every alphabeta run (src/plot.rs:84-137, called at src/boot_model.rs:105-109): box plots of the
+ * n bootstrap alphas and betas (columns 0 and 1 of the bootstrap rows), y = 0 .. 1.3 max */
+int abfit_plot_bootstrap(const char *path, const double *alphas, const double *betas, int32_t n);
+
 #ifdef __cplusplus
 }
 #endif

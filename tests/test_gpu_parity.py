@@ -971,6 +971,7 @@ def test_dmatrix_overlapped_chunks(ab, ctx, oracle, monkeypatch, chunks):
     rng = np.random.default_rng(300 + int(chunks))
     S, L = 23, 330_007
     status, post, meth = synth_methylomes(rng, S, L)
+    monkeypatch.setenv("ABFIT_DEV_DIV_FUSED", "0")  # the two-kernel path (whole methylomes of <= 200 samples take k_fused by default)
     monkeypatch.setenv("ABFIT_DEV_DIV_CHUNKS", "1")
     ref = ctx.dmatrix(status, post, meth, 0.99)
     seg = np.array([0, 5, 64_000, 64_001, 200_000, 200_000, 330_000, 330_007], dtype=np.int64)

@@ -87,8 +87,15 @@ def test_alphabeta_cli_end_to_end(ab, ctx, oracle, tmp_path):
     exe = os.path.join(ROOT, "alphabeta-rs_b200", "alphabeta")
     n = 200
     r = subprocess.run([exe, "-n", os.path.join(GOLDEN, "nodelist.txt"), "-e", os.path.join(GOLDEN, "edgelist.txt"), "-i", str(n),
-                        "-o", outdir, "--seed", "12345"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+                        "-o", outdir, "--seed", "12345"], cwd=tmp_path, capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, ABFIT_PROGRESS="1"))
     assert r.returncode == 0, r.stdout + r.stderr
+    # the two bars of progress::specific (src/progress.rs:5-23) on stderr, finished at n / n
+    assert "ABNeutral" in r.stderr and "BootModel" in r.stderr and f"{n:7d}/{n:<7d}" in r.stderr
+    # bootstrap.png (src/boot_model.rs:105-109)
+    from test_plots import decode_png
+    img, _ = decode_png(os.path.join(outdir, "bootstrap.png"))
+    assert img.shape == (960, 1280, 3) and ((img[:, :, 0] == 255) & (img[:, :, 1] == 0)).sum() > 100
     assert open(os.path.join(outdir, "pedigree.txt"), "rb").read() == open(os.path.join(GOLDEN, "pedigree_generated.txt"), "rb").read()
     # the oracle pipeline on the same seeded inputs
     ped, p0uu, _ = oracle.build_pedigree(os.path.join(GOLDEN, "nodelist.txt"), os.path.join(GOLDEN, "edgelist.txt"), 0.99, resolve_golden)
@@ -196,6 +203,10 @@ def test_metaprofile_cli_fused_pipeline(ab, ctx, oracle, tmp_path):
     assert open(os.path.join(out, "results.txt")).read() == want
     raw = np.load(os.path.join(out, "raw.npy"))
     assert raw.shape == (n_it, 7, len(results)) and np.array_equal(raw, np.stack(raws, axis=2))
+    # metaplot.png (src/cli/metaprofile.rs:113): a valid 1280 x 960 picture with both series
+    from test_plots import decode_png
+    img, _ = decode_png(os.path.join(out, "metaplot.png"))
+    assert img.shape == (960, 1280, 3)
     # --devices: windows sharded over several GPUs (all visible ones; on a one-GPU box three contexts on device 0) give
     # the same files byte for byte
     out2 = os.path.join(tmp_path, "out_multi")
