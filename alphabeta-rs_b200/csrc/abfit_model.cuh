@@ -335,7 +335,15 @@ __device__ __forceinline__ void model_divergence(const WarpCtx &c, int lane, dou
 // D access: broadcast (every lane fits the same observed column, staged in shared memory and
 // read four pairs at a time) or a per-lane column (bootstrap replicates: D*[i] at col[i*32],
 // lane already folded into the pointer; coalesced across the warp).
+// (ROLL: a generated objective may roll its pair loop per accessor type, see abfit_jit.cu)
+#ifndef ABFIT_ROLL_FIT
+#define ABFIT_ROLL_FIT 0
+#endif
+#ifndef ABFIT_ROLL_BOOT
+#define ABFIT_ROLL_BOOT 0
+#endif
 struct DBroadcast {
+    static constexpr bool ROLL = ABFIT_ROLL_FIT != 0;
     const double *D;  // 16-byte aligned
     __device__ __forceinline__ void load4(int i, double d[4]) const
     {
@@ -346,6 +354,7 @@ struct DBroadcast {
     __device__ __forceinline__ double operator()(int i) const { return D[i]; }
 };
 struct DLaneColumn {
+    static constexpr bool ROLL = false;
     const double *col;
     __device__ __forceinline__ void load4(int i, double d[4]) const
     {
@@ -360,6 +369,7 @@ struct DLaneColumn {
 // four pairs in one coalesced 8-byte load from an L2-resident tile (a quarter of the bytes of a stored D*
 // column); pred is a shared-memory broadcast and resid a shared-memory gather.
 struct DGather {
+    static constexpr bool ROLL = ABFIT_ROLL_BOOT != 0;
     const uint2 *tile;    // [group][32] (lane folded in): four u16 byte offsets into resid
     const double *pred;   // shared, 16-byte aligned
     const char *resid;    // shared, at the start of dynamic shared memory

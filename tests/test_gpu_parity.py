@@ -738,6 +738,7 @@ def test_resample_index_check_large_pedigree(ab, ctx):
 
 
 @pytest.mark.parametrize("env", [{}, {"ABFIT_DEV_CHUNK": "40"}, {"ABFIT_DEV_CHUNK": "7"}, {"ABFIT_DEV_PIPES": "2"},
+                                 {"ABFIT_DEV_JIT_ROLL": "0"}, {"ABFIT_DEV_JIT_ROLL": "3", "ABFIT_DEV_CHUNK": "40"},
                                  {"ABFIT_DEV_PIPES": "5", "ABFIT_DEV_CHUNK": "40"}, {"ABFIT_DEV_JIT_WARPS": "2"},
                                  {"ABFIT_DEV_JIT_WARPS": "3", "ABFIT_DEV_CHUNK": "7", "ABFIT_DEV_PIPES": "2"},
                                  {"ABFIT_DEV_SCHED": "1", "ABFIT_DEV_NWARPS": "3", "ABFIT_DEV_CHUNK": "150"},
