@@ -1021,3 +1021,26 @@ def test_dmatrix_fused_kernel(ab, ctx, oracle, monkeypatch, S, L, seg):
         assert np.allclose(g["methsum"], ref["methsum"], rtol=1e-12, atol=0)
         for k in ("methsum", "p0uu"):
             assert np.array_equal(g[k], got[0][k]), k
+
+
+def test_dmatrix_fused_kernel_stress(ab, ctx, oracle, monkeypatch):
+    """k_fused again and again on shapes that maximise the hand-offs of its protocol — 1 to 3 groups per CTA (stage
+    barriers reused or not), 8 k + 1 samples (uneven packer warps), every ring-slot parity — each run bit-compared
+    with the first and the first with the oracle (no race detector on this pool: repetition instead)"""
+    import torch
+    rng = np.random.default_rng(99)
+    monkeypatch.setenv("ABFIT_DEV_DIV_FUSED", "1")
+    for S, L in [(9, 148 * 512 + 65_536 + 17), (17, 3 * 148 * 512 + 1), (64, 70_000), (33, 200_003)]:
+        status, post, meth = synth_methylomes(rng, S, L)
+        d_st, d_po, d_me = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (status, post, meth))
+        first = None
+        for rep in range(25):
+            got = ctx.dmatrix_device(d_st.data_ptr(), d_po.data_ptr(), d_me.data_ptr(), S, L, 0.99)
+            assert got["launches"] <= 4
+            if first is None:
+                first = got
+                D, diff, cnt = oracle.dmatrix(status, post, 0.99)
+                assert np.array_equal(got["diff"][0], diff) and np.array_equal(got["cnt"][0], cnt) and np.array_equal(got["D"][0], D)
+            else:
+                for k in ("diff", "cnt", "nvalid", "methsum", "p0uu", "D"):
+                    assert np.array_equal(got[k], first[k], equal_nan=True), (S, L, rep, k)
