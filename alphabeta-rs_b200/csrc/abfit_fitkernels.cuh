@@ -589,7 +589,9 @@ __device__ __forceinline__ void fit_starts_body_v2(const DevicePools &P, const W
         const DevProblem pb = P.probs[prob];
         double *sl = slots + slot * slot_doubles;
         const double *Dg = P.D + pb.d_off;
-        for (int i = lane; i < pb.n_pairs; i += 32) sl[i] = Dg[i];
+        if (DBroadcast::SUFF) OBJ::stage_stats(Dg, sl, lane);  // experiment: per-triple statistics instead of the column
+        else
+            for (int i = lane; i < pb.n_pairs; i += 32) sl[i] = Dg[i];
         if (lane == 0) {
             sl[npad] = pb.p_uu0;
             sl[npad + 1] = pb.p_mm0;

@@ -342,8 +342,12 @@ __device__ __forceinline__ void model_divergence(const WarpCtx &c, int lane, dou
 #ifndef ABFIT_ROLL_BOOT
 #define ABFIT_ROLL_BOOT 0
 #endif
+#ifndef ABFIT_SUFF_FIT
+#define ABFIT_SUFF_FIT 0
+#endif
 struct DBroadcast {
     static constexpr bool ROLL = ABFIT_ROLL_FIT != 0;
+    static constexpr bool SUFF = ABFIT_SUFF_FIT != 0;  // EXPERIMENT: the slot holds per-triple statistics instead of D
     const double *D;  // 16-byte aligned
     __device__ __forceinline__ void load4(int i, double d[4]) const
     {
@@ -355,6 +359,7 @@ struct DBroadcast {
 };
 struct DLaneColumn {
     static constexpr bool ROLL = false;
+    static constexpr bool SUFF = false;
     const double *col;
     __device__ __forceinline__ void load4(int i, double d[4]) const
     {
@@ -370,6 +375,7 @@ struct DLaneColumn {
 // column); pred is a shared-memory broadcast and resid a shared-memory gather.
 struct DGather {
     static constexpr bool ROLL = ABFIT_ROLL_BOOT != 0;
+    static constexpr bool SUFF = false;
     const uint2 *tile;    // [group][32] (lane folded in): four u16 byte offsets into resid
     const double *pred;   // shared, 16-byte aligned
     const char *resid;    // shared, at the start of dynamic shared memory

@@ -265,6 +265,51 @@ def small_case_c2(ab, ctx, n_starts=1000, n_boot=1000):
             "best": {"alpha": float(b["theta"][0]), "beta": float(b["theta"][1]), "lse": float(b["lse"])}}
 
 
+def suffstats_experiment(ab, ctx, probs, sx, n_windows=2000):
+    """EXPERIMENT, never the default and never part of `value`: the multi-start kernel with
+    the objective evaluated from per-triple sufficient statistics (ABFIT_EXPERIMENT_SUFFSTATS=1; O(distinct triples)
+    per evaluation instead of O(pairs); regrouped sum, so NOT bit-identical).  Same windows, same start simplices, both
+    ways; the experiment's best-of-starts is checked at north_star's tolerances against the exact path: exact RSS at
+    its best theta within 1e-9 relative, alpha / beta within 1e-6."""
+    Ws = min(n_windows, len(probs))
+    P, S = probs[:Ws], np.ascontiguousarray(sx[:Ws])
+    NS = S.shape[1]
+    res, ms = {}, {}
+    old = {k: os.environ.get(k) for k in ("ABFIT_EXPERIMENT_SUFFSTATS", "ABFIT_JIT")}
+    try:
+        os.environ["ABFIT_JIT"] = "1"
+        for mode in ("0", "1"):
+            os.environ["ABFIT_EXPERIMENT_SUFFSTATS"] = mode
+            b = ctx.batch(P)
+            b.upload_starts(S)
+            b.run_fit()
+            t = []
+            for _ in range(3):
+                b.run_fit()
+                t.append(b.timing()["fit_ms"])
+            res[mode], ms[mode] = b.download_fit(), float(np.median(t))
+            b.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    be, bs = res["0"].best, res["1"].best
+    _, lse_at = ctx.cost_batch(P, bs["theta"], np.arange(Ws, dtype=np.int32))
+    rel = lambda a, b: np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+    d_rss, d_a, d_b = rel(lse_at, be["lse"]), rel(bs["theta"][:, 0], be["theta"][:, 0]), rel(bs["theta"][:, 1], be["theta"][:, 1])
+    ok = (d_rss <= 1e-9) & (d_a <= 1e-6) & (d_b <= 1e-6)
+    return {"what": "multi-start objective from per-triple sufficient statistics, ABFIT_EXPERIMENT_SUFFSTATS=1: an experiment, "
+                    "never the default, not in `value` (not bit-identical to the reference's sequential sum)",
+            "windows": Ws, "starts": NS, "multi_start_ms_exact": ms["0"], "multi_start_ms_experiment": ms["1"],
+            "multi_start_Mfits_per_s_exact": Ws * NS / ms["0"] / 1e3, "multi_start_Mfits_per_s_experiment": Ws * NS / ms["1"] / 1e3,
+            "speedup": ms["0"] / ms["1"], "windows_within_tolerance": int(ok.sum()),
+            "tolerance": "exact RSS at the experiment's best theta within 1e-9 relative of the exact path's, alpha and beta within 1e-6",
+            "max_rel_diff": {"rss": float(d_rss.max()), "alpha": float(d_a.max()), "beta": float(d_b.max())},
+            "same_winning_start": float(np.mean(be["start_id"] == bs["start_id"]))}
+
+
 def c5_times(lineages=10, generations=20):
     """time structure of the C5 pedigree: `lineages` lines sampled at generations 1..`generations` from one founder"""
     samples = [(l, g) for l in range(lineages) for g in range(1, generations + 1)]
@@ -450,6 +495,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling side measurement")
     ap.add_argument("--no-c5", action="store_true", help="skip other_configs.c5 / divergence_roofline")
+    ap.add_argument("--no-experiments", action="store_true", help="skip the flagged experiments reported beside the contract line")
     ap.add_argument("--c5-sites", type=int, default=5_000_000)
     ap.add_argument("--no-full-window", action="store_true", help="reference arm: skip the one full 1000 + 100 window")
     args = ap.parse_args()
@@ -678,6 +724,13 @@ def main():
                 raise  # a rank that drops out of the collectives would hang the others
             aux["c5"] = {"error": str(e)}
 
+    experiments = {}
+    if rank == 0 and world == 1 and not args.no_experiments:
+        try:
+            experiments["suffstats"] = suffstats_experiment(ab, ctx, probs, sx)
+        except Exception as e:
+            experiments["suffstats"] = {"error": str(e)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "fits/s",
@@ -688,7 +741,7 @@ def main():
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "evals_per_fit": {"starts": evals_fit / (rsteps * W * NS), "boots": evals_boot / (rsteps * W * NB)},
             "pipelined_sub_batches": n_pipes,
-            "weak": weak, "other_configs": aux,
+            "weak": weak, "other_configs": aux, "experiments": experiments,
         }
         print(json.dumps(line))
     ctx.close()

@@ -160,6 +160,12 @@ extern "C" {
     pub fn abfit_write_analysis(path: *const c_char, analysis: *const f64) -> c_int;
     /// `write_npy` (src/cli/alphabeta.rs:34-35, src/cli/metaprofile.rs:110-111)
     pub fn abfit_write_npy_f64(path: *const c_char, data: *const f64, ndim: i32, shape: *const i64) -> c_int;
+    /// `plot::metaplot` (src/plot.rs:6-82): metaplot.png; any of the four interval arrays may be null
+    pub fn abfit_plot_metaplot(path: *const c_char, n_windows: i32, alpha: *const f64, beta: *const f64,
+                               ci_alpha_lo: *const f64, ci_alpha_hi: *const f64, ci_beta_lo: *const f64,
+                               ci_beta_hi: *const f64) -> c_int;
+    /// `plot::bootstrap` (src/plot.rs:84-137): bootstrap.png from the bootstrap alphas and betas
+    pub fn abfit_plot_bootstrap(path: *const c_char, alphas: *const f64, betas: *const f64, n: i32) -> c_int;
 }
 
 /// Message of the last failed call on this thread.

@@ -1044,3 +1044,37 @@ def test_dmatrix_fused_kernel_stress(ab, ctx, oracle, monkeypatch):
             else:
                 for k in ("diff", "cnt", "nvalid", "methsum", "p0uu", "D"):
                     assert np.array_equal(got[k], first[k], equal_nan=True), (S, L, rep, k)
+
+
+def test_suffstats_experiment_within_tolerance(ab, ctx, oracle, ped351, ped78, monkeypatch):
+    """EXPERIMENT (ABFIT_EXPERIMENT_SUFFSTATS=1, never the default): multi-start objective from per-triple sufficient
+    statistics.  Not bit-identical by construction; what is asserted is north_star's tolerance against the exact path
+    (= the oracle, bit for bit): exact RSS at the experiment's best theta within 1e-9 relative, alpha / beta within
+    1e-6 — on the R-original 351-pair pedigree (C1's data), the 78-pair example pedigree and C4-style synthetic
+    windows; and that the flag really switches the objective (costs differ in the last bits somewhere)."""
+    rng = np.random.default_rng(2024)
+    groups = [[(ped351, 0.75)], [ped78], [synth_problem(rng, ped351) for _ in range(24)]]
+    monkeypatch.setenv("ABFIT_JIT", "1")
+    any_diff = False
+    for cases in groups:
+        probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+        n_starts = 1000 if len(cases) == 1 else 300
+        sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+        res = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("ABFIT_EXPERIMENT_SUFFSTATS", mode)
+            b = ctx.batch(probs)
+            b.upload_starts(sx)
+            assert b.uses_specialised_kernels()
+            b.run_fit()
+            res[mode] = b.download_fit(want_all=True)
+            b.close()
+        monkeypatch.delenv("ABFIT_EXPERIMENT_SUFFSTATS")
+        exact, suff = res["0"], res["1"]
+        _, lse_at = ctx.cost_batch(probs, suff.best["theta"], np.arange(len(probs), dtype=np.int32))
+        for i in range(len(probs)):
+            assert abs(lse_at[i] - exact.best["lse"][i]) <= 1e-9 * abs(exact.best["lse"][i]), i
+            for k in (0, 1):
+                assert abs(suff.best["theta"][i, k] - exact.best["theta"][i, k]) <= 1e-6 * abs(exact.best["theta"][i, k]), (i, k)
+        any_diff |= not np.array_equal(exact.all["cost"], suff.all["cost"])
+    assert any_diff
