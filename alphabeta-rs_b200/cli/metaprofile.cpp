@@ -367,9 +367,19 @@ int main(int argc, char **argv)
         return 1;
     }
     int32_t S = 0, n_pairs = 0;
-    std::vector<char> fbuf(1 << 20);
-    std::vector<double> pairs(5 * 65536);
-    if (abfit_pedigree_graph(nodes.c_str(), edges.c_str(), &S, fbuf.data(), (int32_t)fbuf.size(), &n_pairs, pairs.data(), 65536)) {
+    // sizes first (no outputs), then the graph itself: any number of samples and pairs
+    if (abfit_pedigree_graph(nodes.c_str(), edges.c_str(), &S, nullptr, 0, &n_pairs, nullptr, 0)) {
+        std::printf("Error: Error while building pedigree: %s\n", abfit_last_error());
+        return 1;
+    }
+    if (S < 2 || n_pairs < 1) {
+        std::printf("Error: Error while building pedigree: the nodelist has fewer than two measured samples\n");
+        return 1;
+    }
+    std::vector<char> fbuf((size_t)S * 4097 + 1);  // PATH_MAX + '\n' per measured node
+    std::vector<double> pairs((size_t)5 * n_pairs);
+    if (abfit_pedigree_graph(nodes.c_str(), edges.c_str(), &S, fbuf.data(), (int32_t)std::min<size_t>(fbuf.size(), 0x7fffffff), &n_pairs,
+                             pairs.data(), n_pairs)) {
         std::printf("Error: Error while building pedigree: %s\n", abfit_last_error());
         return 1;
     }

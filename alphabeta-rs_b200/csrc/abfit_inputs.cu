@@ -399,11 +399,17 @@ int abfit_pedigree_graph(const char *nodelist_path, const char *edgelist_path, i
     if (files_out) {
         std::string all;
         for (auto &n : g.meas) all += n.file + "\n";
-        if ((int32_t)all.size() + 1 > files_cap) return ABFIT_ERR_ARG;
+        if ((int64_t)all.size() + 1 > (int64_t)files_cap) {
+            abfit::set_error("abfit_pedigree_graph: files_out is too small for the measured nodes' file names");
+            return ABFIT_ERR_ARG;
+        }
         std::memcpy(files_out, all.c_str(), all.size() + 1);
     }
     if (pairs_out) {
-        if ((int32_t)g.pairs.size() > pairs_cap) return ABFIT_ERR_ARG;
+        if ((int64_t)g.pairs.size() > (int64_t)pairs_cap) {
+            abfit::set_error("abfit_pedigree_graph: pairs_out is too small (call with null outputs first for the counts)");
+            return ABFIT_ERR_ARG;
+        }
         for (size_t r = 0; r < g.pairs.size(); ++r) {
             pairs_out[5 * r + 0] = g.pairs[r].i;
             pairs_out[5 * r + 1] = g.pairs[r].j;
