@@ -5,6 +5,7 @@
 // every numerical result comes from the kernels in abfit_kernels.cu / abfit_divergence.cu.
 // There is deliberately no CPU implementation of the objective or the optimiser in this
 // library: without a CUDA device all compute calls fail.
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -59,6 +60,11 @@ struct abfit_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D of the bootstrap inputs while the multi-start kernel runs
     cudaEvent_t copy_done = nullptr;
+    // abfit_alphabeta_batch: the start simplices are uploaded in chunks; behind every chunk a 4-byte copy raises a device
+    // counter the multi-start kernel watches, so that it starts on the first windows while the rest is still on the bus
+    static constexpr int SX_CHUNKS = 64;
+    int *h_sx_counts = nullptr;  // pinned [SX_CHUNKS]
+    int *d_sx_ready = nullptr;
     cudaDeviceProp prop{};
     int smem_optin = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -116,6 +122,8 @@ struct abfit_batch {
     bool boot_items_v2 = false;  // the bootstrap items were built for the continuous-scheduling kernel
     DevBuf<unsigned long long> d_ids;  // per-window generator keys of abfit_alphabeta_batch_multi
     DevBuf<int> d_cursor;  // item cursors of the continuous-scheduling kernels: [0] multi-start, [1] bootstrap
+    DevBuf<double> d_analysis, d_analysis_scratch;  // bootstrap statistics on the device (abfit_alphabeta_batch)
+    const int *sx_ready = nullptr;  // set by abfit_alphabeta_batch for ONE run_fit: the simplices are still being uploaded
     int jit_warps_fit = 0, jit_warps_boot = 0;  // resident warps = grid of a full machine
     // pipelined fit -> select -> bootstrap: sub-batches of windows, each with its own guided item lists and cursors
     struct Pipe {
@@ -266,6 +274,8 @@ void abfit_ctx_destroy(abfit_ctx *ctx)
     if (ctx->pipe_start) cudaEventDestroy(ctx->pipe_start);
     if (ctx->idx_done) cudaEventDestroy(ctx->idx_done);
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->h_sx_counts) cudaFreeHost(ctx->h_sx_counts);
+    if (ctx->d_sx_ready) cudaFree(ctx->d_sx_ready);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -543,7 +553,7 @@ int abfit_batch_run_fit(abfit_batch *b, int32_t max_iters, double sd_tol, uint32
         if (int rc = jit_launch_fit_starts_v2(b->jit, st, b->pools, b->d_items.p, b->n_items,
                                               (int64_t)b->n_probs * b->n_starts, b->jit_warps_fit, b->d_cursor.p,
                                               b->d_simplices.p, b->n_starts, nm, b->d_all.p, b->d_evals_fit.p,
-                                              jit_smem_fit_v2(b->jit, b->hp.probs[0])))
+                                              jit_smem_fit_v2(b->jit, b->hp.probs[0]), b->sx_ready))
             return rc;
     } else if (b->jit) {
         if (int rc = jit_launch_fit_starts(b->jit, st, b->pools, b->d_items.p, b->n_items, b->shape.n_warps,
@@ -804,6 +814,7 @@ static int run_pipelined_impl(abfit_batch *b, int32_t max_iters_fit, int32_t max
         return abfit_batch_run_boot(b, max_iters_boot, sd_tol, flags);
     }
     const NMParams nm_fit = nm_params(max_iters_fit, sd_tol, flags), nm_boot = nm_params(max_iters_boot, sd_tol, flags);
+    if (b->sx_ready) ABFIT_CUDA(cudaStreamWaitEvent(st, ctx->copy_done, 0));  // the sub-batch launches do not watch the upload
     ABFIT_CUDA(cudaMemsetAsync(b->d_all.p, 0xFF, (size_t)b->n_probs * b->n_starts * sizeof(abfit_fit), st));
     ABFIT_CUDA(cudaMemsetAsync(b->d_evals_fit.p, 0, (size_t)b->n_probs * 8, st));
     ABFIT_CUDA(cudaMemsetAsync(b->d_rows.p, 0xFF, (size_t)b->n_probs * b->n_boot * 7 * 8, st));
@@ -1044,19 +1055,58 @@ static int alphabeta_impl(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_
     }
     abfit_batch *b = ctx->scratch;
     cudaStream_t st = ctx->stream;
+    // ABFIT_DEV_VERBOSE: host-side phases of the call (wall clock)
+    const bool verbose = getenv("ABFIT_DEV_VERBOSE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t_prev = now();
+    const auto t_first = t_prev;
+    auto phase = [&](const char *name) {
+        if (!verbose) return;
+        const auto t = now();
+        fprintf(stderr, "[abfit] alphabeta_batch: %-28s %8.2f ms (at %8.2f)\n", name, std::chrono::duration<double, std::milli>(t - t_prev).count(),
+                std::chrono::duration<double, std::milli>(t - t_first).count());
+        t_prev = t;
+    };
     // the start simplices (the bulk of the fit's input) cross PCIe while the host compiles the pedigrees
     const size_t n_sx = (size_t)n_probs * n_starts * 20;
     if (b->d_simplices.n < n_sx || !b->d_simplices.p) {
         ABFIT_CUDA(cudaStreamSynchronize(st));  // the buffer is about to be reallocated
         if (int rc = b->d_simplices.ensure(n_sx)) return rc;
     }
-    ABFIT_CUDA(cudaMemcpyAsync(b->d_simplices.p, simplices, n_sx * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (!ctx->h_sx_counts) {
+        ABFIT_CUDA(cudaHostAlloc(&ctx->h_sx_counts, abfit_ctx::SX_CHUNKS * sizeof(int), cudaHostAllocDefault));
+        ABFIT_CUDA(cudaMalloc(&ctx->d_sx_ready, sizeof(int)));
+    }
+    {
+        const int per = std::max(256, (n_probs + abfit_ctx::SX_CHUNKS - 1) / abfit_ctx::SX_CHUNKS);  // windows per chunk
+        ABFIT_CUDA(cudaMemsetAsync(ctx->d_sx_ready, 0, sizeof(int), ctx->copy_stream));
+        int c = 0;
+        for (int p0 = 0; p0 < n_probs; p0 += per, ++c) {
+            const int p1 = std::min(n_probs, p0 + per);
+            const size_t o = (size_t)p0 * n_starts * 20, cnt = (size_t)(p1 - p0) * n_starts * 20;
+            ABFIT_CUDA(cudaMemcpyAsync(b->d_simplices.p + o, simplices + o, cnt * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+            ctx->h_sx_counts[c] = p1;
+            ABFIT_CUDA(cudaMemcpyAsync(ctx->d_sx_ready, ctx->h_sx_counts + c, sizeof(int), cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
+    }
     ABFIT_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+    phase("enqueue simplices copy");
     if (int rc = workspace(ctx, probs, n_probs, &b)) return rc;
+    phase("compile pedigrees + pools");
     decide_jit(b, (int64_t)n_starts + n_boot);  // one decision for both phases of this batch
+    phase("decide_jit");
     if (int rc = upload_starts_impl(b, n_starts, nullptr)) return rc;  // before any kernel is enqueued: these may synchronise
+    phase("plan multi-start items");
     if (int rc = boot_alloc(b, n_boot)) return rc;
-    ABFIT_CUDA(cudaStreamWaitEvent(st, ctx->copy_done, 0));
+    if (analysis_out) {  // (allocations before any kernel is enqueued: cudaFree synchronises)
+        if (int rc = b->d_analysis.ensure((size_t)n_probs * 32)) return rc;
+        if (int rc = b->d_analysis_scratch.ensure((size_t)n_probs * 8 * std::max(n_boot, 1))) return rc;
+    }
+    phase("plan bootstrap items");
+    // the continuous-scheduling kernel watches the upload's counter; every other kernel family waits for the whole copy
+    const bool watch_upload = b->jit && b->jit->sched == 2 && !b->shape.wide && !getenv("ABFIT_DEV_NO_UPLOAD_WATCH");
+    if (!watch_upload) ABFIT_CUDA(cudaStreamWaitEvent(st, ctx->copy_done, 0));
+    b->sx_ready = watch_upload ? ctx->d_sx_ready : nullptr;
     // the resample indices (the bulk of the bootstrap's input) cross PCIe under the multi-start kernels
     if (!ctx->idx_done) ABFIT_CUDA(cudaEventCreateWithFlags(&ctx->idx_done, cudaEventDisableTiming));
     ABFIT_CUDA(cudaMemcpyAsync(b->d_idx.p, resample_idx, (size_t)b->total_pairs * n_boot * 4, cudaMemcpyHostToDevice,
@@ -1074,8 +1124,12 @@ static int alphabeta_impl(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_
     b->boot_uploaded = true;
     b->boot_done = false;
     if (int rc = run_pipelined_impl(b, max_iters_fit, max_iters_boot, sd_tol, flags, true, vary_seed, first_problem_id, d_ids,
-                                    ctx->idx_done))
+                                    ctx->idx_done)) {
+        b->sx_ready = nullptr;
         return rc;
+    }
+    b->sx_ready = nullptr;
+    phase("enqueue kernels");
     if (best_out)
         ABFIT_CUDA(cudaMemcpyAsync(best_out, b->d_best.p, (size_t)n_probs * sizeof(abfit_fit), cudaMemcpyDeviceToHost, st));
     if (pred_out)
@@ -1084,13 +1138,22 @@ static int alphabeta_impl(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_
         ABFIT_CUDA(cudaMemcpyAsync(resid_out, b->d_resid.p, (size_t)b->total_pairs * 8, cudaMemcpyDeviceToHost, st));
     if (prob_status_out)
         ABFIT_CUDA(cudaMemcpyAsync(prob_status_out, b->d_status.p, (size_t)n_probs * 4, cudaMemcpyDeviceToHost, st));
+    // bootstrap statistics (RawAnalysis::analyze) behind the bootstrap kernel, on the device: the same operations in the
+    // same order as abfit_analyze (tests/test_gpu_parity.py::test_device_statistics_equal_host_statistics)
+    const bool dev_stats = analysis_out && n_boot >= 2 && !getenv("ABFIT_DEV_HOST_STATS");
+    if (dev_stats) {
+        if (int rc = launch_analyze(st, b->d_rows.p, n_probs, n_boot, b->d_analysis.p, b->d_analysis_scratch.p)) return rc;
+        ABFIT_CUDA(cudaMemcpyAsync(analysis_out, b->d_analysis.p, (size_t)n_probs * 32 * 8, cudaMemcpyDeviceToHost, st));
+    }
     if (int rc = abfit_batch_download_boot(b, rows_out, nullptr)) return rc;
-    if (analysis_out) {
+    phase("kernels + downloads");
+    if (analysis_out && !dev_stats) {
         std::vector<int> rcs(n_probs, 0);
         parallel_for(n_probs, [&](int32_t p) {
             rcs[p] = abfit_analyze(rows_out + (size_t)p * n_boot * 7, n_boot, analysis_out + (size_t)p * 32);
         });
     }
+    phase("bootstrap statistics");
     return 0;
 }
 

@@ -573,7 +573,8 @@ template <class OBJ>
 __device__ __forceinline__ void fit_starts_body_v2(const DevicePools &P, const WorkItem *__restrict__ items, int n_items,
                                                    int *cursor, const double *__restrict__ simplices, int n_starts,
                                                    const NMParams &nm, abfit_fit *__restrict__ all_out,
-                                                   unsigned long long *__restrict__ evals_per_prob)
+                                                   unsigned long long *__restrict__ evals_per_prob,
+                                                   const int *__restrict__ sx_ready)
 {
     extern __shared__ double smem_block[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -589,6 +590,19 @@ __device__ __forceinline__ void fit_starts_body_v2(const DevicePools &P, const W
         const DevProblem pb = P.probs[prob];
         double *sl = slots + slot * slot_doubles;
         const double *Dg = P.D + pb.d_off;
+        if (sx_ready) {
+            // abfit_alphabeta_batch starts this kernel while the start simplices are still crossing PCIe: *sx_ready is
+            // the number of windows whose simplices have landed (written by small copies between the chunks of the
+            // upload, in stream order).  Windows are opened in order, the upload is ~50 x faster than the fits.
+            if (lane == 0) {
+                int have;
+                do {
+                    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(have) : "l"(sx_ready) : "memory");
+                    if (have <= prob) __nanosleep(2000);
+                } while (have <= prob);
+            }
+            __syncwarp();
+        }
         if (DBroadcast::SUFF) OBJ::stage_stats(Dg, sl, lane);  // experiment: per-triple statistics instead of the column
         else
             for (int i = lane; i < pb.n_pairs; i += 32) sl[i] = Dg[i];

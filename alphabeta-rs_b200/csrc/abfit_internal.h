@@ -71,6 +71,9 @@ int launch_model_divergence(cudaStream_t st, const DevicePools &P, const double 
 int launch_gen_vary(cudaStream_t st, uint64_t seed, uint64_t first_problem_id, const unsigned long long *ids, int n_probs,
                     int n_boot, const abfit_fit *best, double *out);
 int launch_fp64_peak(cudaStream_t st, int blocks, int threads, int iters, double *sink);
+// RawAnalysis::analyze of every window's bootstrap rows on the device (same bits as the host's abfit_analyze):
+// rows [n_probs][n_boot][7] -> out [n_probs][32]; scratch [n_probs * 8 * n_boot] doubles
+int launch_analyze(cudaStream_t st, const double *rows, int n_probs, int n_boot, double *out, double *scratch);
 int max_dynamic_smem(int device);
 
 // ---- divergence (abfit_divergence.cu) -------------------------------------------------

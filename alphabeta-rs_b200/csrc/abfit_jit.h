@@ -57,7 +57,8 @@ size_t jit_smem_boot_v2(const JitModule *m, const DevProblem &pb);
 int jit_resident_warps(const JitModule *m, bool boot, const DevProblem &pb, int n_sm);  // grid of a full machine
 int jit_launch_fit_starts_v2(const JitModule *m, cudaStream_t st, DevicePools P, const WorkItem *items, int n_items,
                              int64_t n_fits, int grid_max, int *cursor, const double *simplices, int n_starts, NMParams nm,
-                             abfit_fit *all_out, unsigned long long *evals_per_prob, size_t smem_bytes);
+                             abfit_fit *all_out, unsigned long long *evals_per_prob, size_t smem_bytes,
+                             const int *sx_ready = nullptr /* device int: windows whose start simplices have been uploaded */);
 int jit_launch_fit_boot_gather_v2(const JitModule *m, cudaStream_t st, DevicePools P, const WorkItem *items, int n_items,
                                   int64_t n_fits, int grid_max, int *cursor, int n_boot, const abfit_fit *best,
                                   const double *pred, const double *resid, const int32_t *resample_idx, const double *vary,

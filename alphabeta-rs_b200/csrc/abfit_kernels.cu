@@ -394,6 +394,94 @@ __global__ void k_gen_vary(uint64_t seed, uint64_t first_problem_id, const unsig
     out[i] = vary_coordinate(seed, key, (uint64_t)b, v, j, best[p].theta[j]);
 }
 
+// ---------------------------------------------------------------------------------
+// RawAnalysis::analyze (src/analysis.rs:50-98) on the device: one thread per (window, statistic column), the same
+// sequential sums, Welford updates and linear quantiles as the host's abfit_analyze (csrc/abfit_api.cu) — same
+// operations in the same order, same bits.  The column is copied to a scratch segment of its own and heap-sorted there.
+// rows [n_probs][n_boot][7], out [n_probs][32], scratch [n_probs * 8][n_boot]
+// ---------------------------------------------------------------------------------
+__global__ void k_analyze(const double *__restrict__ rows, int n_probs, int n, double *__restrict__ out, double *__restrict__ scratch)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_probs * 8) return;
+    const int p = t >> 3, f = t & 7;
+    const double *r = rows + (size_t)p * n * 7;
+    double *col = scratch + (size_t)t * n;
+    double *o = out + (size_t)p * 32;
+    const int src = f < 2 ? f : f - 1;  // columns alpha, beta, beta / alpha, weight, intercept, pr_mm, pr_um, pr_uu
+    double sum = 0.0;
+    if (f == 2) {
+        for (int i = 0; i < n; ++i) col[i] = r[7 * (size_t)i + 1] / r[7 * (size_t)i];
+        double q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int i = 0;
+        for (; n - i >= 8; i += 8)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) q[k] += col[i + k];
+        sum += q[0] + q[4];
+        sum += q[1] + q[5];
+        sum += q[2] + q[6];
+        sum += q[3] + q[7];
+        for (; i < n; ++i) sum += col[i];
+    } else {
+        for (int i = 0; i < n; ++i) {
+            col[i] = r[7 * (size_t)i + src];
+            sum += col[i];
+        }
+    }
+    o[f] = sum / (double)n;
+    double mean = 0.0, ssq = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double delta = col[i] - mean;
+        mean = mean + delta / (double)(i + 1);
+        ssq = fma(col[i] - mean, delta, ssq);
+    }
+    o[8 + f] = sqrt(ssq / ((double)n - 1.0));
+    // heap sort, ascending (the order of equal values does not matter for the quantiles)
+    for (int start = n / 2 - 1; start >= 0; --start) {
+        int root = start;
+        const double v = col[root];
+        for (;;) {
+            int child = 2 * root + 1;
+            if (child >= n) break;
+            if (child + 1 < n && col[child] < col[child + 1]) ++child;
+            if (!(v < col[child])) break;
+            col[root] = col[child];
+            root = child;
+        }
+        col[root] = v;
+    }
+    for (int end = n - 1; end > 0; --end) {
+        const double v = col[end];
+        col[end] = col[0];
+        int root = 0;
+        for (;;) {
+            int child = 2 * root + 1;
+            if (child >= end) break;
+            if (child + 1 < end && col[child] < col[child + 1]) ++child;
+            if (!(v < col[child])) break;
+            col[root] = col[child];
+            root = child;
+        }
+        col[root] = v;
+    }
+    const double qs[2] = {0.025, 0.975};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const double pos = (double)(n - 1) * qs[k];
+        const double lo = floor(pos), hi = ceil(pos);
+        const double a = col[(size_t)lo], b2 = col[(size_t)hi];
+        o[16 + 2 * f + k] = a + (b2 - a) * (pos - trunc(pos));
+    }
+}
+
+int launch_analyze(cudaStream_t st, const double *rows, int n_probs, int n_boot, double *out, double *scratch)
+{
+    if (n_probs <= 0) return 0;
+    k_analyze<<<(n_probs * 8 + 63) / 64, 64, 0, st>>>(rows, n_probs, n_boot, out, scratch);
+    ABFIT_CUDA(cudaGetLastError());
+    return 0;
+}
+
 __global__ void k_fp64_peak(int iters, double *sink)
 {
     double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-9, a2 = a0 + 2e-9, a3 = a0 + 3e-9;

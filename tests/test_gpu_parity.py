@@ -1078,3 +1078,24 @@ def test_suffstats_experiment_within_tolerance(ab, ctx, oracle, ped351, ped78, m
                 assert abs(suff.best["theta"][i, k] - exact.best["theta"][i, k]) <= 1e-6 * abs(exact.best["theta"][i, k]), (i, k)
         any_diff |= not np.array_equal(exact.all["cost"], suff.all["cost"])
     assert any_diff
+
+
+@pytest.mark.parametrize("n_boot", [2, 7, 8, 100, 1000])
+def test_device_statistics_equal_host_statistics(ab, ctx, ped351, ped78, monkeypatch, n_boot):
+    """abfit_alphabeta_batch computes RawAnalysis::analyze (src/analysis.rs:50-98) on the device behind the bootstrap
+    kernel: bit-identical to the host's abfit_analyze on the rows it returns (means incl. the 8-accumulator fold of
+    beta / alpha, Welford standard deviations, linear quantiles), for replicate counts around the fold width and
+    the quantile positions"""
+    rng = np.random.default_rng(700 + n_boot)
+    cases = [synth_problem(rng, ped351, n_keep=60) for _ in range(5)] + [ped78]
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    n_starts = 40
+    sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    idx = np.concatenate([ab.gen_resample_idx(SEED, i, n_boot, len(p)).ravel() for i, (p, u) in enumerate(cases)])
+    out = ctx.alphabeta_batch(probs, sx, idx, SEED)
+    for i in range(len(probs)):
+        want = ab.analyze(out["rows"][i])
+        assert np.array_equal(out["analysis"][i], want, equal_nan=True), i
+    monkeypatch.setenv("ABFIT_DEV_HOST_STATS", "1")
+    host = ctx.alphabeta_batch(probs, sx, idx, SEED)
+    assert np.array_equal(host["analysis"], out["analysis"], equal_nan=True) and np.array_equal(host["rows"], out["rows"])
