@@ -828,20 +828,34 @@ int run_divergence(cudaStream_t st, const uint8_t *d_status, const double *d_pos
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     }
-    // One window of more than EXACT_MAX sites whose sample tiles fit one CTA (S <= 200): the fused kernel.
+    // Windows of more than EXACT_MAX sites whose sample tiles fit one CTA (S <= 200): the fused kernel.
     {
         int pack_warps = 8, ring = 2;
         if (const char *e = getenv("ABFIT_DEV_DIV_FUSED_SHAPE")) sscanf(e, "%dx%d", &pack_warps, &ring);
         const int nb_f = (S + 3) / 4, n_tiles_f = nb_f * (nb_f + 1) / 2;
-        const bool can = W == 1 && P > 0 && h_seg[1] - h_seg[0] > EXACT_MAX && n_tiles_f <= 2 * PAIR_THREADS_MAX &&
-                         fused_smem(S, pack_warps, ring) <= (size_t)smem_optin;
+        // (a few long windows — chromosomes — run the kernel once each)
+        bool all_long = W >= 1 && W <= 64;
+        for (int w = 0; w < W && all_long; ++w) all_long = h_seg[w + 1] - h_seg[w] > EXACT_MAX;
+        const bool can = all_long && P > 0 && n_tiles_f <= 2 * PAIR_THREADS_MAX && fused_smem(S, pack_warps, ring) <= (size_t)smem_optin;
         bool fused = can;
         if (const char *e = getenv("ABFIT_DEV_DIV_FUSED")) fused = atoi(e) != 0 && can;
         if (fused) {
             DivArena local;
             DivArena *ar = arena ? arena : &local;
-            const int rc = run_fused(st, d_status, d_post, d_meth, S, L, h_seg[0], h_seg[1], thr, d_D, d_diff, d_cnt, d_methsum,
-                                     d_nvalid, d_p0uu, launches, ms, ar, n_sm, pack_warps, ring, fused_smem(S, pack_warps, ring));
+            int rc = 0;
+            if (ms) ms[0] = ms[1] = 0.f;
+            for (int w = 0; w < W && rc == 0; ++w) {
+                int l1 = 0;
+                float m1[2] = {0.f, 0.f};
+                rc = run_fused(st, d_status, d_post, d_meth, S, L, h_seg[w], h_seg[w + 1], thr, d_D + (size_t)w * P, d_diff + (size_t)w * P,
+                               d_cnt + (size_t)w * P, d_methsum + (size_t)w * S, d_nvalid + (size_t)w * S, d_p0uu ? d_p0uu + w : nullptr, &l1,
+                               ms ? m1 : nullptr, ar, n_sm, pack_warps, ring, fused_smem(S, pack_warps, ring));
+                *launches += l1;
+                if (ms) {
+                    ms[0] += m1[0];
+                    ms[1] += m1[1];
+                }
+            }
             if (!arena) div_arena_release(local);
             return rc;
         }

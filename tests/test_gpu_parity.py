@@ -1099,3 +1099,32 @@ def test_device_statistics_equal_host_statistics(ab, ctx, ped351, ped78, monkeyp
     monkeypatch.setenv("ABFIT_DEV_HOST_STATS", "1")
     host = ctx.alphabeta_batch(probs, sx, idx, SEED)
     assert np.array_equal(host["analysis"], out["analysis"], equal_nan=True) and np.array_equal(host["rows"], out["rows"])
+
+
+def test_dmatrix_fused_kernel_several_long_windows(ab, ctx, oracle, monkeypatch):
+    """a few windows of more than 65 536 sites each (chromosomes): k_fused once per window; integers and D exact per
+    window against the oracle and the two-pass path, per-sample sums within 1e-12; one short window in the list sends
+    the whole call to the two-pass path"""
+    import torch
+    rng = np.random.default_rng(31)
+    S, L = 12, 300_000
+    status, post, meth = synth_methylomes(rng, S, L)
+    d_st, d_po, d_me = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (status, post, meth))
+    seg = [0, 70_001, 170_002, 300_000]
+    run = lambda sg: ctx.dmatrix_device(d_st.data_ptr(), d_po.data_ptr(), d_me.data_ptr(), S, L, 0.99, seg_offsets=sg)
+    monkeypatch.setenv("ABFIT_DEV_DIV_FUSED", "0")
+    ref = run(seg)
+    monkeypatch.delenv("ABFIT_DEV_DIV_FUSED")
+    got = run(seg)
+    assert got["launches"] == 12 and ref["launches"] < 12  # 3 x (k_fused + 3 finalisation kernels)
+    for w in range(3):
+        a, b = seg[w], seg[w + 1]
+        D, diff, cnt = oracle.dmatrix(status[:, a:b], post[:, a:b], 0.99)
+        assert np.array_equal(got["diff"][w], diff) and np.array_equal(got["cnt"][w], cnt) and np.array_equal(got["D"][w], D)
+        p0, rc, nv = oracle.p0uu(post[:, a:b], meth[:, a:b], 0.99)
+        assert np.array_equal(got["nvalid"][w], nv) and abs(got["p0uu"][w] - p0) <= 1e-12 * abs(p0)
+    assert np.array_equal(got["diff"], ref["diff"]) and np.allclose(got["methsum"], ref["methsum"], rtol=1e-12, atol=0)
+    mixed = run([0, 70_001, 70_500, 300_000])
+    assert mixed["launches"] < 12
+    D, diff, cnt = oracle.dmatrix(status[:, 70_001:70_500], post[:, 70_001:70_500], 0.99)
+    assert np.array_equal(mixed["diff"][1], diff) and np.array_equal(mixed["cnt"][1], cnt)
