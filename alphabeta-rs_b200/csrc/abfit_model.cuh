@@ -345,6 +345,9 @@ __device__ __forceinline__ void model_divergence(const WarpCtx &c, int lane, dou
 #ifndef ABFIT_SUFF_FIT
 #define ABFIT_SUFF_FIT 0
 #endif
+#ifndef ABFIT_GATHER_PREFETCH
+#define ABFIT_GATHER_PREFETCH 4  // groups of four pairs the bootstrap's index tile is prefetched ahead (L2 -> L1)
+#endif
 struct DBroadcast {
     static constexpr bool ROLL = ABFIT_ROLL_FIT != 0;
     static constexpr bool SUFF = ABFIT_SUFF_FIT != 0;  // EXPERIMENT: the slot holds per-triple statistics instead of D
@@ -384,7 +387,7 @@ struct DGather {
         const uint2 *p = tile + (size_t)(i >> 2) * 32;
 #ifdef __CUDA_ARCH__
         // the tile streams from L2 once per evaluation: pull the line 4 groups ahead into L1
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 4 * 32));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + ABFIT_GATHER_PREFETCH * 32));
 #endif
         const uint2 w = *p;
         const double2 a = *reinterpret_cast<const double2 *>(pred + i);
