@@ -237,10 +237,11 @@ k_pairs(const unsigned long long *__restrict__ V, const unsigned long long *__re
 // k_pack is bound by HBM and k_pairs by the POPC pipe; run one after the other (or on two streams: the pair kernel
 // leaves a 4-warp packing block no room to keep enough bytes in flight) each leaves the other's resource idle.  Here
 // one persistent CTA per SM does both, warp-specialised:
-//   * FUSED_PACK_WARPS packer warps stream the raw inputs with bulk asynchronous copies (cp.async.bulk -> shared
-//     memory, completion on an mbarrier): a unit is one sample x FUSED_GW words (512 sites: 4 KB posteriorMax + 4 KB
-//     rc.meth.lvl + 512 B status), every packer warp keeps FUSED_RING units in flight — the bytes in flight that
-//     HBM needs (~70 KB per SM) live in shared memory instead of in the registers of 64 resident warps;
+//   * 8 packer warps stream the raw inputs with bulk asynchronous copies (cp.async.bulk -> shared memory, completion
+//     on an mbarrier): a unit is one sample x FUSED_GW words (512 sites: 4 KB posteriorMax + 4 KB rc.meth.lvl + 512 B
+//     status), every packer warp owns 2 ring slots and keeps the next unit's copies in flight while it packs — the
+//     bytes in flight that HBM needs (~70 KB per SM) live in shared memory instead of in the registers of 64 resident
+//     warps;
 //   * a packer turns a landed unit into the three bit-plane words per 64 sites (the same thermometer code as k_pack;
 //     bit b of a word is site b) and writes them into one of two bit-plane stages [word][sample] — the planes never
 //     go to HBM;
@@ -251,7 +252,7 @@ k_pairs(const unsigned long long *__restrict__ V, const unsigned long long *__re
 // the grid.  (Not the same rounding as the 64-word super-blocks of k_pack: both are within 1e-12 of the sequential
 // sum; windows up to EXACT_MAX sites never come here.)
 constexpr int FUSED_GW = 8;            // words per group (= bit-plane stage depth)
-// packer warps x raw units in flight per packer warp: template parameters of k_fused (default 4 x 3)
+// packer warps x ring slots per packer warp are template parameters of k_fused (default 8 x 2, measured: run_divergence)
 constexpr int FUSED_FLUSH_GROUPS = 32; // 256 words: cnt <= 16 384, diff <= 32 768 fit the packed counters
 constexpr int FUSED_RAW_F64 = FUSED_GW * 64 * 8 + 16;   // one f64 array of a unit + alignment slack
 constexpr int FUSED_RAW_U8 = FUSED_GW * 64 + 16;
@@ -294,7 +295,7 @@ __device__ __forceinline__ uint4 lds_u32x4(uint32_t addr)
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
-// acc += m where p (one predicated DADD instead of an add and two selects)
+// acc += m where p (asks for one predicated DADD; ptxas may still turn it into an add and two selects)
 __device__ __forceinline__ void dadd_if(double &acc, double m, bool p)
 {
     asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q add.rn.f64 %0, %0, %1;\n\t}" : "+d"(acc) : "d"(m), "r"((unsigned)p));
