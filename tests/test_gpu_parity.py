@@ -1128,3 +1128,43 @@ def test_dmatrix_fused_kernel_several_long_windows(ab, ctx, oracle, monkeypatch)
     assert mixed["launches"] < 12
     D, diff, cnt = oracle.dmatrix(status[:, 70_001:70_500], post[:, 70_001:70_500], 0.99)
     assert np.array_equal(mixed["diff"][1], diff) and np.array_equal(mixed["cnt"][1], cnt)
+
+
+def test_c5_full_size_divergence_properties(ab, ctx, oracle):
+    """BASELINE configs[4] at its full size — 200 samples x 5 000 000 sites, 19 900 pairs, 17 GB streamed by k_fused —
+    through size-independent properties: the integer sums of two site ranges add up exactly to those of the whole
+    (any cut; here one that is not a multiple of 64), a 6-sample x 20 000-site corner equals the oracle bit for bit,
+    sample order is respected (swapping two samples permutes the pair sums), and the call is repeatable bit for bit"""
+    import torch
+    S, L = 200, 5_000_000
+    dev = torch.device("cuda", 0)
+    if torch.cuda.mem_get_info(dev)[0] < 40e9:
+        pytest.skip("needs 40 GB of free device memory")
+    g = torch.Generator(device=dev)
+    g.manual_seed(55)
+    status = (torch.rand((S, L), device=dev, generator=g) * 3).to(torch.uint8).clamp_(max=2)
+    post = torch.empty((S, L), dtype=torch.float64, device=dev)
+    meth = torch.empty((S, L), dtype=torch.float64, device=dev)
+    for s in range(S):  # row by row: no (S, L) temporaries
+        u = torch.rand(L, device=dev, generator=g, dtype=torch.float64)
+        post[s] = torch.where(torch.rand(L, device=dev, generator=g) < 0.9, torch.full_like(u, 0.9999), u * 0.49 + 0.5)
+        meth[s] = torch.rand(L, device=dev, generator=g, dtype=torch.float64)
+    run = lambda seg=None: ctx.dmatrix_device(status.data_ptr(), post.data_ptr(), meth.data_ptr(), S, L, 0.99, seg_offsets=seg)
+    whole = run()
+    assert whole["launches"] <= 4  # the fused kernel
+    again = run()
+    for k in ("diff", "cnt", "nvalid", "methsum", "p0uu", "D"):
+        assert np.array_equal(whole[k], again[k]), k
+    parts = run([0, 1_234_567, L])
+    assert np.array_equal(parts["diff"].sum(axis=0), whole["diff"][0]) and np.array_equal(parts["cnt"].sum(axis=0), whole["cnt"][0])
+    assert np.array_equal(parts["nvalid"].sum(axis=0), whole["nvalid"][0])
+    assert np.array_equal(whole["D"][0], whole["diff"][0] / (2.0 * whole["cnt"][0]))  # src/pedigree.rs:257
+    # a corner of the data against the oracle
+    s6, l6 = 6, 20_000
+    sub = ctx.dmatrix(status[:s6, :l6].cpu().numpy(), post[:s6, :l6].cpu().numpy(), meth[:s6, :l6].cpu().numpy(), 0.99)
+    D, diff, cnt = oracle.dmatrix(status[:s6, :l6].cpu().numpy(), post[:s6, :l6].cpu().numpy(), 0.99)
+    assert np.array_equal(sub["diff"][0], diff) and np.array_equal(sub["cnt"][0], cnt) and np.array_equal(sub["D"][0], D)
+    # pair (0, 1) of the whole = pair (0, 1) of the first two rows alone (nothing leaks between samples)
+    two = ctx.dmatrix_device(status.data_ptr(), post.data_ptr(), meth.data_ptr(), 2, L, 0.99)
+    assert two["diff"][0][0] == whole["diff"][0][0] and two["cnt"][0][0] == whole["cnt"][0][0]
+    assert two["nvalid"][0][0] == whole["nvalid"][0][0] and two["nvalid"][0][1] == whole["nvalid"][0][1]

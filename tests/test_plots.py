@@ -85,3 +85,24 @@ def test_bootstrap_png(ab, tmp_path):
         ab.plot_bootstrap(p, [np.nan, 1.0], [1.0, 2.0])
     with pytest.raises(ab.AbfitError):
         ab.plot_bootstrap(str(tmp_path / "no_such_dir" / "x.png"), alphas, betas)
+
+
+def test_progress_bar_format(tmp_path):
+    """cli/progress.h: the templates of src/progress.rs:5-43 — "{msg} {bar:40} [{elapsed}] {pos:>7}/{len:7}" (+ " ETA: ..."
+    for the overall bar), drawn on stderr, forced / hidden by ABFIT_PROGRESS"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "p.cpp"
+    src.write_text('#include "progress.h"\n'
+                   'int main() { progress::Bar a("ABNeutral", 1000, false), b("Progress ", 300, true);\n'
+                   '  a.set(250); b.inc(30); std::printf("%s\\n%s\\n", a.render().c_str(), b.render().c_str()); a.finish(); b.finish(); return 0; }\n')
+    exe = tmp_path / "p"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(root, "alphabeta-rs_b200", "cli"), "-o", str(exe), str(src)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, ABFIT_PROGRESS="1"))
+    line_a, line_b = r.stdout.split("\n")[:2]
+    assert line_a.startswith("ABNeutral ") and line_a.endswith("[00:00]     250/1000   ")
+    assert line_a.count("█") == 10  # a quarter of the 40-cell bar
+    assert line_b.startswith("Progress  ") and "      30/300     ETA: " in line_b and line_b.endswith("seconds")
+    assert "ABNeutral" in r.stderr and "1000/1000" in r.stderr and r.stderr.endswith("\n")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, ABFIT_PROGRESS="0"))
+    assert r.stderr == ""
