@@ -732,9 +732,17 @@ static int run_fused(cudaStream_t st, const uint8_t *d_status, const double *d_p
     ABFIT_CUDA(cudaMemcpyAsync(base + o_pt, pairtab.data(), pairtab.size() * sizeof(ushort2), cudaMemcpyHostToDevice, st));
     ABFIT_CUDA(cudaMemsetAsync(d_diff, 0, (size_t)P * 8, st));
     ABFIT_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)P * 8, st));
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    struct Events {  // destroyed on every way out
+        cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+        ~Events()
+        {
+            for (auto &x : e)
+                if (x) cudaEventDestroy(x);
+        }
+    } evs;
+    cudaEvent_t *ev = evs.e;
     if (ms) {
-        for (auto &e : ev) ABFIT_CUDA(cudaEventCreate(&e));
+        for (int i = 0; i < 3; ++i) ABFIT_CUDA(cudaEventCreate(&ev[i]));
         ABFIT_CUDA(cudaEventRecord(ev[0], st));
     }
     int grid = (int)std::min<int64_t>(n_sm, NG);
@@ -775,7 +783,6 @@ static int run_fused(cudaStream_t st, const uint8_t *d_status, const double *d_p
         // ms[0] = the fused pack + pair kernel (all of the HBM traffic), ms[1] = finalisation
         cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
         cudaEventElapsedTime(&ms[1], ev[1], ev[2]);
-        for (auto &e : ev) cudaEventDestroy(e);
     }
     return 0;
 }
