@@ -20,7 +20,11 @@
 // measured nodes being matched to the methylome files by file name; the windows looped over are those of
 // Windows::new (the reference's loop `(0..max).step_by(step)` can run one directory past them); seeded RNG.
 // Like the reference, a window that cannot be fitted prints an error and is skipped, and results.txt pairs the
-// i-th fitted window with the i-th distribution entry (src/cli/metaprofile.rs:76-77).
+// i-th fitted window with the i-th distribution entry (src/cli/metaprofile.rs:76-77).  One more deliberate difference:
+// a window in which the samples list DIFFERENT numbers of sites is skipped with an error; the reference keeps it,
+// prints "Lengths do not match, all bets are off" and fits it with D = 0 for every pair of unequal length
+// (src/pedigree.rs:222-230) — `abfit_pedigree_build` (the `alphabeta` tool) reproduces that rule, the fused window
+// pipeline does not: its divergence call needs index-aligned sites, and a fit on zeros that "are off" helps nobody.
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
