@@ -123,6 +123,8 @@ struct abfit_batch {
     DevBuf<unsigned long long> d_ids;  // per-window generator keys of abfit_alphabeta_batch_multi
     DevBuf<int> d_cursor;  // item cursors of the continuous-scheduling kernels: [0] multi-start, [1] bootstrap
     DevBuf<double> d_analysis, d_analysis_scratch;  // bootstrap statistics on the device (abfit_alphabeta_batch)
+    DevBuf<double> d_wide_ss;      // EXPERIMENT (ABFIT_EXPERIMENT_SUFFSTATS): per-triple statistics of the warp-per-fit kernels
+    DevBuf<long long> d_wide_ss_off;
     const int *sx_ready = nullptr;  // set by abfit_alphabeta_batch for ONE run_fit: the simplices are still being uploaded
     int jit_warps_fit = 0, jit_warps_boot = 0;  // resident warps = grid of a full machine
     // pipelined fit -> select -> bootstrap: sub-batches of windows, each with its own guided item lists and cursors
@@ -546,8 +548,31 @@ int abfit_batch_run_fit(abfit_batch *b, int32_t max_iters, double sd_tol, uint32
     BigScratch big;
     if (int rc = big_scratch(b, (size_t)std::max(std::max(b->n_items, 1) * b->shape.n_warps, b->n_probs), big)) return rc;
     if (b->shape.wide) {
+        const long long *ss_off = nullptr;
+        const double *ss_all = nullptr;
+        int max_trip = 0;
+        const char *ess = getenv("ABFIT_EXPERIMENT_SUFFSTATS");
+        if (ess && atoi(ess) != 0) {
+            // EXPERIMENT, never the default: per-triple statistics of every problem, once per launch
+            std::vector<long long> off(b->n_probs);
+            long long total = 0;
+            for (int p = 0; p < b->n_probs; ++p) {
+                off[p] = total;
+                total += 2 * (long long)b->hp.probs[p].n_trip + 1;
+                max_trip = std::max(max_trip, (int)b->hp.probs[p].n_trip);
+            }
+            if (int rc = b->d_wide_ss.ensure((size_t)total)) return rc;
+            if (int rc = b->d_wide_ss_off.ensure((size_t)b->n_probs)) return rc;
+            ABFIT_CUDA(cudaMemcpyAsync(b->d_wide_ss_off.p, off.data(), (size_t)b->n_probs * 8, cudaMemcpyHostToDevice, st));
+            ABFIT_CUDA(cudaStreamSynchronize(st));  // `off` is pageable
+            if (b->shape.smem_wide + (size_t)(2 * max_trip + 2) * 8 <= (size_t)b->ctx->smem_optin) {
+                if (int rc = launch_wide_stats(st, b->pools, b->n_probs, max_trip, b->d_wide_ss_off.p, b->d_wide_ss.p)) return rc;
+                ss_off = b->d_wide_ss_off.p;
+                ss_all = b->d_wide_ss.p;
+            }
+        }
         if (int rc = launch_fit_starts_wide(st, b->pools, b->d_items.p, b->n_items, b->d_simplices.p, b->n_starts, nm,
-                                            b->d_all.p, b->d_evals_fit.p, b->shape.smem_wide))
+                                            b->d_all.p, b->d_evals_fit.p, b->shape.smem_wide, ss_off, ss_all, max_trip))
             return rc;
     } else if (b->jit && b->jit->sched == 2) {
         if (int rc = jit_launch_fit_starts_v2(b->jit, st, b->pools, b->d_items.p, b->n_items,

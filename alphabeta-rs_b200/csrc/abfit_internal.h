@@ -54,7 +54,9 @@ int launch_fit_boot_gather(cudaStream_t st, const DevicePools &P, const WorkItem
 // warp-per-fit variants (abfit_wide.cuh): one warp per block; dstar_scratch holds scratch_stride doubles per block
 int launch_fit_starts_wide(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items,
                            const double *simplices, int n_starts, NMParams nm, abfit_fit *all_out,
-                           unsigned long long *evals_per_prob, size_t smem_bytes);
+                           unsigned long long *evals_per_prob, size_t smem_bytes, const long long *ss_off = nullptr,
+                           const double *ss_all = nullptr, int max_trip = 0);  // ss_*: the sufficient-statistics EXPERIMENT
+int launch_wide_stats(cudaStream_t st, const DevicePools &P, int n_probs, int max_trip, const long long *ss_off, double *out);
 int launch_fit_boot_wide(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items, int n_boot,
                          const abfit_fit *best, const double *pred, const double *resid, const int32_t *resample_idx,
                          const double *vary, double *dstar_scratch, int64_t scratch_stride, NMParams nm,

@@ -253,10 +253,48 @@ struct WideBoot {
     int *err_flag;
 };
 
+// EXPERIMENT (ABFIT_EXPERIMENT_SUFFSTATS=1): per-triple statistics of every problem's observed column, once per batch.
+// One block per problem, one thread per triple walking the pairs in pedigree order; thread 0 adds the centred sums.
+// out (per problem, at ss_off[p]): [mean_u][count_u][Q]
+__global__ void k_wide_stats(DevicePools P, const long long *__restrict__ ss_off, double *__restrict__ out)
+{
+    const DevProblem pb = P.probs[blockIdx.x];
+    const double *D = P.D + pb.d_off;
+    const uint32_t *tid = P.wtid + pb.wtid_off;
+    double *o = out + ss_off[blockIdx.x];
+    extern __shared__ double q_u[];
+    for (int u = threadIdx.x; u < pb.n_trip; u += blockDim.x) {
+        double s1 = 0.0;
+        int n = 0;
+        for (int i = 0; i < pb.n_pairs; ++i)
+            if (tid[i] == (uint32_t)u) {
+                s1 += D[i];
+                ++n;
+            }
+        const double m = s1 / (double)n;
+        double q = 0.0;
+        for (int i = 0; i < pb.n_pairs; ++i)
+            if (tid[i] == (uint32_t)u) {
+                const double e = D[i] - m;
+                q += e * e;
+            }
+        o[u] = m;
+        o[pb.n_trip + u] = (double)n;
+        q_u[u] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double Q = 0.0;
+        for (int u = 0; u < pb.n_trip; ++u) Q += q_u[u];
+        o[2 * pb.n_trip] = Q;
+    }
+}
+
 template <bool BOOT>
 __global__ void __launch_bounds__(32)
 k_fit_wide(DevicePools P, const WorkItem *__restrict__ items, const double *__restrict__ simplices, int n_per_prob,
-           NMParams nm, abfit_fit *__restrict__ fits_out, unsigned long long *__restrict__ evals_per_prob, WideBoot B)
+           NMParams nm, abfit_fit *__restrict__ fits_out, unsigned long long *__restrict__ evals_per_prob, WideBoot B,
+           const long long *__restrict__ ss_off, const double *__restrict__ ss_all)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x;
@@ -279,6 +317,13 @@ k_fit_wide(DevicePools P, const WorkItem *__restrict__ items, const double *__re
     c.p_mm0 = pb.p_mm0;
     c.eqp = pb.eqp;
     c.penw = pb.penw;
+    c.ss = nullptr;
+    if (!BOOT && ss_all) {  // experiment: the statistics of this problem, staged behind the triple table
+        double *ss = reinterpret_cast<double *>(trip + ((pb.n_trip + 1) & ~1));
+        const double *g = ss_all + ss_off[it.prob];
+        for (int i = lane; i < 2 * pb.n_trip + 1; i += 32) ss[i] = g[i];
+        c.ss = ss;
+    }
     __syncwarp();
     double *drow = BOOT ? B.dstar + (size_t)blockIdx.x * (size_t)B.stride : nullptr;
     unsigned long long my_evals = 0;
@@ -615,16 +660,27 @@ int launch_fit_boot_gather(cudaStream_t st, const DevicePools &P, const WorkItem
     return 0;
 }
 
+int launch_wide_stats(cudaStream_t st, const DevicePools &P, int n_probs, int max_trip, const long long *ss_off, double *out)
+{
+    if (n_probs <= 0) return 0;
+    k_wide_stats<<<n_probs, 256, (size_t)std::max(max_trip, 1) * 8, st>>>(P, ss_off, out);
+    ABFIT_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_fit_starts_wide(cudaStream_t st, const DevicePools &P, const WorkItem *items, int n_items,
                            const double *simplices, int n_starts, NMParams nm, abfit_fit *all_out,
-                           unsigned long long *evals_per_prob, size_t smem_bytes)
+                           unsigned long long *evals_per_prob, size_t smem_bytes, const long long *ss_off,
+                           const double *ss_all, int max_trip)
 {
     if (n_items <= 0) return 0;
+    if (ss_all) smem_bytes += (size_t)(2 * max_trip + 2) * 8;  // experiment: [mean][count][Q] behind the triple table
     if (int rc = prep_kernel(k_fit_wide<false>, smem_bytes, false)) return rc;
     if (getenv("ABFIT_DEV_VERBOSE"))
-        fprintf(stderr, "[abfit] k_fit_wide<starts>: %d blocks x 1 warp, %zu B smem/block\n", n_items, smem_bytes);
+        fprintf(stderr, "[abfit] k_fit_wide<starts>: %d blocks x 1 warp, %zu B smem/block%s\n", n_items, smem_bytes,
+                ss_all ? " (EXPERIMENT: sufficient statistics)" : "");
     k_fit_wide<false><<<n_items, 32, smem_bytes, st>>>(P, items, simplices, n_starts, nm, all_out, evals_per_prob,
-                                                       WideBoot{});
+                                                       WideBoot{}, ss_off, ss_all);
     ABFIT_CUDA(cudaGetLastError());
     return 0;
 }
@@ -640,7 +696,7 @@ int launch_fit_boot_wide(cudaStream_t st, const DevicePools &P, const WorkItem *
     if (getenv("ABFIT_DEV_VERBOSE"))
         fprintf(stderr, "[abfit] k_fit_wide<boot>: %d blocks x 1 warp, %zu B smem/block\n", n_items, smem_bytes);
     WideBoot B{best, pred, resid, resample_idx, vary, dstar_scratch, (long long)scratch_stride, rows_out, err_flag};
-    k_fit_wide<true><<<n_items, 32, smem_bytes, st>>>(P, items, nullptr, n_boot, nm, fits_out, evals_per_prob, B);
+    k_fit_wide<true><<<n_items, 32, smem_bytes, st>>>(P, items, nullptr, n_boot, nm, fits_out, evals_per_prob, B, nullptr, nullptr);
     ABFIT_CUDA(cudaGetLastError());
     return 0;
 }

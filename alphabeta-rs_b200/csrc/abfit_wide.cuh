@@ -40,6 +40,10 @@ struct WideCtx {
     double *term;          //   three exchange buffers of WIDE_CH pair terms
     int32_t n_pairs, n_trip, tmax;
     double p_uu0, p_mm0, eqp, penw;
+    // EXPERIMENT (ABFIT_EXPERIMENT_SUFFSTATS=1, never the default): per-triple sufficient statistics
+    // of the observed column — ss[u] = mean of the D of triple u's pairs, ss[n_trip + u] = their number, ss[2 n_trip] =
+    // the centred sum of squares over all pairs — turn step 3 from O(pairs) into O(triples).  null: the exact sum.
+    const double *ss;
 };
 
 // doubles of per-warp shared memory: tables + exchange buffers + the simplex (25 x 32, LaneSimplex layout)
@@ -115,6 +119,19 @@ __device__ __forceinline__ double objective_wide(const WideCtx &c, int lane, dou
     if (penalty) {
         const double dq = p_uu_est(alpha, beta) - c.eqp;
         pen = c.penw * (dq * dq);
+    }
+    if (c.ss) {
+        // sum_i (D_i - c - dt_u(i))^2 = Q + sum_u n_u (m_u - c - dt_u)^2: triples over the lanes, fixed shuffle tree
+        double part = 0.0;
+        for (int u = lane; u < c.n_trip; u += WW) {
+            const double r = c.ss[u] - icpt - c.dt[u];
+            part += c.ss[c.n_trip + u] * (r * r);
+        }
+#ifdef __CUDA_ARCH__
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+#endif
+        return c.ss[2 * c.n_trip] + part + (double)c.n_pairs * pen;
     }
     constexpr int PER = WIDE_CH / WW;  // 1 on the device
     const int n = c.n_pairs;

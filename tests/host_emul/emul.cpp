@@ -131,6 +131,7 @@ static int stage_wide(const abfit_problem *pb, StagedWide &s)
     s.c.n_pairs = d.n_pairs;
     s.c.n_trip = d.n_trip;
     s.c.tmax = d.tmax;
+    s.c.ss = nullptr;  // the exact sum (the sufficient-statistics experiment is a GPU-side flag)
     s.c.p_uu0 = d.p_uu0;
     s.c.p_mm0 = d.p_mm0;
     s.c.eqp = d.eqp;

@@ -1168,3 +1168,36 @@ def test_c5_full_size_divergence_properties(ab, ctx, oracle):
     two = ctx.dmatrix_device(status.data_ptr(), post.data_ptr(), meth.data_ptr(), 2, L, 0.99)
     assert two["diff"][0][0] == whole["diff"][0][0] and two["cnt"][0][0] == whole["cnt"][0][0]
     assert two["nvalid"][0][0] == whole["nvalid"][0][0] and two["nvalid"][0][1] == whole["nvalid"][0][1]
+
+
+def test_suffstats_experiment_large_pedigree(ab, ctx, oracle, monkeypatch):
+    """the same EXPERIMENT on the warp-per-fit kernels (pedigrees with thousands of pairs, C5's family): objective
+    from per-triple statistics instead of the sequential sum over every pair; best-of-starts against the exact path at
+    north_star's tolerances (exact RSS at the experiment's best theta within 1e-9, alpha / beta within 1e-6)"""
+    import bench
+    rng = np.random.default_rng(77)
+    ped = bench.c5_times(6, 12)  # 72 samples, 2556 pairs
+    th = np.array([2.3e-4, 8.1e-4, 0.04, 0.002])
+    p0uu = 0.74
+    dt, _ = ctx.divergence(ab.Problem(np.column_stack([ped[:, :3], np.zeros(len(ped))]), p0uu, p0uu, 1.0), th)
+    ped[:, 3] = np.maximum(th[3] + dt + rng.normal(0, 4e-4, len(ped)), 0.0)
+    prob = [ab.Problem(ped, p0uu, p0uu, 1.0)]
+    n_starts = 96
+    sx = ab.gen_start_simplices(SEED, 0, n_starts, float(ped[:, 3].max()))[None]
+    monkeypatch.setenv("ABFIT_DEV_WIDE", "1")
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ABFIT_EXPERIMENT_SUFFSTATS", mode)
+        b = ctx.batch(prob)
+        b.upload_starts(sx)
+        b.run_fit()
+        res[mode] = (b.download_fit(want_all=True), b.timing()["fit_ms"])
+        b.close()
+    monkeypatch.delenv("ABFIT_EXPERIMENT_SUFFSTATS")
+    (exact, ms_exact), (suff, ms_suff) = res["0"], res["1"]
+    _, lse_at = ctx.cost_batch(prob, suff.best["theta"], np.zeros(1, dtype=np.int32))
+    assert abs(lse_at[0] - exact.best["lse"][0]) <= 1e-9 * abs(exact.best["lse"][0])
+    for k in (0, 1):
+        assert abs(suff.best["theta"][0, k] - exact.best["theta"][0, k]) <= 1e-6 * abs(exact.best["theta"][0, k]), k
+    assert not np.array_equal(exact.all["cost"], suff.all["cost"])  # the flag did switch the objective
+    assert ms_suff < ms_exact
