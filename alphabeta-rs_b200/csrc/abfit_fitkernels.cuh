@@ -417,7 +417,7 @@ __device__ __forceinline__ void fit_boot_gather_body(const DevicePools &P, const
     const WarpCtx &c = cv.ctx;
     const LaneSimplex &S = cv.simplex;
     uint2 *tile = idx_scratch + (size_t)blockIdx.x * (size_t)scratch_stride + lane;
-    const DGather Dat{tile, spred, reinterpret_cast<const char *>(sresid)};
+    const DGather Dat{tile, spred, reinterpret_cast<const char *>(sresid), nullptr};
     const int32_t *idxp = resample_idx + (size_t)pb.pair_off * n_boot;  // [n_boot][n_pairs] of this problem
     const abfit_fit bm = best[it.prob];
     const int ng4 = (pb.n_pairs + 3) >> 2;
@@ -709,6 +709,8 @@ __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, co
     LaneNM L;
     lane_nm_reset(L);
     int my_slot = 0, my_prob = 0;
+    // EXPERIMENT (ABFIT_EXPERIMENT_SUFFSTATS): per-triple statistics of the lane's replicate, built when it starts
+    double boot_st[OBJ::N_BOOT_STAT > 0 ? OBJ::N_BOOT_STAT : 1];
     V2Queue q;
     for (;;) {
         // warps of a block stay in phase (shared instruction-cache lines); a warp that has left the loop has exited
@@ -741,6 +743,10 @@ __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, co
                     }
                     tile[(size_t)g * 32] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
                 }
+                if (DGather::SUFF) {
+                    const DGather Dst{tile, sl + npad, reinterpret_cast<const char *>(smem_block), nullptr};
+                    OBJ::boot_stats(Dst, boot_st);
+                }
                 // simplex = [best, vary x 4]  (src/boot_model.rs:69-75)
                 const double *vv = vary + ((size_t)q.prob * n_boot + id) * 16;
 #pragma unroll
@@ -760,7 +766,7 @@ __device__ __forceinline__ void fit_boot_gather_body_v2(const DevicePools &P, co
         if (active) {
             const double *sl = slots + my_slot * slot_doubles;
             const WarpCtx c = v2_ctx(nullptr, sl + 2 * npad, n_pairs);
-            const DGather Dat{tile, sl + npad, reinterpret_cast<const char *>(smem_block)};
+            const DGather Dat{tile, sl + npad, reinterpret_cast<const char *>(smem_block), boot_st};
             const double f = OBJ::eval(c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);
             abfit_fit res;
             if (nm_advance(L, S, nm, f, res, amask)) {

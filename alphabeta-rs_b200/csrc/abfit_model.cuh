@@ -359,6 +359,7 @@ struct DBroadcast {
         d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
     }
     __device__ __forceinline__ double operator()(int i) const { return D[i]; }
+    __device__ __forceinline__ double stat(int u) const { return D[u]; }  // SUFF: the slot holds [mean_u][Q]
 };
 struct DLaneColumn {
     static constexpr bool ROLL = false;
@@ -370,18 +371,23 @@ struct DLaneColumn {
         for (int q = 0; q < 4; ++q) d[q] = __ldcg(col + (size_t)(i + q) * 32);
     }
     __device__ __forceinline__ double operator()(int i) const { return __ldcg(col + (size_t)i * 32); }
+    __device__ __forceinline__ double stat(int) const { return 0.0; }
 };
 
 // Bootstrap replicate (src/boot_model.rs:43-57): D*_i = pred_i + resid[idx_i], rebuilt on the fly from
 // the replicate's resample indices.  Only the indices are per-lane data: four u16 per lane and group of
 // four pairs in one coalesced 8-byte load from an L2-resident tile (a quarter of the bytes of a stored D*
 // column); pred is a shared-memory broadcast and resid a shared-memory gather.
+#ifndef ABFIT_SUFF_BOOT
+#define ABFIT_SUFF_BOOT 0
+#endif
 struct DGather {
     static constexpr bool ROLL = ABFIT_ROLL_BOOT != 0;
-    static constexpr bool SUFF = false;
+    static constexpr bool SUFF = ABFIT_SUFF_BOOT != 0;  // EXPERIMENT: `st` holds the replicate's per-triple statistics
     const uint2 *tile;    // [group][32] (lane folded in): four u16 byte offsets into resid
     const double *pred;   // shared, 16-byte aligned
     const char *resid;    // shared, at the start of dynamic shared memory
+    const double *st;     // EXPERIMENT (ABFIT_EXPERIMENT_SUFFSTATS): this lane's [mean_u][Q] of the replicate, else null
     __device__ __forceinline__ void load4(int i, double d[4]) const
     {
         const uint2 *p = tile + (size_t)(i >> 2) * 32;
@@ -403,6 +409,7 @@ struct DGather {
         const uint32_t h = (i & 2) ? w.y : w.x;
         return pred[i] + *reinterpret_cast<const double *>(resid + ((i & 1) ? (h >> 16) : (h & 0xffffu)));
     }
+    __device__ __forceinline__ double stat(int u) const { return st[u]; }
 };
 
 // Objective (src/structs.rs:191-217).  penalty=false gives the penalty-free LSE of

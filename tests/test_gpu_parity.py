@@ -1201,3 +1201,34 @@ def test_suffstats_experiment_large_pedigree(ab, ctx, oracle, monkeypatch):
         assert abs(suff.best["theta"][0, k] - exact.best["theta"][0, k]) <= 1e-6 * abs(exact.best["theta"][0, k]), k
     assert not np.array_equal(exact.all["cost"], suff.all["cost"])  # the flag did switch the objective
     assert ms_suff < ms_exact
+
+
+def test_suffstats_experiment_bootstrap(ab, ctx, ped351, monkeypatch):
+    """EXPERIMENT, mode 2 (ABFIT_EXPERIMENT_SUFFSTATS=2): the bootstrap refits from per-replicate per-triple statistics.
+    Same best models, resamples and vary vertices on both sides; nearly every replicate ends bit-identical, all but a
+    few within 1e-6 in alpha / beta (a replicate whose trajectory parts may stop elsewhere: it is an experiment)"""
+    rng = np.random.default_rng(4242)
+    cases = [synth_problem(rng, ped351) for _ in range(16)]
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    n_starts, n_boot = 120, 100
+    sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    idx = np.concatenate([ab.gen_resample_idx(SEED, i, n_boot, len(p)).ravel() for i, (p, u) in enumerate(cases)])
+    monkeypatch.setenv("ABFIT_JIT", "1")
+    b = ctx.batch(probs)
+    b.upload_starts(sx)
+    b.run_fit()
+    res = b.download_fit()
+    vary = np.stack([ab.gen_vary_vertices(SEED, i, n_boot, res.best[i]["theta"]) for i in range(len(cases))])
+    b.upload_boot(idx, vary)
+    b.run_boot()
+    rows_e, _ = b.download_boot()
+    b.close()
+    monkeypatch.setenv("ABFIT_EXPERIMENT_SUFFSTATS", "2")
+    b = ctx.batch(probs)
+    b.upload_boot(idx, vary, best=res.best, pred=res.pred, resid=res.resid)
+    b.run_boot()
+    rows_s, _ = b.download_boot()
+    b.close()
+    rel = np.abs(rows_s[:, :, :2] - rows_e[:, :, :2]) / np.abs(rows_e[:, :, :2])
+    assert np.mean((rel <= 1e-6).all(axis=2)) >= 0.99
+    assert np.mean((rows_s[:, :, :4] == rows_e[:, :, :4]).all(axis=2)) >= 0.9

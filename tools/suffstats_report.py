@@ -4,7 +4,9 @@ the exact kernels, which are bit-identical to the oracle (tests/test_gpu_parity.
 regrouped, so the Nelder-Mead trajectories differ.  For every window of the C4 synthetic metaprofile (bench.py's
 generator, the same seeded start simplices on both sides) the best-of-starts result is compared at north_star's
 tolerances: RSS 1e-9 relative (the exact objective evaluated at the experiment's best theta), alpha / beta 1e-6.
-  python tools/suffstats_report.py [windows=2000] [starts=1000]  -> one JSON line
+  python tools/suffstats_report.py [windows=2000] [starts=1000] [replicates=100]  -> one JSON line
+(ABFIT_EXPERIMENT_SUFFSTATS=1: multi-start kernel; =2: the bootstrap refits too, compared replicate by replicate from the
+same exact best models)
 """
 import json, os, sys, time
 import numpy as np
@@ -72,4 +74,44 @@ out = {
     "beta_rel_diff_quantiles_50_90_99_max": [float(np.quantile(d_b, q)) for q in (0.5, 0.9, 0.99, 1.0)],
     "verdict": "stays an experiment" if not ok.all() else "all windows within tolerance on this data set",
 }
+# ---- mode 2: the bootstrap refits too (per-replicate statistics), from the EXACT best models on both sides -------------
+NB = int(sys.argv[3]) if len(sys.argv) > 3 else 100
+N = len(shape)
+idx = np.concatenate([ab.gen_resample_idx(bench.SEED, i, NB, N).ravel() for i in range(W)])
+vary = np.stack([ab.gen_vary_vertices(bench.SEED, i, NB, exact.best[i]["theta"]) for i in range(W)])
+
+def run_boot(mode):
+    if mode:
+        os.environ["ABFIT_EXPERIMENT_SUFFSTATS"] = "2"
+    else:
+        os.environ.pop("ABFIT_EXPERIMENT_SUFFSTATS", None)
+    os.environ["ABFIT_JIT"] = "1"
+    b = ctx.batch(probs)
+    b.upload_boot(idx, vary, best=exact.best, pred=exact.pred, resid=exact.resid)
+    b.run_boot()
+    ms = []
+    for _ in range(3):
+        b.run_boot()
+        ms.append(b.timing()["boot_ms"])
+    rows, _ = b.download_boot()
+    b.close()
+    return rows, float(np.median(ms))
+
+rows_e, bms_e = run_boot(False)
+rows_s, bms_s = run_boot(True)
+os.environ.pop("ABFIT_EXPERIMENT_SUFFSTATS", None)
+da, db = rel(rows_s[:, :, 0], rows_e[:, :, 0]), rel(rows_s[:, :, 1], rows_e[:, :, 1])
+an_e = np.stack([ab.analyze(rows_e[i]) for i in range(W)])
+an_s = np.stack([ab.analyze(rows_s[i]) for i in range(W)])
+ci = rel(an_s[:, 16:20], an_e[:, 16:20])  # q0.025 / q0.975 of alpha and beta
+out["bootstrap"] = {
+    "replicates": NB, "boot_ms_exact": bms_e, "boot_ms_suffstats": bms_s, "speedup_bootstrap_kernel": bms_e / bms_s,
+    "replicates_alpha_beta_within_1e-6": float(np.mean((da <= 1e-6) & (db <= 1e-6))),
+    "replicates_bit_identical": float(np.mean((rows_s[:, :, :4] == rows_e[:, :, :4]).all(axis=2))),
+    "alpha_rel_diff_quantiles_50_99_max": [float(np.quantile(da, q)) for q in (0.5, 0.99, 1.0)],
+    "ci_bounds_rel_diff_quantiles_50_99_max": [float(np.quantile(ci, q)) for q in (0.5, 0.99, 1.0)],
+    "windows_with_all_ci_bounds_within_1e-6": int((ci <= 1e-6).all(axis=1).sum()),
+}
+out["step_ms_exact"] = ms_exact + bms_e
+out["step_ms_experiment"] = ms_suff + bms_s
 print(json.dumps(out))
