@@ -265,7 +265,7 @@ def small_case_c2(ab, ctx, n_starts=1000, n_boot=1000):
             "best": {"alpha": float(b["theta"][0]), "beta": float(b["theta"][1]), "lse": float(b["lse"])}}
 
 
-def suffstats_experiment(ab, ctx, probs, sx, n_windows=2000):
+def suffstats_experiment(ab, ctx, probs, sx, n_windows=2000, idx=None, n_boot=0, first=0):
     """EXPERIMENT, never the default and never part of `value`: the multi-start kernel with
     the objective evaluated from per-triple sufficient statistics (ABFIT_EXPERIMENT_SUFFSTATS=1; O(distinct triples)
     per evaluation instead of O(pairs); regrouped sum, so NOT bit-identical).  Same windows, same start simplices, both
@@ -296,6 +296,38 @@ def suffstats_experiment(ab, ctx, probs, sx, n_windows=2000):
             else:
                 os.environ[k] = v
     be, bs = res["0"].best, res["1"].best
+    boot = None
+    if idx is not None and n_boot > 0:
+        # mode 2: the bootstrap refits too, from the exact best models on both sides
+        try:
+            N = P[0].n_pairs
+            I = np.ascontiguousarray(idx[:Ws]).reshape(-1)
+            vary = np.stack([ab.gen_vary_vertices(SEED, first + i, n_boot, be[i]["theta"]) for i in range(Ws)])
+            rows, bms = {}, {}
+            os.environ["ABFIT_JIT"] = "1"
+            for mode in ("0", "2"):
+                os.environ["ABFIT_EXPERIMENT_SUFFSTATS"] = mode
+                b = ctx.batch(P)
+                b.upload_boot(I, vary, best=be, pred=res["0"].pred, resid=res["0"].resid)
+                b.run_boot()
+                t = []
+                for _ in range(3):
+                    b.run_boot()
+                    t.append(b.timing()["boot_ms"])
+                rows[mode], bms[mode] = b.download_boot()[0], float(np.median(t))
+                b.close()
+            r2 = np.abs(rows["2"][:, :, :2] - rows["0"][:, :, :2]) / np.maximum(np.abs(rows["0"][:, :, :2]), 1e-300)
+            boot = {"replicates": n_boot, "bootstrap_ms_exact": bms["0"], "bootstrap_ms_experiment": bms["2"],
+                    "speedup": bms["0"] / bms["2"], "replicates_within_1e-6": float(np.mean((r2 <= 1e-6).all(axis=2))),
+                    "replicates_bit_identical": float(np.mean((rows["2"][:, :, :4] == rows["0"][:, :, :4]).all(axis=2)))}
+        except Exception as e:
+            boot = {"error": str(e)}
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
     _, lse_at = ctx.cost_batch(P, bs["theta"], np.arange(Ws, dtype=np.int32))
     rel = lambda a, b: np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
     d_rss, d_a, d_b = rel(lse_at, be["lse"]), rel(bs["theta"][:, 0], be["theta"][:, 0]), rel(bs["theta"][:, 1], be["theta"][:, 1])
@@ -307,7 +339,8 @@ def suffstats_experiment(ab, ctx, probs, sx, n_windows=2000):
             "speedup": ms["0"] / ms["1"], "windows_within_tolerance": int(ok.sum()),
             "tolerance": "exact RSS at the experiment's best theta within 1e-9 relative of the exact path's, alpha and beta within 1e-6",
             "max_rel_diff": {"rss": float(d_rss.max()), "alpha": float(d_a.max()), "beta": float(d_b.max())},
-            "same_winning_start": float(np.mean(be["start_id"] == bs["start_id"]))}
+            "same_winning_start": float(np.mean(be["start_id"] == bs["start_id"])),
+            "bootstrap_mode_2": boot}
 
 
 def c5_times(lineages=10, generations=20):
@@ -759,7 +792,7 @@ def main():
     experiments = {}
     if rank == 0 and world == 1 and not args.no_experiments:
         try:
-            experiments["suffstats"] = suffstats_experiment(ab, ctx, probs, sx)
+            experiments["suffstats"] = suffstats_experiment(ab, ctx, probs, sx, idx=idx, n_boot=NB, first=first)
         except Exception as e:
             experiments["suffstats"] = {"error": str(e)}
 
