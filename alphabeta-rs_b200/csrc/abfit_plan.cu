@@ -99,8 +99,9 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
         hp.total_pairs += probs[p].n_pairs;
         hp.max_pairs = std::max(hp.max_pairs, probs[p].n_pairs);
     }
-    hp.D.assign((size_t)d_total, 0.0);
-    std::vector<uint32_t> keys((size_t)hp.total_pairs);  // t0 | (t1 - t0) << 8 | (t2 - t0) << 16 per row
+    hp.D.resize((size_t)d_total);  // every element is written by the scan below (the pad of an odd column too)
+    std::vector<uint32_t> &keys = hp.keys;
+    keys.resize((size_t)hp.total_pairs);
     std::vector<int32_t> bad_row(n_probs, -1), max_exp_of(n_probs, 0);
     scan_parallel(n_probs, [&](int p) {
         const abfit_problem &ap = probs[p];
@@ -120,8 +121,16 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
             nan |= (uint8_t)(row[3] != row[3]);
             Dp[i] = row[3];
         }
+        if (ap.n_pairs & 1) Dp[ap.n_pairs] = 0.0;
         max_exp_of[p] = mx;
         hp.d_has_nan[p] = nan;
+    });
+    // does problem p repeat the time structure of problem p - 1?  (parallel; equality is transitive, so "same as the
+    // previous problem" is "same as the last distinct one" in the loop below)
+    std::vector<uint8_t> same_as_prev(n_probs, 0);
+    scan_parallel(n_probs, [&](int p) {
+        if (p > 0 && probs[p - 1].n_pairs == probs[p].n_pairs && bad_row[p] < 0 && bad_row[p - 1] < 0)
+            same_as_prev[p] = std::memcmp(keys.data() + pair_off[p], keys.data() + pair_off[p - 1], (size_t)probs[p].n_pairs * 4) == 0;
     });
 
     // ---- pass 2: programs ------------------------------------------------------------------------------
@@ -153,8 +162,7 @@ int compile_problems(const abfit_problem *probs, int n_probs, HostPlan &hp)
         dp.penw = ap.eqp_weight * (double)ap.n_pairs;  // src/structs.rs:210-211
         const uint32_t *key32 = keys.data() + pair_off[p];
         const int max_exp = max_exp_of[p];
-        if (prev_p >= 0 && probs[prev_p].n_pairs == ap.n_pairs &&
-            std::memcmp(key32, keys.data() + pair_off[prev_p], (size_t)ap.n_pairs * 4) == 0) {
+        if (prev_p >= 0 && same_as_prev[p]) {
             const DevProblem &q = hp.probs[prev_p];
             dp.offs_off = q.offs_off;
             dp.ops_off = q.ops_off;

@@ -18,7 +18,26 @@ struct HostPlan {
     std::vector<uint8_t> d_has_nan;
     int32_t max_pairs = 0;
     int64_t total_pairs = 0;
-    void clear() { *this = HostPlan(); }
+    std::vector<uint32_t> keys;    // scratch of compile_problems: t0 | (t1 - t0) << 8 | (t2 - t0) << 16 per pedigree row
+    // empties the plan but keeps the storage: a context's workspace plan is refilled by every one-shot call, and
+    // returning 50 MB to the allocator only to fault the same pages in again cost milliseconds per call
+    void clear()
+    {
+        probs.clear();
+        D.clear();
+        offs.clear();
+        ops.clear();
+        wtrip.clear();
+        wtid.clear();
+        flops.clear();
+        fp64_instr.clear();
+        n_triples.clear();
+        tmax.clear();
+        d_has_nan.clear();
+        keys.clear();
+        max_pairs = 0;
+        total_pairs = 0;
+    }
 };
 
 // Validates and compiles n_probs problems. Returns 0 or a negative abfit_status (message via set_error).
