@@ -200,10 +200,13 @@ def run_reference_arm(args):
 
     o.build()
     threads = o.hw_threads()
-    # bounded sample: ~ 4 fits per thread and step (literal reference work is ~1.3 s per fit and core, plus the serial
-    # sort_by tail), so that 25 steps and the one full window below end within a few minutes
-    ns = max(8, 4 * threads)
-    nb = max(2, ns // 10)
+    # bounded sample, sized from the step count: literal reference work costs ~0.85 core-seconds per fit (measured:
+    # one full window, 1100 fits, 112 s on 8 cores) and a stalled start alone runs its 10 000 iterations for ~8 s on
+    # one core, so a SHORT sample is slower per fit than the reference really is (one stalled start is the whole
+    # step); the steps get as many starts as ~3 minutes of host time allow, up to the full window.
+    n_steps = max(1, args.warmup + args.steps)
+    ns = int(min(args.starts, max(4 * threads, threads * 180.0 / (n_steps * 0.85 * 1.1))))
+    nb = max(2, ns * args.boots // args.starts)
     vals = []
     for i in range(args.warmup + args.steps):
         v, dt, _ = cpu_reference_sample(shape, ns, nb, literal=True, threads=threads, window=i)
@@ -212,14 +215,18 @@ def run_reference_arm(args):
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([dt for _, dt in vals]) * 1e3)
     full = None
-    if not args.no_full_window:
-        # one whole window exactly as BASELINE configs[3] sizes it (1000 starts + 100 replicates): the serial
-        # sort_by tail grows as n log n, so the bounded sample above flatters the reference slightly
+    if ns >= args.starts:
+        full = {"fits_per_s": value, "seconds": ms / 1e3, "sample": "every timed step is one full window"}
+    elif not args.no_full_window:
+        # one whole window exactly as BASELINE configs[3] sizes it (1000 starts + 100 replicates): the reference's
+        # real rate (stalled starts amortised over 1000 starts; serial sort_by tail of n log n comparisons)
         v, dt, _ = cpu_reference_sample(shape, args.starts, args.boots, literal=True, threads=threads, window=10 ** 6)
         full = {"fits_per_s": v, "seconds": dt, "sample": f"1 window x ({args.starts} starts + {args.boots} replicates), once"}
     sample = (f"1 synthetic C4 window x ({ns} starts + {nb} bootstrap replicates) per step, literal reference work "
               "(per-pair matrix_power, pedigree clone per start, sort_by comparator re-evaluating divergence twice); "
-              "inputs drawn before the clock starts by oracle/gen_py.py; the process maps oracle/libabref.so only")
+              "inputs drawn before the clock starts by oracle/gen_py.py; the process maps oracle/libabref.so only; a sample "
+              "shorter than the full window UNDERSTATES the reference (a stalled start's 10 000 iterations are the "
+              "step's tail): cpu_baseline.full_window is the reference's rate on a whole window")
     line = {
         "impl": "reference", "metric": METRIC, "value": value,
         "unit": "fits/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -765,7 +772,9 @@ def main():
         v, dt, _ = cpu_reference_sample(shape, ns, nb, literal=True, threads=threads)
         v2, dt2, _ = cpu_reference_sample(shape, 16 * ns, 16 * nb, literal=False, threads=threads)
         cpu = {"value": v, "unit": "fits/s", "cores": threads, "kind": "port",
-               "sample": f"1 C4 window x ({ns} starts + {nb} boots), literal reference work incl. the re-evaluating sort_by, {dt:.1f} s",
+               "sample": f"1 C4 window x ({ns} starts + {nb} boots), literal reference work incl. the re-evaluating sort_by, {dt:.1f} s "
+                         "(a sample this short is bounded by its stalled starts, 10 000 iterations each: the whole-window rate "
+                         "is `bench.py --impl reference`'s cpu_baseline.full_window)",
                "minimal_work_value": v2,
                "minimal_work_note": "same port with the power table + stall early-exit the GPU path uses "
                                     f"({16 * ns} starts + {16 * nb} boots, {dt2:.1f} s): separates algorithmic "
