@@ -569,6 +569,95 @@ __device__ __forceinline__ unsigned v2_busy_slots(bool active, int my_slot)
     return busy;
 }
 
+// ---------------------------------------------------------------------------------
+// Drain merging (multi-start kernel, V2_FIT_WARPS > 1).  When the item cursor runs dry every lane still finishes its
+// fit, and Nelder-Mead run lengths spread 3.5x: for the last ~20 ms of a launch the machine is full of warps with a few
+// live lanes each, and a warp instruction costs the FP64 pipe the same whether 3 or 32 of its lanes are live.  With
+// V2_FIT_WARPS warps per block (still independent: own queue state, own slots, NO barrier per evaluation) the warps of
+// a block MERGE at that point: the emptiest warp hands its running fits to idle lanes of the fullest warp that has
+// room for all of them, and exits.  Everything a fit owns is in shared memory or registers: the receiver lane copies
+// the 25-double simplex, takes the LaneNM registers through its own (unused) simplex storage, and keeps reading the
+// window's D column from the DONOR's slot — a block's shared memory outlives the warps that filled it.
+//
+// Protocol (barriers, no polling): a warp that can start no further fit (cursor dry, own item used up) registers in
+// `counts`; once all live warps of the block are registered — a condition that stays true: registration is permanent
+// and an exiting warp leaves both counts at once — every live warp enters a merge round every V2_MERGE_EVERY
+// evaluations: barrier, publish the running lanes, barrier, the same plan computed by every warp, donor parks,
+// barrier, receiver adopts.  bar.sync counts exited warps as arrived, so a warp may leave between rounds.
+// A fit's arithmetic does not depend on the lane that runs it: same bits.
+// ---------------------------------------------------------------------------------
+constexpr int V2_MERGE_EVERY = 8;
+struct V2MergeCtl {
+    int counts;         // (live warps << 8) | registered warps
+    int nact[8];        // per merge round: running fits of warp w (0: exited)
+    unsigned amask[8];  // ... and the lanes that run them
+};
+static_assert(sizeof(V2MergeCtl) <= V2_FIT_CTL_BYTES && V2_FIT_WARPS <= 8, "control words of a merging block");
+
+// One merge round; called by every live warp of the block.  my_slot is the BLOCK-wide slot index (warp * V2_SLOTS + s).
+template <int FW>
+__device__ __forceinline__ void v2_merge_round(V2MergeCtl *ctl, double *smem_block, int warp_doubles, int warp, int lane,
+                                               LaneNM &L, const LaneSimplex &S, int &my_slot, int &my_prob)
+{
+    __syncthreads();
+    const unsigned am = __ballot_sync(FULL, L.phase != PH_IDLE);
+    if (lane == 0) {
+        ctl->nact[warp] = __popc(am);
+        ctl->amask[warp] = am;
+    }
+    __syncthreads();
+    int d = -1, r = -1, nd = 33, nr = 0;
+#pragma unroll
+    for (int w = 0; w < FW; ++w) {
+        const int n = ctl->nact[w];
+        if (n > 0 && n < nd) {
+            d = w;
+            nd = n;
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < FW; ++w) {
+        const int n = ctl->nact[w];
+        if (w != d && n > 0 && n + nd <= 32 && n > nr) {
+            r = w;
+            nr = n;
+        }
+    }
+    if (d < 0 || r < 0) return;  // (block-uniform: every warp read the same words)
+    const unsigned dmask = ctl->amask[d], rfree = ~ctl->amask[r];
+    if (warp == d && ((dmask >> lane) & 1u)) {
+        // park the registers in the simplex storage of the receiver's idle lane that takes this fit over
+        const int tl = __fns(rfree, 0, __popc(dmask & ((1u << lane) - 1u)) + 1);
+        double *ent = smem_block + (size_t)r * warp_doubles + tl;
+        ent[0 * 32] = L.xt[0]; ent[1 * 32] = L.xt[1]; ent[2 * 32] = L.xt[2]; ent[3 * 32] = L.xt[3];
+        ent[4 * 32] = L.fr;
+        ent[5 * 32] = __hiloint2double(L.phase, L.k);
+        ent[6 * 32] = __hiloint2double((int)L.ord, L.iters);
+        ent[7 * 32] = __hiloint2double(L.evals, L.status);
+        ent[8 * 32] = __hiloint2double(L.fit_id, lane);
+        ent[9 * 32] = __hiloint2double(my_prob, my_slot);
+    }
+    __syncthreads();
+    if (warp == r && ((rfree >> lane) & 1u)) {
+        const int rank = __popc(rfree & ((1u << lane) - 1u));
+        if (rank < nd) {
+            const double e5 = S.X[5 * 32], e6 = S.X[6 * 32], e7 = S.X[7 * 32], e8 = S.X[8 * 32], e9 = S.X[9 * 32];
+            L.xt[0] = S.X[0 * 32]; L.xt[1] = S.X[1 * 32]; L.xt[2] = S.X[2 * 32]; L.xt[3] = S.X[3 * 32];
+            L.fr = S.X[4 * 32];
+            L.phase = __double2hiint(e5); L.k = __double2loint(e5);
+            L.ord = (uint32_t)__double2hiint(e6); L.iters = __double2loint(e6);
+            L.evals = __double2hiint(e7); L.status = __double2loint(e7);
+            L.fit_id = __double2hiint(e8);
+            my_prob = __double2hiint(e9);
+            my_slot = __double2loint(e9);
+            const double *src = smem_block + (size_t)d * warp_doubles + __double2loint(e8);  // the donor lane's simplex
+#pragma unroll
+            for (int k = 0; k < 25; ++k) S.X[k * 32] = src[k * 32];  // X[20] and C[5] are contiguous
+        }
+    }
+    if (warp == d) lane_nm_reset(L);  // handed over; the warp leaves through the regular exit
+}
+
 template <class OBJ>
 __device__ __forceinline__ void fit_starts_body_v2(const DevicePools &P, const WorkItem *__restrict__ items, int n_items,
                                                    int *cursor, const double *__restrict__ simplices, int n_starts,
@@ -581,7 +670,16 @@ __device__ __forceinline__ void fit_starts_body_v2(const DevicePools &P, const W
     const int n_pairs = P.probs[items[0].prob].n_pairs;  // one program for the whole batch (host: jit_eligible)
     const int npad = (n_pairs + 1) & ~1;
     const int slot_doubles = v2_fit_slot_doubles(n_pairs);
-    double *smem = smem_block + (size_t)warp * (25 * 32 + V2_SLOTS * slot_doubles);  // this warp's own region
+    constexpr int FW = V2_FIT_WARPS;              // > 1: the block's warps merge when the launch drains (see above)
+    constexpr int NW = FW > 1 ? FW : V2_WARPS;    // warps per block
+    const int warp_doubles = 25 * 32 + V2_SLOTS * slot_doubles;
+    double *smem = smem_block + (size_t)warp * warp_doubles;  // this warp's own region
+    V2MergeCtl *ctl = reinterpret_cast<V2MergeCtl *>(smem_block + (size_t)NW * warp_doubles);
+    if (FW > 1) {
+        if (threadIdx.x == 0) ctl->counts = FW << 8;
+        if (threadIdx.x < 8) ctl->nact[threadIdx.x] = 0;
+        __syncthreads();
+    }
     LaneSimplex S;
     S.X = smem + lane;
     S.C = S.X + 20 * 32;
@@ -617,16 +715,28 @@ __device__ __forceinline__ void fit_starts_body_v2(const DevicePools &P, const W
 
     LaneNM L;
     lane_nm_reset(L);
-    int my_slot = 0, my_prob = 0;
+    int my_slot = 0, my_prob = 0;  // my_slot: FW > 1: block-wide index, warp * V2_SLOTS + slot
     V2Queue q;
+    bool registered = false;  // FW > 1: this warp can start no further fit and is counted in ctl->counts
+    int since = 0;
     for (;;) {
         // warps of a block stay in phase (shared instruction-cache lines); a warp that has left the loop has exited
-        if (V2_WARPS > 1) __syncthreads();
+        if (FW == 1 && V2_WARPS > 1) __syncthreads();
         else __syncwarp();
+        if (FW > 1 && registered && ++since >= V2_MERGE_EVERY) {
+            since = 0;
+            int c = 0;
+            if (lane == 0) c = *reinterpret_cast<volatile int *>(&ctl->counts);
+            c = __shfl_sync(FULL, c, 0);
+            if ((c >> 8) == (c & 0xff) && (c >> 8) > 1)
+                v2_merge_round<FW>(ctl, smem_block, warp_doubles, warp, lane, L, S, my_slot, my_prob);
+        }
         unsigned idle = __ballot_sync(FULL, L.phase == PH_IDLE);
         while (idle) {
             if (q.next >= q.end) {
-                if (!v2_open_next<V2_SLOTS>(q, items, n_items, cursor, lane, v2_busy_slots<V2_SLOTS>(L.phase != PH_IDLE, my_slot), stage)) break;
+                if (!v2_open_next<V2_SLOTS>(q, items, n_items, cursor, lane,
+                                            v2_busy_slots<V2_SLOTS>(L.phase != PH_IDLE, FW > 1 ? my_slot - warp * V2_SLOTS : my_slot), stage))
+                    break;
             }
             const int take = min(__popc(idle), q.end - q.next);
             const int rank = __popc(idle & ((1u << lane) - 1u));
@@ -636,7 +746,7 @@ __device__ __forceinline__ void fit_starts_body_v2(const DevicePools &P, const W
 #pragma unroll
                 for (int k = 0; k < 20; ++k) S.X[k * 32] = sx[k];
                 nm_begin(L, S, id);
-                my_slot = q.cur;
+                my_slot = FW > 1 ? warp * V2_SLOTS + q.cur : q.cur;
                 my_prob = q.prob;
             }
             q.next += take;
@@ -644,9 +754,21 @@ __device__ __forceinline__ void fit_starts_body_v2(const DevicePools &P, const W
         }
         const bool active = (L.phase != PH_IDLE);
         const unsigned amask = __ballot_sync(FULL, active);
-        if (!amask) break;  // nothing runs and nothing could be started: the launch's work is done
+        if (FW > 1 && !registered && q.exhausted && q.next >= q.end) {
+            registered = true;
+            if (lane == 0) atomicAdd(&ctl->counts, 1);
+        }
+        if (!amask) {  // nothing runs and nothing could be started: the launch's work is done
+            if (FW > 1 && lane == 0) {
+                ctl->nact[warp] = 0;
+                __threadfence_block();
+                atomicSub(&ctl->counts, registered ? 0x101 : 0x100);
+            }
+            break;
+        }
         if (active) {
-            const double *sl = slots + my_slot * slot_doubles;
+            const double *sl = FW > 1 ? smem_block + (size_t)(my_slot / V2_SLOTS) * warp_doubles + 25 * 32 + (my_slot % V2_SLOTS) * slot_doubles
+                                      : slots + my_slot * slot_doubles;
             const WarpCtx c = v2_ctx(sl, sl + npad, n_pairs);
             const DBroadcast Dat{sl};
             const double f = OBJ::eval(c, Dat, lane, L.xt[0], L.xt[1], L.xt[2], L.xt[3], L.phase != PH_LSE);

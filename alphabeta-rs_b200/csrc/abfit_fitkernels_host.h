@@ -26,5 +26,14 @@ constexpr int V2_BOOT_SLOTS = 2;
 #define ABFIT_V2_WARPS 1
 #endif
 constexpr int V2_WARPS = ABFIT_V2_WARPS;
+// warps per block of the multi-start kernel when its warps MERGE during the drain (abfit_fitkernels.cuh, "drain
+// merging"): 1 = off (one-warp blocks).  The warps run out of phase (no barrier per evaluation); barriers are used only
+// by the merge rounds at the end of a launch.  A block ends with V2_FIT_CTL_BYTES of control words behind the warps'
+// regions.
+#ifndef ABFIT_V2_FIT_WARPS
+#define ABFIT_V2_FIT_WARPS 1
+#endif
+constexpr int V2_FIT_WARPS = ABFIT_V2_FIT_WARPS;
+constexpr int V2_FIT_CTL_BYTES = 128;
 ABFIT_HD_INLINE int v2_boot_slot_doubles(int n_pairs) { return 2 * ((n_pairs + 1) & ~1) + 8; }
 }  // namespace abfit

@@ -23,6 +23,8 @@ struct JitModule {
     cudaKernel_t fit_boot_gather = nullptr;
     int slots = 4;  // window slots per warp (sched 2)
     int warps = 1;  // warps per block (sched 2): independent warps kept in phase by a block barrier per evaluation
+    int fit_warps = 1;       // warps per block of the multi-start kernel (= warps unless drain merging is on)
+    bool fit_merge = false;  // multi-start kernel built with drain merging (ABFIT_V2_FIT_WARPS > 1)
     int sched = 2;  // 1: block-per-item bodies, 2: continuous lane scheduling (persistent one-warp blocks)
     double compile_seconds = 0.0;
     bool from_disk_cache = false;

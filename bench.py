@@ -715,7 +715,9 @@ def main():
     instr_rate = fp64_peak * 1e12 / 2.0                            # FP64 lane-instructions per second at the DFMA peak
     # DRAM bytes of one multi-start launch at the default 1-GPU configuration, from an ncu capture of this command
     # (profiles/: start simplices in, fit records out; the kernel never re-reads HBM).  Other shapes were not captured.
-    traffic = 1784302336 + 779979008 if (W, NS, NB) == (10000, 1000, 100) else None
+    # profiles/r02v_dram_fit_kernels_w10000.csv: abfit_jit_fit_starts_v2, first captured launch (algorithmic: 160 B of
+    # start simplex in + 64 B of fit record out per fit = 2.24 GB)
+    traffic = 1753669888 + 705587200 if (W, NS, NB) == (10000, 1000, 100) else None
     roofline = {"bound": "fp64", "kernel": "k_fit_starts (multi-start Nelder-Mead)", "achieved": achieved, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "pipe_frac": evals_fit * fl["fp64_instr"] / (fit_ms * 1e-3) / instr_rate,
@@ -725,7 +727,7 @@ def main():
                              "only the 3x3 products may be FMAs (bit-exact contract), so frac <= frac_ceiling x pipe_frac",
                 "fp64_instr_per_eval": fl["fp64_instr"],
                 "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)",
-                "bound_note": "FP64 vector pipe (BASELINE.json: % FP64 peak); no tensor cores, HBM traffic is 2.6 GB per launch",
+                "bound_note": "FP64 vector pipe (BASELINE.json: % FP64 peak); no tensor cores, HBM traffic is 2.5 GB per 1.66 s launch",
                 "peak_source": "DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure; nominal 37.2)",
                 "flops_per_eval": fl["flops"], "evals_per_launch": evals_fit / rsteps,
                 "kernel_ms": fit_ms / rsteps, "kernel_share_of_step": fit_ms / rr["total_ms"],

@@ -742,7 +742,10 @@ def test_resample_index_check_large_pedigree(ab, ctx):
                                  {"ABFIT_DEV_PIPES": "5", "ABFIT_DEV_CHUNK": "40"}, {"ABFIT_DEV_JIT_WARPS": "2"},
                                  {"ABFIT_DEV_JIT_WARPS": "3", "ABFIT_DEV_CHUNK": "7", "ABFIT_DEV_PIPES": "2"},
                                  {"ABFIT_DEV_SCHED": "1", "ABFIT_DEV_NWARPS": "3", "ABFIT_DEV_CHUNK": "150"},
-                                 {"ABFIT_DEV_SCHED": "1", "ABFIT_DEV_NWARPS": "4"}, {"ABFIT_DEV_SCHED": "1"}])
+                                 {"ABFIT_DEV_SCHED": "1", "ABFIT_DEV_NWARPS": "4"}, {"ABFIT_DEV_SCHED": "1"},
+                                 {"ABFIT_DEV_FIT_WARPS": "4"}, {"ABFIT_DEV_FIT_WARPS": "1"}, {"ABFIT_DEV_FIT_WARPS": "4", "ABFIT_DEV_CHUNK": "7"},
+                                 {"ABFIT_DEV_FIT_WARPS": "3", "ABFIT_DEV_CHUNK": "40", "ABFIT_DEV_PIPES": "2"},
+                                 {"ABFIT_DEV_FIT_WARPS": "6", "ABFIT_DEV_CHUNK": "150"}])
 def test_specialised_kernels_are_bit_identical(ab, ctx, oracle, ped351, ped78, monkeypatch, env):
     """run-time specialised kernels (csrc/abfit_jit.cu: the batch's one micro-op program compiled to straight-line
     code by NVRTC) against the interpreter kernels and the oracle: every start, every bootstrap row, same bits.
@@ -789,6 +792,42 @@ def test_specialised_kernels_are_bit_identical(ab, ctx, oracle, ped351, ped78, m
         for f in ("theta", "cost", "lse", "iters", "evals", "status", "start_id"):
             assert np.array_equal(got_all[2][f], allr[f]), f
         monkeypatch.delenv("ABFIT_JIT")
+
+
+@pytest.mark.parametrize("fit_warps,n_starts,chunk", [(4, 500, None), (4, 97, "33"), (6, 300, "40"), (2, 64, "7")])
+def test_drain_merging_stress(ab, ctx, ped351, monkeypatch, fit_warps, n_starts, chunk):
+    """drain merging of the multi-start kernel (ABFIT_DEV_FIT_WARPS: blocks of several independent warps whose
+    emptiest warp hands its running fits to a sibling once the item cursor is dry, abfit_fitkernels.cuh): 40
+    repetitions per shape, every fit record compared bit for bit with the one-warp-block kernel each time (a lost,
+    duplicated or mixed-up lane state changes them or hangs the launch)"""
+    rng = np.random.default_rng(8100 + n_starts)
+    base, _ = synth_problem(rng, ped351)
+    cases = []
+    for _ in range(8):
+        p = base.copy()
+        p[:, 3] = np.maximum(base[:, 3] * rng.uniform(0.7, 1.3) + rng.normal(0, 3e-4, len(base)), 0.0)
+        cases.append((p, float(rng.uniform(0.6, 0.95))))
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    sx = np.stack([ab.gen_start_simplices(SEED, i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    monkeypatch.setenv("ABFIT_JIT", "1")
+    monkeypatch.setenv("ABFIT_DEV_FIT_WARPS", "1")
+    b = ctx.batch(probs)
+    b.upload_starts(sx)
+    assert b.uses_specialised_kernels(), ab.jit_last_error()
+    b.run_fit()
+    ref = b.download_fit(want_all=True).all
+    b.close()
+    monkeypatch.setenv("ABFIT_DEV_FIT_WARPS", str(fit_warps))
+    if chunk:
+        monkeypatch.setenv("ABFIT_DEV_CHUNK", chunk)
+    b = ctx.batch(probs)
+    b.upload_starts(sx)
+    assert b.uses_specialised_kernels(), ab.jit_last_error()
+    for rep in range(40):
+        b.run_fit()
+        got = b.download_fit(want_all=True).all
+        assert got.tobytes() == ref.tobytes(), rep
+    b.close()
 
 
 @pytest.mark.parametrize("n_starts,n_boot", [(1, 1), (33, 31), (97, 100), (257, 7)])
