@@ -118,6 +118,7 @@ def _load() -> C.CDLL:
         "abfit_jit_last_error": (C.c_char_p, []),
         "abfit_analyze": (C.c_int, [vp, i32, vp]),
         "abfit_parse_methylome_line": (C.c_int, [C.c_char_p, i32, vp, vp, vp, vp]),
+        "abfit_parse_methylome_buffer": (C.c_int, [C.c_char_p, i64, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp]),
         "abfit_pedigree_build": (C.c_int, [vp, C.c_char_p, C.c_char_p, dbl, C.POINTER(vp)]),
         "abfit_pedigree_info": (C.c_int, [vp, vp, vp, vp, vp]),
         "abfit_pedigree_graph": (C.c_int, [C.c_char_p, C.c_char_p, vp, C.c_char_p, i32, vp, vp, i32]),
@@ -154,7 +155,7 @@ EXPORTED_SYMBOLS = (
     "abfit_batch_destroy abfit_batch_upload_starts abfit_batch_run_fit abfit_batch_download_fit "
     "abfit_batch_upload_boot abfit_batch_run_boot abfit_batch_download_boot abfit_batch_run_pipelined abfit_batch_pipes abfit_batch_sync "
     "abfit_batch_timing abfit_batch_flops_per_eval abfit_batch_fp64_instr_per_eval abfit_batch_uses_specialised_kernels abfit_jit_dump abfit_jit_last_error abfit_analyze abfit_window_counts abfit_place_sites "
-    "abfit_parse_methylome_line abfit_parse_annotation_line abfit_pedigree_graph abfit_pedigree_build abfit_pedigree_info abfit_pedigree_rows abfit_pedigree_warnings "
+    "abfit_parse_methylome_line abfit_parse_methylome_buffer abfit_parse_annotation_line abfit_pedigree_graph abfit_pedigree_build abfit_pedigree_info abfit_pedigree_rows abfit_pedigree_warnings "
     "abfit_pedigree_free abfit_format_f64 abfit_steady_state abfit_write_pedigree abfit_write_analysis abfit_format_analysis "
     "abfit_write_npy_f64 abfit_write_metaprofile_results abfit_plot_metaplot abfit_plot_bootstrap"
 ).split()
@@ -800,6 +801,26 @@ def parse_methylome_line(line: str, invert_strand: bool = False):
     _check(rc)
     return {"chromosome": int(site[0]["chromosome"]), "start": int(site[0]["start"]), "end": int(site[0]["end"]),
             "strand": int(site[0]["strand"]), "posteriormax": post.value, "status": status.value, "meth_lvl": lvl.value}
+
+
+def parse_methylome_buffer(data: bytes, invert_strand: bool = False, skip_first_line: bool = False, want_lines: bool = False):
+    """abfit_parse_methylome_buffer: every line of a methylome file image that parses as a site, in file order ->
+    dict of arrays (sites: SITE_DTYPE, posteriormax, status, meth_lvl[, line_off, line_len])"""
+    cap = data.count(b"\n") + 1
+    sites = np.zeros(cap, dtype=SITE_DTYPE)
+    post, lvl = np.zeros(cap), np.zeros(cap)
+    status = np.zeros(cap, dtype=np.uint8)
+    off = np.zeros(cap if want_lines else 0, dtype=np.int64)
+    ln = np.zeros(cap if want_lines else 0, dtype=np.int32)
+    n = C.c_int64()
+    _check(_lib.abfit_parse_methylome_buffer(data, len(data), int(invert_strand), int(skip_first_line), cap, _ptr(sites), _ptr(post),
+                                             _ptr(status), _ptr(lvl), _ptr(off) if want_lines else None,
+                                             _ptr(ln) if want_lines else None, C.cast(C.byref(n), C.c_void_p)))
+    k = n.value
+    out = {"sites": sites[:k], "posteriormax": post[:k], "status": status[:k], "meth_lvl": lvl[:k]}
+    if want_lines:
+        out["line_off"], out["line_len"] = off[:k], ln[:k]
+    return out
 
 
 def build_pedigree(ctx: Context, nodelist: str, edgelist: str, posterior_max_filter: float = 0.99):

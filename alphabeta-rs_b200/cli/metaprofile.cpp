@@ -26,6 +26,7 @@
 // (src/pedigree.rs:222-230) — `abfit_pedigree_build` (the `alphabeta` tool) reproduces that rule, the fused window
 // pipeline does not: its divergence call needs index-aligned sites, and a fit on zeros that "are off" helps nobody.
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -37,6 +38,7 @@
 #include <sstream>
 #include <string>
 #include <sys/stat.h>
+#include <thread>
 #include <vector>
 
 #include "../../include/abfit.h"
@@ -80,8 +82,26 @@ struct Sample {
     std::vector<double> post, meth;
     std::vector<int32_t> dist;
     std::vector<int64_t> order, seg;  // sites of window w: order[seg[w] .. seg[w+1]) (file order)
-    std::vector<std::string> original;  // --write-windows: the parsed lines as read (MethylationSite::original)
+    // --write-windows: the parsed lines as read (MethylationSite::original) = slices of the file image
+    std::string image;
+    std::vector<int64_t> line_off;
+    std::vector<int32_t> line_len;
+    std::string original(size_t i) const { return image.substr((size_t)line_off[i], (size_t)line_len[i]); }
 };
+
+static bool read_whole_file(const std::string &path, std::string &out)
+{
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    out.clear();
+    struct stat st;
+    if (fstat(fileno(f), &st) == 0 && st.st_size > 0) out.reserve((size_t)st.st_size);
+    char buf[1 << 16];
+    size_t n;
+    while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, n);
+    std::fclose(f);
+    return true;
+}
 
 int main(int argc, char **argv)
 {
@@ -203,28 +223,42 @@ int main(int argc, char **argv)
     }
     const int n_total = nwin[0] + nwin[1] + nwin[2];
 
+    // One methylome file = one independent unit of work (the reference: rayon par_iter over the files,
+    // src/extract.rs:75): files are loaded, parsed and binned on a small pool of host threads, and the parser itself
+    // splits a file over the threads that are left.
     std::vector<Sample> samples(files.size());
-    for (size_t fi = 0; fi < files.size(); ++fi) {
+    std::vector<std::string> load_error(files.size());
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned outer = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(files.size(), hw), 16));
+    if (!getenv("ABFIT_HOST_THREADS")) setenv("ABFIT_HOST_THREADS", std::to_string(std::max(1u, hw / outer)).c_str(), 0);
+    auto load_sample = [&](size_t fi) -> bool {
         Sample &S = samples[fi];
         S.name = files[fi];
-        std::ifstream f(methylome + "/" + files[fi]);
-        std::string line;
-        bool first = true;
-        abfit_cg_site site;
-        double post, lvl;
-        int32_t status;
-        while (std::getline(f, line)) {
-            if (first) {  // Windows::extract skips the header row (src/windows.rs:322)
-                first = false;
-                continue;
+        // the whole file in one call (parsed on several threads); Windows::extract skips the header row (src/windows.rs:322)
+        if (read_whole_file(methylome + "/" + files[fi], S.image)) {
+            int64_t cap = 1, n = 0;
+            for (char ch : S.image) cap += ch == '\n';
+            S.sites.resize((size_t)cap);
+            S.status.resize((size_t)cap);
+            S.post.resize((size_t)cap);
+            S.meth.resize((size_t)cap);
+            if (write_windows) {
+                S.line_off.resize((size_t)cap);
+                S.line_len.resize((size_t)cap);
             }
-            if (!line.empty() && line.back() == '\r') line.pop_back();
-            if (abfit_parse_methylome_line(line.c_str(), invert, &site, &post, &status, &lvl) != 0) continue;
-            S.sites.push_back(site);
-            if (write_windows) S.original.push_back(line);
-            S.status.push_back((uint8_t)status);
-            S.post.push_back(post);
-            S.meth.push_back(lvl);
+            if (abfit_parse_methylome_buffer(S.image.data(), (int64_t)S.image.size(), invert, 1, cap, S.sites.data(), S.post.data(),
+                                             S.status.data(), S.meth.data(), write_windows ? S.line_off.data() : nullptr,
+                                             write_windows ? S.line_len.data() : nullptr, &n)) {
+                load_error[fi] = abfit_last_error();
+                return false;
+            }
+            S.sites.resize((size_t)n);
+            S.status.resize((size_t)n);
+            S.post.resize((size_t)n);
+            S.meth.resize((size_t)n);
+            S.line_off.resize(write_windows ? (size_t)n : 0);
+            S.line_len.resize(write_windows ? (size_t)n : 0);
+            if (!write_windows) std::string().swap(S.image);
         }
         S.dist.assign(n_total, 0);
         int64_t n_assign = 0;
@@ -266,6 +300,23 @@ int main(int argc, char **argv)
         S.order.resize(asite.size());
         std::vector<int64_t> cur(S.seg.begin(), S.seg.end() - 1);
         for (size_t q = 0; q < asite.size(); ++q) S.order[(size_t)cur[awin[q]]++] = asite[q];
+        return true;
+    };
+    {
+        std::atomic<size_t> next{0};
+        std::atomic<bool> ok{true};
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < outer; ++t)
+            pool.emplace_back([&]() {
+                for (size_t fi; (fi = next.fetch_add(1)) < files.size();)
+                    if (!load_sample(fi)) ok = false;
+            });
+        for (auto &th : pool) th.join();
+        if (!ok) {
+            for (auto &e : load_error)
+                if (!e.empty()) std::printf("Error: %s\n", e.c_str());
+            return 1;
+        }
     }
     // distribution / steady-state files (src/extract.rs:100-151, src/windows.rs:94-176,245-257)
     std::vector<std::vector<double>> ss(samples.size(), std::vector<double>(n_total));
@@ -354,7 +405,7 @@ int main(int argc, char **argv)
                     std::string text = HEADER;
                     for (int64_t q = A.seg[w]; q < A.seg[w + 1]; ++q) {
                         if (q > A.seg[w]) text += "\n";
-                        text += A.original[(size_t)A.order[(size_t)q]];
+                        text += A.original((size_t)A.order[(size_t)q]);
                     }
                     write_text(dir + "/" + A.name, text);
                 }

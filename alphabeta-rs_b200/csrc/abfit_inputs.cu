@@ -8,6 +8,8 @@
 //   Chromosome::try_from                        src/methylation_site.rs:57-68
 //   Pedigree::build                             src/pedigree.rs:92-193
 //   DMatrix::convert (shortest path, t0 rule)   src/pedigree.rs:264-337
+#include <atomic>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +20,8 @@
 #include <queue>
 #include <sstream>
 #include <string>
+#include <string_view>
+#include <thread>
 #include <vector>
 
 #include "abfit_internal.h"
@@ -41,7 +45,7 @@ std::vector<std::string> split_any(const std::string &s, const char *seps)
 }
 
 // <u32 as FromStr>: optional '+', ASCII digits, no overflow
-bool parse_u32(const std::string &s, uint32_t &v)
+bool parse_u32(std::string_view s, uint32_t &v)
 {
     size_t i = (!s.empty() && s[0] == '+') ? 1 : 0;
     if (i >= s.size()) return false;
@@ -55,40 +59,63 @@ bool parse_u32(const std::string &s, uint32_t &v)
     return true;
 }
 
-// <f64 as FromStr>: [+-] (digits [. digits] | . digits) [e[+-]digits] | inf | infinity | nan  (case-insensitive words)
-bool parse_f64(const std::string &s, double &v)
+inline bool is_digit(char c) { return c >= '0' && c <= '9'; }
+inline bool word_is(std::string_view s, const char *w)  // ASCII case-insensitive
+{
+    size_t k = 0;
+    for (; k < s.size() && w[k]; ++k)
+        if ((char)(s[k] | 0x20) != w[k]) return false;
+    return k == s.size() && !w[k];
+}
+
+// <f64 as FromStr>: [+-] (digits [. digits] | . digits) [e[+-]digits] | inf | infinity | nan  (case-insensitive words).
+// The grammar is checked here; the value comes from std::from_chars (correctly rounded, like Rust's and glibc's
+// strtod), with strtod as the fallback for what from_chars reports as out of range (Rust: inf / 0 / subnormal).
+bool parse_f64(std::string_view s, double &v)
 {
     size_t i = 0;
-    if (i < s.size() && (s[i] == '+' || s[i] == '-')) ++i;
-    std::string w;
-    for (size_t k = i; k < s.size(); ++k) w += (char)std::tolower((unsigned char)s[k]);
-    if (w == "inf" || w == "infinity" || w == "nan") {
-        v = std::strtod(s.c_str(), nullptr);
+    bool neg = false;
+    if (i < s.size() && (s[i] == '+' || s[i] == '-')) neg = s[i] == '-', ++i;
+    const std::string_view w = s.substr(i);
+    if (word_is(w, "inf") || word_is(w, "infinity")) {
+        v = neg ? -HUGE_VAL : HUGE_VAL;
         return true;
     }
+    if (word_is(w, "nan")) {
+        v = std::strtod(neg ? "-nan" : "nan", nullptr);
+        return true;
+    }
+    const size_t num0 = i;
     size_t nd = 0;
-    while (i < s.size() && std::isdigit((unsigned char)s[i])) ++i, ++nd;
+    while (i < s.size() && is_digit(s[i])) ++i, ++nd;
     if (i < s.size() && s[i] == '.') {
         ++i;
-        while (i < s.size() && std::isdigit((unsigned char)s[i])) ++i, ++nd;
+        while (i < s.size() && is_digit(s[i])) ++i, ++nd;
     }
     if (nd == 0) return false;
     if (i < s.size() && (s[i] == 'e' || s[i] == 'E')) {
         ++i;
         if (i < s.size() && (s[i] == '+' || s[i] == '-')) ++i;
         size_t ne = 0;
-        while (i < s.size() && std::isdigit((unsigned char)s[i])) ++i, ++ne;
+        while (i < s.size() && is_digit(s[i])) ++i, ++ne;
         if (ne == 0) return false;
     }
     if (i != s.size()) return false;
-    v = std::strtod(s.c_str(), nullptr);  // glibc: correctly rounded, like Rust's
+    double mag;
+    const auto r = std::from_chars(s.data() + num0, s.data() + s.size(), mag);
+    if (r.ec == std::errc() && r.ptr == s.data() + s.size()) {
+        v = neg ? -mag : mag;
+        return true;
+    }
+    const std::string z(s);
+    v = std::strtod(z.c_str(), nullptr);
     return true;
 }
 
 // Chromosome::try_from: Numbered(n) -> n, Mitochondrial -> 256, Chloroplast -> 257
-bool parse_chromosome(std::string s, int32_t &c)
+bool parse_chromosome(std::string_view s, int32_t &c)
 {
-    while (s.rfind("chr", 0) == 0) s = s.substr(3);  // trim_start_matches("chr")
+    while (s.substr(0, 3) == "chr") s.remove_prefix(3);  // trim_start_matches("chr")
     if (s == "M") { c = 256; return true; }
     if (s == "C") { c = 257; return true; }
     uint32_t v;
@@ -107,8 +134,9 @@ struct Site {
 
 uint8_t status_of(char c) { return c == 'M' ? 2 : c == 'I' ? 1 : 0; }  // anything else parses as U (with a warning)
 
-bool cg_fields(const std::vector<std::string> &f, size_t i_chr, const std::string &start, const std::string *end,
-               size_t i_strand, size_t i_cm, size_t i_ct, size_t i_post, size_t i_status, size_t i_lvl, bool invert, Site &o)
+typedef std::string_view SV;
+bool cg_fields(const SV *f, size_t i_chr, SV start, const SV *end, size_t i_strand, size_t i_cm, size_t i_ct, size_t i_post,
+               size_t i_status, size_t i_lvl, bool invert, Site &o)
 {
     uint32_t cm, ct;
     if (!parse_chromosome(f[i_chr], o.chromosome)) return false;
@@ -127,15 +155,32 @@ bool cg_fields(const std::vector<std::string> &f, size_t i_chr, const std::strin
     return true;
 }
 
-// the six formats, tried in the reference's order; 4-field lines all end in the chromatin-state reading
-bool parse_methylome_line(const std::string &line, bool invert, Site &o)
+// splits like str::split: n separators -> n + 1 fields; the first `cap` fields are stored, all are counted
+template <class IsSep>
+inline int split_view(SV line, IsSep is_sep, SV *out, int cap)
 {
-    const std::vector<std::string> f = split_any(line, "\t");
-    if (f.size() == 9 && f[3] == "CG" && cg_fields(f, 0, f[1], nullptr, 2, 4, 5, 6, 7, 8, invert, o)) return true;
-    if (f.size() == 10 && f[3] == "CG" && cg_fields(f, 0, f[1], nullptr, 2, 4, 5, 6, 7, 8, invert, o)) return true;
-    if (f.size() == 11 && f[3] == "CG" && cg_fields(f, 0, f[1], &f[2], 5, 6, 7, 8, 9, 10, invert, o)) return true;
-    const std::vector<std::string> g = split_any(line, "\t ");
-    if (g.size() == 4) {
+    int n = 0;
+    size_t b = 0;
+    for (size_t i = 0; i <= line.size(); ++i)
+        if (i == line.size() || is_sep(line[i])) {
+            if (n < cap) out[n] = line.substr(b, i - b);
+            ++n;
+            b = i + 1;
+        }
+    return n;
+}
+
+// the six formats, tried in the reference's order; 4-field lines all end in the chromatin-state reading.
+// No allocation per line: the methylome files of one run hold 10^8-10^9 lines.
+bool parse_methylome_line(SV line, bool invert, Site &o)
+{
+    SV f[12];
+    const int nf = split_view(line, [](char c) { return c == '\t'; }, f, 12);
+    if (nf == 9 && f[3] == "CG" && cg_fields(f, 0, f[1], nullptr, 2, 4, 5, 6, 7, 8, invert, o)) return true;
+    if (nf == 10 && f[3] == "CG" && cg_fields(f, 0, f[1], nullptr, 2, 4, 5, 6, 7, 8, invert, o)) return true;
+    if (nf == 11 && f[3] == "CG" && cg_fields(f, 0, f[1], &f[2], 5, 6, 7, 8, 9, 10, invert, o)) return true;
+    SV g[4];
+    if (split_view(line, [](char c) { return c == '\t' || c == ' '; }, g, 4) == 4) {
         if (parse_chromosome(g[0], o.chromosome) && parse_u32(g[1], o.start) && parse_u32(g[2], o.end)) {
             o.strand = 0;
             o.posteriormax = 0.0;
@@ -147,13 +192,46 @@ bool parse_methylome_line(const std::string &line, bool invert, Site &o)
     return false;
 }
 
+// One chunk of a file image, lines split like BufRead::lines ('\n'; one trailing '\r' stripped).
+struct ParsedChunk {
+    std::vector<abfit_cg_site> sites;
+    std::vector<double> post, lvl;
+    std::vector<uint8_t> status;
+    std::vector<int64_t> off;
+    std::vector<int32_t> len;
+};
+void parse_chunk(const char *buf, int64_t lo, int64_t hi, bool invert, bool want_lines, ParsedChunk &out)
+{
+    Site s;
+    int64_t b = lo;
+    while (b < hi) {
+        const char *nl = static_cast<const char *>(std::memchr(buf + b, '\n', (size_t)(hi - b)));
+        const int64_t e = nl ? (int64_t)(nl - buf) : hi;
+        int64_t n = e - b;
+        if (n > 0 && buf[b + n - 1] == '\r') --n;
+        if (parse_methylome_line(SV(buf + b, (size_t)n), invert, s)) {
+            out.sites.push_back(abfit_cg_site{s.chromosome, s.start, s.end, s.strand});
+            out.post.push_back(s.posteriormax);
+            out.lvl.push_back(s.meth_lvl);
+            out.status.push_back(s.status);
+            if (want_lines) {
+                out.off.push_back(b);
+                out.len.push_back((int32_t)n);
+            }
+        }
+        b = e + 1;
+    }
+}
+
 bool read_file(const char *path, std::string &out)
 {
-    std::ifstream f(path, std::ios::binary);
+    FILE *f = std::fopen(path, "rb");
     if (!f) return false;
-    std::ostringstream ss;
-    ss << f.rdbuf();
-    out = ss.str();
+    out.clear();
+    char buf[1 << 16];
+    size_t n;
+    while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, n);
+    std::fclose(f);
     return true;
 }
 
@@ -307,6 +385,84 @@ int abfit_parse_methylome_line(const char *line, int32_t invert_strand, abfit_cg
     return 0;
 }
 
+static unsigned host_threads()
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char *e = getenv("ABFIT_HOST_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+    return hw ? hw : 1;
+}
+
+// max_threads: upper bound for this call (callers that already run one call per file on their own threads pass their share)
+static int parse_buffer(const char *buf, int64_t len, int32_t invert_strand, int32_t skip_first_line, int64_t capacity,
+                        abfit_cg_site *sites, double *posterior_max, uint8_t *status, double *meth_lvl, int64_t *line_off,
+                        int32_t *line_len, int64_t *n_out, unsigned max_threads, std::string *err)
+{
+    if ((!buf && len > 0) || len < 0 || !n_out || capacity < 0) return ABFIT_ERR_ARG;
+    *n_out = 0;
+    int64_t lo = 0;
+    if (skip_first_line) {
+        const char *nl = len > 0 ? static_cast<const char *>(std::memchr(buf, '\n', (size_t)len)) : nullptr;
+        lo = nl ? (int64_t)(nl - buf) + 1 : len;
+    }
+    // chunks of ~4 MB cut at line ends, parsed by up to 16 threads, concatenated in file order
+    const int64_t body = len - lo;
+    const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(std::max(1u, max_threads), 16u), body / (1 << 20)));
+    const int n_chunks = n_thr == 1 ? 1 : (int)std::min<int64_t>(4096, std::max<int64_t>(n_thr, body / (4 << 20)));
+    std::vector<int64_t> cut(n_chunks + 1, len);
+    cut[0] = lo;
+    for (int c = 1; c < n_chunks; ++c) {
+        int64_t at = std::max(cut[c - 1], lo + body * c / n_chunks);
+        const char *nl = at < len ? static_cast<const char *>(std::memchr(buf + at, '\n', (size_t)(len - at))) : nullptr;
+        cut[c] = nl ? (int64_t)(nl - buf) + 1 : len;
+    }
+    const bool want_lines = line_off || line_len;
+    std::vector<ParsedChunk> parts(n_chunks);
+    if (n_thr == 1) {
+        for (int c = 0; c < n_chunks; ++c) parse_chunk(buf, cut[c], cut[c + 1], invert_strand != 0, want_lines, parts[c]);
+    } else {
+        std::atomic<int> next{0};
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_thr; ++t)
+            th.emplace_back([&]() {
+                for (int c; (c = next.fetch_add(1)) < n_chunks;)
+                    parse_chunk(buf, cut[c], cut[c + 1], invert_strand != 0, want_lines, parts[c]);
+            });
+        for (auto &x : th) x.join();
+    }
+    int64_t total = 0;
+    for (auto &pc : parts) total += (int64_t)pc.sites.size();
+    *n_out = total;
+    if (!sites && !posterior_max && !status && !meth_lvl && !want_lines) return ABFIT_OK;  // counting call
+    if (total > capacity) {
+        if (err) *err = "abfit_parse_methylome_buffer: " + std::to_string(total) + " sites, room for " + std::to_string(capacity);
+        return ABFIT_ERR_ARG;
+    }
+    int64_t at = 0;
+    for (auto &pc : parts) {
+        const size_t n = pc.sites.size();
+        if (n == 0) continue;
+        if (sites) std::memcpy(sites + at, pc.sites.data(), n * sizeof(abfit_cg_site));
+        if (posterior_max) std::memcpy(posterior_max + at, pc.post.data(), n * sizeof(double));
+        if (status) std::memcpy(status + at, pc.status.data(), n);
+        if (meth_lvl) std::memcpy(meth_lvl + at, pc.lvl.data(), n * sizeof(double));
+        if (line_off) std::memcpy(line_off + at, pc.off.data(), n * sizeof(int64_t));
+        if (line_len) std::memcpy(line_len + at, pc.len.data(), n * sizeof(int32_t));
+        at += (int64_t)n;
+    }
+    return ABFIT_OK;
+}
+
+int abfit_parse_methylome_buffer(const char *buf, int64_t len, int32_t invert_strand, int32_t skip_first_line, int64_t capacity,
+                                 abfit_cg_site *sites, double *posterior_max, uint8_t *status, double *meth_lvl,
+                                 int64_t *line_off, int32_t *line_len, int64_t *n_out)
+{
+    std::string err;
+    const int rc = parse_buffer(buf, len, invert_strand, skip_first_line, capacity, sites, posterior_max, status, meth_lvl, line_off,
+                                line_len, n_out, host_threads(), &err);
+    if (rc && !err.empty()) abfit::set_error(err);
+    return rc;
+}
+
 int abfit_pedigree_build(abfit_ctx *ctx, const char *nodelist_path, const char *edgelist_path, double posterior_max_filter,
                          abfit_pedigree **out)
 {
@@ -318,21 +474,44 @@ int abfit_pedigree_build(abfit_ctx *ctx, const char *nodelist_path, const char *
     const int S = (int)g.meas.size();
     std::vector<std::vector<uint8_t>> st(S);
     std::vector<std::vector<double>> po(S), me(S);
-    for (int s = 0; s < S; ++s) {
-        std::ifstream f(g.meas[s].file);
-        if (!f) {
-            abfit::set_error("Could not open node file: " + g.meas[s].file);
-            return ABFIT_ERR_ARG;
-        }
-        std::string line;
-        Site site;
-        while (std::getline(f, line)) {
-            if (!line.empty() && line.back() == '\r') line.pop_back();  // BufRead::lines strips \r\n
-            if (!parse_methylome_line(line, false, site)) continue;
-            st[s].push_back(site.status);
-            po[s].push_back(site.posteriormax);
-            me[s].push_back(site.meth_lvl);
-        }
+    // one file per host thread (the reference: rayon, src/pedigree.rs:137-157), the parser splits a file over the rest
+    {
+        const unsigned hw = host_threads();
+        const unsigned outer = (unsigned)std::max(1, std::min<int>(std::min<int>(S, (int)hw), 16));
+        const unsigned inner = std::max(1u, hw / outer);
+        std::vector<std::string> errs(S);
+        std::vector<int> rcs(S, 0);
+        std::atomic<int> next{0};
+        auto load = [&](int s) {
+            std::string image;
+            if (!read_file(g.meas[s].file.c_str(), image)) {
+                errs[s] = "Could not open node file: " + g.meas[s].file;
+                rcs[s] = ABFIT_ERR_ARG;
+                return;
+            }
+            // every line that parses as a CG site, header row included in the attempt (BufRead::lines strips \r\n)
+            int64_t cap = 1, n = 0;
+            for (char ch : image) cap += ch == '\n';
+            st[s].resize((size_t)cap);
+            po[s].resize((size_t)cap);
+            me[s].resize((size_t)cap);
+            rcs[s] = parse_buffer(image.data(), (int64_t)image.size(), 0, 0, cap, nullptr, po[s].data(), st[s].data(), me[s].data(),
+                                  nullptr, nullptr, &n, inner, &errs[s]);
+            st[s].resize((size_t)n);
+            po[s].resize((size_t)n);
+            me[s].resize((size_t)n);
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < outer; ++t)
+            pool.emplace_back([&]() {
+                for (int s; (s = next.fetch_add(1)) < S;) load(s);
+            });
+        for (auto &th : pool) th.join();
+        for (int s = 0; s < S; ++s)
+            if (rcs[s]) {
+                abfit::set_error(errs[s]);
+                return rcs[s];
+            }
     }
     std::unique_ptr<abfit_pedigree> ped(new abfit_pedigree());
     ped->n_samples = S;

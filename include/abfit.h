@@ -326,6 +326,16 @@ int abfit_parse_methylome_line(const char *line, int32_t invert_strand, abfit_cg
                                int32_t *status_out, double *meth_lvl_out);
 /* Pedigree::build (src/pedigree.rs:92-193) + DMatrix::convert (:264-337): nodelist + edgelist + the methylome files the
  * nodelist names (relative to the CWD, as in the reference) -> pedigree rows [t0, t1, t2, D] and p0uu. */
+/* The same parser over a whole file image (the reference reads its methylome files line by line on rayon threads,
+ * src/extract.rs:75, src/windows.rs:310-330, src/pedigree.rs:137-157).  Lines are split like BufRead::lines ('\n', one
+ * trailing '\r' stripped); skip_first_line != 0 drops the header row unparsed (Windows::extract, src/windows.rs:322).
+ * Every output may be NULL; each has room for `capacity` entries (the number of lines is always enough).  status: 0 U /
+ * 1 I / 2 M.  line_off / line_len: where each accepted line sits in buf.  *n_out = accepted lines, in file order; with
+ * all outputs NULL the call only counts.  Host only, multi-threaded (ABFIT_HOST_THREADS overrides the thread count).
+ * Returns ABFIT_ERR_ARG when capacity is too small (*n_out is still set). */
+int abfit_parse_methylome_buffer(const char *buf, int64_t len, int32_t invert_strand, int32_t skip_first_line, int64_t capacity,
+                                 abfit_cg_site *sites, double *posterior_max, uint8_t *status, double *meth_lvl,
+                                 int64_t *line_off, int32_t *line_len, int64_t *n_out);
 typedef struct abfit_pedigree abfit_pedigree;
 int abfit_pedigree_build(abfit_ctx *ctx, const char *nodelist_path, const char *edgelist_path, double posterior_max_filter,
                          abfit_pedigree **out);

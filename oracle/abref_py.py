@@ -234,14 +234,15 @@ def parse_methylome_line(line: str, invert_strand: bool = False):
             "posteriormax": _f64_rust(post), "status": _status(status), "meth_lvl": _f64_rust(lvl), "original": line,
         }
 
+    # `location.parse::<u32>()? + 1` (src/methylation_site.rs:166,210): a release build wraps at u32::MAX
     try:
         if len(f) == 9 and f[3] == "CG":
-            return mk(f[0], _u32(f[1]), _u32(f[1]) + 1, f[2], f[6], f[7], f[8], f[4], f[5])
+            return mk(f[0], _u32(f[1]), (_u32(f[1]) + 1) & 0xFFFFFFFF, f[2], f[6], f[7], f[8], f[4], f[5])
     except ValueError:
         pass
     try:
         if len(f) == 10 and f[3] == "CG":
-            return mk(f[0], _u32(f[1]), _u32(f[1]) + 1, f[2], f[6], f[7], f[8], f[4], f[5])
+            return mk(f[0], _u32(f[1]), (_u32(f[1]) + 1) & 0xFFFFFFFF, f[2], f[6], f[7], f[8], f[4], f[5])
     except ValueError:
         pass
     try:

@@ -53,6 +53,100 @@ def test_every_golden_methylome_line_parses_like_the_oracle(ab, oracle):
     assert n > 10000
 
 
+def _fuzz_lines(rng, n):
+    """methylome-like lines with the grammar's corner cases mixed in (numbers Rust accepts and rejects, field counts of
+    all six formats, separators, prefixes)"""
+    nums = ["0", "1", "0.9999", ".5", "5.", "+0.25", "-0.0", "1e-3", "1E+2", "1e", "e5", "0x10", "inf", "-Infinity", "NaN", "nan ",
+            "1e999", "1e-999", "4.9e-324", "0.1234567890123456789", "12345678901234567890", "1_0", "", " 1", "1.2.3", "+", "-",
+            "+.e1", "9007199254740993", "0.30000000000000004", "2.2250738585072011e-308"]
+    ints = ["0", "7", "+12", "-3", "4294967295", "4294967296", "00012", "1.0", "", "12a"]
+    chroms = ["1", "5", "chr2", "chrchr3", "chr", "M", "C", "chrM", "X", "255", "256", "0", "+4", "01"]
+    ctx = ["CG", "CHH", "CHG", "cg", "CG "]
+    out = []
+    for _ in range(n):
+        k = rng.integers(0, 6)
+        pick = lambda a: a[rng.integers(0, len(a))]
+        if k == 0:
+            f = [pick(chroms), pick(ints), pick(["+", "-", "*", ""]), pick(ctx), pick(ints), pick(ints), pick(nums), pick(["U", "M", "I", "", "Q", "MU"]), pick(nums)]
+        elif k == 1:
+            f = [pick(chroms), pick(ints), pick(["+", "-"]), pick(ctx), pick(ints), pick(ints), pick(nums), pick(["U", "M", "I"]), pick(nums), "CGA"]
+        elif k == 2:
+            f = [pick(chroms), pick(ints), pick(ints), "x", "y", pick(["+", "-"]), pick(ints), pick(ints), pick(nums), pick(["U", "M", "I"]), pick(nums)]
+            f[3] = pick(ctx)
+        elif k == 3:
+            f = [pick(chroms), pick(ints), pick(ints), pick(nums)]
+        elif k == 4:
+            f = [pick(chroms) for _ in range(rng.integers(0, 14))]
+        else:
+            f = [pick(chroms), pick(ints), "+", "CG", "1", "2", "0.5", "U", "0.5"]
+        sep = "\t" if rng.random() < 0.85 else pick([" ", "\t\t", ","])
+        out.append(sep.join(f))
+    return out
+
+
+def test_parser_fuzz_against_the_oracle(ab, oracle):
+    rng = np.random.default_rng(4242)
+    lines = _fuzz_lines(rng, 6000)
+    accepted = 0
+    for line in lines:
+        want = oracle.parse_methylome_line(line)
+        got = ab.parse_methylome_line(line)
+        if want is None:
+            assert got is None, line
+            continue
+        accepted += 1
+        assert got is not None, line
+        for k in ("start", "end", "status"):
+            assert got[k] == want[k], (line, k)
+        for k in ("posteriormax", "meth_lvl"):  # same bits, NaN included
+            assert np.float64(got[k]).tobytes() == np.float64(want[k]).tobytes() or (np.isnan(got[k]) and np.isnan(want[k])), (line, k)
+    assert 500 < accepted < 5500
+
+
+@pytest.mark.parametrize("newline,trailing,threads", [("\n", True, None), ("\r\n", True, "1"), ("\n", False, "3"), ("\r\n", False, None)])
+def test_methylome_buffer_parser_equals_the_line_parser(ab, oracle, monkeypatch, newline, trailing, threads):
+    """abfit_parse_methylome_buffer (whole file image, several threads, chunk cuts at line ends) == the per-line parser
+    applied to BufRead::lines of the same bytes: golden files, a 12 MB fuzz image, header skipping, CRLF, missing final
+    newline, empty input"""
+    if threads:
+        monkeypatch.setenv("ABFIT_HOST_THREADS", threads)
+    rng = np.random.default_rng(77)
+    golden = open(os.path.join(GOLDEN, "methylome", "G0.txt")).read().split("\n")
+    golden = [l for l in golden if l]
+    fuzz = _fuzz_lines(rng, 3000)
+    big = (golden + fuzz) * 40  # ~ 230 000 lines, > 8 MB: several chunks per thread
+    for lines, skip in ((golden, True), (golden, False), (fuzz, False), (big, True), ([], False), ([""], True), (["1\t5\t+\tCG\t0\t8\t0.9\tU\t0.1"], False)):
+        data = newline.join(lines) + (newline if trailing and lines else "")
+        got = ab.parse_methylome_buffer(data.encode(), skip_first_line=skip, want_lines=True)
+        want, want_lines = [], []
+        for i, line in enumerate(lines):
+            if skip and i == 0:
+                continue
+            s = ab.parse_methylome_line(line)
+            if s is not None:
+                want.append(s)
+                want_lines.append(line)
+        assert len(got["sites"]) == len(want)
+        if not want:
+            continue
+        assert np.array_equal(got["sites"]["chromosome"], [w["chromosome"] for w in want])
+        assert np.array_equal(got["sites"]["start"], [w["start"] for w in want])
+        assert np.array_equal(got["sites"]["end"], [w["end"] for w in want])
+        assert np.array_equal(got["sites"]["strand"], [w["strand"] for w in want])
+        assert np.array_equal(got["status"], [w["status"] for w in want])
+        assert np.array_equal(got["posteriormax"], np.array([w["posteriormax"] for w in want]), equal_nan=True)
+        assert np.array_equal(got["meth_lvl"], np.array([w["meth_lvl"] for w in want]), equal_nan=True)
+        raw = data.encode()
+        for j in (0, len(want) // 2, len(want) - 1):
+            o, n = int(got["line_off"][j]), int(got["line_len"][j])
+            assert raw[o:o + n].decode() == want_lines[j]
+    # inverted strand, and a capacity that is too small
+    data = "\n".join(golden).encode()
+    inv = ab.parse_methylome_buffer(data, invert_strand=True, skip_first_line=True)
+    fwd = ab.parse_methylome_buffer(data, skip_first_line=True)
+    assert np.array_equal(inv["sites"]["strand"], -fwd["sites"]["strand"]) and len(fwd["sites"]) == 500
+
+
 @pytest.mark.gpu
 def test_pedigree_build_matches_oracle_and_golden(ab, ctx, oracle, monkeypatch, tmp_path):
     """C1: data/nodelist.txt + edgelist.txt -> data/pedigree_generated.txt (bit-exact), and the 13-sample desired_output set"""
