@@ -35,6 +35,7 @@
 #include <dirent.h>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <sys/stat.h>
@@ -101,6 +102,25 @@ static bool read_whole_file(const std::string &path, std::string &out)
     while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, n);
     std::fclose(f);
     return true;
+}
+
+// independent iterations on the host threads (blocks of 8 from a shared counter)
+template <class F>
+static void parallel_for(size_t n, F f)
+{
+    const size_t nt = std::min<size_t>(std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 32), (n + 7) / 8);
+    if (nt <= 1) {
+        for (size_t i = 0; i < n; ++i) f(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < nt; ++t)
+        pool.emplace_back([&]() {
+            for (size_t b; (b = next.fetch_add(8)) < n;)
+                for (size_t i = b; i < std::min(n, b + 8); ++i) f(i);
+        });
+    for (auto &th : pool) th.join();
 }
 
 int main(int argc, char **argv)
@@ -484,16 +504,18 @@ int main(int argc, char **argv)
     const size_t P = (size_t)S * (S - 1) / 2;
     std::vector<uint8_t> st((size_t)S * L);
     std::vector<double> po((size_t)S * L), me((size_t)S * L);
-    for (int s = 0; s < S; ++s) {
+    parallel_for((size_t)S * 8, [&](size_t job) {  // eight slices of the window list per sample
+        const size_t s = job / 8, part = job % 8;
         const Sample &A = samples[sample_of[s]];
-        int64_t o = 0;
-        for (int w : usable)
-            for (int64_t q = A.seg[w]; q < A.seg[w + 1]; ++q, ++o) {
-                st[(size_t)s * L + o] = A.status[(size_t)A.order[q]];
-                po[(size_t)s * L + o] = A.post[(size_t)A.order[q]];
-                me[(size_t)s * L + o] = A.meth[(size_t)A.order[q]];
+        const size_t k0 = usable.size() * part / 8, k1 = usable.size() * (part + 1) / 8;
+        int64_t o = seg[k0];
+        for (size_t k = k0; k < k1; ++k)
+            for (int64_t q = A.seg[usable[k]]; q < A.seg[usable[k] + 1]; ++q, ++o) {
+                st[s * L + o] = A.status[(size_t)A.order[q]];
+                po[s * L + o] = A.post[(size_t)A.order[q]];
+                me[s * L + o] = A.meth[(size_t)A.order[q]];
             }
-    }
+    });
     std::vector<double> D((size_t)std::max(W, 1) * std::max<size_t>(P, 1)), p0uu(std::max(W, 1));
     if (W > 0 && abfit_divergence_multi(ctxs.data(), (int32_t)ctxs.size(), st.data(), po.data(), me.data(), S, L, seg.data(), W, 0.99,
                                         D.data(), nullptr, nullptr, p0uu.data(), nullptr, nullptr)) {
@@ -503,48 +525,59 @@ int main(int argc, char **argv)
     // one problem per window whose pedigree has no NaN (the reference panics on those, src/ab_neutral.rs:28)
     std::vector<int> fitted;
     std::vector<std::vector<double>> peds;
-    for (int k = 0; k < W; ++k) {
-        std::vector<double> ped((size_t)n_pairs * 4);
-        bool ok = n_pairs > 0 && p0uu[k] == p0uu[k];
-        for (int r = 0; r < n_pairs; ++r) {
-            const int i = (int)pairs[5 * r], j = (int)pairs[5 * r + 1];
-            const size_t p = (size_t)i * S - (size_t)i * (i + 1) / 2 + (size_t)(j - i - 1);
-            ped[4 * r + 0] = pairs[5 * r + 2];
-            ped[4 * r + 1] = pairs[5 * r + 3];
-            ped[4 * r + 2] = pairs[5 * r + 4];
-            ped[4 * r + 3] = D[(size_t)k * P + p];
-            ok &= ped[4 * r + 3] == ped[4 * r + 3];
+    {
+        std::vector<std::vector<double>> all((size_t)W);
+        std::vector<uint8_t> good((size_t)W, 0);
+        parallel_for((size_t)W, [&](size_t k) {
+            std::vector<double> ped((size_t)n_pairs * 4);
+            bool ok = n_pairs > 0 && p0uu[k] == p0uu[k];
+            for (int r = 0; r < n_pairs; ++r) {
+                const int i = (int)pairs[5 * r], j = (int)pairs[5 * r + 1];
+                const size_t p = (size_t)i * S - (size_t)i * (i + 1) / 2 + (size_t)(j - i - 1);
+                ped[4 * r + 0] = pairs[5 * r + 2];
+                ped[4 * r + 1] = pairs[5 * r + 3];
+                ped[4 * r + 2] = pairs[5 * r + 4];
+                ped[4 * r + 3] = D[k * P + p];
+                ok &= ped[4 * r + 3] == ped[4 * r + 3];
+            }
+            good[k] = ok;
+            if (ok) all[k] = std::move(ped);
+        });
+        for (int k = 0; k < W; ++k) {
+            if (!good[(size_t)k]) {
+                std::printf("Error: Model failed: window %d has too few valid sites (NaN divergence)\n", usable[k]);
+                continue;
+            }
+            fitted.push_back(k);
+            peds.push_back(std::move(all[(size_t)k]));
         }
-        if (!ok) {
-            std::printf("Error: Model failed: window %d has too few valid sites (NaN divergence)\n", usable[k]);
-            continue;
-        }
-        fitted.push_back(k);
-        peds.push_back(std::move(ped));
     }
     const int F = (int)fitted.size();
     const int n = (int)iterations;
     std::vector<abfit_problem> probs(F);
-    std::vector<double> simplices((size_t)F * n * 20), rows((size_t)F * n * 7), analysis((size_t)F * 32);
-    std::vector<int32_t> idx((size_t)F * n * n_pairs), status(F);
+    // (the two big inputs are written in full by the generators below: no zero-fill of gigabytes first)
+    std::unique_ptr<double[]> simplices(new double[std::max<size_t>(1, (size_t)F * n * 20)]);
+    std::unique_ptr<int32_t[]> idx(new int32_t[std::max<size_t>(1, (size_t)F * n * n_pairs)]);
+    std::vector<double> rows((size_t)F * n * 7), analysis((size_t)F * 32);
+    std::vector<int32_t> status(F);
     std::vector<abfit_fit> best(F);
     std::vector<uint64_t> ids(F);  // every window's generator key is its position in the genome-wide window list
-    for (int f = 0; f < F; ++f) {
+    parallel_for((size_t)F, [&](size_t f) {
         const int k = fitted[f];
         ids[f] = (uint64_t)usable[k];
         probs[f] = abfit_problem{peds[f].data(), n_pairs, p0uu[k], p0uu[k], 1.0};
         double max_div = peds[f][3];
         for (int r = 1; r < n_pairs; ++r) max_div = std::max(max_div, peds[f][4 * r + 3]);
-        abfit_gen_start_simplices(seed, (uint64_t)usable[k], n, max_div, simplices.data() + (size_t)f * n * 20);
-        abfit_gen_resample_idx(seed, (uint64_t)usable[k], n, n_pairs, idx.data() + (size_t)f * n * n_pairs);
-    }
+        abfit_gen_start_simplices(seed, (uint64_t)usable[k], n, max_div, simplices.get() + (size_t)f * n * 20);
+        abfit_gen_resample_idx(seed, (uint64_t)usable[k], n, n_pairs, idx.get() + (size_t)f * n * n_pairs);
+    });
     // start simplices, resample indices and vary vertices of a window are all keyed by (seed, window id): its result
     // does not depend on which other windows are fitted with it, nor on how the windows are sharded over the GPUs
     // progress::multi(total_steps) (src/cli/metaprofile.rs:46): one step per window; the windows are fitted in one batched
     // call, so the bar stands at the windows prepared so far while the GPUs work and jumps to the end afterwards
     progress::Bar pb("Progress ", (unsigned long long)n_total, true);
     pb.set((unsigned long long)(n_total - F));
-    if (F > 0 && abfit_alphabeta_batch_multi(ctxs.data(), (int32_t)ctxs.size(), probs.data(), F, n, simplices.data(), n, idx.data(), seed,
+    if (F > 0 && abfit_alphabeta_batch_multi(ctxs.data(), (int32_t)ctxs.size(), probs.data(), F, n, simplices.get(), n, idx.get(), seed,
                                              0, ids.data(), 10000, 1000, DBL_EPSILON, 0, best.data(), nullptr, nullptr,
                                              status.data(), rows.data(), analysis.data())) {
         std::printf("Error: %s\n", abfit_last_error());
