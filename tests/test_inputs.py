@@ -103,6 +103,39 @@ def test_parser_fuzz_against_the_oracle(ab, oracle):
     assert 500 < accepted < 5500
 
 
+def test_parser_f64_is_correctly_rounded(ab):
+    """<f64 as FromStr> is correctly rounded; so is Python's float().  20 000 random decimal strings (up to 25
+    significant digits, exponents across the whole range incl. subnormals, overflow to inf and underflow to 0) through
+    the whole-file parser, compared bit for bit"""
+    rng = np.random.default_rng(99)
+    texts = []
+    for _ in range(20000):
+        nd = int(rng.integers(1, 26))
+        digits = "".join(str(int(d)) for d in rng.integers(0, 10, nd))
+        k = int(rng.integers(0, nd + 1))
+        mant = digits[:k] + "." + digits[k:] if rng.random() < 0.8 else digits
+        if mant.startswith("."):
+            mant = mant if rng.random() < 0.5 else "0" + mant
+        form = rng.integers(0, 4)
+        if form == 0:
+            t = mant
+        elif form == 1:
+            t = mant + "e" + str(int(rng.integers(-30, 30)))
+        elif form == 2:
+            e = int(rng.integers(-345, 320))
+            t = mant + "E" + ("+" if e >= 0 and rng.random() < 0.3 else "") + str(e)
+        else:
+            t = mant + "e-" + str(int(rng.integers(290, 330)))
+        texts.append(("-" if rng.random() < 0.2 else "+" if rng.random() < 0.1 else "") + t)
+    data = "\n".join(f"1\t{i + 1}\t+\tCG\t0\t8\t{t}\tU\t{texts[-1 - i]}" for i, t in enumerate(texts)).encode()
+    got = ab.parse_methylome_buffer(data)
+    assert len(got["sites"]) == len(texts)
+    want = np.array([float(t) for t in texts])
+    assert got["posteriormax"].tobytes() == want.tobytes()
+    assert got["meth_lvl"].tobytes() == want[::-1].tobytes()
+    assert np.isinf(want).any() and (want == 0).any() and ((np.abs(want) < 2.3e-308) & (want != 0)).any()
+
+
 @pytest.mark.parametrize("newline,trailing,threads", [("\n", True, None), ("\r\n", True, "1"), ("\n", False, "3"), ("\r\n", False, None)])
 def test_methylome_buffer_parser_equals_the_line_parser(ab, oracle, monkeypatch, newline, trailing, threads):
     """abfit_parse_methylome_buffer (whole file image, several threads, chunk cuts at line ends) == the per-line parser
