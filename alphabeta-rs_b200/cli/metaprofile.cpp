@@ -278,6 +278,13 @@ int main(int argc, char **argv)
             S.meth.resize((size_t)n);
             S.line_off.resize(write_windows ? (size_t)n : 0);
             S.line_len.resize(write_windows ? (size_t)n : 0);
+            // (cap counted every line of the file, CG or not: give the difference back)
+            S.sites.shrink_to_fit();
+            S.status.shrink_to_fit();
+            S.post.shrink_to_fit();
+            S.meth.shrink_to_fit();
+            S.line_off.shrink_to_fit();
+            S.line_len.shrink_to_fit();
             if (!write_windows) std::string().swap(S.image);
         }
         S.dist.assign(n_total, 0);
