@@ -166,6 +166,12 @@ extern "C" {
                                ci_beta_hi: *const f64) -> c_int;
     /// `plot::bootstrap` (src/plot.rs:84-137): bootstrap.png from the bootstrap alphas and betas
     pub fn abfit_plot_bootstrap(path: *const c_char, alphas: *const f64, betas: *const f64, n: i32) -> c_int;
+    /// `MethylationSite::from_methylome_file_line` (src/methylation_site.rs:146-362) over a whole file image, in place of
+    /// the `BufRead::lines` loops of `Windows::extract` (src/windows.rs:310-330) and `Pedigree::build`
+    /// (src/pedigree.rs:137-157).  Every output may be null; `capacity` = number of lines is always enough.
+    pub fn abfit_parse_methylome_buffer(buf: *const c_char, len: i64, invert_strand: i32, skip_first_line: i32, capacity: i64,
+                                        sites: *mut abfit_cg_site, posterior_max: *mut f64, status: *mut u8,
+                                        meth_lvl: *mut f64, line_off: *mut i64, line_len: *mut i32, n_out: *mut i64) -> c_int;
 }
 
 /// Message of the last failed call on this thread.
