@@ -20,11 +20,9 @@
 // measured nodes being matched to the methylome files by file name; the windows looped over are those of
 // Windows::new (the reference's loop `(0..max).step_by(step)` can run one directory past them); seeded RNG.
 // Like the reference, a window that cannot be fitted prints an error and is skipped, and results.txt pairs the
-// i-th fitted window with the i-th distribution entry (src/cli/metaprofile.rs:76-77).  One more deliberate difference:
-// a window in which the samples list DIFFERENT numbers of sites is skipped with an error; the reference keeps it,
-// prints "Lengths do not match, all bets are off" and fits it with D = 0 for every pair of unequal length
-// (src/pedigree.rs:222-230) — `abfit_pedigree_build` (the `alphabeta` tool) reproduces that rule, the fused window
-// pipeline does not: its divergence call needs index-aligned sites, and a fit on zeros that "are off" helps nobody.
+// i-th fitted window with the i-th distribution entry (src/cli/metaprofile.rs:76-77).  A window in which the samples
+// list DIFFERENT numbers of sites is kept, as in the reference: "Lengths do not match, all bets are off", D = 0 for
+// every pair of unequal length (src/pedigree.rs:222-230; one console line per window here, one per pair there).
 #include <algorithm>
 #include <atomic>
 #include <cfloat>
@@ -492,42 +490,113 @@ int main(int argc, char **argv)
             std::printf("Error: %s\n", abfit_last_error());
             return 1;
         }
-    // windows whose samples all list the same number of sites go into one divergence call
-    std::vector<int> usable;
-    std::vector<int64_t> seg{0};
+    // Windows whose samples all list the same number of sites ("regular") go into ONE divergence call.  A window whose
+    // samples list different numbers of sites is kept, as in the reference: DMatrix::from prints "Lengths do not match, all
+    // bets are off" and leaves D = 0 for every pair of unequal length (src/pedigree.rs:222-230); pairs of equal length are
+    // compared index by index, every sample's methylation level comes from its own sites (one small divergence call per
+    // group of equally long samples of such a window, on the first device).
+    std::vector<int> usable;       // every window that gets a pedigree, in window order
+    std::vector<int> reg_of;       // usable index -> index among the regular windows, -1: unequal site counts
+    std::vector<int> reg_windows;  // the regular windows
+    std::vector<int64_t> seg{0};   // their segment offsets
+    auto win_len = [&](int s, int w) { return samples[sample_of[s]].seg[w + 1] - samples[sample_of[s]].seg[w]; };
     for (int w = 0; w < n_total; ++w) {
-        const int64_t len = samples[sample_of[0]].seg[w + 1] - samples[sample_of[0]].seg[w];
-        bool same = len > 0;
-        for (int s = 1; s < S; ++s) same &= samples[sample_of[s]].seg[w + 1] - samples[sample_of[s]].seg[w] == len;
-        if (!same) {
-            std::printf("Error: Model failed: window %d is empty or its samples list different numbers of sites\n", w);
+        const int64_t len = win_len(0, w);
+        bool same = true, any = len > 0;
+        for (int s = 1; s < S; ++s) {
+            same &= win_len(s, w) == len;
+            any |= win_len(s, w) > 0;
+        }
+        if (!any) {
+            std::printf("Error: Model failed: window %d is empty\n", w);
             continue;
         }
         usable.push_back(w);
-        seg.push_back(seg.back() + len);
+        if (same) {
+            reg_of.push_back((int)reg_windows.size());
+            reg_windows.push_back(w);
+            seg.push_back(seg.back() + len);
+        } else {
+            reg_of.push_back(-1);
+        }
     }
     const int64_t L = seg.back();
-    const int W = (int)usable.size();
+    const int W = (int)usable.size(), WR = (int)reg_windows.size();
     const size_t P = (size_t)S * (S - 1) / 2;
-    std::vector<uint8_t> st((size_t)S * L);
-    std::vector<double> po((size_t)S * L), me((size_t)S * L);
-    parallel_for((size_t)S * 8, [&](size_t job) {  // eight slices of the window list per sample
-        const size_t s = job / 8, part = job % 8;
-        const Sample &A = samples[sample_of[s]];
-        const size_t k0 = usable.size() * part / 8, k1 = usable.size() * (part + 1) / 8;
-        int64_t o = seg[k0];
-        for (size_t k = k0; k < k1; ++k)
-            for (int64_t q = A.seg[usable[k]]; q < A.seg[usable[k] + 1]; ++q, ++o) {
-                st[s * L + o] = A.status[(size_t)A.order[q]];
-                po[s * L + o] = A.post[(size_t)A.order[q]];
-                me[s * L + o] = A.meth[(size_t)A.order[q]];
+    std::vector<double> D((size_t)std::max(W, 1) * std::max<size_t>(P, 1), 0.0), p0uu(std::max(W, 1));
+    {
+        std::vector<uint8_t> st((size_t)S * L);
+        std::vector<double> po((size_t)S * L), me((size_t)S * L);
+        parallel_for((size_t)S * 8, [&](size_t job) {  // eight slices of the window list per sample
+            const size_t s = job / 8, part = job % 8;
+            const Sample &A = samples[sample_of[s]];
+            const size_t k0 = reg_windows.size() * part / 8, k1 = reg_windows.size() * (part + 1) / 8;
+            int64_t o = seg[k0];
+            for (size_t k = k0; k < k1; ++k)
+                for (int64_t q = A.seg[reg_windows[k]]; q < A.seg[reg_windows[k] + 1]; ++q, ++o) {
+                    st[s * L + o] = A.status[(size_t)A.order[q]];
+                    po[s * L + o] = A.post[(size_t)A.order[q]];
+                    me[s * L + o] = A.meth[(size_t)A.order[q]];
+                }
+        });
+        std::vector<double> Dr((size_t)std::max(WR, 1) * std::max<size_t>(P, 1)), p0r(std::max(WR, 1));
+        if (WR > 0 && abfit_divergence_multi(ctxs.data(), (int32_t)ctxs.size(), st.data(), po.data(), me.data(), S, L, seg.data(), WR,
+                                             0.99, Dr.data(), nullptr, nullptr, p0r.data(), nullptr, nullptr)) {
+            std::printf("Error: %s\n", abfit_last_error());
+            return 1;
+        }
+        for (int k = 0; k < W; ++k)
+            if (reg_of[k] >= 0) {
+                std::copy(Dr.begin() + (size_t)reg_of[k] * P, Dr.begin() + (size_t)(reg_of[k] + 1) * P, D.begin() + (size_t)k * P);
+                p0uu[k] = p0r[reg_of[k]];
             }
-    });
-    std::vector<double> D((size_t)std::max(W, 1) * std::max<size_t>(P, 1)), p0uu(std::max(W, 1));
-    if (W > 0 && abfit_divergence_multi(ctxs.data(), (int32_t)ctxs.size(), st.data(), po.data(), me.data(), S, L, seg.data(), W, 0.99,
-                                        D.data(), nullptr, nullptr, p0uu.data(), nullptr, nullptr)) {
-        std::printf("Error: %s\n", abfit_last_error());
-        return 1;
+    }
+    for (int k = 0; k < W; ++k) {
+        if (reg_of[k] >= 0) continue;
+        const int w = usable[k];
+        std::printf("Lengths do not match, all bets are off: window %d (pairs of samples with different site counts get D = 0)\n", w);
+        std::map<int64_t, std::vector<int>> by_len;
+        for (int s = 0; s < S; ++s) by_len[win_len(s, w)].push_back(s);
+        std::vector<double> level(S, 0.0);  // mean rc.meth.lvl of every sample's own sites (src/pedigree.rs:171-172)
+        for (auto &kv : by_len) {
+            const std::vector<int> &grp = kv.second;
+            const int G = (int)grp.size();
+            const int64_t len = kv.first;
+            if (len == 0) {
+                for (int s : grp) level[s] = 0.0 / 0.0;  // 0 / 0 = NaN, as in the reference
+                continue;
+            }
+            std::vector<uint8_t> gs((size_t)G * len);
+            std::vector<double> gp((size_t)G * len), gm((size_t)G * len);
+            for (int q = 0; q < G; ++q) {
+                const Sample &A = samples[sample_of[grp[q]]];
+                int64_t o = 0;
+                for (int64_t i = A.seg[w]; i < A.seg[w + 1]; ++i, ++o) {
+                    gs[(size_t)q * len + o] = A.status[(size_t)A.order[i]];
+                    gp[(size_t)q * len + o] = A.post[(size_t)A.order[i]];
+                    gm[(size_t)q * len + o] = A.meth[(size_t)A.order[i]];
+                }
+            }
+            const size_t PG = (size_t)G * (G - 1) / 2;
+            std::vector<double> Dg(std::max<size_t>(PG, 1)), methsum(G);
+            std::vector<int64_t> nvalid(G);
+            if (abfit_divergence(ctxs[0], gs.data(), gp.data(), gm.data(), G, len, nullptr, 1, 0.99, Dg.data(), nullptr, nullptr, nullptr,
+                                 methsum.data(), nvalid.data())) {
+                std::printf("Error: %s\n", abfit_last_error());
+                return 1;
+            }
+            size_t p = 0;
+            for (int a = 0; a < G; ++a) {
+                level[grp[a]] = methsum[a] / (double)nvalid[a];
+                for (int b = a + 1; b < G; ++b) {
+                    const int i = grp[a], j = grp[b];  // ascending sample order inside a group
+                    D[(size_t)k * P + (size_t)i * S - (size_t)i * (i + 1) / 2 + (size_t)(j - i - 1)] = Dg[p++];
+                }
+            }
+        }
+        double acc = 0.0;  // src/pedigree.rs:179-183
+        for (int s = 0; s < S; ++s) acc += 1.0 - level[s];
+        p0uu[k] = acc / (double)S;
     }
     // one problem per window whose pedigree has no NaN (the reference panics on those, src/ab_neutral.rs:28)
     std::vector<int> fitted;

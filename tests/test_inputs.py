@@ -258,9 +258,23 @@ def test_metaprofile_extraction_files_match_the_reference_output(tmp_path):
 
 
 @pytest.mark.gpu
-def test_metaprofile_cli_fused_pipeline(ab, ctx, oracle, tmp_path):
+@pytest.mark.parametrize("ragged", [False, True])
+def test_metaprofile_cli_fused_pipeline(ab, ctx, oracle, tmp_path, ragged):
     """`metaprofile ... alphabeta` on the example methylomes with an annotation that covers them: results.txt and raw.npy
-    equal the reference's per-window loop restated with the oracle (same seeds)"""
+    equal the reference's per-window loop restated with the oracle (same seeds).  ragged: two CG lines are taken out of
+    one sample's file, so some windows list different numbers of sites per sample — the reference keeps those windows
+    with D = 0 for every pair of unequal length (DMatrix::from, src/pedigree.rs:222-230)"""
+    meth_dir = os.path.join(GOLDEN, "methylome")
+    if ragged:
+        meth_dir = os.path.join(tmp_path, "methylome")
+        os.makedirs(meth_dir)
+        for name in sorted(os.listdir(os.path.join(GOLDEN, "methylome"))):
+            lines = open(os.path.join(GOLDEN, "methylome", name)).read().split("\n")
+            if name == "G1_2.txt":
+                cg = [i for i, l in enumerate(lines) if oracle.parse_methylome_line(l) is not None]
+                keep = set(range(len(lines))) - {cg[len(cg) // 3], cg[2 * len(cg) // 3]}
+                lines = [l for i, l in enumerate(lines) if i in keep]
+            open(os.path.join(meth_dir, name), "w").write("\n".join(lines))
     ann = os.path.join(tmp_path, "ann.bed")
     genes = [(1, 300, 700, "-"), (1, 250, 800, "+"), (2, 1200, 1600, "+"), (2, 1250, 1650, "-"), (3, 600, 900, "*"),
              (4, 1200, 1550, "-"), (4, 1150, 1600, "+"), (5, 300, 900, "*"), ("C", 200, 900, "+"), ("C", 150, 950, "-"),
@@ -270,7 +284,7 @@ def test_metaprofile_cli_fused_pipeline(ab, ctx, oracle, tmp_path):
     os.makedirs(out)
     exe = os.path.join(ROOT, "alphabeta-rs_b200", "metaprofile")
     n_it, seed = 60, 777
-    r = subprocess.run([exe, "-m", os.path.join(GOLDEN, "methylome"), "-g", ann, "-w", "10", "-s", "5", "-c", "200", "-o", out,
+    r = subprocess.run([exe, "-m", meth_dir, "-g", ann, "-w", "10", "-s", "5", "-c", "200", "-o", out,
                         "--name", "run7", "--iterations", str(n_it), "--seed", str(seed), "alphabeta",
                         "--nodes", os.path.join(GOLDEN, "nodelist.txt"), "--edges", os.path.join(GOLDEN, "edgelist.txt")],
                        capture_output=True, text=True, timeout=300)
@@ -282,7 +296,7 @@ def test_metaprofile_cli_fused_pipeline(ab, ctx, oracle, tmp_path):
     # different orders, so a window holds different rows of each file
     per_sample = []
     for node in info["nodes"]:
-        path = resolve_golden(node["file"])
+        path = os.path.join(meth_dir, os.path.basename(resolve_golden(node["file"])))
         sites, st, po, me = [], [], [], []
         for line in open(path).read().split("\n")[1:]:
             q = oracle.parse_methylome_line(line)
@@ -295,15 +309,33 @@ def test_metaprofile_cli_fused_pipeline(ab, ctx, oracle, tmp_path):
     flags = oracle.FAST_DIVERGENCE | oracle.EARLY_EXIT_ON_STALL
     results, raws = [], []
     f = 0
+    n_ragged = 0
     for w in range(len(dist)):
         cols = [[si for si, ww in ps[1] if ww == w] for ps in per_sample]
-        if not cols[0] or len({len(c) for c in cols}) != 1:
+        if not any(cols):
             continue
-        status = np.stack([ps[2][c] for ps, c in zip(per_sample, cols)])
-        post = np.stack([ps[3][c] for ps, c in zip(per_sample, cols)])
-        meth = np.stack([ps[4][c] for ps, c in zip(per_sample, cols)])
-        D, _, _ = oracle.dmatrix(status, post, 0.99)
-        p0 = oracle.p0uu(post, meth, 0.99)[0]
+        if len({len(c) for c in cols}) == 1:
+            status = np.stack([ps[2][c] for ps, c in zip(per_sample, cols)])
+            post = np.stack([ps[3][c] for ps, c in zip(per_sample, cols)])
+            meth = np.stack([ps[4][c] for ps, c in zip(per_sample, cols)])
+            D, _, _ = oracle.dmatrix(status, post, 0.99)
+            p0 = oracle.p0uu(post, meth, 0.99)[0]
+        else:  # DMatrix::from: pairs of unequal length keep D = 0; every sample's level comes from its own sites
+            n_ragged += 1
+            S_ = len(cols)
+            D = np.zeros(S_ * (S_ - 1) // 2)
+            p = 0
+            for i in range(S_):
+                for j in range(i + 1, S_):
+                    if len(cols[i]) == len(cols[j]):
+                        D[p] = oracle.dmatrix(np.stack([per_sample[i][2][cols[i]], per_sample[j][2][cols[j]]]),
+                                              np.stack([per_sample[i][3][cols[i]], per_sample[j][3][cols[j]]]), 0.99)[0][0]
+                    p += 1
+            own = [oracle.p0uu(ps[3][c][None, :], ps[4][c][None, :], 0.99)[0] if c else float("nan") for ps, c in zip(per_sample, cols)]
+            acc = 0.0
+            for v in own:  # src/pedigree.rs:179-183: sum of (1 - level) in sample order, / S
+                acc += v
+            p0 = acc / S_
         if np.isnan(D).any() or np.isnan(p0):
             continue
         ped = ped6.copy()
@@ -320,7 +352,7 @@ def test_metaprofile_cli_fused_pipeline(ab, ctx, oracle, tmp_path):
         results.append((region, best["theta"].copy(), oracle.analyze(rows), 1.0 - p0))
         raws.append(rows)
         f += 1
-    assert len(results) >= 20
+    assert len(results) >= 20 and (n_ragged > 0) == ragged
     want = oracle.metaprofile_results_text("run7", dist[:len(results)], [r_[0] for r_ in results], [r_[1] for r_ in results],
                                            [r_[2] for r_ in results], [r_[3] for r_ in results])
     if os.environ.get("ABFIT_TEST_DUMP"):
@@ -340,7 +372,7 @@ def test_metaprofile_cli_fused_pipeline(ab, ctx, oracle, tmp_path):
     os.makedirs(out2)
     nd = ab.device_count()
     devs = f"0-{nd - 1}" if nd >= 2 else "0,0,0"
-    r2 = subprocess.run([exe, "-m", os.path.join(GOLDEN, "methylome"), "-g", ann, "-w", "10", "-s", "5", "-c", "200", "-o", out2,
+    r2 = subprocess.run([exe, "-m", meth_dir, "-g", ann, "-w", "10", "-s", "5", "-c", "200", "-o", out2,
                          "--name", "run7", "--iterations", str(n_it), "--seed", str(seed), "--devices", devs, "alphabeta",
                          "--nodes", os.path.join(GOLDEN, "nodelist.txt"), "--edges", os.path.join(GOLDEN, "edgelist.txt")],
                         capture_output=True, text=True, timeout=300)
