@@ -203,9 +203,9 @@ def run_reference_arm(args):
     # bounded sample, sized from the step count: literal reference work costs ~0.85 core-seconds per fit (measured:
     # one full window, 1100 fits, 112 s on 8 cores) and a stalled start alone runs its 10 000 iterations for ~8 s on
     # one core, so a SHORT sample is slower per fit than the reference really is (one stalled start is the whole
-    # step); the steps get as many starts as ~3 minutes of host time allow, up to the full window.
+    # step); the steps get as many starts as ~2.5 minutes of host time allow, up to the full window.
     n_steps = max(1, args.warmup + args.steps)
-    ns = int(min(args.starts, max(4 * threads, threads * 180.0 / (n_steps * 0.85 * 1.1))))
+    ns = int(min(args.starts, max(4 * threads, threads * 150.0 / (n_steps * 0.85 * 1.1))))
     nb = max(2, ns * args.boots // args.starts)
     vals = []
     for i in range(args.warmup + args.steps):
