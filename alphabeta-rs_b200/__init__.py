@@ -269,9 +269,12 @@ def alphabeta_batch_multi(ctxs: Sequence["Context"], probs, simplices, resample_
     n_probs = len(probs)
     simplices = _f64(simplices)
     n_starts = simplices.size // (n_probs * 20)
-    idx = np.ascontiguousarray(resample_idx, dtype=np.int32)
     total = sum(p.n_pairs for p in probs)
-    n_boot = idx.size // total
+    if isinstance(resample_idx, (int, np.integer)):  # a replicate count: the indices are drawn on the device
+        idx, n_boot = None, int(resample_idx)
+    else:
+        idx = np.ascontiguousarray(resample_idx, dtype=np.int32)
+        n_boot = idx.size // total
     best = np.zeros(n_probs, dtype=FIT_DTYPE)
     pred, resid = np.empty(total), np.empty(total)
     status = np.zeros(n_probs, dtype=np.int32)
@@ -438,9 +441,12 @@ class Context:
         n_probs = len(probs)
         simplices = _f64(simplices)
         n_starts = simplices.size // (n_probs * 20)
-        idx = np.ascontiguousarray(resample_idx, dtype=np.int32)
         total = sum(p.n_pairs for p in probs)
-        n_boot = idx.size // total
+        if isinstance(resample_idx, (int, np.integer)):  # a replicate count: the indices are drawn on the device
+            idx, n_boot = None, int(resample_idx)       # (the numbers of gen_resample_idx(seed, window key, ...))
+        else:
+            idx = np.ascontiguousarray(resample_idx, dtype=np.int32)
+            n_boot = idx.size // total
         best = np.zeros(n_probs, dtype=FIT_DTYPE) if best is None else best
         pred = np.empty(total) if pred is None else pred
         resid = np.empty(total) if resid is None else resid

@@ -631,9 +631,8 @@ int main(int argc, char **argv)
     const int F = (int)fitted.size();
     const int n = (int)iterations;
     std::vector<abfit_problem> probs(F);
-    // (the two big inputs are written in full by the generators below: no zero-fill of gigabytes first)
+    // (written in full by the generator below: no zero-fill of gigabytes first)
     std::unique_ptr<double[]> simplices(new double[std::max<size_t>(1, (size_t)F * n * 20)]);
-    std::unique_ptr<int32_t[]> idx(new int32_t[std::max<size_t>(1, (size_t)F * n * n_pairs)]);
     std::vector<double> rows((size_t)F * n * 7), analysis((size_t)F * 32);
     std::vector<int32_t> status(F);
     std::vector<abfit_fit> best(F);
@@ -645,15 +644,16 @@ int main(int argc, char **argv)
         double max_div = peds[f][3];
         for (int r = 1; r < n_pairs; ++r) max_div = std::max(max_div, peds[f][4 * r + 3]);
         abfit_gen_start_simplices(seed, (uint64_t)usable[k], n, max_div, simplices.get() + (size_t)f * n * 20);
-        abfit_gen_resample_idx(seed, (uint64_t)usable[k], n, n_pairs, idx.get() + (size_t)f * n * n_pairs);
     });
     // start simplices, resample indices and vary vertices of a window are all keyed by (seed, window id): its result
-    // does not depend on which other windows are fitted with it, nor on how the windows are sharded over the GPUs
+    // does not depend on which other windows are fitted with it, nor on how the windows are sharded over the GPUs.
+    // The resample indices (4 x iterations x pairs bytes per window: 14 GB for 10 000 windows at -i 1000) are drawn on
+    // the device (resample_idx = NULL): the numbers abfit_gen_resample_idx(seed, window id, ...) gives.
     // progress::multi(total_steps) (src/cli/metaprofile.rs:46): one step per window; the windows are fitted in one batched
     // call, so the bar stands at the windows prepared so far while the GPUs work and jumps to the end afterwards
     progress::Bar pb("Progress ", (unsigned long long)n_total, true);
     pb.set((unsigned long long)(n_total - F));
-    if (F > 0 && abfit_alphabeta_batch_multi(ctxs.data(), (int32_t)ctxs.size(), probs.data(), F, n, simplices.get(), n, idx.get(), seed,
+    if (F > 0 && abfit_alphabeta_batch_multi(ctxs.data(), (int32_t)ctxs.size(), probs.data(), F, n, simplices.get(), n, nullptr, seed,
                                              0, ids.data(), 10000, 1000, DBL_EPSILON, 0, best.data(), nullptr, nullptr,
                                              status.data(), rows.data(), analysis.data())) {
         std::printf("Error: %s\n", abfit_last_error());

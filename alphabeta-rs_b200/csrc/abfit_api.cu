@@ -1071,7 +1071,7 @@ static int alphabeta_impl(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_
                           int32_t max_iters_boot, double sd_tol, uint32_t flags, abfit_fit *best_out, double *pred_out,
                           double *resid_out, int32_t *prob_status_out, double *rows_out, double *analysis_out)
 {
-    if (!simplices || !resample_idx || n_starts <= 0 || n_boot <= 0 || !rows_out) return ABFIT_ERR_ARG;
+    if (!simplices || n_starts <= 0 || n_boot <= 0 || !rows_out) return ABFIT_ERR_ARG;  // (resample_idx NULL: drawn on the device)
     if (!ctx || n_probs <= 0) return ABFIT_ERR_ARG;
     ABFIT_CUDA(cudaSetDevice(ctx->device));
     if (!ctx->scratch) {
@@ -1132,16 +1132,23 @@ static int alphabeta_impl(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_
     const bool watch_upload = b->jit && b->jit->sched == 2 && !b->shape.wide && !getenv("ABFIT_DEV_NO_UPLOAD_WATCH");
     if (!watch_upload) ABFIT_CUDA(cudaStreamWaitEvent(st, ctx->copy_done, 0));
     b->sx_ready = watch_upload ? ctx->d_sx_ready : nullptr;
-    // the resample indices (the bulk of the bootstrap's input) cross PCIe under the multi-start kernels
-    if (!ctx->idx_done) ABFIT_CUDA(cudaEventCreateWithFlags(&ctx->idx_done, cudaEventDisableTiming));
-    ABFIT_CUDA(cudaMemcpyAsync(b->d_idx.p, resample_idx, (size_t)b->total_pairs * n_boot * 4, cudaMemcpyHostToDevice,
-                               ctx->copy_stream));
-    ABFIT_CUDA(cudaEventRecord(ctx->idx_done, ctx->copy_stream));
     const unsigned long long *d_ids = nullptr;
     if (problem_ids) {  // every window keeps its own key, whatever its position in this batch
         if (int rc = b->d_ids.ensure(n_probs)) return rc;
         ABFIT_CUDA(cudaMemcpyAsync(b->d_ids.p, problem_ids, (size_t)n_probs * 8, cudaMemcpyHostToDevice, st));
         d_ids = b->d_ids.p;
+    }
+    if (!ctx->idx_done) ABFIT_CUDA(cudaEventCreateWithFlags(&ctx->idx_done, cudaEventDisableTiming));
+    if (resample_idx) {
+        // the resample indices (the bulk of the bootstrap's input) cross PCIe under the multi-start kernels
+        ABFIT_CUDA(cudaMemcpyAsync(b->d_idx.p, resample_idx, (size_t)b->total_pairs * n_boot * 4, cudaMemcpyHostToDevice,
+                                   ctx->copy_stream));
+        ABFIT_CUDA(cudaEventRecord(ctx->idx_done, ctx->copy_stream));
+    } else {
+        // ... or are drawn on the device (boot_model::run draws them itself, src/boot_model.rs:43-48): the numbers of
+        // abfit_gen_resample_idx(vary_seed, window key, ...), ahead of the fit kernels on the same stream
+        if (int rc = launch_gen_resample(st, vary_seed, first_problem_id, d_ids, b->pools.probs, n_probs, n_boot, b->d_idx.p)) return rc;
+        ABFIT_CUDA(cudaEventRecord(ctx->idx_done, st));
     }
     // fit -> select -> Model::vary x 4 per replicate around each window's best model (src/boot_model.rs:69-75: drawn on
     // the device right behind the selection kernel — the same numbers abfit_gen_vary_vertices gives on the host — so
@@ -1208,7 +1215,7 @@ int abfit_alphabeta_batch_multi(abfit_ctx *const *ctxs, int32_t n_ctx, const abf
                                 abfit_fit *best_out, double *pred_out, double *resid_out, int32_t *prob_status_out,
                                 double *rows_out, double *analysis_out)
 {
-    if (!ctxs || n_ctx <= 0 || !probs || n_probs <= 0 || !simplices || !resample_idx || !rows_out) return ABFIT_ERR_ARG;
+    if (!ctxs || n_ctx <= 0 || !probs || n_probs <= 0 || !simplices || !rows_out) return ABFIT_ERR_ARG;
     for (int r = 0; r < n_ctx; ++r)
         if (!ctxs[r]) return ABFIT_ERR_ARG;
     const int world = std::min<int>(n_ctx, n_probs);
@@ -1221,7 +1228,8 @@ int abfit_alphabeta_batch_multi(abfit_ctx *const *ctxs, int32_t n_ctx, const abf
         shard_range(n_probs, r, world, first, count);
         const int64_t po = pair_off[first];
         rcs[r] = alphabeta_impl(ctxs[r], probs + first, (int32_t)count, n_starts, simplices + (size_t)first * n_starts * 20,
-                                n_boot, resample_idx + (size_t)po * n_boot, vary_seed, first_problem_id + (uint64_t)first,
+                                n_boot, resample_idx ? resample_idx + (size_t)po * n_boot : nullptr, vary_seed,
+                                first_problem_id + (uint64_t)first,
                                 problem_ids ? problem_ids + first : nullptr, max_iters_fit, max_iters_boot, sd_tol, flags,
                                 best_out ? best_out + first : nullptr, pred_out ? pred_out + po : nullptr,
                                 resid_out ? resid_out + po : nullptr, prob_status_out ? prob_status_out + first : nullptr,

@@ -72,6 +72,10 @@ int launch_model_divergence(cudaStream_t st, const DevicePools &P, const double 
 // (ids: optional device array of per-window generator keys, else first_problem_id + window)
 int launch_gen_vary(cudaStream_t st, uint64_t seed, uint64_t first_problem_id, const unsigned long long *ids, int n_probs,
                     int n_boot, const abfit_fit *best, double *out);
+// resample indices of every (window, replicate, pair) drawn on the device (same numbers as abfit_gen_resample_idx):
+// out[pair_off * n_boot + b * n_pairs + i]
+int launch_gen_resample(cudaStream_t st, uint64_t seed, uint64_t first_problem_id, const unsigned long long *ids,
+                        const DevProblem *probs, int n_probs, int n_boot, int32_t *out);
 int launch_fp64_peak(cudaStream_t st, int blocks, int threads, int iters, double *sink);
 // RawAnalysis::analyze of every window's bootstrap rows on the device (same bits as the host's abfit_analyze):
 // rows [n_probs][n_boot][7] -> out [n_probs][32]; scratch [n_probs * 8 * n_boot] doubles

@@ -439,6 +439,27 @@ __global__ void k_gen_vary(uint64_t seed, uint64_t first_problem_id, const unsig
     out[i] = vary_coordinate(seed, key, (uint64_t)b, v, j, best[p].theta[j]);
 }
 
+// Resample indices of every (window, replicate, pair) drawn on the device (src/boot_model.rs:43-48: the reference draws
+// them inside boot_model::run): the numbers abfit_gen_resample_idx gives on the host — integer hashing and one
+// double multiplication — in the layout abfit_boot_batch takes, out[pair_off * n_boot + b * n_pairs + i].
+// Blocks walk over the windows, threads over a window's n_boot * n_pairs entries.
+__global__ void k_gen_resample(uint64_t seed, uint64_t first_problem_id, const unsigned long long *__restrict__ ids,
+                               const DevProblem *__restrict__ probs, int n_probs, int n_boot, int32_t *__restrict__ out)
+{
+    for (int p = blockIdx.x; p < n_probs; p += gridDim.x) {
+        const int n_pairs = probs[p].n_pairs;
+        const uint64_t key = ids ? (uint64_t)ids[p] : first_problem_id + (uint64_t)p;
+        int32_t *o = out + (size_t)probs[p].pair_off * n_boot;
+        const size_t n = (size_t)n_boot * n_pairs;
+        for (size_t e = threadIdx.x; e < n; e += blockDim.x) {
+            const uint64_t b = e / (size_t)n_pairs, i = e - b * (size_t)n_pairs;
+            int32_t k = (int32_t)(u01(seed, 3, key, b, i) * (double)n_pairs);
+            if (k >= n_pairs) k = n_pairs - 1;
+            o[e] = k;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // RawAnalysis::analyze (src/analysis.rs:50-98) on the device: one thread per (window, statistic column), the same
 // sequential sums, Welford updates and linear quantiles as the host's abfit_analyze (csrc/abfit_api.cu) — same
@@ -740,6 +761,15 @@ int launch_gen_vary(cudaStream_t st, uint64_t seed, uint64_t first_problem_id, c
     const size_t n = (size_t)n_probs * n_boot * 16;
     if (n == 0) return 0;
     k_gen_vary<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(seed, first_problem_id, ids, n_probs, n_boot, best, out);
+    ABFIT_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_gen_resample(cudaStream_t st, uint64_t seed, uint64_t first_problem_id, const unsigned long long *ids,
+                        const DevProblem *probs, int n_probs, int n_boot, int32_t *out)
+{
+    if (n_probs <= 0 || n_boot <= 0) return 0;
+    k_gen_resample<<<(unsigned)std::min(n_probs, 148 * 16), 256, 0, st>>>(seed, first_problem_id, ids, probs, n_probs, n_boot, out);
     ABFIT_CUDA(cudaGetLastError());
     return 0;
 }

@@ -174,6 +174,10 @@ int abfit_boot_batch(abfit_ctx *ctx, const abfit_problem *probs, int32_t n_probs
  * behind the best-of-starts selection (same counter-based generator, same bits), so the bootstrap starts without a
  * round trip through the host.  The start simplices cross PCIe while the host compiles the pedigrees, the resample
  * indices under the multi-start kernel, and the fit results come back under the bootstrap kernel.
+ *  resample_idx  as in abfit_boot_batch, or NULL: the indices are drawn on the device, as boot_model::run draws its own
+ *                (src/boot_model.rs:43-48) — the numbers abfit_gen_resample_idx(vary_seed, first_problem_id + window
+ *                [or problem_ids[window]], n_boot, n_pairs) returns, without generating and copying 4 n_boot n_pairs
+ *                bytes per window on the host
  *  rows_out      [n_probs][n_boot][7]   (required)
  *  analysis_out  [n_probs][32]          RawAnalysis::analyze per window (may be NULL)
  *  best_out, pred_out, resid_out, prob_status_out as in abfit_fit_batch (may be NULL) */

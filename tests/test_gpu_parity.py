@@ -982,6 +982,30 @@ def test_multi_device_alphabeta_equals_single_device(ab, ctx, ctx_pool, ped351, 
     assert np.array_equal(sub["rows"], many["rows"][keep]) and np.array_equal(sub["best"]["theta"], many["best"]["theta"][keep])
 
 
+def test_resample_indices_drawn_on_the_device(ab, ctx, ctx_pool, ped351, ped78):
+    """abfit_alphabeta_batch / _multi with resample_idx = NULL: the indices are drawn on the device (k_gen_resample) and
+    are the numbers abfit_gen_resample_idx returns — every output equals, byte for byte, the call that is handed the
+    host-generated indices; ragged pedigrees, consecutive keys with an offset, per-window keys, several contexts"""
+    rng = np.random.default_rng(73)
+    cases = [synth_problem(rng, ped351, n_keep=k) for k in (60, 33, 90, 17)] + [synth_problem(rng, ped78[0]), synth_problem(rng, ped351)]
+    probs = [ab.Problem(p, u, u, 1.0) for p, u in cases]
+    n_starts, n_boot = 64, 37
+    keys = ("best", "pred", "resid", "status", "rows", "analysis")
+    sx = np.stack([ab.gen_start_simplices(SEED, 7 + i, n_starts, float(p[:, 3].max())) for i, (p, u) in enumerate(cases)])
+    idx = np.concatenate([ab.gen_resample_idx(SEED, 7 + i, n_boot, len(p)).ravel() for i, (p, u) in enumerate(cases)])
+    host = ctx.alphabeta_batch(probs, sx, idx, SEED, first_problem_id=7)
+    dev = ctx.alphabeta_batch(probs, sx, n_boot, SEED, first_problem_id=7)
+    for k in keys:
+        assert host[k].tobytes() == dev[k].tobytes(), k
+    ids = np.array([3, 4, 9, 10, 40, 41], dtype=np.uint64)
+    idx2 = np.concatenate([ab.gen_resample_idx(SEED, int(i), n_boot, len(p)).ravel() for i, (p, u) in zip(ids, cases)])
+    host2 = ab.alphabeta_batch_multi(ctx_pool, probs, sx, idx2, SEED, problem_ids=ids)
+    dev2 = ab.alphabeta_batch_multi(ctx_pool, probs, sx, n_boot, SEED, problem_ids=ids)
+    for k in keys:
+        assert host2[k].tobytes() == dev2[k].tobytes(), k
+    assert host["rows"].tobytes() != host2["rows"].tobytes()  # (the keys matter)
+
+
 def test_multi_device_divergence(ab, ctx, ctx_pool, oracle):
     """abfit_divergence_multi: window-sharded = single device bit for bit; site-sharded whole methylomes: integer sums
     and D exact, p0uu within 1e-12 (north_star)"""
