@@ -103,6 +103,39 @@ def test_parser_fuzz_against_the_oracle(ab, oracle):
     assert 500 < accepted < 5500
 
 
+def test_annotation_parser_fuzz_against_the_oracle(ab, oracle):
+    """Gene::from_annotation_file_line (src/genes.rs:166-216): every golden annotation line, and 4000 lines with the
+    field count, the separators, the strand column and the numbers perturbed, product == oracle restatement"""
+    rng = np.random.default_rng(515)
+    golden = [l for l in open(os.path.join(GOLDEN, "annotation.bed")).read().split("\n")]
+    chroms = ["1", "5", "chr2", "chrchr3", "chr", "M", "C", "chrM", "X", "255", "256", "+4", ""]
+    ints = ["0", "7", "+12", "-3", "4294967295", "4294967296", "00012", "1.0", "", "12a", "300", "90000"]
+    strands = ["+", "-", "*", ".", "", "++", "sense"]
+    lines = list(golden)
+    for _ in range(4000):
+        pick = lambda a: a[rng.integers(0, len(a))]
+        k = rng.integers(0, 4)
+        if k == 0:
+            f = [pick(chroms), pick(ints), pick(ints), "AT1G01", "gbM", pick(strands)]
+        elif k == 1:
+            f = [pick(chroms), pick(ints), pick(ints), pick(ints), pick(strands), "AT1G01"]
+        elif k == 2:
+            f = [pick(chroms + ints + strands) for _ in range(rng.integers(0, 9))]
+        else:
+            f = golden[rng.integers(0, len(golden) - 1)].split("\t")
+            if f and rng.random() < 0.5:
+                f[rng.integers(0, len(f))] = pick(chroms + ints + strands)
+        lines.append(pick(["\t", "\t", " ", ",", "\t "]).join(f))
+    n_ok = 0
+    for line in lines:
+        for inv in (False, True):
+            want = oracle.parse_annotation_line(line, inv)
+            got = ab.parse_annotation_line(line, inv)
+            assert got == (None if want is None else tuple(int(x) for x in want)), (line, inv, got, want)
+        n_ok += want is not None
+    assert n_ok > len(golden) - 5 and n_ok < len(lines) - 1000
+
+
 def test_parser_f64_is_correctly_rounded(ab):
     """<f64 as FromStr> is correctly rounded; so is Python's float().  20 000 random decimal strings (up to 25
     significant digits, exponents across the whole range incl. subnormals, overflow to inf and underflow to 0) through
