@@ -308,25 +308,10 @@ def parse_edgelist(text: str, nodes):
     return edges
 
 
-def build_pedigree(nodelist_path: str, edgelist_path: str, thr: float, resolve=lambda p: p):
-    """Pedigree::build (src/pedigree.rs:92-193) + DMatrix::convert (:264-337).
-    Returns (pedigree [n,4], p0uu, dict with the per-sample arrays)."""
-    nodes = parse_nodelist(open(nodelist_path).read())
-    if not nodes:
-        raise ValueError("No nodes could be parsed from the nodelist")
-    edges = parse_edgelist(open(edgelist_path).read(), nodes)
-    meas = [n for n in nodes if n["meth"]]
-    data = [read_methylome(resolve(n["file"])) for n in meas]
-    lens = {len(d[0]) for d in data}
-    S = len(meas)
-    if len(lens) == 1:
-        status = np.stack([d[0] for d in data])
-        post = np.stack([d[1] for d in data])
-        meth = np.stack([d[2] for d in data])
-        D, diff, cnt = dmatrix(status, post, thr)
-        p0, rc, nv = p0uu(post, meth, thr)
-    else:
-        raise NotImplementedError("ragged site lists: the reference sets D = 0 for such pairs")
+def pedigree_pairs(meas, edges):
+    """DMatrix::convert (src/pedigree.rs:264-337) without the divergences: for every pair i < j of measured nodes that
+    the edge graph connects, (i, j, t0, t1, t2) with t0 = the smallest generation on the shortest path (edge weight =
+    |generation difference|), in pair order."""
     # graph: undirected, weight = |generation difference| (src/pedigree.rs:265-277)
     adj = {}
     gen_of = {}
@@ -359,8 +344,8 @@ def build_pedigree(nodelist_path: str, edgelist_path: str, thr: float, resolve=l
                     heapq.heappush(pq, (nd, v))
         return None
 
-    rows = []
-    p = 0
+    out = []
+    S = len(meas)
     for i in range(S):
         for j in range(i + 1, S):
             r = shortest(meas[i]["id"], meas[j]["id"]) if meas[i]["id"] in adj or meas[i]["id"] == meas[j]["id"] else None
@@ -369,8 +354,30 @@ def build_pedigree(nodelist_path: str, edgelist_path: str, thr: float, resolve=l
                 t0 = float(min(gen_of[n] for n in path))
                 t1, t2 = float(meas[i]["generation"]), float(meas[j]["generation"])
                 assert float(dist) == t1 - t0 + t2 - t0
-                rows.append([t0, t1, t2, D[p]])
-            p += 1
+                out.append((i, j, t0, t1, t2))
+    return out
+
+
+def build_pedigree(nodelist_path: str, edgelist_path: str, thr: float, resolve=lambda p: p):
+    """Pedigree::build (src/pedigree.rs:92-193) + DMatrix::convert (:264-337).
+    Returns (pedigree [n,4], p0uu, dict with the per-sample arrays)."""
+    nodes = parse_nodelist(open(nodelist_path).read())
+    if not nodes:
+        raise ValueError("No nodes could be parsed from the nodelist")
+    edges = parse_edgelist(open(edgelist_path).read(), nodes)
+    meas = [n for n in nodes if n["meth"]]
+    data = [read_methylome(resolve(n["file"])) for n in meas]
+    lens = {len(d[0]) for d in data}
+    S = len(meas)
+    if len(lens) == 1:
+        status = np.stack([d[0] for d in data])
+        post = np.stack([d[1] for d in data])
+        meth = np.stack([d[2] for d in data])
+        D, diff, cnt = dmatrix(status, post, thr)
+        p0, rc, nv = p0uu(post, meth, thr)
+    else:
+        raise NotImplementedError("ragged site lists: the reference sets D = 0 for such pairs")
+    rows = [[t0, t1, t2, D[i * S - i * (i + 1) // 2 + (j - i - 1)]] for i, j, t0, t1, t2 in pedigree_pairs(meas, edges)]
     ped = np.array(rows, dtype=np.float64).reshape(-1, 4)
     return ped, p0, {"status": status, "post": post, "meth": meth, "D": D, "diff": diff, "cnt": cnt, "rc": rc,
                      "nvalid": nv, "nodes": meas}

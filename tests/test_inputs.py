@@ -103,6 +103,48 @@ def test_parser_fuzz_against_the_oracle(ab, oracle):
     assert 500 < accepted < 5500
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_pedigree_graph_random_trees_against_the_oracle(ab, oracle, tmp_path, seed):
+    """abfit_pedigree_graph (nodelist / edgelist parsing, shortest path, t0 rule: src/pedigree.rs:99-135,264-337) on
+    random lineage trees — branching founders, unmeasured intermediate nodes, generation gaps, separators mixed, an
+    isolated measured node, edges naming unknown nodes — against the oracle's restatement: same measured files, same
+    (i, j, t0, t1, t2) rows in the same order"""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(4, 40))
+    gen = [0]
+    parent = [-1]
+    for k in range(1, n):
+        q = int(rng.integers(0, k))
+        parent.append(q)
+        gen.append(gen[q] + int(rng.integers(1, 4)))
+    meth = [rng.random() < 0.6 for _ in range(n)]
+    meth[-1] = meth[-2] = True
+    sep = lambda: ["\t", ",", " "][int(rng.integers(0, 3))]
+    lines = ["filename,node,gen,meth"]
+    for k in range(n):
+        s1 = sep()
+        lines.append(s1.join([f"/data/m_{k}.txt" if meth[k] else "-", f"N{k}", str(gen[k]), "Y" if meth[k] else "N"]))
+        if rng.random() < 0.1:
+            lines.append("")  # blank lines count towards the ids
+    lines.append("\t".join([f"/data/m_lonely.txt", "LONELY", "7", "Y"]))  # measured, but no edge reaches it
+    lines.append("bad line")
+    edges = ["from,to"]
+    for k in range(1, n):
+        a, b = (f"N{parent[k]}", f"N{k}") if rng.random() < 0.7 else (f"N{k}", f"N{parent[k]}")
+        edges.append(sep().join([a, b]))
+    edges.append("N0,GHOST")
+    nl, el = os.path.join(tmp_path, "nodes.txt"), os.path.join(tmp_path, "edges.txt")
+    open(nl, "w").write("\n".join(lines) + "\n")
+    open(el, "w").write("\n".join(edges) + "\n")
+    files, pairs = ab.pedigree_graph(nl, el)
+    nodes = oracle.parse_nodelist(open(nl).read())
+    meas = [x for x in nodes if x["meth"]]
+    want = oracle.pedigree_pairs(meas, oracle.parse_edgelist(open(el).read(), nodes))
+    assert files == [x["file"] for x in meas]
+    assert len(want) > 0 and pairs.shape == (len(want), 5)
+    assert np.array_equal(pairs, np.array(want, dtype=np.float64))
+
+
 def test_annotation_parser_fuzz_against_the_oracle(ab, oracle):
     """Gene::from_annotation_file_line (src/genes.rs:166-216): every golden annotation line, and 4000 lines with the
     field count, the separators, the strand column and the numbers perturbed, product == oracle restatement"""
