@@ -165,7 +165,7 @@ class ClockSampler:
 # twin of the seeded generators (oracle/gen_py.py, pinned bit for bit against libabfit's in tests/test_abi.py), so
 # this arm never touches the product library, and they are drawn BEFORE the clock starts.
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_sample(shape, n_starts_sample, n_boot_sample, literal=True, threads=None, window=0):
+def cpu_reference_sample(shape, n_starts_sample, n_boot_sample, literal=True, threads=None, window=0, balance=True):
     """times ab_neutral::run + boot_model::run of ONE synthetic window on the host cores.
     literal=True: the reference's own work (per-pair matrix_power, pedigree clone per start, all max_iters on
     stalled starts, best-of-starts through the sort_by whose comparator re-evaluates divergence() twice)."""
@@ -181,6 +181,14 @@ def cpu_reference_sample(shape, n_starts_sample, n_boot_sample, literal=True, th
     idx = g.gen_resample_idx(SEED, window, n_boot_sample, len(ped))
     # (the vary vertices depend on the fit result: Model::vary is drawn inside the timed region, as in the reference)
     flags = o.LITERAL_SORT if literal else (o.FAST_DIVERGENCE | o.EARLY_EXIT_ON_STALL)
+    if literal and balance and n_starts_sample < 1000:
+        # A stalled start runs all 10 000 iterations (~20 000 evaluations against a median of ~850).  Over the 1000 starts
+        # of a real window rayon's work stealing hides those behind the rest; a bounded sample would instead wait for the
+        # one that happens to be handed out last.  So the sample's starts are handed out longest first (lengths from the
+        # minimal-work port, before the clock starts) — the balance the reference reaches on a whole window.
+        _, _, quick, _, _ = o.ab_neutral(pb, sx, max_iters=10000, flags=o.FAST_DIVERGENCE | o.EARLY_EXIT_ON_STALL, n_threads=threads)
+        length = np.where(quick["status"] == 3, 1 << 30, quick["evals"].astype(np.int64))
+        sx = np.ascontiguousarray(sx[np.argsort(-length, kind="stable")])
     t0 = time.perf_counter()
     rc, best, allr, pred, resid = o.ab_neutral(pb, sx, max_iters=10000, flags=flags, n_threads=threads)
     vary = g.gen_vary_vertices(SEED, window, n_boot_sample, best["theta"])
@@ -224,9 +232,10 @@ def run_reference_arm(args):
         full = {"fits_per_s": v, "seconds": dt, "sample": f"1 window x ({args.starts} starts + {args.boots} replicates), once"}
     sample = (f"1 synthetic C4 window x ({ns} starts + {nb} bootstrap replicates) per step, literal reference work "
               "(per-pair matrix_power, pedigree clone per start, sort_by comparator re-evaluating divergence twice); "
-              "inputs drawn before the clock starts by oracle/gen_py.py; the process maps oracle/libabref.so only; a sample "
-              "shorter than the full window UNDERSTATES the reference (a stalled start's 10 000 iterations are the "
-              "step's tail): cpu_baseline.full_window is the reference's rate on a whole window")
+              "inputs drawn before the clock starts by oracle/gen_py.py; the process maps oracle/libabref.so only; the "
+              "sample's starts are handed to the threads longest first (a stalled start runs 10 000 iterations: rayon hides "
+              "those behind the other 999 starts of a whole window, a short sample handed out in index order would wait "
+              "for them and UNDERSTATE the reference); cpu_baseline.full_window is the rate on a whole window")
     line = {
         "impl": "reference", "metric": METRIC, "value": value,
         "unit": "fits/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
