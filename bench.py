@@ -784,8 +784,8 @@ def main():
         v2, dt2, _ = cpu_reference_sample(shape, 16 * ns, 16 * nb, literal=False, threads=threads)
         cpu = {"value": v, "unit": "fits/s", "cores": threads, "kind": "port",
                "sample": f"1 C4 window x ({ns} starts + {nb} boots), literal reference work incl. the re-evaluating sort_by, {dt:.1f} s "
-                         "(a sample this short is bounded by its stalled starts, 10 000 iterations each: the whole-window rate "
-                         "is `bench.py --impl reference`'s cpu_baseline.full_window)",
+                         "(starts handed to the threads longest first; a sample this short is still bounded by one stalled start, "
+                         "10 000 iterations: the whole-window rate is `bench.py --impl reference`'s cpu_baseline.full_window)",
                "minimal_work_value": v2,
                "minimal_work_note": "same port with the power table + stall early-exit the GPU path uses "
                                     f"({16 * ns} starts + {16 * nb} boots, {dt2:.1f} s): separates algorithmic "
